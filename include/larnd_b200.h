@@ -1,0 +1,203 @@
+/*
+ * larnd_b200 — C ABI of the B200-native (sm_100a) larnd-sim hot path.
+ *
+ * The reference (pgranger23/larnd-sim-jax) has no FFI boundary: its boundary is the set of
+ * Python/JAX functions of src/larndsim/sim_jax.py.  Each entry point below replaces the XLA
+ * lowering of one of them and is what a jax.ffi custom-call handler (or the ctypes binding
+ * of larndsim_b200) binds to:
+ *
+ *   larnd_lut_create        <- load_lut's device-side products + the per-call
+ *                              jnp.cumsum(response_template)          consts_jax.py:387-449, sim_jax.py:228
+ *   larnd_lut_forward       <- simulate_wfs = simulate_drift_new + unique/renumber
+ *                              + simulate_signals                      sim_jax.py:689-736 (375-453, 717-725, 142-286)
+ *   larnd_lut_backward      <- jax.grad through simulate_wfs           (VJP w.r.t. the fitted Params leaves)
+ *   larnd_fee_forward       <- simulate_stochastic = get_adc_values + digitize + id2pixel
+ *                              + get_pixel_coordinates + get_hit_z + parse_output
+ *                                                                      sim_jax.py:738-769, fee_jax.py:57-71,170-279
+ *   larnd_fee_backward      <- jax.grad through get_adc_values/digitize (VJP w.r.t. the waveforms)
+ *   larnd_mc_forward        <- simulate_drift(mc_diff) + current_mc + accumulate_signals_parametrized
+ *                                                                      sim_jax.py:122-139,289-335; detsim_jax.py:207-228,618-639
+ *   larnd_mc_backward       <- jax.grad through the same
+ *
+ * Conventions: plain pointers and sizes, no allocation and no host synchronisation inside
+ * (workspace is caller-provided, its size queried with larnd_workspace_bytes); every pointer
+ * named *_d is DEVICE memory; `stream` is a cudaStream_t passed as void*; functions return 0 on
+ * success or a negative LARND_E_* code, with a message available from larnd_last_error().
+ * All arithmetic is float32; ids are int32 (the reference never enables x64).
+ */
+#ifndef LARND_B200_H
+#define LARND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LARND_ABI_VERSION 1
+#define LARND_MAX_TPC 8
+#define LARND_MAX_TEMPLATES 128
+#define LARND_NB_TRAN_BINS 5   /* params.nb_tran_diff_bins, consts_jax.py:158,294 */
+#define LARND_MAX_ADC 10       /* params.MAX_ADC_VALUES,    consts_jax.py:279   */
+
+enum {
+  LARND_OK = 0,
+  LARND_E_ARG = -1,       /* invalid argument / unsupported configuration */
+  LARND_E_CUDA = -2,      /* CUDA runtime error (message has the detail) */
+  LARND_E_CAPACITY = -3   /* caller-provided capacity too small (host-side check) */
+};
+
+/* Differentiable parameters (optimize/ranges.py:7-21).  Gradients are returned in this order. */
+enum {
+  LARND_P_AB = 0, LARND_P_KB, LARND_P_EFIELD, LARND_P_LIFETIME, LARND_P_LONG_DIFF, LARND_P_TRAN_DIFF,
+  LARND_P_SHIFT_X, LARND_P_SHIFT_Y, LARND_P_SHIFT_Z, LARND_P_ALPHA, LARND_P_BETA, LARND_P_R_PARAM,
+  LARND_P_LAR_DENSITY, LARND_P_MEV_TO_ELECTRONS, LARND_P_VDRIFT /* never read by the reference: grad == 0 */,
+  LARND_NPARAMS
+};
+
+/* Column indices of the (N, ncols) float32 `tracks` array (row-major, reference `fields` tuple). */
+typedef struct larnd_columns {
+  int32_t ncols;
+  int32_t eventID, x, y, z, z_start, z_end, dx, dEdx, dE, t0;
+} larnd_columns_t;
+
+/* Simulation constants, already rounded the way the reference's weak-typed Python floats are
+ * (one f32 rounding of the double-precision constant expression).  Mirrors the fields of
+ * Params_template that the hot path reads (consts_jax.py:80-160). */
+typedef struct larnd_params {
+  /* recombination (quenching_jax.py:18-75) */
+  int32_t recombination_mode;   /* 1 BOX, 2 BIRKS, 3 ELLIPSOID */
+  float Ab, kb, alpha, beta, inv_R2 /* 1/R_param^2 */, efield_rho /* eField*lArDensity */, MeVToElectrons;
+  /* drift (drifting_jax.py:19-58) */
+  float vdrift, lifetime, long_diff, tran_diff, size_margin;
+  float shift_x, shift_y, shift_z;
+  int32_t n_tpc;
+  float tpc_borders[LARND_MAX_TPC][3][2];
+  /* pixelisation (detsim_jax.py:232-244,494-512; sim_jax.py:398-450) */
+  float pixel_pitch, bin_width /* pitch / nb_sampling_bins_per_pixel */, half_pitch;
+  int32_t nb_sampling_bins_per_pixel, n_pixels_x, n_pixels_y, number_pix_neighbors;
+  float tran_bin_edges[LARND_NB_TRAN_BINS + 1];  /* jnp.linspace(-2w, 3w, 6) */
+  /* time axis (sim_jax.py:147-178) */
+  float t_sampling;
+  int32_t n_ticks;        /* int(time_interval[1]/t_sampling)+1, includes the garbage tick 0 */
+  int32_t signal_length;  /* L */
+  int32_t n_templates;    /* len(long_diff_template) */
+  float long_diff_template[LARND_MAX_TEMPLATES];
+  /* front end (fee_jax.py:57-71,170-279) */
+  float discrimination_threshold, reset_noise_charge, uncorrelated_noise_charge;
+  float gain, v_cm, v_ref_minus_cm, v_pedestal, adc_counts, hit_prob_threshold;
+  int32_t hold_interval;  /* round((3+ADC_HOLD_DELAY)*CLOCK_CYCLE/t_sampling) */
+  int32_t max_adc_values;
+  /* MC-current mode (detsim_jax.py:618-639) */
+  int32_t diffusion_in_current_sim;
+  /* derivative helpers computed on the host in double precision */
+  float dvdrift_dEfield;  /* d get_vdrift / d eField */
+  float eField, lArDensity, R_param;
+} larnd_params_t;
+
+typedef struct larnd_lut larnd_lut_t; /* opaque: compacted response rows + cumulative tables on the device */
+
+const char* larnd_last_error(void);
+int larnd_abi_version(void);
+
+/* Builds the device tables for one (response_template, signal_length) pair:
+ *   neighbour rows  R0[ci][cj][Nt-L..Nt)          (template 0, all Nx*Ny bins)
+ *   main rows       Rm[tpl][ci<5][cj<5][Nt-L..Nt) (all templates, the 5x5 collecting bins)
+ *   cumulative sums C0[ci][cj][0..Nt), Cm[tpl][ci<5][cj<5][0..Nt)  == jnp.cumsum(response_template,-1)
+ * `bank_d` is the (n_templates, nx, ny, nt) float32 template bank on the device (load_lut's output);
+ * it is only read during this call. */
+int larnd_lut_create(const float* bank_d, int n_templates, int nx, int ny, int nt, int signal_length,
+                     void* stream, larnd_lut_t** out);
+void larnd_lut_destroy(larnd_lut_t* lut);
+
+/* Workspace (device) size for a batch of n_segments whose local event ids are < n_events
+ * (padding rows carry eventID -1) — both larnd_lut_* and larnd_mc_* use it. */
+size_t larnd_workspace_bytes(int64_t n_segments, int32_t n_events, int32_t n_tpc, int32_t n_pixels_x, int32_t n_pixels_y);
+
+/* simulate_wfs.  Outputs:
+ *   unique_pixels_d (npix_capacity) int32 : sorted unique main-pixel ids, front-padded with -1 exactly
+ *                                           like sim_jax.py:717-721 for a padded size of npix_capacity
+ *   wfs_d (npix_capacity, n_ticks) float32: FULL waveform rows including garbage column 0
+ *                                           (simulate_signals' return; simulate_wfs is wfs[:,1:])
+ *   counts_d[4] int32                     : {n_unique_main_pixels, n_negative_ids, overflow_flag, n_chunks}
+ * overflow_flag != 0 means npix_capacity < n_unique+1: outputs are then invalid.
+ * flags: bit0 = skip the garbage row (contributions the reference routes to row 0 are dropped;
+ *        NOT reference-identical for wfs[0]). */
+int larnd_lut_forward(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
+                      const larnd_params_t* params, const larnd_lut_t* lut, int32_t n_events,
+                      int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                      int32_t* unique_pixels_d, float* wfs_d, int32_t* counts_d, void* stream);
+
+/* Only the drift/pixelisation stage + unique/renumber (simulate_drift_new + sim_jax.py:717-725):
+ * fills the workspace segment records and unique_pixels_d/counts_d.  Lets a caller size wfs exactly
+ * (the reference's pad_size(n_unique+1)) before calling larnd_lut_accumulate. */
+int larnd_lut_prepare(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
+                      const larnd_params_t* params, const larnd_lut_t* lut, int32_t n_events,
+                      void* workspace_d, size_t workspace_bytes, int32_t* counts_d, void* stream);
+int larnd_lut_accumulate(int64_t n_segments, const larnd_params_t* params, const larnd_lut_t* lut,
+                         int32_t n_events, int32_t npix_capacity, int32_t flags, void* workspace_d,
+                         size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d, int32_t* counts_d,
+                         void* stream);
+
+/* VJP of simulate_wfs w.r.t. the LARND_NPARAMS fitted parameters.  Must follow a forward/prepare call
+ * on the same workspace.  g_wfs_d is (npix_capacity, n_ticks) with row stride g_row_stride floats
+ * (column 0 = garbage tick, never read: a gradient of simulate_wfs' (npix, n_ticks-1) output is passed as
+ * g - 1 with stride n_ticks-1).  counts_d = the forward call's counts.  flags bit0: gradients of rows the
+ * forward treats as garbage (id < 0 or not a main pixel) are taken as zero and skipped.
+ * grad_params_d[LARND_NPARAMS] is ACCUMULATED into (caller zeroes). */
+int larnd_lut_backward(int64_t n_segments, const larnd_params_t* params, const larnd_lut_t* lut,
+                       int32_t n_events, int32_t npix_capacity, int32_t flags, void* workspace_d,
+                       size_t workspace_bytes, const int32_t* counts_d, const float* g_wfs_d, int64_t g_row_stride,
+                       float* grad_params_d, void* stream);
+
+/* simulate_stochastic on (npix, n_ticks-1) waveforms (row stride wfs_row_stride floats, first column =
+ * reference tick index 0 of wfs[:,1:]).  noise_d: NULL (noise-free) or standard normals laid out as
+ * [base(npix) | extra(10,npix) | pass(10,npix) | fail(10,npix)].
+ * Dense outputs (npix,10): adc_d (digitized ADC), ticks_d (float, integer valued), pixel_z_d.
+ * Per-pixel outputs (npix): pixel_x_d, pixel_y_d, event_d (int32).
+ * Compacted outputs (capacity npix*10, first n_valid entries meaningful, parse_output order):
+ *   hit_adc_d, hit_x_d, hit_y_d, hit_z_d, hit_ticks_d, hit_prob_d (float), hit_event_d, hit_pixel_d (int32),
+ *   n_valid_d[1].  saved_d (npix, 32) float: per-row state needed by larnd_fee_backward. */
+int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
+                      const larnd_params_t* params, const float* noise_d,
+                      float* adc_d, float* ticks_d, float* pixel_z_d, float* pixel_x_d, float* pixel_y_d,
+                      int32_t* event_d, float* saved_d,
+                      float* hit_adc_d, float* hit_x_d, float* hit_y_d, float* hit_z_d, float* hit_ticks_d,
+                      float* hit_prob_d, int32_t* hit_event_d, int32_t* hit_pixel_d, int32_t* n_valid_d,
+                      void* scratch_d, size_t scratch_bytes, void* stream);
+size_t larnd_fee_scratch_bytes(int32_t npix);
+
+/* VJP of get_adc_values+digitize: g_adc_d (npix,10) -> g_wfs_d (npix, n_ticks-1) with row stride. */
+int larnd_fee_backward(const float* g_adc_d, const float* ticks_d, const float* saved_d, int32_t npix,
+                       const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, void* stream);
+
+/* MC-current mode with number_pix_neighbors = 0 and mc_diff = True.  rnd_d: (N,3) standard normals
+ * (the reference draws random.normal(key,(N,3)), detsim_jax.py:393).  Same output convention as
+ * larnd_lut_forward. */
+int larnd_mc_forward(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
+                     const larnd_params_t* params, const float* rnd_d, int32_t n_events, int32_t npix_capacity,
+                     void* workspace_d, size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d,
+                     int32_t* counts_d, void* stream);
+int larnd_mc_backward(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
+                      const larnd_params_t* params, const float* rnd_d, int32_t n_events, int32_t npix_capacity,
+                      void* workspace_d, size_t workspace_bytes, const float* g_wfs_d, int64_t g_row_stride,
+                      float* grad_params_d, void* stream);
+
+/* Layout of the per-segment records inside the workspace (for tests / debugging): field f of segment s
+ * is ((float*)workspace_d)[f * n_segments + s]; integer fields are bit-cast int32. */
+enum {
+  LARND_F_Q = 0, LARND_F_FRAC, LARND_F_SL, LARND_F_A, LARND_F_B, LARND_F_C,
+  LARND_F_WX0, LARND_F_WX1, LARND_F_WX2, LARND_F_WX3, LARND_F_WX4,
+  LARND_F_WY0, LARND_F_WY1, LARND_F_WY2, LARND_F_WY3, LARND_F_WY4,
+  LARND_F_TD, LARND_F_X0, LARND_F_Y0, LARND_F_ST, LARND_F_REC, LARND_F_FT,
+  LARND_F_XI /* recombination csi */, LARND_F_COS2 /* cos^2(phi), ellipsoid model */,
+  LARND_I_T0 /* Nt-L-ct */, LARND_I_IDX, LARND_I_BX, LARND_I_BY, LARND_I_EP /* event*n_tpc+plane */,
+  LARND_I_FLAGS /* bit0 TPC mask, bit1 z>z_anode, bit2 z>z_cathode */, LARND_I_MAINPIX,
+  LARND_NFIELDS
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LARND_B200_H */

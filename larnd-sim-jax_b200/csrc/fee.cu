@@ -1,0 +1,316 @@
+// K5 front-end electronics: fused discriminator / ADC / digitiser / coordinates / hit compaction, sm_100a.
+//
+// Replaces the XLA lowering of simulate_stochastic (reference sim_jax.py:738-769):
+//   get_adc_values (fee_jax.py:170-279: cumsum, 10x {first threshold crossing, hold-delay sample, reject,
+//   subtract, clamp}), digitize (fee_jax.py:57-71), id2pixel / get_pixel_coordinates / get_hit_z
+//   (detsim_jax.py:265-319) and parse_output (sim_jax.py:620-647).
+//
+// One warp owns one pixel row (n_ticks-1 samples, 8 KB in shared memory).  The running sum is formed
+// strictly left to right in float32 by lane 0 (bit-identical to a sequential cumsum, so threshold
+// crossings match the oracle exactly); the ten discriminator passes are warp-cooperative ballot scans
+// over the row in shared memory.  HBM traffic = one read of the waveform + O(10) words per row.
+#include "larnd_common.cuh"
+
+namespace {
+
+constexpr int FEE_WARPS = 4;
+constexpr int FEE_THREADS = FEE_WARPS * 32;
+
+struct FeeArgs {
+  const float* wfs;
+  int64_t stride;
+  const int32_t* unique_pixels;
+  int npix;
+  int ntw;  // n_ticks - 1
+  const float* noise;
+  float* adc; float* ticks; float* pixel_z; float* pixel_x; float* pixel_y; int32_t* event; float* saved;
+  int32_t* row_counts;
+};
+
+__device__ __forceinline__ int floordiv_pos(int a, int b) { return floordiv_i(a, b); }
+
+__global__ void __launch_bounds__(FEE_THREADS)
+k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_params_t p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * FEE_WARPS + wid;
+  if (row >= F.npix) return;
+  const int Nt = F.ntw;
+  float* c = smem + (size_t)wid * Nt;
+  const float* w = F.wfs + (int64_t)row * F.stride;
+  for (int t = lane; t < Nt; t += 32) c[t] = __fmul_rn(w[t], p.t_sampling);  // q = wfs * t_sampling
+  __syncwarp();
+  if (lane == 0) {  // sequential float32 running sum (fee_jax.py:193)
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int t = 0; t < Nt; ++t) {
+      acc = __fadd_rn(acc, c[t]);
+      c[t] = acc;
+    }
+  }
+  __syncwarp();
+  const float thr = p.discrimination_threshold;
+  const int interval = p.hold_interval;
+  const int nmax = p.max_adc_values;
+  const float* nz = F.noise;
+  const int64_t np = F.npix;
+  float base = nz ? __fmul_rn(nz[row], p.reset_noise_charge) : 0.0f;
+  // pixel geometry (id2pixel with Python floor semantics; negative ids give event < 0)
+  const int pid = F.unique_pixels[row];
+  const int nx = p.n_pixels_x, ny = p.n_pixels_y, ntpc = p.n_tpc;
+  const int xp = pid - floordiv_pos(pid, nx) * nx;
+  const int t1 = floordiv_pos(pid, nx);
+  const int yp = t1 - floordiv_pos(t1, ny) * ny;
+  const int t2 = floordiv_pos(pid, nx * ny);
+  const int plane = t2 - floordiv_pos(t2, ntpc) * ntpc;
+  const int ev = floordiv_pos(pid, nx * ny * ntpc);
+  const float z_anode = p.tpc_borders[plane][2][0], z_high = p.tpc_borders[plane][2][1];
+  const float dz = __fsub_rn(z_high, z_anode);
+  const float sgn = dz > 0.0f ? 1.0f : (dz < 0.0f ? -1.0f : 0.0f);
+  const float adc_scale_den = p.v_ref_minus_cm;
+  unsigned hit_mask = 0, spos_mask = 0, slope_mask = 0;
+  int n_valid = 0;
+  for (int it = 0; it < nmax; ++it) {
+    // first t with q_sum[t] <= thr <= q_sum[t+1] (fee_jax.py:200-203); fill value Nt-2
+    int idx_t = Nt - 2;
+    for (int t0 = 0; t0 < Nt - 1; t0 += 32) {
+      int t = t0 + lane;
+      bool hit = false;
+      if (t < Nt - 1) {
+        float a = __fadd_rn(base, c[t]), b = __fadd_rn(base, c[t + 1]);
+        hit = (b >= thr) && (a <= thr);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { idx_t = t0 + __ffs(m) - 1; break; }
+    }
+    int end = idx_t + 1 + interval;
+    if (end >= Nt) end = Nt - 1;
+    const float q_nn = c[end];
+    const float q_vals = __fadd_rn(base, q_nn);
+    const float extra = nz ? __fmul_rn(nz[np * (1 + it) + row], p.uncorrelated_noise_charge) : 0.0f;
+    float adc = (q_nn != 0.0f) ? __fadd_rn(q_vals, extra) : q_nn;
+    const bool cond = (adc < thr) || (idx_t == Nt - 2);
+    if (cond) adc = 0.0f;
+    const float ic = cond ? (float)(Nt - 2) : (float)idx_t;
+    base = nz ? (cond ? __fmul_rn(nz[np * (21 + it) + row], p.uncorrelated_noise_charge)
+                      : __fmul_rn(nz[np * (11 + it) + row], p.reset_noise_charge))
+              : 0.0f;
+    int end2 = idx_t + 1 + interval + 1;
+    if (end2 >= Nt) end2 = Nt - 1;
+    const float sub = c[end2];
+    __syncwarp();
+    for (int t = lane; t < Nt; t += 32) {
+      float v = __fsub_rn(c[t], sub);
+      c[t] = (v < 0.0f) ? 0.0f : v;
+    }
+    __syncwarp();
+    // digitize (fee_jax.py:68-69)
+    float inner = __fsub_rn(__fadd_rn(__fmul_rn(adc, p.gain), p.v_pedestal), p.v_cm);
+    float dig = __fdiv_rn(__fmul_rn(fmaxf(inner, 0.0f), p.adc_counts), adc_scale_den);
+    const bool sloped = (inner > 0.0f) && (dig < p.adc_counts);
+    dig = fminf(dig, p.adc_counts);
+    const float hp = (ic < (float)(Nt - 3)) ? 1.0f : 0.0f;
+    const float pz = __fadd_rn(z_anode, __fmul_rn(__fmul_rn(__fmul_rn(ic, p.t_sampling), p.vdrift), sgn));
+    if (!cond) hit_mask |= 1u << it;
+    if (sub > 0.0f) spos_mask |= 1u << it;
+    if (sloped && !cond) slope_mask |= 1u << it;
+    if (hp > p.hit_prob_threshold && ev >= 0 && pid >= 0) ++n_valid;
+    if (lane == 0) {
+      F.adc[(int64_t)row * nmax + it] = dig;
+      F.ticks[(int64_t)row * nmax + it] = ic;
+      F.pixel_z[(int64_t)row * nmax + it] = pz;
+      if (F.saved) F.saved[(int64_t)row * 32 + it] = (float)idx_t;
+    }
+  }
+  if (lane == 0) {
+    F.pixel_x[row] = __fadd_rn(__fadd_rn(__fmul_rn((float)xp, p.pixel_pitch), p.tpc_borders[plane][0][0]), p.half_pitch);
+    F.pixel_y[row] = __fadd_rn(__fadd_rn(__fmul_rn((float)yp, p.pixel_pitch), p.tpc_borders[plane][1][0]), p.half_pitch);
+    F.event[row] = ev;
+    F.row_counts[row] = n_valid;
+    if (F.saved) {
+      F.saved[(int64_t)row * 32 + 10] = __int_as_float((int)hit_mask);
+      F.saved[(int64_t)row * 32 + 11] = __int_as_float((int)spos_mask);
+      F.saved[(int64_t)row * 32 + 12] = __int_as_float((int)slope_mask);
+    }
+  }
+}
+
+// exclusive scan of row_counts (single CTA, looped) -> offsets, total
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
+                                                      int32_t* __restrict__ total) {
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n; b0 += 1024) {
+    int i = b0 + threadIdx.x;
+    int v = i < n ? counts[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int x = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += u;
+      }
+      wsum[lane] = x;
+    }
+    __syncthreads();
+    int off = carry + (wid > 0 ? wsum[wid - 1] : 0) + inc - v;
+    if (i < n) offsets[i] = off;
+    int blk_total = wsum[31];
+    __syncthreads();
+    if (threadIdx.x == 0) carry += blk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+struct CompactArgs {
+  const float* adc; const float* ticks; const float* pixel_z; const float* pixel_x; const float* pixel_y;
+  const int32_t* event; const int32_t* unique_pixels; const int32_t* offsets;
+  float* hit_adc; float* hit_x; float* hit_y; float* hit_z; float* hit_ticks; float* hit_prob;
+  int32_t* hit_event; int32_t* hit_pixel;
+  int npix, nmax, ntw;
+  float hit_prob_threshold;
+};
+
+// parse_output (sim_jax.py:620-647): row-major stable compaction of valid (pixel, hit) slots
+__global__ void k_compact_hits(const __grid_constant__ CompactArgs C) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= C.npix) return;
+  const int pid = C.unique_pixels[row], ev = C.event[row];
+  if (ev < 0 || pid < 0) return;
+  int o = C.offsets[row];
+  for (int k = 0; k < C.nmax; ++k) {
+    float tk = C.ticks[(int64_t)row * C.nmax + k];
+    float hp = (tk < (float)(C.ntw - 3)) ? 1.0f : 0.0f;
+    if (hp > C.hit_prob_threshold) {
+      C.hit_adc[o] = C.adc[(int64_t)row * C.nmax + k];
+      C.hit_x[o] = C.pixel_x[row];
+      C.hit_y[o] = C.pixel_y[row];
+      C.hit_z[o] = C.pixel_z[(int64_t)row * C.nmax + k];
+      C.hit_ticks[o] = tk;
+      C.hit_prob[o] = hp;
+      C.hit_event[o] = ev;
+      C.hit_pixel[o] = pid;
+      ++o;
+    }
+  }
+}
+
+// VJP of get_adc_values + digitize.  With c^k the running sum after k subtractions, hit k samples
+// v_k = c^k[e_k] and subtracts S_k = c^k[e2_k]; c^{k+1} = relu(c^k - S_k).  A value that is still positive
+// at step k was never clamped, so the adjoint of c^0 is supported on the <= 20 positions {e_k, e2_k}:
+//   T_k = g_k*hit_k + Sbar_k*[S_k > 0],   Sbar_k = -sum_{k' > k} T_k',
+//   cbar[e_k] += g_k*hit_k,  cbar[e2_k] += Sbar_k*[S_k > 0],   g_wfs[t] = t_sampling * sum_{t' >= t} cbar[t'].
+__global__ void __launch_bounds__(128)
+k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved, int npix, int ntw,
+               const __grid_constant__ larnd_params_t p, float* __restrict__ g_wfs, int64_t g_stride) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= npix) return;
+  const int nmax = p.max_adc_values;
+  const float* sv = saved + (int64_t)row * 32;
+  const unsigned hit_mask = (unsigned)__float_as_int(sv[10]);
+  const unsigned spos_mask = (unsigned)__float_as_int(sv[11]);
+  const unsigned slope_mask = (unsigned)__float_as_int(sv[12]);
+  const float slope = p.gain * p.adc_counts / p.v_ref_minus_cm;
+  int pos[2 * LARND_MAX_ADC];
+  float val[2 * LARND_MAX_ADC];
+  float tail = 0.0f;  // sum_{k' > k} T_k'
+  for (int k = nmax - 1; k >= 0; --k) {
+    const int idx_t = (int)sv[k];
+    int e = idx_t + 1 + p.hold_interval; if (e >= ntw) e = ntw - 1;
+    int e2 = idx_t + 2 + p.hold_interval; if (e2 >= ntw) e2 = ntw - 1;
+    const float gk = ((hit_mask >> k) & 1u) && ((slope_mask >> k) & 1u) ? g_adc[(int64_t)row * nmax + k] * slope : 0.0f;
+    const float sbar = ((spos_mask >> k) & 1u) ? -tail : 0.0f;
+    pos[2 * k] = e; val[2 * k] = gk;
+    pos[2 * k + 1] = e2; val[2 * k + 1] = sbar;
+    tail += gk + sbar;
+  }
+  float* out = g_wfs + (int64_t)row * g_stride;
+  const bool any = hit_mask != 0;
+  for (int t = lane; t < ntw; t += 32) {
+    float s = 0.0f;
+    if (any) {
+      for (int k = 0; k < 2 * nmax; ++k) s += (pos[k] >= t) ? val[k] : 0.0f;
+    }
+    out[t] = s * p.t_sampling;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t larnd_fee_scratch_bytes(int32_t npix) { return align_up((size_t)npix * 2 * sizeof(int32_t) + 64, 256); }
+
+extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
+                                 const larnd_params_t* params, const float* noise_d, float* adc_d, float* ticks_d,
+                                 float* pixel_z_d, float* pixel_x_d, float* pixel_y_d, int32_t* event_d, float* saved_d,
+                                 float* hit_adc_d, float* hit_x_d, float* hit_y_d, float* hit_z_d, float* hit_ticks_d,
+                                 float* hit_prob_d, int32_t* hit_event_d, int32_t* hit_pixel_d, int32_t* n_valid_d,
+                                 void* scratch_d, size_t scratch_bytes, void* stream) {
+  if (!wfs_d || !unique_pixels_d || !params || !adc_d || !ticks_d || !pixel_z_d || !pixel_x_d || !pixel_y_d || !event_d ||
+      !n_valid_d || !scratch_d) {
+    larnd_set_error("larnd_fee_forward: null argument");
+    return LARND_E_ARG;
+  }
+  if (params->max_adc_values < 1 || params->max_adc_values > LARND_MAX_ADC) {
+    larnd_set_error("larnd_fee_forward: MAX_ADC_VALUES=%d unsupported (1..%d)", params->max_adc_values, LARND_MAX_ADC);
+    return LARND_E_ARG;
+  }
+  if (scratch_bytes < larnd_fee_scratch_bytes(npix)) {
+    larnd_set_error("larnd_fee_forward: scratch too small");
+    return LARND_E_CAPACITY;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntw = params->n_ticks - 1;
+  if (npix == 0) { LARND_CUDA(cudaMemsetAsync(n_valid_d, 0, sizeof(int32_t), st)); return LARND_OK; }
+  FeeArgs F;
+  F.wfs = wfs_d; F.stride = wfs_row_stride; F.unique_pixels = unique_pixels_d; F.npix = npix; F.ntw = ntw;
+  F.noise = noise_d; F.adc = adc_d; F.ticks = ticks_d; F.pixel_z = pixel_z_d; F.pixel_x = pixel_x_d; F.pixel_y = pixel_y_d;
+  F.event = event_d; F.saved = saved_d;
+  F.row_counts = reinterpret_cast<int32_t*>(scratch_d);
+  int32_t* offsets = F.row_counts + npix;
+  size_t smem = (size_t)FEE_WARPS * ntw * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LARND_CUDA(cudaFuncSetAttribute(k_fee_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) { larnd_set_error("larnd_fee_forward: n_ticks too large for shared memory"); return LARND_E_ARG; }
+  k_fee_forward<<<(npix + FEE_WARPS - 1) / FEE_WARPS, FEE_THREADS, smem, st>>>(F, *params);
+  LARND_LAUNCH_CHECK("k_fee_forward");
+  k_scan_counts<<<1, 1024, 0, st>>>(F.row_counts, npix, offsets, n_valid_d);
+  LARND_LAUNCH_CHECK("k_scan_counts");
+  if (hit_adc_d) {
+    CompactArgs C;
+    C.adc = adc_d; C.ticks = ticks_d; C.pixel_z = pixel_z_d; C.pixel_x = pixel_x_d; C.pixel_y = pixel_y_d; C.event = event_d;
+    C.unique_pixels = unique_pixels_d; C.offsets = offsets;
+    C.hit_adc = hit_adc_d; C.hit_x = hit_x_d; C.hit_y = hit_y_d; C.hit_z = hit_z_d; C.hit_ticks = hit_ticks_d; C.hit_prob = hit_prob_d;
+    C.hit_event = hit_event_d; C.hit_pixel = hit_pixel_d;
+    C.npix = npix; C.nmax = params->max_adc_values; C.ntw = ntw; C.hit_prob_threshold = params->hit_prob_threshold;
+    k_compact_hits<<<(npix + 127) / 128, 128, 0, st>>>(C);
+    LARND_LAUNCH_CHECK("k_compact_hits");
+  }
+  return LARND_OK;
+}
+
+extern "C" int larnd_fee_backward(const float* g_adc_d, const float* ticks_d, const float* saved_d, int32_t npix,
+                                  const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, void* stream) {
+  (void)ticks_d;
+  if (!g_adc_d || !saved_d || !params || !g_wfs_d) { larnd_set_error("larnd_fee_backward: null argument"); return LARND_E_ARG; }
+  if (npix == 0) return LARND_OK;
+  k_fee_backward<<<(npix + 3) / 4, 128, 0, (cudaStream_t)stream>>>(g_adc_d, saved_d, npix, params->n_ticks - 1, *params,
+                                                                 g_wfs_d, g_row_stride);
+  LARND_LAUNCH_CHECK("k_fee_backward");
+  return LARND_OK;
+}

@@ -1,0 +1,98 @@
+// Internal declarations shared by the larnd_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "larnd_b200.h"
+
+#define LARND_WARP 32
+#define LARND_OFF_PAD 4  // response rows are stored as [0,0,R[0..L-1],0,0]: Lp = L + 4, sample k at index k+2
+
+// Device tables built by larnd_lut_create (see lut_tables.cu).
+struct larnd_lut {
+  int ntpl, nx, ny, nt, L, Lp;
+  float* r0;  // [nx*ny][Lp]          template 0, last L samples of every (ci,cj) bin
+  float* rm;  // [ntpl][25][Lp]       all templates, collecting bins ci,cj < 5
+  float* c0;  // [nx*ny][nt]          running sum of template 0
+  float* cm;  // [ntpl][25][nt]       running sum of all templates, collecting bins
+};
+
+// Views into the caller-provided workspace.
+struct Workspace {
+  float* rec;         // LARND_NFIELDS x N (SoA)
+  uint32_t* bitmap;   // n_words
+  uint32_t* wprefix;  // n_words (exclusive popcount prefix)
+  uint32_t* bsums;    // block sums for the scan
+  float* partials;    // per-chunk gradient partials (n_chunks_max x 16)
+  int64_t n;
+  int64_t n_words;
+  int64_t n_scan_blocks;
+  int32_t pid_offset;  // nx*ny*ntpc: bit index of pixel id p is p + pid_offset (event -1 ids are negative)
+  int64_t n_chunks_max;
+};
+
+#define LARND_SCAN_WORDS_PER_BLOCK 2048
+#define LARND_CHUNK 128  // segments per accumulate CTA
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool larnd_carve_workspace(void* base, size_t bytes, int64_t n, int32_t n_events, int32_t ntpc, int32_t nx,
+                           int32_t ny, Workspace* ws);
+void larnd_set_error(const char* fmt, ...);
+int larnd_check_cuda(cudaError_t e, const char* what);
+#define LARND_CUDA(call)                                   \
+  do {                                                     \
+    int _rc = larnd_check_cuda((call), #call);             \
+    if (_rc != 0) return _rc;                              \
+  } while (0)
+#define LARND_LAUNCH_CHECK(name) LARND_CUDA(cudaGetLastError())
+
+// ---- device helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ int floordiv_i(int a, int b) {  // python-style floor division, b > 0
+  int q = a / b;
+  return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+// pixel2id with int32 wrap-around (detsim_jax.py:232-244; x64 is never enabled in the reference)
+__device__ __forceinline__ int pixel2id_dev(int px, int py, int ep, int nx, int ny) {
+  if (px >= nx || py >= ny || px < 0 || py < 0) return -1;
+  unsigned u = (unsigned)ep * (unsigned)ny + (unsigned)py;
+  u = u * (unsigned)nx + (unsigned)px;
+  return (int)u;
+}
+
+struct RowLookup {
+  const uint32_t* bitmap;
+  const uint32_t* wprefix;
+  int64_t n_words;
+  int pid_offset;
+  int n_unique;  // number of distinct main pixel ids
+  int n_neg;     // ids < -1
+  int npix;      // padded length of unique_pixels
+};
+
+// Row of pixel id `pid` in the reference's sorted, -1 padded unique_pixels (sim_jax.py:717-725,152-154).
+// Returns -1 when pid is not in the list.  pid == -1 always matches (the appended -1 entry).
+__device__ __forceinline__ int lookup_row(const RowLookup& lk, int pid) {
+  if (pid == -1) return lk.n_neg;
+  long long b = (long long)pid + lk.pid_offset;
+  if (b < 0 || (b >> 5) >= lk.n_words) return -1;
+  uint32_t w = __ldg(lk.bitmap + (b >> 5));
+  uint32_t bit = 1u << (b & 31);
+  if (!(w & bit)) return -1;
+  int rank = (int)__ldg(lk.wprefix + (b >> 5)) + __popc(w & (bit - 1));
+  return pid < 0 ? rank : lk.npix - lk.n_unique + rank;
+}
+
+// kernels / launchers implemented in the .cu files
+int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& cols, const larnd_params_t& p,
+                         const larnd_lut* lut, const Workspace& ws, int32_t* counts, cudaStream_t st);
+int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t* unique_pixels,
+                        int32_t* counts, cudaStream_t st);
+int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st);
+int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                            int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
+int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                                int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride, float* grad_params,
+                                const int32_t* counts, cudaStream_t st);

@@ -1,0 +1,95 @@
+// Device tables derived once from the response template bank (reference: consts_jax.py:387-449 builds the
+// bank; sim_jax.py:228 recomputes jnp.cumsum(response_template) over the whole 1.58 GB bank on EVERY call —
+// here the running sums are hoisted to LUT-load time and restricted to the rows the path can touch:
+// template 0 for every (ci,cj) bin (neighbours, sim_jax.py:221-222,250-255) and all templates for the 5x5
+// collecting bins (main pixels: currents_idx in [0,4], sim_jax.py:435,184-190,236-241)).
+#include "larnd_common.cuh"
+
+namespace {
+
+// compact rows: [0, 0, R[nt-L .. nt-1], 0, 0]
+__global__ void k_compact_rows(const float* __restrict__ bank, int nx, int ny, int nt, int L, int Lp, int ntpl,
+                               float* __restrict__ r0, float* __restrict__ rm) {
+  const int n0 = nx * ny;
+  const int nrows = n0 + ntpl * 25;
+  for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const float* src;
+    float* dst;
+    if (r < n0) {
+      src = bank + (int64_t)r * nt;
+      dst = r0 + (int64_t)r * Lp;
+    } else {
+      int m = r - n0, t = m / 25, b = m % 25, ci = b / 5, cj = b % 5;
+      src = bank + (((int64_t)t * nx + ci) * ny + cj) * nt;
+      dst = rm + (int64_t)m * Lp;
+    }
+    for (int k = threadIdx.x; k < Lp; k += blockDim.x) {
+      int kk = k - 2;
+      dst[k] = (kk >= 0 && kk < L) ? src[nt - L + kk] : 0.0f;
+    }
+  }
+}
+
+// float32 running sum along time, strictly left to right (bit-identical to a sequential cumsum)
+__global__ void k_cumsum_rows(const float* __restrict__ bank, int nx, int ny, int nt, int ntpl,
+                              float* __restrict__ c0, float* __restrict__ cm) {
+  const int n0 = nx * ny;
+  const int nrows = n0 + ntpl * 25;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const float* src;
+  float* dst;
+  if (r < n0) {
+    src = bank + (int64_t)r * nt;
+    dst = c0 + (int64_t)r * nt;
+  } else {
+    int m = r - n0, t = m / 25, b = m % 25, ci = b / 5, cj = b % 5;
+    src = bank + (((int64_t)t * nx + ci) * ny + cj) * nt;
+    dst = cm + (int64_t)m * nt;
+  }
+  float acc = 0.0f;
+  for (int k = 0; k < nt; ++k) {
+    acc = __fadd_rn(acc, src[k]);
+    dst[k] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int larnd_lut_create(const float* bank_d, int n_templates, int nx, int ny, int nt, int signal_length,
+                                void* stream, larnd_lut_t** out) {
+  if (!bank_d || !out || n_templates < 3 || n_templates > LARND_MAX_TEMPLATES || nx < 5 || ny < 5 || nt < 2 ||
+      signal_length < 1 || signal_length > nt) {
+    larnd_set_error("larnd_lut_create: invalid shape (ntpl=%d nx=%d ny=%d nt=%d L=%d)", n_templates, nx, ny, nt,
+                    signal_length);
+    return LARND_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  larnd_lut* lut = new larnd_lut();
+  lut->ntpl = n_templates; lut->nx = nx; lut->ny = ny; lut->nt = nt; lut->L = signal_length;
+  lut->Lp = signal_length + LARND_OFF_PAD;
+  size_t n0 = (size_t)nx * ny, nm = (size_t)n_templates * 25;
+  lut->r0 = lut->rm = lut->c0 = lut->cm = nullptr;
+  int rc = LARND_OK;
+  auto fail = [&](int code) { larnd_lut_destroy(lut); return code; };
+  if ((rc = larnd_check_cuda(cudaMalloc(&lut->r0, n0 * lut->Lp * sizeof(float)), "cudaMalloc r0"))) return fail(rc);
+  if ((rc = larnd_check_cuda(cudaMalloc(&lut->rm, nm * lut->Lp * sizeof(float)), "cudaMalloc rm"))) return fail(rc);
+  if ((rc = larnd_check_cuda(cudaMalloc(&lut->c0, n0 * nt * sizeof(float)), "cudaMalloc c0"))) return fail(rc);
+  if ((rc = larnd_check_cuda(cudaMalloc(&lut->cm, nm * nt * sizeof(float)), "cudaMalloc cm"))) return fail(rc);
+  int nrows = (int)(n0 + nm);
+  k_compact_rows<<<min(nrows, 148 * 8), 128, 0, st>>>(bank_d, nx, ny, nt, signal_length, lut->Lp, n_templates, lut->r0, lut->rm);
+  if ((rc = larnd_check_cuda(cudaGetLastError(), "k_compact_rows"))) return fail(rc);
+  k_cumsum_rows<<<(nrows + 63) / 64, 64, 0, st>>>(bank_d, nx, ny, nt, n_templates, lut->c0, lut->cm);
+  if ((rc = larnd_check_cuda(cudaGetLastError(), "k_cumsum_rows"))) return fail(rc);
+  *out = lut;
+  return LARND_OK;
+}
+
+extern "C" void larnd_lut_destroy(larnd_lut_t* lut) {
+  if (!lut) return;
+  cudaFree(lut->r0);
+  cudaFree(lut->rm);
+  cudaFree(lut->c0);
+  cudaFree(lut->cm);
+  delete lut;
+}

@@ -1,0 +1,342 @@
+// K1 segment_prepare + K2 unique/renumber (bitmap + popcount scan), sm_100a.
+//
+// Replaces the XLA lowering of simulate_drift_new (reference sim_jax.py:375-453: shift_tracks :109-119,
+// quench quenching_jax.py:38-75, drift drifting_jax.py:19-58, get_bin_shifts detsim_jax.py:494-512,
+// density_2d detsim_jax.py:332-354, pixel2id detsim_jax.py:232-244) and of the
+// jnp.unique / sort / searchsorted block of simulate_wfs (sim_jax.py:717-725).
+//
+// Everything that feeds an integer result (bins, pixel ids, ticks, template index) is written with
+// explicit round-to-nearest intrinsics so that nvcc cannot contract mul+add into FMA: the reference
+// evaluates these op by op in float32 and the ids must match bit for bit.
+#include "larnd_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// jnp.floor_divide for floats (_float_divmod): round((a - fmod(a,b))/b) with sign fix-up
+__device__ __forceinline__ float floor_divide_f(float a, float b) {
+  float mod = fmodf(a, b);
+  float div = fdiv(fsub(a, mod), b);
+  if (mod != 0.0f && ((b < 0.0f) != (mod < 0.0f))) div = fsub(div, 1.0f);
+  return roundf(div);  // lax.round: half away from zero
+}
+// jnp.remainder for floats
+__device__ __forceinline__ float remainder_f(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.0f && ((m < 0.0f) != (b < 0.0f))) m = fadd(m, b);
+  return m;
+}
+
+constexpr int PREP_THREADS = 128;
+
+__global__ void __launch_bounds__(PREP_THREADS)
+k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ larnd_columns_t cols,
+          const __grid_constant__ larnd_params_t p, int nt, float* __restrict__ rec, uint32_t* __restrict__ bitmap,
+          int64_t n_words, int pid_offset, int32_t* __restrict__ counts) {
+  extern __shared__ float srow[];
+  const int ncols = cols.ncols;
+  const int stride = ncols | 1;  // odd stride: conflict-free row reads
+  const int64_t base = (int64_t)blockIdx.x * PREP_THREADS;
+  const int rows_here = (int)min((int64_t)PREP_THREADS, n - base);
+  const int total = rows_here * ncols;
+  const float* src = tracks + base * ncols;
+  for (int i = threadIdx.x; i < total; i += PREP_THREADS) {
+    int r = i / ncols, c = i - r * ncols;
+    srow[r * stride + c] = __ldg(src + i);  // coalesced stream of the 104-byte records
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  const bool active = t < rows_here;
+  int pid = 0;
+  bool pid_ok = false;
+  if (active) {
+    const float* tr = srow + t * stride;
+    const int64_t s = base + t;
+    // shift_tracks
+    float x = fsub(tr[cols.x], p.shift_x);
+    float y = fsub(tr[cols.y], p.shift_y);
+    float z = fsub(tr[cols.z], p.shift_z);
+    float dEdx = tr[cols.dEdx], dE = tr[cols.dE];
+    // quench
+    float recomb, xi, cos2 = 0.0f;
+    if (p.recombination_mode == 2) {
+      xi = fdiv(fmul(p.kb, dEdx), p.efield_rho);
+      recomb = fdiv(p.Ab, fadd(1.0f, xi));
+    } else if (p.recombination_mode == 1) {
+      float csi = fdiv(fmul(p.beta, dEdx), p.efield_rho);
+      recomb = fmaxf(0.0f, fdiv(logf(fadd(p.alpha, csi)), csi));
+      xi = csi;
+    } else {
+      float zs = fsub(tr[cols.z_start], p.shift_z), ze = fsub(tr[cols.z_end], p.shift_z);
+      float cosphi = fdiv(fabsf(fsub(ze, zs)), fadd(tr[cols.dx], 1e-10f));
+      float c2 = fmul(cosphi, cosphi);
+      float bphi = fdiv(p.beta, __fsqrt_rn(fadd(fsub(1.0f, c2), fmul(p.inv_R2, c2))));
+      float csi = fdiv(fmul(bphi, dEdx), p.efield_rho);
+      recomb = fmaxf(0.0f, fdiv(logf(fadd(p.alpha, csi)), fadd(csi, 1e-10f)));
+      xi = csi;
+      cos2 = c2;
+    }
+    float ne = fmul(fmul(recomb, dE), p.MeVToElectrons);
+    // drift: TPC membership (first TPC that contains the point, argmax of the boolean row)
+    int plane = 0;
+    bool inside = false;
+    for (int k = p.n_tpc - 1; k >= 0; --k) {
+      float za = p.tpc_borders[k][2][0], zc = p.tpc_borders[k][2][1];
+      float zmin = fminf(fsub(zc, p.size_margin), fsub(za, p.size_margin));
+      float zmax = fmaxf(fadd(zc, p.size_margin), fadd(za, p.size_margin));
+      bool c = x >= fsub(p.tpc_borders[k][0][0], p.size_margin) && x <= fadd(p.tpc_borders[k][0][1], p.size_margin) &&
+               y >= fsub(p.tpc_borders[k][1][0], p.size_margin) && y <= fadd(p.tpc_borders[k][1][1], p.size_margin) &&
+               z >= zmin && z <= zmax;
+      if (c) { plane = k; inside = true; }
+    }
+    const float z_anode = p.tpc_borders[plane][2][0];
+    const float z_cath = p.tpc_borders[plane][2][1];
+    float dd = fadd(fabsf(fsub(z, z_anode)), 1e-6f);
+    float td = fdiv(dd, p.vdrift);
+    float life = expf(-fdiv(td, p.lifetime));
+    float q = fmul(fmul(ne, life), inside ? 1.0f : 0.0f);
+    float sl_cm = __fsqrt_rn(fmul(fmul(td, 2.0f), p.long_diff));
+    float sT = __fsqrt_rn(fmul(fmul(td, 2.0f), p.tran_diff));
+    // sub-pixel bins and in-bin position
+    float xr = fsub(x, p.tpc_borders[plane][0][0]);
+    float yr = fsub(y, p.tpc_borders[plane][1][0]);
+    int bx = (int)floor_divide_f(xr, p.bin_width);
+    int by = (int)floor_divide_f(yr, p.bin_width);
+    float x0 = remainder_f(xr, p.bin_width);
+    float y0 = remainder_f(yr, p.bin_width);
+    // transverse diffusion weights: 5 bin integrals per axis, outer edges forced to -1/+1
+    const float s2sig = fmul(1.41421354f, sT);
+    float ex[LARND_NB_TRAN_BINS + 1], ey[LARND_NB_TRAN_BINS + 1];
+    ex[0] = ey[0] = -1.0f;
+    ex[LARND_NB_TRAN_BINS] = ey[LARND_NB_TRAN_BINS] = 1.0f;
+#pragma unroll
+    for (int k = 1; k < LARND_NB_TRAN_BINS; ++k) {
+      ex[k] = erff(fdiv(fsub(p.tran_bin_edges[k], x0), s2sig));
+      ey[k] = erff(fdiv(fsub(p.tran_bin_edges[k], y0), s2sig));
+    }
+#pragma unroll
+    for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
+      rec[(int64_t)(LARND_F_WX0 + k) * n + s] = fmul(0.5f, fsub(ex[k + 1], ex[k]));
+      rec[(int64_t)(LARND_F_WY0 + k) * n + s] = fmul(0.5f, fsub(ey[k + 1], ey[k]));
+    }
+    // time to the cathode -> tick + fraction (sim_jax.py:418-420,157-159)
+    float t0 = fdiv(fabsf(fsub(z, z_cath)), p.vdrift);
+    float ft = fdiv(t0, p.t_sampling);
+    int ct = (int)floorf(ft);
+    ct = max(0, min(ct, nt - 1));
+    float frac = fsub(ft, (float)ct);
+    // longitudinal diffusion in ticks -> template index + Lagrange weights (sim_jax.py:423,162-168)
+    float sl = fdiv(fdiv(sl_cm, p.vdrift), p.t_sampling);
+    int lo = 0, hi = p.n_templates;  // searchsorted side='left': number of template values < sl
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (p.long_diff_template[mid] < sl) lo = mid + 1; else hi = mid;
+    }
+    int idx = max(1, min(lo, p.n_templates - 2));
+    float t0v = p.long_diff_template[idx - 1], t1v = p.long_diff_template[idx], t2v = p.long_diff_template[idx + 1];
+    float a = fdiv(fmul(fsub(sl, t1v), fsub(sl, t2v)), fmul(fsub(t0v, t1v), fsub(t0v, t2v)));
+    float b = fdiv(fmul(fsub(sl, t0v), fsub(sl, t2v)), fmul(fsub(t1v, t0v), fsub(t1v, t2v)));
+    float c = fdiv(fmul(fsub(sl, t0v), fsub(sl, t1v)), fmul(fsub(t2v, t0v), fsub(t2v, t1v)));
+    int ev = (int)tr[cols.eventID];
+    int ep = ev * p.n_tpc + plane;
+    const int nb = p.nb_sampling_bins_per_pixel;
+    pid = pixel2id_dev(floordiv_i(bx, nb), floordiv_i(by, nb), ep, p.n_pixels_x, p.n_pixels_y);
+    pid_ok = true;
+    int flags = (inside ? 1 : 0) | (fsub(z, z_anode) > 0.0f ? 2 : 0) | (fsub(z, z_cath) > 0.0f ? 4 : 0);
+    rec[(int64_t)LARND_F_Q * n + s] = q;
+    rec[(int64_t)LARND_F_FRAC * n + s] = frac;
+    rec[(int64_t)LARND_F_SL * n + s] = sl;
+    rec[(int64_t)LARND_F_A * n + s] = a;
+    rec[(int64_t)LARND_F_B * n + s] = b;
+    rec[(int64_t)LARND_F_C * n + s] = c;
+    rec[(int64_t)LARND_F_TD * n + s] = td;
+    rec[(int64_t)LARND_F_X0 * n + s] = x0;
+    rec[(int64_t)LARND_F_Y0 * n + s] = y0;
+    rec[(int64_t)LARND_F_ST * n + s] = sT;
+    rec[(int64_t)LARND_F_REC * n + s] = recomb;
+    rec[(int64_t)LARND_F_FT * n + s] = ft;
+    rec[(int64_t)LARND_F_XI * n + s] = xi;
+    rec[(int64_t)LARND_F_COS2 * n + s] = cos2;
+    int* irec = reinterpret_cast<int*>(rec);
+    irec[(int64_t)LARND_I_T0 * n + s] = nt - p.signal_length - ct;
+    irec[(int64_t)LARND_I_IDX * n + s] = idx;
+    irec[(int64_t)LARND_I_BX * n + s] = bx;
+    irec[(int64_t)LARND_I_BY * n + s] = by;
+    irec[(int64_t)LARND_I_EP * n + s] = ep;
+    irec[(int64_t)LARND_I_FLAGS * n + s] = flags;
+    irec[(int64_t)LARND_I_MAINPIX * n + s] = pid;
+  }
+  // mark the main pixel in the bitmap: one atomic per distinct id per warp
+  unsigned live = __ballot_sync(0xffffffffu, pid_ok);
+  if (pid_ok) {
+    unsigned peers = __match_any_sync(live, pid);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      long long bidx = (long long)pid + pid_offset;
+      if (bidx < 0 || (bidx >> 5) >= n_words) {
+        atomicOr(counts + 2, 2);  // event id outside the declared [-1, n_events) range
+      } else {
+        uint32_t bit = 1u << (bidx & 31);
+        if (!(__ldg(bitmap + (bidx >> 5)) & bit)) atomicOr(bitmap + (bidx >> 5), bit);
+      }
+    }
+  }
+}
+
+// ---- popcount scan over the bitmap -------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int WORDS_PER_THREAD = LARND_SCAN_WORDS_PER_BLOCK / SCAN_THREADS;  // 8
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int offset = wid > 0 ? warp_sums[wid - 1] : 0;
+  if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return offset + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_block_sums(const uint32_t* __restrict__ bitmap, int64_t n_words, uint32_t* __restrict__ bsums) {
+  int64_t w0 = (int64_t)blockIdx.x * LARND_SCAN_WORDS_PER_BLOCK + threadIdx.x * WORDS_PER_THREAD;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < WORDS_PER_THREAD; ++k)
+    if (w0 + k < n_words) c += __popc(bitmap[w0 + k]);
+  int total;
+  block_exclusive_scan(c, &total);
+  if (threadIdx.x == 0) bsums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_bsums(uint32_t* __restrict__ bsums, int64_t n_blocks, int32_t* __restrict__ counts) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < n_blocks; b0 += SCAN_THREADS) {
+    int64_t i = b0 + threadIdx.x;
+    int v = i < n_blocks ? (int)bsums[i] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, &total);
+    int c = carry;
+    if (i < n_blocks) bsums[i] = c + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[0] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_final(const uint32_t* __restrict__ bitmap, int64_t n_words, const uint32_t* __restrict__ bsums,
+             uint32_t* __restrict__ wprefix, int pid_offset, int32_t* __restrict__ counts) {
+  int64_t w0 = (int64_t)blockIdx.x * LARND_SCAN_WORDS_PER_BLOCK + threadIdx.x * WORDS_PER_THREAD;
+  uint32_t words[WORDS_PER_THREAD];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < WORDS_PER_THREAD; ++k) {
+    words[k] = (w0 + k < n_words) ? bitmap[w0 + k] : 0u;
+    c += __popc(words[k]);
+  }
+  int ex = block_exclusive_scan(c, nullptr) + (int)bsums[blockIdx.x];
+  const int64_t m1_bit = (int64_t)pid_offset - 1;  // bit of pixel id -1
+#pragma unroll
+  for (int k = 0; k < WORDS_PER_THREAD; ++k) {
+    if (w0 + k < n_words) {
+      wprefix[w0 + k] = (uint32_t)ex;
+      if (w0 + k == (m1_bit >> 5)) counts[1] = ex + __popc(words[k] & ((1u << (m1_bit & 31)) - 1u));  // ids < -1
+    }
+    ex += __popc(words[k]);
+  }
+}
+
+// unique_pixels = sort(pad(append(unique(main_pixels), -1), -1)) (sim_jax.py:717-721)
+__global__ void k_emit_unique(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wprefix, int64_t n_words,
+                              int pid_offset, int32_t npix, int32_t* __restrict__ unique_pixels, int32_t* __restrict__ counts) {
+  const int n_unique = counts[0];
+  if (n_unique + 1 > npix) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(counts + 2, 1);
+    return;
+  }
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t w = gtid; w < n_words; w += gsz) {
+    uint32_t word = bitmap[w];
+    int rank = (int)wprefix[w];
+    while (word) {
+      int b = __ffs(word) - 1;
+      word &= word - 1;
+      int pid = (int)((w << 5) + b - pid_offset);
+      int row = pid < 0 ? rank : npix - n_unique + rank;  // ids <= -1 keep their rank; ids >= 0 sit at the end
+      unique_pixels[row] = pid;
+      ++rank;
+    }
+  }
+  // the block of -1 entries: one appended + padding (+ the natural -1 written above, same value)
+  const int n_neg = counts[1];
+  const int64_t m1_bit = (int64_t)pid_offset - 1;
+  const int has_m1 = (bitmap[m1_bit >> 5] >> (m1_bit & 31)) & 1;
+  const int n_pos = n_unique - n_neg - has_m1;
+  for (int64_t i = n_neg + gtid; i < npix - n_pos; i += gsz) unique_pixels[i] = -1;
+}
+
+}  // namespace
+
+int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& cols, const larnd_params_t& p,
+                         const larnd_lut* lut, const Workspace& ws, int32_t* counts, cudaStream_t st) {
+  LARND_CUDA(cudaMemsetAsync(ws.bitmap, 0, ws.n_words * sizeof(uint32_t), st));
+  LARND_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
+  if (n == 0) return LARND_OK;
+  const int stride = cols.ncols | 1;
+  size_t smem = (size_t)PREP_THREADS * stride * sizeof(float);
+  int64_t blocks = (n + PREP_THREADS - 1) / PREP_THREADS;
+  k_prepare<<<(unsigned)blocks, PREP_THREADS, smem, st>>>(tracks, n, cols, p, lut ? lut->nt : 0, ws.rec, ws.bitmap,
+                                                         ws.n_words, ws.pid_offset, counts);
+  LARND_LAUNCH_CHECK("k_prepare");
+  return LARND_OK;
+}
+
+int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st) {
+  (void)p;
+  k_scan_block_sums<<<(unsigned)ws.n_scan_blocks, SCAN_THREADS, 0, st>>>(ws.bitmap, ws.n_words, ws.bsums);
+  LARND_LAUNCH_CHECK("k_scan_block_sums");
+  k_scan_bsums<<<1, SCAN_THREADS, 0, st>>>(ws.bsums, ws.n_scan_blocks, counts);
+  LARND_LAUNCH_CHECK("k_scan_bsums");
+  k_scan_final<<<(unsigned)ws.n_scan_blocks, SCAN_THREADS, 0, st>>>(ws.bitmap, ws.n_words, ws.bsums, ws.wprefix,
+                                                                    ws.pid_offset, counts);
+  LARND_LAUNCH_CHECK("k_scan_final");
+  return LARND_OK;
+}
+
+int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t* unique_pixels,
+                        int32_t* counts, cudaStream_t st) {
+  (void)p;
+  int64_t blocks = (ws.n_words + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  k_emit_unique<<<(unsigned)blocks, 256, 0, st>>>(ws.bitmap, ws.wprefix, ws.n_words, ws.pid_offset, npix_capacity,
+                                                  unique_pixels, counts);
+  LARND_LAUNCH_CHECK("k_emit_unique");
+  return LARND_OK;
+}

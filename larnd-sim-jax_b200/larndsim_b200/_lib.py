@@ -1,0 +1,135 @@
+"""ctypes binding of liblarnd_b200.so (the C ABI declared in include/larnd_b200.h).
+
+The shared library is built in-tree by :func:`build_library` (nvcc, sm_100a) and loaded lazily.  There is
+no CPU fallback: if the library is missing or cannot be loaded every kernel entry point raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(os.path.dirname(HERE), "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+LIB_PATH = os.path.join(HERE, "liblarnd_b200.so")
+SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_bwd.cu", "fee.cu", "mc_current.cu"]
+
+MAX_TPC = 8
+MAX_TEMPLATES = 128
+NB_TRAN_BINS = 5
+MAX_ADC = 10
+NPARAMS = 15
+PARAM_ORDER = ("Ab", "kb", "eField", "lifetime", "long_diff", "tran_diff", "shift_x", "shift_y", "shift_z",
+               "alpha", "beta", "R_param", "lArDensity", "MeVToElectrons", "vdrift")
+
+# record fields inside the workspace (enum in larnd_b200.h)
+REC_FIELDS = ("Q", "FRAC", "SL", "A", "B", "C", "WX0", "WX1", "WX2", "WX3", "WX4", "WY0", "WY1", "WY2", "WY3", "WY4",
+              "TD", "X0", "Y0", "ST", "REC", "FT", "XI", "COS2", "T0", "IDX", "BX", "BY", "EP", "FLAGS", "MAINPIX")
+REC_INT_FIELDS = ("T0", "IDX", "BX", "BY", "EP", "FLAGS", "MAINPIX")
+
+
+class Columns(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("ncols", "eventID", "x", "y", "z", "z_start", "z_end", "dx", "dEdx", "dE", "t0")]
+
+
+class ParamsPOD(C.Structure):
+    _fields_ = [
+        ("recombination_mode", C.c_int32),
+        ("Ab", C.c_float), ("kb", C.c_float), ("alpha", C.c_float), ("beta", C.c_float), ("inv_R2", C.c_float),
+        ("efield_rho", C.c_float), ("MeVToElectrons", C.c_float),
+        ("vdrift", C.c_float), ("lifetime", C.c_float), ("long_diff", C.c_float), ("tran_diff", C.c_float),
+        ("size_margin", C.c_float),
+        ("shift_x", C.c_float), ("shift_y", C.c_float), ("shift_z", C.c_float),
+        ("n_tpc", C.c_int32),
+        ("tpc_borders", C.c_float * 2 * 3 * MAX_TPC),
+        ("pixel_pitch", C.c_float), ("bin_width", C.c_float), ("half_pitch", C.c_float),
+        ("nb_sampling_bins_per_pixel", C.c_int32), ("n_pixels_x", C.c_int32), ("n_pixels_y", C.c_int32),
+        ("number_pix_neighbors", C.c_int32),
+        ("tran_bin_edges", C.c_float * (NB_TRAN_BINS + 1)),
+        ("t_sampling", C.c_float),
+        ("n_ticks", C.c_int32), ("signal_length", C.c_int32), ("n_templates", C.c_int32),
+        ("long_diff_template", C.c_float * MAX_TEMPLATES),
+        ("discrimination_threshold", C.c_float), ("reset_noise_charge", C.c_float),
+        ("uncorrelated_noise_charge", C.c_float),
+        ("gain", C.c_float), ("v_cm", C.c_float), ("v_ref_minus_cm", C.c_float), ("v_pedestal", C.c_float),
+        ("adc_counts", C.c_float), ("hit_prob_threshold", C.c_float),
+        ("hold_interval", C.c_int32), ("max_adc_values", C.c_int32),
+        ("diffusion_in_current_sim", C.c_int32),
+        ("dvdrift_dEfield", C.c_float),
+        ("eField", C.c_float), ("lArDensity", C.c_float), ("R_param", C.c_float),
+    ]
+
+
+class LarndError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def nvcc_command(out=LIB_PATH, extra=()):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    return (["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+             "-Xcompiler", "-fPIC", "-shared", "-I" + INCLUDE, "-o", out] + list(extra) + srcs)
+
+
+def build_library(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into liblarnd_b200.so (in-tree, next to this file)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = nvcc_command()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(" ".join(cmd))
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise LarndError("nvcc failed:\n" + res.stderr)
+    return LIB_PATH
+
+
+def _declare(lib):
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    PP, PC = C.POINTER(ParamsPOD), C.POINTER(Columns)
+    lib.larnd_last_error.restype = C.c_char_p
+    lib.larnd_abi_version.restype = C.c_int
+    lib.larnd_lut_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    lib.larnd_lut_destroy.argtypes = [vp]
+    lib.larnd_lut_destroy.restype = None
+    lib.larnd_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
+    lib.larnd_workspace_bytes.restype = sz
+    lib.larnd_lut_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp]
+    lib.larnd_lut_prepare.argtypes = [vp, i64, PC, PP, vp, i32, vp, sz, vp, vp]
+    lib.larnd_lut_accumulate.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp]
+    lib.larnd_lut_backward.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
+    lib.larnd_fee_forward.argtypes = [vp, i64, vp, i32, PP, vp] + [vp] * 16 + [vp, sz, vp]
+    lib.larnd_fee_scratch_bytes.argtypes = [i32]
+    lib.larnd_fee_scratch_bytes.restype = sz
+    lib.larnd_fee_backward.argtypes = [vp, vp, vp, i32, PP, vp, i64, vp]
+    if hasattr(lib, "larnd_mc_forward"):
+        lib.larnd_mc_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, vp, vp]
+        lib.larnd_mc_backward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, i64, vp, vp]
+    for name in ("larnd_lut_create", "larnd_lut_forward", "larnd_lut_prepare", "larnd_lut_accumulate", "larnd_lut_backward",
+                 "larnd_fee_forward", "larnd_fee_backward", "larnd_mc_forward", "larnd_mc_backward"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_int
+
+
+def get_lib():
+    """Load the CUDA library; raises LarndError (never falls back to a CPU path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LarndError("liblarnd_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(the CUDA extension is mandatory, there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise LarndError("larnd_b200 error %d: %s" % (rc, get_lib().larnd_last_error().decode()))

@@ -1,0 +1,46 @@
+"""Consumer-side helpers kept for drop-in use of the simulated hits: adc2charge and the weighted-MMD
+``mse_adc`` loss (reference: larndsim.losses_jax :380-383, :14-39, :58-82), as differentiable torch ops.
+The losses are O(hits^2) on <= 1e3 hits and are not part of the accelerated path."""
+import torch
+
+from . import sim as _sim
+
+
+def adc2charge(dw, params):
+    return (dw / params.ADC_COUNTS * (params.V_REF - params.V_CM) + params.V_CM - params.V_PEDESTAL) / params.GAIN * 1e-3
+
+
+def rbf_kernel(x, y, sigma):
+    d2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    return torch.exp(-d2 / (2 * sigma ** 2))
+
+
+def mmd(x, y, px, py, sigma):
+    kxx = (rbf_kernel(x, x, sigma) * px[:, None] * px[None, :]).sum()
+    kyy = (rbf_kernel(y, y, sigma) * py[:, None] * py[None, :]).sum()
+    kxy = (rbf_kernel(x, y, sigma) * px[:, None] * py[None, :]).sum()
+    sx, sy = px.sum(), py.sum()
+    return kxx / sx ** 2 + kyy / sy ** 2 - 2 * kxy / (sx * sy)
+
+
+def mse_adc(params, Q, x, y, z, ticks, hit_prob, event, ref_Q, ref_x, ref_y, ref_z, ref_ticks, ref_hit_prob, ref_event,
+            sigma=1, lambda_Q=1):
+    w_ref, w = ref_Q * ref_hit_prob, Q * hit_prob
+    ref_st = torch.stack((ref_x + ref_event * 1e5, ref_y, ref_z), dim=-1)
+    st = torch.stack((x + event * 1e5, y, z), dim=-1)
+    mmd_term = mmd(st, ref_st, w, w_ref, sigma)
+    tot_ref, tot = w_ref.sum(), w.sum()
+    charge_loss = ((tot - tot_ref) / (tot_ref + 1e-6)) ** 2
+    aux = {"charge_loss": charge_loss, "mmd_loss_term": mmd_term, "Q": Q, "ref_Q": ref_Q, "ref_hit_prob": ref_hit_prob,
+           "hit_prob": hit_prob}
+    return mmd_term + lambda_Q * charge_loss, aux
+
+
+def params_loss(params, response, ref_adcs, ref_x, ref_y, ref_z, ref_ticks, ref_hit_prob, ref_event, tracks, fields,
+                rngkey=None, loss_fn=mse_adc, **loss_kwargs):
+    """loss(params) through simulate_wfs + simulate_stochastic (reference: losses_jax.py:385-398)."""
+    wfs, unique_pixels = _sim.simulate_wfs(params, response, tracks, fields)
+    adcs, x, y, z, ticks, hit_prob, event, _ = _sim.simulate_stochastic(params, wfs, unique_pixels, rngseed=rngkey)
+    Q, ref_Q = adc2charge(adcs, params), adc2charge(ref_adcs, params)
+    return loss_fn(params, Q, x, y, z, ticks, hit_prob, event.float(), ref_Q, ref_x, ref_y, ref_z, ref_ticks, ref_hit_prob,
+                   ref_event.float(), **loss_kwargs)

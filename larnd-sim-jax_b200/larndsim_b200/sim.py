@@ -1,0 +1,394 @@
+"""Simulation drivers: host-side mirror of the reference's ``larndsim.sim_jax``.
+
+Same public names and call signatures — ``simulate_wfs`` (sim_jax.py:689), ``simulate_stochastic`` (:738),
+``simulate_parametrized`` (:339), ``simulate_drift_new`` (:375), ``simulate_signals`` (:142), ``parse_output``
+(:620), ``pad_size`` (:61), ``shift_tracks`` (:109) — but arrays are CUDA ``torch`` tensors and the work is done
+by the hand-written sm_100a kernels of liblarnd_b200.so, reached through the C ABI (include/larnd_b200.h) and
+wrapped in ``torch.autograd.Function`` (the role ``jax.custom_vjp`` plays for the jax.ffi binding, see
+INTEGRATION.md).  There is no CPU path: a missing library or a CPU tensor raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .consts import RecombinationMode, linspace_f32, vdrift_and_derivative
+
+size_history_dict = {}
+
+
+def pad_size(cur_size, tag, pad_threshold=0.05):
+    """Shape bucketing with the reference's semantics (sim_jax.py:61-102): reuse a known size within
+    ``pad_threshold`` or create ``cur*(1+thr/2)``.  Kept so that output shapes seen by callers are the
+    reference's; the kernels themselves never recompile."""
+    single = isinstance(cur_size, (int, np.integer))
+    cur = (int(cur_size),) if single else tuple(int(c) for c in cur_size)
+    hist = size_history_dict.setdefault(tag, [])
+    if cur in hist:
+        return cur[0] if single else cur
+    for size in hist:
+        if all(c <= s <= c * (1 + pad_threshold) for c, s in zip(cur, size)):
+            return size[0] if single else size
+    new = tuple(int(c * (1 + pad_threshold / 2) + 0.5) for c in cur)
+    hist.append(new)
+    hist.sort()
+    return new[0] if single else new
+
+
+def get_size_history():
+    return size_history_dict
+
+
+# ------------------------------------------------------------------------------------------ parameter block
+def _f(params, name):
+    return params.value(name)
+
+
+def make_pod(params, lut_shape=None):
+    """Fill the C parameter block.  Python-float constant expressions are evaluated in double and rounded to
+    float32 once, which is what the reference's weak-typed constants do under jit."""
+    P = _lib.ParamsPOD()
+    mode = params.recombination_mode
+    P.recombination_mode = mode.value if isinstance(mode, RecombinationMode) else int(mode)
+    P.Ab, P.kb, P.alpha, P.beta = _f(params, "Ab"), _f(params, "kb"), _f(params, "alpha"), _f(params, "beta")
+    P.inv_R2 = 1.0 / _f(params, "R_param") ** 2
+    P.efield_rho = _f(params, "eField") * _f(params, "lArDensity")
+    P.MeVToElectrons = _f(params, "MeVToElectrons")
+    v, dv = vdrift_and_derivative(params)
+    P.vdrift, P.dvdrift_dEfield = v, dv
+    P.lifetime, P.long_diff, P.tran_diff = _f(params, "lifetime"), _f(params, "long_diff"), _f(params, "tran_diff")
+    P.size_margin = params.size_margin
+    P.shift_x, P.shift_y, P.shift_z = _f(params, "shift_x"), _f(params, "shift_y"), _f(params, "shift_z")
+    borders = np.asarray(params.tpc_borders, dtype=np.float64)
+    if borders.ndim != 3 or borders.shape[0] > _lib.MAX_TPC:
+        raise ValueError("tpc_borders must have shape (n_tpc<=%d, 3, 2)" % _lib.MAX_TPC)
+    P.n_tpc = borders.shape[0]
+    for i in range(borders.shape[0]):
+        for j in range(3):
+            for k in range(2):
+                P.tpc_borders[i][j][k] = borders[i, j, k]
+    nb = int(params.nb_sampling_bins_per_pixel)
+    P.pixel_pitch = params.pixel_pitch
+    P.bin_width = params.pixel_pitch / nb
+    P.half_pitch = params.pixel_pitch / 2
+    P.nb_sampling_bins_per_pixel = nb
+    P.n_pixels_x, P.n_pixels_y = int(params.n_pixels_x), int(params.n_pixels_y)
+    P.number_pix_neighbors = int(params.number_pix_neighbors)
+    if int(params.nb_tran_diff_bins) != _lib.NB_TRAN_BINS:
+        raise ValueError("nb_tran_diff_bins must be %d" % _lib.NB_TRAN_BINS)
+    sym = (_lib.NB_TRAN_BINS - 1) // 2
+    w = params.pixel_pitch / nb
+    for i, e in enumerate(linspace_f32(np.float32(-sym * w), np.float32((sym + 1) * w), _lib.NB_TRAN_BINS + 1)):
+        P.tran_bin_edges[i] = e
+    P.t_sampling = params.t_sampling
+    P.n_ticks = int(params.time_interval[1] / params.t_sampling) + 1
+    P.signal_length = int(params.signal_length)
+    tpl = np.asarray(params.long_diff_template, dtype=np.float32)
+    if tpl.shape[0] > _lib.MAX_TEMPLATES:
+        raise ValueError("too many longitudinal-diffusion templates")
+    P.n_templates = tpl.shape[0] if lut_shape is None else int(lut_shape[0])
+    for i, t in enumerate(tpl):
+        P.long_diff_template[i] = t
+    P.discrimination_threshold = params.DISCRIMINATION_THRESHOLD
+    P.reset_noise_charge = params.RESET_NOISE_CHARGE
+    P.uncorrelated_noise_charge = params.UNCORRELATED_NOISE_CHARGE
+    P.gain, P.v_cm, P.v_pedestal = params.GAIN, params.V_CM, params.V_PEDESTAL
+    P.v_ref_minus_cm = params.V_REF - params.V_CM
+    P.adc_counts = params.ADC_COUNTS
+    P.hit_prob_threshold = params.hit_prob_threshold
+    P.hold_interval = round((3 * params.CLOCK_CYCLE + params.ADC_HOLD_DELAY * params.CLOCK_CYCLE) / params.t_sampling)
+    P.max_adc_values = int(params.MAX_ADC_VALUES)
+    P.diffusion_in_current_sim = int(bool(params.diffusion_in_current_sim))
+    P.eField, P.lArDensity, P.R_param = _f(params, "eField"), _f(params, "lArDensity"), _f(params, "R_param")
+    return P
+
+
+def make_columns(fields):
+    fields = tuple(fields)
+    c = _lib.Columns()
+    c.ncols = len(fields)
+    for name in ("eventID", "x", "y", "z", "z_start", "z_end", "dx", "dEdx", "dE", "t0"):
+        if name not in fields:
+            raise ValueError("tracks are missing the '%s' column" % name)
+        setattr(c, name, fields.index(name))
+    return c
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _check_cuda(t, name):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise _lib.LarndError("%s must be a CUDA torch tensor (larndsim_b200 has no CPU path)" % name)
+
+
+# ------------------------------------------------------------------------------------------ LUT handle cache
+class _LutHandle:
+    def __init__(self, bank, L):
+        self.bank = bank  # keeps the pointer alive / unique
+        self.L = L
+        self.shape = tuple(bank.shape)
+        h = C.c_void_p()
+        ntpl, nx, ny, nt = self.shape
+        _lib.check(_lib.get_lib().larnd_lut_create(_ptr(bank), ntpl, nx, ny, nt, L, _stream(), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.get_lib().larnd_lut_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_lut_cache = {}
+
+
+def get_lut(response_template, signal_length):
+    """Device tables (compacted response rows + running sums) for (response_template, signal_length); built
+    once and cached — the reference recomputes cumsum(response_template) on every call (sim_jax.py:228)."""
+    _check_cuda(response_template, "response_template")
+    if response_template.dtype != torch.float32 or response_template.dim() != 4:
+        raise ValueError("response_template must be a float32 (n_templates, Nx, Ny, Nt) tensor")
+    rt = response_template.contiguous()
+    key = (rt.data_ptr(), tuple(rt.shape), int(signal_length), rt.device.index, rt._version)
+    h = _lut_cache.get(key)
+    if h is None:
+        with torch.cuda.device(rt.device):
+            h = _LutHandle(rt, int(signal_length))
+        if len(_lut_cache) > 8:
+            _lut_cache.pop(next(iter(_lut_cache)))
+        _lut_cache[key] = h
+    return h
+
+
+# ------------------------------------------------------------------------------------------ LUT waveform simulation
+class LutState:
+    """Everything a backward pass (or a kernel-level test) needs from one forward call."""
+    __slots__ = ("workspace", "counts", "n", "n_events", "npix", "pod", "lut", "unique_pixels", "wfs_full", "flags")
+
+
+def n_events_of(tracks, fields):
+    """Upper bound (max local event id + 1) used to size the pixel bitmap; one tiny device reduction + sync, the
+    counterpart of the host-side event-id validation the reference runs per batch (optimize/simulate.py:111-113)."""
+    ev = tracks[:, tuple(fields).index("eventID")]
+    return max(int(ev.max().item()) + 1, 0) if ev.numel() else 0
+
+
+def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n_events=None, flags=0, out=None):
+    """prepare -> unique/renumber -> accumulate.  ``npix_capacity=None`` reproduces the reference's padded size
+    pad_size(n_unique+1,'unique_pixels',0.2) (one 16-byte D2H read, like jnp.unique's sync); an explicit
+    capacity keeps the whole call asynchronous.  Returns a LutState."""
+    _check_cuda(tracks, "tracks")
+    if tracks.dtype != torch.float32 or tracks.dim() != 2:
+        raise ValueError("tracks must be a float32 (N, n_fields) tensor")
+    tracks = tracks.contiguous()
+    lib = _lib.get_lib()
+    with torch.cuda.device(tracks.device):
+        lut = get_lut(response_template, params.signal_length)
+        pod = make_pod(params, lut.shape)
+        cols = make_columns(fields)
+        n = tracks.shape[0]
+        if n_events is None:
+            n_events = n_events_of(tracks, fields)
+        ws_bytes = lib.larnd_workspace_bytes(n, n_events, pod.n_tpc, pod.n_pixels_x, pod.n_pixels_y)
+        st = LutState()
+        st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=tracks.device)
+        st.counts = torch.zeros(4, dtype=torch.int32, device=tracks.device)
+        st.n, st.n_events, st.pod, st.lut, st.flags = n, n_events, pod, lut, int(flags)
+        _lib.check(lib.larnd_lut_prepare(_ptr(tracks), n, C.byref(cols), C.byref(pod), lut.handle, n_events,
+                                         _ptr(st.workspace), ws_bytes, _ptr(st.counts), _stream()))
+        if npix_capacity is None:
+            cnt = st.counts.cpu()
+            if int(cnt[2]) != 0:
+                raise ValueError("eventID outside [-1, n_events) found in tracks")
+            npix_capacity = pad_size(int(cnt[0]) + 1, "unique_pixels", 0.2)
+        st.npix = int(npix_capacity)
+        if out is None:
+            st.unique_pixels = torch.empty(st.npix, dtype=torch.int32, device=tracks.device)
+            st.wfs_full = torch.empty((st.npix, pod.n_ticks), dtype=torch.float32, device=tracks.device)
+        else:
+            st.unique_pixels, st.wfs_full = out
+        _lib.check(lib.larnd_lut_accumulate(n, C.byref(pod), lut.handle, n_events, st.npix, st.flags, _ptr(st.workspace),
+                                            ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_full), _ptr(st.counts), _stream()))
+    return st
+
+
+def lut_backward(st, g_wfs, skip_garbage=False):
+    """VJP of simulate_wfs: g_wfs is the gradient of the (Npix, Nticks-1) output.  Returns a float32 tensor of
+    LARND_NPARAMS parameter gradients (order _lib.PARAM_ORDER)."""
+    lib = _lib.get_lib()
+    g = g_wfs.contiguous()
+    nt1 = st.pod.n_ticks - 1
+    if tuple(g.shape) != (st.npix, nt1):
+        raise ValueError("gradient shape %s != %s" % (tuple(g.shape), (st.npix, nt1)))
+    grad = torch.zeros(_lib.NPARAMS, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        # column c of the full row (c >= 1) is g[:, c-1]: pass g - 1 element with stride Nticks-1
+        _lib.check(lib.larnd_lut_backward(st.n, C.byref(st.pod), st.lut.handle, st.n_events, st.npix,
+                                          1 if skip_garbage else 0, _ptr(st.workspace), st.workspace.numel(),
+                                          _ptr(st.counts), C.c_void_p(g.data_ptr() - 4), nt1, _ptr(grad), _stream()))
+    return grad
+
+
+class _SimulateWfs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, params, response_template, tracks, fields, names, npix_capacity, n_events):
+        st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
+        ctx.st = st
+        ctx.names = names
+        ctx.mark_non_differentiable(st.unique_pixels)
+        return st.wfs_full[:, 1:], st.unique_pixels
+
+    @staticmethod
+    def backward(ctx, g_wfs, _g_pix):
+        grad_all = lut_backward(ctx.st, g_wfs)
+        idx = torch.tensor([_lib.PARAM_ORDER.index(n) for n in ctx.names], device=grad_all.device)
+        return (grad_all[idx],) + (None,) * 7
+
+
+def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, n_events=None):
+    """(wfs (Npix, Nticks-1) float32, unique_pixels (Npix,) int32 sorted, -1 padded at the front).
+    Reference: sim_jax.py:689-736.  Differentiable w.r.t. the Params fields built with build_params_class."""
+    leaves = params.grad_leaves()
+    if leaves and torch.is_grad_enabled():
+        names = tuple(n for n, _ in leaves)
+        theta = torch.stack([t.to(tracks.device, torch.float32) for _, t in leaves])
+        return _SimulateWfs.apply(theta, params, response_template, tracks, tuple(fields), names, npix_capacity, n_events)
+    st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
+    return st.wfs_full[:, 1:], st.unique_pixels
+
+
+def simulate_signals_state(params, response_template, tracks, fields, **kw):
+    """Kernel-level access for tests: returns the LutState (full waveforms incl. garbage column, workspace)."""
+    return lut_forward(params, response_template, tracks, fields, **kw)
+
+
+def record_fields(st):
+    """Per-segment records written by the prepare kernel as {name: tensor} (ints as int32)."""
+    n = st.n
+    rec = st.workspace[: len(_lib.REC_FIELDS) * n * 4].view(torch.float32).view(len(_lib.REC_FIELDS), n)
+    out = {}
+    for i, name in enumerate(_lib.REC_FIELDS):
+        out[name] = rec[i].view(torch.int32) if name in _lib.REC_INT_FIELDS else rec[i]
+    return out
+
+
+# ------------------------------------------------------------------------------------------ front end
+class FeeState:
+    __slots__ = ("adc", "ticks", "pixel_z", "pixel_x", "pixel_y", "event", "saved", "hits", "n_valid", "npix", "pod")
+
+
+def fee_forward(params, wfs, unique_pixels, noise=None, compact=True, pod=None):
+    """Runs the fused FEE kernel on (Npix, Nticks-1) waveforms (any row stride)."""
+    _check_cuda(wfs, "wfs")
+    _check_cuda(unique_pixels, "unique_pixels")
+    lib = _lib.get_lib()
+    if wfs.dtype != torch.float32 or wfs.dim() != 2 or wfs.stride(1) != 1:
+        wfs = wfs.contiguous().float()
+    unique_pixels = unique_pixels.to(torch.int32).contiguous()
+    pod = make_pod(params) if pod is None else pod
+    npix, ntw = wfs.shape
+    if ntw != pod.n_ticks - 1:
+        raise ValueError("wfs has %d ticks, params imply %d" % (ntw, pod.n_ticks - 1))
+    dev = wfs.device
+    fs = FeeState()
+    fs.npix, fs.pod = npix, pod
+    k = pod.max_adc_values
+    with torch.cuda.device(dev):
+        fs.adc = torch.empty((npix, k), dtype=torch.float32, device=dev)
+        fs.ticks = torch.empty((npix, k), dtype=torch.float32, device=dev)
+        fs.pixel_z = torch.empty((npix, k), dtype=torch.float32, device=dev)
+        fs.pixel_x = torch.empty(npix, dtype=torch.float32, device=dev)
+        fs.pixel_y = torch.empty(npix, dtype=torch.float32, device=dev)
+        fs.event = torch.empty(npix, dtype=torch.int32, device=dev)
+        fs.saved = torch.zeros((npix, 32), dtype=torch.float32, device=dev)
+        fs.n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
+        scratch = torch.empty(lib.larnd_fee_scratch_bytes(npix), dtype=torch.uint8, device=dev)
+        if compact:
+            hf = torch.empty((6, npix * k), dtype=torch.float32, device=dev)
+            hi = torch.empty((2, npix * k), dtype=torch.int32, device=dev)
+            hp = [_ptr(hf[i]) for i in range(6)] + [_ptr(hi[0]), _ptr(hi[1])]
+            fs.hits = (hf, hi)
+        else:
+            hp = [C.c_void_p(0)] * 8
+            fs.hits = None
+        if noise is not None:
+            noise = noise.to(dev, torch.float32).contiguous()
+            if noise.numel() != npix * (1 + 3 * k):
+                raise ValueError("noise must hold npix*(1+3*MAX_ADC_VALUES) standard normals")
+        _lib.check(lib.larnd_fee_forward(_ptr(wfs), wfs.stride(0), _ptr(unique_pixels), npix, C.byref(pod), _ptr(noise),
+                                         _ptr(fs.adc), _ptr(fs.ticks), _ptr(fs.pixel_z), _ptr(fs.pixel_x), _ptr(fs.pixel_y),
+                                         _ptr(fs.event), _ptr(fs.saved), *hp, _ptr(fs.n_valid),
+                                         _ptr(scratch), scratch.numel(), _stream()))
+    return fs
+
+
+def fee_backward(fs, g_adc):
+    lib = _lib.get_lib()
+    g = g_adc.contiguous().float()
+    ntw = fs.pod.n_ticks - 1
+    out = torch.empty((fs.npix, ntw), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(lib.larnd_fee_backward(_ptr(g), _ptr(fs.ticks), _ptr(fs.saved), fs.npix, C.byref(fs.pod), _ptr(out), ntw, _stream()))
+    return out
+
+
+class _FeeAdc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wfs, params, unique_pixels, noise):
+        fs = fee_forward(params, wfs, unique_pixels, noise, compact=False)
+        ctx.fs = fs
+        ctx.mark_non_differentiable(fs.ticks, fs.pixel_x, fs.pixel_y, fs.event)
+        return fs.adc, fs.ticks, fs.pixel_x, fs.pixel_y, fs.event
+
+    @staticmethod
+    def backward(ctx, g_adc, *_unused):
+        return fee_backward(ctx.fs, g_adc), None, None, None
+
+
+def make_noise(params, npix, rngseed, device):
+    """Standard normals for the FEE noise terms, laid out [base | extra(10) | pass(10) | fail(10)].
+    NOT bit-compatible with jax.random (threefry parity is out of scope)."""
+    if params.RESET_NOISE_CHARGE == 0 and params.UNCORRELATED_NOISE_CHARGE == 0:
+        return None
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(rngseed) if rngseed is not None else 0)
+    return torch.randn(npix * (1 + 3 * int(params.MAX_ADC_VALUES)), generator=gen, device=device, dtype=torch.float32)
+
+
+def parse_output(params, adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, unique_pixels):
+    """Stable compaction of valid hits (reference: sim_jax.py:620-647).  Returns the padded-free arrays and
+    nb_valid (callers of the reference slice [:nb_valid]; here the slicing is already done)."""
+    mask = (hit_prob > params.hit_prob_threshold) & (event[:, None] >= 0) & (unique_pixels[:, None] >= 0)
+    k = mask.shape[1]
+    fm = mask.reshape(-1)
+    rep = lambda a: a.repeat_interleave(k)
+    out = (adcs.reshape(-1)[fm], rep(pixel_x)[fm], rep(pixel_y)[fm], pixel_z.reshape(-1)[fm], ticks.reshape(-1)[fm],
+           hit_prob.reshape(-1)[fm], rep(event)[fm], rep(unique_pixels)[fm])
+    return out + (int(fm.sum().item()),)
+
+
+def simulate_stochastic(params, wfs, unique_pixels, rngseed):
+    """(adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, hit_pixels), each (nb_valid,).
+    Reference: sim_jax.py:738-769.  Differentiable through adcs (w.r.t. wfs) and pixel_z (w.r.t. eField)."""
+    from .detsim import get_hit_z
+    noise = make_noise(params, wfs.shape[0], rngseed, wfs.device)
+    need_grad = torch.is_grad_enabled() and (wfs.requires_grad or bool(params.grad_leaves()))
+    if not need_grad:
+        fs = fee_forward(params, wfs, unique_pixels, noise, compact=True)
+        nv = int(fs.n_valid.item())
+        hf, hi = fs.hits
+        return hf[0, :nv], hf[1, :nv], hf[2, :nv], hf[3, :nv], hf[4, :nv], hf[5, :nv], hi[0, :nv], hi[1, :nv]
+    adcs, ticks, pixel_x, pixel_y, event = _FeeAdc.apply(wfs, params, unique_pixels, noise)
+    hit_prob = torch.where(ticks < wfs.shape[1] - 3, 1.0, 0.0)
+    plane = torch.div(unique_pixels, params.n_pixels_x * params.n_pixels_y, rounding_mode="floor") % np.asarray(params.tpc_borders).shape[0]
+    pixel_z = get_hit_z(params, ticks.reshape(-1), plane.repeat_interleave(ticks.shape[1])).reshape(ticks.shape)
+    out = parse_output(params, adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, unique_pixels.to(torch.int32))
+    return out[:8]
