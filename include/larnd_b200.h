@@ -181,8 +181,8 @@ int larnd_mc_forward(const float* tracks_d, int64_t n_segments, const larnd_colu
                      int32_t* counts_d, void* stream);
 int larnd_mc_backward(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
                       const larnd_params_t* params, const float* rnd_d, int32_t n_events, int32_t npix_capacity,
-                      void* workspace_d, size_t workspace_bytes, const float* g_wfs_d, int64_t g_row_stride,
-                      float* grad_params_d, void* stream);
+                      void* workspace_d, size_t workspace_bytes, const int32_t* counts_d, const float* g_wfs_d,
+                      int64_t g_row_stride, float* grad_params_d, void* stream);
 
 /* Layout of the per-segment records inside the workspace (for tests / debugging): field f of segment s
  * is ((float*)workspace_d)[f * n_segments + s]; integer fields are bit-cast int32. */

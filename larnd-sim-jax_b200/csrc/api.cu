@@ -115,7 +115,7 @@ extern "C" int larnd_lut_accumulate(int64_t n, const larnd_params_t* p, const la
   }
   cudaStream_t st = (cudaStream_t)stream;
   LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * p->n_ticks * sizeof(float), st));
-  if ((rc = larnd_launch_unique(ws, *p, npix_capacity, unique_pixels_d, counts_d, st))) return rc;
+  if ((rc = larnd_launch_unique(ws, *p, npix_capacity, /*extra=*/1, unique_pixels_d, counts_d, st))) return rc;
   return larnd_launch_accumulate(n, *p, lut, ws, npix_capacity, flags, wfs_d, counts_d, st);
 }
 

@@ -88,7 +88,7 @@ __device__ __forceinline__ int lookup_row(const RowLookup& lk, int pid) {
 // kernels / launchers implemented in the .cu files
 int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& cols, const larnd_params_t& p,
                          const larnd_lut* lut, const Workspace& ws, int32_t* counts, cudaStream_t st);
-int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t* unique_pixels,
+int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t extra, int32_t* unique_pixels,
                         int32_t* counts, cudaStream_t st);
 int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,

@@ -9,27 +9,9 @@
 // explicit round-to-nearest intrinsics so that nvcc cannot contract mul+add into FMA: the reference
 // evaluates these op by op in float32 and the ids must match bit for bit.
 #include "larnd_common.cuh"
+#include "segment_physics.cuh"
 
 namespace {
-
-__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-
-// jnp.floor_divide for floats (_float_divmod): round((a - fmod(a,b))/b) with sign fix-up
-__device__ __forceinline__ float floor_divide_f(float a, float b) {
-  float mod = fmodf(a, b);
-  float div = fdiv(fsub(a, mod), b);
-  if (mod != 0.0f && ((b < 0.0f) != (mod < 0.0f))) div = fsub(div, 1.0f);
-  return roundf(div);  // lax.round: half away from zero
-}
-// jnp.remainder for floats
-__device__ __forceinline__ float remainder_f(float a, float b) {
-  float m = fmodf(a, b);
-  if (m != 0.0f && ((m < 0.0f) != (b < 0.0f))) m = fadd(m, b);
-  return m;
-}
 
 constexpr int PREP_THREADS = 128;
 
@@ -56,51 +38,11 @@ k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ l
   if (active) {
     const float* tr = srow + t * stride;
     const int64_t s = base + t;
-    // shift_tracks
-    float x = fsub(tr[cols.x], p.shift_x);
-    float y = fsub(tr[cols.y], p.shift_y);
-    float z = fsub(tr[cols.z], p.shift_z);
-    float dEdx = tr[cols.dEdx], dE = tr[cols.dE];
-    // quench
-    float recomb, xi, cos2 = 0.0f;
-    if (p.recombination_mode == 2) {
-      xi = fdiv(fmul(p.kb, dEdx), p.efield_rho);
-      recomb = fdiv(p.Ab, fadd(1.0f, xi));
-    } else if (p.recombination_mode == 1) {
-      float csi = fdiv(fmul(p.beta, dEdx), p.efield_rho);
-      recomb = fmaxf(0.0f, fdiv(logf(fadd(p.alpha, csi)), csi));
-      xi = csi;
-    } else {
-      float zs = fsub(tr[cols.z_start], p.shift_z), ze = fsub(tr[cols.z_end], p.shift_z);
-      float cosphi = fdiv(fabsf(fsub(ze, zs)), fadd(tr[cols.dx], 1e-10f));
-      float c2 = fmul(cosphi, cosphi);
-      float bphi = fdiv(p.beta, __fsqrt_rn(fadd(fsub(1.0f, c2), fmul(p.inv_R2, c2))));
-      float csi = fdiv(fmul(bphi, dEdx), p.efield_rho);
-      recomb = fmaxf(0.0f, fdiv(logf(fadd(p.alpha, csi)), fadd(csi, 1e-10f)));
-      xi = csi;
-      cos2 = c2;
-    }
-    float ne = fmul(fmul(recomb, dE), p.MeVToElectrons);
-    // drift: TPC membership (first TPC that contains the point, argmax of the boolean row)
-    int plane = 0;
-    bool inside = false;
-    for (int k = p.n_tpc - 1; k >= 0; --k) {
-      float za = p.tpc_borders[k][2][0], zc = p.tpc_borders[k][2][1];
-      float zmin = fminf(fsub(zc, p.size_margin), fsub(za, p.size_margin));
-      float zmax = fmaxf(fadd(zc, p.size_margin), fadd(za, p.size_margin));
-      bool c = x >= fsub(p.tpc_borders[k][0][0], p.size_margin) && x <= fadd(p.tpc_borders[k][0][1], p.size_margin) &&
-               y >= fsub(p.tpc_borders[k][1][0], p.size_margin) && y <= fadd(p.tpc_borders[k][1][1], p.size_margin) &&
-               z >= zmin && z <= zmax;
-      if (c) { plane = k; inside = true; }
-    }
-    const float z_anode = p.tpc_borders[plane][2][0];
-    const float z_cath = p.tpc_borders[plane][2][1];
-    float dd = fadd(fabsf(fsub(z, z_anode)), 1e-6f);
-    float td = fdiv(dd, p.vdrift);
-    float life = expf(-fdiv(td, p.lifetime));
-    float q = fmul(fmul(ne, life), inside ? 1.0f : 0.0f);
-    float sl_cm = __fsqrt_rn(fmul(fmul(td, 2.0f), p.long_diff));
-    float sT = __fsqrt_rn(fmul(fmul(td, 2.0f), p.tran_diff));
+    const SegPhys ph = segment_physics(tr, cols, p);
+    const float x = ph.x, y = ph.y, z = ph.z, q = ph.q, td = ph.td, sl_cm = ph.sl_cm, sT = ph.sT;
+    const float recomb = ph.recomb, xi = ph.xi, cos2 = ph.cos2, z_anode = ph.z_anode, z_cath = ph.z_cath;
+    const int plane = ph.plane;
+    const bool inside = ph.inside;
     // sub-pixel bins and in-bin position
     float xr = fsub(x, p.tpc_borders[plane][0][0]);
     float yr = fsub(y, p.tpc_borders[plane][1][0]);
@@ -273,9 +215,10 @@ k_scan_final(const uint32_t* __restrict__ bitmap, int64_t n_words, const uint32_
 
 // unique_pixels = sort(pad(append(unique(main_pixels), -1), -1)) (sim_jax.py:717-721)
 __global__ void k_emit_unique(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wprefix, int64_t n_words,
-                              int pid_offset, int32_t npix, int32_t* __restrict__ unique_pixels, int32_t* __restrict__ counts) {
+                              int pid_offset, int32_t npix, int32_t extra, int32_t* __restrict__ unique_pixels,
+                              int32_t* __restrict__ counts) {
   const int n_unique = counts[0];
-  if (n_unique + 1 > npix) {
+  if (n_unique + extra > npix) {  // extra = 1: the -1 appended by simulate_wfs (sim_jax.py:718); 0 for the MC path (:363-366)
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(counts + 2, 1);
     return;
   }
@@ -329,13 +272,13 @@ int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* cou
   return LARND_OK;
 }
 
-int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t* unique_pixels,
+int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t extra, int32_t* unique_pixels,
                         int32_t* counts, cudaStream_t st) {
   (void)p;
   int64_t blocks = (ws.n_words + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  k_emit_unique<<<(unsigned)blocks, 256, 0, st>>>(ws.bitmap, ws.wprefix, ws.n_words, ws.pid_offset, npix_capacity,
+  k_emit_unique<<<(unsigned)blocks, 256, 0, st>>>(ws.bitmap, ws.wprefix, ws.n_words, ws.pid_offset, npix_capacity, extra,
                                                   unique_pixels, counts);
   LARND_LAUNCH_CHECK("k_emit_unique");
   return LARND_OK;

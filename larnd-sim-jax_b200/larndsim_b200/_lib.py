@@ -110,7 +110,7 @@ def _declare(lib):
     lib.larnd_fee_backward.argtypes = [vp, vp, vp, i32, PP, vp, i64, vp]
     if hasattr(lib, "larnd_mc_forward"):
         lib.larnd_mc_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, vp, vp]
-        lib.larnd_mc_backward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, i64, vp, vp]
+        lib.larnd_mc_backward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     for name in ("larnd_lut_create", "larnd_lut_forward", "larnd_lut_prepare", "larnd_lut_accumulate", "larnd_lut_backward",
                  "larnd_fee_forward", "larnd_fee_backward", "larnd_mc_forward", "larnd_mc_backward"):
         if hasattr(lib, name):

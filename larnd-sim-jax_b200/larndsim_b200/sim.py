@@ -392,3 +392,106 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
     pixel_z = get_hit_z(params, ticks.reshape(-1), plane.repeat_interleave(ticks.shape[1])).reshape(ticks.shape)
     out = parse_output(params, adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, unique_pixels.to(torch.int32))
     return out[:8]
+
+
+# ------------------------------------------------------------------------------------------ MC-current mode
+def mc_normals(n, rngseed, device):
+    """The (N,3) standard normals of generate_electrons (reference: detsim_jax.py:393).  NOT bit-compatible with
+    jax.random; pass ``rnd=`` to simulate_parametrized to inject specific draws."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(rngseed))
+    return torch.randn((n, 3), generator=gen, device=device, dtype=torch.float32)
+
+
+def mc_forward(params, tracks, fields, rnd, npix_capacity=None, n_events=None):
+    """prepare (drift + electron smearing + pixel ids) -> unique -> analytic current -> scatter.  Returns a LutState
+    (wfs_full includes the garbage column 0)."""
+    _check_cuda(tracks, "tracks")
+    tracks = tracks.contiguous()
+    rnd = rnd.to(tracks.device, torch.float32).contiguous()
+    lib = _lib.get_lib()
+    if not hasattr(lib, "larnd_mc_forward"):
+        raise _lib.LarndError("library was built without the MC-current kernels")
+    with torch.cuda.device(tracks.device):
+        pod = make_pod(params)
+        cols = make_columns(fields)
+        n = tracks.shape[0]
+        if n_events is None:
+            n_events = n_events_of(tracks, fields)
+        ws_bytes = lib.larnd_workspace_bytes(n, n_events, pod.n_tpc, pod.n_pixels_x, pod.n_pixels_y)
+        st = LutState()
+        st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=tracks.device)
+        st.counts = torch.zeros(4, dtype=torch.int32, device=tracks.device)
+        st.n, st.n_events, st.pod, st.lut, st.flags = n, n_events, pod, (cols, rnd), 0
+        if npix_capacity is None:
+            npix_capacity = _mc_count_unique(lib, tracks, n, cols, pod, rnd, n_events, st, ws_bytes)
+        st.npix = int(npix_capacity)
+        st.unique_pixels = torch.empty(st.npix, dtype=torch.int32, device=tracks.device)
+        st.wfs_full = torch.empty((st.npix, pod.n_ticks), dtype=torch.float32, device=tracks.device)
+        _lib.check(lib.larnd_mc_forward(_ptr(tracks), n, C.byref(cols), C.byref(pod), _ptr(rnd), n_events, st.npix,
+                                        _ptr(st.workspace), ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_full),
+                                        _ptr(st.counts), _stream()))
+    return st
+
+
+def _mc_count_unique(lib, tracks, n, cols, pod, rnd, n_events, st, ws_bytes):
+    """Exact number of distinct pixel ids -> the reference's pad_size(n_unique, 'unique_pixels') (sim_jax.py:363-364).
+    A throw-away forward with capacity 1 fills counts[0] (the kernels bail out on the capacity flag without touching
+    the 1-row dummy outputs); one 16-byte D2H read, the counterpart of jnp.unique's host sync."""
+    tmp_u = torch.empty(1, dtype=torch.int32, device=tracks.device)
+    tmp_w = torch.empty((1, pod.n_ticks), dtype=torch.float32, device=tracks.device)
+    rc = lib.larnd_mc_forward(_ptr(tracks), n, C.byref(cols), C.byref(pod), _ptr(rnd), n_events, 1, _ptr(st.workspace), ws_bytes,
+                              _ptr(tmp_u), _ptr(tmp_w), _ptr(st.counts), _stream())
+    _lib.check(rc)
+    cnt = st.counts.cpu()
+    if int(cnt[2]) & 2:
+        raise ValueError("eventID outside [-1, n_events) found in tracks")
+    return pad_size(max(int(cnt[0]), 1), "unique_pixels")
+
+
+def mc_backward(st, tracks, g_wfs):
+    lib = _lib.get_lib()
+    g = g_wfs.contiguous()
+    nt1 = st.pod.n_ticks - 1
+    cols, rnd = st.lut
+    grad = torch.zeros(_lib.NPARAMS, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(lib.larnd_mc_backward(_ptr(tracks), st.n, C.byref(cols), C.byref(st.pod), _ptr(rnd), st.n_events, st.npix,
+                                         _ptr(st.workspace), st.workspace.numel(), _ptr(st.counts),
+                                         C.c_void_p(g.data_ptr() - 4), nt1, _ptr(grad), _stream()))
+    return grad
+
+
+class _SimulateMcWfs(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, params, tracks, fields, names, rnd, npix_capacity, n_events):
+        st = mc_forward(params, tracks, fields, rnd, npix_capacity, n_events)
+        ctx.st, ctx.names, ctx.tracks = st, names, tracks
+        ctx.mark_non_differentiable(st.unique_pixels)
+        return st.wfs_full[:, 1:], st.unique_pixels
+
+    @staticmethod
+    def backward(ctx, g_wfs, _g):
+        grad_all = mc_backward(ctx.st, ctx.tracks, g_wfs)
+        idx = torch.tensor([_lib.PARAM_ORDER.index(n) for n in ctx.names], device=grad_all.device)
+        return (grad_all[idx],) + (None,) * 7
+
+
+def simulate_parametrized(params, tracks, fields, rngseed=0, rnd=None, npix_capacity=None, n_events=None):
+    """MC-current simulation: (adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, unique_pixels) per valid hit.
+    Reference: sim_jax.py:339-372 (requires number_pix_neighbors = 0 and mc_diff = True, the only configuration the
+    reference itself supports)."""
+    if not params.mc_diff:
+        raise ValueError("simulate_parametrized requires mc_diff=True (the reference's non-MC branch reads the never-set "
+                         "params.tran_diff_bin_edges)")
+    if rnd is None:
+        rnd = mc_normals(tracks.shape[0], rngseed, tracks.device)
+    leaves = params.grad_leaves()
+    if leaves and torch.is_grad_enabled():
+        names = tuple(n for n, _ in leaves)
+        theta = torch.stack([t.to(tracks.device, torch.float32) for _, t in leaves])
+        wfs, upix = _SimulateMcWfs.apply(theta, params, tracks, tuple(fields), names, rnd, npix_capacity, n_events)
+    else:
+        st = mc_forward(params, tracks, fields, rnd, npix_capacity, n_events)
+        wfs, upix = st.wfs_full[:, 1:], st.unique_pixels
+    return simulate_stochastic(params, wfs, upix, (rngseed or 0) + 1)
