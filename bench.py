@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native larnd-sim hot path (LUT mode), see DESIGN.md §Measurement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--segments S]
+
+One *step* = one pass of the hot path over one synthetic spill batch of the prepared_data shape
+(SURVEY.md §8d config 5): prepare -> unique/renumber -> LUT accumulate -> fused FEE/ADC (+ hit compaction).
+`value`     : forward segments/s with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`       : the same through the public API with the batch in pinned HOST memory: H2D copy of the tracks and
+              D2H read-back of the hit list inside the timed region.
+`fwd_grad`  : forward + loss + backward (FEE VJP -> accumulate VJP -> 15 parameter gradients, all-reduced over ranks).
+`roofline`  : dominant kernel (k_lut_accumulate), algorithmic HBM bytes / CUDA-event kernel time vs the measured peak.
+`cpu_baseline`: the numpy oracle (a port of the reference algorithm; JAX is not installable here) on host cores.
+--impl reference times that oracle port on all host cores (the reference itself needs jax, absent from the image).
+Multi-GPU: events are independent, so every rank simulates its own batch (weak scaling); the only collective is the
+16-float all-reduce of (loss, gradients) in the fwd+grad step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "larnd-sim-jax_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "segments/s fwd (LUT mode)"
+NEIGH, SIGLEN, PRECISION = 4, 100, 0.01
+GEOM = os.path.join(ROOT, "larnd-sim-jax_b200", "larndsim_b200", "data", "module0_geometry.json")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--segments", type=int, default=10_000_000, help="segments per GPU (weak scaling)")
+    ap.add_argument("--cpu-sample", type=int, default=12_000, help="segments of the workload timed on the CPU oracle")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-garbage", action="store_true", help="also report the variant that drops the garbage row")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_params(n_neigh=NEIGH, siglen=SIGLEN):
+    from oracle import consts as oc
+    return oc.params_from_geometry_json(GEOM).replace(number_pix_neighbors=n_neigh, signal_length=siglen,
+                                                      electron_sampling_resolution=PRECISION, RESET_NOISE_CHARGE=0,
+                                                      UNCORRELATED_NOISE_CHARGE=0, time_window=siglen)
+
+
+_G = {}  # large read-only arrays shared with forked workers (not pickled per job)
+
+
+def _oracle_worker(job):
+    """One shard of the CPU baseline: full oracle forward (simulate_wfs + simulate_stochastic) on a slice of segments."""
+    tracks, fields = job
+    bank, cum = _G["bank"], _G["cum"]
+    from oracle import larnd_oracle as lo
+    p = oracle_params()
+    ev = tracks[:, fields.index("eventID")]
+    tracks = tracks.copy()
+    tracks[:, fields.index("eventID")] = ev - ev.min()
+    wfs, uniq = lo.simulate_wfs(p, bank, tracks, fields, history={}, response_cum=cum)
+    out = lo.simulate_stochastic(p, wfs, uniq)
+    return len(out[0])
+
+
+def cpu_oracle_rate(tracks, bank32, fields, nproc, per_proc):
+    """segments/s of the oracle port over `nproc` processes each handling `per_proc` segments."""
+    from oracle import larnd_oracle as lo
+    if _G.get("bank") is not bank32:
+        _G["bank"], _G["cum"] = bank32, lo.response_cumsum(bank32)
+    jobs = [(tracks[i * per_proc:(i + 1) * per_proc], fields) for i in range(nproc)]
+    jobs = [j for j in jobs if len(j[0])]
+    nseg = sum(len(j[0]) for j in jobs)
+    t = time.time()
+    if len(jobs) == 1:
+        _oracle_worker(jobs[0])
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            pool.map(_oracle_worker, jobs)
+    return nseg / (time.time() - t), nseg
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from larndsim_b200 import synthetic
+    from oracle import consts as oc
+    cores = os.cpu_count() or 1
+    per_proc = 2500
+    tracks, _ = synthetic.synthetic_tracks(per_proc * cores, seed=1234, precision=PRECISION)
+    p = oracle_params()
+    bank32 = oc.build_response_template(synthetic.synthetic_response(), p, n_templates=32)
+    fields = synthetic.FIELDS
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, nseg = cpu_oracle_rate(tracks, bank32, fields, cores, per_proc)
+        if i >= args.warmup:
+            rates.append(r)
+    val = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * nseg / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic_spill (straight tracks chopped at 0.01 cm), LUT mode n=4 L=100, bounded sample of %d segments/step" % nseg,
+                   "number_pix_neighbors": NEIGH, "signal_length": SIGLEN},
+        "cpu_baseline": {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
+                         "sample": "%d segments/step, %d processes x %d segments, numpy oracle port of the reference algorithm "
+                                   "(the reference needs jax, not installable in this image)" % (nseg, cores, per_proc)},
+        "e2e": {"value": val, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import larndsim_b200 as lb
+    from larndsim_b200 import _lib, sim, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lb.build_library()
+    lib = lb.get_lib()
+
+    fields = synthetic.FIELDS
+    Params = lb.build_params_class([])
+    params = lb.load_geometry_json(Params, GEOM).replace(number_pix_neighbors=NEIGH, signal_length=SIGLEN,
+                                                          electron_sampling_resolution=PRECISION, RESET_NOISE_CHARGE=0,
+                                                          UNCORRELATED_NOISE_CHARGE=0, time_window=SIGLEN)
+    t_gen = time.time()
+    tracks_np, n_events = synthetic.synthetic_tracks(args.segments, seed=1234 + rank, precision=PRECISION)
+    nseg = tracks_np.shape[0]
+    tracks_host = torch.from_numpy(tracks_np).pin_memory()
+    tracks = tracks_host.to(dev, non_blocking=True)
+    resp = synthetic.synthetic_response()
+    from larndsim_b200.consts import build_response_template
+    bank = build_response_template(resp, params, device=dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+
+    # size the outputs once (the reference pads the pixel list per batch; the capacity mode needs no host sync per step)
+    st0 = sim.lut_forward(params, bank, tracks, fields, n_events=n_events)
+    n_unique = int(st0.counts[0].item())
+    npix = st0.npix
+    out = (st0.unique_pixels, st0.wfs_full)
+    pod = st0.pod
+    del st0
+
+    def fwd(flags=0, src=tracks):
+        st = sim.lut_forward(params, bank, src, fields, npix_capacity=npix, n_events=n_events, flags=flags, out=out)
+        fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True, pod=pod)
+        return st, fs
+
+    # target for the fit-style loss: the ADCs of a slightly different detector (lifetime -10 %)
+    st, fs = fwd()
+    p_tgt = params.replace(lifetime=params.lifetime * 0.9)
+    st_t = sim.lut_forward(p_tgt, bank, tracks, fields, npix_capacity=npix, n_events=n_events)
+    fs_t = sim.fee_forward(p_tgt, st_t.wfs_full[:, 1:], st_t.unique_pixels, None, compact=False, pod=pod)
+    adc_target = fs_t.adc.clone()
+    del st_t, fs_t
+
+    def fwd_grad():
+        st, fs = fwd(flags=0)
+        diff = (fs.adc - adc_target) * (st.unique_pixels >= 0).unsqueeze(1)  # only real pixels enter the loss (parse_output)
+        loss = (diff * diff).sum()
+        g_wfs = sim.fee_backward(fs, 2.0 * diff)
+        grad = sim.lut_backward(st, g_wfs, skip_garbage=True)  # rows with id < 0 produce no hits -> zero gradient
+        red = torch.cat([loss.reshape(1), grad])
+        if world > 1:
+            dist.all_reduce(red)
+        return red
+
+    hit_host = torch.empty((8, npix * pod.max_adc_values // 4 + 1024), dtype=torch.float32).pin_memory()
+    nv_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        src = tracks_host.to(dev, non_blocking=True)  # H2D of the batch (pinned)
+        st, fs = fwd(src=src)
+        nv_host.copy_(fs.n_valid, non_blocking=True)
+        hf, hi = fs.hits
+        cap = hit_host.shape[1]
+        hit_host[:6].copy_(hf[:, :cap], non_blocking=True)   # D2H of the compacted hit list (bounded by capacity)
+        hit_host[6:8].copy_(hi[:, :cap].view(torch.float32), non_blocking=True)
+        return fs
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_fwd, clocks = timed(fwd, args.steps, args.warmup, sampler)
+    ms_e2e, _ = timed(e2e_step, args.steps, max(1, args.warmup // 3))
+    ms_fg, _ = timed(fwd_grad, args.steps, max(1, args.warmup // 3))
+    ms_skip = None
+    if args.skip_garbage:
+        ms_skip, _ = timed(lambda: fwd(flags=1), args.steps, 1)
+        fwd()
+
+    # per-kernel device times of the dominant kernels, same launches as above
+    lib.larnd_profile_enable(1)
+    import ctypes as C
+    buf = (C.c_float * 4)()
+    kt = np.zeros((args.steps, 4))
+    for i in range(args.steps):
+        fwd_grad()
+        lib.larnd_profile_read(buf)
+        kt[i] = list(buf)
+    lib.larnd_profile_enable(0)
+    k_ms = kt.mean(axis=0)
+    n_valid = int(fs.n_valid.item())
+    total_seg = nseg * world
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nticks, L = pod.n_ticks, SIGLEN
+        # algorithmic (compulsory) HBM bytes of the forward path per segment, SURVEY.md §8d:
+        lut_window = 4 * L * (25 * 3 + (10 * NEIGH + 5) ** 2)
+        b_seg = 104 + 4.0 * (n_unique + 1) * nticks / nseg + lut_window / nseg
+        c_seg = (25 + (2 * NEIGH + 1) ** 2) * (2 * L + 2)
+        achieved = b_seg * nseg / (k_ms[1] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_seg / (ms_fwd * 1e-3), "unit": "segments/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_fwd, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic_spill: %d segments/GPU (straight tracks chopped at %.2f cm, %d events), LUT mode, "
+                                   "synthetic (45,45,1950) response x 100 templates" % (nseg, PRECISION, n_events),
+                       "number_pix_neighbors": NEIGH, "signal_length": SIGLEN, "n_unique_pixels": n_unique, "npix_padded": npix,
+                       "hits": n_valid, "l2": "inputs (%.0f MB tracks + %.0f MB waveforms) exceed the 126 MB L2" %
+                                              (nseg * 104 / 1e6, npix * nticks * 4 / 1e6),
+                       "garbage_row": "computed (reference-identical)"},
+            "clocks": clocks,
+            "e2e": {"value": total_seg / (ms_e2e * 1e-3), "unit": "segments/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(tracks_host.numel() * 4), "d2h_bytes_per_step": int(hit_host.numel() * 4 + 4)},
+            "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": total_seg / (ms_fg * 1e-3), "unit": "segments/s",
+                         "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none"},
+            "gpu_launches": int(args.steps * 9),
+            "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
+            "roofline": {"kernel": "k_lut_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_segment": b_seg,
+                         "note": "accumulate is bound by on-chip gather/FMA issue, not HBM (SURVEY §8d); contributions/s below",
+                         "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3)},
+            "setup_s": t_gen,
+        }
+        if ms_skip is not None:
+            line["value_skip_garbage_row"] = total_seg / (ms_skip * 1e-3)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import consts as oc
+            sample = tracks_np[: args.cpu_sample]
+            bank32 = bank[:32].cpu().numpy()
+            _ = oc
+            rate, ns = cpu_oracle_rate(sample, bank32, fields, 1, len(sample))
+            line["cpu_baseline"] = {"value": rate, "unit": "segments/s", "cores": 1, "kind": "port",
+                                    "sample": "first %d segments of the same workload, numpy oracle port, 1 process" % ns}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

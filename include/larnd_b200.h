@@ -184,6 +184,15 @@ int larnd_mc_backward(const float* tracks_d, int64_t n_segments, const larnd_col
                       void* workspace_d, size_t workspace_bytes, const int32_t* counts_d, const float* g_wfs_d,
                       int64_t g_row_stride, float* grad_params_d, void* stream);
 
+/* Optional device-side timing of the dominant kernels (used by bench.py for the roofline numbers): when
+ * enabled, CUDA events are recorded on the launching stream immediately around
+ *   slot 0: k_prepare   slot 1: k_lut_accumulate   slot 2: k_lut_backward   slot 3: k_fee_forward
+ * larnd_profile_read synchronises on those events and returns the elapsed milliseconds of the LAST launch of
+ * each kernel (-1 if it has not run since larnd_profile_enable(1)). */
+#define LARND_PROF_SLOTS 4
+int larnd_profile_enable(int on);
+int larnd_profile_read(float* ms_out /* [LARND_PROF_SLOTS] */);
+
 /* Layout of the per-segment records inside the workspace (for tests / debugging): field f of segment s
  * is ((float*)workspace_d)[f * n_segments + s]; integer fields are bit-cast int32. */
 enum {

@@ -304,6 +304,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.skip_garbage = flags & 1;
   const int64_t chunks = (n + S - 1) / S;
   const int need = lut->L + 2 + 32;  // window + room for the tick drift inside a chunk
+  prof_begin(1, st);
   if (need <= 32 * 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
   else if (need <= 32 * 6) k_lut_accumulate<6><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
   else if (need <= 32 * 8) k_lut_accumulate<8><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
@@ -313,6 +314,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
     larnd_set_error("signal_length %d too large for the register window (max %d)", lut->L, 32 * 16 - 34);
     return LARND_E_ARG;
   }
+  prof_end(1, st);
   LARND_LAUNCH_CHECK("k_lut_accumulate");
   return LARND_OK;
 }

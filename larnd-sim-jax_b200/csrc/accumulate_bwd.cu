@@ -325,7 +325,9 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   A.partials = ws.partials;
   A.skip_garbage = flags & 1;
   const int64_t chunks = (n + S - 1) / S;
+  prof_begin(2, st);
   k_lut_backward<<<(unsigned)chunks, BWD_THREADS, 0, st>>>(A, p);
+  prof_end(2, st);
   LARND_LAUNCH_CHECK("k_lut_backward");
   k_reduce_partials<<<LARND_NPARAMS, 256, 0, st>>>(ws.partials, chunks, grad_params);
   LARND_LAUNCH_CHECK("k_reduce_partials");

@@ -19,6 +19,35 @@ int larnd_check_cuda(cudaError_t e, const char* what) {
   return LARND_E_CUDA;
 }
 
+bool g_prof_on = false;
+ProfSlot g_prof[LARND_PROF_SLOTS];
+
+extern "C" int larnd_profile_enable(int on) {
+  static bool created = false;
+  if (on && !created) {
+    for (int i = 0; i < LARND_PROF_SLOTS; ++i) {
+      LARND_CUDA(cudaEventCreate(&g_prof[i].start));
+      LARND_CUDA(cudaEventCreate(&g_prof[i].stop));
+    }
+    created = true;
+  }
+  for (int i = 0; i < LARND_PROF_SLOTS; ++i) g_prof[i].used = false;
+  g_prof_on = on != 0;
+  return LARND_OK;
+}
+
+extern "C" int larnd_profile_read(float* ms_out) {
+  if (!ms_out) { larnd_set_error("larnd_profile_read: null argument"); return LARND_E_ARG; }
+  for (int i = 0; i < LARND_PROF_SLOTS; ++i) {
+    ms_out[i] = -1.0f;
+    if (g_prof_on && g_prof[i].used) {
+      LARND_CUDA(cudaEventSynchronize(g_prof[i].stop));
+      LARND_CUDA(cudaEventElapsedTime(&ms_out[i], g_prof[i].start, g_prof[i].stop));
+    }
+  }
+  return LARND_OK;
+}
+
 extern "C" const char* larnd_last_error(void) { return g_err; }
 extern "C" int larnd_abi_version(void) { return LARND_ABI_VERSION; }
 

@@ -287,7 +287,9 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
     attr_set = true;
   }
   if (smem > 200 * 1024) { larnd_set_error("larnd_fee_forward: n_ticks too large for shared memory"); return LARND_E_ARG; }
+  prof_begin(3, st);
   k_fee_forward<<<(npix + FEE_WARPS - 1) / FEE_WARPS, FEE_THREADS, smem, st>>>(F, *params);
+  prof_end(3, st);
   LARND_LAUNCH_CHECK("k_fee_forward");
   k_scan_counts<<<1, 1024, 0, st>>>(F.row_counts, npix, offsets, n_valid_d);
   LARND_LAUNCH_CHECK("k_scan_counts");

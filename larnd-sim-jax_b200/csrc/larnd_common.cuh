@@ -48,6 +48,13 @@ int larnd_check_cuda(cudaError_t e, const char* what);
   } while (0)
 #define LARND_LAUNCH_CHECK(name) LARND_CUDA(cudaGetLastError())
 
+// optional event timing around the dominant kernels (larnd_profile_enable / larnd_profile_read)
+struct ProfSlot { cudaEvent_t start, stop; bool used; };
+extern bool g_prof_on;
+extern ProfSlot g_prof[LARND_PROF_SLOTS];
+inline void prof_begin(int slot, cudaStream_t st) { if (g_prof_on) cudaEventRecord(g_prof[slot].start, st); }
+inline void prof_end(int slot, cudaStream_t st) { if (g_prof_on) { cudaEventRecord(g_prof[slot].stop, st); g_prof[slot].used = true; } }
+
 // ---- device helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ int floordiv_i(int a, int b) {  // python-style floor division, b > 0
   int q = a / b;

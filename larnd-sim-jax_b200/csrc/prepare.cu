@@ -254,8 +254,10 @@ int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& 
   const int stride = cols.ncols | 1;
   size_t smem = (size_t)PREP_THREADS * stride * sizeof(float);
   int64_t blocks = (n + PREP_THREADS - 1) / PREP_THREADS;
+  prof_begin(0, st);
   k_prepare<<<(unsigned)blocks, PREP_THREADS, smem, st>>>(tracks, n, cols, p, lut ? lut->nt : 0, ws.rec, ws.bitmap,
                                                          ws.n_words, ws.pid_offset, counts);
+  prof_end(0, st);
   LARND_LAUNCH_CHECK("k_prepare");
   return LARND_OK;
 }

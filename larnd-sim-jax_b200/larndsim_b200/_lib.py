@@ -105,6 +105,10 @@ def _declare(lib):
     lib.larnd_lut_accumulate.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp]
     lib.larnd_lut_backward.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     lib.larnd_fee_forward.argtypes = [vp, i64, vp, i32, PP, vp] + [vp] * 16 + [vp, sz, vp]
+    lib.larnd_profile_enable.argtypes = [C.c_int]
+    lib.larnd_profile_enable.restype = C.c_int
+    lib.larnd_profile_read.argtypes = [C.POINTER(C.c_float)]
+    lib.larnd_profile_read.restype = C.c_int
     lib.larnd_fee_scratch_bytes.argtypes = [i32]
     lib.larnd_fee_scratch_bytes.restype = sz
     lib.larnd_fee_backward.argtypes = [vp, vp, vp, i32, PP, vp, i64, vp]

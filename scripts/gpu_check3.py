@@ -8,32 +8,11 @@ import larndsim_b200 as lb
 from larndsim_b200 import sim, _lib
 lb.build_library()
 dev='cuda'
-kw=dict(number_pix_neighbors=2, signal_length=150)
-op=cm.oracle_params(**kw); pp=cm.product_params(**kw)
-bank=cm.synthetic_bank(32,25,25,1950)
 tr=cm.small_batch(400, ifile=0, ibatch=1, pad=0, precision=0.01)
-print('tracks',tr.shape)
-# reference forward (f64) to fix the pixel list
-wfs64, uniq, d, full64 = lo.simulate_wfs(op, bank, tr, cm.FIELDS, dt=np.float64, history={}, return_aux=True)
-Npix=len(uniq)
+trd=torch.as_tensor(tr,device=dev)
 rng=np.random.default_rng(5)
 t=np.arange(2000)
-G=(rng.uniform(0.5,1.5,(Npix,1))*(1+0.5*np.sin(t[None,:]/37.0+rng.uniform(0,6,(Npix,1))))).astype(np.float32)
-def L_oracle(p):
-    w,u=lo.simulate_wfs(p, bank, tr, cm.FIELDS, dt=np.float64, pad_to=Npix)
-    assert np.array_equal(u,uniq)
-    return float((w*G.astype(np.float64)).sum())
-st=sim.lut_forward(pp, torch.as_tensor(bank,device=dev), torch.as_tensor(tr,device=dev), cm.FIELDS, npix_capacity=Npix)
-w32=st.wfs_full[:,1:].cpu().numpy()
-print('fwd relerr vs f64', np.abs(w32-wfs64).max()/np.abs(wfs64).max())
-grad=sim.lut_backward(st, torch.as_tensor(G,device=dev)).cpu().numpy()
 names=_lib.PARAM_ORDER
-steps=dict(Ab=1e-6,kb=1e-7,eField=1e-7,lifetime=1e-2,long_diff=1e-11,tran_diff=1e-11,shift_x=1e-6,shift_y=1e-6,shift_z=1e-6,lArDensity=1e-6,MeVToElectrons=1e-1)
-for nme,h in steps.items():
-    base=getattr(op,nme)
-    fd=(L_oracle(op.replace(**{nme:base+h}))-L_oracle(op.replace(**{nme:base-h})))/(2*h)
-    g=grad[names.index(nme)]
-    print('LUT grad %-16s kernel % .6e  fd % .6e  rel %.2e'%(nme,g,fd,abs(g-fd)/(abs(fd)+1e-30)))
 # ---- MC mode
 kwm=dict(number_pix_neighbors=0, signal_length=150, mc_diff=True)
 opm=cm.oracle_params(**kwm); ppm=cm.product_params(**kwm)

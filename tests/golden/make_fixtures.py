@@ -28,6 +28,8 @@ def main():
         os.path.join(REF, "src/larndsim/detector_properties/module0.yaml"),
         os.path.join(REF, "src/larndsim/pixel_layouts/multi_tile_layout-2.4.16_v4.yaml"))
     consts.save_geometry_json(p, os.path.join(HERE, "module0_geometry.json"))
+    # the package ships the same derived geometry for bench.py / smoke() (no YAML on the GPU box)
+    consts.save_geometry_json(p, os.path.join(HERE, "..", "..", "larnd-sim-jax_b200", "larndsim_b200", "data", "module0_geometry.json"))
     for i in range(5):
         seg = H5Lite(os.path.join(REF, "prepared_data/input_%d.h5" % i)).read("/segments")
         np.savez_compressed(os.path.join(HERE, "segments_input_%d.npz" % i), segments=seg)
