@@ -94,6 +94,7 @@ typedef struct larnd_params {
   /* derivative helpers computed on the host in double precision */
   float dvdrift_dEfield;  /* d get_vdrift / d eField */
   float eField, lArDensity, R_param;
+  float ts_vdrift;        /* float32(t_sampling) * float32(vdrift): XLA folds the two scalars of get_hit_z (detsim_jax.py:318) */
 } larnd_params_t;
 
 typedef struct larnd_lut larnd_lut_t; /* opaque: compacted response rows + cumulative tables on the device */

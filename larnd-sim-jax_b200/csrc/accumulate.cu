@@ -41,12 +41,32 @@ struct AccArgs {
   int skip_garbage;
 };
 
+constexpr int KP = 16;           // tick positions per run (impulse train length)
+constexpr int SPAN_MAX = KP - 2;  // max (T0max - T0min) inside a run
+
+// A *run* = consecutive segments that share (event, plane, sub-pixel bin, template index) and whose start ticks lie
+// within SPAN_MAX of each other.  They read the same response rows for every unit, so their deposits are merged
+// into an impulse train over tick positions before the response row is applied once per position:
+//   h[m]  = sum q*f at T0 = tmin+m  +  sum q*(1-f) at T0 = tmin+m-1            (window part, sim_jax.py:190-194)
+//   moments per T0 position for the boundary correction (sim_jax.py:236-247), which is bilinear in (1-f, f):
+//   A1 = sum q(1-f), A2 = sum q(1-f)^2, A3 = sum q f(1-f), B1 = sum q f, B3 = sum q f^2
+struct RunInfo {
+  int start, len, tmin, span;
+  int ep, pxy;      // event*ntpc+plane, main pixel (x | y << 16)
+  int bx, by;       // sub-pixel bin of the run
+  int idx;          // longitudinal-diffusion template index
+  int fast;         // whole window inside the readout (no garbage-tick handling needed)
+};
+
 struct ChunkSmem {
   float4 seg[S];   // q, frac, T0 (int bits), bxm | bym << 8
   int2 key[S];     // ep, (mpx & 0xffff) | (mpy << 16)
   float a[S], b[S], c[S];
   int idx[S], bx[S], by[S];
   float wx[LARND_NB_TRAN_BINS][S], wy[LARND_NB_TRAN_BINS][S];
+  RunInfo run[S];
+  float rh[S][KP], rA1[S][KP], rA2[S][KP], rA3[S][KP], rB1[S][KP], rB3[S][KP];  // neighbour impulse train + moments
+  int nruns;
   int next_unit;
 };
 
@@ -144,15 +164,64 @@ __device__ __forceinline__ float boundary_delta(const float* crow, int ct, int n
   return cl - (ca * (1.0f - f) + cb * f);
 }
 
+// Applies one impulse train to the register window: for every tick position j of the run,
+//   acc[col] += h_j * Rblend[col - (tmin + j)]   for col - (tmin+j) in [0, L)
+//   acc[col] += E_j                              for col == tmin + j - 1   (merged boundary corrections)
+// Lane j holds h[NR][j] and E_j; they are broadcast with shuffles.  Only valid for "fast" runs (all ticks inside
+// the readout window).
+template <int NS, int NR>
+__device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmin, int npos, const float (&h)[NR], float E,
+                                            const float* const (&rows)[NR], int L, int lane) {
+  for (int j = 0; j < npos; ++j) {
+    float hj[NR];
+    bool any = false;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      hj[r] = __shfl_sync(0xffffffffu, h[r], j);
+      any |= (hj[r] != 0.0f);
+    }
+    const float Ej = __shfl_sync(0xffffffffu, E, j);
+    if (!any && Ej == 0.0f) continue;  // warp-uniform
+    const int xb0 = tbase - (tmin + j);  // x of lane 0, slot 0
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int xs = xb0 + 32 * s;
+      if (xs + 31 < -1 || xs >= L) continue;  // warp-uniform
+      const int x = xs + lane;
+      const int xc = min(max(x, -2), L);
+      float v = hj[0] * __ldg(rows[0] + xc + 2);
+#pragma unroll
+      for (int r = 1; r < NR; ++r) v = fmaf(hj[r], __ldg(rows[r] + xc + 2), v);
+      acc[s] += (x == -1) ? Ej : v;
+    }
+  }
+}
+
+// merged boundary correction of a run for one response bin: lane m <-> T0 = tmin + m
+__device__ __forceinline__ float run_correction(const float* crow, int tmin, int nt, int L, float A1, float A2, float A3,
+                                                float B1, float B3, int lane) {
+  int ct = nt - L - (tmin + lane);
+  ct = max(0, min(ct, nt - 1));
+  const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1)), Cl = __ldg(crow + nt - L);
+  const float e1 = Cl * A1 - Ca * A2 - Cb * A3;  // lands on tick T0      (weight 1-f)
+  const float e0 = Cl * B1 - Ca * A3 - Cb * B3;  // lands on tick T0 - 1  (weight f)
+  // impulse position j covers tick tmin + j - 1:  E_j = e0_j + e1_{j-1}
+  float e1_up = __shfl_up_sync(0xffffffffu, e1, 1);
+  if (lane == 0) e1_up = 0.0f;
+  return e0 + e1_up;
+}
+
 template <int NS>
 __global__ void __launch_bounds__(ACC_THREADS)
 k_lut_accumulate(const __grid_constant__ AccArgs A) {
-  __shared__ ChunkSmem sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(smem_raw);
   if (A.counts[2] != 0) return;  // capacity overflow / bad event ids flagged upstream
   const int lane = threadIdx.x & 31;
   const int64_t s_base = (int64_t)blockIdx.x * S;
   const int ns = (int)min((int64_t)S, A.n - s_base);
   const int nb = A.nb;
+  const int L = A.L;
   // ---- stage the chunk's segment records --------------------------------------------------------------
   for (int t = threadIdx.x; t < ns; t += ACC_THREADS) {
     const int64_t s = s_base + t;
@@ -177,14 +246,58 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
       sm.wy[k][t] = rec[(int64_t)(LARND_F_WY0 + k) * n + s];
     }
   }
-  if (threadIdx.x == 0) sm.next_unit = 0;
+  __syncthreads();
+  // ---- cut the chunk into runs (serial, ~ns steps; negligible next to the accumulate work) ------------------
+  if (threadIdx.x == 0) {
+    int nr = 0;
+    int cur = -1, tmin = 0, tmax = 0;
+    for (int t = 0; t < ns; ++t) {
+      const int T0 = __float_as_int(sm.seg[t].z);
+      bool fresh = cur < 0;
+      if (!fresh) {
+        const int t0s = sm.run[cur].start;
+        fresh = sm.key[t].x != sm.key[t0s].x || sm.bx[t] != sm.bx[t0s] || sm.by[t] != sm.by[t0s] || sm.idx[t] != sm.idx[t0s] ||
+                max(tmax, T0) - min(tmin, T0) > SPAN_MAX;
+      }
+      if (fresh) {
+        if (cur >= 0) { sm.run[cur].len = t - sm.run[cur].start; sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
+        cur = nr++;
+        sm.run[cur].start = t;
+        tmin = tmax = T0;
+      } else {
+        tmin = min(tmin, T0);
+        tmax = max(tmax, T0);
+      }
+    }
+    if (cur >= 0) { sm.run[cur].len = ns - sm.run[cur].start; sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
+    sm.nruns = nr;
+    sm.next_unit = 0;
+  }
+  __syncthreads();
+  const int nruns = sm.nruns;
+  // ---- per-run neighbour impulse train and correction moments (thread per run) ------------------------------
+  for (int r = threadIdx.x; r < nruns; r += ACC_THREADS) {
+    RunInfo& R = sm.run[r];
+    const int t0s = R.start;
+    R.ep = sm.key[t0s].x; R.pxy = sm.key[t0s].y; R.bx = sm.bx[t0s]; R.by = sm.by[t0s]; R.idx = sm.idx[t0s];
+    R.fast = (R.tmin >= 2) && (R.tmin + R.span + L <= A.nticks - 1);
+    for (int k = 0; k < KP; ++k) { sm.rh[r][k] = 0.f; sm.rA1[r][k] = 0.f; sm.rA2[r][k] = 0.f; sm.rA3[r][k] = 0.f; sm.rB1[r][k] = 0.f; sm.rB3[r][k] = 0.f; }
+    for (int t = t0s; t < t0s + R.len; ++t) {
+      const float4 sg = sm.seg[t];
+      const float q = sg.x, f = sg.y, omf = 1.0f - f;
+      const int m = __float_as_int(sg.z) - R.tmin;
+      sm.rh[r][m] += q * f;
+      sm.rh[r][m + 1] += q * omf;
+      sm.rA1[r][m] += q * omf; sm.rA2[r][m] += q * omf * omf; sm.rA3[r][m] += q * f * omf;
+      sm.rB1[r][m] += q * f;   sm.rB3[r][m] += q * f * f;
+    }
+  }
   __syncthreads();
 
   RowLookup lk = A.lk;
   lk.n_unique = A.counts[0];
   lk.n_neg = A.counts[1];
   const int n_units = 25 + A.P * A.P;
-  const int slack = (32 * NS - (A.L + 2)) / 2;
   float acc[NS];
 #pragma unroll
   for (int j = 0; j < NS; ++j) acc[j] = 0.0f;
@@ -203,17 +316,16 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
       const int u = unit - 25;
       const int dx = u / A.P - A.n_neigh, dy = u % A.P - A.n_neigh;
       const bool centre = (dx == 0 && dy == 0);
-      for (int t = 0; t < ns; ++t) {
-        const float4 sg = sm.seg[t];
-        const int2 key = sm.key[t];
-        if (key.x != cur_k0 || key.y != cur_k1) {
-          cur_k0 = key.x; cur_k1 = key.y;
-          const int mpx = (int)(short)(key.y & 0xffff), mpy = key.y >> 16;
+      for (int r = 0; r < nruns; ++r) {
+        const RunInfo R = sm.run[r];
+        if (R.ep != cur_k0 || R.pxy != cur_k1) {
+          cur_k0 = R.ep; cur_k1 = R.pxy;
+          const int mpx = (int)(short)(R.pxy & 0xffff), mpy = R.pxy >> 16;
           int row;
           bool garbage;
           if (centre) { row = 0; garbage = true; }  // centre id is overwritten with -999 -> never matches -> row 0
           else {
-            int pid = pixel2id_dev(mpx + dx, mpy + dy, key.x, A.nxp, A.nyp);
+            int pid = pixel2id_dev(mpx + dx, mpy + dy, R.ep, A.nxp, A.nyp);
             row = lookup_row(lk, pid);
             garbage = row < 0 || pid < 0;
             if (row < 0) row = 0;  // sim_jax.py:724-725
@@ -222,60 +334,100 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
           if (row != cur_row) { flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane); cur_row = row; }
         }
         if (cur_row < 0) continue;
-        const float q = sg.x, f = sg.y;
-        if (q == 0.0f) continue;
-        const int T0 = __float_as_int(sg.z);
-        if (T0 - 1 < tbase || T0 + A.L >= tbase + 32 * NS) {
+        const int span = R.span;
+        if (R.tmin - 1 < tbase || R.tmin + span + L >= tbase + 32 * NS) {
           flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
-          tbase = T0 - 1 - slack;
+          tbase = R.tmin - 1 - (32 * NS - (L + 2 + span)) / 2;
         }
-        const int bm = __float_as_int(sg.w);
-        const int vx = 2 * (bm & 0xff) - A.half2 - 2 * nb * dx;
-        const int vy = 2 * (bm >> 8) - A.half2 - 2 * nb * dy;
-        const int ci = abs(vx) >> 1, cj = abs(vy) >> 1;
-        const int bin = ci * A.ny_lut + cj;
+        const int mpx_ = floordiv_i(R.bx, nb), mpy_ = floordiv_i(R.by, nb);
+        const int vx = 2 * (R.bx - mpx_ * nb) - A.half2 - 2 * nb * dx;
+        const int vy = 2 * (R.by - mpy_ * nb) - A.half2 - 2 * nb * dy;
+        const int bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
         const float* const rows[1] = {A.r0 + (int64_t)bin * A.Lp};
-        const float cf[1] = {1.0f};
-        const float D = boundary_delta(A.c0 + (int64_t)bin * A.nt, A.nt - A.L - T0, A.nt, A.L, f, lane);
-        add_contribution<NS, 1>(acc, g0, g0_used, tbase, T0, q * f, q * (1.0f - f), D, rows, cf, A, lane);
+        const float* crow = A.c0 + (int64_t)bin * A.nt;
+        if (R.fast) {
+          const int kk = min(lane, KP - 1);
+          const float hl = lane < KP ? sm.rh[r][kk] : 0.f;
+          float E = run_correction(crow, R.tmin, A.nt, L, sm.rA1[r][kk], sm.rA2[r][kk], sm.rA3[r][kk], sm.rB1[r][kk], sm.rB3[r][kk], lane);
+          if (lane > span + 1) E = 0.f;
+          const float h[1] = {hl};
+          apply_train<NS, 1>(acc, tbase, R.tmin, span + 2, h, E, rows, L, lane);
+        } else {
+          // run touches the ends of the readout window: per-segment path with garbage-tick handling
+          const float cf[1] = {1.0f};
+          for (int t = R.start; t < R.start + R.len; ++t) {
+            const float4 sg = sm.seg[t];
+            const float q = sg.x, f = sg.y;
+            if (q == 0.0f) continue;
+            const int T0 = __float_as_int(sg.z);
+            const float D = boundary_delta(crow, A.nt - L - T0, A.nt, L, f, lane);
+            add_contribution<NS, 1>(acc, g0, g0_used, tbase, T0, q * f, q * (1.0f - f), D, rows, cf, A, lane);
+          }
+        }
       }
     } else {
       // ---------------- main unit: diffusion bin (i, j), 3-template blend -----------------------------
       const int bi = unit / LARND_NB_TRAN_BINS, bj = unit % LARND_NB_TRAN_BINS;
       const int sym = (LARND_NB_TRAN_BINS - 1) / 2;
-      int cix = 0, ciy = 0;
-      for (int t = 0; t < ns; ++t) {
-        const float4 sg = sm.seg[t];
-        const int ep = sm.key[t].x;
-        const int bxx = sm.bx[t] + bi - sym, byy = sm.by[t] + bj - sym;
+      for (int r = 0; r < nruns; ++r) {
+        const RunInfo R = sm.run[r];
+        const int bxx = R.bx + bi - sym, byy = R.by + bj - sym;
         const int px = floordiv_i(bxx, nb), py = floordiv_i(byy, nb);
         const int k1 = (px & 0xffff) | (py << 16);
-        if (ep != cur_k0 || k1 != cur_k1) {
-          cur_k0 = ep; cur_k1 = k1;
-          int pid = pixel2id_dev(px, py, ep, A.nxp, A.nyp);
+        if (R.ep != cur_k0 || k1 != cur_k1) {
+          cur_k0 = R.ep; cur_k1 = k1;
+          int pid = pixel2id_dev(px, py, R.ep, A.nxp, A.nyp);
           int row = lookup_row(lk, pid);  // not in the list -> dropped (sim_jax.py:152-154)
           if (A.skip_garbage && pid < 0) row = -1;
           if (row != cur_row) { flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane); cur_row = row; }
         }
         if (cur_row < 0) continue;
-        const float q = sg.x, f = sg.y;
-        const float qb = (sm.wx[bi][t] * sm.wy[bj][t]) * q;
-        if (qb == 0.0f) continue;
-        const int T0 = __float_as_int(sg.z);
-        if (T0 - 1 < tbase || T0 + A.L >= tbase + 32 * NS) {
+        const int span = R.span;
+        if (R.tmin - 1 < tbase || R.tmin + span + L >= tbase + 32 * NS) {
           flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
-          tbase = T0 - 1 - slack;
+          tbase = R.tmin - 1 - (32 * NS - (L + 2 + span)) / 2;
         }
-        cix = abs(2 * (bxx - px * nb) - A.half2) >> 1;
-        ciy = abs(2 * (byy - py * nb) - A.half2) >> 1;
-        const int idx = sm.idx[t];
+        const int cix = abs(2 * (bxx - px * nb) - A.half2) >> 1;
+        const int ciy = abs(2 * (byy - py * nb) - A.half2) >> 1;
+        const int idx = R.idx;
         const int bin = cix * 5 + ciy;
         const float* const rows[3] = {A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp,
                                       A.rm + (int64_t)(idx * 25 + bin) * A.Lp,
                                       A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp};
-        const float cf[3] = {sm.a[t], sm.b[t], sm.c[t]};
-        const float D = boundary_delta(A.cm + (int64_t)(idx * 25 + bin) * A.nt, A.nt - A.L - T0, A.nt, A.L, f, lane);
-        add_contribution<NS, 3>(acc, g0, g0_used, tbase, T0, qb * f, qb * (1.0f - f), D, rows, cf, A, lane);
+        const float* crow = A.cm + (int64_t)(idx * 25 + bin) * A.nt;
+        if (R.fast) {
+          // build this bin's impulse trains (one per template) and correction moments: lane <-> tick position
+          float h[3] = {0.f, 0.f, 0.f};
+          float A1 = 0.f, A2 = 0.f, A3 = 0.f, B1 = 0.f, B3 = 0.f;
+          for (int t = R.start; t < R.start + R.len; ++t) {
+            const float4 sg = sm.seg[t];
+            const float f = sg.y, omf = 1.0f - f;
+            const float w = (sm.wx[bi][t] * sm.wy[bj][t]) * sg.x;
+            const int m = __float_as_int(sg.z) - R.tmin;
+            const float wf = w * f, wo = w * omf;
+            const float ca = sm.a[t], cb = sm.b[t], cc = sm.c[t];
+            if (lane == m) {
+              h[0] = fmaf(wf, ca, h[0]); h[1] = fmaf(wf, cb, h[1]); h[2] = fmaf(wf, cc, h[2]);
+              A1 += wo; A2 = fmaf(wo, omf, A2); A3 = fmaf(wf, omf, A3); B1 += wf; B3 = fmaf(wf, f, B3);
+            } else if (lane == m + 1) {
+              h[0] = fmaf(wo, ca, h[0]); h[1] = fmaf(wo, cb, h[1]); h[2] = fmaf(wo, cc, h[2]);
+            }
+          }
+          float E = run_correction(crow, R.tmin, A.nt, L, A1, A2, A3, B1, B3, lane);
+          if (lane > span + 1) E = 0.f;
+          apply_train<NS, 3>(acc, tbase, R.tmin, span + 2, h, E, rows, L, lane);
+        } else {
+          for (int t = R.start; t < R.start + R.len; ++t) {
+            const float4 sg = sm.seg[t];
+            const float q = sg.x, f = sg.y;
+            const float qb = (sm.wx[bi][t] * sm.wy[bj][t]) * q;
+            if (qb == 0.0f) continue;
+            const int T0 = __float_as_int(sg.z);
+            const float cf[3] = {sm.a[t], sm.b[t], sm.c[t]};
+            const float D = boundary_delta(crow, A.nt - L - T0, A.nt, L, f, lane);
+            add_contribution<NS, 3>(acc, g0, g0_used, tbase, T0, qb * f, qb * (1.0f - f), D, rows, cf, A, lane);
+          }
+        }
       }
     }
     flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
@@ -303,13 +455,23 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.wfs = wfs;
   A.skip_garbage = flags & 1;
   const int64_t chunks = (n + S - 1) / S;
-  const int need = lut->L + 2 + 32;  // window + room for the tick drift inside a chunk
+  const int need = lut->L + 2 + SPAN_MAX + 32;  // run window + room for the tick drift between runs of a chunk
+  const size_t smem = sizeof(ChunkSmem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
   prof_begin(1, st);
-  if (need <= 32 * 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
-  else if (need <= 32 * 6) k_lut_accumulate<6><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
-  else if (need <= 32 * 8) k_lut_accumulate<8><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
-  else if (need <= 32 * 12) k_lut_accumulate<12><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
-  else if (need <= 32 * 16) k_lut_accumulate<16><<<(unsigned)chunks, ACC_THREADS, 0, st>>>(A);
+  if (need <= 32 * 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (need <= 32 * 6) k_lut_accumulate<6><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (need <= 32 * 8) k_lut_accumulate<8><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (need <= 32 * 12) k_lut_accumulate<12><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (need <= 32 * 16) k_lut_accumulate<16><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
   else {
     larnd_set_error("signal_length %d too large for the register window (max %d)", lut->L, 32 * 16 - 34);
     return LARND_E_ARG;

@@ -110,7 +110,8 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
     const bool sloped = (inner > 0.0f) && (dig < p.adc_counts);
     dig = fminf(dig, p.adc_counts);
     const float hp = (ic < (float)(Nt - 3)) ? 1.0f : 0.0f;
-    const float pz = __fadd_rn(z_anode, __fmul_rn(__fmul_rn(__fmul_rn(ic, p.t_sampling), p.vdrift), sgn));
+    // z_anode + ticks * (t_sampling * v) * sign: XLA folds the two scalars (pinned by the goldens' pix_z)
+    const float pz = __fadd_rn(z_anode, __fmul_rn(__fmul_rn(ic, p.ts_vdrift), sgn));
     if (!cond) hit_mask |= 1u << it;
     if (sub > 0.0f) spos_mask |= 1u << it;
     if (sloped && !cond) slope_mask |= 1u << it;
@@ -123,8 +124,9 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
     }
   }
   if (lane == 0) {
-    F.pixel_x[row] = __fadd_rn(__fadd_rn(__fmul_rn((float)xp, p.pixel_pitch), p.tpc_borders[plane][0][0]), p.half_pitch);
-    F.pixel_y[row] = __fadd_rn(__fadd_rn(__fmul_rn((float)yp, p.pixel_pitch), p.tpc_borders[plane][1][0]), p.half_pitch);
+    // fma(pitch_index, pitch, border) + pitch/2: XLA:CPU contracts the multiply-add (pinned by the goldens' pix_x/pix_y)
+    F.pixel_x[row] = __fadd_rn(__fmaf_rn((float)xp, p.pixel_pitch, p.tpc_borders[plane][0][0]), p.half_pitch);
+    F.pixel_y[row] = __fadd_rn(__fmaf_rn((float)yp, p.pixel_pitch, p.tpc_borders[plane][1][0]), p.half_pitch);
     F.event[row] = ev;
     F.row_counts[row] = n_valid;
     if (F.saved) {

@@ -64,8 +64,8 @@ k_mc_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant_
     const int yp = q1 - floordiv_i(q1, ny) * ny;
     const int q2 = floordiv_i(pid, nx * ny);
     const int pl = q2 - floordiv_i(q2, p.n_tpc) * p.n_tpc;
-    const float xpix = fadd(fadd(fmul((float)xp, p.pixel_pitch), p.tpc_borders[pl][0][0]), p.half_pitch);
-    const float ypix = fadd(fadd(fmul((float)yp, p.pixel_pitch), p.tpc_borders[pl][1][0]), p.half_pitch);
+    const float xpix = fadd(__fmaf_rn((float)xp, p.pixel_pitch, p.tpc_borders[pl][0][0]), p.half_pitch);
+    const float ypix = fadd(__fmaf_rn((float)yp, p.pixel_pitch, p.tpc_borders[pl][1][0]), p.half_pitch);
     const float dxs = fsub(xe, xpix), dys = fsub(ye, ypix);
     // current_mc timing
     const float dza = fsub(ze, ph.z_anode);

@@ -57,6 +57,7 @@ class ParamsPOD(C.Structure):
         ("diffusion_in_current_sim", C.c_int32),
         ("dvdrift_dEfield", C.c_float),
         ("eField", C.c_float), ("lArDensity", C.c_float), ("R_param", C.c_float),
+        ("ts_vdrift", C.c_float),
     ]
 
 

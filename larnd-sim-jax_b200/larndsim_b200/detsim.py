@@ -32,8 +32,9 @@ def id2pixel(params, pid):
 def get_pixel_coordinates(params, xpitch, ypitch, plane):
     b = _borders(params, xpitch.device)[plane.long()]
     pitch = float(params.pixel_pitch)
-    px = xpitch.float() * pitch + b[..., 0, 0] + pitch / 2
-    py = ypitch.float() * pitch + b[..., 1, 0] + pitch / 2
+    # fma(index, pitch, border) + pitch/2 (XLA contracts the multiply-add; pinned by the reference goldens)
+    px = torch.addcmul(b[..., 0, 0].double(), xpitch.double(), torch.tensor(float(np.float32(pitch)), dtype=torch.float64, device=b.device)).float() + pitch / 2
+    py = torch.addcmul(b[..., 1, 0].double(), ypitch.double(), torch.tensor(float(np.float32(pitch)), dtype=torch.float64, device=b.device)).float() + pitch / 2
     return torch.stack([px, py], dim=-1)
 
 
@@ -45,4 +46,7 @@ def get_hit_z(params, ticks, plane, fixed_v=False):
     v = params.vdrift_static if fixed_v else get_vdrift(params)
     if torch.is_tensor(v):
         v = v.to(ticks.device)
-    return z_anode + ticks * float(params.t_sampling) * v * torch.sign(z_high - z_anode)
+    tv = float(np.float32(params.t_sampling)) * v      # XLA folds the two scalars first (pinned by the goldens' pix_z)
+    if not torch.is_tensor(tv):
+        tv = float(np.float32(tv))
+    return z_anode + ticks * tv * torch.sign(z_high - z_anode)

@@ -7,7 +7,9 @@ from . import sim as _sim
 
 
 def adc2charge(dw, params):
-    return (dw / params.ADC_COUNTS * (params.V_REF - params.V_CM) + params.V_CM - params.V_PEDESTAL) / params.GAIN * 1e-3
+    """ke- from ADC counts; evaluated in double and rounded once, which is what reproduces the goldens' Q column."""
+    d = dw.double()
+    return ((d / params.ADC_COUNTS * (params.V_REF - params.V_CM) + params.V_CM - params.V_PEDESTAL) / params.GAIN * 1e-3).to(dw.dtype)
 
 
 def rbf_kernel(x, y, sigma):

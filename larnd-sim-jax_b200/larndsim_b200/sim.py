@@ -101,6 +101,7 @@ def make_pod(params, lut_shape=None):
     P.max_adc_values = int(params.MAX_ADC_VALUES)
     P.diffusion_in_current_sim = int(bool(params.diffusion_in_current_sim))
     P.eField, P.lArDensity, P.R_param = _f(params, "eField"), _f(params, "lArDensity"), _f(params, "R_param")
+    P.ts_vdrift = float(np.float32(params.t_sampling) * np.float32(v))
     return P
 
 

@@ -285,13 +285,21 @@ def id2pixel(params, pid):
     return pid % nx, (pid // nx) % ny, (pid // (nx * ny)) % ntpc, pid // (nx * ny * ntpc)
 
 
+def _fma(a, b, c, dt):
+    """fused multiply-add with a single rounding (exact product of two float32 fits a double)."""
+    if dt is np.float64:
+        return a * b + c
+    return (np.asarray(a, np.float64) * np.float64(b) + np.asarray(c, np.float64)).astype(dt)
+
+
 def get_pixel_coordinates(params, xpitch, ypitch, plane, dt=np.float32):
-    """detsim_jax.py:296-306."""
+    """detsim_jax.py:296-306.  XLA:CPU contracts ``xpitch*pitch + border`` into one FMA; the goldens
+    (output/jax_ref/*.h5 pix_x, pix_y) are reproduced bit for bit only with that contraction."""
     b = _borders(params, dt)[np.asarray(plane).astype(np.int32)]
     pitch = dt(params.pixel_pitch)
     half = dt(params.pixel_pitch / 2)
-    px = np.asarray(xpitch).astype(dt) * pitch + b[..., 0, 0] + half
-    py = np.asarray(ypitch).astype(dt) * pitch + b[..., 1, 0] + half
+    px = _fma(np.asarray(xpitch).astype(dt), pitch, b[..., 0, 0], dt) + half
+    py = _fma(np.asarray(ypitch).astype(dt), pitch, b[..., 1, 0], dt) + half
     return np.stack([px, py], axis=-1)
 
 
@@ -299,7 +307,9 @@ def get_hit_z(params, ticks, plane, vdrift, dt=np.float32):
     """detsim_jax.py:308-319 (fixed_v=False)."""
     b = _borders(params, dt)[np.asarray(plane).astype(np.int32)]
     z_anode, z_high = b[..., 2, 0], b[..., 2, 1]
-    return z_anode + np.asarray(ticks, dtype=dt) * dt(params.t_sampling) * dt(vdrift) * np.sign(z_high - z_anode)
+    # XLA folds the two scalar factors: ticks * (t_sampling * v) * sign — pinned bit for bit by the goldens' pix_z
+    tv = dt(dt(params.t_sampling) * dt(vdrift))
+    return z_anode + np.asarray(ticks, dtype=dt) * tv * np.sign(z_high - z_anode)
 
 
 def diffusion_weights_1d(bins, x0, sigma, dt):
@@ -526,9 +536,10 @@ def digitize(params, integral, dt=np.float32):
 
 def adc2charge(dw, params, dt=np.float32):
     """losses_jax.py:380-383 (ke-)."""
-    dw = np.asarray(dw, dtype=dt)
-    return ((dw / dt(params.ADC_COUNTS) * dt(params.V_REF - params.V_CM) + dt(params.V_CM) - dt(params.V_PEDESTAL))
-            / dt(params.GAIN) * dt(1e-3)).astype(dt)
+    # XLA's constant folding + FMA contraction make the jitted float32 expression agree with the correctly rounded
+    # result; the goldens' Q column is reproduced bit for bit by evaluating in double and rounding once.
+    dw = np.asarray(dw, dtype=np.float64)
+    return ((dw / params.ADC_COUNTS * (params.V_REF - params.V_CM) + params.V_CM - params.V_PEDESTAL) / params.GAIN * 1e-3).astype(dt)
 
 
 def get_adc_values(params, pixels_signals, dt=np.float32, noise=None):

@@ -1,0 +1,360 @@
+"""Parity of the CUDA path (through the C ABI / ctypes host mirror) against the numpy oracle.  GPU only.
+
+Bars (north star): pixel ids, tick indices, template indices and hit sets bit-exact; waveforms within
+WFS_RTOL of the row maximum (float32 accumulation order differs from the oracle's float64 scatter-add);
+ADC values within ADC_ATOL counts; gradients within GRAD_RTOL of float64 central differences."""
+import numpy as np
+import pytest
+
+import common as cm
+from oracle import consts as oc
+from oracle import larnd_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+WFS_RTOL = 5e-6     # |wfs_cuda - wfs_oracle| <= WFS_RTOL * max|row| (+ tiny absolute floor)
+ADC_ATOL = 2e-3     # ADC counts (reference's own acceptance bar is 1e-2, optimize/comparison.py:183)
+GRAD_RTOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def torch_dev(cuda_lib):
+    import torch
+    return torch.device("cuda", 0)
+
+
+def _run_lut(torch_dev, tr, bank, npix=None, **kw):
+    import torch
+    from larndsim_b200 import sim
+    pp = cm.product_params(**kw)
+    st = sim.lut_forward(pp, torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev), cm.FIELDS,
+                         npix_capacity=npix)
+    torch.cuda.synchronize()
+    return pp, st
+
+
+GARBAGE_RTOL = 1e-3  # column 0 (the garbage tick the reference drops, sim_jax.py:736) is a cancellation-prone float32 sum:
+                     # the oracle's own float32 and float64 evaluations differ by ~2e-4 there
+
+
+def _check_wfs(w, ref, rows=None):
+    if rows is not None:
+        w, ref = w[rows], ref[rows]
+    if w.shape[1] == 2001:  # full rows: column 0 is the garbage tick
+        g, gr = w[:, 0], ref[:, 0]
+        assert (np.abs(g - gr) <= GARBAGE_RTOL * np.maximum(np.abs(gr), np.abs(ref).max(axis=1)) + 1e-3).all()
+        w, ref = w[:, 1:], ref[:, 1:]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    err = np.abs(w - ref)
+    assert (err <= WFS_RTOL * scale + 1e-3).all(), "max rel-to-row-max error %.3g" % (err / (scale + 1e-30)).max()
+
+
+def _check_records(st, d, op, L, nt=1950):
+    from larndsim_b200 import sim
+    rec = {k: v.cpu().numpy() for k, v in sim.record_fields(st).items()}
+    assert np.array_equal(rec["MAINPIX"], d["main_pixels"])
+    assert np.array_equal(rec["BX"], d["bins_pitches"][:, 0]) and np.array_equal(rec["BY"], d["bins_pitches"][:, 1])
+    ts = np.float32(op.t_sampling)
+    ft = d["t0_neigh"] / ts
+    ct = np.clip(np.floor(ft).astype(np.int32), 0, nt - 1)
+    assert np.array_equal(rec["T0"], nt - L - ct)
+    assert np.array_equal(rec["FRAC"], (ft - ct).astype(np.float32))
+    tv = np.asarray(op.long_diff_template, dtype=np.float32)
+    assert np.array_equal(rec["IDX"], np.clip(np.searchsorted(tv, d["long_diff_seg"]), 1, tv.shape[0] - 2))
+    q = d["nelectrons_neigh"]
+    assert np.allclose(rec["Q"], q, rtol=2e-6, atol=1e-6)
+    wx = np.stack([rec["WX%d" % i] for i in range(5)], 1)
+    wy = np.stack([rec["WY%d" % i] for i in range(5)], 1)
+    assert np.abs(wx - d["wx"]).max() < 5e-7 and np.abs(wy - d["wy"]).max() < 5e-7
+
+
+def _hits_equal(out_o, out_p):
+    names = ["adc", "x", "y", "z", "ticks", "hit_prob", "event", "pixel"]
+    got = [t.detach().cpu().numpy() for t in out_p]
+    assert len(got[0]) == len(out_o[0]), "hit count %d vs oracle %d" % (len(got[0]), len(out_o[0]))
+    for n, a, b in zip(names, out_o, got):
+        if n == "adc":
+            assert np.abs(a - b).max() <= ADC_ATOL if len(a) else True
+        else:
+            assert np.array_equal(a, b), n
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=4, L=100, prec=0.005, nseg=2500, pad=60, ibatch=1),    # optimize/simulate_test.sh settings
+    dict(n=2, L=150, prec=0.01, nseg=2000, pad=0, ibatch=0),      # optimize/fit_test.sh --lut settings
+    dict(n=0, L=100, prec=0.01, nseg=800, pad=10, ibatch=2),      # no neighbours
+    dict(n=1, L=30, prec=0.01, nseg=800, pad=10, ibatch=3),       # short window -> 4-slot kernel
+    dict(n=2, L=400, prec=0.05, nseg=600, pad=0, ibatch=0),       # optimize/simulate_fwd.sh window -> 16-slot kernel
+])
+def test_lut_forward_matches_oracle(torch_dev, cfg):
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=cfg["n"], signal_length=cfg["L"])
+    nx = max(10 * cfg["n"] + 5, 5)
+    bank = cm.synthetic_bank(32, nx, nx, 1950)
+    tr = cm.small_batch(cfg["nseg"], ibatch=cfg["ibatch"], pad=cfg["pad"], precision=cfg["prec"])
+    op = cm.oracle_params(**kw)
+    wfs_o, uniq_o, d, full_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={}, return_aux=True)
+    pp, st = _run_lut(torch_dev, tr, bank, npix=len(uniq_o), **kw)
+    assert st.counts.cpu().numpy()[2] == 0
+    _check_records(st, d, op, cfg["L"])
+    assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
+    _check_wfs(st.wfs_full.cpu().numpy(), full_o)
+    out_o = lo.simulate_stochastic(op, wfs_o, uniq_o)
+    out_p = sim.simulate_stochastic(pp, st.wfs_full[:, 1:], st.unique_pixels, 0)
+    _hits_equal(out_o, out_p)
+
+
+def test_exact_shape_mode_reproduces_reference_padding(torch_dev):
+    """npix_capacity=None follows pad_size(n_unique+1,'unique_pixels',0.2) (sim_jax.py:717-721)."""
+    import torch
+    from larndsim_b200 import sim
+    sim.size_history_dict.clear()
+    bank = cm.synthetic_bank(32, 25, 25, 1950)
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    hist = {}
+    for ib in (0, 1, 2):
+        tr = cm.small_batch(700 + 150 * ib, ibatch=ib, pad=5, precision=0.01)
+        wfs_o, uniq_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history=hist)
+        wfs, upix = sim.simulate_wfs(pp, torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev), cm.FIELDS)
+        assert tuple(wfs.shape) == wfs_o.shape
+        assert np.array_equal(upix.cpu().numpy(), uniq_o)
+        _check_wfs(wfs.cpu().numpy(), wfs_o)
+
+
+def test_unsorted_segments_and_edges(torch_dev):
+    """Shuffled rows (no runs, constant row/window flushes), segments next to the anode (windows sticking out of the
+    readout -> garbage tick 0) and outside every TPC."""
+    rng = np.random.default_rng(3)
+    tr = cm.small_batch(900, ibatch=1, pad=0, precision=0.01)
+    c = cm.FIELDS.index
+    near = tr[:300].copy()
+    shift = 30.45 - np.abs(near[:, c("z")]).max()
+    for col in ("z", "z_start", "z_end"):
+        near[:, c(col)] += np.sign(near[:, c(col)]) * shift     # last ~1 cm before the anode: T0 < 2
+    far = tr[300:360].copy()
+    far[:, c("x")] += 100.0                                      # outside every TPC: masked, pixel id -1
+    allr = np.concatenate([tr, near, far])
+    allr = allr[rng.permutation(len(allr))]
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = cm.synthetic_bank(48, 25, 25, 1950)   # masked segments drift "through" the other TPC: larger sigma_L, higher templates
+    op = cm.oracle_params(**kw)
+    wfs_o, uniq_o, d, full_o = lo.simulate_wfs(op, bank, allr, cm.FIELDS, history={}, return_aux=True)
+    pp, st = _run_lut(torch_dev, allr, bank, npix=len(uniq_o), **kw)
+    assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
+    w = st.wfs_full.cpu().numpy()
+    assert np.abs(full_o[:, 0]).max() > 0, "test must exercise the garbage tick"
+    _check_wfs(w, full_o)
+
+
+def test_skip_garbage_flag_only_changes_garbage_rows(torch_dev):
+    from larndsim_b200 import sim
+    import torch
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = cm.synthetic_bank(32, 25, 25, 1950)
+    tr = cm.small_batch(800, ibatch=0, pad=12, precision=0.01)
+    pp = cm.product_params(**kw)
+    b, t = torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev)
+    full = sim.lut_forward(pp, b, t, cm.FIELDS)
+    skip = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=full.npix, flags=1)
+    valid = (full.unique_pixels >= 0).cpu().numpy()
+    a, s = full.wfs_full.cpu().numpy(), skip.wfs_full.cpu().numpy()
+    _check_wfs(s, a, rows=valid)
+    assert np.abs(s[~valid]).max() == 0.0
+
+
+def test_empty_and_all_padding_batches(torch_dev):
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=1, signal_length=50)
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    pp = cm.product_params(**kw)
+    b = torch.as_tensor(bank, device=torch_dev)
+    empty = torch.zeros((0, 26), device=torch_dev)
+    st = sim.lut_forward(pp, b, empty, cm.FIELDS, npix_capacity=4, n_events=0)
+    assert st.counts.cpu().numpy()[0] == 0 and (st.unique_pixels.cpu().numpy() == -1).all() and float(st.wfs_full.abs().max()) == 0.0
+    pad = lo.pad_batch(np.zeros((0, 26), np.float32), 50, cm.FIELDS)
+    op = cm.oracle_params(**kw)
+    wfs_o, uniq_o = lo.simulate_wfs(op, bank, pad, cm.FIELDS, history={})
+    st = sim.lut_forward(pp, b, torch.as_tensor(pad, device=torch_dev), cm.FIELDS, npix_capacity=len(uniq_o))
+    assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
+    assert float(st.wfs_full.abs().max()) == 0.0
+    hits = sim.simulate_stochastic(pp, st.wfs_full[:, 1:], st.unique_pixels, 0)
+    assert all(len(h) == 0 for h in hits)
+
+
+def test_capacity_overflow_and_bad_event_ids_are_flagged(torch_dev):
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=1, signal_length=50)
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    pp = cm.product_params(**kw)
+    tr = cm.small_batch(1500, ibatch=0, pad=0, precision=0.01)   # spans several events
+    assert tr[:, 0].max() >= 1
+    b, t = torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev)
+    st = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=2)
+    assert st.counts.cpu().numpy()[2] & 1
+    st = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=64, n_events=1)   # events 1.. are out of the declared range
+    assert st.counts.cpu().numpy()[2] & 2
+    with pytest.raises(ValueError):
+        sim.lut_forward(pp, b, t, cm.FIELDS, n_events=1)
+    from larndsim_b200 import LarndError
+    with pytest.raises(LarndError):
+        sim.lut_forward(pp, b, torch.as_tensor(tr), cm.FIELDS)                # CPU tensor: no CPU path
+    with pytest.raises(LarndError):
+        sim.lut_forward(cm.product_params(number_pix_neighbors=3, signal_length=50), b, t, cm.FIELDS)  # LUT too small
+
+
+def test_fee_with_injected_noise_matches_oracle(torch_dev):
+    import torch
+    from larndsim_b200 import sim
+    rng = np.random.default_rng(11)
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = cm.synthetic_bank(32, 25, 25, 1950)
+    tr = cm.small_batch(1500, ibatch=1, pad=0, precision=0.01)
+    op = cm.oracle_params(**kw).replace(RESET_NOISE_CHARGE=900, UNCORRELATED_NOISE_CHARGE=500)
+    pp = cm.product_params(**kw).replace(RESET_NOISE_CHARGE=900, UNCORRELATED_NOISE_CHARGE=500)
+    wfs_o, uniq_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={})
+    npix = len(uniq_o)
+    z = rng.normal(size=(31, npix)).astype(np.float32)
+    noise = dict(base=z[0], extra=z[1:11], **{"pass": z[11:21], "fail": z[21:31]})
+    adc_o, ticks_o = lo.get_adc_values(op, wfs_o, noise=noise)
+    fs = sim.fee_forward(pp, torch.as_tensor(wfs_o, device=torch_dev), torch.as_tensor(uniq_o, device=torch_dev),
+                         torch.as_tensor(z.reshape(-1), device=torch_dev), compact=False)
+    assert np.array_equal(fs.ticks.cpu().numpy(), ticks_o)
+    assert np.array_equal(fs.adc.cpu().numpy(), lo.digitize(op, adc_o))
+
+
+def test_lut_gradients_match_float64_finite_differences(torch_dev):
+    import torch
+    from larndsim_b200 import _lib, sim
+    kw = dict(number_pix_neighbors=2, signal_length=150)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    bank = cm.synthetic_bank(32, 25, 25, 1950)
+    tr = cm.small_batch(300, ibatch=1, pad=0, precision=0.01)
+    _, uniq, d, full = lo.simulate_wfs(op, bank, tr, cm.FIELDS, dt=np.float64, history={}, return_aux=True)
+    npix = len(uniq)
+    rng = np.random.default_rng(5)
+    t = np.arange(2000)
+    G = (rng.uniform(0.5, 1.5, (npix, 1)) * (1 + 0.5 * np.sin(t[None, :] / 37.0 + rng.uniform(0, 6, (npix, 1))))).astype(np.float32)
+
+    def L(p):
+        w, _ = lo.simulate_wfs(p, bank, tr, cm.FIELDS, dt=np.float64, pad_to=npix)
+        return float((w * G.astype(np.float64)).sum())
+
+    st = sim.lut_forward(pp, torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev), cm.FIELDS, npix_capacity=npix)
+    grad = sim.lut_backward(st, torch.as_tensor(G, device=torch_dev)).cpu().numpy()
+    steps = dict(Ab=1e-6, kb=1e-7, eField=1e-7, lifetime=1e-2, long_diff=1e-11, tran_diff=1e-11, shift_x=1e-6, shift_z=1e-6,
+                 MeVToElectrons=1e-1)
+    for name, h in steps.items():
+        base = getattr(op, name)
+        fd = (L(op.replace(**{name: base + h})) - L(op.replace(**{name: base - h}))) / (2 * h)
+        g = grad[_lib.PARAM_ORDER.index(name)]
+        assert abs(g - fd) <= GRAD_RTOL * abs(fd) + 1e-6 * abs(grad).max(), (name, g, fd)
+    assert grad[_lib.PARAM_ORDER.index("vdrift")] == 0.0   # params.vdrift is never read by the reference
+
+
+def test_autograd_end_to_end(torch_dev):
+    """build_params_class leaves get gradients through simulate_wfs + simulate_stochastic, like jax.grad in the reference."""
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=2, signal_length=150)
+    names = ("Ab", "kb", "eField", "lifetime", "tran_diff", "long_diff")
+    P = cm.product_params(grad=names, **kw)
+    op = cm.oracle_params(**kw)
+    bank = cm.synthetic_bank(32, 25, 25, 1950)
+    tr = cm.small_batch(400, ibatch=1, pad=0, precision=0.01)
+    wfs, upix = sim.simulate_wfs(P, torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev), cm.FIELDS)
+    out = sim.simulate_stochastic(P, wfs, upix, 0)
+    loss = (out[0] ** 2).sum() * 1e-4 + (out[3] ** 2).sum() * 1e-3
+    loss.backward()
+
+    def L(p):
+        w, u = lo.simulate_wfs(p, bank, tr, cm.FIELDS, dt=np.float64, history={})
+        o = lo.simulate_stochastic(p, w, u, dt=np.float64)
+        return float((o[0] ** 2).sum() * 1e-4 + (o[3] ** 2).sum() * 1e-3)
+
+    assert abs(float(loss) - L(op)) < 1e-4 * abs(L(op))
+    for name, h in dict(Ab=1e-6, kb=1e-7, eField=1e-7, lifetime=1e-2, tran_diff=1e-11, long_diff=1e-11).items():
+        base = getattr(op, name)
+        fd = (L(op.replace(**{name: base + h})) - L(op.replace(**{name: base - h}))) / (2 * h)
+        g = float(getattr(P, name).grad)
+        assert abs(g - fd) <= GRAD_RTOL * abs(fd) + 1e-9, (name, g, fd)
+
+
+def test_mc_mode_matches_oracle(torch_dev):
+    import torch
+    from larndsim_b200 import _lib, sim
+    rng = np.random.default_rng(9)
+    kw = dict(number_pix_neighbors=0, signal_length=150, mc_diff=True)
+    for diff_in_current in (True, False):
+        op = cm.oracle_params(**kw).replace(diffusion_in_current_sim=diff_in_current)
+        pp = cm.product_params(**kw).replace(diffusion_in_current_sim=diff_in_current)
+        tr = cm.small_batch(500, ibatch=1, pad=8, precision=0.01)
+        rnd = rng.normal(size=(tr.shape[0], 3)).astype(np.float32)
+        out_o, wfull_o, uniq_o = lo.simulate_parametrized(op, tr, cm.FIELDS, rnd, history={}, return_wfs=True)
+        trd, rndd = torch.as_tensor(tr, device=torch_dev), torch.as_tensor(rnd, device=torch_dev)
+        st = sim.mc_forward(pp, trd, cm.FIELDS, rndd, npix_capacity=len(uniq_o))
+        assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
+        valid = uniq_o >= 0
+        w = st.wfs_full.cpu().numpy()
+        scale = np.abs(wfull_o[valid]).max(axis=1, keepdims=True)
+        assert (np.abs(w[valid] - wfull_o[valid]) <= 2e-5 * scale + 1e-2).all()
+        out_p = sim.simulate_parametrized(pp, trd, cm.FIELDS, rnd=rndd, npix_capacity=len(uniq_o))
+        got = [t.cpu().numpy() for t in out_p]
+        assert len(got[0]) == len(out_o[0])
+        assert np.array_equal(got[4], out_o[4]) and np.array_equal(got[7], out_o[7])
+        assert np.abs(got[0] - out_o[0]).max() <= ADC_ATOL
+    # gradients of the diffusion-in-current variant
+    op = cm.oracle_params(**kw)
+    pp = cm.product_params(**kw)
+    tr = cm.small_batch(300, ibatch=1, pad=0, precision=0.01)
+    rnd = rng.normal(size=(tr.shape[0], 3)).astype(np.float32)
+    _, wfull, uniq = lo.simulate_parametrized(op, tr, cm.FIELDS, rnd, history={}, return_wfs=True)
+    G = (rng.uniform(0.5, 1.5, (len(uniq), 1)) * (1 + 0.5 * np.sin(np.arange(2000)[None, :] / 37.0))).astype(np.float32)
+    G[uniq < 0] = 0
+    trd = torch.as_tensor(tr, device=torch_dev)
+    st = sim.mc_forward(pp, trd, cm.FIELDS, torch.as_tensor(rnd, device=torch_dev), npix_capacity=len(uniq))
+    grad = sim.mc_backward(st, trd, torch.as_tensor(G, device=torch_dev)).cpu().numpy()
+
+    def L(p):
+        _, w, _ = lo.simulate_parametrized(p, tr, cm.FIELDS, rnd, dt=np.float64, pad_to=len(uniq), return_wfs=True)
+        return float((w[:, 1:] * G.astype(np.float64)).sum())
+
+    for name, h in dict(Ab=1e-6, eField=1e-7, lifetime=1e-2, long_diff=1e-11, shift_z=1e-6, shift_x=1e-6).items():
+        base = getattr(op, name)
+        fd = (L(op.replace(**{name: base + h})) - L(op.replace(**{name: base - h}))) / (2 * h)
+        g = grad[_lib.PARAM_ORDER.index(name)]
+        assert abs(g - fd) <= 5e-3 * abs(fd) + 1e-6 * abs(grad).max(), (name, g, fd)
+
+
+def test_full_fixture_batch_and_size_independent_properties(torch_dev):
+    """A complete simulate_test.sh batch (input_0, batch 1: 10 879 segments + reference padding) against the oracle,
+    then properties that hold at any size: linearity in the charge scale and additivity over disjoint event sets."""
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=4, signal_length=100)
+    bank = cm.synthetic_bank(32, 45, 45, 1950)
+    arr, _ = cm.fixture_batches(0, 0.005)[1]
+    tr = lo.pad_batch(arr, int(arr.shape[0] * 1.25 + 0.5), cm.FIELDS)
+    op = cm.oracle_params(**kw)
+    wfs_o, uniq_o, d, full_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={}, response_cum=cm.synthetic_bank_cum(32, 45, 45, 1950),
+                                               return_aux=True)
+    pp, st = _run_lut(torch_dev, tr, bank, npix=len(uniq_o), **kw)
+    assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
+    _check_wfs(st.wfs_full.cpu().numpy(), full_o)
+    _hits_equal(lo.simulate_stochastic(op, wfs_o, uniq_o), sim.simulate_stochastic(pp, st.wfs_full[:, 1:], st.unique_pixels, 0))
+    # linearity: MeVToElectrons x2 -> waveforms x2 (exactly, power of two)
+    b, t = torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev)
+    st2 = sim.lut_forward(pp.replace(MeVToElectrons=2 * pp.MeVToElectrons), b, t, cm.FIELDS, npix_capacity=st.npix)
+    assert torch.allclose(st2.wfs_full, 2 * st.wfs_full, rtol=1e-5, atol=1e-3)
+    # additivity: events are independent (the event id is part of the pixel key)
+    ev = t[:, cm.FIELDS.index("eventID")]
+    lo_half, hi_half = t[(ev >= 0) & (ev < 2)], t[ev >= 2]
+    sa = sim.lut_forward(pp, b, lo_half, cm.FIELDS, n_events=3)
+    sb = sim.lut_forward(pp, b, hi_half, cm.FIELDS, n_events=3)
+    tot = {int(p): w for p, w in zip(st.unique_pixels.cpu().numpy(), st.wfs_full.cpu().numpy()) if p >= 0}
+    for part in (sa, sb):
+        for p, w in zip(part.unique_pixels.cpu().numpy(), part.wfs_full.cpu().numpy()):
+            if p >= 0:
+                _check_wfs(w[None, 1:], tot[int(p)][None, 1:])

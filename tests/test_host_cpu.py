@@ -1,0 +1,203 @@
+"""CPU-only tests of the host logic: C-ABI surface, parameter container, shape bucketing, synthetic generators,
+event sharding with a world_size-2 gloo group.  No compute call is made on the CUDA library."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import common as cm
+from oracle import consts as oc
+from oracle import larnd_oracle as lo
+
+ROOT = cm.ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import larndsim_b200
+    larndsim_b200.build_library()
+    return larndsim_b200.get_lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "larnd_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(larnd_[a-z_0-9]+)\s*\(", hdr))
+    assert {"larnd_lut_forward", "larnd_lut_backward", "larnd_fee_forward", "larnd_fee_backward", "larnd_mc_forward",
+            "larnd_mc_backward", "larnd_lut_create", "larnd_workspace_bytes", "larnd_last_error"} <= names
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in include/larnd_b200.h is not exported" % n
+    assert lib.larnd_abi_version() == 1
+
+
+def test_params_pod_layout_matches_the_header(lib, tmp_path):
+    """sizeof/offsetof of the ctypes mirror == the C struct compiled from the header."""
+    from larndsim_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "larnd_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", '
+                   'sizeof(larnd_params_t), offsetof(larnd_params_t, tpc_borders), offsetof(larnd_params_t, long_diff_template), '
+                   'offsetof(larnd_params_t, ts_vdrift), sizeof(larnd_columns_t));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    P = _lib.ParamsPOD
+    assert got == [ctypes.sizeof(P), P.tpc_borders.offset, P.long_diff_template.offset, P.ts_vdrift.offset, ctypes.sizeof(_lib.Columns)]
+
+
+def test_workspace_size_and_argument_errors_without_gpu(lib):
+    n = lib.larnd_workspace_bytes(1000, 3, 2, 140, 280)
+    assert n > 31 * 1000 * 4 and lib.larnd_workspace_bytes(-1, 3, 2, 140, 280) == 0
+    assert lib.larnd_lut_create(None, 100, 45, 45, 1950, 100, None, None) != 0
+    assert b"invalid" in lib.larnd_last_error()
+
+
+def test_params_container_mirrors_reference_semantics():
+    import torch
+    import larndsim_b200 as lb
+    P = lb.build_params_class(["Ab", "eField"])
+    p = lb.load_geometry_json(P, cm.GEOM)
+    assert torch.is_tensor(p.Ab) and p.Ab.requires_grad and not torch.is_tensor(p.kb)
+    assert [n for n, _ in p.grad_leaves()] == ["Ab", "eField"]
+    q = p.replace(signal_length=77, lifetime=1234.0)
+    assert q.signal_length == 77 and p.signal_length == 150 and q.lifetime == 1234.0 and type(q) is type(p)
+    with pytest.raises(AttributeError):
+        p.signal_length = 3
+    with pytest.raises(ValueError):
+        lb.build_params_class(["not_a_param"])
+    v = lb.get_vdrift(p)
+    assert torch.is_tensor(v) and abs(float(v) - oc.get_vdrift(cm.oracle_params())) < 1e-6
+    v.backward()
+    assert abs(float(p.eField.grad) - 0.1598) < 1e-3          # dv/dE at 0.5 kV/cm
+    assert abs(lb.get_vdrift(lb.load_geometry_json(lb.build_params_class([]), cm.GEOM)) - 0.159645) < 1e-6
+
+
+def test_parameter_block_matches_oracle_constants():
+    from larndsim_b200 import sim
+    pp, op = cm.product_params(), cm.oracle_params()
+    pod = sim.make_pod(pp)
+    f = np.float32
+    assert f(pod.vdrift) == f(oc.get_vdrift(op)) and pod.n_ticks == 2001 and pod.hold_interval == lo.hold_interval(op)
+    assert f(pod.bin_width) == f(op.pixel_pitch / 10) and f(pod.efield_rho) == f(op.eField * op.lArDensity)
+    sym, w = 2, op.pixel_pitch / 10
+    assert np.array_equal(np.array(list(pod.tran_bin_edges), dtype=f), oc.linspace_jnp(f(-sym * w), f((sym + 1) * w), 6))
+    assert np.array_equal(np.array(list(pod.long_diff_template)[:100], dtype=f), np.asarray(op.long_diff_template, dtype=f))
+    assert np.allclose(np.array(pod.tpc_borders)[:2], np.asarray(op.tpc_borders, dtype=f))
+    assert f(pod.ts_vdrift) == f(f(op.t_sampling) * f(oc.get_vdrift(op)))
+
+
+def test_pad_size_matches_oracle_and_reference_rule():
+    from larndsim_b200 import sim
+    sim.size_history_dict.clear()
+    hist = {}
+    for n in (100, 103, 99, 250, 255, 262, 251, 1000, 1040, 1060):
+        assert sim.pad_size(n, "t", 0.2) == lo.pad_size(n, "t", 0.2, hist)
+    assert sim.pad_size(100, "fresh", 0.5) == 125 and sim.pad_size(110, "fresh", 0.5) == 125 and sim.pad_size(126, "fresh", 0.5) == 158
+    assert sim.pad_size((10, 20), "nd", 0.1) == (11, 21)
+
+
+def test_synthetic_generators():
+    from larndsim_b200 import synthetic
+    assert synthetic.FIELDS == cm.FIELDS
+    a = synthetic.synthetic_response(7, 6, 300)
+    assert np.array_equal(a, oc.synthetic_response(7, 6, 300))           # product and oracle generators are identical
+    assert np.allclose(a[:5, :5].sum(-1) * 0.1, 1.0, atol=1e-5) and np.abs(a[5:].sum(-1)).max() < 1e-4
+    tr, nev = synthetic.synthetic_tracks(20000, seed=3, precision=0.01)
+    c = cm.FIELDS.index
+    assert tr.shape == (20000, 26) and tr.dtype == np.float32 and nev == int(tr[:, c("eventID")].max()) + 1
+    assert np.abs(tr[:, c("x")]).max() < 31.1 and np.abs(tr[:, c("y")]).max() < 62.1 and np.abs(tr[:, c("z")]).max() < 30.6
+    assert np.allclose(tr[:, c("dE")], tr[:, c("dEdx")] * tr[:, c("dx")], rtol=1e-5)
+    assert (np.diff(tr[:, c("eventID")]) >= 0).all()
+    tr2, _ = synthetic.synthetic_tracks(20000, seed=3, precision=0.01)
+    assert np.array_equal(tr, tr2)
+
+
+def test_chop_tracks_conserves_energy_and_length():
+    arr, _ = cm.fixture_batches(1, 0.01)[0]
+    seg = np.load(os.path.join(cm.GOLD, "segments_input_1.npz"))["segments"]
+    c = cm.FIELDS.index
+    tot = sum(a[:, c("dx")].sum() for a, _ in cm.fixture_batches(1, 0.01))
+    assert tot <= seg["dx"].sum() * (1 + 1e-4) and tot > 0.5 * seg["dx"].sum()     # over-long trajectories are dropped
+    assert arr[:, c("dx")].max() <= 0.01 + 1e-6
+    one = lo.structured_to_f32(lo.swap_xz_structured(seg[:1]))
+    ch = lo.chop_tracks(one, cm.FIELDS, 0.01)
+    assert abs(ch[:, c("dE")].sum() - one[0, c("dE")]) < 1e-4 * one[0, c("dE")]
+    assert np.allclose(ch[-1, [c("x_end"), c("y_end"), c("z_end")]], one[0, [c("x_end"), c("y_end"), c("z_end")]])
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "larnd-sim-jax_b200", "larndsim_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from larndsim_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.LarndError):
+        _lib.get_lib()
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    from larndsim_b200 import LarndError, sim
+    with pytest.raises(LarndError):
+        sim.simulate_wfs(cm.product_params(), torch.zeros(3, 5, 5, 10), torch.zeros(4, 26), cm.FIELDS)
+
+
+def test_event_partition_is_balanced_and_complete():
+    from larndsim_b200 import parallel
+    rng = np.random.default_rng(0)
+    ev = np.sort(rng.integers(0, 37, size=5000))
+    ev[:11] = -1
+    for world in (1, 2, 3, 8):
+        parts = parallel.event_partition(ev, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 37 and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        sizes = [int(((ev >= lo_) & (ev < hi)).sum()) for lo_, hi in parts]
+        assert sum(sizes) == int((ev >= 0).sum()) and max(sizes) - min(sizes) < 2 * 5000 / 37 + 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "larnd-sim-jax_b200")); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from larndsim_b200 import parallel
+import common as cm
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"], rank=rank, world_size=world)
+arr, _ = cm.fixture_batches(0, 0.01)[0]
+local, nev, first = parallel.shard_tracks(arr, cm.FIELDS, rank, world)
+ev = local[:, 0]
+assert ev.min() == 0 and ev.max() == nev - 1
+# every rank contributes its segment count, its dE sum and a fake 15-vector of gradients
+red = torch.tensor([float(local.shape[0]), float(local[:, cm.FIELDS.index("dE")].sum())] + [float(rank + 1)] * 15, dtype=torch.float64)
+parallel.allreduce_sum_(red)
+assert int(red[0]) == arr.shape[0], (int(red[0]), arr.shape[0])
+assert abs(float(red[1]) - float(arr[:, cm.FIELDS.index("dE")].sum())) < 1e-3
+assert float(red[2]) == sum(range(1, world + 1))
+g = parallel.allgather(torch.tensor([float(rank), float(nev)]))
+assert g.shape == (world, 2) and int(g[:, 1].sum()) == int(arr[:, 0].max()) + 1
+assert parallel.scan_points_for_rank(10, rank, world) == list(range(rank, 10, world))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_event_sharding_and_collectives_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out
+        assert "ok" in out

