@@ -50,10 +50,11 @@ constexpr int SPAN_MAX = KP - 2;  // max (T0max - T0min) inside a run
 //   h[m]  = sum q*f at T0 = tmin+m  +  sum q*(1-f) at T0 = tmin+m-1            (window part, sim_jax.py:190-194)
 //   moments per T0 position for the boundary correction (sim_jax.py:236-247), which is bilinear in (1-f, f):
 //   A1 = sum q(1-f), A2 = sum q(1-f)^2, A3 = sum q f(1-f), B1 = sum q f, B3 = sum q f^2
-struct RunInfo {
+struct __align__(16) RunInfo {
   int start, len, tmin, span;
   int ep, pxy;      // event*ntpc+plane, main pixel (x | y << 16)
-  int bx, by;       // sub-pixel bin of the run
+  int mpx, mpy;     // main pixel
+  int bxm, bym;     // sub-pixel bin inside the main pixel, 0 .. nb-1
   int idx;          // longitudinal-diffusion template index
   int fast;         // whole window inside the readout (no garbage-tick handling needed)
 };
@@ -65,6 +66,10 @@ struct ChunkSmem {
   int idx[S], bx[S], by[S];
   float wx[LARND_NB_TRAN_BINS][S], wy[LARND_NB_TRAN_BINS][S];
   RunInfo run[S];
+  // per-segment products used when a main (diffusion-bin) unit builds its impulse trains: multiply by Wx[i]*Wy[j]
+  float4 pf[S];    // q f a, q f b, q f c, q f                (deposit at T0)
+  float4 po[S];    // q(1-f) a, q(1-f) b, q(1-f) c, q(1-f)    (deposit at T0+1)
+  float4 pm[S];    // q(1-f)^2, q f(1-f), q f^2, unused       (correction moments A2, A3, B3)
   float rh[S][KP], rA1[S][KP], rA2[S][KP], rA3[S][KP], rB1[S][KP], rB3[S][KP];  // neighbour impulse train + moments
   int nruns;
   int next_unit;
@@ -166,13 +171,18 @@ __device__ __forceinline__ float boundary_delta(const float* crow, int ct, int n
 
 // Applies one impulse train to the register window: for every tick position j of the run,
 //   acc[col] += h_j * Rblend[col - (tmin + j)]   for col - (tmin+j) in [0, L)
-//   acc[col] += E_j                              for col == tmin + j - 1   (merged boundary corrections)
-// Lane j holds h[NR][j] and E_j; they are broadcast with shuffles.  Only valid for "fast" runs (all ticks inside
-// the readout window).
+// Lane j holds h[NR][j]; it is broadcast with a shuffle.  Each lane walks one pointer per response row; the slot
+// offset is an immediate (32*s floats) and lanes outside the response window are predicated off, so the inner
+// loop is one compare + NR loads + NR FMAs per 32 ticks.
 template <int NS, int NR>
-__device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmin, int npos, const float (&h)[NR], float E,
+__device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmin, int npos, const float (&h)[NR],
                                             const float* const (&rows)[NR], int L, int lane) {
-  for (int j = 0; j < npos; ++j) {
+  // x = col - (tmin + j) for slot 0 of this lane; response sample k lives at row[k + 2]
+  int x0 = tbase + lane - tmin;
+  const float* p[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) p[r] = rows[r] + (x0 + 2);
+  for (int j = 0; j < npos; ++j, --x0) {
     float hj[NR];
     bool any = false;
 #pragma unroll
@@ -180,20 +190,34 @@ __device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmi
       hj[r] = __shfl_sync(0xffffffffu, h[r], j);
       any |= (hj[r] != 0.0f);
     }
-    const float Ej = __shfl_sync(0xffffffffu, E, j);
-    if (!any && Ej == 0.0f) continue;  // warp-uniform
-    const int xb0 = tbase - (tmin + j);  // x of lane 0, slot 0
+    if (any) {  // warp-uniform
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const int xs = xb0 + 32 * s;
-      if (xs + 31 < -1 || xs >= L) continue;  // warp-uniform
-      const int x = xs + lane;
-      const int xc = min(max(x, -2), L);
-      float v = hj[0] * __ldg(rows[0] + xc + 2);
+      for (int s = 0; s < NS; ++s) {
+        const bool in = (unsigned)(x0 + 32 * s) < (unsigned)L;
 #pragma unroll
-      for (int r = 1; r < NR; ++r) v = fmaf(hj[r], __ldg(rows[r] + xc + 2), v);
-      acc[s] += (x == -1) ? Ej : v;
+        for (int r = 0; r < NR; ++r) {
+          const float v = in ? __ldg(p[r] + 32 * s) : 0.0f;
+          acc[s] = fmaf(hj[r], v, acc[s]);
+        }
+      }
     }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) --p[r];
+  }
+}
+
+// Adds the merged boundary corrections of a run: lane j holds E_j, which belongs to tick tmin - 1 + j.
+template <int NS>
+__device__ __forceinline__ void add_corrections(float (&acc)[NS], int tbase, int tmin, float E, int lane) {
+  const int off = tmin - 1 - tbase;           // >= 0 by construction of the window
+  const int rot = off & 31, s0 = off >> 5;
+  const float Er = __shfl_sync(0xffffffffu, E, (lane - rot) & 31);  // lane l now holds E_{(l - rot) mod 32}
+  const float lo = (lane >= rot) ? Er : 0.0f;  // ticks in slot s0
+  const float hi = (lane < rot) ? Er : 0.0f;   // wrapped into slot s0 + 1 (E_j = 0 for j >= KP keeps this exact)
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (s == s0) acc[s] += lo;
+    if (s == s0 + 1) acc[s] += hi;
   }
 }
 
@@ -208,7 +232,7 @@ __device__ __forceinline__ float run_correction(const float* crow, int tmin, int
   // impulse position j covers tick tmin + j - 1:  E_j = e0_j + e1_{j-1}
   float e1_up = __shfl_up_sync(0xffffffffu, e1, 1);
   if (lane == 0) e1_up = 0.0f;
-  return e0 + e1_up;
+  return e0 + e1_up;  // callers zero lanes > span + 1
 }
 
 template <int NS>
@@ -240,6 +264,13 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
     sm.idx[t] = irec[(int64_t)LARND_I_IDX * n + s];
     sm.bx[t] = bx;
     sm.by[t] = by;
+    {
+      const float q = sm.seg[t].x, f = sm.seg[t].y, o = 1.0f - f;
+      const float qf = q * f, qo = q * o;
+      sm.pf[t] = make_float4(qf * sm.a[t], qf * sm.b[t], qf * sm.c[t], qf);
+      sm.po[t] = make_float4(qo * sm.a[t], qo * sm.b[t], qo * sm.c[t], qo);
+      sm.pm[t] = make_float4(qo * o, qf * o, qf * f, 0.0f);
+    }
 #pragma unroll
     for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
       sm.wx[k][t] = rec[(int64_t)(LARND_F_WX0 + k) * n + s];
@@ -279,7 +310,9 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
   for (int r = threadIdx.x; r < nruns; r += ACC_THREADS) {
     RunInfo& R = sm.run[r];
     const int t0s = R.start;
-    R.ep = sm.key[t0s].x; R.pxy = sm.key[t0s].y; R.bx = sm.bx[t0s]; R.by = sm.by[t0s]; R.idx = sm.idx[t0s];
+    R.ep = sm.key[t0s].x; R.pxy = sm.key[t0s].y; R.idx = sm.idx[t0s];
+    R.mpx = floordiv_i(sm.bx[t0s], nb); R.mpy = floordiv_i(sm.by[t0s], nb);
+    R.bxm = sm.bx[t0s] - R.mpx * nb; R.bym = sm.by[t0s] - R.mpy * nb;
     R.fast = (R.tmin >= 2) && (R.tmin + R.span + L <= A.nticks - 1);
     for (int k = 0; k < KP; ++k) { sm.rh[r][k] = 0.f; sm.rA1[r][k] = 0.f; sm.rA2[r][k] = 0.f; sm.rA3[r][k] = 0.f; sm.rB1[r][k] = 0.f; sm.rB3[r][k] = 0.f; }
     for (int t = t0s; t < t0s + R.len; ++t) {
@@ -320,12 +353,11 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
         const RunInfo R = sm.run[r];
         if (R.ep != cur_k0 || R.pxy != cur_k1) {
           cur_k0 = R.ep; cur_k1 = R.pxy;
-          const int mpx = (int)(short)(R.pxy & 0xffff), mpy = R.pxy >> 16;
           int row;
           bool garbage;
           if (centre) { row = 0; garbage = true; }  // centre id is overwritten with -999 -> never matches -> row 0
           else {
-            int pid = pixel2id_dev(mpx + dx, mpy + dy, R.ep, A.nxp, A.nyp);
+            int pid = pixel2id_dev(R.mpx + dx, R.mpy + dy, R.ep, A.nxp, A.nyp);
             row = lookup_row(lk, pid);
             garbage = row < 0 || pid < 0;
             if (row < 0) row = 0;  // sim_jax.py:724-725
@@ -339,9 +371,8 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
           flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
           tbase = R.tmin - 1 - (32 * NS - (L + 2 + span)) / 2;
         }
-        const int mpx_ = floordiv_i(R.bx, nb), mpy_ = floordiv_i(R.by, nb);
-        const int vx = 2 * (R.bx - mpx_ * nb) - A.half2 - 2 * nb * dx;
-        const int vy = 2 * (R.by - mpy_ * nb) - A.half2 - 2 * nb * dy;
+        const int vx = 2 * R.bxm - A.half2 - 2 * nb * dx;
+        const int vy = 2 * R.bym - A.half2 - 2 * nb * dy;
         const int bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
         const float* const rows[1] = {A.r0 + (int64_t)bin * A.Lp};
         const float* crow = A.c0 + (int64_t)bin * A.nt;
@@ -351,7 +382,8 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
           float E = run_correction(crow, R.tmin, A.nt, L, sm.rA1[r][kk], sm.rA2[r][kk], sm.rA3[r][kk], sm.rB1[r][kk], sm.rB3[r][kk], lane);
           if (lane > span + 1) E = 0.f;
           const float h[1] = {hl};
-          apply_train<NS, 1>(acc, tbase, R.tmin, span + 2, h, E, rows, L, lane);
+          apply_train<NS, 1>(acc, tbase, R.tmin, span + 2, h, rows, L, lane);
+          add_corrections<NS>(acc, tbase, R.tmin, E, lane);
         } else {
           // run touches the ends of the readout window: per-segment path with garbage-tick handling
           const float cf[1] = {1.0f};
@@ -371,8 +403,11 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
       const int sym = (LARND_NB_TRAN_BINS - 1) / 2;
       for (int r = 0; r < nruns; ++r) {
         const RunInfo R = sm.run[r];
-        const int bxx = R.bx + bi - sym, byy = R.by + bj - sym;
-        const int px = floordiv_i(bxx, nb), py = floordiv_i(byy, nb);
+        // bin (i,j) of the 5x5 diffusion stencil: in-pixel bin index and the pixel it falls on (at most one pixel away)
+        int bxq = R.bxm + bi - sym, byq = R.bym + bj - sym;
+        int px = R.mpx, py = R.mpy;
+        if (bxq < 0) { bxq += nb; --px; } else if (bxq >= nb) { bxq -= nb; ++px; }
+        if (byq < 0) { byq += nb; --py; } else if (byq >= nb) { byq -= nb; ++py; }
         const int k1 = (px & 0xffff) | (py << 16);
         if (R.ep != cur_k0 || k1 != cur_k1) {
           cur_k0 = R.ep; cur_k1 = k1;
@@ -387,8 +422,8 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
           flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
           tbase = R.tmin - 1 - (32 * NS - (L + 2 + span)) / 2;
         }
-        const int cix = abs(2 * (bxx - px * nb) - A.half2) >> 1;
-        const int ciy = abs(2 * (byy - py * nb) - A.half2) >> 1;
+        const int cix = abs(2 * bxq - A.half2) >> 1;
+        const int ciy = abs(2 * byq - A.half2) >> 1;
         const int idx = R.idx;
         const int bin = cix * 5 + ciy;
         const float* const rows[3] = {A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp,
@@ -400,22 +435,21 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
           float h[3] = {0.f, 0.f, 0.f};
           float A1 = 0.f, A2 = 0.f, A3 = 0.f, B1 = 0.f, B3 = 0.f;
           for (int t = R.start; t < R.start + R.len; ++t) {
-            const float4 sg = sm.seg[t];
-            const float f = sg.y, omf = 1.0f - f;
-            const float w = (sm.wx[bi][t] * sm.wy[bj][t]) * sg.x;
-            const int m = __float_as_int(sg.z) - R.tmin;
-            const float wf = w * f, wo = w * omf;
-            const float ca = sm.a[t], cb = sm.b[t], cc = sm.c[t];
-            if (lane == m) {
-              h[0] = fmaf(wf, ca, h[0]); h[1] = fmaf(wf, cb, h[1]); h[2] = fmaf(wf, cc, h[2]);
-              A1 += wo; A2 = fmaf(wo, omf, A2); A3 = fmaf(wf, omf, A3); B1 += wf; B3 = fmaf(wf, f, B3);
-            } else if (lane == m + 1) {
-              h[0] = fmaf(wo, ca, h[0]); h[1] = fmaf(wo, cb, h[1]); h[2] = fmaf(wo, cc, h[2]);
-            }
+            const float w = sm.wx[bi][t] * sm.wy[bj][t];
+            const int m = __float_as_int(sm.seg[t].z) - R.tmin;
+            const float4 pf = sm.pf[t], po = sm.po[t], pm = sm.pm[t];
+            const float w0 = (lane == m) ? w : 0.0f;       // deposits / moments at T0
+            const float w1 = (lane == m + 1) ? w : 0.0f;   // (1-f) deposit one tick later
+            h[0] = fmaf(w0, pf.x, fmaf(w1, po.x, h[0]));
+            h[1] = fmaf(w0, pf.y, fmaf(w1, po.y, h[1]));
+            h[2] = fmaf(w0, pf.z, fmaf(w1, po.z, h[2]));
+            A1 = fmaf(w0, po.w, A1); A2 = fmaf(w0, pm.x, A2); A3 = fmaf(w0, pm.y, A3);
+            B1 = fmaf(w0, pf.w, B1); B3 = fmaf(w0, pm.z, B3);
           }
           float E = run_correction(crow, R.tmin, A.nt, L, A1, A2, A3, B1, B3, lane);
           if (lane > span + 1) E = 0.f;
-          apply_train<NS, 3>(acc, tbase, R.tmin, span + 2, h, E, rows, L, lane);
+          apply_train<NS, 3>(acc, tbase, R.tmin, span + 2, h, rows, L, lane);
+          add_corrections<NS>(acc, tbase, R.tmin, E, lane);
         } else {
           for (int t = R.start; t < R.start + R.len; ++t) {
             const float4 sg = sm.seg[t];

@@ -37,7 +37,17 @@ GARBAGE_RTOL = 1e-3  # column 0 (the garbage tick the reference drops, sim_jax.p
                      # the oracle's own float32 and float64 evaluations differ by ~2e-4 there
 
 
-def _check_wfs(w, ref, rows=None):
+GARBAGE_ROW_RTOL = 1e-4  # rows of pixel ids < 0 (discarded by parse_output) collect contributions from every segment through
+                         # many separate float32 atomic flushes; their rounding noise grows with the number of flushes
+
+
+def _check_wfs(w, ref, rows=None, uniq=None):
+    if uniq is not None:
+        bad = np.asarray(uniq) < 0
+        if bad.any():
+            sc = np.abs(ref[bad]).max(axis=1, keepdims=True)
+            assert (np.abs(w[bad] - ref[bad]) <= GARBAGE_ROW_RTOL * sc + 1e-3).all()
+        rows = ~bad if rows is None else (rows & ~bad)
     if rows is not None:
         w, ref = w[rows], ref[rows]
     if w.shape[1] == 2001:  # full rows: column 0 is the garbage tick
@@ -144,7 +154,7 @@ def test_unsorted_segments_and_edges(torch_dev):
     assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
     w = st.wfs_full.cpu().numpy()
     assert np.abs(full_o[:, 0]).max() > 0, "test must exercise the garbage tick"
-    _check_wfs(w, full_o)
+    _check_wfs(w, full_o, uniq=uniq_o)
 
 
 def test_skip_garbage_flag_only_changes_garbage_rows(torch_dev):
