@@ -54,7 +54,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -78,7 +81,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in (self.rows[self.first:] or self.rows[-3:]):
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -258,6 +261,8 @@ def run_ours(args):
         return fs
 
     def timed(fn, steps, warmup, sampler=None):
+        if sampler:
+            sampler.start()          # nvidia-smi needs ~0.3 s to start streaming: launch it before the warm-up
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -265,7 +270,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
         if sampler:
-            sampler.start()
+            sampler.mark()           # only samples taken from here on (timed region, GPU under load) are summarised
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):

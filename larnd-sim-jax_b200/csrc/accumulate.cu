@@ -20,7 +20,6 @@
 namespace {
 
 constexpr int ACC_THREADS = 256;
-constexpr int ACC_WARPS = ACC_THREADS / 32;
 constexpr int S = LARND_CHUNK;
 
 struct AccArgs {
@@ -216,8 +215,10 @@ __device__ __forceinline__ void add_corrections(float (&acc)[NS], int tbase, int
   const float hi = (lane < rot) ? Er : 0.0f;   // wrapped into slot s0 + 1 (E_j = 0 for j >= KP keeps this exact)
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    if (s == s0) acc[s] += lo;
-    if (s == s0 + 1) acc[s] += hi;
+    if (s == s0) {            // warp-uniform; the window construction guarantees s0 + 1 < NS whenever hi != 0
+      acc[s] += lo;
+      if (s + 1 < NS) acc[s + 1] += hi;
+    }
   }
 }
 
