@@ -1,16 +1,18 @@
 // K3b + K1b: VJP of simulate_wfs (reference sim_jax.py:689-736) w.r.t. the fitted Params leaves, sm_100a.
 //
 // The reference obtains this by jax.grad through gather / scatter-add / erf / sqrt (optimize/fit_params.py:731).
-// Here the backward pass is the *gather* form of K3: a warp owns a segment, walks its 25 + (2n+1)^2 target
-// rows, reads the upstream gradient row window g[row, T0-1 .. T0+L] (coalesced, L1/L2-resident because
-// consecutive segments hit the same rows) together with the same response rows as the forward pass, and
-// accumulates lane-partial derivatives w.r.t. the per-segment continuous quantities
-//     q, frac, (a, b, c), Wx[5], Wy[5]
-// (everything else on the path is an integer index, hence has zero gradient).  One warp
-// reduction per segment, then the closed-form chain rule through drift / quench / diffusion-weight math
-// (drifting_jax.py:42-50, quenching_jax.py:18-35, detsim_jax.py:332-341, sim_jax.py:157-168,406-423) gives the
-// LARND_NPARAMS parameter gradients; they are block-reduced, written as per-chunk partials and summed in
-// double precision by a second tiny kernel (deterministic, no float atomics).
+// Here the backward pass is the *gather* form of K3 and uses the same run decomposition: consecutive segments that
+// share (event, plane, sub-pixel bin, template index) read the same response rows, so for every target row the
+// kernel first correlates the upstream gradient window with the response row once per tick position of the run,
+//     G[j] = sum_x g[row, tmin + j + x] * R[x],
+// and then every segment of the run (one lane per segment) picks its two positions:
+//     d/dq += f G[m] + (1-f) G[m+1] + boundary term,      d/dfrac += q (G[m] - G[m+1]) + boundary terms,
+// plus, for the 25 diffusion bins, the derivatives w.r.t. the Lagrange weights (a,b,c) and the diffusion weights
+// Wx[5], Wy[5].  Everything else on the path is an integer index with zero gradient.  A warp owns a
+// run; after walking the 25 + (2n+1)^2 target rows each lane applies the closed-form chain rule through drift /
+// quench / diffusion-weight math for its own segment (drifting_jax.py:42-50, quenching_jax.py:18-35,
+// detsim_jax.py:332-341, sim_jax.py:157-168,406-423).  The LARND_NPARAMS parameter gradients are reduced per CTA,
+// written as per-chunk partials and summed in double by a second tiny kernel (deterministic, no float atomics).
 #include "larnd_common.cuh"
 
 namespace {
@@ -18,6 +20,9 @@ namespace {
 constexpr int BWD_THREADS = 256;
 constexpr int BWD_WARPS = BWD_THREADS / 32;
 constexpr int S = LARND_CHUNK;
+constexpr int KP = 16;
+constexpr int SPAN_MAX = KP - 2;
+constexpr int MAX_UNITS = 25 + 15 * 15;
 
 struct BwdArgs {
   const float* rec;
@@ -39,52 +44,177 @@ struct BwdArgs {
   int skip_garbage;
 };
 
+struct BRun {
+  int start, len, tmin, span;
+};
+
+struct BwdSmem {
+  float4 seg[S];  // q, frac, T0 (int bits), unused
+  int ep[S], bx[S], by[S], idx[S], flags[S];
+  float a[S], b[S], c[S];
+  float wx[5][S], wy[5][S];
+  BRun run[S];
+  int nruns;
+  int next_run;
+  int rows[BWD_WARPS][MAX_UNITS];
+  float dwx[BWD_WARPS][5][32], dwy[BWD_WARPS][5][32];
+  float grad[BWD_WARPS][16];
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-__global__ void __launch_bounds__(BWD_THREADS)
-k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_params_t p) {
-  __shared__ int s_rows[BWD_WARPS][25 + 15 * 15];
-  __shared__ float s_grad[BWD_WARPS][16];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float gacc[LARND_NPARAMS];  // lane 0 only
+// gradient window registers: gr[i] = g[row, tmin + lane + 32 i]; ticks beyond the readout read as zero
+template <int NG>
+__device__ __forceinline__ void load_gwin(float (&gr)[NG], const float* grow, int tmin, int nticks, int lane) {
 #pragma unroll
-  for (int k = 0; k < LARND_NPARAMS; ++k) gacc[k] = 0.0f;
+  for (int i = 0; i < NG; ++i) {
+    const int col = tmin + lane + 32 * i;
+    gr[i] = (col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
+  }
+}
+
+// G[j] = sum_x g[tmin + j + x] R[x] for one response row; result for position j is left in lane j of the return value
+template <int NG>
+__device__ __forceinline__ float correlate(const float (&gr)[NG], const float* rowp, int npos, int L, int lane) {
+  float Gl = 0.0f;
+  const float* p = rowp + 2 + lane;
+  int x0 = lane;
+  for (int j = 0; j < npos; ++j, --p, --x0) {
+    float part = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const bool in = (unsigned)(x0 + 32 * i) < (unsigned)L;
+      const float v = in ? __ldg(p + 32 * i) : 0.0f;
+      part = fmaf(gr[i], v, part);
+    }
+    part = warp_sum(part);
+    if (lane == j) Gl = part;
+  }
+  return Gl;
+}
+
+// per-segment (slow path, runs touching the ends of the readout): lane-partial sums of one (segment, row) pair.
+// Returns through references: G0 = sum gw*v0, G1 = sum gw*v1 for each of NR rows, and the boundary g values.
+template <int NR>
+__device__ __forceinline__ void slow_sums(const float* grow, const float* const (&rows)[NR], int T0, int L, int nticks, int lane,
+                                          float (&G0)[NR], float (&G1)[NR], float& gB, float& gA) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { G0[r] = 0.f; G1[r] = 0.f; }
+  gB = 0.f; gA = 0.f;
+  for (int x = -1 + lane; x <= L; x += 32) {
+    const int col = T0 + x;
+    const bool inb = col >= 1 && col <= nticks - 1;
+    const float gv = inb ? __ldg(grow + col) : 0.0f;
+    const float gw = (col >= 2) ? gv : 0.0f;               // window deposits are valid for ticks 2 .. nticks-1
+    const float gc = (col <= nticks - 2) ? gv : 0.0f;      // boundary deposits are valid for ticks 1 .. nticks-2
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      G0[r] = fmaf(gw, __ldg(rows[r] + x + 2), G0[r]);
+      G1[r] = fmaf(gw, __ldg(rows[r] + x + 1), G1[r]);
+    }
+    if (x == -1) gB = gc;
+    if (x == 0) gA = gc;
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) { G0[r] = warp_sum(G0[r]); G1[r] = warp_sum(G1[r]); }
+  gB = warp_sum(gB);
+  gA = warp_sum(gA);
+}
+
+template <int NG>
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_params_t p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool bad = A.counts[2] != 0;
   const int64_t s_base = (int64_t)blockIdx.x * S;
   const int ns = bad ? 0 : (int)min((int64_t)S, A.n - s_base);
+  const int nb = A.nb, L = A.L, nt = A.nt;
+  const int64_t n = A.n;
+  const int* irec = reinterpret_cast<const int*>(A.rec);
+  // ---- stage the chunk ----------------------------------------------------------------------------------
+  for (int t = threadIdx.x; t < ns; t += BWD_THREADS) {
+    const int64_t s = s_base + t;
+    sm.seg[t] = make_float4(A.rec[(int64_t)LARND_F_Q * n + s], A.rec[(int64_t)LARND_F_FRAC * n + s],
+                            __int_as_float(irec[(int64_t)LARND_I_T0 * n + s]), 0.0f);
+    sm.ep[t] = irec[(int64_t)LARND_I_EP * n + s];
+    sm.bx[t] = irec[(int64_t)LARND_I_BX * n + s];
+    sm.by[t] = irec[(int64_t)LARND_I_BY * n + s];
+    sm.idx[t] = irec[(int64_t)LARND_I_IDX * n + s];
+    sm.flags[t] = irec[(int64_t)LARND_I_FLAGS * n + s];
+    sm.a[t] = A.rec[(int64_t)LARND_F_A * n + s];
+    sm.b[t] = A.rec[(int64_t)LARND_F_B * n + s];
+    sm.c[t] = A.rec[(int64_t)LARND_F_C * n + s];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      sm.wx[k][t] = A.rec[(int64_t)(LARND_F_WX0 + k) * n + s];
+      sm.wy[k][t] = A.rec[(int64_t)(LARND_F_WY0 + k) * n + s];
+    }
+  }
+  __syncthreads();
+  // ---- runs: same key, start ticks within SPAN_MAX, at most 32 segments (one lane per segment) ---------------
+  if (threadIdx.x == 0) {
+    int nr = 0, cur = -1, tmin = 0, tmax = 0;
+    for (int t = 0; t < ns; ++t) {
+      if (!(sm.flags[t] & 1)) continue;  // outside every TPC: q == 0 and dq/dtheta == 0 (mask factor) -> no gradient
+      const int T0 = __float_as_int(sm.seg[t].z);
+      bool fresh = cur < 0;
+      if (!fresh) {
+        const int t0s = sm.run[cur].start;
+        fresh = sm.ep[t] != sm.ep[t0s] || sm.bx[t] != sm.bx[t0s] || sm.by[t] != sm.by[t0s] || sm.idx[t] != sm.idx[t0s] ||
+                max(tmax, T0) - min(tmin, T0) > SPAN_MAX || t - t0s >= 32 ||
+                t != sm.run[cur].start + sm.run[cur].len;  // masked segment in between: keep runs contiguous
+      }
+      if (fresh) {
+        if (cur >= 0) { sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
+        cur = nr++;
+        sm.run[cur].start = t;
+        sm.run[cur].len = 1;
+        tmin = tmax = T0;
+      } else {
+        sm.run[cur].len += 1;
+        tmin = min(tmin, T0);
+        tmax = max(tmax, T0);
+      }
+    }
+    if (cur >= 0) { sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
+    sm.nruns = nr;
+    sm.next_run = 0;
+  }
+  __syncthreads();
+  const int nruns = sm.nruns;
   RowLookup lk = A.lk;
   lk.n_unique = A.counts[0];
   lk.n_neg = A.counts[1];
-  const int nb = A.nb, L = A.L, nt = A.nt;
   const int n_units = 25 + A.P * A.P;
-  const int sym = (LARND_NB_TRAN_BINS - 1) / 2;
-  const int* irec = reinterpret_cast<const int*>(A.rec);
-  const int64_t n = A.n;
-
-  for (int t = wid; t < ns; t += BWD_WARPS) {
-    const int64_t s = s_base + t;
-    const float q = A.rec[(int64_t)LARND_F_Q * n + s];
-    const float f = A.rec[(int64_t)LARND_F_FRAC * n + s];
-    const int T0 = irec[(int64_t)LARND_I_T0 * n + s];
-    const int bx = irec[(int64_t)LARND_I_BX * n + s], by = irec[(int64_t)LARND_I_BY * n + s];
-    const int ep = irec[(int64_t)LARND_I_EP * n + s];
-    const int idx = irec[(int64_t)LARND_I_IDX * n + s];
-    const int flags = irec[(int64_t)LARND_I_FLAGS * n + s];
-    if (!(flags & 1)) continue;  // outside every TPC: q == 0 and d q = 0 (mask factor)
-    const float ca_ = A.rec[(int64_t)LARND_F_A * n + s], cb_ = A.rec[(int64_t)LARND_F_B * n + s],
-                cc_ = A.rec[(int64_t)LARND_F_C * n + s];
-    float wx[5], wy[5];
+  const int sym = 2;
+  float gacc[LARND_NPARAMS];  // per-lane partial parameter gradients
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      wx[k] = A.rec[(int64_t)(LARND_F_WX0 + k) * n + s];
-      wy[k] = A.rec[(int64_t)(LARND_F_WY0 + k) * n + s];
-    }
+  for (int k = 0; k < LARND_NPARAMS; ++k) gacc[k] = 0.0f;
+
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(&sm.next_run, 1);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    if (r >= nruns) break;
+    const BRun R = sm.run[r];
+    const int t0s = R.start;
+    const int tl = t0s + min(lane, R.len - 1);          // this lane's segment (lanes >= len mirror the last one, unused)
+    const bool live = lane < R.len;
+    const float4 sg = sm.seg[tl];
+    const float q = sg.x, f = sg.y, omf = 1.0f - f;
+    const int T0 = __float_as_int(sg.z);
+    const int m = T0 - R.tmin;
+    const int ep = sm.ep[t0s], bx = sm.bx[t0s], by = sm.by[t0s], idx = sm.idx[t0s];
     const int mpx = floordiv_i(bx, nb), mpy = floordiv_i(by, nb);
     const int bxm = bx - mpx * nb, bym = by - mpy * nb;
+    const bool fast = (R.tmin >= 2) && (R.tmin + R.span + L <= A.nticks - 1);
+    const int npos = R.span + 2;
     // ---- target rows of all units (lane-parallel lookups) ---------------------------------------------
     __syncwarp();
     for (int u = lane; u < n_units; u += 32) {
@@ -108,17 +238,20 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
           if (A.skip_garbage && garbage) row = -1;
         }
       }
-      s_rows[wid][u] = row;
+      sm.rows[wid][u] = row;
     }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { sm.dwx[wid][k][lane] = 0.f; sm.dwy[wid][k][lane] = 0.f; }
     __syncwarp();
-    const int ct = nt - L - T0;
-    const int ct1 = min(ct + 1, nt - 1);
-    const bool fast = (T0 >= 2) && (T0 + L <= A.nticks - 1);
-    float dq = 0.f, df = 0.f, da = 0.f, db = 0.f, dc = 0.f;  // lane partials
-    float dw = 0.f;                                           // lanes 0..4: dWx[i]; lanes 5..9: dWy[j]
-    const float omf = 1.0f - f;
+    float dq = 0.f, df = 0.f, da = 0.f, db = 0.f, dc = 0.f;  // per-lane (= per-segment) accumulators
+    const float ca_ = sm.a[tl], cb_ = sm.b[tl], cc_ = sm.c[tl];
+    // boundary-correction tables are read at ct(m) = nt - L - (tmin + lane) by lane m
+    int ctl = nt - L - (R.tmin + lane);
+    ctl = max(0, min(ctl, nt - 1));
+    const int ctl1 = min(ctl + 1, nt - 1);
+
     for (int u = 0; u < n_units; ++u) {
-      const int row = s_rows[wid][u];
+      const int row = sm.rows[wid][u];
       if (row < 0) continue;
       const float* grow = A.g + (int64_t)row * A.g_stride;
       if (u >= 25) {
@@ -128,24 +261,36 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         const int bin = ci * A.ny_lut + cj;
         const float* rowp = A.r0 + (int64_t)bin * A.Lp;
         const float* crow = A.c0 + (int64_t)bin * nt;
-        const float Ca = __ldg(crow + ct), Cb = __ldg(crow + ct1), Cl = __ldg(crow + nt - L);
-        const float D = Cl - (Ca * omf + Cb * f);
-        const float dD = -(Cb - Ca);
-        for (int x = -1 + lane; x <= L; x += 32) {
-          const int col = T0 + x;
-          float gw, gc;
-          if (fast) { gw = gc = __ldg(grow + col); }
-          else {
-            const bool inb = col >= 1 && col <= A.nticks - 1;
-            const float gv = inb ? __ldg(grow + col) : 0.0f;
-            gw = (col >= 2) ? gv : 0.0f;
-            gc = (col <= A.nticks - 2) ? gv : 0.0f;
+        if (fast) {
+          float gr[NG];
+          load_gwin<NG>(gr, grow, R.tmin, A.nticks, lane);
+          const float Gl = correlate<NG>(gr, rowp, npos, L, lane);
+          const float gC = __ldg(grow + R.tmin - 1 + min(lane, npos));       // tick tmin - 1 + lane
+          const float Cav = __ldg(crow + ctl), Cbv = __ldg(crow + ctl1), Cl = __ldg(crow + nt - L);
+          const float G0 = __shfl_sync(0xffffffffu, Gl, m), G1 = __shfl_sync(0xffffffffu, Gl, m + 1);
+          const float gB = __shfl_sync(0xffffffffu, gC, m), gA = __shfl_sync(0xffffffffu, gC, m + 1);
+          const float Ca = __shfl_sync(0xffffffffu, Cav, m), Cb = __shfl_sync(0xffffffffu, Cbv, m);
+          const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
+          const float gm = fmaf(f, gB, omf * gA);
+          dq += fmaf(f, G0, omf * G1) + gm * D;
+          df += q * ((G0 - G1) + (gB - gA) * D + gm * dD);
+        } else {
+          for (int t = 0; t < R.len; ++t) {
+            const float4 s2 = sm.seg[t0s + t];
+            const int T2 = __float_as_int(s2.z);
+            const float f2 = s2.y, o2 = 1.0f - f2;
+            const float* const rows[1] = {rowp};
+            float G0[1], G1[1], gB, gA;
+            slow_sums<1>(grow, rows, T2, L, A.nticks, lane, G0, G1, gB, gA);
+            const int ct = nt - L - T2;
+            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1)), Cl = __ldg(crow + nt - L);
+            const float D = Cl - (Ca * o2 + Cb * f2), dD = -(Cb - Ca);
+            const float gm = fmaf(f2, gB, o2 * gA);
+            if (lane == t) {
+              dq += fmaf(f2, G0[0], o2 * G1[0]) + gm * D;
+              df += s2.x * ((G0[0] - G1[0]) + (gB - gA) * D + gm * dD);
+            }
           }
-          const float v0 = __ldg(rowp + x + 2), v1 = __ldg(rowp + x + 1);
-          const float cD = (x == -1) ? gc * f : ((x == 0) ? gc * omf : 0.0f);   // d/d(q D)
-          const float cDs = (x == -1) ? gc : ((x == 0) ? -gc : 0.0f);           // coefficient of q*D in d/df
-          dq = fmaf(gw, fmaf(f, v0, omf * v1), fmaf(cD, D, dq));
-          df = fmaf(q, fmaf(gw, v0 - v1, fmaf(cDs, D, cD * dD)), df);
         }
       } else {
         const int bi = u / 5, bj = u % 5;
@@ -157,55 +302,67 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         const float* rb = A.rm + (int64_t)(idx * 25 + bin) * A.Lp;
         const float* rc = A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp;
         const float* crow = A.cm + (int64_t)(idx * 25 + bin) * nt;
-        const float Ca = __ldg(crow + ct), Cb = __ldg(crow + ct1), Cl = __ldg(crow + nt - L);
-        const float D = Cl - (Ca * omf + Cb * f);
-        const float dD = -(Cb - Ca);
-        const float w = wx[bi] * wy[bj];
-        const float qb = w * q;
-        float P = 0.f, Sa = 0.f, Sb = 0.f, Sc = 0.f, Fd = 0.f;
-        for (int x = -1 + lane; x <= L; x += 32) {
-          const int col = T0 + x;
-          float gw, gc;
-          if (fast) { gw = gc = __ldg(grow + col); }
-          else {
-            const bool inb = col >= 1 && col <= A.nticks - 1;
-            const float gv = inb ? __ldg(grow + col) : 0.0f;
-            gw = (col >= 2) ? gv : 0.0f;
-            gc = (col <= A.nticks - 2) ? gv : 0.0f;
+        const float wxv = sm.wx[bi][tl], wyv = sm.wy[bj][tl];
+        const float w = wxv * wyv;
+        if (fast) {
+          float gr[NG];
+          load_gwin<NG>(gr, grow, R.tmin, A.nticks, lane);
+          const float Gla = correlate<NG>(gr, ra, npos, L, lane);
+          const float Glb = correlate<NG>(gr, rb, npos, L, lane);
+          const float Glc = correlate<NG>(gr, rc, npos, L, lane);
+          const float gC = __ldg(grow + R.tmin - 1 + min(lane, npos));
+          const float Cav = __ldg(crow + ctl), Cbv = __ldg(crow + ctl1), Cl = __ldg(crow + nt - L);
+          const float a0 = __shfl_sync(0xffffffffu, Gla, m), a1 = __shfl_sync(0xffffffffu, Gla, m + 1);
+          const float b0 = __shfl_sync(0xffffffffu, Glb, m), b1 = __shfl_sync(0xffffffffu, Glb, m + 1);
+          const float c0v = __shfl_sync(0xffffffffu, Glc, m), c1v = __shfl_sync(0xffffffffu, Glc, m + 1);
+          const float gB = __shfl_sync(0xffffffffu, gC, m), gA = __shfl_sync(0xffffffffu, gC, m + 1);
+          const float Ca = __shfl_sync(0xffffffffu, Cav, m), Cb = __shfl_sync(0xffffffffu, Cbv, m);
+          const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
+          const float gm = fmaf(f, gB, omf * gA);
+          const float Sa = fmaf(f, a0, omf * a1), Sb = fmaf(f, b0, omf * b1), Sc = fmaf(f, c0v, omf * c1v);
+          const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
+          const float Fd = fmaf(ca_, a0 - a1, fmaf(cb_, b0 - b1, cc_ * (c0v - c1v))) + (gB - gA) * D + gm * dD;
+          const float qb = w * q;
+          dq = fmaf(w, Pv, dq);
+          df = fmaf(qb, Fd, df);
+          da = fmaf(qb, Sa, da);
+          db = fmaf(qb, Sb, db);
+          dc = fmaf(qb, Sc, dc);
+          sm.dwx[wid][bi][lane] += wyv * q * Pv;
+          sm.dwy[wid][bj][lane] += wxv * q * Pv;
+        } else {
+          for (int t = 0; t < R.len; ++t) {
+            const float4 s2 = sm.seg[t0s + t];
+            const int T2 = __float_as_int(s2.z);
+            const float f2 = s2.y, o2 = 1.0f - f2;
+            const float* const rows[3] = {ra, rb, rc};
+            float G0[3], G1[3], gB, gA;
+            slow_sums<3>(grow, rows, T2, L, A.nticks, lane, G0, G1, gB, gA);
+            const int ct = nt - L - T2;
+            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1)), Cl = __ldg(crow + nt - L);
+            const float D = Cl - (Ca * o2 + Cb * f2), dD = -(Cb - Ca);
+            const float gm = fmaf(f2, gB, o2 * gA);
+            if (lane == t) {
+              const float Sa = fmaf(f2, G0[0], o2 * G1[0]), Sb = fmaf(f2, G0[1], o2 * G1[1]), Sc = fmaf(f2, G0[2], o2 * G1[2]);
+              const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
+              const float Fd = fmaf(ca_, G0[0] - G1[0], fmaf(cb_, G0[1] - G1[1], cc_ * (G0[2] - G1[2]))) + (gB - gA) * D + gm * dD;
+              const float qb = w * q;
+              dq = fmaf(w, Pv, dq);
+              df = fmaf(qb, Fd, df);
+              da = fmaf(qb, Sa, da);
+              db = fmaf(qb, Sb, db);
+              dc = fmaf(qb, Sc, dc);
+              sm.dwx[wid][bi][lane] += wyv * q * Pv;
+              sm.dwy[wid][bj][lane] += wxv * q * Pv;
+            }
           }
-          const float a0 = __ldg(ra + x + 2), a1 = __ldg(ra + x + 1);
-          const float b0 = __ldg(rb + x + 2), b1 = __ldg(rb + x + 1);
-          const float c0v = __ldg(rc + x + 2), c1v = __ldg(rc + x + 1);
-          const float ta = fmaf(f, a0, omf * a1), tb = fmaf(f, b0, omf * b1), tc = fmaf(f, c0v, omf * c1v);
-          const float bl0 = fmaf(ca_, a0, fmaf(cb_, b0, cc_ * c0v));
-          const float bl1 = fmaf(ca_, a1, fmaf(cb_, b1, cc_ * c1v));
-          const float cD = (x == -1) ? gc * f : ((x == 0) ? gc * omf : 0.0f);
-          const float cDs = (x == -1) ? gc : ((x == 0) ? -gc : 0.0f);
-          Sa = fmaf(gw, ta, Sa);
-          Sb = fmaf(gw, tb, Sb);
-          Sc = fmaf(gw, tc, Sc);
-          P = fmaf(gw, fmaf(ca_, ta, fmaf(cb_, tb, cc_ * tc)), fmaf(cD, D, P));
-          Fd = fmaf(gw, bl0 - bl1, fmaf(cDs, D, fmaf(cD, dD, Fd)));
         }
-        da = fmaf(qb, Sa, da);
-        db = fmaf(qb, Sb, db);
-        dc = fmaf(qb, Sc, dc);
-        df = fmaf(qb, Fd, df);
-        dq = fmaf(w, P, dq);
-        const float Pt = warp_sum(P);
-        if (lane == bi) dw = fmaf(wy[bj] * q, Pt, dw);
-        if (lane == 5 + bj) dw = fmaf(wx[bi] * q, Pt, dw);
       }
     }
-    dq = warp_sum(dq); df = warp_sum(df); da = warp_sum(da); db = warp_sum(db); dc = warp_sum(dc);
-    float gwx[5], gwy[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      gwx[k] = __shfl_sync(0xffffffffu, dw, k);
-      gwy[k] = __shfl_sync(0xffffffffu, dw, 5 + k);
-    }
-    if (lane == 0) {
-      // ---- K1b: chain rule through the per-segment preparation ---------------------------------------
+    // ---- K1b: chain rule through the per-segment preparation, one lane per segment ---------------------------
+    if (live) {
+      const int64_t s = s_base + tl;
+      const int flags = sm.flags[tl];
       const float sl = A.rec[(int64_t)LARND_F_SL * n + s];
       const float sT = A.rec[(int64_t)LARND_F_ST * n + s];
       const float td = A.rec[(int64_t)LARND_F_TD * n + s];
@@ -229,7 +386,8 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         for (int k = 1; k < 5; ++k) {
           const float ux = (p.tran_bin_edges[k] - x0) * inv, uy = (p.tran_bin_edges[k] - y0) * inv;
           const float px_ = two_over_sqrt_pi * expf(-ux * ux), py_ = two_over_sqrt_pi * expf(-uy * uy);
-          const float gEx = 0.5f * (gwx[k - 1] - gwx[k]), gEy = 0.5f * (gwy[k - 1] - gwy[k]);
+          const float gEx = 0.5f * (sm.dwx[wid][k - 1][lane] - sm.dwx[wid][k][lane]);
+          const float gEy = 0.5f * (sm.dwy[wid][k - 1][lane] - sm.dwy[wid][k][lane]);
           g_x0 += gEx * (-px_ * inv);
           g_y0 += gEy * (-py_ * inv);
           g_sT += gEx * (-px_ * ux / sT) + gEy * (-py_ * uy / sT);
@@ -247,8 +405,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
       gacc[LARND_P_SHIFT_X] += -g_x0;
       gacc[LARND_P_SHIFT_Y] += -g_y0;
       gacc[LARND_P_MEV_TO_ELECTRONS] += dq * q / p.MeVToElectrons;
-      // recombination factor: q is linear in it
-      float g_rec = (recb != 0.0f) ? dq * q / recb : 0.0f;
+      float g_rec = (recb != 0.0f) ? dq * q / recb : 0.0f;  // q is linear in the recombination factor
       float g_E = g_v * p.dvdrift_dEfield;
       if (p.recombination_mode == 2) {          // Birks: rec = Ab / (1 + xi), xi = kb dEdx / (E rho)
         const float dn = 1.0f + xi;
@@ -273,15 +430,16 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
       gacc[LARND_P_EFIELD] += g_E;
     }
   }
-  // ---- block reduction -> per-chunk partials ----------------------------------------------------------
-  if (lane == 0) {
+  // ---- warp + block reduction -> per-chunk partials ----------------------------------------------------------
 #pragma unroll
-    for (int k = 0; k < LARND_NPARAMS; ++k) s_grad[wid][k] = gacc[k];
+  for (int k = 0; k < LARND_NPARAMS; ++k) {
+    const float v = warp_sum(gacc[k]);
+    if (lane == 0) sm.grad[wid][k] = v;
   }
   __syncthreads();
   if (threadIdx.x < LARND_NPARAMS) {
     float v = 0.f;
-    for (int w = 0; w < BWD_WARPS; ++w) v += s_grad[w][threadIdx.x];
+    for (int w = 0; w < BWD_WARPS; ++w) v += sm.grad[w][threadIdx.x];
     A.partials[(int64_t)blockIdx.x * 16 + threadIdx.x] = v;
   }
 }
@@ -299,6 +457,21 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const float* __restrict
     __syncthreads();
   }
   if (threadIdx.x == 0) grad[pidx] += (float)sm[0];
+}
+
+template <int NG>
+int launch_bwd(const BwdArgs& A, const larnd_params_t& p, int64_t chunks, cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t smem = sizeof(BwdSmem);
+  if (!attr_done) {
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_backward<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  prof_begin(2, st);
+  k_lut_backward<NG><<<(unsigned)chunks, BWD_THREADS, smem, st>>>(A, p);
+  prof_end(2, st);
+  LARND_LAUNCH_CHECK("k_lut_backward");
+  return LARND_OK;
 }
 
 }  // namespace
@@ -325,10 +498,15 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   A.partials = ws.partials;
   A.skip_garbage = flags & 1;
   const int64_t chunks = (n + S - 1) / S;
-  prof_begin(2, st);
-  k_lut_backward<<<(unsigned)chunks, BWD_THREADS, 0, st>>>(A, p);
-  prof_end(2, st);
-  LARND_LAUNCH_CHECK("k_lut_backward");
+  const int need = lut->L + SPAN_MAX + 2;  // gradient window of a run: ticks tmin .. tmin + span + 1 + L - 1
+  int rc;
+  if (need <= 32 * 2) rc = launch_bwd<2>(A, p, chunks, st);
+  else if (need <= 32 * 4) rc = launch_bwd<4>(A, p, chunks, st);
+  else if (need <= 32 * 6) rc = launch_bwd<6>(A, p, chunks, st);
+  else if (need <= 32 * 10) rc = launch_bwd<10>(A, p, chunks, st);
+  else if (need <= 32 * 16) rc = launch_bwd<16>(A, p, chunks, st);
+  else { larnd_set_error("signal_length %d too large for the backward register window", lut->L); return LARND_E_ARG; }
+  if (rc) return rc;
   k_reduce_partials<<<LARND_NPARAMS, 256, 0, st>>>(ws.partials, chunks, grad_params);
   LARND_LAUNCH_CHECK("k_reduce_partials");
   return LARND_OK;
