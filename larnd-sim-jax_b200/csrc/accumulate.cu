@@ -15,6 +15,8 @@
 // and FMAs into the registers; the window is flushed with coalesced red.global.add.f32 only when the
 // target row or the tick window changes (consecutive segments of a track share both), so global atomics
 // drop from ~2x10^4 per segment to a few hundred per chunk.
+#include <stdlib.h>
+
 #include "larnd_common.cuh"
 
 namespace {
@@ -490,25 +492,34 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.wfs = wfs;
   A.skip_garbage = flags & 1;
   const int64_t chunks = (n + S - 1) / S;
-  const int need = lut->L + 2 + SPAN_MAX + 32;  // run window + room for the tick drift between runs of a chunk
+  // register window = run window (L + 2 + span) + slack for the tick drift between consecutive runs of a track;
+  // more slack = fewer flushes but more predicated-off slots in the inner loop.  LARND_ACC_NS overrides (tuning).
+  int need = lut->L + 2 + SPAN_MAX;  // measured on B200: the tightest window wins (4 slots vs 6 at L=100: -15 % time)
   const size_t smem = sizeof(ChunkSmem);
   static bool attr_done = false;
   if (!attr_done) {
     LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
+  int ns_sel = (need + 31) / 32;
+  if (const char* e = getenv("LARND_ACC_NS")) {
+    int v = atoi(e);
+    if (32 * v >= lut->L + 2 + SPAN_MAX) ns_sel = v;
+  }
   prof_begin(1, st);
-  if (need <= 32 * 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
-  else if (need <= 32 * 6) k_lut_accumulate<6><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
-  else if (need <= 32 * 8) k_lut_accumulate<8><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
-  else if (need <= 32 * 12) k_lut_accumulate<12><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
-  else if (need <= 32 * 16) k_lut_accumulate<16><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  if (ns_sel <= 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (ns_sel <= 5) k_lut_accumulate<5><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (ns_sel <= 6) k_lut_accumulate<6><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (ns_sel <= 8) k_lut_accumulate<8><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (ns_sel <= 12) k_lut_accumulate<12><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
+  else if (ns_sel <= 16) k_lut_accumulate<16><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
   else {
-    larnd_set_error("signal_length %d too large for the register window (max %d)", lut->L, 32 * 16 - 34);
+    larnd_set_error("signal_length %d too large for the register window (max %d)", lut->L, 32 * 16 - 2 - SPAN_MAX);
     return LARND_E_ARG;
   }
   prof_end(1, st);
