@@ -17,21 +17,34 @@ def rbf_kernel(x, y, sigma):
     return torch.exp(-d2 / (2 * sigma ** 2))
 
 
-def mmd(x, y, px, py, sigma):
-    kxx = (rbf_kernel(x, x, sigma) * px[:, None] * px[None, :]).sum()
-    kyy = (rbf_kernel(y, y, sigma) * py[:, None] * py[None, :]).sum()
-    kxy = (rbf_kernel(x, y, sigma) * px[:, None] * py[None, :]).sum()
-    sx, sy = px.sum(), py.sum()
+def _kernel_sum(x, y, px, py, sigma, block=4096):
+    """sum_ij K(x_i, y_j) px_i py_j, blocked over rows so that large hit lists do not materialise an N x M matrix."""
+    tot = x.new_zeros(())
+    for i in range(0, x.shape[0], block):
+        tot = tot + (rbf_kernel(x[i:i + block], y, sigma) * px[i:i + block, None] * py[None, :]).sum()
+    return tot
+
+
+def mmd(x, y, px, py, sigma, reduce=None):
+    """Weighted MMD^2.  ``reduce``: optional differentiable sum over ranks applied to the five sums (events never
+    interact across ranks: the event*1e5 offset puts them > 1e5 apart), see parallel.allreduce_sum_differentiable."""
+    sums = torch.stack([_kernel_sum(x, x, px, px, sigma), _kernel_sum(y, y, py, py, sigma), _kernel_sum(x, y, px, py, sigma),
+                        px.sum(), py.sum()])
+    if reduce is not None:
+        sums = reduce(sums)
+    kxx, kyy, kxy, sx, sy = sums
     return kxx / sx ** 2 + kyy / sy ** 2 - 2 * kxy / (sx * sy)
 
 
 def mse_adc(params, Q, x, y, z, ticks, hit_prob, event, ref_Q, ref_x, ref_y, ref_z, ref_ticks, ref_hit_prob, ref_event,
-            sigma=1, lambda_Q=1):
+            sigma=1, lambda_Q=1, reduce=None):
     w_ref, w = ref_Q * ref_hit_prob, Q * hit_prob
     ref_st = torch.stack((ref_x + ref_event * 1e5, ref_y, ref_z), dim=-1)
     st = torch.stack((x + event * 1e5, y, z), dim=-1)
-    mmd_term = mmd(st, ref_st, w, w_ref, sigma)
+    mmd_term = mmd(st, ref_st, w, w_ref, sigma, reduce)
     tot_ref, tot = w_ref.sum(), w.sum()
+    if reduce is not None:
+        tot_ref, tot = reduce(torch.stack([tot_ref, tot]))
     charge_loss = ((tot - tot_ref) / (tot_ref + 1e-6)) ** 2
     aux = {"charge_loss": charge_loss, "mmd_loss_term": mmd_term, "Q": Q, "ref_Q": ref_Q, "ref_hit_prob": ref_hit_prob,
            "hit_prob": hit_prob}

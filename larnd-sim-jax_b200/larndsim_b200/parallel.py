@@ -66,3 +66,23 @@ def allgather(t):
 def scan_points_for_rank(n_points, rank, world_size):
     """Round-robin assignment of likelihood-scan grid points to ranks."""
     return list(range(rank, n_points, world_size))
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """y = sum over ranks of x.  Every rank evaluates the same global loss from y, so the gradient that flows back to the
+    local x is the upstream gradient itself; the parameter gradients of the ranks are then summed by the caller
+    (allreduce_sum_) — the two-phase scheme of SURVEY.md §8e for losses normalised by global sums."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = x.clone()
+        allreduce_sum_(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def allreduce_sum_differentiable(x):
+    return _AllReduceSum.apply(x)

@@ -368,3 +368,22 @@ def test_full_fixture_batch_and_size_independent_properties(torch_dev):
         for p, w in zip(part.unique_pixels.cpu().numpy(), part.wfs_full.cpu().numpy()):
             if p >= 0:
                 _check_wfs(w[None, 1:], tot[int(p)][None, 1:])
+
+
+def test_fit_and_scan_drivers(torch_dev):
+    """The reference's convergence criterion (tests/test_fit_convergence.py:21-45): no NaN and the mean of the last 5
+    losses is below the mean of the first 5; plus a 3x3 likelihood scan whose minimum sits at the nominal point."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(cm.ROOT, "examples"))
+    import fit_demo
+    import scan_2d
+    hist, target = fit_demo.run_fit(("Ab", "lifetime"), iterations=14, n_segments=12000, lr=0.03, device=torch_dev, verbose=False)
+    losses = np.array([h[0] for h in hist])
+    assert np.isfinite(losses).all() and losses[-5:].mean() < losses[:5].mean()
+    theta0, theta1 = hist[0][1], hist[-1][1]
+    tgt = np.array([target["Ab"], target["lifetime"]])
+    assert np.abs(theta1 - tgt).sum() < np.abs(theta0 - tgt).sum()          # moved towards the target parameters
+    a1, a2, out = scan_2d.run_scan("Ab", "lifetime", grid=3, n_segments=8000, device=torch_dev)
+    assert np.isfinite(out).all()
+    assert np.unravel_index(np.argmin(out[..., 0]), (3, 3))[0] in (0, 1)        # nominal Ab = 0.8 lies between grid points 0 and 1

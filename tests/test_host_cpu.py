@@ -201,3 +201,49 @@ def test_event_sharding_and_collectives_world_size_2(tmp_path):
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+_WORKER_AR = r"""
+import os, sys
+sys.path.insert(0, os.path.join(sys.argv[1], "larnd-sim-jax_b200"))
+import torch, torch.distributed as dist
+from larndsim_b200 import parallel
+from larndsim_b200.losses import mse_adc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"], rank=rank, world_size=world)
+torch.manual_seed(0)
+n = 40
+ev = torch.arange(n) // 10                      # 4 events, 2 per rank
+Q0 = torch.rand(n, dtype=torch.float64) + 0.5
+pos = torch.rand(n, 3, dtype=torch.float64) * 3
+refQ = Q0 * 1.1; refpos = pos + 0.05
+def loss_of(scale, sel, reduce):
+    Q = Q0[sel] * scale
+    l, _ = mse_adc(None, Q, pos[sel, 0], pos[sel, 1], pos[sel, 2], None, torch.ones_like(Q), ev[sel].double(),
+                   refQ[sel], refpos[sel, 0], refpos[sel, 1], refpos[sel, 2], None, torch.ones_like(Q), ev[sel].double(), reduce=reduce)
+    return l
+s_all = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+full = loss_of(s_all, slice(None), None); full.backward()
+s_loc = torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+sel = (ev // 2) == rank
+part = loss_of(s_loc, sel, parallel.allreduce_sum_differentiable); part.backward()
+g = s_loc.grad.clone(); parallel.allreduce_sum_(g)
+assert abs(float(part) - float(full)) < 1e-12, (float(part), float(full))
+assert abs(float(g) - float(s_all.grad)) < 1e-10, (float(g), float(s_all.grad))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_loss_matches_single_process(tmp_path):
+    """Two-phase reduction of mse_adc: loss and gradient from 2 event shards == single process."""
+    script = tmp_path / "worker_ar.py"
+    script.write_text(_WORKER_AR)
+    port = 31500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out
