@@ -28,7 +28,7 @@ NOMINAL = dict(Ab=0.8, kb=0.0486, eField=0.5, lifetime=2.2e3, long_diff=4.0e-6, 
 TARGET = dict(Ab=0.83, kb=0.055, eField=0.52, lifetime=1.8e3, long_diff=5.0e-6, tran_diff=10e-6)
 
 
-def run_fit(names=("Ab", "kb", "lifetime"), iterations=30, n_segments=40000, lr=0.02, seed=5, device=None, verbose=True):
+def run_fit(names=("Ab", "eField"), iterations=30, n_segments=40000, lr=0.01, seed=5, device=None, verbose=True):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if device is None:
@@ -77,7 +77,7 @@ def run_fit(names=("Ab", "kb", "lifetime"), iterations=30, n_segments=40000, lr=
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--iterations", type=int, default=30)
-    ap.add_argument("--params", default="Ab,kb,lifetime")
+    ap.add_argument("--params", default="Ab,eField")
     ap.add_argument("--segments", type=int, default=40000)
     a = ap.parse_args()
     run_fit(tuple(a.params.split(",")), a.iterations, a.segments)

@@ -42,7 +42,7 @@ struct AccArgs {
   int skip_garbage;
 };
 
-constexpr int KP = 16;           // tick positions per run (impulse train length)
+constexpr int KP = 8;            // tick positions per run (impulse train length)
 constexpr int SPAN_MAX = KP - 2;  // max (T0max - T0min) inside a run
 
 // A *run* = consecutive segments that share (event, plane, sub-pixel bin, template index) and whose start ticks lie

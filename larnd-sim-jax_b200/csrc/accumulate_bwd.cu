@@ -20,7 +20,7 @@ namespace {
 constexpr int BWD_THREADS = 256;
 constexpr int BWD_WARPS = BWD_THREADS / 32;
 constexpr int S = LARND_CHUNK;
-constexpr int KP = 16;
+constexpr int KP = 8;
 constexpr int SPAN_MAX = KP - 2;
 constexpr int MAX_UNITS = 25 + 15 * 15;
 

@@ -378,11 +378,11 @@ def test_fit_and_scan_drivers(torch_dev):
     sys.path.insert(0, os.path.join(cm.ROOT, "examples"))
     import fit_demo
     import scan_2d
-    hist, target = fit_demo.run_fit(("Ab", "lifetime"), iterations=14, n_segments=12000, lr=0.03, device=torch_dev, verbose=False)
+    hist, target = fit_demo.run_fit(("Ab", "eField"), iterations=16, n_segments=12000, lr=0.01, device=torch_dev, verbose=False)
     losses = np.array([h[0] for h in hist])
     assert np.isfinite(losses).all() and losses[-5:].mean() < losses[:5].mean()
     theta0, theta1 = hist[0][1], hist[-1][1]
-    tgt = np.array([target["Ab"], target["lifetime"]])
+    tgt = np.array([target["Ab"], target["eField"]])
     assert np.abs(theta1 - tgt).sum() < np.abs(theta0 - tgt).sum()          # moved towards the target parameters
     a1, a2, out = scan_2d.run_scan("Ab", "lifetime", grid=3, n_segments=8000, device=torch_dev)
     assert np.isfinite(out).all()
