@@ -31,6 +31,8 @@ struct AccArgs {
   const float* rm;
   const float* c0;
   const float* cm;
+  const float* sr;  // neighbourhood sums of r0 / c0 per in-pixel bin (larnd_common.cuh)
+  const float* sc;
   int nt, L, Lp, ny_lut, nx_lut;
   int nticks;
   int nb, half2;  // bins per pixel; 2*(nb/2) - 1
@@ -175,9 +177,9 @@ __device__ __forceinline__ float boundary_delta(const float* crow, int ct, int n
 // Lane j holds h[NR][j]; it is broadcast with a shuffle.  Each lane walks one pointer per response row; the slot
 // offset is an immediate (32*s floats) and lanes outside the response window are predicated off, so the inner
 // loop is one compare + NR loads + NR FMAs per 32 ticks.
-template <int NS, int NR>
+template <int NS, int NR, bool DUAL = false>
 __device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmin, int npos, const float (&h)[NR],
-                                            const float* const (&rows)[NR], int L, int lane) {
+                                            const float* const (&rows)[NR], int L, int lane, float* accg = nullptr) {
   // x = col - (tmin + j) for slot 0 of this lane; response sample k lives at row[k + 2]
   int x0 = tbase + lane - tmin;
   const float* p[NR];
@@ -199,6 +201,7 @@ __device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmi
         for (int r = 0; r < NR; ++r) {
           const float v = in ? __ldg(p[r] + 32 * s) : 0.0f;
           acc[s] = fmaf(hj[r], v, acc[s]);
+          if (DUAL) accg[s] = fmaf(-hj[r], v, accg[s]);  // the same deposit leaves waveform row 0 (see the garbage-sum unit)
         }
       }
     }
@@ -208,8 +211,8 @@ __device__ __forceinline__ void apply_train(float (&acc)[NS], int tbase, int tmi
 }
 
 // Adds the merged boundary corrections of a run: lane j holds E_j, which belongs to tick tmin - 1 + j.
-template <int NS>
-__device__ __forceinline__ void add_corrections(float (&acc)[NS], int tbase, int tmin, float E, int lane) {
+template <int NS, bool DUAL = false>
+__device__ __forceinline__ void add_corrections(float (&acc)[NS], int tbase, int tmin, float E, int lane, float* accg = nullptr) {
   const int off = tmin - 1 - tbase;           // >= 0 by construction of the window
   const int rot = off & 31, s0 = off >> 5;
   const float Er = __shfl_sync(0xffffffffu, E, (lane - rot) & 31);  // lane l now holds E_{(l - rot) mod 32}
@@ -219,7 +222,11 @@ __device__ __forceinline__ void add_corrections(float (&acc)[NS], int tbase, int
   for (int s = 0; s < NS; ++s) {
     if (s == s0) {            // warp-uniform; the window construction guarantees s0 + 1 < NS whenever hi != 0
       acc[s] += lo;
-      if (s + 1 < NS) acc[s + 1] += hi;
+      if (DUAL) accg[s] -= lo;
+      if (s + 1 < NS) {
+        acc[s + 1] += hi;
+        if (DUAL) accg[s + 1] -= hi;
+      }
     }
   }
 }
@@ -333,12 +340,14 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
   RowLookup lk = A.lk;
   lk.n_unique = A.counts[0];
   lk.n_neg = A.counts[1];
-  const int n_units = 25 + A.P * A.P;
-  float acc[NS];
+  // units: 25 diffusion bins, (2n+1)^2 relative neighbour pixels, and one "garbage-sum" unit (see below)
+  const int n_neigh_units = A.P * A.P;
+  const int n_units = 25 + n_neigh_units + (A.skip_garbage ? 0 : 1);
+  float acc[NS], accg[NS];
 #pragma unroll
-  for (int j = 0; j < NS; ++j) acc[j] = 0.0f;
-  float g0 = 0.0f;
-  bool g0_used = false;
+  for (int j = 0; j < NS; ++j) { acc[j] = 0.0f; accg[j] = 0.0f; }
+  float g0 = 0.0f, g0g = 0.0f;
+  bool g0_used = false, g0g_used = false;
 
   for (;;) {
     int unit = 0;
@@ -348,45 +357,69 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
     int cur_row = -1, tbase = 0;
     int cur_k0 = INT32_MIN, cur_k1 = INT32_MIN;
     if (unit >= 25) {
-      // ---------------- neighbour unit: relative pixel (dx, dy), template 0, full charge --------------
+      // ---------------- neighbour units: template 0, full segment charge (sim_jax.py:197-225,250-261) ----------
+      // A neighbour pixel that is not a main pixel of the batch is routed to waveform row 0 by the reference
+      // (sim_jax.py:724-725); along a track that is ~85 % of the (2n+1)^2 neighbours.  By linearity
+      //     row0 += sum_{all neighbours} h * R_u  -  sum_{neighbours with their own row} h * R_u
+      // so one unit applies the precomputed neighbourhood-sum row (A.sr / A.sc) to row 0, and only the neighbours
+      // that own a row do real work: they add to their row and subtract the same deposit from row 0.
+      const bool sum_unit = unit == 25 + n_neigh_units;
       const int u = unit - 25;
-      const int dx = u / A.P - A.n_neigh, dy = u % A.P - A.n_neigh;
+      const int dx = sum_unit ? 0 : u / A.P - A.n_neigh, dy = sum_unit ? 0 : u % A.P - A.n_neigh;
       const bool centre = (dx == 0 && dy == 0);
+      if (centre && !sum_unit) continue;  // the centre id is overwritten with -999: never matches, lives in row 0 only
+      const bool dual = !sum_unit && !A.skip_garbage;
       for (int r = 0; r < nruns; ++r) {
         const RunInfo R = sm.run[r];
         if (R.ep != cur_k0 || R.pxy != cur_k1) {
           cur_k0 = R.ep; cur_k1 = R.pxy;
-          int row;
-          bool garbage;
-          if (centre) { row = 0; garbage = true; }  // centre id is overwritten with -999 -> never matches -> row 0
-          else {
-            int pid = pixel2id_dev(R.mpx + dx, R.mpy + dy, R.ep, A.nxp, A.nyp);
+          int row = 0;
+          if (!sum_unit) {
+            const int pid = pixel2id_dev(R.mpx + dx, R.mpy + dy, R.ep, A.nxp, A.nyp);
             row = lookup_row(lk, pid);
-            garbage = row < 0 || pid < 0;
-            if (row < 0) row = 0;  // sim_jax.py:724-725
+            if (row <= 0) row = -1;                              // row 0 / not a main pixel: covered by the sum unit
+            else if (A.skip_garbage && pid < 0) row = -1;
           }
-          if (A.skip_garbage && garbage) row = -1;
-          if (row != cur_row) { flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane); cur_row = row; }
+          if (row != cur_row) {
+            flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
+            if (dual) flush_row<NS>(accg, g0g, g0g_used, 0, tbase, A, lane);
+            cur_row = row;
+          }
         }
         if (cur_row < 0) continue;
         const int span = R.span;
         if (R.tmin - 1 < tbase || R.tmin + span + L >= tbase + 32 * NS) {
           flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
+          if (dual) flush_row<NS>(accg, g0g, g0g_used, 0, tbase, A, lane);
           tbase = R.tmin - 1 - (32 * NS - (L + 2 + span)) / 2;
         }
-        const int vx = 2 * R.bxm - A.half2 - 2 * nb * dx;
-        const int vy = 2 * R.bym - A.half2 - 2 * nb * dy;
-        const int bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
-        const float* const rows[1] = {A.r0 + (int64_t)bin * A.Lp};
-        const float* crow = A.c0 + (int64_t)bin * A.nt;
+        const float* rowp;
+        const float* crow;
+        if (sum_unit) {
+          const int sb = R.bxm * nb + R.bym;
+          rowp = A.sr + (int64_t)sb * A.Lp;
+          crow = A.sc + (int64_t)sb * A.nt;
+        } else {
+          const int vx = 2 * R.bxm - A.half2 - 2 * nb * dx;
+          const int vy = 2 * R.bym - A.half2 - 2 * nb * dy;
+          const int bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
+          rowp = A.r0 + (int64_t)bin * A.Lp;
+          crow = A.c0 + (int64_t)bin * A.nt;
+        }
+        const float* const rows[1] = {rowp};
         if (R.fast) {
           const int kk = min(lane, KP - 1);
           const float hl = lane < KP ? sm.rh[r][kk] : 0.f;
           float E = run_correction(crow, R.tmin, A.nt, L, sm.rA1[r][kk], sm.rA2[r][kk], sm.rA3[r][kk], sm.rB1[r][kk], sm.rB3[r][kk], lane);
           if (lane > span + 1) E = 0.f;
           const float h[1] = {hl};
-          apply_train<NS, 1>(acc, tbase, R.tmin, span + 2, h, rows, L, lane);
-          add_corrections<NS>(acc, tbase, R.tmin, E, lane);
+          if (dual) {
+            apply_train<NS, 1, true>(acc, tbase, R.tmin, span + 2, h, rows, L, lane, accg);
+            add_corrections<NS, true>(acc, tbase, R.tmin, E, lane, accg);
+          } else {
+            apply_train<NS, 1>(acc, tbase, R.tmin, span + 2, h, rows, L, lane);
+            add_corrections<NS>(acc, tbase, R.tmin, E, lane);
+          }
         } else {
           // run touches the ends of the readout window: per-segment path with garbage-tick handling
           const float cf[1] = {1.0f};
@@ -397,9 +430,11 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
             const int T0 = __float_as_int(sg.z);
             const float D = boundary_delta(crow, A.nt - L - T0, A.nt, L, f, lane);
             add_contribution<NS, 1>(acc, g0, g0_used, tbase, T0, q * f, q * (1.0f - f), D, rows, cf, A, lane);
+            if (dual) add_contribution<NS, 1>(accg, g0g, g0g_used, tbase, T0, -q * f, -q * (1.0f - f), D, rows, cf, A, lane);
           }
         }
       }
+      if (dual) flush_row<NS>(accg, g0g, g0g_used, 0, tbase, A, lane);
     } else {
       // ---------------- main unit: diffusion bin (i, j), 3-template blend -----------------------------
       const int bi = unit / LARND_NB_TRAN_BINS, bj = unit % LARND_NB_TRAN_BINS;
@@ -478,7 +513,11 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   if (n == 0) return LARND_OK;
   AccArgs A;
   A.rec = ws.rec; A.n = n;
-  A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm;
+  {
+    int rc0 = larnd_lut_ensure_neighbour_sums(const_cast<larnd_lut*>(lut), p.nb_sampling_bins_per_pixel, p.number_pix_neighbors, st);
+    if (rc0) return rc0;
+  }
+  A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm; A.sr = lut->sr; A.sc = lut->sc;
   A.nt = lut->nt; A.L = lut->L; A.Lp = lut->Lp; A.ny_lut = lut->ny; A.nx_lut = lut->nx;
   A.nticks = p.n_ticks;
   A.nb = p.nb_sampling_bins_per_pixel;

@@ -16,7 +16,15 @@ struct larnd_lut {
   float* rm;  // [ntpl][25][Lp]       all templates, collecting bins ci,cj < 5
   float* c0;  // [nx*ny][nt]          running sum of template 0
   float* cm;  // [ntpl][25][nt]       running sum of all templates, collecting bins
+  // Sum of the neighbour rows over the whole (2n+1)^2 neighbourhood for every in-pixel bin (bxm, bym):
+  //   sr[bxm*nb+bym][Lp] = sum_{dx,dy} r0[ci(bxm,dx)][cj(bym,dy)],   sc likewise for c0.
+  // Everything a segment deposits on neighbour pixels that are NOT main pixels lands in waveform row 0
+  // (sim_jax.py:724-725); by linearity that is (sum over all neighbours) - (the few that are main pixels).
+  int sum_nb, sum_n;
+  float* sr;  // [nb*nb][Lp]
+  float* sc;  // [nb*nb][nt]
 };
+int larnd_lut_ensure_neighbour_sums(larnd_lut* lut, int nb, int n, cudaStream_t st);
 
 // Views into the caller-provided workspace.
 struct Workspace {

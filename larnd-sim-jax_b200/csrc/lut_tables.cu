@@ -54,7 +54,41 @@ __global__ void k_cumsum_rows(const float* __restrict__ bank, int nx, int ny, in
   }
 }
 
+// neighbourhood sums (see larnd_common.cuh): one block per in-pixel bin
+__global__ void k_neighbour_sums(const float* __restrict__ r0, const float* __restrict__ c0, int ny, int nt, int Lp, int nb, int n,
+                                 float* __restrict__ sr, float* __restrict__ sc) {
+  const int bxm = blockIdx.x / nb, bym = blockIdx.x % nb;
+  const int half2 = 2 * (nb / 2) - 1;
+  for (int k = threadIdx.x; k < Lp + nt; k += blockDim.x) {
+    float acc = 0.0f;
+    for (int dx = -n; dx <= n; ++dx) {
+      const int ci = abs(2 * bxm - half2 - 2 * nb * dx) >> 1;
+      for (int dy = -n; dy <= n; ++dy) {
+        const int cj = abs(2 * bym - half2 - 2 * nb * dy) >> 1;
+        const int bin = ci * ny + cj;
+        acc += (k < Lp) ? r0[(int64_t)bin * Lp + k] : c0[(int64_t)bin * nt + (k - Lp)];
+      }
+    }
+    if (k < Lp) sr[(int64_t)blockIdx.x * Lp + k] = acc;
+    else sc[(int64_t)blockIdx.x * nt + (k - Lp)] = acc;
+  }
+}
+
 }  // namespace
+
+int larnd_lut_ensure_neighbour_sums(larnd_lut* lut, int nb, int n, cudaStream_t st) {
+  if (lut->sr && lut->sum_nb == nb && lut->sum_n == n) return LARND_OK;
+  if (lut->sr && lut->sum_nb != nb) { cudaFree(lut->sr); cudaFree(lut->sc); lut->sr = lut->sc = nullptr; }
+  if (!lut->sr) {
+    LARND_CUDA(cudaMalloc(&lut->sr, (size_t)nb * nb * lut->Lp * sizeof(float)));
+    LARND_CUDA(cudaMalloc(&lut->sc, (size_t)nb * nb * lut->nt * sizeof(float)));
+  }
+  k_neighbour_sums<<<nb * nb, 256, 0, st>>>(lut->r0, lut->c0, lut->ny, lut->nt, lut->Lp, nb, n, lut->sr, lut->sc);
+  LARND_LAUNCH_CHECK("k_neighbour_sums");
+  lut->sum_nb = nb;
+  lut->sum_n = n;
+  return LARND_OK;
+}
 
 extern "C" int larnd_lut_create(const float* bank_d, int n_templates, int nx, int ny, int nt, int signal_length,
                                 void* stream, larnd_lut_t** out) {
@@ -70,6 +104,8 @@ extern "C" int larnd_lut_create(const float* bank_d, int n_templates, int nx, in
   lut->Lp = signal_length + LARND_OFF_PAD;
   size_t n0 = (size_t)nx * ny, nm = (size_t)n_templates * 25;
   lut->r0 = lut->rm = lut->c0 = lut->cm = nullptr;
+  lut->sr = lut->sc = nullptr;
+  lut->sum_nb = lut->sum_n = -1;
   int rc = LARND_OK;
   auto fail = [&](int code) { larnd_lut_destroy(lut); return code; };
   if ((rc = larnd_check_cuda(cudaMalloc(&lut->r0, n0 * lut->Lp * sizeof(float)), "cudaMalloc r0"))) return fail(rc);
@@ -91,5 +127,7 @@ extern "C" void larnd_lut_destroy(larnd_lut_t* lut) {
   cudaFree(lut->rm);
   cudaFree(lut->c0);
   cudaFree(lut->cm);
+  cudaFree(lut->sr);
+  cudaFree(lut->sc);
   delete lut;
 }
