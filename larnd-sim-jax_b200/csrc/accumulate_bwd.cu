@@ -59,6 +59,7 @@ struct BwdSmem {
   int rows[BWD_WARPS][MAX_UNITS];
   float dwx[BWD_WARPS][5][32], dwy[BWD_WARPS][5][32];
   float grad[BWD_WARPS][16];
+  float gl[LARND_NPARAMS][BWD_THREADS];  // per-thread parameter-gradient accumulators (kept out of the register file)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -126,7 +127,7 @@ __device__ __forceinline__ void slow_sums(const float* grow, const float* const 
 }
 
 template <int NG>
-__global__ void __launch_bounds__(BWD_THREADS, 2)
+__global__ void __launch_bounds__(BWD_THREADS, 3)
 k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_params_t p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
@@ -193,9 +194,9 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
   lk.n_neg = A.counts[1];
   const int n_units = 25 + A.P * A.P;
   const int sym = 2;
-  float gacc[LARND_NPARAMS];  // per-lane partial parameter gradients
 #pragma unroll
-  for (int k = 0; k < LARND_NPARAMS; ++k) gacc[k] = 0.0f;
+  for (int k = 0; k < LARND_NPARAMS; ++k) sm.gl[k][threadIdx.x] = 0.0f;
+#define GACC(k) sm.gl[k][threadIdx.x]
 
   for (;;) {
     int r = 0;
@@ -398,44 +399,45 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
       const float g_ft = df;
       const float g_td = dq * (-q / tau) + (td > 0.f ? (g_sl * sl + g_sT * sT) / (2.0f * td) : 0.f);
       const float g_v = g_td * (-td / v) + g_ft * (-ft / v) + g_sl * (-sl / v);
-      gacc[LARND_P_SHIFT_Z] += g_td * (-sgn_a / v) + g_ft * (-sgn_c / (v * ts));
-      gacc[LARND_P_LIFETIME] += dq * q * td / (tau * tau);
-      if (p.long_diff > 0.f) gacc[LARND_P_LONG_DIFF] += g_sl * sl / (2.0f * p.long_diff);
-      if (p.tran_diff > 0.f) gacc[LARND_P_TRAN_DIFF] += g_sT * sT / (2.0f * p.tran_diff);
-      gacc[LARND_P_SHIFT_X] += -g_x0;
-      gacc[LARND_P_SHIFT_Y] += -g_y0;
-      gacc[LARND_P_MEV_TO_ELECTRONS] += dq * q / p.MeVToElectrons;
+      GACC(LARND_P_SHIFT_Z) += g_td * (-sgn_a / v) + g_ft * (-sgn_c / (v * ts));
+      GACC(LARND_P_LIFETIME) += dq * q * td / (tau * tau);
+      if (p.long_diff > 0.f) GACC(LARND_P_LONG_DIFF) += g_sl * sl / (2.0f * p.long_diff);
+      if (p.tran_diff > 0.f) GACC(LARND_P_TRAN_DIFF) += g_sT * sT / (2.0f * p.tran_diff);
+      GACC(LARND_P_SHIFT_X) += -g_x0;
+      GACC(LARND_P_SHIFT_Y) += -g_y0;
+      GACC(LARND_P_MEV_TO_ELECTRONS) += dq * q / p.MeVToElectrons;
       float g_rec = (recb != 0.0f) ? dq * q / recb : 0.0f;  // q is linear in the recombination factor
       float g_E = g_v * p.dvdrift_dEfield;
       if (p.recombination_mode == 2) {          // Birks: rec = Ab / (1 + xi), xi = kb dEdx / (E rho)
         const float dn = 1.0f + xi;
-        gacc[LARND_P_AB] += g_rec * recb / p.Ab;
+        GACC(LARND_P_AB) += g_rec * recb / p.Ab;
         const float g_xi = g_rec * (-recb / dn);
-        if (p.kb != 0.f) gacc[LARND_P_KB] += g_xi * xi / p.kb;
+        if (p.kb != 0.f) GACC(LARND_P_KB) += g_xi * xi / p.kb;
         g_E += g_xi * (-xi / p.eField);
-        gacc[LARND_P_LAR_DENSITY] += g_xi * (-xi / p.lArDensity);
+        GACC(LARND_P_LAR_DENSITY) += g_xi * (-xi / p.lArDensity);
       } else if (recb > 0.0f) {                 // Box / Ellipsoid: rec = log(alpha + xi) / (xi [+1e-10])
         const float den = (p.recombination_mode == 3) ? xi + 1e-10f : xi;
         const float lg = logf(p.alpha + xi);
-        gacc[LARND_P_ALPHA] += g_rec / ((p.alpha + xi) * den);
+        GACC(LARND_P_ALPHA) += g_rec / ((p.alpha + xi) * den);
         const float g_xi = g_rec * (1.0f / ((p.alpha + xi) * den) - lg / (den * den));
-        gacc[LARND_P_BETA] += g_xi * xi / p.beta;
+        GACC(LARND_P_BETA) += g_xi * xi / p.beta;
         g_E += g_xi * (-xi / p.eField);
-        gacc[LARND_P_LAR_DENSITY] += g_xi * (-xi / p.lArDensity);
+        GACC(LARND_P_LAR_DENSITY) += g_xi * (-xi / p.lArDensity);
         if (p.recombination_mode == 3) {
           const float gg = 1.0f - cos2 + p.inv_R2 * cos2;   // b_phi = beta / sqrt(gg)
-          gacc[LARND_P_R_PARAM] += g_xi * xi * cos2 / (p.R_param * p.R_param * p.R_param * gg);
+          GACC(LARND_P_R_PARAM) += g_xi * xi * cos2 / (p.R_param * p.R_param * p.R_param * gg);
         }
       }
-      gacc[LARND_P_EFIELD] += g_E;
+      GACC(LARND_P_EFIELD) += g_E;
     }
   }
   // ---- warp + block reduction -> per-chunk partials ----------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < LARND_NPARAMS; ++k) {
-    const float v = warp_sum(gacc[k]);
+    const float v = warp_sum(GACC(k));
     if (lane == 0) sm.grad[wid][k] = v;
   }
+#undef GACC
   __syncthreads();
   if (threadIdx.x < LARND_NPARAMS) {
     float v = 0.f;
