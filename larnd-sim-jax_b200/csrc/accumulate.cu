@@ -74,6 +74,9 @@ struct ChunkSmem {
   float4 po[S];    // q(1-f) a, q(1-f) b, q(1-f) c, q(1-f)    (deposit at T0+1)
   float4 pm[S];    // q(1-f)^2, q f(1-f), q f^2, unused       (correction moments A2, A3, B3)
   float rh[S][KP], rA1[S][KP], rA2[S][KP], rA3[S][KP], rB1[S][KP], rB3[S][KP];  // neighbour impulse train + moments
+  // transverse-diffusion bins that fall on the same pixel with the same response row are merged ("groups"); per
+  // in-pixel bin index b: number of groups, pixel offset + 1, response index and member mask of each group
+  unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   int nruns;
   int next_unit;
 };
@@ -287,6 +290,21 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
       sm.wy[k][t] = rec[(int64_t)(LARND_F_WY0 + k) * n + s];
     }
   }
+  if (threadIdx.x < nb && threadIdx.x < 16) {
+    const int bq = threadIdx.x;
+    int ng = 0;
+    for (int i = 0; i < LARND_NB_TRAN_BINS; ++i) {
+      int qb = bq + i - (LARND_NB_TRAN_BINS - 1) / 2, ox = 0;
+      if (qb < 0) { qb += nb; ox = -1; } else if (qb >= nb) { qb -= nb; ox = 1; }
+      const int ci = abs(2 * qb - A.half2) >> 1;
+      int g = -1;
+      for (int k = 0; k < ng; ++k)
+        if (sm.g_ox[bq][k] == ox + 1 && sm.g_ci[bq][k] == ci) g = k;
+      if (g < 0) { g = ng++; sm.g_ox[bq][g] = ox + 1; sm.g_ci[bq][g] = ci; sm.g_mask[bq][g] = 0; }
+      sm.g_mask[bq][g] |= 1 << i;
+    }
+    sm.g_n[bq] = ng;
+  }
   __syncthreads();
   // ---- cut the chunk into runs (serial, ~ns steps; negligible next to the accumulate work) ------------------
   if (threadIdx.x == 0) {
@@ -326,6 +344,19 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
     R.fast = (R.tmin >= 2) && (R.tmin + R.span + L <= A.nticks - 1);
     for (int k = 0; k < KP; ++k) { sm.rh[r][k] = 0.f; sm.rA1[r][k] = 0.f; sm.rA2[r][k] = 0.f; sm.rA3[r][k] = 0.f; sm.rB1[r][k] = 0.f; sm.rB3[r][k] = 0.f; }
     for (int t = t0s; t < t0s + R.len; ++t) {
+      // merge the 5 per-axis diffusion weights into per-group weights (in place: slot g <- sum of the group's members)
+      float vx[5], vy[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) { vx[k] = sm.wx[k][t]; vy[k] = sm.wy[k][t]; }
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {
+        const int mx = g < sm.g_n[R.bxm] ? sm.g_mask[R.bxm][g] : 0, my = g < sm.g_n[R.bym] ? sm.g_mask[R.bym][g] : 0;
+        float sx = 0.f, sy = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { sx += (mx >> k & 1) ? vx[k] : 0.f; sy += (my >> k & 1) ? vy[k] : 0.f; }
+        sm.wx[g][t] = sx;
+        sm.wy[g][t] = sy;
+      }
       const float4 sg = sm.seg[t];
       const float q = sg.x, f = sg.y, omf = 1.0f - f;
       const int m = __float_as_int(sg.z) - R.tmin;
@@ -436,16 +467,13 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
       }
       if (dual) flush_row<NS>(accg, g0g, g0g_used, 0, tbase, A, lane);
     } else {
-      // ---------------- main unit: diffusion bin (i, j), 3-template blend -----------------------------
-      const int bi = unit / LARND_NB_TRAN_BINS, bj = unit % LARND_NB_TRAN_BINS;
-      const int sym = (LARND_NB_TRAN_BINS - 1) / 2;
+      // ---------------- main unit: group (gx, gy) of merged diffusion bins, 3-template blend -----------
+      // the 25 bins of the stencil collapse to n_gx * n_gy (9 .. 25, 19 on average) distinct (pixel, response row) pairs
+      const int bi = unit / LARND_NB_TRAN_BINS, bj = unit % LARND_NB_TRAN_BINS;  // group indices
       for (int r = 0; r < nruns; ++r) {
         const RunInfo R = sm.run[r];
-        // bin (i,j) of the 5x5 diffusion stencil: in-pixel bin index and the pixel it falls on (at most one pixel away)
-        int bxq = R.bxm + bi - sym, byq = R.bym + bj - sym;
-        int px = R.mpx, py = R.mpy;
-        if (bxq < 0) { bxq += nb; --px; } else if (bxq >= nb) { bxq -= nb; ++px; }
-        if (byq < 0) { byq += nb; --py; } else if (byq >= nb) { byq -= nb; ++py; }
+        if (bi >= sm.g_n[R.bxm] || bj >= sm.g_n[R.bym]) continue;   // this run has fewer groups
+        const int px = R.mpx + (int)sm.g_ox[R.bxm][bi] - 1, py = R.mpy + (int)sm.g_ox[R.bym][bj] - 1;
         const int k1 = (px & 0xffff) | (py << 16);
         if (R.ep != cur_k0 || k1 != cur_k1) {
           cur_k0 = R.ep; cur_k1 = k1;
@@ -460,8 +488,7 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
           flush_row<NS>(acc, g0, g0_used, cur_row, tbase, A, lane);
           tbase = R.tmin - 1 - (32 * NS - (L + 2 + span)) / 2;
         }
-        const int cix = abs(2 * bxq - A.half2) >> 1;
-        const int ciy = abs(2 * byq - A.half2) >> 1;
+        const int cix = sm.g_ci[R.bxm][bi], ciy = sm.g_ci[R.bym][bj];
         const int idx = R.idx;
         const int bin = cix * 5 + ciy;
         const float* const rows[3] = {A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp,

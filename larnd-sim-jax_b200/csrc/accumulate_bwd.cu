@@ -22,7 +22,6 @@ constexpr int BWD_WARPS = BWD_THREADS / 32;
 constexpr int S = LARND_CHUNK;
 constexpr int KP = 8;
 constexpr int SPAN_MAX = KP - 2;
-constexpr int MAX_UNITS = 25 + 15 * 15;
 
 struct BwdArgs {
   const float* rec;
@@ -44,8 +43,13 @@ struct BwdArgs {
   int skip_garbage;
 };
 
+constexpr int MAXK = 16;        // distinct main pixels per chunk served from the shared row table
+constexpr int TWMAX = 15;       // table width 2*max(n,1)+1 for n <= 7
+
 struct BRun {
   int start, len, tmin, span;
+  int key;                      // index into the key table, or -1 (table full: look rows up directly)
+  int mpx, mpy, ep;
 };
 
 struct BwdSmem {
@@ -54,9 +58,14 @@ struct BwdSmem {
   float a[S], b[S], c[S];
   float wx[5][S], wy[5][S];
   BRun run[S];
-  int nruns;
+  int nruns, nkeys;
   int next_run;
-  int rows[BWD_WARPS][MAX_UNITS];
+  int kep[MAXK], kpx[MAXK], kpy[MAXK];
+  int krow[MAXK][TWMAX * TWMAX];            // raw row of pixel (mpx+dx, mpy+dy): -1 absent, bit 30 = id < 0
+  unsigned char klist[MAXK][TWMAX * TWMAX]; // neighbour units (index into the P x P stencil) that have work
+  int kcount[MAXK];
+  // transverse-diffusion bins that share pixel and response row are merged ("groups"), per in-pixel bin index b:
+  unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   float dwx[BWD_WARPS][5][32], dwy[BWD_WARPS][5][32];
   float grad[BWD_WARPS][16];
   float gl[LARND_NPARAMS][BWD_THREADS];  // per-thread parameter-gradient accumulators (kept out of the register file)
@@ -66,6 +75,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Sums 8 lane-partial values over the warp with 10 shuffles (instead of 40): after three halving exchanges every lane
+// holds one partially reduced value, two more butterflies finish it; the total of v[j] is returned in lane j (j < 8).
+__device__ __forceinline__ float reduce8_to_lane(const float (&v)[8], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float w[4], x[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b3 ? w[i] : w[i + 2], keep = b3 ? w[i + 2] : w[i];
+    x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float y = (b2 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, b2 ? x[0] : x[1], 4);
+  y += __shfl_xor_sync(0xffffffffu, y, 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  // lane l now holds the total of value index (l >> 2) & 7
+  return __shfl_sync(0xffffffffu, y, (lane & 7) * 4);
 }
 
 // gradient window registers: gr[i] = g[row, tmin + lane + 32 i]; ticks beyond the readout read as zero
@@ -78,28 +109,27 @@ __device__ __forceinline__ void load_gwin(float (&gr)[NG], const float* grow, in
   }
 }
 
-// G[j] = sum_x g[tmin + j + x] R[x] for one response row; result for position j is left in lane j of the return value
+// G[j] = sum_x g[tmin + j + x] R[x], j < npos <= 8, for one response row; the total for position j ends up in lane j
 template <int NG>
 __device__ __forceinline__ float correlate(const float (&gr)[NG], const float* rowp, int npos, int L, int lane) {
-  float Gl = 0.0f;
+  float part[8];
   const float* p = rowp + 2 + lane;
-  int x0 = lane;
-  for (int j = 0; j < npos; ++j, --p, --x0) {
-    float part = 0.0f;
 #pragma unroll
-    for (int i = 0; i < NG; ++i) {
-      const bool in = (unsigned)(x0 + 32 * i) < (unsigned)L;
-      const float v = in ? __ldg(p + 32 * i) : 0.0f;
-      part = fmaf(gr[i], v, part);
+  for (int j = 0; j < 8; ++j) {
+    part[j] = 0.0f;
+    if (j < npos) {  // warp-uniform
+#pragma unroll
+      for (int i = 0; i < NG; ++i) {
+        const bool in = (unsigned)(lane - j + 32 * i) < (unsigned)L;
+        const float v = in ? __ldg(p + (32 * i - j)) : 0.0f;
+        part[j] = fmaf(gr[i], v, part[j]);
+      }
     }
-    part = warp_sum(part);
-    if (lane == j) Gl = part;
   }
-  return Gl;
+  return reduce8_to_lane(part, lane);
 }
 
 // per-segment (slow path, runs touching the ends of the readout): lane-partial sums of one (segment, row) pair.
-// Returns through references: G0 = sum gw*v0, G1 = sum gw*v1 for each of NR rows, and the boundary g values.
 template <int NR>
 __device__ __forceinline__ void slow_sums(const float* grow, const float* const (&rows)[NR], int T0, int L, int nticks, int lane,
                                           float (&G0)[NR], float (&G1)[NR], float& gB, float& gA) {
@@ -126,6 +156,12 @@ __device__ __forceinline__ void slow_sums(const float* grow, const float* const 
   gA = warp_sum(gA);
 }
 
+__device__ __forceinline__ int raw_row(const RowLookup& lk, int px, int py, int ep, int nxp, int nyp) {
+  const int pid = pixel2id_dev(px, py, ep, nxp, nyp);
+  const int row = lookup_row(lk, pid);
+  return row < 0 ? -1 : (row | (pid < 0 ? (1 << 30) : 0));
+}
+
 template <int NG>
 __global__ void __launch_bounds__(BWD_THREADS, 3)
 k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_params_t p) {
@@ -138,6 +174,10 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
   const int nb = A.nb, L = A.L, nt = A.nt;
   const int64_t n = A.n;
   const int* irec = reinterpret_cast<const int*>(A.rec);
+  const int tm = max(A.n_neigh, 1), TW = 2 * tm + 1;  // row table covers the (2 tm + 1)^2 pixels around a main pixel
+  RowLookup lk = A.lk;
+  lk.n_unique = A.counts[0];
+  lk.n_neg = A.counts[1];
   // ---- stage the chunk ----------------------------------------------------------------------------------
   for (int t = threadIdx.x; t < ns; t += BWD_THREADS) {
     const int64_t s = s_base + t;
@@ -157,10 +197,26 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
       sm.wy[k][t] = A.rec[(int64_t)(LARND_F_WY0 + k) * n + s];
     }
   }
+  // bin groups of the 5-wide diffusion stencil for every in-pixel bin index b (pure function of b and nb)
+  if (threadIdx.x < nb && threadIdx.x < 16) {
+    const int bq = threadIdx.x;
+    int ng = 0;
+    for (int i = 0; i < 5; ++i) {
+      int q = bq + i - 2, ox = 0;
+      if (q < 0) { q += nb; ox = -1; } else if (q >= nb) { q -= nb; ox = 1; }
+      const int ci = abs(2 * q - A.half2) >> 1;
+      int g = -1;
+      for (int k = 0; k < ng; ++k)
+        if (sm.g_ox[bq][k] == ox + 1 && sm.g_ci[bq][k] == ci) g = k;
+      if (g < 0) { g = ng++; sm.g_ox[bq][g] = ox + 1; sm.g_ci[bq][g] = ci; sm.g_mask[bq][g] = 0; }
+      sm.g_mask[bq][g] |= 1 << i;
+    }
+    sm.g_n[bq] = ng;
+  }
   __syncthreads();
   // ---- runs: same key, start ticks within SPAN_MAX, at most 32 segments (one lane per segment) ---------------
   if (threadIdx.x == 0) {
-    int nr = 0, cur = -1, tmin = 0, tmax = 0;
+    int nr = 0, cur = -1, tmin = 0, tmax = 0, nk = 0;
     for (int t = 0; t < ns; ++t) {
       if (!(sm.flags[t] & 1)) continue;  // outside every TPC: q == 0 and dq/dtheta == 0 (mask factor) -> no gradient
       const int T0 = __float_as_int(sm.seg[t].z);
@@ -174,8 +230,17 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
       if (fresh) {
         if (cur >= 0) { sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
         cur = nr++;
-        sm.run[cur].start = t;
-        sm.run[cur].len = 1;
+        BRun& R = sm.run[cur];
+        R.start = t;
+        R.len = 1;
+        R.ep = sm.ep[t];
+        R.mpx = floordiv_i(sm.bx[t], nb);
+        R.mpy = floordiv_i(sm.by[t], nb);
+        int key = -1;
+        for (int k = 0; k < nk; ++k)
+          if (sm.kep[k] == R.ep && sm.kpx[k] == R.mpx && sm.kpy[k] == R.mpy) key = k;
+        if (key < 0 && nk < MAXK) { key = nk++; sm.kep[key] = R.ep; sm.kpx[key] = R.mpx; sm.kpy[key] = R.mpy; }
+        R.key = key;
         tmin = tmax = T0;
       } else {
         sm.run[cur].len += 1;
@@ -185,17 +250,38 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
     }
     if (cur >= 0) { sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
     sm.nruns = nr;
+    sm.nkeys = nk;
     sm.next_run = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < LARND_NPARAMS; ++k) sm.gl[k][threadIdx.x] = 0.0f;
+  __syncthreads();
+  // ---- row table: one warp per distinct main pixel ------------------------------------------------------------------
+  for (int k = wid; k < sm.nkeys; k += BWD_WARPS) {
+    int cnt = 0;
+    for (int e0 = 0; e0 < TW * TW; e0 += 32) {
+      const int e = e0 + lane;
+      int raw = -1;
+      bool work = false;
+      if (e < TW * TW) {
+        const int dx = e / TW - tm, dy = e % TW - tm;
+        raw = raw_row(lk, sm.kpx[k] + dx, sm.kpy[k] + dy, sm.kep[k], A.nxp, A.nyp);
+        sm.krow[k][e] = raw;
+        // neighbour units with work: inside the stencil, not the centre (-999), and — when garbage gradients are known to
+        // be zero — only pixels that own a non-garbage row
+        const bool in_stencil = abs(dx) <= A.n_neigh && abs(dy) <= A.n_neigh;
+        const bool centre = dx == 0 && dy == 0;
+        if (A.skip_garbage) work = in_stencil && !centre && raw >= 0 && !(raw & (1 << 30));
+        else work = in_stencil;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, work);
+      if (work) sm.klist[k][cnt + __popc(m & ((1u << lane) - 1))] = (unsigned char)e;
+      cnt += __popc(m);
+    }
+    if (lane == 0) sm.kcount[k] = cnt;
   }
   __syncthreads();
   const int nruns = sm.nruns;
-  RowLookup lk = A.lk;
-  lk.n_unique = A.counts[0];
-  lk.n_neg = A.counts[1];
-  const int n_units = 25 + A.P * A.P;
-  const int sym = 2;
-#pragma unroll
-  for (int k = 0; k < LARND_NPARAMS; ++k) sm.gl[k][threadIdx.x] = 0.0f;
 #define GACC(k) sm.gl[k][threadIdx.x]
 
   for (;;) {
@@ -211,100 +297,47 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
     const float q = sg.x, f = sg.y, omf = 1.0f - f;
     const int T0 = __float_as_int(sg.z);
     const int m = T0 - R.tmin;
-    const int ep = sm.ep[t0s], bx = sm.bx[t0s], by = sm.by[t0s], idx = sm.idx[t0s];
-    const int mpx = floordiv_i(bx, nb), mpy = floordiv_i(by, nb);
-    const int bxm = bx - mpx * nb, bym = by - mpy * nb;
+    const int ep = R.ep, idx = sm.idx[t0s];
+    const int mpx = R.mpx, mpy = R.mpy;
+    const int bxm = sm.bx[t0s] - mpx * nb, bym = sm.by[t0s] - mpy * nb;
     const bool fast = (R.tmin >= 2) && (R.tmin + R.span + L <= A.nticks - 1);
     const int npos = R.span + 2;
-    // ---- target rows of all units (lane-parallel lookups) ---------------------------------------------
-    __syncwarp();
-    for (int u = lane; u < n_units; u += 32) {
-      int row;
-      if (u < 25) {
-        const int bi = u / 5, bj = u % 5;
-        const int px = floordiv_i(bx + bi - sym, nb), py = floordiv_i(by + bj - sym, nb);
-        const int pid = pixel2id_dev(px, py, ep, A.nxp, A.nyp);
-        row = lookup_row(lk, pid);  // absent -> dropped
-        if (A.skip_garbage && pid < 0) row = -1;
-      } else {
-        const int v = u - 25;
-        const int dx = v / A.P - A.n_neigh, dy = v % A.P - A.n_neigh;
-        if (dx == 0 && dy == 0) {
-          row = A.skip_garbage ? -1 : 0;
-        } else {
-          const int pid = pixel2id_dev(mpx + dx, mpy + dy, ep, A.nxp, A.nyp);
-          row = lookup_row(lk, pid);
-          const bool garbage = row < 0 || pid < 0;
-          if (row < 0) row = 0;
-          if (A.skip_garbage && garbage) row = -1;
-        }
-      }
-      sm.rows[wid][u] = row;
-    }
 #pragma unroll
     for (int k = 0; k < 5; ++k) { sm.dwx[wid][k][lane] = 0.f; sm.dwy[wid][k][lane] = 0.f; }
-    __syncwarp();
     float dq = 0.f, df = 0.f, da = 0.f, db = 0.f, dc = 0.f;  // per-lane (= per-segment) accumulators
     const float ca_ = sm.a[tl], cb_ = sm.b[tl], cc_ = sm.c[tl];
     // boundary-correction tables are read at ct(m) = nt - L - (tmin + lane) by lane m
     int ctl = nt - L - (R.tmin + lane);
     ctl = max(0, min(ctl, nt - 1));
     const int ctl1 = min(ctl + 1, nt - 1);
+    auto table_row = [&](int dx, int dy) -> int {
+      return R.key >= 0 ? sm.krow[R.key][(dx + tm) * TW + (dy + tm)] : raw_row(lk, mpx + dx, mpy + dy, ep, A.nxp, A.nyp);
+    };
 
-    for (int u = 0; u < n_units; ++u) {
-      const int row = sm.rows[wid][u];
-      if (row < 0) continue;
-      const float* grow = A.g + (int64_t)row * A.g_stride;
-      if (u >= 25) {
-        const int v = u - 25;
-        const int dx = v / A.P - A.n_neigh, dy = v % A.P - A.n_neigh;
-        const int ci = abs(2 * bxm - A.half2 - 2 * nb * dx) >> 1, cj = abs(2 * bym - A.half2 - 2 * nb * dy) >> 1;
-        const int bin = ci * A.ny_lut + cj;
-        const float* rowp = A.r0 + (int64_t)bin * A.Lp;
-        const float* crow = A.c0 + (int64_t)bin * nt;
-        if (fast) {
-          float gr[NG];
-          load_gwin<NG>(gr, grow, R.tmin, A.nticks, lane);
-          const float Gl = correlate<NG>(gr, rowp, npos, L, lane);
-          const float gC = __ldg(grow + R.tmin - 1 + min(lane, npos));       // tick tmin - 1 + lane
-          const float Cav = __ldg(crow + ctl), Cbv = __ldg(crow + ctl1), Cl = __ldg(crow + nt - L);
-          const float G0 = __shfl_sync(0xffffffffu, Gl, m), G1 = __shfl_sync(0xffffffffu, Gl, m + 1);
-          const float gB = __shfl_sync(0xffffffffu, gC, m), gA = __shfl_sync(0xffffffffu, gC, m + 1);
-          const float Ca = __shfl_sync(0xffffffffu, Cav, m), Cb = __shfl_sync(0xffffffffu, Cbv, m);
-          const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
-          const float gm = fmaf(f, gB, omf * gA);
-          dq += fmaf(f, G0, omf * G1) + gm * D;
-          df += q * ((G0 - G1) + (gB - gA) * D + gm * dD);
-        } else {
-          for (int t = 0; t < R.len; ++t) {
-            const float4 s2 = sm.seg[t0s + t];
-            const int T2 = __float_as_int(s2.z);
-            const float f2 = s2.y, o2 = 1.0f - f2;
-            const float* const rows[1] = {rowp};
-            float G0[1], G1[1], gB, gA;
-            slow_sums<1>(grow, rows, T2, L, A.nticks, lane, G0, G1, gB, gA);
-            const int ct = nt - L - T2;
-            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1)), Cl = __ldg(crow + nt - L);
-            const float D = Cl - (Ca * o2 + Cb * f2), dD = -(Cb - Ca);
-            const float gm = fmaf(f2, gB, o2 * gA);
-            if (lane == t) {
-              dq += fmaf(f2, G0[0], o2 * G1[0]) + gm * D;
-              df += s2.x * ((G0[0] - G1[0]) + (gB - gA) * D + gm * dD);
-            }
-          }
-        }
-      } else {
-        const int bi = u / 5, bj = u % 5;
-        const int bxx = bx + bi - sym, byy = by + bj - sym;
-        const int px = floordiv_i(bxx, nb), py = floordiv_i(byy, nb);
-        const int cix = abs(2 * (bxx - px * nb) - A.half2) >> 1, ciy = abs(2 * (byy - py * nb) - A.half2) >> 1;
+    // ---------------- main pixels: merged diffusion-bin groups, 3-template blend ------------------------------------
+    const int ngx = sm.g_n[bxm], ngy = sm.g_n[bym];
+    for (int gx = 0; gx < ngx; ++gx) {
+      const int ox = (int)sm.g_ox[bxm][gx] - 1, cix = sm.g_ci[bxm][gx], mx = sm.g_mask[bxm][gx];
+      float gwx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) gwx += (mx >> i & 1) ? sm.wx[i][tl] : 0.f;
+      for (int gy = 0; gy < ngy; ++gy) {
+        const int oy = (int)sm.g_ox[bym][gy] - 1, ciy = sm.g_ci[bym][gy], my = sm.g_mask[bym][gy];
+        const int raw = table_row(ox, oy);
+        if (raw < 0) continue;                                   // not a main pixel: dropped (sim_jax.py:152-154)
+        if (A.skip_garbage && (raw & (1 << 30))) continue;
+        const int row = raw & ~(1 << 30);
+        float gwy = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) gwy += (my >> j & 1) ? sm.wy[j][tl] : 0.f;
+        const float w = gwx * gwy;
+        const float* grow = A.g + (int64_t)row * A.g_stride;
         const int bin = cix * 5 + ciy;
         const float* ra = A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp;
         const float* rb = A.rm + (int64_t)(idx * 25 + bin) * A.Lp;
         const float* rc = A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp;
         const float* crow = A.cm + (int64_t)(idx * 25 + bin) * nt;
-        const float wxv = sm.wx[bi][tl], wyv = sm.wy[bj][tl];
-        const float w = wxv * wyv;
+        float Pv = 0.f;
         if (fast) {
           float gr[NG];
           load_gwin<NG>(gr, grow, R.tmin, A.nticks, lane);
@@ -321,7 +354,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
           const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
           const float gm = fmaf(f, gB, omf * gA);
           const float Sa = fmaf(f, a0, omf * a1), Sb = fmaf(f, b0, omf * b1), Sc = fmaf(f, c0v, omf * c1v);
-          const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
+          Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
           const float Fd = fmaf(ca_, a0 - a1, fmaf(cb_, b0 - b1, cc_ * (c0v - c1v))) + (gB - gA) * D + gm * dD;
           const float qb = w * q;
           dq = fmaf(w, Pv, dq);
@@ -329,8 +362,6 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
           da = fmaf(qb, Sa, da);
           db = fmaf(qb, Sb, db);
           dc = fmaf(qb, Sc, dc);
-          sm.dwx[wid][bi][lane] += wyv * q * Pv;
-          sm.dwy[wid][bj][lane] += wxv * q * Pv;
         } else {
           for (int t = 0; t < R.len; ++t) {
             const float4 s2 = sm.seg[t0s + t];
@@ -345,7 +376,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
             const float gm = fmaf(f2, gB, o2 * gA);
             if (lane == t) {
               const float Sa = fmaf(f2, G0[0], o2 * G1[0]), Sb = fmaf(f2, G0[1], o2 * G1[1]), Sc = fmaf(f2, G0[2], o2 * G1[2]);
-              const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
+              Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
               const float Fd = fmaf(ca_, G0[0] - G1[0], fmaf(cb_, G0[1] - G1[1], cc_ * (G0[2] - G1[2]))) + (gB - gA) * D + gm * dD;
               const float qb = w * q;
               dq = fmaf(w, Pv, dq);
@@ -353,9 +384,65 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
               da = fmaf(qb, Sa, da);
               db = fmaf(qb, Sb, db);
               dc = fmaf(qb, Sc, dc);
-              sm.dwx[wid][bi][lane] += wyv * q * Pv;
-              sm.dwy[wid][bj][lane] += wxv * q * Pv;
             }
+          }
+        }
+        // d/dWx_i = sum_j Wy_j q P_ij with P_ij = Pv for every member (i,j) of this group
+        const float px_ = gwy * q * Pv, py_ = gwx * q * Pv;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          if (mx >> i & 1) sm.dwx[wid][i][lane] += px_;
+          if (my >> i & 1) sm.dwy[wid][i][lane] += py_;
+        }
+      }
+    }
+    // ---------------- neighbour pixels: template 0, full charge ---------------------------------------------------------
+    const int n_list = R.key >= 0 ? sm.kcount[R.key] : TW * TW;
+    for (int li = 0; li < n_list; ++li) {
+      const int e = R.key >= 0 ? (int)sm.klist[R.key][li] : li;
+      const int dx = e / TW - tm, dy = e % TW - tm;
+      int row;
+      {
+        if (abs(dx) > A.n_neigh || abs(dy) > A.n_neigh) continue;
+        const bool centre = dx == 0 && dy == 0;
+        const int raw = centre ? -1 : table_row(dx, dy);
+        const bool garbage = raw < 0 || (raw & (1 << 30));
+        if (A.skip_garbage && garbage) continue;
+        row = raw < 0 ? 0 : (raw & ~(1 << 30));               // absent / centre -> waveform row 0 (sim_jax.py:724-725)
+      }
+      const float* grow = A.g + (int64_t)row * A.g_stride;
+      const int ci = abs(2 * bxm - A.half2 - 2 * nb * dx) >> 1, cj = abs(2 * bym - A.half2 - 2 * nb * dy) >> 1;
+      const int bin = ci * A.ny_lut + cj;
+      const float* rowp = A.r0 + (int64_t)bin * A.Lp;
+      const float* crow = A.c0 + (int64_t)bin * nt;
+      if (fast) {
+        float gr[NG];
+        load_gwin<NG>(gr, grow, R.tmin, A.nticks, lane);
+        const float Gl = correlate<NG>(gr, rowp, npos, L, lane);
+        const float gC = __ldg(grow + R.tmin - 1 + min(lane, npos));       // tick tmin - 1 + lane
+        const float Cav = __ldg(crow + ctl), Cbv = __ldg(crow + ctl1), Cl = __ldg(crow + nt - L);
+        const float G0 = __shfl_sync(0xffffffffu, Gl, m), G1 = __shfl_sync(0xffffffffu, Gl, m + 1);
+        const float gB = __shfl_sync(0xffffffffu, gC, m), gA = __shfl_sync(0xffffffffu, gC, m + 1);
+        const float Ca = __shfl_sync(0xffffffffu, Cav, m), Cb = __shfl_sync(0xffffffffu, Cbv, m);
+        const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
+        const float gm = fmaf(f, gB, omf * gA);
+        dq += fmaf(f, G0, omf * G1) + gm * D;
+        df += q * ((G0 - G1) + (gB - gA) * D + gm * dD);
+      } else {
+        for (int t = 0; t < R.len; ++t) {
+          const float4 s2 = sm.seg[t0s + t];
+          const int T2 = __float_as_int(s2.z);
+          const float f2 = s2.y, o2 = 1.0f - f2;
+          const float* const rows[1] = {rowp};
+          float G0[1], G1[1], gB, gA;
+          slow_sums<1>(grow, rows, T2, L, A.nticks, lane, G0, G1, gB, gA);
+          const int ct = nt - L - T2;
+          const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1)), Cl = __ldg(crow + nt - L);
+          const float D = Cl - (Ca * o2 + Cb * f2), dD = -(Cb - Ca);
+          const float gm = fmaf(f2, gB, o2 * gA);
+          if (lane == t) {
+            dq += fmaf(f2, G0[0], o2 * G1[0]) + gm * D;
+            df += s2.x * ((G0[0] - G1[0]) + (gB - gA) * D + gm * dD);
           }
         }
       }
@@ -430,6 +517,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
       }
       GACC(LARND_P_EFIELD) += g_E;
     }
+    __syncwarp();
   }
   // ---- warp + block reduction -> per-chunk partials ----------------------------------------------------------
 #pragma unroll
