@@ -38,16 +38,33 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   const int Nt = F.ntw;
   float* c = smem + (size_t)wid * Nt;
   const float* w = F.wfs + (int64_t)row * F.stride;
-  for (int t = lane; t < Nt; t += 32) c[t] = __fmul_rn(w[t], p.t_sampling);  // q = wfs * t_sampling
+  int t_first = Nt, t_last = -1;  // first / last tick with a non-zero sample
+  for (int t = lane; t < Nt; t += 32) {
+    const float qv = __fmul_rn(w[t], p.t_sampling);  // q = wfs * t_sampling
+    c[t] = qv;
+    if (qv != 0.0f) { t_first = min(t_first, t); t_last = t; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, o));
+    t_last = max(t_last, __shfl_xor_sync(0xffffffffu, t_last, o));
+  }
   __syncwarp();
-  if (lane == 0) {  // sequential float32 running sum (fee_jax.py:193)
+  // sequential float32 running sum (fee_jax.py:193), strictly left to right.  Adding the zero samples before the first
+  // and after the last non-zero tick does not change a float32 sum, so only [t_first, t_last] is walked serially and the
+  // constant tail is filled in parallel.
+  float total = 0.0f;
+  if (lane == 0) {
     float acc = 0.0f;
 #pragma unroll 8
-    for (int t = 0; t < Nt; ++t) {
+    for (int t = t_first; t <= t_last; ++t) {
       acc = __fadd_rn(acc, c[t]);
       c[t] = acc;
     }
+    total = acc;
   }
+  total = __shfl_sync(0xffffffffu, total, 0);
+  for (int t = max(t_last + 1, 0) + lane; t < Nt; t += 32) c[t] = total;
   __syncwarp();
   const float thr = p.discrimination_threshold;
   const int interval = p.hold_interval;
@@ -99,9 +116,12 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
     if (end2 >= Nt) end2 = Nt - 1;
     const float sub = c[end2];
     __syncwarp();
+    float vmax = 0.0f;
     for (int t = lane; t < Nt; t += 32) {
       float v = __fsub_rn(c[t], sub);
-      c[t] = (v < 0.0f) ? 0.0f : v;
+      v = (v < 0.0f) ? 0.0f : v;
+      c[t] = v;
+      vmax = fmaxf(vmax, v);
     }
     __syncwarp();
     // digitize (fee_jax.py:68-69)
@@ -121,6 +141,28 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
       F.ticks[(int64_t)row * nmax + it] = ic;
       F.pixel_z[(int64_t)row * nmax + it] = pz;
       if (F.saved) F.saved[(int64_t)row * 32 + it] = (float)idx_t;
+    }
+    // Early exit (noise-free only): after the clamp the row is >= 0, so every later subtraction is >= 0 and the row can only
+    // shrink; once its maximum is below the threshold no later pass can find a crossing.  The remaining passes of the
+    // reference all return (adc 0, tick Nt-2): write them directly.
+    if (!nz && it + 1 < nmax) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (vmax < thr) {
+        const float inner0 = __fsub_rn(__fadd_rn(__fmul_rn(0.0f, p.gain), p.v_pedestal), p.v_cm);
+        const float dig0 = fminf(__fdiv_rn(__fmul_rn(fmaxf(inner0, 0.0f), p.adc_counts), adc_scale_den), p.adc_counts);
+        const float ic0 = (float)(Nt - 2);
+        const float pz0 = __fadd_rn(z_anode, __fmul_rn(__fmul_rn(ic0, p.ts_vdrift), sgn));
+        const bool counts_valid = (ic0 < (float)(Nt - 3) ? 1.0f : 0.0f) > p.hit_prob_threshold && ev >= 0 && pid >= 0;
+        for (int k = it + 1 + lane; k < nmax; k += 32) {
+          F.adc[(int64_t)row * nmax + k] = dig0;
+          F.ticks[(int64_t)row * nmax + k] = ic0;
+          F.pixel_z[(int64_t)row * nmax + k] = pz0;
+          if (F.saved) F.saved[(int64_t)row * 32 + k] = ic0;
+        }
+        if (counts_valid) n_valid += nmax - it - 1;
+        break;
+      }
     }
   }
   if (lane == 0) {
