@@ -241,7 +241,7 @@ def run_ours(args):
         diff = (fs.adc - adc_target) * (st.unique_pixels >= 0).unsqueeze(1)  # only real pixels enter the loss (parse_output)
         loss = (diff * diff).sum()
         g_wfs = sim.fee_backward(fs, 2.0 * diff)
-        grad = sim.lut_backward(st, g_wfs, skip_garbage=True)  # rows with id < 0 produce no hits -> zero gradient
+        grad = sim.lut_backward(st, g_wfs)  # rows of ids < 0 carry zero gradient: detected on the device, their work is skipped
         red = torch.cat([loss.reshape(1), grad])
         if world > 1:
             dist.all_reduce(red)

@@ -41,6 +41,7 @@ struct BwdArgs {
   int64_t g_stride;
   float* partials;
   int skip_garbage;
+  const int* garbage_grad_nonzero;  // device flag written by k_garbage_grad_flag
 };
 
 constexpr int MAXK = 16;        // distinct main pixels per chunk served from the shared row table
@@ -162,9 +163,22 @@ __device__ __forceinline__ int raw_row(const RowLookup& lk, int px, int py, int 
   return row < 0 ? -1 : (row | (pid < 0 ? (1 << 30) : 0));
 }
 
+// Rows 0 .. n_neg of the waveform buffer belong to pixel ids < 0 (padding events and the -1 entries): the reference's own
+// callers never look at them (parse_output, sim_jax.py:621), so their upstream gradient is zero for every loss built on
+// hits.  This kernel checks that on the device; when it holds, all work whose only effect is on those rows is skipped.
+__global__ void k_garbage_grad_flag(const float* __restrict__ g, int64_t g_stride, int nticks, const int32_t* __restrict__ counts,
+                                    int* __restrict__ flag) {
+  const int n_rows = counts[1] + 1;
+  bool nz = false;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x)
+    for (int t = 1 + threadIdx.x; t < nticks; t += blockDim.x) nz |= g[(int64_t)r * g_stride + t] != 0.0f;
+  if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 template <int NG>
 __global__ void __launch_bounds__(BWD_THREADS, 3)
 k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_params_t p) {
+  const bool skip_garbage = A.skip_garbage || (*A.garbage_grad_nonzero == 0);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -271,7 +285,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         // be zero — only pixels that own a non-garbage row
         const bool in_stencil = abs(dx) <= A.n_neigh && abs(dy) <= A.n_neigh;
         const bool centre = dx == 0 && dy == 0;
-        if (A.skip_garbage) work = in_stencil && !centre && raw >= 0 && !(raw & (1 << 30));
+        if (skip_garbage) work = in_stencil && !centre && raw >= 0 && !(raw & (1 << 30));
         else work = in_stencil;
       }
       const unsigned m = __ballot_sync(0xffffffffu, work);
@@ -325,7 +339,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         const int oy = (int)sm.g_ox[bym][gy] - 1, ciy = sm.g_ci[bym][gy], my = sm.g_mask[bym][gy];
         const int raw = table_row(ox, oy);
         if (raw < 0) continue;                                   // not a main pixel: dropped (sim_jax.py:152-154)
-        if (A.skip_garbage && (raw & (1 << 30))) continue;
+        if (skip_garbage && (raw & (1 << 30))) continue;
         const int row = raw & ~(1 << 30);
         float gwy = 0.f;
 #pragma unroll
@@ -407,7 +421,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         const bool centre = dx == 0 && dy == 0;
         const int raw = centre ? -1 : table_row(dx, dy);
         const bool garbage = raw < 0 || (raw & (1 << 30));
-        if (A.skip_garbage && garbage) continue;
+        if (skip_garbage && garbage) continue;
         row = raw < 0 ? 0 : (raw & ~(1 << 30));               // absent / centre -> waveform row 0 (sim_jax.py:724-725)
       }
       const float* grow = A.g + (int64_t)row * A.g_stride;
@@ -588,6 +602,11 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   A.partials = ws.partials;
   A.skip_garbage = flags & 1;
   const int64_t chunks = (n + S - 1) / S;
+  int* gflag = reinterpret_cast<int*>(ws.partials + (size_t)ws.n_chunks_max * 16) - 4;  // last 16 bytes of the partials area
+  LARND_CUDA(cudaMemsetAsync(gflag, 0, sizeof(int), st));
+  k_garbage_grad_flag<<<32, 256, 0, st>>>(g_wfs, g_stride, p.n_ticks, counts, gflag);
+  LARND_LAUNCH_CHECK("k_garbage_grad_flag");
+  A.garbage_grad_nonzero = gflag;
   const int need = lut->L + SPAN_MAX + 2;  // gradient window of a run: ticks tmin .. tmin + span + 1 + L - 1
   int rc;
   if (need <= 32 * 2) rc = launch_bwd<2>(A, p, chunks, st);
