@@ -42,7 +42,10 @@ struct AccArgs {
   const int32_t* counts;
   float* wfs;
   int skip_garbage;
+  int slow_only;  // 1: only segments whose window touches the ends of the readout (the rest is done by accumulate_sorted.cu)
 };
+
+__device__ __forceinline__ bool seg_is_fast(int T0, int L, int nticks) { return T0 >= 2 && T0 + L <= nticks - 2; }
 
 constexpr int KP = 8;            // tick positions per run (impulse train length)
 constexpr int SPAN_MAX = KP - 2;  // max (T0max - T0min) inside a run
@@ -77,6 +80,7 @@ struct ChunkSmem {
   // transverse-diffusion bins that fall on the same pixel with the same response row are merged ("groups"); per
   // in-pixel bin index b: number of groups, pixel offset + 1, response index and member mask of each group
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
+  unsigned char fastseg[S];
   int nruns;
   int next_unit;
 };
@@ -259,6 +263,12 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
   const int ns = (int)min((int64_t)S, A.n - s_base);
   const int nb = A.nb;
   const int L = A.L;
+  if (A.slow_only) {  // nothing to do for a chunk without boundary segments (the common case)
+    int slow = 0;
+    if ((int)threadIdx.x < ns)
+      slow = !seg_is_fast(reinterpret_cast<const int*>(A.rec)[(int64_t)LARND_I_T0 * A.n + s_base + threadIdx.x], L, A.nticks);
+    if (!__syncthreads_or(slow)) return;
+  }
   // ---- stage the chunk's segment records --------------------------------------------------------------
   for (int t = threadIdx.x; t < ns; t += ACC_THREADS) {
     const int64_t s = s_base + t;
@@ -277,6 +287,7 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
     sm.idx[t] = irec[(int64_t)LARND_I_IDX * n + s];
     sm.bx[t] = bx;
     sm.by[t] = by;
+    sm.fastseg[t] = seg_is_fast(irec[(int64_t)LARND_I_T0 * n + s], L, A.nticks);
     {
       const float q = sm.seg[t].x, f = sm.seg[t].y, o = 1.0f - f;
       const float qf = q * f, qo = q * o;
@@ -312,11 +323,16 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
     int cur = -1, tmin = 0, tmax = 0;
     for (int t = 0; t < ns; ++t) {
       const int T0 = __float_as_int(sm.seg[t].z);
+      if (A.slow_only && sm.fastseg[t]) {  // handled by the class-sorted kernel
+        if (cur >= 0) { sm.run[cur].len = t - sm.run[cur].start; sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
+        cur = -1;
+        continue;
+      }
       bool fresh = cur < 0;
       if (!fresh) {
         const int t0s = sm.run[cur].start;
         fresh = sm.key[t].x != sm.key[t0s].x || sm.bx[t] != sm.bx[t0s] || sm.by[t] != sm.by[t0s] || sm.idx[t] != sm.idx[t0s] ||
-                max(tmax, T0) - min(tmin, T0) > SPAN_MAX;
+                sm.fastseg[t] != sm.fastseg[t0s] || max(tmax, T0) - min(tmin, T0) > SPAN_MAX;
       }
       if (fresh) {
         if (cur >= 0) { sm.run[cur].len = t - sm.run[cur].start; sm.run[cur].tmin = tmin; sm.run[cur].span = tmax - tmin; }
@@ -538,6 +554,13 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                             int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
   if (n == 0) return LARND_OK;
+  const bool slow_only = (flags & LARND_ACC_SLOW_ONLY) != 0;
+  if (!slow_only && larnd_sorted_supported(p, lut)) {
+    // large batches: class-sorted kernel (accumulate_sorted.cu).  LARND_ACC_IMPL = chunk | sorted overrides the size rule.
+    bool sorted = n >= LARND_SORTED_MIN_SEGMENTS;
+    if (const char* e = getenv("LARND_ACC_IMPL")) sorted = e[0] == 's';
+    if (sorted) return larnd_launch_accumulate_sorted(n, p, lut, ws, npix_capacity, flags, wfs, counts, st);
+  }
   AccArgs A;
   A.rec = ws.rec; A.n = n;
   {
@@ -557,6 +580,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.counts = counts;
   A.wfs = wfs;
   A.skip_garbage = flags & 1;
+  A.slow_only = slow_only ? 1 : 0;
   const int64_t chunks = (n + S - 1) / S;
   // register window = run window (L + 2 + span) + slack for the tick drift between consecutive runs of a track;
   // more slack = fewer flushes but more predicated-off slots in the inner loop.  LARND_ACC_NS overrides (tuning).
@@ -577,7 +601,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
     int v = atoi(e);
     if (32 * v >= lut->L + 2 + SPAN_MAX) ns_sel = v;
   }
-  prof_begin(1, st);
+  if (!slow_only) prof_begin(1, st);
   if (ns_sel <= 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
   else if (ns_sel <= 5) k_lut_accumulate<5><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
   else if (ns_sel <= 6) k_lut_accumulate<6><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
@@ -588,7 +612,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
     larnd_set_error("signal_length %d too large for the register window (max %d)", lut->L, 32 * 16 - 2 - SPAN_MAX);
     return LARND_E_ARG;
   }
-  prof_end(1, st);
+  if (!slow_only) prof_end(1, st);
   LARND_LAUNCH_CHECK("k_lut_accumulate");
   return LARND_OK;
 }

@@ -1,0 +1,590 @@
+// K3' class-sorted lut_accumulate (forward), sm_100a — the large-batch path of simulate_signals
+// (reference sim_jax.py:142-286; same arithmetic as accumulate.cu, different work decomposition).
+//
+// accumulate.cu walks a chunk of consecutive segments and re-reads the response rows from L1/L2 for every
+// (run, unit) pair: ~75 % of its instructions are gather/bookkeeping around the multiply-adds.  Here the runs of
+// the whole batch are first SORTED BY RESPONSE CLASS (longitudinal template index, sub-pixel bin inside the pixel):
+// every run of a class reads the same response rows for the same unit, so a warp loads the rows of its unit ONCE
+// into registers — for every tick of its 32*NS-tick window and every impulse position j < KPT the sample
+// R[x - 1 - j] — and then streams the runs of the class through pure FFMAs:
+//
+//   k_build_runs     chunk of 128 segments -> runs (same definition as accumulate.cu, only "fast" segments whose
+//                    whole window lies inside the readout), class histogram                          [global atomics]
+//   k_class_scan     exclusive scan of the histogram -> class offsets, tile table (<= 32 runs of one class)
+//   k_scatter_runs   counting-sort scatter of the run records
+//   k_acc_tiles      persistent CTAs pull tiles; per tile 8 warps pull units (merged diffusion-bin groups,
+//                    the neighbourhood-sum row, neighbour pixels that own a waveform row).  Per (unit, tile):
+//                    lane <-> run builds the impulse trains + boundary corrections in shared memory, then
+//                    lane <-> tick applies them from the register-resident response and flushes every
+//                    (run, unit) window with coalesced red.global.add.f32.
+//
+// Segments whose window touches the ends of the readout (garbage tick 0 handling, sim_jax.py:177-178,243-244)
+// are left to accumulate.cu's per-segment path (larnd_launch_accumulate with mode = slow-only).
+#include "larnd_common.cuh"
+
+namespace {
+
+constexpr int TR = 32;              // runs per tile (lane <-> run in the build phases)
+constexpr int KPT = 6;              // impulse positions per run
+constexpr int SPAN_MAX_S = KPT - 2;  // max (T0max - T0min) inside a run
+constexpr int MAXLEN = 16;          // segments per run (bounds the divergence of the lane <-> run build loops)
+constexpr int TILE_THREADS = 256;
+constexpr int NW = TILE_THREADS / 32;
+constexpr int HS = 3 * KPT + 1;     // per-lane stride of the train buffer (odd: conflict-free)
+constexpr int ES = KPT + 1;         // per-lane stride of the correction buffer (odd)
+constexpr int MS = 5 * KPT + 1;     // per-run stride of the neighbour moments (odd)
+
+struct SortArgs {
+  const float* rec;
+  int64_t n;
+  const float* r0;
+  const float* rm;
+  const float* c0;
+  const float* cm;
+  const float* sr;
+  const float* sc;
+  int nt, L, Lp, ny_lut;
+  int nticks;
+  int nb, half2;
+  int n_neigh, P;
+  int nxp, nyp;
+  int ntpl;
+  RowLookup lk;
+  const int32_t* counts;
+  float* wfs;
+  int skip_garbage;
+  int4* runs_tmp;
+  int4* runs;
+  int* class_count;
+  int* class_start;
+  int* cursor;
+  int4* tile_info;
+  int* gcnt;  // [0] number of runs, [1] number of tiles, [2] tile counter
+  int ncls;
+  float* row0;  // [gridDim][nticks] per-CTA private copies of waveform row 0 (the garbage row every CTA adds to)
+};
+
+__device__ __forceinline__ bool seg_is_fast(int T0, int L, int nticks) { return T0 >= 2 && T0 + L <= nticks - 2; }
+
+// ------------------------------------------------------------------------------------------------ run building
+__global__ void __launch_bounds__(LARND_CHUNK)
+k_build_runs(const __grid_constant__ SortArgs A) {
+  __shared__ int s_ep[LARND_CHUNK], s_bx[LARND_CHUNK], s_by[LARND_CHUNK], s_idx[LARND_CHUNK], s_T0[LARND_CHUNK];
+  __shared__ unsigned char s_fast[LARND_CHUNK], s_kh[LARND_CHUNK], s_head[LARND_CHUNK];
+  __shared__ int s_wcnt[LARND_CHUNK / 32], s_base;
+  if (A.counts[2] != 0) return;
+  const int t = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * LARND_CHUNK;
+  const int ns = (int)min((int64_t)LARND_CHUNK, A.n - base);
+  const int* irec = reinterpret_cast<const int*>(A.rec);
+  if (t < ns) {
+    const int64_t s = base + t;
+    s_ep[t] = irec[(int64_t)LARND_I_EP * A.n + s];
+    s_bx[t] = irec[(int64_t)LARND_I_BX * A.n + s];
+    s_by[t] = irec[(int64_t)LARND_I_BY * A.n + s];
+    s_idx[t] = irec[(int64_t)LARND_I_IDX * A.n + s];
+    const int T0 = irec[(int64_t)LARND_I_T0 * A.n + s];
+    s_T0[t] = T0;
+    s_fast[t] = seg_is_fast(T0, A.L, A.nticks);
+  }
+  s_head[t] = 0;
+  __syncthreads();
+  bool kh = false;
+  if (t < ns) {
+    kh = t == 0 || s_ep[t] != s_ep[t - 1] || s_bx[t] != s_bx[t - 1] || s_by[t] != s_by[t - 1] || s_idx[t] != s_idx[t - 1] ||
+         s_fast[t] != s_fast[t - 1];
+    s_kh[t] = kh;
+  }
+  __syncthreads();
+  // the head of every key-run walks it once and cuts it greedily on the tick span / length limits
+  if (kh && s_fast[t]) {
+    int tmin = s_T0[t], tmax = tmin, start = t;
+    s_head[t] = 1;
+    for (int u = t + 1; u < ns && !s_kh[u]; ++u) {
+      const int T0 = s_T0[u];
+      if (max(tmax, T0) - min(tmin, T0) > SPAN_MAX_S || u - start >= MAXLEN) {
+        s_head[u] = 1;
+        start = u;
+        tmin = tmax = T0;
+      } else {
+        tmin = min(tmin, T0);
+        tmax = max(tmax, T0);
+      }
+    }
+  }
+  __syncthreads();
+  const bool head = t < ns && s_head[t];
+  const unsigned bal = __ballot_sync(0xffffffffu, head);
+  const int lane = t & 31, wid = t >> 5;
+  if (lane == 0) s_wcnt[wid] = __popc(bal);
+  __syncthreads();
+  int before = __popc(bal & ((1u << lane) - 1u));
+  int total = 0;
+#pragma unroll
+  for (int w = 0; w < LARND_CHUNK / 32; ++w) {
+    if (w < wid) before += s_wcnt[w];
+    total += s_wcnt[w];
+  }
+  if (t == 0) s_base = total > 0 ? atomicAdd(A.gcnt, total) : 0;
+  __syncthreads();
+  if (head) {
+    int tmin = s_T0[t], tmax = tmin, len = 1;
+    for (int u = t + 1; u < ns && !s_kh[u] && !s_head[u]; ++u) {
+      tmin = min(tmin, s_T0[u]);
+      tmax = max(tmax, s_T0[u]);
+      ++len;
+    }
+    const int nb = A.nb;
+    const int bxm = s_bx[t] - floordiv_i(s_bx[t], nb) * nb, bym = s_by[t] - floordiv_i(s_by[t], nb) * nb;
+    const int cls = (s_idx[t] * nb + bxm) * nb + bym;
+    A.runs_tmp[s_base + before] = make_int4((int)(base + t), len | ((tmax - tmin) << 16), tmin, cls);
+    atomicAdd(A.class_count + cls, 1);
+  }
+}
+
+// exclusive scans over the class histogram: run offsets and tile offsets; then the tile table
+__global__ void __launch_bounds__(1024)
+k_class_scan(const __grid_constant__ SortArgs A) {
+  __shared__ int s_w[2][32];
+  __shared__ int carry[2];
+  if (A.counts[2] != 0) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
+  __syncthreads();
+  for (int c0 = 0; c0 < A.ncls; c0 += 1024) {
+    const int c = c0 + threadIdx.x;
+    const int cnt = c < A.ncls ? A.class_count[c] : 0;
+    int v[2] = {cnt, (cnt + TR - 1) / TR};
+    int inc[2] = {v[0], v[1]};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, inc[k], o);
+        if (lane >= o) inc[k] += u;
+      }
+      if (lane == 31) s_w[k][wid] = inc[k];
+    }
+    __syncthreads();
+    if (wid < 2) {
+      int w = s_w[wid][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      s_w[wid][lane] = w;
+    }
+    __syncthreads();
+    int ex[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) ex[k] = carry[k] + (wid > 0 ? s_w[k][wid - 1] : 0) + inc[k] - v[k];
+    if (c < A.ncls) {
+      A.class_start[c] = ex[0];
+      A.cursor[c] = ex[0];
+      for (int i = 0; i < v[1]; ++i)  // tiles of this class
+        A.tile_info[ex[1] + i] = make_int4(c, ex[0] + i * TR, min(TR, cnt - i * TR), 0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry[0] += s_w[0][31]; carry[1] += s_w[1][31]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) A.gcnt[1] = carry[1];
+}
+
+__global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
+  if (A.counts[2] != 0) return;
+  const int nruns = A.gcnt[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nruns; i += gridDim.x * blockDim.x) {
+    const int4 e = A.runs_tmp[i];
+    const int pos = atomicAdd(A.cursor + e.w, 1);
+    A.runs[pos] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tile consumer
+struct TileSmem {
+  int4 run[TR];                 // start, len | span << 16, tmin, class
+  int ep[TR], mpx[TR], mpy[TR];
+  float hN[TR][KPT];            // neighbour impulse train (full segment charge)
+  float mom[TR][MS];            // neighbour correction moments A1,A2,A3,B1,B3 per position
+  float ph[NW][TR * HS];        // per-warp trains of the current unit: [run][3*j + template]
+  float pE[NW][TR * ES];        // per-warp merged boundary corrections: [run][position]
+  unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
+  int tile, next_unit;
+};
+
+template <int NS, int NR>
+__device__ __forceinline__ void load_response(float (&Rw)[3][NS][KPT], const float* const (&rows)[NR], int Lp, int lane) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const int ix = 32 * s + lane + 1 - j;  // sample k = x - 1 - j lives at row[k + 2]
+        Rw[r][s][j] = ((unsigned)ix < (unsigned)Lp) ? __ldg(rows[r] + ix) : 0.0f;
+      }
+}
+
+template <int NS>
+__device__ __forceinline__ void flush_window(const float (&acc)[NS], float* wfs, int64_t nticks, int row, int tmin, int lane,
+                                             float sign) {
+  float* dst = wfs + (int64_t)row * nticks + (tmin - 1) + lane;
+  const int lim = (int)nticks - (tmin - 1) - lane;  // columns left in the row (never reached by a finite fast run)
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+    if (acc[s] != 0.0f && 32 * s < lim) atomicAdd(dst + 32 * s, sign * acc[s]);  // RED.E.ADD.F32, coalesced
+}
+
+template <int NS>
+__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? 2 : 1)
+k_acc_tiles(const __grid_constant__ SortArgs A) {
+  __shared__ TileSmem sm;
+  if (A.counts[2] != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = A.nb, L = A.L;
+  const int* irec = reinterpret_cast<const int*>(A.rec);
+  const int64_t n = A.n;
+  RowLookup lk = A.lk;
+  lk.n_unique = A.counts[0];
+  lk.n_neg = A.counts[1];
+  // merged transverse-diffusion groups per in-pixel bin (same tables as accumulate.cu)
+  if (threadIdx.x < nb && threadIdx.x < 16) {
+    const int bq = threadIdx.x;
+    int ng = 0;
+    for (int i = 0; i < LARND_NB_TRAN_BINS; ++i) {
+      int qb = bq + i - (LARND_NB_TRAN_BINS - 1) / 2, ox = 0;
+      if (qb < 0) { qb += nb; ox = -1; } else if (qb >= nb) { qb -= nb; ox = 1; }
+      const int ci = abs(2 * qb - A.half2) >> 1;
+      int g = -1;
+      for (int k = 0; k < ng; ++k)
+        if (sm.g_ox[bq][k] == ox + 1 && sm.g_ci[bq][k] == ci) g = k;
+      if (g < 0) { g = ng++; sm.g_ox[bq][g] = ox + 1; sm.g_ci[bq][g] = ci; sm.g_mask[bq][g] = 0; }
+      sm.g_mask[bq][g] |= 1 << i;
+    }
+    sm.g_n[bq] = ng;
+  }
+  const int ntiles = A.gcnt[1];
+  const int n_neigh_units = A.P * A.P;
+  const int n_units = 25 + 1 + n_neigh_units;  // merged diffusion groups, neighbourhood-sum row, neighbour pixels
+  float* myh = sm.ph[warp];
+  float* myE = sm.pE[warp];
+  // Waveform row 0 collects the neighbourhood sum of EVERY run (sim_jax.py:724-725): ~13 windows per run from all CTAs
+  // onto the same 8 KB would serialise in the L2 atomic units, so each CTA reduces into a private copy (summed by
+  // k_reduce_row0 afterwards).
+  float* row0 = A.row0 + (int64_t)blockIdx.x * A.nticks;
+
+  for (;;) {
+    __syncthreads();  // everybody is done with the previous tile
+    if (threadIdx.x == 0) { sm.tile = atomicAdd(A.gcnt + 2, 1); sm.next_unit = 0; }
+    __syncthreads();
+    const int tile = sm.tile;
+    if (tile >= ntiles) break;
+    const int4 ti = A.tile_info[tile];
+    const int cls = ti.x, count = ti.z;
+    const int bym = cls % nb, bxm = (cls / nb) % nb, idx = cls / (nb * nb);
+    // ---- stage the runs; neighbour impulse train + correction moments (thread <-> run) -------------------------
+    if (threadIdx.x < count) {
+      const int r = threadIdx.x;
+      const int4 e = A.runs[ti.y + r];
+      sm.run[r] = e;
+      const int64_t s0 = e.x;
+      sm.ep[r] = irec[(int64_t)LARND_I_EP * n + s0];
+      sm.mpx[r] = floordiv_i(irec[(int64_t)LARND_I_BX * n + s0], nb);
+      sm.mpy[r] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
+#pragma unroll
+      for (int k = 0; k < KPT; ++k) sm.hN[r][k] = 0.0f;
+      for (int k = 0; k < 5 * KPT; ++k) sm.mom[r][k] = 0.0f;
+      const int len = e.y & 0xffff, tmin = e.z;
+      for (int t = 0; t < len; ++t) {
+        const int64_t s = s0 + t;
+        const float q = A.rec[(int64_t)LARND_F_Q * n + s], f = A.rec[(int64_t)LARND_F_FRAC * n + s], o = 1.0f - f;
+        const int m = irec[(int64_t)LARND_I_T0 * n + s] - tmin;
+        sm.hN[r][m] += q * f;
+        sm.hN[r][m + 1] += q * o;
+        float* mo = sm.mom[r] + 5 * m;
+        mo[0] += q * o; mo[1] += q * o * o; mo[2] += q * f * o; mo[3] += q * f; mo[4] += q * f * f;
+      }
+    }
+    __syncthreads();
+
+    for (;;) {
+      int unit = 0;
+      if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);
+      unit = __shfl_sync(0xffffffffu, unit, 0);
+      if (unit >= n_units) break;
+      float Rw[3][NS][KPT];
+      if (unit < 25) {
+        // ---------------- merged diffusion-bin group (gi, gj): 3-template blend on a main pixel ----------------
+        const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
+        if (gi >= sm.g_n[bxm] || gj >= sm.g_n[bym]) continue;
+        const int bin = (int)sm.g_ci[bxm][gi] * 5 + (int)sm.g_ci[bym][gj];
+        const unsigned mx = sm.g_mask[bxm][gi], my = sm.g_mask[bym][gj];
+        const int ox = (int)sm.g_ox[bxm][gi] - 1, oy = (int)sm.g_ox[bym][gj] - 1;
+        int row = -1;
+        if (lane < count) {
+          const int pid = pixel2id_dev(sm.mpx[lane] + ox, sm.mpy[lane] + oy, sm.ep[lane], A.nxp, A.nyp);
+          row = lookup_row(lk, pid);  // not in the list -> dropped (sim_jax.py:152-154)
+          if (A.skip_garbage && pid < 0) row = -1;
+        }
+        if (__ballot_sync(0xffffffffu, row >= 0) == 0u) continue;
+        // build: lane <-> run
+        if (row >= 0) {
+          float* h = myh + lane * HS;
+          float* E = myE + lane * ES;
+#pragma unroll
+          for (int k = 0; k < 3 * KPT; ++k) h[k] = 0.0f;
+#pragma unroll
+          for (int k = 0; k < ES; ++k) E[k] = 0.0f;
+          const int4 e = sm.run[lane];
+          const int len = e.y & 0xffff, tmin = e.z;
+          const float* crow = A.cm + (int64_t)(idx * 25 + bin) * A.nt;
+          const float Cl = __ldg(crow + A.nt - L);
+          for (int t = 0; t < len; ++t) {
+            const int64_t s = (int64_t)e.x + t;
+            float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+            for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
+              if (mx >> k & 1) sx += A.rec[(int64_t)(LARND_F_WX0 + k) * n + s];
+              if (my >> k & 1) sy += A.rec[(int64_t)(LARND_F_WY0 + k) * n + s];
+            }
+            const float w = sx * sy;
+            const float q = A.rec[(int64_t)LARND_F_Q * n + s], f = A.rec[(int64_t)LARND_F_FRAC * n + s];
+            const float ca = A.rec[(int64_t)LARND_F_A * n + s], cb = A.rec[(int64_t)LARND_F_B * n + s],
+                        cc = A.rec[(int64_t)LARND_F_C * n + s];
+            const int T0 = irec[(int64_t)LARND_I_T0 * n + s];
+            const int m = T0 - tmin;
+            const float qf = (w * q) * f, qo = (w * q) * (1.0f - f);
+            float* hm = h + 3 * m;
+            hm[0] = fmaf(qf, ca, hm[0]); hm[1] = fmaf(qf, cb, hm[1]); hm[2] = fmaf(qf, cc, hm[2]);
+            hm[3] = fmaf(qo, ca, hm[3]); hm[4] = fmaf(qo, cb, hm[4]); hm[5] = fmaf(qo, cc, hm[5]);
+            // boundary correction of this segment (sim_jax.py:236-247): D lands on tick T0 (weight 1-f) and T0-1 (f)
+            int ct = A.nt - L - T0;
+            ct = max(0, min(ct, A.nt - 1));
+            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
+            const float D = Cl - (Ca * (1.0f - f) + Cb * f);
+            E[m] = fmaf(qf, D, E[m]);
+            E[m + 1] = fmaf(qo, D, E[m + 1]);
+          }
+        }
+        __syncwarp();
+        const float* const rows[3] = {A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp, A.rm + (int64_t)(idx * 25 + bin) * A.Lp,
+                                      A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp};
+        load_response<NS, 3>(Rw, rows, A.Lp, lane);
+        // consume: lane <-> tick
+        for (int p = 0; p < count; ++p) {
+          const int rowp = __shfl_sync(0xffffffffu, row, p);
+          if (rowp < 0) continue;
+          const int4 e = sm.run[p];
+          const int npos = (e.y >> 16) + 2;
+          const float* h = myh + p * HS;
+          float acc[NS];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
+#pragma unroll
+          for (int j = 0; j < KPT; ++j) {
+            if (j < npos) {
+              const float h0 = h[3 * j], h1 = h[3 * j + 1], h2 = h[3 * j + 2];
+#pragma unroll
+              for (int s = 0; s < NS; ++s) acc[s] = fmaf(h2, Rw[2][s][j], fmaf(h1, Rw[1][s][j], fmaf(h0, Rw[0][s][j], acc[s])));
+            }
+          }
+          if (lane < ES) acc[0] += myE[p * ES + lane];
+          flush_window<NS>(acc, A.wfs, A.nticks, rowp, e.z, lane, 1.0f);
+        }
+        __syncwarp();
+      } else {
+        // ---------------- neighbour pixels: template 0, full segment charge (sim_jax.py:197-225,250-261) ----------
+        // unit 25 = the neighbourhood-sum row into waveform row 0; the others add to the neighbour's own row (if it
+        // is a main pixel of the batch) and take the same deposit back out of row 0 (see accumulate.cu)
+        const bool sum_unit = unit == 25;
+        if (sum_unit && A.skip_garbage) continue;
+        const int u = unit - 26;
+        const int dx = sum_unit ? 0 : u / A.P - A.n_neigh, dy = sum_unit ? 0 : u % A.P - A.n_neigh;
+        if (!sum_unit && dx == 0 && dy == 0) continue;  // the centre id is -999: row 0 only (inside the sum row)
+        int row = -1;
+        if (lane < count) {
+          if (sum_unit) row = 0;
+          else {
+            const int pid = pixel2id_dev(sm.mpx[lane] + dx, sm.mpy[lane] + dy, sm.ep[lane], A.nxp, A.nyp);
+            row = lookup_row(lk, pid);
+            if (row <= 0) row = -1;
+            else if (A.skip_garbage && pid < 0) row = -1;
+          }
+        }
+        unsigned owned = __ballot_sync(0xffffffffu, row >= 0);
+        if (owned == 0u) continue;
+        const float* rowp0;
+        const float* crow;
+        if (sum_unit) {
+          const int sb = bxm * nb + bym;
+          rowp0 = A.sr + (int64_t)sb * A.Lp;
+          crow = A.sc + (int64_t)sb * A.nt;
+        } else {
+          const int vx = 2 * bxm - A.half2 - 2 * nb * dx, vy = 2 * bym - A.half2 - 2 * nb * dy;
+          const int bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
+          rowp0 = A.r0 + (int64_t)bin * A.Lp;
+          crow = A.c0 + (int64_t)bin * A.nt;
+        }
+        if (row >= 0) {  // merged corrections from the run's moments: E_j = e0_j + e1_{j-1}
+          const int4 e = sm.run[lane];
+          const int span = e.y >> 16, tmin = e.z;
+          const float Cl = __ldg(crow + A.nt - L);
+          float e1prev = 0.0f;
+          float* E = myE + lane * ES;
+#pragma unroll
+          for (int j = 0; j < ES; ++j) {
+            float Ej = 0.0f;
+            if (j <= span + 1) {
+              float e1 = 0.0f, e0 = 0.0f;
+              if (j <= span) {
+                int ct = A.nt - L - (tmin + j);
+                ct = max(0, min(ct, A.nt - 1));
+                const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
+                const float* mo = sm.mom[lane] + 5 * j;
+                e1 = Cl * mo[0] - Ca * mo[1] - Cb * mo[2];
+                e0 = Cl * mo[3] - Ca * mo[2] - Cb * mo[4];
+              }
+              Ej = e0 + e1prev;
+              e1prev = e1;
+            }
+            E[j] = Ej;
+          }
+        }
+        __syncwarp();
+        const float* const rows[1] = {rowp0};
+        load_response<NS, 1>(Rw, rows, A.Lp, lane);
+        const bool dual = !sum_unit && !A.skip_garbage;
+        while (owned) {
+          const int p = __ffs(owned) - 1;
+          owned &= owned - 1;
+          const int rowp = __shfl_sync(0xffffffffu, row, p);
+          const int4 e = sm.run[p];
+          const int npos = (e.y >> 16) + 2;
+          float acc[NS];
+#pragma unroll
+          for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
+#pragma unroll
+          for (int j = 0; j < KPT; ++j) {
+            if (j < npos) {
+              const float hj = sm.hN[p][j];
+#pragma unroll
+              for (int s = 0; s < NS; ++s) acc[s] = fmaf(hj, Rw[0][s][j], acc[s]);
+            }
+          }
+          if (lane < ES) acc[0] += myE[p * ES + lane];
+          if (sum_unit) flush_window<NS>(acc, row0, A.nticks, 0, e.z, lane, 1.0f);
+          else flush_window<NS>(acc, A.wfs, A.nticks, rowp, e.z, lane, 1.0f);
+          if (dual) flush_window<NS>(acc, row0, A.nticks, 0, e.z, lane, -1.0f);
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+__global__ void k_reduce_row0(const float* __restrict__ row0, int ncopies, int nticks, float* __restrict__ wfs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nticks) return;
+  float acc = 0.0f;
+  for (int k = 0; k < ncopies; ++k) acc += row0[(int64_t)k * nticks + c];
+  if (acc != 0.0f) atomicAdd(wfs + c, acc);
+}
+
+}  // namespace
+
+size_t larnd_sorted_workspace_bytes(int64_t n) {
+  size_t b = 0;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  b += align_up(nn * sizeof(int4), 256) * 2;                                       // runs_tmp, runs
+  b += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256) * 3;                    // class_count, class_start, cursor
+  b += align_up((nn / TR + LARND_NCLS_MAX + 1) * sizeof(int4), 256);               // tile_info
+  b += 256;                                                                        // counters
+  b += align_up((size_t)LARND_ROW0_COPIES * LARND_ROW0_TICKS_MAX * sizeof(float), 256);  // private garbage rows
+  return b;
+}
+
+void larnd_carve_sorted(char* p, int64_t n, Workspace* ws) {
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  ws->runs_tmp = p; p += align_up(nn * sizeof(int4), 256);
+  ws->runs = p; p += align_up(nn * sizeof(int4), 256);
+  ws->class_count = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
+  ws->class_start = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
+  ws->cursor = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
+  ws->tile_info = p; p += align_up((nn / TR + LARND_NCLS_MAX + 1) * sizeof(int4), 256);
+  ws->gcnt = reinterpret_cast<int*>(p); p += 256;
+  ws->row0 = reinterpret_cast<float*>(p);
+}
+
+int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut) {
+  const int nb = p.nb_sampling_bins_per_pixel;
+  if (lut->ntpl * nb * nb > LARND_NCLS_MAX) return 0;
+  if (lut->L + 2 + SPAN_MAX_S > 32 * 6) return 0;
+  if (p.n_ticks > LARND_ROW0_TICKS_MAX) return 0;
+  return 1;
+}
+
+int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                                   int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
+  if (n == 0) return LARND_OK;
+  if (n >= (int64_t)1 << 31) { larnd_set_error("sorted accumulate: n must be < 2^31"); return LARND_E_ARG; }
+  SortArgs A;
+  A.rec = ws.rec; A.n = n;
+  {
+    int rc0 = larnd_lut_ensure_neighbour_sums(const_cast<larnd_lut*>(lut), p.nb_sampling_bins_per_pixel, p.number_pix_neighbors, st);
+    if (rc0) return rc0;
+  }
+  A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm; A.sr = lut->sr; A.sc = lut->sc;
+  A.nt = lut->nt; A.L = lut->L; A.Lp = lut->Lp; A.ny_lut = lut->ny;
+  A.nticks = p.n_ticks;
+  A.nb = p.nb_sampling_bins_per_pixel;
+  A.half2 = 2 * (A.nb / 2) - 1;
+  A.n_neigh = p.number_pix_neighbors;
+  A.P = 2 * A.n_neigh + 1;
+  A.nxp = p.n_pixels_x; A.nyp = p.n_pixels_y;
+  A.ntpl = lut->ntpl;
+  A.lk.bitmap = ws.bitmap; A.lk.wprefix = ws.wprefix; A.lk.n_words = ws.n_words; A.lk.pid_offset = ws.pid_offset;
+  A.lk.n_unique = 0; A.lk.n_neg = 0; A.lk.npix = npix_capacity;
+  A.counts = counts;
+  A.wfs = wfs;
+  A.skip_garbage = flags & 1;
+  A.runs_tmp = reinterpret_cast<int4*>(ws.runs_tmp);
+  A.runs = reinterpret_cast<int4*>(ws.runs);
+  A.class_count = ws.class_count; A.class_start = ws.class_start; A.cursor = ws.cursor;
+  A.tile_info = reinterpret_cast<int4*>(ws.tile_info);
+  A.gcnt = ws.gcnt;
+  A.ncls = lut->ntpl * A.nb * A.nb;
+  LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * sizeof(int), st));
+  LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 16, st));
+  const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
+  prof_begin(1, st);
+  k_build_runs<<<(unsigned)chunks, LARND_CHUNK, 0, st>>>(A);
+  LARND_LAUNCH_CHECK("k_build_runs");
+  k_class_scan<<<1, 1024, 0, st>>>(A);
+  LARND_LAUNCH_CHECK("k_class_scan");
+  {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_scatter_runs<<<(unsigned)blocks, 256, 0, st>>>(A);
+    LARND_LAUNCH_CHECK("k_scatter_runs");
+  }
+  const int need = lut->L + 2 + SPAN_MAX_S;
+  int nsm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = min(nsm * 2, LARND_ROW0_COPIES);
+  A.row0 = ws.row0;
+  if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)grid * p.n_ticks * sizeof(float), st));
+  if (need <= 32 * 4) k_acc_tiles<4><<<grid, TILE_THREADS, 0, st>>>(A);
+  else if (need <= 32 * 5) k_acc_tiles<5><<<grid, TILE_THREADS, 0, st>>>(A);
+  else k_acc_tiles<6><<<grid, TILE_THREADS, 0, st>>>(A);
+  LARND_LAUNCH_CHECK("k_acc_tiles");
+  if (!A.skip_garbage) {
+    k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, grid, p.n_ticks, wfs);
+    LARND_LAUNCH_CHECK("k_reduce_row0");
+  }
+  // segments whose window touches the ends of the readout: per-segment path of accumulate.cu
+  int rc = larnd_launch_accumulate(n, p, lut, ws, npix_capacity, flags | LARND_ACC_SLOW_ONLY, wfs, counts, st);
+  prof_end(1, st);
+  return rc;
+}

@@ -38,7 +38,26 @@ struct Workspace {
   int64_t n_scan_blocks;
   int32_t pid_offset;  // nx*ny*ntpc: bit index of pixel id p is p + pid_offset (event -1 ids are negative)
   int64_t n_chunks_max;
+  // class-sorted accumulate (accumulate_sorted.cu): run records before / after the counting sort, class histogram,
+  // offsets and scatter cursors, tile table, counters {n_runs, n_tiles, tile counter}
+  char* runs_tmp;
+  char* runs;
+  int* class_count;
+  int* class_start;
+  int* cursor;
+  char* tile_info;
+  int* gcnt;
+  float* row0;
 };
+
+#define LARND_NCLS_MAX (LARND_MAX_TEMPLATES * 11 * 11)  // response classes: template index x in-pixel bin
+#define LARND_ROW0_COPIES 512                            // private garbage-row copies (>= CTAs of k_acc_tiles)
+#define LARND_ROW0_TICKS_MAX 8192
+#define LARND_ACC_SLOW_ONLY 0x100                        // internal flag of larnd_launch_accumulate
+#define LARND_SORTED_MIN_SEGMENTS 200000                 // below this the chunk kernel wins (few runs per class)
+size_t larnd_sorted_workspace_bytes(int64_t n);
+void larnd_carve_sorted(char* p, int64_t n, Workspace* ws);
+int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut);
 
 #define LARND_SCAN_WORDS_PER_BLOCK 2048
 #define LARND_CHUNK 128  // segments per accumulate CTA
@@ -108,6 +127,8 @@ int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t np
 int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                             int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
+int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                                   int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                 int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride, float* grad_params,
                                 const int32_t* counts, cudaStream_t st);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "liblarnd_b200.so")
-SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_bwd.cu", "fee.cu", "mc_current.cu"]
+SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "fee.cu", "mc_current.cu"]
 
 MAX_TPC = 8
 MAX_TEMPLATES = 128

@@ -89,6 +89,14 @@ def _hits_equal(out_o, out_p):
             assert np.array_equal(a, b), n
 
 
+@pytest.fixture(params=["chunk", "sorted"])
+def acc_impl(request, monkeypatch):
+    """Both accumulate kernels: the chunk kernel (accumulate.cu, small batches) and the class-sorted kernel
+    (accumulate_sorted.cu, picked automatically for >= 200k segments; forced here through LARND_ACC_IMPL)."""
+    monkeypatch.setenv("LARND_ACC_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("cfg", [
     dict(n=4, L=100, prec=0.005, nseg=2500, pad=60, ibatch=1),    # optimize/simulate_test.sh settings
     dict(n=2, L=150, prec=0.01, nseg=2000, pad=0, ibatch=0),      # optimize/fit_test.sh --lut settings
@@ -96,7 +104,7 @@ def _hits_equal(out_o, out_p):
     dict(n=1, L=30, prec=0.01, nseg=800, pad=10, ibatch=3),       # short window -> 4-slot kernel
     dict(n=2, L=400, prec=0.05, nseg=600, pad=0, ibatch=0),       # optimize/simulate_fwd.sh window -> 16-slot kernel
 ])
-def test_lut_forward_matches_oracle(torch_dev, cfg):
+def test_lut_forward_matches_oracle(torch_dev, cfg, acc_impl):
     from larndsim_b200 import sim
     kw = dict(number_pix_neighbors=cfg["n"], signal_length=cfg["L"])
     nx = max(10 * cfg["n"] + 5, 5)
@@ -132,7 +140,7 @@ def test_exact_shape_mode_reproduces_reference_padding(torch_dev):
         _check_wfs(wfs.cpu().numpy(), wfs_o)
 
 
-def test_unsorted_segments_and_edges(torch_dev):
+def test_unsorted_segments_and_edges(torch_dev, acc_impl):
     """Shuffled rows (no runs, constant row/window flushes), segments next to the anode (windows sticking out of the
     readout -> garbage tick 0) and outside every TPC."""
     rng = np.random.default_rng(3)
@@ -157,7 +165,7 @@ def test_unsorted_segments_and_edges(torch_dev):
     _check_wfs(w, full_o, uniq=uniq_o)
 
 
-def test_skip_garbage_flag_only_changes_garbage_rows(torch_dev):
+def test_skip_garbage_flag_only_changes_garbage_rows(torch_dev, acc_impl):
     from larndsim_b200 import sim
     import torch
     kw = dict(number_pix_neighbors=2, signal_length=100)
@@ -338,7 +346,7 @@ def test_mc_mode_matches_oracle(torch_dev):
         assert abs(g - fd) <= 5e-3 * abs(fd) + 1e-6 * abs(grad).max(), (name, g, fd)
 
 
-def test_full_fixture_batch_and_size_independent_properties(torch_dev):
+def test_full_fixture_batch_and_size_independent_properties(torch_dev, acc_impl):
     """A complete simulate_test.sh batch (input_0, batch 1: 10 879 segments + reference padding) against the oracle,
     then properties that hold at any size: linearity in the charge scale and additivity over disjoint event sets."""
     import torch
