@@ -45,8 +45,6 @@ struct AccArgs {
   int slow_only;  // 1: only segments whose window touches the ends of the readout (the rest is done by accumulate_sorted.cu)
 };
 
-__device__ __forceinline__ bool seg_is_fast(int T0, int L, int nticks) { return T0 >= 2 && T0 + L <= nticks - 2; }
-
 constexpr int KP = 8;            // tick positions per run (impulse train length)
 constexpr int SPAN_MAX = KP - 2;  // max (T0max - T0min) inside a run
 

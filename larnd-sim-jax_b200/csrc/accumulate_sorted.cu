@@ -27,7 +27,7 @@ namespace {
 constexpr int TR = 32;              // runs per tile (lane <-> run in the build phases)
 constexpr int KPT = 6;              // impulse positions per run
 constexpr int SPAN_MAX_S = KPT - 2;  // max (T0max - T0min) inside a run
-constexpr int MAXLEN = 16;          // segments per run (bounds the divergence of the lane <-> run build loops)
+constexpr int MAXLEN = 8;           // segments per run (bounds the divergence of the lane <-> run build loops)
 constexpr int TILE_THREADS = 256;
 constexpr int NW = TILE_THREADS / 32;
 constexpr int HS = 3 * KPT + 1;     // per-lane stride of the train buffer (odd: conflict-free)
@@ -63,8 +63,6 @@ struct SortArgs {
   int ncls;
   float* row0;  // [gridDim][nticks] per-CTA private copies of waveform row 0 (the garbage row every CTA adds to)
 };
-
-__device__ __forceinline__ bool seg_is_fast(int T0, int L, int nticks) { return T0 >= 2 && T0 + L <= nticks - 2; }
 
 // ------------------------------------------------------------------------------------------------ run building
 __global__ void __launch_bounds__(LARND_CHUNK)
@@ -203,15 +201,22 @@ __global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------ tile consumer
+constexpr int SEGMAX = TR * MAXLEN;  // segments per tile
+
 struct TileSmem {
   int4 run[TR];                 // start, len | span << 16, tmin, class
-  int ep[TR], mpx[TR], mpy[TR];
+  int ep[TR], mpx[TR], mpy[TR], soff[TR];
+  // per-segment data of the tile, staged once (thread <-> segment) and read by every unit's build phase
+  float qf[SEGMAX], qo[SEGMAX], ca[SEGMAX], cb[SEGMAX], cc[SEGMAX], fr[SEGMAX];
+  int m[SEGMAX];                // T0 - tmin of the run
+  float wxg[5][SEGMAX], wyg[5][SEGMAX];  // transverse weights merged per group of the class
+  unsigned char owner[SEGMAX];
   float hN[TR][KPT];            // neighbour impulse train (full segment charge)
   float mom[TR][MS];            // neighbour correction moments A1,A2,A3,B1,B3 per position
   float ph[NW][TR * HS];        // per-warp trains of the current unit: [run][3*j + template]
   float pE[NW][TR * ES];        // per-warp merged boundary corrections: [run][position]
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
-  int tile, next_unit;
+  int tile, next_unit, nseg;
 };
 
 template <int NS, int NR>
@@ -227,20 +232,66 @@ __device__ __forceinline__ void load_response(float (&Rw)[3][NS][KPT], const flo
       }
 }
 
-template <int NS>
-__device__ __forceinline__ void flush_window(const float (&acc)[NS], float* wfs, int64_t nticks, int row, int tmin, int lane,
-                                             float sign) {
-  float* dst = wfs + (int64_t)row * nticks + (tmin - 1) + lane;
-  const int lim = (int)nticks - (tmin - 1) - lane;  // columns left in the row (never reached by a finite fast run)
+// acc[x] += sum_{j < NPOS} sum_r h[j*NR + r] * R_r[x - 1 - j]: pure FFMAs on the register-resident response
+template <int NS, int NR, int NPOS>
+__device__ __forceinline__ void conv_fixed(float (&acc)[NS], const float (&Rw)[3][NS][KPT], const float* __restrict__ h) {
 #pragma unroll
-  for (int s = 0; s < NS; ++s)
-    if (acc[s] != 0.0f && 32 * s < lim) atomicAdd(dst + 32 * s, sign * acc[s]);  // RED.E.ADD.F32, coalesced
+  for (int j = 0; j < NPOS; ++j) {
+    float hv[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) hv[r] = h[NR * j + r];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[s] = fmaf(hv[r], Rw[r][s][j], acc[s]);
+  }
+}
+
+template <int NS, int NR>
+__device__ __forceinline__ void conv(float (&acc)[NS], const float (&Rw)[3][NS][KPT], const float* __restrict__ h, int npos) {
+  switch (npos) {  // warp-uniform: one branch per (run, unit) instead of one per position
+    case 2: conv_fixed<NS, NR, 2>(acc, Rw, h); break;
+    case 3: conv_fixed<NS, NR, 3>(acc, Rw, h); break;
+    case 4: conv_fixed<NS, NR, 4>(acc, Rw, h); break;
+    case 5: conv_fixed<NS, NR, 5>(acc, Rw, h); break;
+    default: conv_fixed<NS, NR, KPT>(acc, Rw, h); break;
+  }
+}
+
+// Adds one (run, unit) window to a waveform row: acc = window part, Ev = merged boundary correction of this lane
+// (slot 0, lanes < ES).  Column of (slot s, lane) is tmin - 1 + 32 s + lane.  Window samples are valid on columns
+// >= 2, corrections on columns >= 1; what falls below goes to the garbage column 0 (sim_jax.py:177-178,243-244).
+template <int NS>
+__device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, float* rowbase, int tmin, int nticks, int lane,
+                                            float sign) {
+  if (tmin >= 2 && tmin - 2 + 32 * NS < nticks) {  // warp-uniform, the common case: whole register window inside the row
+    float* dst = rowbase + (tmin - 1) + lane;
+    const float v0 = acc[0] + Ev;
+    if (v0 != 0.0f) atomicAdd(dst, sign * v0);  // RED.E.ADD.F32, coalesced
+#pragma unroll
+    for (int s = 1; s < NS; ++s)
+      if (acc[s] != 0.0f) atomicAdd(dst + 32 * s, sign * acc[s]);
+  } else {
+    float g = 0.0f;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int col = tmin - 1 + 32 * s + lane;
+      const float w = acc[s], e = (s == 0) ? Ev : 0.0f;
+      const float v = (col >= 2 ? w : 0.0f) + (col >= 1 ? e : 0.0f);
+      g += (col < 2 ? w : 0.0f) + (col < 1 ? e : 0.0f);
+      if (v != 0.0f && col < nticks) atomicAdd(rowbase + col, sign * v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    if (lane == 0 && g != 0.0f) atomicAdd(rowbase, sign * g);
+  }
 }
 
 template <int NS>
 __global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? 2 : 1)
 k_acc_tiles(const __grid_constant__ SortArgs A) {
-  __shared__ TileSmem sm;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
   if (A.counts[2] != 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb = A.nb, L = A.L;
@@ -284,27 +335,75 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
     const int4 ti = A.tile_info[tile];
     const int cls = ti.x, count = ti.z;
     const int bym = cls % nb, bxm = (cls / nb) % nb, idx = cls / (nb * nb);
-    // ---- stage the runs; neighbour impulse train + correction moments (thread <-> run) -------------------------
+    // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
+    if (warp == 0) {
+      int len = 0;
+      if (lane < count) {
+        const int4 e = A.runs[ti.y + lane];
+        sm.run[lane] = e;
+        const int64_t s0 = e.x;
+        sm.ep[lane] = irec[(int64_t)LARND_I_EP * n + s0];
+        sm.mpx[lane] = floordiv_i(irec[(int64_t)LARND_I_BX * n + s0], nb);
+        sm.mpy[lane] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
+        len = e.y & 0xffff;
+      }
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      const int off = inc - len;
+      sm.soff[lane] = off;
+      for (int t = 0; t < len; ++t) sm.owner[off + t] = (unsigned char)lane;
+      if (lane == 31) sm.nseg = inc;
+    }
+    __syncthreads();
+    // ---- stage the segments (thread <-> segment): products, Lagrange weights, group-merged transverse weights ---
+    for (int i = threadIdx.x; i < sm.nseg; i += TILE_THREADS) {
+      const int r = sm.owner[i];
+      const int4 e = sm.run[r];
+      const int64_t s = (int64_t)e.x + (i - sm.soff[r]);
+      const float q = A.rec[(int64_t)LARND_F_Q * n + s], f = A.rec[(int64_t)LARND_F_FRAC * n + s];
+      sm.qf[i] = q * f;
+      sm.qo[i] = q * (1.0f - f);
+      sm.fr[i] = f;
+      sm.ca[i] = A.rec[(int64_t)LARND_F_A * n + s];
+      sm.cb[i] = A.rec[(int64_t)LARND_F_B * n + s];
+      sm.cc[i] = A.rec[(int64_t)LARND_F_C * n + s];
+      sm.m[i] = irec[(int64_t)LARND_I_T0 * n + s] - e.z;
+      float vx[LARND_NB_TRAN_BINS], vy[LARND_NB_TRAN_BINS];
+#pragma unroll
+      for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
+        vx[k] = A.rec[(int64_t)(LARND_F_WX0 + k) * n + s];
+        vy[k] = A.rec[(int64_t)(LARND_F_WY0 + k) * n + s];
+      }
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {
+        const int mx = g < sm.g_n[bxm] ? sm.g_mask[bxm][g] : 0, my = g < sm.g_n[bym] ? sm.g_mask[bym][g] : 0;
+        float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+        for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) { sx += (mx >> k & 1) ? vx[k] : 0.0f; sy += (my >> k & 1) ? vy[k] : 0.0f; }
+        sm.wxg[g][i] = sx;
+        sm.wyg[g][i] = sy;
+      }
+    }
+    __syncthreads();
+    // ---- neighbour impulse train + correction moments (thread <-> run) -------------------------------------------
     if (threadIdx.x < count) {
       const int r = threadIdx.x;
-      const int4 e = A.runs[ti.y + r];
-      sm.run[r] = e;
-      const int64_t s0 = e.x;
-      sm.ep[r] = irec[(int64_t)LARND_I_EP * n + s0];
-      sm.mpx[r] = floordiv_i(irec[(int64_t)LARND_I_BX * n + s0], nb);
-      sm.mpy[r] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
 #pragma unroll
       for (int k = 0; k < KPT; ++k) sm.hN[r][k] = 0.0f;
       for (int k = 0; k < 5 * KPT; ++k) sm.mom[r][k] = 0.0f;
-      const int len = e.y & 0xffff, tmin = e.z;
+      const int len = sm.run[r].y & 0xffff, so = sm.soff[r];
       for (int t = 0; t < len; ++t) {
-        const int64_t s = s0 + t;
-        const float q = A.rec[(int64_t)LARND_F_Q * n + s], f = A.rec[(int64_t)LARND_F_FRAC * n + s], o = 1.0f - f;
-        const int m = irec[(int64_t)LARND_I_T0 * n + s] - tmin;
-        sm.hN[r][m] += q * f;
-        sm.hN[r][m + 1] += q * o;
+        const int i = so + t;
+        const float qf = sm.qf[i], qo = sm.qo[i], f = sm.fr[i], o = 1.0f - f;
+        const int m = sm.m[i];
+        sm.hN[r][m] += qf;
+        sm.hN[r][m + 1] += qo;
         float* mo = sm.mom[r] + 5 * m;
-        mo[0] += q * o; mo[1] += q * o * o; mo[2] += q * f * o; mo[3] += q * f; mo[4] += q * f * f;
+        mo[0] += qo; mo[1] += qo * o; mo[2] += qf * o; mo[3] += qf; mo[4] += qf * f;
       }
     }
     __syncthreads();
@@ -320,7 +419,6 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
         if (gi >= sm.g_n[bxm] || gj >= sm.g_n[bym]) continue;
         const int bin = (int)sm.g_ci[bxm][gi] * 5 + (int)sm.g_ci[bym][gj];
-        const unsigned mx = sm.g_mask[bxm][gi], my = sm.g_mask[bym][gj];
         const int ox = (int)sm.g_ox[bxm][gi] - 1, oy = (int)sm.g_ox[bym][gj] - 1;
         int row = -1;
         if (lane < count) {
@@ -338,31 +436,24 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
 #pragma unroll
           for (int k = 0; k < ES; ++k) E[k] = 0.0f;
           const int4 e = sm.run[lane];
-          const int len = e.y & 0xffff, tmin = e.z;
+          const int len = e.y & 0xffff, tmin = e.z, so = sm.soff[lane];
           const float* crow = A.cm + (int64_t)(idx * 25 + bin) * A.nt;
           const float Cl = __ldg(crow + A.nt - L);
+          const float* wxp = sm.wxg[gi];
+          const float* wyp = sm.wyg[gj];
           for (int t = 0; t < len; ++t) {
-            const int64_t s = (int64_t)e.x + t;
-            float sx = 0.0f, sy = 0.0f;
-#pragma unroll
-            for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
-              if (mx >> k & 1) sx += A.rec[(int64_t)(LARND_F_WX0 + k) * n + s];
-              if (my >> k & 1) sy += A.rec[(int64_t)(LARND_F_WY0 + k) * n + s];
-            }
-            const float w = sx * sy;
-            const float q = A.rec[(int64_t)LARND_F_Q * n + s], f = A.rec[(int64_t)LARND_F_FRAC * n + s];
-            const float ca = A.rec[(int64_t)LARND_F_A * n + s], cb = A.rec[(int64_t)LARND_F_B * n + s],
-                        cc = A.rec[(int64_t)LARND_F_C * n + s];
-            const int T0 = irec[(int64_t)LARND_I_T0 * n + s];
-            const int m = T0 - tmin;
-            const float qf = (w * q) * f, qo = (w * q) * (1.0f - f);
+            const int i = so + t;
+            const int m = sm.m[i];
+            // boundary correction of this segment (sim_jax.py:236-247): D lands on tick T0 (weight 1-f) and T0-1 (f)
+            int ct = A.nt - L - (tmin + m);
+            ct = max(0, min(ct, A.nt - 1));
+            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
+            const float w = wxp[i] * wyp[i];
+            const float qf = w * sm.qf[i], qo = w * sm.qo[i], f = sm.fr[i];
+            const float ca = sm.ca[i], cb = sm.cb[i], cc = sm.cc[i];
             float* hm = h + 3 * m;
             hm[0] = fmaf(qf, ca, hm[0]); hm[1] = fmaf(qf, cb, hm[1]); hm[2] = fmaf(qf, cc, hm[2]);
             hm[3] = fmaf(qo, ca, hm[3]); hm[4] = fmaf(qo, cb, hm[4]); hm[5] = fmaf(qo, cc, hm[5]);
-            // boundary correction of this segment (sim_jax.py:236-247): D lands on tick T0 (weight 1-f) and T0-1 (f)
-            int ct = A.nt - L - T0;
-            ct = max(0, min(ct, A.nt - 1));
-            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
             const float D = Cl - (Ca * (1.0f - f) + Cb * f);
             E[m] = fmaf(qf, D, E[m]);
             E[m + 1] = fmaf(qo, D, E[m + 1]);
@@ -377,21 +468,12 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
           const int rowp = __shfl_sync(0xffffffffu, row, p);
           if (rowp < 0) continue;
           const int4 e = sm.run[p];
-          const int npos = (e.y >> 16) + 2;
-          const float* h = myh + p * HS;
           float acc[NS];
 #pragma unroll
           for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
-#pragma unroll
-          for (int j = 0; j < KPT; ++j) {
-            if (j < npos) {
-              const float h0 = h[3 * j], h1 = h[3 * j + 1], h2 = h[3 * j + 2];
-#pragma unroll
-              for (int s = 0; s < NS; ++s) acc[s] = fmaf(h2, Rw[2][s][j], fmaf(h1, Rw[1][s][j], fmaf(h0, Rw[0][s][j], acc[s])));
-            }
-          }
-          if (lane < ES) acc[0] += myE[p * ES + lane];
-          flush_window<NS>(acc, A.wfs, A.nticks, rowp, e.z, lane, 1.0f);
+          conv<NS, 3>(acc, Rw, myh + p * HS, (e.y >> 16) + 2);
+          const float Ev = lane < ES ? myE[p * ES + lane] : 0.0f;
+          emit_window<NS>(acc, Ev, A.wfs + (int64_t)rowp * A.nticks, e.z, A.nticks, lane, 1.0f);
         }
         __syncwarp();
       } else {
@@ -461,22 +543,14 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
           owned &= owned - 1;
           const int rowp = __shfl_sync(0xffffffffu, row, p);
           const int4 e = sm.run[p];
-          const int npos = (e.y >> 16) + 2;
           float acc[NS];
 #pragma unroll
           for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
-#pragma unroll
-          for (int j = 0; j < KPT; ++j) {
-            if (j < npos) {
-              const float hj = sm.hN[p][j];
-#pragma unroll
-              for (int s = 0; s < NS; ++s) acc[s] = fmaf(hj, Rw[0][s][j], acc[s]);
-            }
-          }
-          if (lane < ES) acc[0] += myE[p * ES + lane];
-          if (sum_unit) flush_window<NS>(acc, row0, A.nticks, 0, e.z, lane, 1.0f);
-          else flush_window<NS>(acc, A.wfs, A.nticks, rowp, e.z, lane, 1.0f);
-          if (dual) flush_window<NS>(acc, row0, A.nticks, 0, e.z, lane, -1.0f);
+          conv<NS, 1>(acc, Rw, sm.hN[p], (e.y >> 16) + 2);
+          const float Ev = lane < ES ? myE[p * ES + lane] : 0.0f;
+          if (sum_unit) emit_window<NS>(acc, Ev, row0, e.z, A.nticks, lane, 1.0f);
+          else emit_window<NS>(acc, Ev, A.wfs + (int64_t)rowp * A.nticks, e.z, A.nticks, lane, 1.0f);
+          if (dual) emit_window<NS>(acc, Ev, row0, e.z, A.nticks, lane, -1.0f);
         }
         __syncwarp();
       }
@@ -575,9 +649,17 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
   const int grid = min(nsm * 2, LARND_ROW0_COPIES);
   A.row0 = ws.row0;
   if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)grid * p.n_ticks * sizeof(float), st));
-  if (need <= 32 * 4) k_acc_tiles<4><<<grid, TILE_THREADS, 0, st>>>(A);
-  else if (need <= 32 * 5) k_acc_tiles<5><<<grid, TILE_THREADS, 0, st>>>(A);
-  else k_acc_tiles<6><<<grid, TILE_THREADS, 0, st>>>(A);
+  const size_t smem = sizeof(TileSmem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  if (need <= 32 * 4) k_acc_tiles<4><<<grid, TILE_THREADS, smem, st>>>(A);
+  else if (need <= 32 * 5) k_acc_tiles<5><<<grid, TILE_THREADS, smem, st>>>(A);
+  else k_acc_tiles<6><<<grid, TILE_THREADS, smem, st>>>(A);
   LARND_LAUNCH_CHECK("k_acc_tiles");
   if (!A.skip_garbage) {
     k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, grid, p.n_ticks, wfs);

@@ -88,6 +88,10 @@ __device__ __forceinline__ int floordiv_i(int a, int b) {  // python-style floor
   return (a % b != 0 && a < 0) ? q - 1 : q;
 }
 
+// Segments whose response window ends inside the readout are handled by the class-sorted kernel (windows sticking out
+// at the LOW end are handled there too: garbage column 0); the rest goes through accumulate.cu's per-segment path.
+__device__ __forceinline__ bool seg_is_fast(int T0, int L, int nticks) { return T0 + L <= nticks - 2; }
+
 // pixel2id with int32 wrap-around (detsim_jax.py:232-244; x64 is never enabled in the reference)
 __device__ __forceinline__ int pixel2id_dev(int px, int py, int ep, int nx, int ny) {
   if (px >= nx || py >= ny || px < 0 || py < 0) return -1;
