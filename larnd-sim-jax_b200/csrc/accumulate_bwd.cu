@@ -13,6 +13,8 @@
 // quench / diffusion-weight math for its own segment (drifting_jax.py:42-50, quenching_jax.py:18-35,
 // detsim_jax.py:332-341, sim_jax.py:157-168,406-423).  The LARND_NPARAMS parameter gradients are reduced per CTA,
 // written as per-chunk partials and summed in double by a second tiny kernel (deterministic, no float atomics).
+#include <stdlib.h>
+
 #include "larnd_common.cuh"
 
 namespace {
@@ -42,6 +44,7 @@ struct BwdArgs {
   float* partials;
   int skip_garbage;
   const int* garbage_grad_nonzero;  // device flag written by k_garbage_grad_flag
+  int sorted_active;  // the class-sorted kernel (accumulate_bwd_sorted.cu) runs too and takes every segment it can handle
 };
 
 constexpr int MAXK = 16;        // distinct main pixels per chunk served from the shared row table
@@ -192,6 +195,17 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
   RowLookup lk = A.lk;
   lk.n_unique = A.counts[0];
   lk.n_neg = A.counts[1];
+  // With the class-sorted kernel active and zero garbage-row gradients, only segments whose window ends beyond the
+  // readout are left for this kernel (none for the usual Nt/L); otherwise it does everything and the sorted kernel idles.
+  const bool slow_only = A.sorted_active && skip_garbage;
+  if (slow_only) {
+    int slow = 0;
+    if ((int)threadIdx.x < ns) slow = !seg_is_fast(irec[(int64_t)LARND_I_T0 * n + s_base + threadIdx.x], L, A.nticks);
+    if (!__syncthreads_or(slow)) {
+      if (threadIdx.x < LARND_NPARAMS) A.partials[(int64_t)blockIdx.x * 16 + threadIdx.x] = 0.0f;
+      return;
+    }
+  }
   // ---- stage the chunk ----------------------------------------------------------------------------------
   for (int t = threadIdx.x; t < ns; t += BWD_THREADS) {
     const int64_t s = s_base + t;
@@ -234,6 +248,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
     for (int t = 0; t < ns; ++t) {
       if (!(sm.flags[t] & 1)) continue;  // outside every TPC: q == 0 and dq/dtheta == 0 (mask factor) -> no gradient
       const int T0 = __float_as_int(sm.seg[t].z);
+      if (slow_only && seg_is_fast(T0, L, A.nticks)) continue;  // done by the class-sorted kernel
       bool fresh = cur < 0;
       if (!fresh) {
         const int t0s = sm.run[cur].start;
@@ -571,7 +586,6 @@ int launch_bwd(const BwdArgs& A, const larnd_params_t& p, int64_t chunks, cudaSt
     LARND_CUDA(cudaFuncSetAttribute(k_lut_backward<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  prof_begin(2, st);
   k_lut_backward<NG><<<(unsigned)chunks, BWD_THREADS, smem, st>>>(A, p);
   prof_end(2, st);
   LARND_LAUNCH_CHECK("k_lut_backward");
@@ -607,6 +621,20 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   k_garbage_grad_flag<<<32, 256, 0, st>>>(g_wfs, g_stride, p.n_ticks, counts, gflag);
   LARND_LAUNCH_CHECK("k_garbage_grad_flag");
   A.garbage_grad_nonzero = gflag;
+  // large batches: the class-sorted kernel does the bulk (LARND_ACC_IMPL = chunk | sorted overrides the size rule)
+  bool sorted = larnd_sorted_supported(p, lut) && n >= LARND_SORTED_MIN_SEGMENTS;
+  if (const char* e = getenv("LARND_ACC_IMPL")) sorted = larnd_sorted_supported(p, lut) && e[0] == 's';
+  A.sorted_active = sorted ? 1 : 0;
+  prof_begin(2, st);
+  if (sorted) {
+    float* sorted_partials = ws.partials + (size_t)ws.n_chunks_max * 16;
+    int n_slots = 0;
+    int rc0 = larnd_launch_accumulate_bwd_sorted(n, p, lut, ws, npix_capacity, flags, g_wfs, g_stride, sorted_partials, &n_slots,
+                                                 gflag, counts, st);
+    if (rc0) return rc0;
+    k_reduce_partials<<<LARND_NPARAMS, 256, 0, st>>>(sorted_partials, n_slots, grad_params);
+    LARND_LAUNCH_CHECK("k_reduce_partials");
+  }
   const int need = lut->L + SPAN_MAX + 2;  // gradient window of a run: ticks tmin .. tmin + span + 1 + L - 1
   int rc;
   if (need <= 32 * 2) rc = launch_bwd<2>(A, p, chunks, st);

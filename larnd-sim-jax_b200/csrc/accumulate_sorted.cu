@@ -20,185 +20,9 @@
 //
 // Segments whose window touches the ends of the readout (garbage tick 0 handling, sim_jax.py:177-178,243-244)
 // are left to accumulate.cu's per-segment path (larnd_launch_accumulate with mode = slow-only).
-#include "larnd_common.cuh"
+#include "sorted_runs.cuh"
 
 namespace {
-
-constexpr int TR = 32;              // runs per tile (lane <-> run in the build phases)
-constexpr int KPT = 6;              // impulse positions per run
-constexpr int SPAN_MAX_S = KPT - 2;  // max (T0max - T0min) inside a run
-constexpr int MAXLEN = 8;           // segments per run (bounds the divergence of the lane <-> run build loops)
-constexpr int TILE_THREADS = 256;
-constexpr int NW = TILE_THREADS / 32;
-constexpr int HS = 3 * KPT + 1;     // per-lane stride of the train buffer (odd: conflict-free)
-constexpr int ES = KPT + 1;         // per-lane stride of the correction buffer (odd)
-constexpr int MS = 5 * KPT + 1;     // per-run stride of the neighbour moments (odd)
-
-struct SortArgs {
-  const float* rec;
-  int64_t n;
-  const float* r0;
-  const float* rm;
-  const float* c0;
-  const float* cm;
-  const float* sr;
-  const float* sc;
-  int nt, L, Lp, ny_lut;
-  int nticks;
-  int nb, half2;
-  int n_neigh, P;
-  int nxp, nyp;
-  int ntpl;
-  RowLookup lk;
-  const int32_t* counts;
-  float* wfs;
-  int skip_garbage;
-  int4* runs_tmp;
-  int4* runs;
-  int* class_count;
-  int* class_start;
-  int* cursor;
-  int4* tile_info;
-  int* gcnt;  // [0] number of runs, [1] number of tiles, [2] tile counter
-  int ncls;
-  float* row0;  // [gridDim][nticks] per-CTA private copies of waveform row 0 (the garbage row every CTA adds to)
-};
-
-// ------------------------------------------------------------------------------------------------ run building
-__global__ void __launch_bounds__(LARND_CHUNK)
-k_build_runs(const __grid_constant__ SortArgs A) {
-  __shared__ int s_ep[LARND_CHUNK], s_bx[LARND_CHUNK], s_by[LARND_CHUNK], s_idx[LARND_CHUNK], s_T0[LARND_CHUNK];
-  __shared__ unsigned char s_fast[LARND_CHUNK], s_kh[LARND_CHUNK], s_head[LARND_CHUNK];
-  __shared__ int s_wcnt[LARND_CHUNK / 32], s_base;
-  if (A.counts[2] != 0) return;
-  const int t = threadIdx.x;
-  const int64_t base = (int64_t)blockIdx.x * LARND_CHUNK;
-  const int ns = (int)min((int64_t)LARND_CHUNK, A.n - base);
-  const int* irec = reinterpret_cast<const int*>(A.rec);
-  if (t < ns) {
-    const int64_t s = base + t;
-    s_ep[t] = irec[(int64_t)LARND_I_EP * A.n + s];
-    s_bx[t] = irec[(int64_t)LARND_I_BX * A.n + s];
-    s_by[t] = irec[(int64_t)LARND_I_BY * A.n + s];
-    s_idx[t] = irec[(int64_t)LARND_I_IDX * A.n + s];
-    const int T0 = irec[(int64_t)LARND_I_T0 * A.n + s];
-    s_T0[t] = T0;
-    s_fast[t] = seg_is_fast(T0, A.L, A.nticks);
-  }
-  s_head[t] = 0;
-  __syncthreads();
-  bool kh = false;
-  if (t < ns) {
-    kh = t == 0 || s_ep[t] != s_ep[t - 1] || s_bx[t] != s_bx[t - 1] || s_by[t] != s_by[t - 1] || s_idx[t] != s_idx[t - 1] ||
-         s_fast[t] != s_fast[t - 1];
-    s_kh[t] = kh;
-  }
-  __syncthreads();
-  // the head of every key-run walks it once and cuts it greedily on the tick span / length limits
-  if (kh && s_fast[t]) {
-    int tmin = s_T0[t], tmax = tmin, start = t;
-    s_head[t] = 1;
-    for (int u = t + 1; u < ns && !s_kh[u]; ++u) {
-      const int T0 = s_T0[u];
-      if (max(tmax, T0) - min(tmin, T0) > SPAN_MAX_S || u - start >= MAXLEN) {
-        s_head[u] = 1;
-        start = u;
-        tmin = tmax = T0;
-      } else {
-        tmin = min(tmin, T0);
-        tmax = max(tmax, T0);
-      }
-    }
-  }
-  __syncthreads();
-  const bool head = t < ns && s_head[t];
-  const unsigned bal = __ballot_sync(0xffffffffu, head);
-  const int lane = t & 31, wid = t >> 5;
-  if (lane == 0) s_wcnt[wid] = __popc(bal);
-  __syncthreads();
-  int before = __popc(bal & ((1u << lane) - 1u));
-  int total = 0;
-#pragma unroll
-  for (int w = 0; w < LARND_CHUNK / 32; ++w) {
-    if (w < wid) before += s_wcnt[w];
-    total += s_wcnt[w];
-  }
-  if (t == 0) s_base = total > 0 ? atomicAdd(A.gcnt, total) : 0;
-  __syncthreads();
-  if (head) {
-    int tmin = s_T0[t], tmax = tmin, len = 1;
-    for (int u = t + 1; u < ns && !s_kh[u] && !s_head[u]; ++u) {
-      tmin = min(tmin, s_T0[u]);
-      tmax = max(tmax, s_T0[u]);
-      ++len;
-    }
-    const int nb = A.nb;
-    const int bxm = s_bx[t] - floordiv_i(s_bx[t], nb) * nb, bym = s_by[t] - floordiv_i(s_by[t], nb) * nb;
-    const int cls = (s_idx[t] * nb + bxm) * nb + bym;
-    A.runs_tmp[s_base + before] = make_int4((int)(base + t), len | ((tmax - tmin) << 16), tmin, cls);
-    atomicAdd(A.class_count + cls, 1);
-  }
-}
-
-// exclusive scans over the class histogram: run offsets and tile offsets; then the tile table
-__global__ void __launch_bounds__(1024)
-k_class_scan(const __grid_constant__ SortArgs A) {
-  __shared__ int s_w[2][32];
-  __shared__ int carry[2];
-  if (A.counts[2] != 0) return;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
-  __syncthreads();
-  for (int c0 = 0; c0 < A.ncls; c0 += 1024) {
-    const int c = c0 + threadIdx.x;
-    const int cnt = c < A.ncls ? A.class_count[c] : 0;
-    int v[2] = {cnt, (cnt + TR - 1) / TR};
-    int inc[2] = {v[0], v[1]};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, inc[k], o);
-        if (lane >= o) inc[k] += u;
-      }
-      if (lane == 31) s_w[k][wid] = inc[k];
-    }
-    __syncthreads();
-    if (wid < 2) {
-      int w = s_w[wid][lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += u;
-      }
-      s_w[wid][lane] = w;
-    }
-    __syncthreads();
-    int ex[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) ex[k] = carry[k] + (wid > 0 ? s_w[k][wid - 1] : 0) + inc[k] - v[k];
-    if (c < A.ncls) {
-      A.class_start[c] = ex[0];
-      A.cursor[c] = ex[0];
-      for (int i = 0; i < v[1]; ++i)  // tiles of this class
-        A.tile_info[ex[1] + i] = make_int4(c, ex[0] + i * TR, min(TR, cnt - i * TR), 0);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { carry[0] += s_w[0][31]; carry[1] += s_w[1][31]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) A.gcnt[1] = carry[1];
-}
-
-__global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
-  if (A.counts[2] != 0) return;
-  const int nruns = A.gcnt[0];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nruns; i += gridDim.x * blockDim.x) {
-    const int4 e = A.runs_tmp[i];
-    const int pos = atomicAdd(A.cursor + e.w, 1);
-    A.runs[pos] = e;
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ tile consumer
 constexpr int SEGMAX = TR * MAXLEN;  // segments per tile
@@ -216,6 +40,7 @@ struct TileSmem {
   float ph[NW][TR * HS];        // per-warp trains of the current unit: [run][3*j + template]
   float pE[NW][TR * ES];        // per-warp merged boundary corrections: [run][position]
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
+  signed char udx[225], udy[225];  // relative pixel of every neighbour unit (P <= 15)
   int tile, next_unit, nseg;
 };
 
@@ -249,13 +74,13 @@ __device__ __forceinline__ void conv_fixed(float (&acc)[NS], const float (&Rw)[3
 
 template <int NS, int NR>
 __device__ __forceinline__ void conv(float (&acc)[NS], const float (&Rw)[3][NS][KPT], const float* __restrict__ h, int npos) {
-  switch (npos) {  // warp-uniform: one branch per (run, unit) instead of one per position
-    case 2: conv_fixed<NS, NR, 2>(acc, Rw, h); break;
-    case 3: conv_fixed<NS, NR, 3>(acc, Rw, h); break;
-    case 4: conv_fixed<NS, NR, 4>(acc, Rw, h); break;
-    case 5: conv_fixed<NS, NR, 5>(acc, Rw, h); break;
-    default: conv_fixed<NS, NR, KPT>(acc, Rw, h); break;
-  }
+  // warp-uniform: a short compare chain per (run, unit) instead of one branch per position (no jump table)
+  if (npos <= 3) {
+    if (npos == 2) conv_fixed<NS, NR, 2>(acc, Rw, h);
+    else conv_fixed<NS, NR, 3>(acc, Rw, h);
+  } else if (npos == 4) conv_fixed<NS, NR, 4>(acc, Rw, h);
+  else if (npos == 5) conv_fixed<NS, NR, 5>(acc, Rw, h);
+  else conv_fixed<NS, NR, KPT>(acc, Rw, h);
 }
 
 // Adds one (run, unit) window to a waveform row: acc = window part, Ev = merged boundary correction of this lane
@@ -316,6 +141,10 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
     }
     sm.g_n[bq] = ng;
   }
+  for (int u = threadIdx.x; u < A.P * A.P; u += TILE_THREADS) {
+    sm.udx[u] = (signed char)(u / A.P - A.n_neigh);
+    sm.udy[u] = (signed char)(u % A.P - A.n_neigh);
+  }
   const int ntiles = A.gcnt[1];
   const int n_neigh_units = A.P * A.P;
   const int n_units = 25 + 1 + n_neigh_units;  // merged diffusion groups, neighbourhood-sum row, neighbour pixels
@@ -334,7 +163,8 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
     if (tile >= ntiles) break;
     const int4 ti = A.tile_info[tile];
     const int cls = ti.x, count = ti.z;
-    const int bym = cls % nb, bxm = (cls / nb) % nb, idx = cls / (nb * nb);
+    const int cls_b = cls / (SPAN_MAX_S + 1);  // class = ((idx * nb + bxm) * nb + bym) * (SPAN_MAX_S + 1) + span
+    const int bym = cls_b % nb, bxm = (cls_b / nb) % nb, idx = cls_b / (nb * nb);
     // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
     if (warp == 0) {
       int len = 0;
@@ -483,7 +313,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         const bool sum_unit = unit == 25;
         if (sum_unit && A.skip_garbage) continue;
         const int u = unit - 26;
-        const int dx = sum_unit ? 0 : u / A.P - A.n_neigh, dy = sum_unit ? 0 : u % A.P - A.n_neigh;
+        const int dx = sum_unit ? 0 : (int)sm.udx[u], dy = sum_unit ? 0 : (int)sm.udy[u];
         if (!sum_unit && dx == 0 && dy == 0) continue;  // the centre id is -999: row 0 only (inside the sum row)
         int row = -1;
         if (lane < count) {
@@ -593,7 +423,7 @@ void larnd_carve_sorted(char* p, int64_t n, Workspace* ws) {
 
 int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut) {
   const int nb = p.nb_sampling_bins_per_pixel;
-  if (lut->ntpl * nb * nb > LARND_NCLS_MAX) return 0;
+  if (lut->ntpl * nb * nb * (SPAN_MAX_S + 1) > LARND_NCLS_MAX) return 0;
   if (lut->L + 2 + SPAN_MAX_S > 32 * 6) return 0;
   if (p.n_ticks > LARND_ROW0_TICKS_MAX) return 0;
   return 1;
@@ -602,52 +432,20 @@ int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut) {
 int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                    int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
   if (n == 0) return LARND_OK;
-  if (n >= (int64_t)1 << 31) { larnd_set_error("sorted accumulate: n must be < 2^31"); return LARND_E_ARG; }
   SortArgs A;
-  A.rec = ws.rec; A.n = n;
   {
     int rc0 = larnd_lut_ensure_neighbour_sums(const_cast<larnd_lut*>(lut), p.nb_sampling_bins_per_pixel, p.number_pix_neighbors, st);
     if (rc0) return rc0;
   }
-  A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm; A.sr = lut->sr; A.sc = lut->sc;
-  A.nt = lut->nt; A.L = lut->L; A.Lp = lut->Lp; A.ny_lut = lut->ny;
-  A.nticks = p.n_ticks;
-  A.nb = p.nb_sampling_bins_per_pixel;
-  A.half2 = 2 * (A.nb / 2) - 1;
-  A.n_neigh = p.number_pix_neighbors;
-  A.P = 2 * A.n_neigh + 1;
-  A.nxp = p.n_pixels_x; A.nyp = p.n_pixels_y;
-  A.ntpl = lut->ntpl;
-  A.lk.bitmap = ws.bitmap; A.lk.wprefix = ws.wprefix; A.lk.n_words = ws.n_words; A.lk.pid_offset = ws.pid_offset;
-  A.lk.n_unique = 0; A.lk.n_neg = 0; A.lk.npix = npix_capacity;
-  A.counts = counts;
   A.wfs = wfs;
   A.skip_garbage = flags & 1;
-  A.runs_tmp = reinterpret_cast<int4*>(ws.runs_tmp);
-  A.runs = reinterpret_cast<int4*>(ws.runs);
-  A.class_count = ws.class_count; A.class_start = ws.class_start; A.cursor = ws.cursor;
-  A.tile_info = reinterpret_cast<int4*>(ws.tile_info);
-  A.gcnt = ws.gcnt;
-  A.ncls = lut->ntpl * A.nb * A.nb;
-  LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * sizeof(int), st));
-  LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 16, st));
-  const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
   prof_begin(1, st);
-  k_build_runs<<<(unsigned)chunks, LARND_CHUNK, 0, st>>>(A);
-  LARND_LAUNCH_CHECK("k_build_runs");
-  k_class_scan<<<1, 1024, 0, st>>>(A);
-  LARND_LAUNCH_CHECK("k_class_scan");
   {
-    int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    k_scatter_runs<<<(unsigned)blocks, 256, 0, st>>>(A);
-    LARND_LAUNCH_CHECK("k_scatter_runs");
+    int rc0 = sorted_fill_and_build(A, n, p, lut, ws, npix_capacity, counts, st);
+    if (rc0) return rc0;
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
-  int nsm = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-  const int grid = min(nsm * 2, LARND_ROW0_COPIES);
-  A.row0 = ws.row0;
+  const int grid = sorted_grid(2, LARND_ROW0_COPIES);
   if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)grid * p.n_ticks * sizeof(float), st));
   const size_t smem = sizeof(TileSmem);
   static bool attr_done = false;

@@ -65,7 +65,7 @@ extern "C" size_t larnd_workspace_bytes(int64_t n, int32_t n_events, int32_t ntp
   b += align_up((size_t)LARND_NFIELDS * (size_t)(n > 0 ? n : 1) * sizeof(float), 256);
   b += align_up((size_t)nw * 4, 256) * 2;
   b += align_up((size_t)nsb * 4, 256);
-  b += align_up((size_t)nchunks * 16 * sizeof(float), 256);
+  b += align_up((size_t)(nchunks + LARND_BWD_SORTED_SLOTS) * 16 * sizeof(float), 256);
   b += larnd_sorted_workspace_bytes(n);
   return b;
 }
@@ -89,7 +89,7 @@ bool larnd_carve_workspace(void* base, size_t bytes, int64_t n, int32_t n_events
   ws->bsums = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)ws->n_scan_blocks * 4, 256);
   ws->partials = reinterpret_cast<float*>(p);
-  p += align_up((size_t)ws->n_chunks_max * 16 * sizeof(float), 256);
+  p += align_up((size_t)(ws->n_chunks_max + LARND_BWD_SORTED_SLOTS) * 16 * sizeof(float), 256);
   larnd_carve_sorted(p, n, ws);
   return true;
 }

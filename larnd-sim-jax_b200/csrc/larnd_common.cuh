@@ -50,9 +50,10 @@ struct Workspace {
   float* row0;
 };
 
-#define LARND_NCLS_MAX (LARND_MAX_TEMPLATES * 11 * 11)  // response classes: template index x in-pixel bin
+#define LARND_NCLS_MAX (LARND_MAX_TEMPLATES * 11 * 11 * 5)  // response classes: template index x in-pixel bin x tick span
 #define LARND_ROW0_COPIES 512                            // private garbage-row copies (>= CTAs of k_acc_tiles)
 #define LARND_ROW0_TICKS_MAX 8192
+#define LARND_BWD_SORTED_SLOTS 1280                      // per-warp gradient partials of the class-sorted backward kernel
 #define LARND_ACC_SLOW_ONLY 0x100                        // internal flag of larnd_launch_accumulate
 #define LARND_SORTED_MIN_SEGMENTS 200000                 // below this the chunk kernel wins (few runs per class)
 size_t larnd_sorted_workspace_bytes(int64_t n);
@@ -133,6 +134,10 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
                             int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                    int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
+int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                                       int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride,
+                                       float* sorted_partials, int* n_slots_out, const int* gflag, const int32_t* counts,
+                                       cudaStream_t st);
 int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                 int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride, float* grad_params,
                                 const int32_t* counts, cudaStream_t st);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "liblarnd_b200.so")
-SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "fee.cu", "mc_current.cu"]
+SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu"]
 
 MAX_TPC = 8
 MAX_TEMPLATES = 128
@@ -77,7 +77,7 @@ def nvcc_command(out=LIB_PATH, extra=()):
 def build_library(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into liblarnd_b200.so (in-tree, next to this file)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(CSRC, "sorted_runs.cuh"), os.path.join(CSRC, "segment_physics.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = nvcc_command()

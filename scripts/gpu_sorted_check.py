@@ -40,3 +40,24 @@ for flags in (0, 1):
     print("flags=%d: max |sorted-chunk| / rowmax: valid rows %.3g, all rows cols>=1 %.3g, garbage col %.3g" % (
         flags, err[valid][:, 1:].max().item(), err[:, 1:].max().item(), err[:, 0].max().item()))
     print("   row0 rel diff %.3g" % ((a[0] - b[0]).abs().max() / (a[0].abs().max() + 1e-9)).item())
+
+# ---- backward: class-sorted vs chunk kernel on the same upstream gradient ---------------------------------------
+torch.manual_seed(0)
+grads = {}
+for impl in ("chunk", "sorted"):
+    os.environ["LARND_ACC_IMPL"] = impl
+    st = sim.lut_forward(params, bank, tracks, synthetic.FIELDS, npix_capacity=npix, n_events=nev)
+    if impl == "chunk":
+        g = torch.randn((npix, st.pod.n_ticks - 1), device=dev) * (st.unique_pixels >= 0).unsqueeze(1)
+    for rep in range(2):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gr = sim.lut_backward(st, g)
+        e1.record(); torch.cuda.synchronize()
+    print("%s backward: %.3f ms" % (impl, e0.elapsed_time(e1)), flush=True)
+    grads[impl] = gr.double().cpu()
+a, b = grads["chunk"], grads["sorted"]
+print("grad chunk ", a.tolist())
+print("grad sorted", b.tolist())
+print("max rel diff", ((a - b).abs() / (a.abs() + 1e-30)).max().item())

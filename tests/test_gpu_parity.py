@@ -243,7 +243,7 @@ def test_fee_with_injected_noise_matches_oracle(torch_dev):
     assert np.array_equal(fs.adc.cpu().numpy(), lo.digitize(op, adc_o))
 
 
-def test_lut_gradients_match_float64_finite_differences(torch_dev):
+def test_lut_gradients_match_float64_finite_differences(torch_dev, acc_impl):
     import torch
     from larndsim_b200 import _lib, sim
     kw = dict(number_pix_neighbors=2, signal_length=150)
@@ -272,7 +272,7 @@ def test_lut_gradients_match_float64_finite_differences(torch_dev):
     assert grad[_lib.PARAM_ORDER.index("vdrift")] == 0.0   # params.vdrift is never read by the reference
 
 
-def test_autograd_end_to_end(torch_dev):
+def test_autograd_end_to_end(torch_dev, acc_impl):
     """build_params_class leaves get gradients through simulate_wfs + simulate_stochastic, like jax.grad in the reference."""
     import torch
     from larndsim_b200 import sim
