@@ -205,10 +205,15 @@ def run_ours(args):
                                                           electron_sampling_resolution=PRECISION, RESET_NOISE_CHARGE=0,
                                                           UNCORRELATED_NOISE_CHARGE=0, time_window=SIGLEN)
     t_gen = time.time()
-    tracks_np, n_events = synthetic.synthetic_tracks(args.segments, seed=1234 + rank, precision=PRECISION)
-    nseg = tracks_np.shape[0]
-    tracks_host = torch.from_numpy(tracks_np).pin_memory()
-    tracks = tracks_host.to(dev, non_blocking=True)
+    # raw tracks (one row per track, the prepared_data shape) -> chopped on the DEVICE (csrc/chop.cu, bit-identical to the
+    # reference's host-side chop_tracks); the chopped batch is the input of `value` and of `e2e`, the raw rows of `e2e_raw`
+    from larndsim_b200 import dataio
+    raw_np, n_events = synthetic.synthetic_raw_tracks(args.segments, seed=1234 + rank, precision=PRECISION)
+    raw_host = torch.from_numpy(raw_np).pin_memory()
+    tracks = dataio.chop_tracks(raw_host.to(dev), fields, PRECISION)
+    nseg = tracks.shape[0]
+    tracks_host = tracks.cpu().pin_memory()
+    tracks_np = tracks_host.numpy()
     resp = synthetic.synthetic_response()
     from larndsim_b200.consts import build_response_template
     bank = build_response_template(resp, params, device=dev)
@@ -289,6 +294,28 @@ def run_ours(args):
         state["i"] += 1
         return fs
 
+    # End-to-end from the RAW rows: H2D of the un-chopped tracks (a few hundred KB), chop on the device,
+    # forward, D2H of the hit list — the reference chops on the host and ships 104 B per chopped segment.
+    raw_dev = torch.empty(raw_host.shape, dtype=torch.float32, device=dev)
+    chop_buf = torch.empty_like(tracks)
+
+    def e2e_raw_step():
+        main = torch.cuda.current_stream()
+        raw_dev.copy_(raw_host, non_blocking=True)
+        dataio.chop_tracks(raw_dev, fields, PRECISION, out=chop_buf)
+        st, fs = fwd(src=chop_buf)
+        done = torch.cuda.Event()
+        done.record(main)
+        hf, hi = fs.hits
+        cap = hit_host.shape[1]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            nv_host.copy_(fs.n_valid, non_blocking=True)
+            hit_host[:6].copy_(hf[:, :cap], non_blocking=True)
+            hit_host[6:8].copy_(hi[:, :cap].view(torch.float32), non_blocking=True)
+            hf.record_stream(copy_stream); hi.record_stream(copy_stream); fs.n_valid.record_stream(copy_stream)
+        return fs
+
     def timed(fn, steps, warmup, sampler=None, join=None):
         if sampler:
             sampler.start()          # nvidia-smi needs ~0.3 s to start streaming: launch it before the warm-up
@@ -320,6 +347,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_fwd, clocks = timed(fwd, args.steps, args.warmup, sampler)
     ms_e2e, _ = timed(e2e_step, args.steps, max(2, args.warmup // 3), join=copy_stream)
+    ms_e2e_raw, _ = timed(e2e_raw_step, args.steps, max(2, args.warmup // 3), join=copy_stream)
     ms_fg, _ = timed(fwd_grad, args.steps, max(1, args.warmup // 3))
     ms_skip = None
     if args.skip_garbage:
@@ -361,11 +389,14 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": total_seg / (ms_e2e * 1e-3), "unit": "segments/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(tracks_host.numel() * 4), "d2h_bytes_per_step": int(hit_host.numel() * 4 + 4)},
+            "e2e_raw": {"value": total_seg / (ms_e2e_raw * 1e-3), "unit": "segments/s", "ms_per_step": ms_e2e_raw,
+                        "h2d_bytes_per_step": int(raw_host.numel() * 4), "d2h_bytes_per_step": int(hit_host.numel() * 4 + 4),
+                        "note": "un-chopped tracks uploaded, chop_tracks on the device (csrc/chop.cu)"},
             "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": total_seg / (ms_fg * 1e-3), "unit": "segments/s",
                          "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none"},
-            "gpu_launches": int(args.steps * 9),
+            "gpu_launches": int(args.steps * 14),  # prepare 1 + unique/scan 4 + sorted accumulate 6 + FEE/compaction 3
             "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
-            "roofline": {"kernel": "k_lut_accumulate", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate incl. run sort)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_segment": b_seg,
                          "note": "accumulate is bound by on-chip gather/FMA issue, not HBM (SURVEY §8d); contributions/s below",

@@ -185,6 +185,22 @@ int larnd_mc_backward(const float* tracks_d, int64_t n_segments, const larnd_col
                       void* workspace_d, size_t workspace_bytes, const int32_t* counts_d, const float* g_wfs_d,
                       int64_t g_row_stride, float* grad_params_d, void* stream);
 
+/* Device-side chop_tracks (replaces optimize/dataio.py:63-106, a Python loop per raw row on the host).
+ * raw_d: (m, ncols) float32 raw segments in the file's column order; every raw row becomes
+ * max(ceil(length / precision), 1) rows of the same width with start/end/mid points, dx and dE subdivided exactly as
+ * numpy evaluates the reference expressions (float64 for steps*precision*direction, float32 elsewhere).
+ *   larnd_chop_count : offsets_d[0..m) = exclusive prefix of the piece counts, offsets_d[m] = total (int64, device)
+ *   larnd_chop_tracks: writes the total x ncols output; does nothing if the total exceeds `capacity` rows
+ *                      (the caller reads offsets_d[m] to size / validate the output). */
+typedef struct larnd_chop_columns {
+  int32_t ncols;
+  int32_t x, y, z, x_start, y_start, z_start, x_end, y_end, z_end, dx, dE;
+} larnd_chop_columns_t;
+int larnd_chop_count(const float* raw_d, int64_t m, const larnd_chop_columns_t* cols, double precision,
+                     int64_t* offsets_d, void* stream);
+int larnd_chop_tracks(const float* raw_d, int64_t m, const larnd_chop_columns_t* cols, double precision,
+                      const int64_t* offsets_d, float* out_d, int64_t capacity, void* stream);
+
 /* Optional device-side timing of the dominant kernels (used by bench.py for the roofline numbers): when
  * enabled, CUDA events are recorded on the launching stream immediately around
  *   slot 0: k_prepare   slot 1: k_lut_accumulate   slot 2: k_lut_backward   slot 3: k_fee_forward

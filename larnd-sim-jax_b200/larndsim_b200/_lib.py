@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "liblarnd_b200.so")
-SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu"]
+SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu", "chop.cu"]
 
 MAX_TPC = 8
 MAX_TEMPLATES = 128
@@ -30,6 +30,11 @@ REC_INT_FIELDS = ("T0", "IDX", "BX", "BY", "EP", "FLAGS", "MAINPIX")
 
 class Columns(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ncols", "eventID", "x", "y", "z", "z_start", "z_end", "dx", "dEdx", "dE", "t0")]
+
+
+class ChopColumns(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("ncols", "x", "y", "z", "x_start", "y_start", "z_start", "x_end", "y_end", "z_end",
+                                         "dx", "dE")]
 
 
 class ParamsPOD(C.Structure):
@@ -113,6 +118,11 @@ def _declare(lib):
     lib.larnd_fee_scratch_bytes.argtypes = [i32]
     lib.larnd_fee_scratch_bytes.restype = sz
     lib.larnd_fee_backward.argtypes = [vp, vp, vp, i32, PP, vp, i64, vp]
+    PCC = C.POINTER(ChopColumns)
+    lib.larnd_chop_count.argtypes = [vp, i64, PCC, C.c_double, vp, vp]
+    lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]
+    lib.larnd_chop_count.restype = C.c_int
+    lib.larnd_chop_tracks.restype = C.c_int
     if hasattr(lib, "larnd_mc_forward"):
         lib.larnd_mc_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, vp, vp]
         lib.larnd_mc_backward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, i64, vp, vp]

@@ -73,6 +73,54 @@ def synthetic_tracks(n_segments, seed=1234, precision=0.01, first_event=0):
     return np.ascontiguousarray(tracks, dtype=np.float32), n_events
 
 
+def synthetic_raw_tracks(n_segments, seed=1234, precision=0.01, first_event=0):
+    """(raw (M,26) float32, n_events): the same events as synthetic_tracks but ONE ROW PER TRACK (un-chopped, the shape of
+    the prepared_data files); chopping them at ``precision`` (dataio.chop_tracks on the device, or the reference's
+    chop_tracks) yields at least ``n_segments`` rows."""
+    rng = np.random.default_rng(seed)
+    c = {n: i for i, n in enumerate(FIELDS)}
+    rows = []
+    total = 0
+    ev = first_event
+    while total < n_segments:
+        ntracks = int(rng.integers(1, 5))
+        for trk in range(ntracks):
+            sign = 1.0 if rng.random() < 0.5 else -1.0
+            start = np.array([rng.uniform(-30, 30), rng.uniform(-61, 61), sign * rng.uniform(0.5, 30.0)])
+            while True:
+                d = rng.normal(size=3)
+                d /= np.linalg.norm(d)
+                if abs(d[2]) < 0.966:
+                    break
+            length = rng.uniform(10, 60)
+            lims = []
+            for k, (lo, hi) in enumerate(((-30.9, 30.9), (-61.9, 61.9), (0.2, 30.5) if sign > 0 else (-30.5, -0.2))):
+                if d[k] > 0:
+                    lims.append((hi - start[k]) / d[k])
+                elif d[k] < 0:
+                    lims.append((lo - start[k]) / d[k])
+            length = max(min([length] + lims), precision)
+            dedx = float(np.exp(rng.uniform(math.log(1.5), math.log(25.0))))
+            t0 = rng.uniform(1e-4, 3e-3)
+            row = np.zeros(len(FIELDS), dtype=np.float32)
+            for k, ax in enumerate("xyz"):
+                row[c[ax + "_start"]] = start[k]
+                row[c[ax + "_end"]] = start[k] + length * d[k]
+                row[c[ax]] = 0.5 * (row[c[ax + "_start"]] + row[c[ax + "_end"]])
+            row[c["dx"]] = length
+            row[c["dEdx"]] = dedx
+            row[c["dE"]] = dedx * length
+            row[c["eventID"]] = ev - first_event
+            row[c["trackID"]] = trk
+            row[c["pdgId"]] = 13
+            row[c["t0"]] = row[c["t0_start"]] = row[c["t0_end"]] = t0
+            rows.append(row)
+            total += max(int(math.ceil(length / precision)), 1)
+        ev += 1
+    raw = np.stack(rows, axis=0)
+    return np.ascontiguousarray(raw, dtype=np.float32), ev - first_event
+
+
 def synthetic_response(nx=45, ny=45, nt=1950, seed=7, t_sampling=0.1):
     """Synthetic stand-in for the missing response_44.npy: collecting bins (i,j < 5) carry a unipolar pulse
     (tau ~ 12 ticks, peak ~70 ticks before the end of the axis, one electron = unit integral), the others a

@@ -395,3 +395,32 @@ def test_fit_and_scan_drivers(torch_dev):
     a1, a2, out = scan_2d.run_scan("Ab", "lifetime", grid=3, n_segments=8000, device=torch_dev)
     assert np.isfinite(out).all()
     assert np.unravel_index(np.argmin(out[..., 0]), (3, 3))[0] in (0, 1)        # nominal Ab = 0.8 lies between grid points 0 and 1
+
+
+def test_device_chop_tracks_is_bit_identical_to_numpy(torch_dev):
+    """k_chop_* (csrc/chop.cu) against the oracle's restatement of chop_tracks (optimize/dataio.py:63-106) on every raw
+    fixture row, at the three sampling resolutions the reference scripts use; plus degenerate rows (zero length)."""
+    import torch
+    from larndsim_b200 import dataio
+    seg = lo.swap_xz_structured(np.load(cm.GOLD + "/segments_input_0.npz")["segments"])
+    raw = lo.structured_to_f32(seg)
+    raw = np.concatenate([raw, raw[:3]])
+    c = cm.FIELDS.index
+    for ax in "xyz":                       # a zero-length row: one piece, direction 0/1e-10
+        raw[-1, c(ax + "_end")] = raw[-1, c(ax + "_start")]
+    raw[-2, c("x_end")] = raw[-2, c("x_start")] + np.float32(0.02)   # exactly 2 pieces at 0.01 on one axis
+    raw[-2, c("y_end")] = raw[-2, c("y_start")]
+    raw[-2, c("z_end")] = raw[-2, c("z_start")]
+    t = torch.as_tensor(raw, device=torch_dev)
+    for prec in (0.005, 0.01, 0.05):
+        ref = lo.chop_tracks(raw, cm.FIELDS, prec)
+        got = dataio.chop_tracks(t, cm.FIELDS, prec).cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "chopped rows differ at precision %g" % prec
+        off = dataio.chop_offsets(t, cm.FIELDS, prec).cpu().numpy()
+        assert off[-1] == ref.shape[0] and off[0] == 0
+    # capacity too small: nothing is written, the total is still reported
+    out = torch.full((10, raw.shape[1]), -7.0, device=torch_dev)
+    dataio.chop_tracks(t, cm.FIELDS, 0.01, out=out)
+    assert (out == -7.0).all()
+    assert dataio.chop_tracks(t[:0], cm.FIELDS, 0.01).shape[0] == 0
