@@ -102,6 +102,12 @@ typedef struct larnd_lut larnd_lut_t; /* opaque: compacted response rows + cumul
 const char* larnd_last_error(void);
 int larnd_abi_version(void);
 
+/* Template bank of load_lut (consts_jax.py:427-447): bank_d (n_templates, nx, ny, nt) float32 with
+ * bank[t] = response (*) gauss[t] ('same' convolution along time, zero padded) for t >= 1 and bank[0] = response.
+ * gauss_d: (n_templates, taps) normalised Gaussians, taps odd (2*long_diff_extent + 1). */
+int larnd_build_bank(const float* response_d, int nx, int ny, int nt, const float* gauss_d, int n_templates, int taps,
+                     float* bank_d, void* stream);
+
 /* Builds the device tables for one (response_template, signal_length) pair:
  *   neighbour rows  R0[ci][cj][Nt-L..Nt)          (template 0, all Nx*Ny bins)
  *   main rows       Rm[tpl][ci<5][cj<5][Nt-L..Nt) (all templates, the 5x5 collecting bins)
@@ -200,6 +206,17 @@ int larnd_chop_count(const float* raw_d, int64_t m, const larnd_chop_columns_t* 
                      int64_t* offsets_d, void* stream);
 int larnd_chop_tracks(const float* raw_d, int64_t m, const larnd_chop_columns_t* cols, double precision,
                       const int64_t* offsets_d, float* out_d, int64_t capacity, void* stream);
+
+/* jax.random-compatible random numbers (Threefry-2x32; replaces jax.random.key/split/normal at fee_jax.py:186,237-255,271,
+ * detsim_jax.py:393, sim_jax.py:359-360,757).  key = the two uint32 words of jax.random.key(seed) = {seed >> 32, seed};
+ * partitionable = 1 follows jax_threefry_partitionable (default since JAX 0.5.0), 0 the original counter layout.
+ *   larnd_rng_split     : random.split(key, num) -> keys_out[num][2] (host memory, computed on the host)
+ *   larnd_rng_normal    : random.normal(key, shape) for prod(shape) = n float32 values, row-major, into device memory
+ *   larnd_rng_fee_noise : all standard normals get_adc_values draws, in larnd_fee_forward's noise layout
+ *                         [base(npix) | extra(n_adc,npix) | pass(n_adc,npix) | fail(n_adc,npix)] */
+int larnd_rng_split(const uint32_t key[2], int num, int partitionable, uint32_t* keys_out);
+int larnd_rng_normal(const uint32_t key[2], int64_t n, int partitionable, float* out_d, void* stream);
+int larnd_rng_fee_noise(const uint32_t key[2], int32_t npix, int32_t n_adc, int partitionable, float* noise_d, void* stream);
 
 /* Optional device-side timing of the dominant kernels (used by bench.py for the roofline numbers): when
  * enabled, CUDA events are recorded on the launching stream immediately around

@@ -131,3 +131,55 @@ extern "C" void larnd_lut_destroy(larnd_lut_t* lut) {
   cudaFree(lut->sc);
   delete lut;
 }
+
+// ---- template bank builder (reference: load_lut, consts_jax.py:427-447) ---------------------------------------------
+// bank[t][row][k] = sum_m gauss[t][m] * response[row][k + half - m]   ('same' convolution, zero padded), t >= 1;
+// bank[0] = response.  One CTA per (row, block of templates): the response row sits in shared memory, every thread
+// produces one output sample per template; 100 x 2025 x 1950 x 41 multiply-adds and one 1.58 GB write in total.
+namespace {
+constexpr int BANK_TPL_PER_CTA = 10;
+__global__ void __launch_bounds__(256)
+k_build_bank(const float* __restrict__ response, int nrows, int nt, const float* __restrict__ gauss, int ntpl, int taps,
+             float* __restrict__ bank) {
+  extern __shared__ float s_row[];  // [half zeros | response row | half zeros], then the Gaussians of this CTA's templates
+  const int half = taps / 2;
+  const int row = blockIdx.x;
+  const int t_lo = blockIdx.y * BANK_TPL_PER_CTA, t_hi = min(ntpl, t_lo + BANK_TPL_PER_CTA);
+  float* s_g = s_row + nt + 2 * half;
+  for (int k = threadIdx.x; k < nt + 2 * half; k += blockDim.x) {
+    const int kk = k - half;
+    s_row[k] = (kk >= 0 && kk < nt) ? response[(int64_t)row * nt + kk] : 0.0f;
+  }
+  for (int k = threadIdx.x; k < (t_hi - t_lo) * taps; k += blockDim.x) s_g[k] = gauss[(int64_t)t_lo * taps + k];
+  __syncthreads();
+  for (int t = t_lo; t < t_hi; ++t) {
+    float* dst = bank + ((int64_t)t * nrows + row) * nt;
+    const float* g = s_g + (t - t_lo) * taps;
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+      float acc;
+      if (t == 0) {
+        acc = s_row[k + half];
+      } else {
+        acc = 0.0f;
+        for (int m = 0; m < taps; ++m) acc = fmaf(g[m], s_row[k + 2 * half - m], acc);  // response[k + half - m]
+      }
+      dst[k] = acc;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int larnd_build_bank(const float* response_d, int nx, int ny, int nt, const float* gauss_d, int n_templates, int taps,
+                                float* bank_d, void* stream) {
+  if (!response_d || !gauss_d || !bank_d || nx < 1 || ny < 1 || nt < 1 || n_templates < 1 || taps < 1 || (taps & 1) == 0) {
+    larnd_set_error("larnd_build_bank: invalid argument (taps must be odd)");
+    return LARND_E_ARG;
+  }
+  const size_t smem = (size_t)(nt + 2 * (taps / 2) + BANK_TPL_PER_CTA * taps) * sizeof(float);
+  if (smem > 200 * 1024) { larnd_set_error("larnd_build_bank: response row too long for shared memory"); return LARND_E_ARG; }
+  LARND_CUDA(cudaFuncSetAttribute(k_build_bank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(nx * ny), (unsigned)((n_templates + BANK_TPL_PER_CTA - 1) / BANK_TPL_PER_CTA));
+  k_build_bank<<<grid, 256, smem, (cudaStream_t)stream>>>(response_d, nx * ny, nt, gauss_d, n_templates, taps, bank_d);
+  LARND_LAUNCH_CHECK("k_build_bank");
+  return LARND_OK;
+}

@@ -192,19 +192,23 @@ def gaussian_bank_kernels(params):
 def build_response_template(response, params, device="cuda"):
     """Template bank (n_templates, Nx, Ny, Nt): row t = response convolved ('same') with the normalised
     Gaussian of width long_diff_template[t] ticks; row 0 = the raw response (reference: consts_jax.py:427-447).
-    One-off set-up work, done with a batched torch conv1d on the device."""
-    resp = torch.as_tensor(np.asarray(response, dtype=np.float32), device=device)
+    Built on the device by k_build_bank (csrc/lut_tables.cu)."""
+    import ctypes as C
+    from . import _lib
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.LarndError("build_response_template needs a CUDA device (larndsim_b200 has no CPU path)")
+    resp = torch.as_tensor(np.ascontiguousarray(response, dtype=np.float32), device=dev)
+    if resp.dim() != 3:
+        raise ValueError("response must have shape (Nx, Ny, Nt)")
     nx, ny, nt = resp.shape
-    g = torch.as_tensor(gaussian_bank_kernels(params), device=device)
+    g = torch.as_tensor(gaussian_bank_kernels(params), device=dev).contiguous()
     ntpl, taps = g.shape
-    bank = torch.empty((ntpl, nx, ny, nt), dtype=torch.float32, device=device)
-    rows = resp.reshape(nx * ny, 1, nt)
-    step = 16
-    for t0 in range(0, ntpl, step):
-        k = g[t0:t0 + step].flip(-1).unsqueeze(1)  # conv1d is a correlation
-        out = torch.nn.functional.conv1d(rows, k, padding=taps // 2)  # (rows, k, nt)
-        bank[t0:t0 + step] = out.permute(1, 0, 2).reshape(-1, nx, ny, nt)
-    bank[0] = resp
+    bank = torch.empty((ntpl, nx, ny, nt), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.get_lib().larnd_build_bank(C.c_void_p(resp.data_ptr()), nx, ny, nt, C.c_void_p(g.data_ptr()), ntpl, taps,
+                                                   C.c_void_p(bank.data_ptr()), st))
     return bank
 
 

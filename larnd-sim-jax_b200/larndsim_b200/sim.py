@@ -355,13 +355,14 @@ class _FeeAdc(torch.autograd.Function):
 
 
 def make_noise(params, npix, rngseed, device):
-    """Standard normals for the FEE noise terms, laid out [base | extra(10) | pass(10) | fail(10)].
-    NOT bit-compatible with jax.random (threefry parity is out of scope)."""
+    """Standard normals for the FEE noise terms, laid out [base | extra(10) | pass(10) | fail(10)]: the draws
+    get_adc_values makes from jax.random.key(rngseed) (fee_jax.py:186,237-255,271), generated on the device with the same
+    Threefry-2x32 stream (csrc/rng.cu).  ``rngseed`` may also be a key (two uint32 words, e.g. from jrandom.split)."""
     if params.RESET_NOISE_CHARGE == 0 and params.UNCORRELATED_NOISE_CHARGE == 0:
         return None
-    gen = torch.Generator(device=device)
-    gen.manual_seed(int(rngseed) if rngseed is not None else 0)
-    return torch.randn(npix * (1 + 3 * int(params.MAX_ADC_VALUES)), generator=gen, device=device, dtype=torch.float32)
+    from . import jrandom
+    k = rngseed if isinstance(rngseed, (tuple, list)) else jrandom.key(int(rngseed) if rngseed is not None else 0)
+    return jrandom.fee_noise(k, npix, int(params.MAX_ADC_VALUES), device)
 
 
 def parse_output(params, adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, unique_pixels):
@@ -397,11 +398,11 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
 
 # ------------------------------------------------------------------------------------------ MC-current mode
 def mc_normals(n, rngseed, device):
-    """The (N,3) standard normals of generate_electrons (reference: detsim_jax.py:393).  NOT bit-compatible with
-    jax.random; pass ``rnd=`` to simulate_parametrized to inject specific draws."""
-    gen = torch.Generator(device=device)
-    gen.manual_seed(int(rngseed))
-    return torch.randn((n, 3), generator=gen, device=device, dtype=torch.float32)
+    """The (N,3) standard normals of generate_electrons: random.normal(rngkey1, (N,3)) with rngkey1, rngkey2 =
+    random.split(random.key(rngseed)) (reference: sim_jax.py:359-360, detsim_jax.py:393), same Threefry stream."""
+    from . import jrandom
+    k1, _ = jrandom.split(jrandom.key(int(rngseed)), 2)
+    return jrandom.normal(k1, (n, 3), device)
 
 
 def mc_forward(params, tracks, fields, rnd, npix_capacity=None, n_events=None):
@@ -495,4 +496,6 @@ def simulate_parametrized(params, tracks, fields, rngseed=0, rnd=None, npix_capa
     else:
         st = mc_forward(params, tracks, fields, rnd, npix_capacity, n_events)
         wfs, upix = st.wfs_full[:, 1:], st.unique_pixels
-    return simulate_stochastic(params, wfs, upix, (rngseed or 0) + 1)
+    from . import jrandom
+    _, rngkey2 = jrandom.split(jrandom.key(int(rngseed or 0)), 2)   # the FEE uses the second half of the split (sim_jax.py:360,368)
+    return simulate_stochastic(params, wfs, upix, rngkey2)

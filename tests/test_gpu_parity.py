@@ -424,3 +424,55 @@ def test_device_chop_tracks_is_bit_identical_to_numpy(torch_dev):
     dataio.chop_tracks(t, cm.FIELDS, 0.01, out=out)
     assert (out == -7.0).all()
     assert dataio.chop_tracks(t[:0], cm.FIELDS, 0.01).shape[0] == 0
+
+
+def test_template_bank_builder_matches_oracle(torch_dev):
+    """k_build_bank (load_lut's Gaussian template bank, consts_jax.py:427-447) against the oracle's scipy construction."""
+    from larndsim_b200.consts import build_response_template
+    op, pp = cm.oracle_params(), cm.product_params()
+    resp = oc.synthetic_response(7, 6, 1950)
+    ref = oc.build_response_template(resp, op)
+    got = build_response_template(resp, pp, device=torch_dev).cpu().numpy()
+    assert got.shape == ref.shape == (100, 7, 6, 1950)
+    assert np.array_equal(got[0], resp)                      # row 0 is the raw response, bit for bit
+    scale = np.abs(ref).max(axis=-1, keepdims=True) + 1e-30
+    assert (np.abs(got - ref) / scale).max() < 2e-6
+
+
+def test_threefry_normals_match_the_jax_restatement(torch_dev):
+    """csrc/rng.cu against oracle/jax_random.py (itself pinned to values published by JAX): normals for both counter
+    layouts, odd sizes and an (N,3) shape, and the complete noise buffer of get_adc_values."""
+    from larndsim_b200 import jrandom
+    from oracle import jax_random as jr
+    for part in (True, False):
+        for seed, shape in ((0, (1,)), (42, (7,)), (5, (1001,)), (9, (333, 3))):
+            ref = jr.normal(jr.key(seed), shape, part)
+            got = jrandom.normal(jrandom.key(seed), shape, torch_dev, part).cpu().numpy()
+            assert got.shape == ref.shape
+            assert np.abs(got - ref).max() <= 2e-6 * (1 + np.abs(ref).max()), (part, seed)
+        ref = jr.fee_noise(3, 37, 10, part)
+        got = jrandom.fee_noise(jrandom.key(3), 37, 10, torch_dev, part).cpu().numpy()
+        assert np.abs(got - ref).max() <= 4e-6
+    assert abs(float(jrandom.normal(jrandom.key(42), (), torch_dev, True)) - (-0.028304616)) < 1e-6   # value printed in the JAX docs
+
+
+def test_noisy_fee_uses_the_jax_noise_stream(torch_dev):
+    """simulate_stochastic with noise switched on draws jax.random.key(rngseed)'s normals: same hits as the oracle fed with
+    the restated jax stream."""
+    import torch
+    from larndsim_b200 import sim
+    from oracle import jax_random as jr
+    kw = dict(number_pix_neighbors=1, signal_length=100, RESET_NOISE_CHARGE=900.0, UNCORRELATED_NOISE_CHARGE=500.0)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    tr = cm.small_batch(500, ibatch=2, pad=4, precision=0.01)
+    wfs_o, uniq_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={})
+    z = jr.fee_noise(11, len(uniq_o), 10, True).reshape(31, len(uniq_o))
+    noise = dict(base=z[0], extra=z[1:11], **{"pass": z[11:21], "fail": z[21:31]})
+    out_o = lo.simulate_stochastic(op, wfs_o, uniq_o, noise=noise)
+    w, u = torch.as_tensor(wfs_o, device=torch_dev), torch.as_tensor(uniq_o, device=torch_dev)
+    out_p = sim.simulate_stochastic(pp, w, u, 11)
+    got = [t.detach().cpu().numpy() for t in out_p]
+    assert len(got[0]) == len(out_o[0]) and len(got[0]) > 0
+    assert np.array_equal(got[4], out_o[4]) and np.array_equal(got[7], out_o[7])
+    assert np.abs(got[0] - out_o[0]).max() < 5e-3

@@ -247,3 +247,15 @@ def test_sharded_loss_matches_single_process(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out
+
+
+def test_host_side_key_split_matches_the_jax_restatement(lib):
+    """larnd_rng_split runs on the host (no GPU needed): same keys as oracle/jax_random.split in both counter layouts."""
+    from larndsim_b200 import jrandom
+    from oracle import jax_random as jr
+    for seed in (0, 7, 2 ** 40 + 3):
+        for part in (True, False):
+            for num in (1, 2, 5):
+                got = jrandom.split(jrandom.key(seed), num, part)
+                ref = [tuple(int(v) for v in k) for k in jr.split(jr.key(seed), num, part)]
+                assert got == ref, (seed, part, num)

@@ -106,3 +106,23 @@ def test_oracle_end_to_end_is_self_consistent():
     assert abs(collected - q_tot) < 0.05 * q_tot
     hits = lo.simulate_stochastic(p, wfs, uniq)
     assert np.isin(hits[7], uniq[uniq >= 0]).all() and len(hits[0]) > 0
+
+
+def test_jax_random_restatement_reproduces_published_values():
+    """oracle/jax_random.py against (i) the Random123 known-answer vectors JAX's own suite checks
+    (jax tests/random_test.py::testThreefry2x32) and (ii) outputs printed in the JAX documentation / README for both
+    counter layouts: random.normal(random.key(42)) = -0.028304616 (threefry_partitionable, JAX >= 0.5) and -0.18471177
+    (original), random.normal(PRNGKey(0), (3,)) = [1.8160863, -0.48262316, 0.33988908] and
+    random.split(PRNGKey(0)) = [[4146024105, 967050713], [2718843009, 1272950319]] (original)."""
+    from oracle import jax_random as jr
+    kat = [((0, 0), (0, 0), (0x6b200159, 0x99ba4efe)),
+           ((0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x1cb996fc, 0xbb002be7)),
+           ((0x13198a2e, 0x03707344), (0x243f6a88, 0x85a308d3), (0xc4923a9c, 0x483df7a0))]
+    for k, x, exp in kat:
+        o0, o1 = jr.threefry2x32(k[0], k[1], np.array([x[0]], np.uint32), np.array([x[1]], np.uint32))
+        assert (int(o0[0]), int(o1[0])) == exp
+    assert abs(float(jr.normal(jr.key(42), (), True)) - (-0.028304616)) < 1e-7
+    assert abs(float(jr.normal(jr.key(42), (), False)) - (-0.18471177)) < 1e-7
+    assert abs(float(jr.normal(jr.key(0), (), False)) - (-0.20584226)) < 1e-7
+    assert np.allclose(jr.normal(jr.key(0), (3,), False), [1.8160863, -0.48262316, 0.33988908], rtol=0, atol=2e-7)
+    assert [tuple(int(v) for v in k) for k in jr.split(jr.key(0), 2, False)] == [(4146024105, 967050713), (2718843009, 1272950319)]
