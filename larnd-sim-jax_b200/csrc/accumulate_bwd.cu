@@ -621,12 +621,11 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   k_garbage_grad_flag<<<32, 256, 0, st>>>(g_wfs, g_stride, p.n_ticks, counts, gflag);
   LARND_LAUNCH_CHECK("k_garbage_grad_flag");
   A.garbage_grad_nonzero = gflag;
-  // The class-sorted backward kernel (accumulate_bwd_sorted.cu) is parity-tested but not yet faster than this kernel
-  // (one warp per tile is latency-bound at 8 warps/SM: 65 ms vs 65 ms per 10 M segments on B200), so it is opt-in:
-  // LARND_BWD_IMPL=sorted.  Tests force it through LARND_ACC_IMPL=sorted as well.
-  bool sorted = false;
+  // large batches: the class-sorted kernel (accumulate_bwd_sorted.cu) does the bulk.  LARND_BWD_IMPL / LARND_ACC_IMPL =
+  // chunk | sorted override the size rule (the tests force both paths on small batches).
+  bool sorted = larnd_sorted_supported(p, lut) && n >= LARND_SORTED_MIN_SEGMENTS;
   if (const char* e = getenv("LARND_BWD_IMPL")) sorted = larnd_sorted_supported(p, lut) && e[0] == 's';
-  else if (const char* e2 = getenv("LARND_ACC_IMPL")) sorted = larnd_sorted_supported(p, lut) && e2[0] == 's' && n < LARND_SORTED_MIN_SEGMENTS;
+  else if (const char* e2 = getenv("LARND_ACC_IMPL")) sorted = larnd_sorted_supported(p, lut) && e2[0] == 's';
   A.sorted_active = sorted ? 1 : 0;
   prof_begin(2, st);
   if (sorted) {
