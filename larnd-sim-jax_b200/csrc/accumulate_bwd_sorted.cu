@@ -11,6 +11,9 @@
 // d/dfrac, d/d(a,b,c), d/dWx, d/dWy, added to per-segment accumulators in shared memory (float atomics: different warps
 // work on different units of the same segments).  Threads <-> segments then apply the closed-form chain rule through
 // drift / quench / diffusion (K1b); the 15 parameter gradients are block-reduced into partials summed in double.
+// (A tensor-core form of the correlation — mma.sync m16n8k8 TF32 over the 32 runs of a tile — was measured on B200 and
+// rejected: 55 ms vs 34 ms per 10 M segments, because the kernel is bound by the latency of the scattered gradient-row
+// loads, not by issue slots, and TF32 loses ~1 % on d/d(long_diff), whose three template terms cancel to first order.)
 // Work whose only effect is on garbage rows is skipped: their upstream gradient is zero, checked on the device by
 // k_garbage_grad_flag.  If it is NOT zero, or for segments whose window ends beyond the readout, accumulate_bwd.cu's
 // kernel does the work instead (device-side switch, no host synchronisation).
@@ -94,10 +97,17 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
     const float* grow = A.g + (int64_t)rowp * A.g_stride;
     // upstream-gradient window (coalesced) and the running sums at the run's tick positions: all loads first
     float graw[NS];
+    const bool inside = tmin >= 2 && tmin - 2 + 32 * NS < nticks;  // warp-uniform, the common case: whole window inside the row
+    if (inside) {
+      const float* gp = grow + (tmin - 1 + lane);
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const int col = tmin - 1 + 32 * s + lane;
-      graw[s] = (col >= 1 && col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
+      for (int s = 0; s < NS; ++s) graw[s] = __ldg(gp + 32 * s);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int col = tmin - 1 + 32 * s + lane;
+        graw[s] = (col >= 1 && col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
+      }
     }
     int ctl = nt - L - (tmin + lane);
     ctl = max(0, min(ctl, nt - 1));
@@ -107,7 +117,8 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
     for (int k = 0; k < NR * NPOS; ++k) part[k] = 0.0f;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-      const float gv = (tmin - 1 + 32 * s + lane >= 2) ? graw[s] : 0.0f;  // window samples live on ticks >= 2, corrections on >= 1
+      // window samples live on ticks >= 2, corrections on >= 1 (only differs for runs at the low end of the readout)
+      const float gv = (inside || tmin - 1 + 32 * s + lane >= 2) ? graw[s] : 0.0f;
 #pragma unroll
       for (int j = 0; j < NPOS; ++j)
 #pragma unroll
