@@ -378,6 +378,15 @@ def run_ours(args):
         b_seg = 104 + 4.0 * (n_unique + 1) * nticks / nseg + lut_window / nseg
         c_seg = (25 + (2 * NEIGH + 1) ** 2) * (2 * L + 2)
         achieved = b_seg * nseg / (k_ms[1] * 1e-3) / 1e9
+        # DRAM bytes of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full`
+        # capture at the 10 M-segment workload (profiles/r1_traffic_10M.json), scaled to this run's segment count
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic_10M.json")) as fh:
+                tj = json.load(fh)
+            traffic = float(tj["k_acc_tiles<4>"][0]["dram_bytes"]) * nseg / 10010184.0
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": total_seg / (ms_fwd * 1e-3), "unit": "segments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_fwd, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -399,7 +408,7 @@ def run_ours(args):
             "gpu_launches": int(args.steps * 14),  # prepare 1 + unique/scan 4 + sorted accumulate 6 + FEE/compaction 3
             "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
             "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate incl. run sort)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_segment": b_seg,
                          "note": "accumulate is bound by on-chip gather/FMA issue, not HBM (SURVEY §8d); contributions/s below",
                          "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3)},

@@ -179,6 +179,17 @@ size_t larnd_fee_scratch_bytes(int32_t npix);
 int larnd_fee_backward(const float* g_adc_d, const float* ticks_d, const float* saved_d, int32_t npix,
                        const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, void* stream);
 
+/* Noise-averaged ("probabilistic") front end, forward: get_adc_values_average_noise_vmap (fee_jax.py:390-461).
+ * wfs_d: (npix, n_ticks) waveforms (row stride in floats).  Outputs (npix, MAX_ADC_VALUES, n_ticks-1) each:
+ *   log_prob_d : log-probability that hit number k of the pixel triggers at tick t (log_total_hit_dist_tick)
+ *   charge_d   : expected integrated charge of such a hit (esperance_value; digitize() maps it to ADC)
+ *   top_ticks_d: optional (npix, MAX_ADC_VALUES, n_paths) int32, the ticks kept by the beam search (may be NULL)
+ * n_paths = params.fee_paths_scaling (20); sigma = params->reset_noise_charge must be > 0. */
+size_t larnd_prob_fee_scratch_bytes(int32_t npix, int32_t n_ticks, int32_t n_paths, int32_t n_steps);
+int larnd_prob_fee_forward(const float* wfs_d, int64_t wfs_row_stride, int32_t npix, int32_t n_ticks,
+                           const larnd_params_t* params, int32_t n_paths, float stop_threshold, float* log_prob_d,
+                           float* charge_d, int32_t* top_ticks_d, void* scratch_d, size_t scratch_bytes, void* stream);
+
 /* MC-current mode with number_pix_neighbors = 0 and mc_diff = True.  rnd_d: (N,3) standard normals
  * (the reference draws random.normal(key,(N,3)), detsim_jax.py:393).  Same output convention as
  * larnd_lut_forward. */

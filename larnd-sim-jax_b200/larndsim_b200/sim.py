@@ -396,6 +396,18 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
     return out[:8]
 
 
+def simulate_probabilistic(params, wfs, unique_pixels):
+    """(adcs_distrib (Npix,10,Nticks-1), pixel_x, pixel_y, ticks_prob (log-probabilities), event) — reference:
+    sim_jax.py:772-812.  Forward only in this build."""
+    from .detsim import get_pixel_coordinates, id2pixel
+    from .fee import digitize, get_adc_values_average_noise_vmap
+    ticks_prob, charge_distrib = get_adc_values_average_noise_vmap(params, wfs)
+    adcs_distrib = digitize(params, charge_distrib)
+    px, py, plane, event = id2pixel(params, unique_pixels)
+    coords = get_pixel_coordinates(params, px, py, plane)
+    return adcs_distrib, coords[:, 0], coords[:, 1], ticks_prob, event
+
+
 # ------------------------------------------------------------------------------------------ MC-current mode
 def mc_normals(n, rngseed, device):
     """The (N,3) standard normals of generate_electrons: random.normal(rngkey1, (N,3)) with rngkey1, rngkey2 =
