@@ -476,3 +476,38 @@ def test_noisy_fee_uses_the_jax_noise_stream(torch_dev):
     assert len(got[0]) == len(out_o[0]) and len(got[0]) > 0
     assert np.array_equal(got[4], out_o[4]) and np.array_equal(got[7], out_o[7])
     assert np.abs(got[0] - out_o[0]).max() < 5e-3
+
+
+def test_probabilistic_front_end_forward_matches_oracle(torch_dev):
+    """k_prob_* (get_adc_values_average_noise_vmap, fee_jax.py:334-461) against oracle/prob_fee.py.  The log-probabilities
+    contain log(Phi(a) - Phi(b)) of nearly equal arguments, which is float32 noise wherever the probability itself is
+    ~1e-7 (in the reference too), so values are compared as probabilities and through get_average_hit_values."""
+    import torch
+    from larndsim_b200 import fee, sim
+    from oracle import prob_fee as pf
+    kw = dict(number_pix_neighbors=1, signal_length=100, RESET_NOISE_CHARGE=900.0)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    tr = cm.small_batch(600, ibatch=2, pad=2, precision=0.01)
+    wfs_o, uniq_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={})
+    amp = np.abs(wfs_o).sum(axis=1)
+    sel = np.concatenate([np.argsort(-amp)[:9], np.argsort(amp)[:3]])
+    w = np.ascontiguousarray(wfs_o[sel])
+    lp_o, q_o, top_o = pf.get_adc_values_average_noise(op, w, return_state=True)
+    lp, qd, top = fee.get_adc_values_average_noise_vmap(pp, torch.as_tensor(w, device=torch_dev), return_top_ticks=True)
+    lp, qd, top = lp.cpu().numpy(), qd.cpu().numpy(), top.cpu().numpy()
+    assert lp.shape == lp_o.shape == (len(sel), 10, 1999)
+    assert np.abs(qd - q_o).max() <= 1e-6 * np.abs(q_o).max() + 1e-2          # esperance_value: plain float32 arithmetic
+    assert np.abs(np.exp(lp) - np.exp(lp_o)).max() < 5e-4
+    et_o, eq_o, lam_o = pf.get_average_hit_values(np.exp(lp_o), q_o)
+    et, eq, lam = [t.cpu().numpy() for t in fee.get_average_hit_values(torch.as_tensor(np.exp(lp)), torch.as_tensor(qd))]
+    assert np.abs(lam - lam_o).max() < 2e-3
+    big = lam_o > 1e-2
+    assert big.sum() >= 9 and np.abs(et - et_o)[big].max() < 0.05 and (np.abs(eq - eq_o)[big] / np.abs(eq_o[big])).max() < 1e-3
+    strong = lam_o[:, 0] > 0.5
+    assert np.array_equal(np.sort(top[strong, 0], axis=1), np.sort(top_o[strong, 0], axis=1))   # beam of the first hit
+    # simulate_probabilistic wrapper: shapes and the digitised distribution
+    out = sim.simulate_probabilistic(pp, torch.as_tensor(w, device=torch_dev), torch.as_tensor(uniq_o[sel], device=torch_dev))
+    ref = pf.simulate_probabilistic(op, w, uniq_o[sel])
+    assert np.abs(out[0].cpu().numpy() - ref[0]).max() < 2e-3 and np.array_equal(out[4].cpu().numpy(), ref[4])
+    assert np.allclose(out[1].cpu().numpy(), ref[1]) and np.allclose(out[2].cpu().numpy(), ref[2])
