@@ -186,9 +186,20 @@ int larnd_fee_backward(const float* g_adc_d, const float* ticks_d, const float* 
  *   top_ticks_d: optional (npix, MAX_ADC_VALUES, n_paths) int32, the ticks kept by the beam search (may be NULL)
  * n_paths = params.fee_paths_scaling (20); sigma = params->reset_noise_charge must be > 0. */
 size_t larnd_prob_fee_scratch_bytes(int32_t npix, int32_t n_ticks, int32_t n_paths, int32_t n_steps);
+/* state_d: optional (npix, MAX_ADC_VALUES, 2*n_paths) float, the path charges and log-probabilities BEFORE every step;
+ * flags_d: optional (MAX_ADC_VALUES+1) int32, whether step k ran (the reference stops all pixels globally).  Both, and
+ * top_ticks_d, are what larnd_prob_fee_backward needs. */
 int larnd_prob_fee_forward(const float* wfs_d, int64_t wfs_row_stride, int32_t npix, int32_t n_ticks,
                            const larnd_params_t* params, int32_t n_paths, float stop_threshold, float* log_prob_d,
-                           float* charge_d, int32_t* top_ticks_d, void* scratch_d, size_t scratch_bytes, void* stream);
+                           float* charge_d, int32_t* top_ticks_d, float* state_d, int32_t* flags_d, void* scratch_d,
+                           size_t scratch_bytes, void* stream);
+/* VJP of the above w.r.t. the waveforms (beam ticks and stop flags are the forward's, like lax.stop_gradient in
+ * fee_jax.py:380): g_log_prob_d, g_charge_d (npix, MAX_ADC_VALUES, n_ticks-1) -> g_wfs_d (npix, n_ticks). */
+size_t larnd_prob_fee_bwd_scratch_bytes(int32_t npix, int32_t n_ticks, int32_t n_paths);
+int larnd_prob_fee_backward(const float* wfs_d, int64_t wfs_row_stride, int32_t npix, int32_t n_ticks,
+                            const larnd_params_t* params, int32_t n_paths, const float* g_log_prob_d, const float* g_charge_d,
+                            const float* log_prob_d, const float* state_d, const int32_t* top_ticks_d, const int32_t* flags_d,
+                            float* g_wfs_d, int64_t g_row_stride, void* scratch_d, size_t scratch_bytes, void* stream);
 
 /* MC-current mode with number_pix_neighbors = 0 and mc_diff = True.  rnd_d: (N,3) standard normals
  * (the reference draws random.normal(key,(N,3)), detsim_jax.py:393).  Same output convention as

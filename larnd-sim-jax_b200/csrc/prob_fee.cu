@@ -86,7 +86,8 @@ template <int NP>
 __global__ void __launch_bounds__(PF_THREADS)
 k_prob_step(const float* __restrict__ qsum, const float* __restrict__ cmf, const float* __restrict__ cmr, int npix, int nt,
             float* __restrict__ charges, float* __restrict__ lps, int* __restrict__ flags, int step, int nsteps, float zscale, float thr,
-            int interval, float log_stop, float* __restrict__ out_lp, float* __restrict__ out_q, int* __restrict__ out_top) {
+            int interval, float log_stop, float* __restrict__ out_lp, float* __restrict__ out_q, int* __restrict__ out_top,
+            float* __restrict__ out_state) {
   extern __shared__ float smf[];
   float* s_q = smf;              // [nt]
   float* s_f = s_q + nt;         // [nt]
@@ -113,6 +114,10 @@ k_prob_step(const float* __restrict__ qsum, const float* __restrict__ cmf, const
   if (threadIdx.x < NP) {
     s_c[threadIdx.x] = charges[(int64_t)pix * NP + threadIdx.x];
     s_lp[threadIdx.x] = lps[(int64_t)pix * NP + threadIdx.x];
+    if (out_state) {  // path state BEFORE this step (needed by the backward pass)
+      out_state[((int64_t)pix * nsteps + step) * 2 * NP + threadIdx.x] = s_c[threadIdx.x];
+      out_state[((int64_t)pix * nsteps + step) * 2 * NP + NP + threadIdx.x] = s_lp[threadIdx.x];
+    }
   }
   __syncthreads();
   for (int t = threadIdx.x; t < ntm; t += PF_THREADS) {
@@ -204,7 +209,8 @@ extern "C" size_t larnd_prob_fee_scratch_bytes(int32_t npix, int32_t n_ticks, in
 
 extern "C" int larnd_prob_fee_forward(const float* wfs_d, int64_t wfs_row_stride, int32_t npix, int32_t n_ticks,
                                       const larnd_params_t* p, int32_t n_paths, float stop_threshold, float* log_prob_d,
-                                      float* charge_d, int32_t* top_ticks_d, void* scratch_d, size_t scratch_bytes, void* stream) {
+                                      float* charge_d, int32_t* top_ticks_d, float* state_d, int32_t* flags_d, void* scratch_d,
+                                      size_t scratch_bytes, void* stream) {
   if (!p || (!wfs_d && npix > 0) || !log_prob_d || !charge_d || !scratch_d || npix < 0 || n_ticks < 2) {
     larnd_set_error("larnd_prob_fee_forward: bad argument");
     return LARND_E_ARG;
@@ -232,8 +238,244 @@ extern "C" int larnd_prob_fee_forward(const float* wfs_d, int64_t wfs_row_stride
   for (int s = 0; s < nsteps; ++s) {
     k_prob_step<20><<<npix, PF_THREADS, smem, st>>>(qsum, cmf, cmr, npix, n_ticks, charges, lps, flags, s, nsteps, zscale,
                                                      p->discrimination_threshold, p->hold_interval, logf(stop_threshold), log_prob_d,
-                                                     charge_d, top_ticks_d);
+                                                     charge_d, top_ticks_d, state_d);
     LARND_LAUNCH_CHECK("k_prob_step");
   }
+  if (flags_d) LARND_CUDA(cudaMemcpyAsync(flags_d, flags, (size_t)(nsteps + 1) * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return LARND_OK;
+}
+
+// =============================================================================================== backward
+// VJP of the beam search w.r.t. the waveforms.  The discrete choices (beam ticks, global stop flags) are the forward's
+// (lax.stop_gradient in the reference, fee_jax.py:380).  Steps are walked in reverse with the adjoint of the path state
+// (d charges, d log-probabilities) as carry; every step recomputes its log-probability terms and their partials.
+namespace {
+
+__device__ __forceinline__ float log_ndtr_prime(float x, float l) { return 0.39894228f * expf(-0.5f * x * x - l); }  // pdf / cdf
+
+// value and partials of log_diff_ndtr(a, b)
+__device__ __forceinline__ float ldn_grad(float a, float b, float& da, float& db) {
+  const float la = log_ndtr_f(a), lb = log_ndtr_f(b);
+  const bool gt = a > b;
+  const float sd = gt ? lb - la : -1.0f;
+  const float esd = expf(sd);
+  const float ne = -expm1f(sd);
+  const float arg = (ne - 1e-30f) * 1e10f;
+  const float ns = 1e-30f + softplus_f(arg) / 1e10f;
+  const float lt = logf(ns);
+  const float lts = soft_max_f(lt, -100.0f, 10.0f);
+  const float lpv = la + lts;
+  const float w = sigmoid_f(1000.0f * (a - b));
+  const float k = gt ? sigmoid_f((lt + 100.0f) * 10.0f) * (1.0f / ns) * sigmoid_f(arg) * (-esd) : 0.0f;  // d lts / d sd
+  const float dab = 1000.0f * w * (1.0f - w) * (lpv + 1000.0f);
+  da = w * (1.0f - k) * log_ndtr_prime(a, la) + dab;
+  db = w * k * log_ndtr_prime(b, lb) - dab;
+  return w * lpv + (1.0f - w) * (-1000.0f);
+}
+
+__global__ void k_prob_bwd_setup(const float* __restrict__ wfs, int64_t stride, int npix, int nt, float t_sampling,
+                                 float* __restrict__ qsum, float* __restrict__ cmf, int* __restrict__ amax, float* __restrict__ dq,
+                                 float* __restrict__ dcmf, float* __restrict__ carry, int npaths) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const float* w = wfs + (int64_t)pix * stride;
+  float acc = 0.0f, mx = -INFINITY;
+  int im = 0;
+  for (int t = 0; t < nt; ++t) {
+    acc = __fadd_rn(acc, __fmul_rn(w[t], t_sampling));
+    qsum[(int64_t)pix * nt + t] = acc;
+    if (acc > mx) { mx = acc; im = t; }  // first index attaining the running maximum
+    cmf[(int64_t)pix * nt + t] = mx;
+    amax[(int64_t)pix * nt + t] = im;
+    dq[(int64_t)pix * nt + t] = 0.0f;
+    dcmf[(int64_t)pix * nt + t] = 0.0f;
+  }
+  for (int k = 0; k < 2 * npaths; ++k) carry[(int64_t)pix * 2 * npaths + k] = 0.0f;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(PF_THREADS)
+k_prob_bwd_step(const float* __restrict__ qsum, const float* __restrict__ cmf, int npix, int nt, const float* __restrict__ state,
+                const int* __restrict__ top, const int* __restrict__ flags, int step, int nsteps, float zscale, float thr, int interval,
+                const float* __restrict__ lp_fwd, const float* __restrict__ g_lp, const float* __restrict__ g_q,
+                float* __restrict__ dq, float* __restrict__ dcmf, float* __restrict__ carry) {
+  if (flags[step] == 0) return;  // inactive step: constants out, carry passes through
+  extern __shared__ float smf[];
+  float* s_q = smf;            // [nt]
+  float* s_f = s_q + nt;       // [nt]
+  float* s_gt = s_f + nt;      // [nt] adjoint of log_total_dist_tick (non-zero at the beam ticks only)
+  float* s_dqt = s_gt + nt;    // [nt] contributions to d q_sum[t]
+  float* s_dqs = s_dqt + nt;   // [nt] contributions destined to d q_sum[shifted(t)]
+  float* s_dft = s_dqs + nt;   // [nt] contributions to d cmf[t]
+  float* s_dft1 = s_dft + nt;  // [nt] contributions destined to d cmf[t + 1]
+  float* s_dqt1 = s_dft1 + nt; // [nt] contributions destined to d q_sum[t + 1]
+  __shared__ float s_c[PF_MAXPATHS], s_lp[PF_MAXPATHS], s_dc1[PF_MAXPATHS], s_dlp1[PF_MAXPATHS];
+  __shared__ int s_top[PF_MAXPATHS];
+  __shared__ float s_red[PF_THREADS / 32][2 * PF_MAXPATHS];
+  const int pix = blockIdx.x, ntm = nt - 1;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < nt; t += PF_THREADS) {
+    s_q[t] = qsum[(int64_t)pix * nt + t];
+    s_f[t] = cmf[(int64_t)pix * nt + t];
+    s_gt[t] = 0.0f; s_dqt[t] = 0.0f; s_dqs[t] = 0.0f; s_dft[t] = 0.0f; s_dft1[t] = 0.0f; s_dqt1[t] = 0.0f;
+  }
+  if (threadIdx.x < NP) {
+    s_c[threadIdx.x] = state[((int64_t)pix * nsteps + step) * 2 * NP + threadIdx.x];
+    s_lp[threadIdx.x] = state[((int64_t)pix * nsteps + step) * 2 * NP + NP + threadIdx.x];
+    s_top[threadIdx.x] = top[((int64_t)pix * nsteps + step) * NP + threadIdx.x];
+    s_dc1[threadIdx.x] = carry[(int64_t)pix * 2 * NP + threadIdx.x];
+    s_dlp1[threadIdx.x] = carry[(int64_t)pix * 2 * NP + NP + threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x < NP) {
+    const int tk = s_top[threadIdx.x];
+    s_gt[tk] = s_dlp1[threadIdx.x];                                   // new_log_prob[k] = log_total_dist_tick[top_k]  (distinct ticks)
+    const int bn = min(min(tk + interval + 1, nt - 1) + 1, nt - 1);   // charges_new[k] = q_sum[best_next]
+    atomicAdd(dq + (int64_t)pix * nt + bn, s_dc1[threadIdx.x]);
+  }
+  __syncthreads();
+  float dc[NP], dlp[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) { dc[p] = 0.0f; dlp[p] = 0.0f; }
+  const float* glp = g_lp + ((int64_t)pix * nsteps + step) * ntm;
+  const float* gq = g_q + ((int64_t)pix * nsteps + step) * ntm;
+  const float* lpf = lp_fwd + ((int64_t)pix * nsteps + step) * ntm;
+  for (int t = threadIdx.x; t < ntm; t += PF_THREADS) {
+    const int sh = min(t + interval + 1, nt - 1);
+    const float q_t = s_q[t], q_t1 = s_q[t + 1], q_sh = s_q[sh], f_t = s_f[t], f_t1 = s_f[t + 1];
+    const float esp = q_sh + thr - 0.5f * (q_t1 + q_t);
+    const float w2 = sigmoid_f(10.0f * (esp - thr));
+    const float g_hit = glp[t], lse_hit = lpf[t], g_tot = s_gt[t];
+    float lse_tot = 0.0f;
+    if (g_tot != 0.0f) {  // beam ticks only: logsumexp over the paths of (log_guess + previous log-probability)
+      float vb[NP], mb = -INFINITY;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const float c = s_c[p];
+        vb[p] = log_diff_ndtr_f(((f_t1 - c) - thr) * zscale, ((f_t - c) - thr) * zscale) + s_lp[p];
+        mb = fmaxf(mb, vb[p]);
+      }
+      float sb = 0.0f;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) sb += expf(vb[p] - mb);
+      lse_tot = logf(sb) + mb;
+    }
+    float d_esp = 0.0f, a_qs = 0.0f, a_qt = 0.0f, a_ft1 = 0.0f, a_ft = 0.0f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const float c = s_c[p], lp = s_lp[p];
+      float dga, dgb, dea, deb;
+      const float vg = ldn_grad(((f_t1 - c) - thr) * zscale, ((f_t - c) - thr) * zscale, dga, dgb);
+      const float ve = ldn_grad(((q_sh - c) - thr) * zscale, ((q_t - c) - thr) * zscale, dea, deb);
+      const float m = fminf(ve, vg);
+      const float dme = ve < vg ? 1.0f : (ve == vg ? 0.5f : 0.0f), dmg = 1.0f - dme;
+      const float sm1 = soft_max_f(m, -1000.0f, 1.0f);
+      const float le = w2 * sm1 + (1.0f - w2) * (-1000.0f);
+      const float G_le = expf((le + lp) - lse_hit) * g_hit;
+      const float G_vt = g_tot != 0.0f ? expf((vg + lp) - lse_tot) * g_tot : 0.0f;
+      dlp[p] += G_le + G_vt;
+      d_esp += G_le * 10.0f * w2 * (1.0f - w2) * (sm1 + 1000.0f);
+      const float G_m = G_le * w2 * sigmoid_f(m + 1000.0f);
+      const float G_ve = G_m * dme, G_vg = G_m * dmg + G_vt;
+      const float xa_e = G_ve * dea * zscale, xb_e = G_ve * deb * zscale, xa_g = G_vg * dga * zscale, xb_g = G_vg * dgb * zscale;
+      a_qs += xa_e; a_qt += xb_e; a_ft1 += xa_g; a_ft += xb_g;
+      dc[p] -= (xa_e + xb_e) + (xa_g + xb_g);
+    }
+    d_esp += gq[t];
+    s_dqs[t] = a_qs + d_esp;
+    s_dqt[t] = a_qt - 0.5f * d_esp;
+    s_dqt1[t] = -0.5f * d_esp;
+    s_dft[t] = a_ft;
+    s_dft1[t] = a_ft1;
+  }
+  __syncthreads();
+  // scatter the per-tick contributions to their destinations (each destination index is owned by one thread)
+  for (int u = threadIdx.x; u < nt; u += PF_THREADS) {
+    float a = (u < ntm ? s_dqt[u] : 0.0f) + (u >= 1 ? s_dqt1[u - 1] : 0.0f);
+    float b = (u < ntm ? s_dft[u] : 0.0f) + (u >= 1 ? s_dft1[u - 1] : 0.0f);
+    if (u < nt - 1) {
+      const int t = u - interval - 1;               // shifted(t) = u, unclipped
+      if (t >= 0 && t < ntm) a += s_dqs[t];
+    } else {
+      for (int t = max(0, nt - 2 - interval); t < ntm; ++t) a += s_dqs[t];  // every t whose shifted tick is clipped to nt-1
+    }
+    dq[(int64_t)pix * nt + u] += a;
+    dcmf[(int64_t)pix * nt + u] += b;
+  }
+  // block reduction of the path adjoints -> carry for the previous step
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float v0 = dc[p], v1 = dlp[p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+    if (lane == 0) { s_red[wid][p] = v0; s_red[wid][NP + p] = v1; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * NP) {
+    float v = 0.0f;
+    for (int w = 0; w < PF_THREADS / 32; ++w) v += s_red[w][threadIdx.x];
+    carry[(int64_t)pix * 2 * NP + threadIdx.x] = v;
+  }
+}
+
+// d q_sum[argmax] += d cmf, then d wfs = t_sampling * reverse cumsum of d q_sum
+__global__ void k_prob_bwd_finish(const float* __restrict__ dq, const float* __restrict__ dcmf, const int* __restrict__ amax, int npix,
+                                  int nt, float t_sampling, float* __restrict__ dq_tmp, float* __restrict__ g_wfs, int64_t g_stride) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float* tmp = dq_tmp + (int64_t)pix * nt;
+  for (int t = 0; t < nt; ++t) tmp[t] = dq[(int64_t)pix * nt + t];
+  for (int t = 0; t < nt; ++t) tmp[amax[(int64_t)pix * nt + t]] += dcmf[(int64_t)pix * nt + t];
+  float acc = 0.0f;
+  for (int t = nt - 1; t >= 0; --t) {
+    acc += tmp[t];
+    g_wfs[(int64_t)pix * g_stride + t] = acc * t_sampling;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t larnd_prob_fee_bwd_scratch_bytes(int32_t npix, int32_t n_ticks, int32_t n_paths) {
+  if (npix < 0 || n_ticks < 2 || n_paths < 1) return 0;
+  return align_up((size_t)npix * n_ticks * 4, 256) * 6 + align_up((size_t)npix * 2 * n_paths * 4, 256);
+}
+
+extern "C" int larnd_prob_fee_backward(const float* wfs_d, int64_t wfs_row_stride, int32_t npix, int32_t n_ticks,
+                                       const larnd_params_t* p, int32_t n_paths, const float* g_log_prob_d, const float* g_charge_d,
+                                       const float* log_prob_d, const float* state_d, const int32_t* top_ticks_d, const int32_t* flags_d,
+                                       float* g_wfs_d, int64_t g_row_stride, void* scratch_d, size_t scratch_bytes, void* stream) {
+  if (!p || !g_log_prob_d || !g_charge_d || !log_prob_d || !state_d || !top_ticks_d || !flags_d || !g_wfs_d || !scratch_d || npix < 0 ||
+      n_ticks < 2) {
+    larnd_set_error("larnd_prob_fee_backward: bad argument");
+    return LARND_E_ARG;
+  }
+  if (n_paths != 20) { larnd_set_error("larnd_prob_fee_backward: fee_paths_scaling must be 20"); return LARND_E_ARG; }
+  if (scratch_bytes < larnd_prob_fee_bwd_scratch_bytes(npix, n_ticks, n_paths)) { larnd_set_error("prob_fee backward scratch too small"); return LARND_E_CAPACITY; }
+  if (npix == 0) return LARND_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nsteps = p->max_adc_values;
+  char* b = reinterpret_cast<char*>(scratch_d);
+  const size_t row = align_up((size_t)npix * n_ticks * 4, 256);
+  float* qsum = reinterpret_cast<float*>(b); b += row;
+  float* cmf = reinterpret_cast<float*>(b); b += row;
+  int* amax = reinterpret_cast<int*>(b); b += row;
+  float* dq = reinterpret_cast<float*>(b); b += row;
+  float* dcmf = reinterpret_cast<float*>(b); b += row;
+  float* tmp = reinterpret_cast<float*>(b); b += row;
+  float* carry = reinterpret_cast<float*>(b);
+  k_prob_bwd_setup<<<(npix + 63) / 64, 64, 0, st>>>(wfs_d, wfs_row_stride, npix, n_ticks, p->t_sampling, qsum, cmf, amax, dq, dcmf, carry, n_paths);
+  LARND_LAUNCH_CHECK("k_prob_bwd_setup");
+  const size_t smem = (size_t)8 * n_ticks * sizeof(float);
+  if (smem > 200 * 1024) { larnd_set_error("larnd_prob_fee_backward: too many ticks for shared memory"); return LARND_E_ARG; }
+  LARND_CUDA(cudaFuncSetAttribute(k_prob_bwd_step<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const float zscale = 1.0f / p->reset_noise_charge;
+  for (int s = nsteps - 1; s >= 0; --s) {
+    k_prob_bwd_step<20><<<npix, PF_THREADS, smem, st>>>(qsum, cmf, npix, n_ticks, state_d, top_ticks_d, flags_d, s, nsteps, zscale,
+                                                         p->discrimination_threshold, p->hold_interval, log_prob_d, g_log_prob_d,
+                                                         g_charge_d, dq, dcmf, carry);
+    LARND_LAUNCH_CHECK("k_prob_bwd_step");
+  }
+  k_prob_bwd_finish<<<(npix + 63) / 64, 64, 0, st>>>(dq, dcmf, amax, npix, n_ticks, p->t_sampling, tmp, g_wfs_d, g_row_stride);
+  LARND_LAUNCH_CHECK("k_prob_bwd_finish");
   return LARND_OK;
 }

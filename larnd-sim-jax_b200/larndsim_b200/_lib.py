@@ -128,8 +128,12 @@ def _declare(lib):
         getattr(lib, name).restype = C.c_int
     lib.larnd_prob_fee_scratch_bytes.argtypes = [i32, i32, i32, i32]
     lib.larnd_prob_fee_scratch_bytes.restype = sz
-    lib.larnd_prob_fee_forward.argtypes = [vp, i64, i32, i32, PP, i32, C.c_float, vp, vp, vp, vp, sz, vp]
+    lib.larnd_prob_fee_forward.argtypes = [vp, i64, i32, i32, PP, i32, C.c_float, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.larnd_prob_fee_forward.restype = C.c_int
+    lib.larnd_prob_fee_bwd_scratch_bytes.argtypes = [i32, i32, i32]
+    lib.larnd_prob_fee_bwd_scratch_bytes.restype = sz
+    lib.larnd_prob_fee_backward.argtypes = [vp, i64, i32, i32, PP, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp, sz, vp]
+    lib.larnd_prob_fee_backward.restype = C.c_int
     PCC = C.POINTER(ChopColumns)
     lib.larnd_chop_count.argtypes = [vp, i64, PCC, C.c_double, vp, vp]
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]

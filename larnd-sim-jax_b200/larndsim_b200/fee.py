@@ -26,33 +26,71 @@ def get_adc_values(params, pixels_signals, noise_rng_key=None):
     return integral, fs.ticks
 
 
-def get_adc_values_average_noise_vmap(params, wfs, stop_threshold=1e-9, return_top_ticks=False):
-    """(log_prob_distrib (Npix, MAX_ADC_VALUES, Nticks-1), charge_distrib (same shape)) — the noise-averaged beam-search
-    front end of the reference (fee_jax.py:390-461), run by the k_prob_* kernels (csrc/prob_fee.cu).  Forward only in this
-    round: the VJP w.r.t. the waveforms is the next row of the build plan."""
+def _prob_forward(params, w, stop_threshold, want_state):
     import ctypes as C
     from . import _lib
-    _sim._check_cuda(wfs, "wfs")
-    if torch.is_grad_enabled() and wfs.requires_grad:
-        raise NotImplementedError("the probabilistic front end is forward-only in this build (no VJP yet)")
-    w = wfs.detach()
-    if w.dtype != torch.float32 or w.dim() != 2 or w.stride(1) != 1:
-        w = w.contiguous().float()
     lib = _lib.get_lib()
     pod = _sim.make_pod(params)
     npix, nt = w.shape
     k, npaths = pod.max_adc_values, int(params.fee_paths_scaling)
     dev = w.device
+    vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
     with torch.cuda.device(dev):
         lp = torch.empty((npix, k, nt - 1), dtype=torch.float32, device=dev)
         qd = torch.empty((npix, k, nt - 1), dtype=torch.float32, device=dev)
-        top = torch.empty((npix, k, npaths), dtype=torch.int32, device=dev) if return_top_ticks else None
+        top = torch.empty((npix, k, npaths), dtype=torch.int32, device=dev) if want_state else None
+        state = torch.empty((npix, k, 2 * npaths), dtype=torch.float32, device=dev) if want_state else None
+        flags = torch.zeros(k + 1, dtype=torch.int32, device=dev) if want_state else None
         scratch = torch.empty(lib.larnd_prob_fee_scratch_bytes(npix, nt, npaths, k), dtype=torch.uint8, device=dev)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(lib.larnd_prob_fee_forward(C.c_void_p(w.data_ptr()), w.stride(0), npix, nt, C.byref(pod), npaths,
-                                              float(stop_threshold), C.c_void_p(lp.data_ptr()), C.c_void_p(qd.data_ptr()),
-                                              C.c_void_p(top.data_ptr()) if top is not None else C.c_void_p(0),
-                                              C.c_void_p(scratch.data_ptr()), scratch.numel(), st))
+        _lib.check(lib.larnd_prob_fee_forward(vp(w), w.stride(0), npix, nt, C.byref(pod), npaths, float(stop_threshold), vp(lp), vp(qd),
+                                              vp(top), vp(state), vp(flags), vp(scratch), scratch.numel(), st))
+    return lp, qd, top, state, flags, pod
+
+
+class _ProbFee(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wfs, params, stop_threshold):
+        w = wfs.detach()
+        if w.dtype != torch.float32 or w.stride(1) != 1:
+            w = w.contiguous().float()
+        lp, qd, top, state, flags, pod = _prob_forward(params, w, stop_threshold, True)
+        ctx.save_for_backward(w, lp, top, state, flags)
+        ctx.pod, ctx.npaths = pod, int(params.fee_paths_scaling)
+        return lp, qd
+
+    @staticmethod
+    def backward(ctx, g_lp, g_q):
+        import ctypes as C
+        from . import _lib
+        w, lp, top, state, flags = ctx.saved_tensors
+        lib = _lib.get_lib()
+        npix, nt = w.shape
+        g_lp = (torch.zeros_like(lp) if g_lp is None else g_lp).contiguous().float()
+        g_q = (torch.zeros_like(lp) if g_q is None else g_q).contiguous().float()
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(w.device):
+            g = torch.empty((npix, nt), dtype=torch.float32, device=w.device)
+            scratch = torch.empty(lib.larnd_prob_fee_bwd_scratch_bytes(npix, nt, ctx.npaths), dtype=torch.uint8, device=w.device)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.larnd_prob_fee_backward(vp(w), w.stride(0), npix, nt, C.byref(ctx.pod), ctx.npaths, vp(g_lp), vp(g_q), vp(lp),
+                                                   vp(state), vp(top), vp(flags), vp(g), nt, vp(scratch), scratch.numel(), st))
+        return g, None, None
+
+
+def get_adc_values_average_noise_vmap(params, wfs, stop_threshold=1e-9, return_top_ticks=False):
+    """(log_prob_distrib (Npix, MAX_ADC_VALUES, Nticks-1), charge_distrib (same shape)) — the noise-averaged beam-search
+    front end of the reference (fee_jax.py:390-461), run by the k_prob_* kernels (csrc/prob_fee.cu).  Differentiable
+    w.r.t. the waveforms (the beam ticks are the forward's, like lax.stop_gradient in the reference)."""
+    _sim._check_cuda(wfs, "wfs")
+    if wfs.dim() != 2:
+        raise ValueError("wfs must be (Npix, Nticks)")
+    if torch.is_grad_enabled() and wfs.requires_grad and not return_top_ticks:
+        return _ProbFee.apply(wfs, params, stop_threshold)
+    w = wfs.detach()
+    if w.dtype != torch.float32 or w.stride(1) != 1:
+        w = w.contiguous().float()
+    lp, qd, top, _, _, _ = _prob_forward(params, w, stop_threshold, return_top_ticks)
     return (lp, qd, top) if return_top_ticks else (lp, qd)
 
 

@@ -398,7 +398,7 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
 
 def simulate_probabilistic(params, wfs, unique_pixels):
     """(adcs_distrib (Npix,10,Nticks-1), pixel_x, pixel_y, ticks_prob (log-probabilities), event) — reference:
-    sim_jax.py:772-812.  Forward only in this build."""
+    sim_jax.py:772-812.  Differentiable through adcs_distrib and ticks_prob w.r.t. the waveforms."""
     from .detsim import get_pixel_coordinates, id2pixel
     from .fee import digitize, get_adc_values_average_noise_vmap
     ticks_prob, charge_distrib = get_adc_values_average_noise_vmap(params, wfs)

@@ -87,7 +87,7 @@ def top_k_indices(v, k):
     return np.argsort(-v, kind="stable")[:k]
 
 
-def find_one_hit_step(q_sum, prev_charges, prev_log_prob, sigma, threshold, interval, nvalues):
+def find_one_hit_step(q_sum, prev_charges, prev_log_prob, sigma, threshold, interval, nvalues, force_top=None):
     """One beam-search step for ONE pixel (fee_jax.py:334-388).  q_sum (Nt,), prev_* (nvalues,)."""
     dt = q_sum.dtype.type
     nt = q_sum.shape[0]
@@ -110,14 +110,17 @@ def find_one_hit_step(q_sum, prev_charges, prev_log_prob, sigma, threshold, inte
     fend = np.clip(shifted + interval + 1, 0, nt - 1)
     lf = log_ndtr(((mfs[:, fend] - next_q - thr) * z).astype(q_sum.dtype))
     lsel = logsumexp((log_guess + lf + prev_log_prob[:, None]).astype(q_sum.dtype), 0)
-    top = top_k_indices(lsel, nvalues)
+    top = top_k_indices(lsel, nvalues) if force_top is None else np.asarray(force_top)
     new_lp = log_tot[top]
     best_next = np.clip(shifted[top] + 1, 0, nt - 1)
     return (q_sum[best_next], new_lp), (log_hit, esp), top
 
 
-def get_adc_values_average_noise(params, wfs, stop_threshold=1e-9, dt=np.float32, return_state=False):
-    """(log_prob_distrib (Npix, MAX_ADC, Nt-1), charge_distrib (Npix, MAX_ADC, Nt-1)) — fee_jax.py:390-461."""
+def get_adc_values_average_noise(params, wfs, stop_threshold=1e-9, dt=np.float32, return_state=False, force_tops=None,
+                                 force_active=None):
+    """(log_prob_distrib (Npix, MAX_ADC, Nt-1), charge_distrib (Npix, MAX_ADC, Nt-1)) — fee_jax.py:390-461.
+    ``force_tops`` / ``force_active`` pin the discrete choices (beam ticks, global stop flags per step) so that finite
+    differences of a float64 evaluation differentiate the same smooth branch as a float32 run."""
     wfs = np.asarray(wfs, dtype=dt)
     npix, nt = wfs.shape
     nv = int(params.fee_paths_scaling)
@@ -144,12 +147,13 @@ def get_adc_values_average_noise(params, wfs, stop_threshold=1e-9, dt=np.float32
             tot = np.empty(npix, dt)
             for p in range(npix):
                 (c_new, lp_new), (lh, esp), top = find_one_hit_step(q_sum[p], charges[p], lps[p], params.RESET_NOISE_CHARGE,
-                                                                   params.DISCRIMINATION_THRESHOLD, interval, nv)
+                                                                   params.DISCRIMINATION_THRESHOLD, interval, nv,
+                                                                   None if force_tops is None else force_tops[p, s])
                 charges[p], lps[p] = c_new, lp_new
                 out_lp[p, s], out_q[p, s] = lh, esp
                 tops[p, s] = top
                 tot[p] = logsumexp(lp_new, 0)
-            active = bool(np.any(tot > dt(math.log(stop_threshold))))
+            active = bool(np.any(tot > dt(math.log(stop_threshold)))) if force_active is None else bool(force_active[s + 1])
         else:
             out_lp[:, s] = -1000.0
             out_q[:, s] = 0.0

@@ -511,3 +511,48 @@ def test_probabilistic_front_end_forward_matches_oracle(torch_dev):
     ref = pf.simulate_probabilistic(op, w, uniq_o[sel])
     assert np.abs(out[0].cpu().numpy() - ref[0]).max() < 2e-3 and np.array_equal(out[4].cpu().numpy(), ref[4])
     assert np.allclose(out[1].cpu().numpy(), ref[1]) and np.allclose(out[2].cpu().numpy(), ref[2])
+
+
+def test_probabilistic_front_end_gradient_matches_finite_differences(torch_dev):
+    """VJP of the beam search w.r.t. the waveforms (k_prob_bwd_*) against central differences of the float64 oracle with
+    the discrete choices (beam ticks, stop flags) pinned to the kernel's forward.  A small positive tilt keeps the running
+    sum strictly increasing so that the running maximum has a unique arg-max (no kinks)."""
+    import torch
+    from larndsim_b200 import fee
+    from oracle import prob_fee as pf
+    kw = dict(number_pix_neighbors=1, signal_length=100, RESET_NOISE_CHARGE=900.0)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    tr = cm.small_batch(600, ibatch=2, pad=2, precision=0.01)
+    wfs_o, _ = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={})
+    sel = np.argsort(-np.abs(wfs_o).sum(axis=1))[:3]
+    w = np.ascontiguousarray(wfs_o[sel] + 2.0).astype(np.float32)
+    rng = np.random.default_rng(2)
+    wt = torch.as_tensor(w, device=torch_dev).requires_grad_(True)
+    lp, qd = fee.get_adc_values_average_noise_vmap(pp, wt)
+    _, _, top = fee.get_adc_values_average_noise_vmap(pp, wt.detach(), return_top_ticks=True)
+    # loss: probability-weighted sums, the kind of quantity the probabilistic losses build (bounded weights)
+    A = rng.uniform(0.5, 1.5, size=lp.shape).astype(np.float32)
+    B = rng.uniform(-1, 1, size=lp.shape).astype(np.float32) * 1e-3
+    loss = (torch.exp(lp) * torch.as_tensor(A, device=torch_dev)).sum() + (torch.exp(lp) * qd * torch.as_tensor(B, device=torch_dev)).sum()
+    loss.backward()
+    g = wt.grad.cpu().numpy().astype(np.float64)
+    tops = top.cpu().numpy()
+
+    def L(x):
+        l, q = pf.get_adc_values_average_noise(op, x, dt=np.float64, force_tops=tops)
+        return float((np.exp(l) * A).sum() + (np.exp(l) * q * B).sum())
+
+    assert abs(float(loss) - L(w.astype(np.float64))) < 2e-3 * abs(L(w.astype(np.float64)))
+    checked = 0
+    for pix in range(len(sel)):
+        peak = int(np.argmax(w[pix]))
+        for t in (peak - 30, peak - 5, peak, peak + 7, peak + 40, 100):
+            h = 0.05 * max(1.0, abs(w[pix, t]))
+            xp, xm = w.astype(np.float64).copy(), w.astype(np.float64).copy()
+            xp[pix, t] += h
+            xm[pix, t] -= h
+            fd = (L(xp) - L(xm)) / (2 * h)
+            assert abs(g[pix, t] - fd) <= 2e-2 * abs(fd) + 2e-3 * np.abs(g[pix]).max(), (pix, t, g[pix, t], fd)
+            checked += 1
+    assert checked == 18 and np.abs(g).max() > 0
