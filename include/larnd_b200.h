@@ -240,6 +240,15 @@ int larnd_rng_split(const uint32_t key[2], int num, int partitionable, uint32_t*
 int larnd_rng_normal(const uint32_t key[2], int64_t n, int partitionable, float* out_d, void* stream);
 int larnd_rng_fee_noise(const uint32_t key[2], int32_t npix, int32_t n_adc, int partitionable, float* noise_d, void* stream);
 
+/* Weighted RBF field of a point set: for every target t (n_targets, 3)
+ *   field[t] = { sum_j w_j K(t, z_j),  sum_j w_j K(t, z_j) (z_j - t) }   with K = exp(-|t - z|^2 / (2 sigma^2)),
+ * the building block of the MMD loss (losses_jax.py:14-39) and of its gradient w.r.t. positions and weights.  Pairs
+ * further apart than 15 sigma (exactly 0 in float32; e.g. hits of different events, offset by 1e5) are skipped per tile. */
+size_t larnd_rbf_field_scratch_bytes(int32_t n_targets, int32_t n_sources);
+int larnd_rbf_field(const float* targets_d, int32_t n_targets, const float* sources_d, const float* weights_d,
+                    int32_t n_sources, float sigma, float* field_d /* (n_targets, 4) */, void* scratch_d, size_t scratch_bytes,
+                    void* stream);
+
 /* Optional device-side timing of the dominant kernels (used by bench.py for the roofline numbers): when
  * enabled, CUDA events are recorded on the launching stream immediately around
  *   slot 0: k_prepare   slot 1: k_lut_accumulate   slot 2: k_lut_backward   slot 3: k_fee_forward

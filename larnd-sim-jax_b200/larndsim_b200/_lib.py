@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "liblarnd_b200.so")
-SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu", "chop.cu", "rng.cu", "prob_fee.cu"]
+SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu", "chop.cu", "rng.cu", "prob_fee.cu", "losses.cu"]
 
 MAX_TPC = 8
 MAX_TEMPLATES = 128
@@ -134,6 +134,10 @@ def _declare(lib):
     lib.larnd_prob_fee_bwd_scratch_bytes.restype = sz
     lib.larnd_prob_fee_backward.argtypes = [vp, i64, i32, i32, PP, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp, sz, vp]
     lib.larnd_prob_fee_backward.restype = C.c_int
+    lib.larnd_rbf_field_scratch_bytes.argtypes = [i32, i32]
+    lib.larnd_rbf_field_scratch_bytes.restype = sz
+    lib.larnd_rbf_field.argtypes = [vp, i32, vp, vp, i32, C.c_float, vp, vp, sz, vp]
+    lib.larnd_rbf_field.restype = C.c_int
     PCC = C.POINTER(ChopColumns)
     lib.larnd_chop_count.argtypes = [vp, i64, PCC, C.c_double, vp, vp]
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]

@@ -25,11 +25,55 @@ def _kernel_sum(x, y, px, py, sigma, block=4096):
     return tot
 
 
+def rbf_field(targets, sources, weights, sigma):
+    """(N, 4) field {sum_j w_j K(t, z_j), sum_j w_j K(t, z_j) (z_j - t)} of the weighted sources at the targets, computed by
+    the tiled k_rbf_field kernel (csrc/losses.cu); pairs beyond 15 sigma are skipped (exactly zero in float32)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.get_lib()
+    t = targets.detach().contiguous().float()
+    z = sources.detach().contiguous().float()
+    w = weights.detach().contiguous().float()
+    out = torch.empty((t.shape[0], 4), dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        scratch = torch.empty(max(lib.larnd_rbf_field_scratch_bytes(t.shape[0], z.shape[0]), 4), dtype=torch.uint8, device=t.device)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        vp = lambda a: C.c_void_p(a.data_ptr())
+        _lib.check(lib.larnd_rbf_field(vp(t), t.shape[0], vp(z), vp(w), z.shape[0], float(sigma), vp(out), vp(scratch), scratch.numel(), st))
+    return out
+
+
+class _KernelSums(torch.autograd.Function):
+    """(K_xx, K_yy, K_xy) of the weighted MMD with gradients w.r.t. x and px (the reference side y, py is data)."""
+
+    @staticmethod
+    def forward(ctx, x, px, y, py, sigma):
+        fxx = rbf_field(x, x, px, sigma)
+        fxy = rbf_field(x, y, py, sigma)
+        fyy = rbf_field(y, y, py, sigma)
+        ctx.save_for_backward(fxx, fxy, px.detach())
+        ctx.sigma = float(sigma)
+        pxd, pyd = px.detach().float(), py.detach().float()
+        return torch.stack([(pxd * fxx[:, 0]).sum(), (pyd * fyy[:, 0]).sum(), (pxd * fxy[:, 0]).sum()])
+
+    @staticmethod
+    def backward(ctx, g):
+        fxx, fxy, px = ctx.saved_tensors
+        inv = 1.0 / (ctx.sigma * ctx.sigma)
+        g_x = (2.0 * g[0] * px[:, None] * fxx[:, 1:] + g[2] * px[:, None] * fxy[:, 1:]) * inv
+        g_px = 2.0 * g[0] * fxx[:, 0] + g[2] * fxy[:, 0]
+        return g_x, g_px, None, None, None
+
+
 def mmd(x, y, px, py, sigma, reduce=None):
     """Weighted MMD^2.  ``reduce``: optional differentiable sum over ranks applied to the five sums (events never
     interact across ranks: the event*1e5 offset puts them > 1e5 apart), see parallel.allreduce_sum_differentiable."""
-    sums = torch.stack([_kernel_sum(x, x, px, px, sigma), _kernel_sum(y, y, py, py, sigma), _kernel_sum(x, y, px, py, sigma),
-                        px.sum(), py.sum()])
+    if x.is_cuda and x.shape[-1] == 3:   # tiled CUDA kernel (csrc/losses.cu); the torch expression below serves CPU tensors
+        ks = _KernelSums.apply(x, px, y, py, sigma)
+        sums = torch.cat([ks, torch.stack([px.sum(), py.sum()])])
+    else:
+        sums = torch.stack([_kernel_sum(x, x, px, px, sigma), _kernel_sum(y, y, py, py, sigma), _kernel_sum(x, y, px, py, sigma),
+                            px.sum(), py.sum()])
     if reduce is not None:
         sums = reduce(sums)
     kxx, kyy, kxy, sx, sy = sums

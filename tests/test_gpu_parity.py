@@ -556,3 +556,34 @@ def test_probabilistic_front_end_gradient_matches_finite_differences(torch_dev):
             assert abs(g[pix, t] - fd) <= 2e-2 * abs(fd) + 2e-3 * np.abs(g[pix]).max(), (pix, t, g[pix, t], fd)
             checked += 1
     assert checked == 18 and np.abs(g).max() > 0
+
+
+def test_mmd_kernel_matches_dense_evaluation(torch_dev):
+    """k_rbf_field (tiled, far tiles skipped) against the dense float64 evaluation of the reference's mmd
+    (losses_jax.py:14-39) on event-offset hit clouds, values and gradients w.r.t. positions and weights."""
+    import torch
+    from larndsim_b200 import losses
+    rng = np.random.default_rng(4)
+    def cloud(n, nev):
+        ev = np.sort(rng.integers(0, nev, n))
+        return np.stack([rng.normal(0, 3, n) + ev * 1e5, rng.normal(0, 3, n), rng.normal(0, 3, n)], 1), rng.uniform(0.5, 2, n)
+    (x, px), (y, py) = cloud(700, 5), cloud(650, 5)
+    # the event offset of 1e5 per event costs float32 position bits (in the reference too): compare on the float32-rounded inputs
+    x, px, y, py = [a.astype(np.float32).astype(np.float64) for a in (x, px, y, py)]
+    sigma = 1.3
+    xt = torch.tensor(x, dtype=torch.float32, device=torch_dev, requires_grad=True)
+    pt = torch.tensor(px, dtype=torch.float32, device=torch_dev, requires_grad=True)
+    yt, qt = torch.tensor(y, dtype=torch.float32, device=torch_dev), torch.tensor(py, dtype=torch.float32, device=torch_dev)
+    val = losses.mmd(xt, yt, pt, qt, sigma)
+    val.backward()
+    xd = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    pd = torch.tensor(px, dtype=torch.float64, requires_grad=True)
+    yd, qd = torch.tensor(y, dtype=torch.float64), torch.tensor(py, dtype=torch.float64)
+    K = lambda a, b: torch.exp(-((a[:, None, :] - b[None, :, :]) ** 2).sum(-1) / (2 * sigma ** 2))
+    ref = ((K(xd, xd) * pd[:, None] * pd[None, :]).sum() / pd.sum() ** 2 + (K(yd, yd) * qd[:, None] * qd[None, :]).sum() / qd.sum() ** 2
+           - 2 * (K(xd, yd) * pd[:, None] * qd[None, :]).sum() / (pd.sum() * qd.sum()))
+    ref.backward()
+    assert abs(float(val) - float(ref)) < 2e-5 * max(abs(float(ref)), 1e-3) + 1e-7
+    gx, gp = xt.grad.cpu().double(), pt.grad.cpu().double()
+    assert (gx - xd.grad).abs().max() < 1e-4 * xd.grad.abs().max() + 1e-9
+    assert (gp - pd.grad).abs().max() < 1e-4 * pd.grad.abs().max() + 1e-9
