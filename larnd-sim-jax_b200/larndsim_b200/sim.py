@@ -40,6 +40,17 @@ def get_size_history():
     return size_history_dict
 
 
+def shift_tracks(params, tracks, fields):
+    """Subtracts (shift_x, shift_y, shift_z) from the nine coordinate columns (reference: sim_jax.py:109-119)."""
+    f = tuple(fields)
+    out = tracks.clone()
+    for ax in "xyz":
+        sh = params.value("shift_" + ax)
+        for col in (ax, ax + "_start", ax + "_end"):
+            out[:, f.index(col)] -= sh
+    return out
+
+
 # ------------------------------------------------------------------------------------------ parameter block
 def _f(params, name):
     return params.value(name)
@@ -269,6 +280,76 @@ def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, 
 def simulate_signals_state(params, response_template, tracks, fields, **kw):
     """Kernel-level access for tests: returns the LutState (full waveforms incl. garbage column, workspace)."""
     return lut_forward(params, response_template, tracks, fields, **kw)
+
+
+def simulate_drift_new(params, tracks, fields, response_template=None, n_events=None):
+    """The ten per-segment arrays of the reference's simulate_drift_new (sim_jax.py:375-453), rebuilt from the records the
+    prepare kernel writes: (main_pixels, pixels (N,5,5), nelectrons (N*25), t0_after_diff (N*25), long_diff (N*25),
+    currents_idx (N*25,2), pIDs_neigh (N,P,P), currents_idx_neigh (N*P*P,2), nelectrons_neigh (N), t0_neigh (N)).
+    The fused kernels never materialise these streams; this view exists for inspection and tests."""
+    from .detsim import pixel2id
+    _check_cuda(tracks, "tracks")
+    lib = _lib.get_lib()
+    tracks = tracks.contiguous()
+    n = tracks.shape[0]
+    cols = make_columns(fields)
+    if n_events is None:
+        n_events = n_events_of(tracks, fields)
+    with torch.cuda.device(tracks.device):
+        if response_template is not None:
+            lut = get_lut(response_template, params.signal_length)
+            pod = make_pod(params, lut.shape)
+        else:
+            fake = _FakeLut(params)
+            lut, pod = fake, make_pod(params, fake.shape)
+        st = LutState()
+        ws_bytes = lib.larnd_workspace_bytes(n, n_events, pod.n_tpc, pod.n_pixels_x, pod.n_pixels_y)
+        st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=tracks.device)
+        st.counts = torch.zeros(4, dtype=torch.int32, device=tracks.device)
+        st.n = n
+        _lib.check(lib.larnd_lut_prepare(_ptr(tracks), n, C.byref(cols), C.byref(pod), lut.handle, n_events, _ptr(st.workspace),
+                                         ws_bytes, _ptr(st.counts), _stream()))
+    r = record_fields(st)
+    nb, nn, ntpc = pod.nb_sampling_bins_per_pixel, pod.number_pix_neighbors, pod.n_tpc
+    dev = tracks.device
+    fd = lambda a, b: torch.div(a, b, rounding_mode="floor")
+    ep = r["EP"]
+    event, plane = fd(ep, ntpc), ep - fd(ep, ntpc) * ntpc
+    k = torch.arange(-2, 3, device=dev, dtype=torch.int32)
+    bxs, bys = r["BX"][:, None] + k[None, :], r["BY"][:, None] + k[None, :]
+    pixels = pixel2id(params, fd(bxs, nb)[:, :, None].expand(-1, 5, 5), fd(bys, nb)[:, None, :].expand(-1, 5, 5), plane[:, None, None], event[:, None, None])
+    wx = torch.stack([r["WX%d" % i] for i in range(5)], 1)
+    wy = torch.stack([r["WY%d" % i] for i in range(5)], 1)
+    nelectrons = (r["Q"][:, None, None] * (wx[:, :, None] * wy[:, None, :])).reshape(-1)
+    t0 = r["FT"] * float(np.float32(params.t_sampling))
+    cidx = lambda b: (torch.remainder(b, nb).float() - nb // 2 + 0.5).abs().to(torch.int32)
+    currents_idx = torch.stack([cidx(bxs)[:, :, None].expand(-1, 5, 5), cidx(bys)[:, None, :].expand(-1, 5, 5)], -1).reshape(-1, 2)
+    g = torch.arange(-nn, nn + 1, device=dev, dtype=torch.int32)
+    mpx, mpy = fd(r["BX"], nb), fd(r["BY"], nb)
+    pids_neigh = pixel2id(params, (mpx[:, None] + g[None, :])[:, :, None].expand(-1, 2 * nn + 1, 2 * nn + 1),
+                          (mpy[:, None] + g[None, :])[:, None, :].expand(-1, 2 * nn + 1, 2 * nn + 1), plane[:, None, None], event[:, None, None]).clone()
+    pids_neigh[:, nn, nn] = -999
+    cn = lambda b: (torch.remainder(b, nb).float()[:, None] - nb // 2 + 0.5 - (g * nb).float()[None, :]).abs().to(torch.int32)
+    cin = torch.stack([cn(r["BX"])[:, :, None].expand(-1, 2 * nn + 1, 2 * nn + 1), cn(r["BY"])[:, None, :].expand(-1, 2 * nn + 1, 2 * nn + 1)], -1).reshape(-1, 2)
+    rep = lambda a: a[:, None].expand(-1, 25).reshape(-1)
+    return r["MAINPIX"], pixels, nelectrons, rep(t0), rep(r["SL"]), currents_idx, pids_neigh, cin, r["Q"], t0
+
+
+class _FakeLut:
+    """larnd_lut_prepare reads only the LUT's shape (bins per axis for the argument check, Nt for the start tick, which
+    is not one of simulate_drift_new's outputs): a zero 3-template bank of the minimal size stands in when no response
+    is given."""
+    _cache = {}
+
+    def __init__(self, params, nt=1950):
+        need = int(params.nb_sampling_bins_per_pixel) * int(params.number_pix_neighbors) + int(params.nb_sampling_bins_per_pixel) // 2
+        need = max(need, 5)
+        key = (need, int(params.signal_length), nt, torch.cuda.current_device())
+        h = _FakeLut._cache.get(key)
+        if h is None:
+            h = _LutHandle(torch.zeros((3, need, need, nt), dtype=torch.float32, device="cuda"), int(params.signal_length))
+            _FakeLut._cache[key] = h
+        self.handle, self.shape = h.handle, h.shape
 
 
 def record_fields(st):

@@ -587,3 +587,43 @@ def test_mmd_kernel_matches_dense_evaluation(torch_dev):
     gx, gp = xt.grad.cpu().double(), pt.grad.cpu().double()
     assert (gx - xd.grad).abs().max() < 1e-4 * xd.grad.abs().max() + 1e-9
     assert (gp - pd.grad).abs().max() < 1e-4 * pd.grad.abs().max() + 1e-9
+
+
+def test_simulate_drift_new_view_and_mirror_helpers(torch_dev):
+    """The reference-shaped per-segment arrays rebuilt from the prepare kernel's records (sim.simulate_drift_new) and the
+    detsim mirror helpers (get_bin_shifts, get_pixels, density_2d, shift_tracks, generate_electrons) against the oracle."""
+    import torch
+    from larndsim_b200 import detsim, jrandom, sim
+    from oracle import jax_random as jr
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    tr = cm.small_batch(700, ibatch=1, pad=6, precision=0.01)
+    d = lo.simulate_drift_new(op, tr, cm.FIELDS)
+    t = torch.as_tensor(tr, device=torch_dev)
+    out = sim.simulate_drift_new(pp, t, cm.FIELDS)
+    names = ("main_pixels", "pixels", "nelectrons", "t0_after_diff", "long_diff", "currents_idx", "pIDs_neigh", "currents_idx_neigh",
+             "nelectrons_neigh", "t0_neigh")
+    for name, got in zip(names, out):
+        ref, g = d[name], got.cpu().numpy()
+        assert g.shape == ref.shape, name
+        if ref.dtype.kind in "iu":
+            assert np.array_equal(g, ref), name
+        else:
+            assert np.allclose(g, ref, rtol=3e-6, atol=1e-6 * np.abs(ref).max()), name
+    # helpers on the drifted tracks
+    drifted = torch.as_tensor(d["tracks"], device=torch_dev)
+    assert np.array_equal(detsim.get_bin_shifts(pp, drifted, cm.FIELDS).cpu().numpy(), d["bins_pitches"])
+    assert np.array_equal(detsim.get_pixels(pp, drifted, cm.FIELDS)[:, 2, 2].cpu().numpy(), d["main_pixels"])
+    edges = torch.as_tensor(oc.linspace_jnp(np.float32(-2 * op.pixel_pitch / 10), np.float32(3 * op.pixel_pitch / 10), 6), device=torch_dev)
+    w2d = detsim.density_2d(edges, torch.as_tensor(d["x0"], device=torch_dev), torch.as_tensor(d["y0"], device=torch_dev),
+                            torch.as_tensor(d["sigma_t"], device=torch_dev)).cpu().numpy()
+    ok = d["sigma_t"] > 0
+    assert np.abs(w2d[ok] - (d["wx"][:, :, None] * d["wy"][:, None, :])[ok]).max() < 1e-6
+    assert np.allclose(sim.shift_tracks(pp.replace(shift_x=0.3, shift_z=-0.2), t, cm.FIELDS).cpu().numpy(),
+                       lo.shift_tracks(op.replace(shift_x=0.3, shift_z=-0.2), tr, cm.FIELDS, np.float32))
+    k1 = jrandom.split(jrandom.key(5), 2)[0]
+    el = detsim.generate_electrons(drifted, cm.FIELDS, k1, apply_long_diffusion=False).cpu().numpy()
+    rnd = jr.normal(jr.split(jr.key(5), 2)[0], (len(tr), 3))
+    c = cm.FIELDS.index
+    assert np.allclose(el[:, c("x")], d["tracks"][:, c("x")] + rnd[:, 0] * d["tracks"][:, c("tran_diff")], atol=1e-5)
+    assert np.array_equal(el[:, c("z")], d["tracks"][:, c("z")])

@@ -259,3 +259,36 @@ def test_host_side_key_split_matches_the_jax_restatement(lib):
                 got = jrandom.split(jrandom.key(seed), num, part)
                 ref = [tuple(int(v) for v in k) for k in jr.split(jr.key(seed), num, part)]
                 assert got == ref, (seed, part, num)
+
+
+def test_event_id_validators_have_the_reference_error_behaviour():
+    """detsim validators (detsim_jax.py:26-152): ValueError below -1 / non-contiguous local ids, OverflowError beyond the
+    int64-safe packing limit, silent on empty or all-padding input; bin ids round-trip."""
+    import torch
+    from larndsim_b200 import detsim
+    p = cm.product_params()
+    detsim.validate_local_event_ids([])
+    detsim.validate_local_event_ids([-1, -1])
+    detsim.validate_local_event_ids([0, 1, -1, 2, 2])
+    with pytest.raises(ValueError):
+        detsim.validate_local_event_ids([0, 2])
+    with pytest.raises(ValueError):
+        detsim.validate_local_event_ids([-2, 0])
+    detsim.validate_event_ids_for_packing(p, np.array([0, 5, -1]), kind="pixel", context="t")
+    with pytest.raises(ValueError):
+        detsim.validate_event_ids_for_packing(p, [-3], kind="pixel")
+    with pytest.raises(ValueError):
+        detsim.validate_event_ids_for_packing(p, [1], kind="voxel")
+    lim = detsim.max_safe_event_id_for_pixel_packing(p)
+    assert lim == (np.iinfo(np.int64).max - (140 * 280 * 2 - 1)) // (140 * 280 * 2)
+    with pytest.raises(OverflowError):
+        detsim.validate_event_ids_for_packing(p, [lim + 1], kind="pixel")
+    assert detsim.max_possible_pixel_id(p, 3) == ((3 * 2 + 1) * 280 + 279) * 140 + 139
+    detsim.validate_packed_ids_for_decoding(p, [0, 78400 * 7 + 5, -1])
+    with pytest.raises(ValueError):
+        detsim.validate_packed_ids_for_decoding(p, [-5])
+    bx, by = torch.tensor([0, 1399, 17]), torch.tensor([2799, 0, 33])
+    pl, ev = torch.tensor([0, 1, 1]), torch.tensor([0, 3, 9])
+    bid = detsim.bin2id(p, bx, by, pl, ev)
+    assert [t.tolist() for t in detsim.id2bin(p, bid)] == [bx.tolist(), by.tolist(), pl.tolist(), ev.tolist()]
+    assert detsim.bin2id(p, torch.tensor([1400]), torch.tensor([0]), torch.tensor([0]), torch.tensor([0])).item() == -1
