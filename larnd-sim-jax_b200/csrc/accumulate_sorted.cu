@@ -112,6 +112,64 @@ __device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, fl
   }
 }
 
+// Consume loop of one unit: every run of `todo` gets its window computed from the register-resident response and flushed.
+// Two runs are in flight per iteration (independent FFMA chains hide the 4-cycle dependency latency) and the number of
+// impulse positions is a compile-time constant (uniform per tile: the class key contains the tick span).
+template <int NS, int NR, int NPOS>
+__device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
+                                              const float* __restrict__ hbuf, int hstride, const float* __restrict__ Ebuf,
+                                              float* __restrict__ row0, int mode /* 0 own row, 1 sum row -> row0, 2 own row and -row0 */,
+                                              int lane) {
+  while (todo) {
+    const int p0 = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const bool two = NR == 3 && todo != 0u;  // neighbour units (one template, dual flush) run one window at a time: measured faster
+    const int p1 = two ? __ffs(todo) - 1 : p0;
+    if (two) todo &= todo - 1;
+    const int r0 = __shfl_sync(0xffffffffu, row, p0), r1 = __shfl_sync(0xffffffffu, row, p1);
+    const int t0 = sm.run[p0].z, t1 = sm.run[p1].z;
+    const float* h0 = hbuf + p0 * hstride;
+    const float* h1 = hbuf + p1 * hstride;
+    float a0[NS], a1[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { a0[s] = 0.0f; a1[s] = 0.0f; }
+#pragma unroll
+    for (int j = 0; j < NPOS; ++j) {
+      float u[NR], v[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) { u[r] = h0[NR * j + r]; v[r] = h1[NR * j + r]; }
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          a0[s] = fmaf(u[r], Rw[r][s][j], a0[s]);
+          a1[s] = fmaf(v[r], Rw[r][s][j], a1[s]);
+        }
+    }
+    const float E0 = lane < ES ? Ebuf[p0 * ES + lane] : 0.0f;
+    const float E1 = lane < ES ? Ebuf[p1 * ES + lane] : 0.0f;
+    if (mode == 1) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, 1.0f);
+    else emit_window<NS>(a0, E0, A.wfs + (int64_t)r0 * A.nticks, t0, A.nticks, lane, 1.0f);
+    if (mode == 2) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, -1.0f);
+    if (two) {
+      if (mode == 1) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, 1.0f);
+      else emit_window<NS>(a1, E1, A.wfs + (int64_t)r1 * A.nticks, t1, A.nticks, lane, 1.0f);
+      if (mode == 2) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, -1.0f);
+    }
+  }
+}
+
+template <int NS, int NR>
+__device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
+                                                   const float* hbuf, int hstride, const float* Ebuf, float* row0, int mode, int lane, int npos) {
+  if (npos <= 3) {
+    if (npos == 2) consume_pairs<NS, NR, 2>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+    else consume_pairs<NS, NR, 3>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  } else if (npos == 4) consume_pairs<NS, NR, 4>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else if (npos == 5) consume_pairs<NS, NR, 5>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else consume_pairs<NS, NR, KPT>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+}
+
 template <int NS>
 __global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? 2 : 1)
 k_acc_tiles(const __grid_constant__ SortArgs A) {
@@ -164,6 +222,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
     const int4 ti = A.tile_info[tile];
     const int cls = ti.x, count = ti.z;
     const int cls_b = cls / (SPAN_MAX_S + 1);  // class = ((idx * nb + bxm) * nb + bym) * (SPAN_MAX_S + 1) + span
+    const int npos = cls % (SPAN_MAX_S + 1) + 2;  // impulse positions of every run of this tile
     const int bym = cls_b % nb, bxm = (cls_b / nb) % nb, idx = cls_b / (nb * nb);
     // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
     if (warp == 0) {
@@ -294,17 +353,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
                                       A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp};
         load_response<NS, 3>(Rw, rows, A.Lp, lane);
         // consume: lane <-> tick
-        for (int p = 0; p < count; ++p) {
-          const int rowp = __shfl_sync(0xffffffffu, row, p);
-          if (rowp < 0) continue;
-          const int4 e = sm.run[p];
-          float acc[NS];
-#pragma unroll
-          for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
-          conv<NS, 3>(acc, Rw, myh + p * HS, (e.y >> 16) + 2);
-          const float Ev = lane < ES ? myE[p * ES + lane] : 0.0f;
-          emit_window<NS>(acc, Ev, A.wfs + (int64_t)rowp * A.nticks, e.z, A.nticks, lane, 1.0f);
-        }
+        consume_pairs_npos<NS, 3>(A, sm, Rw, __ballot_sync(0xffffffffu, row >= 0), row, myh, HS, myE, row0, 0, lane, npos);
         __syncwarp();
       } else {
         // ---------------- neighbour pixels: template 0, full segment charge (sim_jax.py:197-225,250-261) ----------
@@ -368,20 +417,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         const float* const rows[1] = {rowp0};
         load_response<NS, 1>(Rw, rows, A.Lp, lane);
         const bool dual = !sum_unit && !A.skip_garbage;
-        while (owned) {
-          const int p = __ffs(owned) - 1;
-          owned &= owned - 1;
-          const int rowp = __shfl_sync(0xffffffffu, row, p);
-          const int4 e = sm.run[p];
-          float acc[NS];
-#pragma unroll
-          for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
-          conv<NS, 1>(acc, Rw, sm.hN[p], (e.y >> 16) + 2);
-          const float Ev = lane < ES ? myE[p * ES + lane] : 0.0f;
-          if (sum_unit) emit_window<NS>(acc, Ev, row0, e.z, A.nticks, lane, 1.0f);
-          else emit_window<NS>(acc, Ev, A.wfs + (int64_t)rowp * A.nticks, e.z, A.nticks, lane, 1.0f);
-          if (dual) emit_window<NS>(acc, Ev, row0, e.z, A.nticks, lane, -1.0f);
-        }
+        consume_pairs_npos<NS, 1>(A, sm, Rw, owned, row, &sm.hN[0][0], KPT, myE, row0, sum_unit ? 1 : (dual ? 2 : 0), lane, npos);
         __syncwarp();
       }
     }
