@@ -15,6 +15,7 @@
 // written as per-chunk partials and summed in double by a second tiny kernel (deterministic, no float atomics).
 #include <stdlib.h>
 
+#include "bwd_chain.cuh"
 #include "larnd_common.cuh"
 
 namespace {
@@ -226,21 +227,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
     }
   }
   // bin groups of the 5-wide diffusion stencil for every in-pixel bin index b (pure function of b and nb)
-  if (threadIdx.x < nb && threadIdx.x < 16) {
-    const int bq = threadIdx.x;
-    int ng = 0;
-    for (int i = 0; i < 5; ++i) {
-      int q = bq + i - 2, ox = 0;
-      if (q < 0) { q += nb; ox = -1; } else if (q >= nb) { q -= nb; ox = 1; }
-      const int ci = abs(2 * q - A.half2) >> 1;
-      int g = -1;
-      for (int k = 0; k < ng; ++k)
-        if (sm.g_ox[bq][k] == ox + 1 && sm.g_ci[bq][k] == ci) g = k;
-      if (g < 0) { g = ng++; sm.g_ox[bq][g] = ox + 1; sm.g_ci[bq][g] = ci; sm.g_mask[bq][g] = 0; }
-      sm.g_mask[bq][g] |= 1 << i;
-    }
-    sm.g_n[bq] = ng;
-  }
+  if (threadIdx.x < nb && threadIdx.x < 16) build_bin_groups(threadIdx.x, nb, A.half2, sm.g_n[threadIdx.x], sm.g_ox[threadIdx.x], sm.g_ci[threadIdx.x], sm.g_mask[threadIdx.x]);
   __syncthreads();
   // ---- runs: same key, start ticks within SPAN_MAX, at most 32 segments (one lane per segment) ---------------
   if (threadIdx.x == 0) {
@@ -478,73 +465,10 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
     }
     // ---- K1b: chain rule through the per-segment preparation, one lane per segment ---------------------------
     if (live) {
-      const int64_t s = s_base + tl;
-      const int flags = sm.flags[tl];
-      const float sl = A.rec[(int64_t)LARND_F_SL * n + s];
-      const float sT = A.rec[(int64_t)LARND_F_ST * n + s];
-      const float td = A.rec[(int64_t)LARND_F_TD * n + s];
-      const float x0 = A.rec[(int64_t)LARND_F_X0 * n + s], y0 = A.rec[(int64_t)LARND_F_Y0 * n + s];
-      const float recb = A.rec[(int64_t)LARND_F_REC * n + s];
-      const float ft = A.rec[(int64_t)LARND_F_FT * n + s];
-      const float xi = A.rec[(int64_t)LARND_F_XI * n + s];
-      const float cos2 = A.rec[(int64_t)LARND_F_COS2 * n + s];
-      // Lagrange weights (sim_jax.py:165-168)
-      const float t0v = p.long_diff_template[idx - 1], t1v = p.long_diff_template[idx], t2v = p.long_diff_template[idx + 1];
-      const float das = ((sl - t1v) + (sl - t2v)) / ((t0v - t1v) * (t0v - t2v));
-      const float dbs = ((sl - t0v) + (sl - t2v)) / ((t1v - t0v) * (t1v - t2v));
-      const float dcs = ((sl - t0v) + (sl - t1v)) / ((t2v - t0v) * (t2v - t1v));
-      const float g_sl = da * das + db * dbs + dc * dcs;
-      // diffusion weights W_k = 0.5 (E_{k+1} - E_k), E_k = erf((edge_k - x0)/(sqrt2 sT)) for k = 1..4
-      float g_x0 = 0.f, g_y0 = 0.f, g_sT = 0.f;
-      if (sT > 0.0f) {
-        const float inv = 1.0f / (1.41421354f * sT);
-        const float two_over_sqrt_pi = 1.12837917f;
+      float dwx[5], dwy[5];
 #pragma unroll
-        for (int k = 1; k < 5; ++k) {
-          const float ux = (p.tran_bin_edges[k] - x0) * inv, uy = (p.tran_bin_edges[k] - y0) * inv;
-          const float px_ = two_over_sqrt_pi * expf(-ux * ux), py_ = two_over_sqrt_pi * expf(-uy * uy);
-          const float gEx = 0.5f * (sm.dwx[wid][k - 1][lane] - sm.dwx[wid][k][lane]);
-          const float gEy = 0.5f * (sm.dwy[wid][k - 1][lane] - sm.dwy[wid][k][lane]);
-          g_x0 += gEx * (-px_ * inv);
-          g_y0 += gEy * (-py_ * inv);
-          g_sT += gEx * (-px_ * ux / sT) + gEy * (-py_ * uy / sT);
-        }
-      }
-      const float v = p.vdrift, tau = p.lifetime, ts = p.t_sampling;
-      const float sgn_a = (flags & 2) ? 1.0f : -1.0f, sgn_c = (flags & 4) ? 1.0f : -1.0f;
-      const float g_ft = df;
-      const float g_td = dq * (-q / tau) + (td > 0.f ? (g_sl * sl + g_sT * sT) / (2.0f * td) : 0.f);
-      const float g_v = g_td * (-td / v) + g_ft * (-ft / v) + g_sl * (-sl / v);
-      GACC(LARND_P_SHIFT_Z) += g_td * (-sgn_a / v) + g_ft * (-sgn_c / (v * ts));
-      GACC(LARND_P_LIFETIME) += dq * q * td / (tau * tau);
-      if (p.long_diff > 0.f) GACC(LARND_P_LONG_DIFF) += g_sl * sl / (2.0f * p.long_diff);
-      if (p.tran_diff > 0.f) GACC(LARND_P_TRAN_DIFF) += g_sT * sT / (2.0f * p.tran_diff);
-      GACC(LARND_P_SHIFT_X) += -g_x0;
-      GACC(LARND_P_SHIFT_Y) += -g_y0;
-      GACC(LARND_P_MEV_TO_ELECTRONS) += dq * q / p.MeVToElectrons;
-      float g_rec = (recb != 0.0f) ? dq * q / recb : 0.0f;  // q is linear in the recombination factor
-      float g_E = g_v * p.dvdrift_dEfield;
-      if (p.recombination_mode == 2) {          // Birks: rec = Ab / (1 + xi), xi = kb dEdx / (E rho)
-        const float dn = 1.0f + xi;
-        GACC(LARND_P_AB) += g_rec * recb / p.Ab;
-        const float g_xi = g_rec * (-recb / dn);
-        if (p.kb != 0.f) GACC(LARND_P_KB) += g_xi * xi / p.kb;
-        g_E += g_xi * (-xi / p.eField);
-        GACC(LARND_P_LAR_DENSITY) += g_xi * (-xi / p.lArDensity);
-      } else if (recb > 0.0f) {                 // Box / Ellipsoid: rec = log(alpha + xi) / (xi [+1e-10])
-        const float den = (p.recombination_mode == 3) ? xi + 1e-10f : xi;
-        const float lg = logf(p.alpha + xi);
-        GACC(LARND_P_ALPHA) += g_rec / ((p.alpha + xi) * den);
-        const float g_xi = g_rec * (1.0f / ((p.alpha + xi) * den) - lg / (den * den));
-        GACC(LARND_P_BETA) += g_xi * xi / p.beta;
-        g_E += g_xi * (-xi / p.eField);
-        GACC(LARND_P_LAR_DENSITY) += g_xi * (-xi / p.lArDensity);
-        if (p.recombination_mode == 3) {
-          const float gg = 1.0f - cos2 + p.inv_R2 * cos2;   // b_phi = beta / sqrt(gg)
-          GACC(LARND_P_R_PARAM) += g_xi * xi * cos2 / (p.R_param * p.R_param * p.R_param * gg);
-        }
-      }
-      GACC(LARND_P_EFIELD) += g_E;
+      for (int k = 0; k < 5; ++k) { dwx[k] = sm.dwx[wid][k][lane]; dwy[k] = sm.dwy[wid][k][lane]; }
+      chain_rule_segment(p, A.rec, n, s_base + tl, idx, q, dq, df, da, db, dc, dwx, dwy, [&](int k, float v) { GACC(k) += v; });
     }
     __syncwarp();
   }

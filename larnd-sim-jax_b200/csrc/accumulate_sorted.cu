@@ -184,21 +184,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
   lk.n_unique = A.counts[0];
   lk.n_neg = A.counts[1];
   // merged transverse-diffusion groups per in-pixel bin (same tables as accumulate.cu)
-  if (threadIdx.x < nb && threadIdx.x < 16) {
-    const int bq = threadIdx.x;
-    int ng = 0;
-    for (int i = 0; i < LARND_NB_TRAN_BINS; ++i) {
-      int qb = bq + i - (LARND_NB_TRAN_BINS - 1) / 2, ox = 0;
-      if (qb < 0) { qb += nb; ox = -1; } else if (qb >= nb) { qb -= nb; ox = 1; }
-      const int ci = abs(2 * qb - A.half2) >> 1;
-      int g = -1;
-      for (int k = 0; k < ng; ++k)
-        if (sm.g_ox[bq][k] == ox + 1 && sm.g_ci[bq][k] == ci) g = k;
-      if (g < 0) { g = ng++; sm.g_ox[bq][g] = ox + 1; sm.g_ci[bq][g] = ci; sm.g_mask[bq][g] = 0; }
-      sm.g_mask[bq][g] |= 1 << i;
-    }
-    sm.g_n[bq] = ng;
-  }
+  if (threadIdx.x < nb && threadIdx.x < 16) build_bin_groups(threadIdx.x, nb, A.half2, sm.g_n[threadIdx.x], sm.g_ox[threadIdx.x], sm.g_ci[threadIdx.x], sm.g_mask[threadIdx.x]);
   for (int u = threadIdx.x; u < A.P * A.P; u += TILE_THREADS) {
     sm.udx[u] = (signed char)(u / A.P - A.n_neigh);
     sm.udy[u] = (signed char)(u % A.P - A.n_neigh);

@@ -93,6 +93,25 @@ __device__ __forceinline__ int floordiv_i(int a, int b) {  // python-style floor
 // at the LOW end are handled there too: garbage column 0); the rest goes through accumulate.cu's per-segment path.
 __device__ __forceinline__ bool seg_is_fast(int T0, int L, int nticks) { return T0 + L <= nticks - 2; }
 
+// The 5-wide transverse-diffusion stencil around in-pixel bin bq touches bins bq-2 .. bq+2; bins that fall on the same
+// pixel (offset -1 / 0 / +1) with the same response row (|distance to the pixel centre|) are merged into *groups*.
+// Fills, for one bq: number of groups, and per group pixel offset + 1, response index, member mask (bit i = stencil bin i).
+__device__ __forceinline__ void build_bin_groups(int bq, int nb, int half2, unsigned char& g_n, unsigned char (&g_ox)[5],
+                                                 unsigned char (&g_ci)[5], unsigned char (&g_mask)[5]) {
+  int ng = 0;
+  for (int i = 0; i < LARND_NB_TRAN_BINS; ++i) {
+    int qb = bq + i - (LARND_NB_TRAN_BINS - 1) / 2, ox = 0;
+    if (qb < 0) { qb += nb; ox = -1; } else if (qb >= nb) { qb -= nb; ox = 1; }
+    const int ci = abs(2 * qb - half2) >> 1;
+    int g = -1;
+    for (int k = 0; k < ng; ++k)
+      if (g_ox[k] == ox + 1 && g_ci[k] == ci) g = k;
+    if (g < 0) { g = ng++; g_ox[g] = ox + 1; g_ci[g] = ci; g_mask[g] = 0; }
+    g_mask[g] |= 1 << i;
+  }
+  g_n = ng;
+}
+
 // pixel2id with int32 wrap-around (detsim_jax.py:232-244; x64 is never enabled in the reference)
 __device__ __forceinline__ int pixel2id_dev(int px, int py, int ep, int nx, int ny) {
   if (px >= nx || py >= ny || px < 0 || py < 0) return -1;

@@ -82,7 +82,7 @@ def nvcc_command(out=LIB_PATH, extra=()):
 def build_library(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into liblarnd_b200.so (in-tree, next to this file)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(CSRC, "sorted_runs.cuh"), os.path.join(CSRC, "segment_physics.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(CSRC, "sorted_runs.cuh"), os.path.join(CSRC, "bwd_chain.cuh"), os.path.join(CSRC, "segment_physics.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = nvcc_command()
