@@ -37,6 +37,14 @@ struct BwdSortArgs {
   const int* garbage_grad_nonzero;
 };
 
+constexpr int BSLOTS = 32 / MAXLEN;  // runs whose segments are processed together (lanes <-> (slot, segment))
+struct PairSlots {
+  float G[BSLOTS][GSB];        // G[NR*j + r] of the run parked in the slot
+  float gpos[BSLOTS][KPT + 2]; // upstream gradient at ticks tmin - 1 + j
+  float ca[BSLOTS][KPT + 2], cb[BSLOTS][KPT + 2];  // running sums of the response at ct(tmin + j), ct + 1
+  int p[BSLOTS];
+};
+
 struct BwdTileSmem {
   int4 run[TR];
   int ep[TR], mpx[TR], mpy[TR], soff[TR];
@@ -45,7 +53,7 @@ struct BwdTileSmem {
   int m[SEGMAX_B], sid[SEGMAX_B];            // T0 - tmin (INT32_MIN: outside every TPC, no gradient), global segment index
   unsigned char owner[SEGMAX_B];
   float acc[NACC][SEGMAX_B];
-  float Gs[BT_WARPS][GSB];
+  PairSlots ps[BT_WARPS];
   float gl[LARND_NPARAMS][BT_THREADS];       // per-thread parameter-gradient accumulators (kept out of the register file)
   float red[BT_WARPS][16];
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
@@ -88,84 +96,95 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   const SortArgs& S = A.S;
   const int nt = S.nt, L = S.L, nticks = S.nticks;
   const float Cl = __ldg(crow + nt - L);
-  float* Gs = sm.Gs[warp];
+  PairSlots& ps = sm.ps[warp];
   while (todo) {
-    const int p = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int rowp = __shfl_sync(0xffffffffu, row, p);
-    const int4 e = sm.run[p];
-    const int len = e.y & 0xffff, tmin = e.z;
-    const float* grow = A.g + (int64_t)rowp * A.g_stride;
-    // upstream-gradient window (coalesced) and the running sums at the run's tick positions: all loads first
-    float graw[NS];
-    const bool inside = tmin >= 2 && tmin - 2 + 32 * NS < nticks;  // warp-uniform, the common case: whole window inside the row
-    if (inside) {
-      const float* gp = grow + (tmin - 1 + lane);
+    // ---- up to 4 runs: correlate, reduce, park the results in the warp's slots -------------------------------------
+    int nslot = 0;
+#pragma unroll 1
+    for (; nslot < BSLOTS && todo; ++nslot) {
+      const int p = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int rowp = __shfl_sync(0xffffffffu, row, p);
+      const int tmin = sm.run[p].z;
+      const float* grow = A.g + (int64_t)rowp * A.g_stride;
+      // upstream-gradient window (coalesced) and the running sums at the run's tick positions: all loads first
+      float graw[NS];
+      const bool inside = tmin >= 2 && tmin - 2 + 32 * NS < nticks;  // warp-uniform, the common case: whole window inside the row
+      if (inside) {
+        const float* gp = grow + (tmin - 1 + lane);
 #pragma unroll
-      for (int s = 0; s < NS; ++s) graw[s] = __ldg(gp + 32 * s);
-    } else {
+        for (int s = 0; s < NS; ++s) graw[s] = __ldg(gp + 32 * s);
+      } else {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const int col = tmin - 1 + 32 * s + lane;
+          graw[s] = (col >= 1 && col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
+        }
+      }
+      int ctl = nt - L - (tmin + lane);
+      ctl = max(0, min(ctl, nt - 1));
+      if (lane <= KPT) {  // lane j <-> position j: gradient at tick tmin - 1 + j, running sums at ct(tmin + j)
+        ps.gpos[nslot][lane] = graw[0];
+        ps.ca[nslot][lane] = __ldg(crow + ctl);
+        ps.cb[nslot][lane] = __ldg(crow + min(ctl + 1, nt - 1));
+      }
+      if (lane == 0) ps.p[nslot] = p;
+      float part[NR * NPOS];
+#pragma unroll
+      for (int k = 0; k < NR * NPOS; ++k) part[k] = 0.0f;
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        const int col = tmin - 1 + 32 * s + lane;
-        graw[s] = (col >= 1 && col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
+        // window samples live on ticks >= 2, corrections on >= 1 (only differs for runs at the low end of the readout)
+        const float gv = (inside || tmin - 1 + 32 * s + lane >= 2) ? graw[s] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPOS; ++j)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) part[NR * j + r] = fmaf(gv, Rw[r][s][j], part[NR * j + r]);
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < NR * NPOS; c0 += 8) {
+        float v8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v8[k] = (c0 + k < NR * NPOS) ? part[(c0 + k < NR * NPOS) ? c0 + k : 0] : 0.0f;
+        const float tot = reduce8_to_lane_s(v8, lane);
+        if (lane < 8) ps.G[nslot][c0 + lane] = tot;  // G[NR*j + r]
       }
     }
-    int ctl = nt - L - (tmin + lane);
-    ctl = max(0, min(ctl, nt - 1));
-    const float CaPos = __ldg(crow + ctl), CbPos = __ldg(crow + min(ctl + 1, nt - 1));  // lane j <-> position j
-    float part[NR * NPOS];
-#pragma unroll
-    for (int k = 0; k < NR * NPOS; ++k) part[k] = 0.0f;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      // window samples live on ticks >= 2, corrections on >= 1 (only differs for runs at the low end of the readout)
-      const float gv = (inside || tmin - 1 + 32 * s + lane >= 2) ? graw[s] : 0.0f;
-#pragma unroll
-      for (int j = 0; j < NPOS; ++j)
-#pragma unroll
-        for (int r = 0; r < NR; ++r) part[NR * j + r] = fmaf(gv, Rw[r][s][j], part[NR * j + r]);
-    }
     __syncwarp();
-#pragma unroll
-    for (int c0 = 0; c0 < NR * NPOS; c0 += 8) {
-      float v8[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v8[k] = (c0 + k < NR * NPOS) ? part[(c0 + k < NR * NPOS) ? c0 + k : 0] : 0.0f;
-      const float tot = reduce8_to_lane_s(v8, lane);
-      if (lane < 8) Gs[c0 + lane] = tot;  // G[NR*j + r]
-    }
-    __syncwarp();
-    // lanes <-> segments of the run
-    const int i = sm.soff[p] + min(lane, len - 1);
-    const int m = sm.m[i];
-    const bool live = lane < len && m != INT32_MIN;
-    const int ms = live ? m : 0;
-    const float gB = __shfl_sync(0xffffffffu, graw[0], ms);        // tick T0 - 1 = tmin - 1 + m
-    const float gA = __shfl_sync(0xffffffffu, graw[0], ms + 1);    // tick T0
-    const float Ca = __shfl_sync(0xffffffffu, CaPos, ms), Cb = __shfl_sync(0xffffffffu, CbPos, ms);
-    if (live) {
-      const float q = sm.q[i], f = sm.f[i], omf = 1.0f - f;
-      const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
-      const float gm = fmaf(f, gB, omf * gA);
-      if (NR == 3) {
-        const float a0 = Gs[3 * m], b0 = Gs[3 * m + 1], c0v = Gs[3 * m + 2], a1 = Gs[3 * m + 3], b1 = Gs[3 * m + 4], c1v = Gs[3 * m + 5];
-        const float ca_ = sm.ca[i], cb_ = sm.cb[i], cc_ = sm.cc[i];
-        const float gwx = sm.wxg[gi][i], gwy = sm.wyg[gj][i];
-        const float Sa = fmaf(f, a0, omf * a1), Sb = fmaf(f, b0, omf * b1), Sc = fmaf(f, c0v, omf * c1v);
-        const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
-        const float Fd = fmaf(ca_, a0 - a1, fmaf(cb_, b0 - b1, cc_ * (c0v - c1v))) + (gB - gA) * D + gm * dD;
-        const float w = gwx * gwy, qb = w * q;
-        atomicAdd(&sm.acc[0][i], w * Pv);
-        atomicAdd(&sm.acc[1][i], qb * Fd);
-        atomicAdd(&sm.acc[2][i], qb * Sa);
-        atomicAdd(&sm.acc[3][i], qb * Sb);
-        atomicAdd(&sm.acc[4][i], qb * Sc);
-        atomicAdd(&sm.acc[5 + gi][i], gwy * q * Pv);   // d/dWx_k for every member k of group gi
-        atomicAdd(&sm.acc[10 + gj][i], gwx * q * Pv);
-      } else {
-        const float G0 = Gs[m], G1 = Gs[m + 1];
-        atomicAdd(&sm.acc[0][i], fmaf(f, G0, omf * G1) + gm * D);
-        atomicAdd(&sm.acc[1][i], q * ((G0 - G1) + (gB - gA) * D + gm * dD));
+    // ---- lanes <-> (slot, segment): 4 runs x up to 8 segments in one pass --------------------------------------------
+    const int slot = lane >> 3, t = lane & 7;
+    if (slot < nslot) {
+      const int p = ps.p[slot];
+      const int len = sm.run[p].y & 0xffff;
+      const int i = sm.soff[p] + t;
+      const int m = t < len ? sm.m[i] : INT32_MIN;
+      if (m != INT32_MIN) {
+        const float* Gs = ps.G[slot];
+        const float gB = ps.gpos[slot][m], gA = ps.gpos[slot][m + 1];   // ticks T0 - 1 and T0
+        const float Ca = ps.ca[slot][m], Cb = ps.cb[slot][m];
+        const float q = sm.q[i], f = sm.f[i], omf = 1.0f - f;
+        const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
+        const float gm = fmaf(f, gB, omf * gA);
+        if (NR == 3) {
+          const float a0 = Gs[3 * m], b0 = Gs[3 * m + 1], c0v = Gs[3 * m + 2], a1 = Gs[3 * m + 3], b1 = Gs[3 * m + 4], c1v = Gs[3 * m + 5];
+          const float ca_ = sm.ca[i], cb_ = sm.cb[i], cc_ = sm.cc[i];
+          const float gwx = sm.wxg[gi][i], gwy = sm.wyg[gj][i];
+          const float Sa = fmaf(f, a0, omf * a1), Sb = fmaf(f, b0, omf * b1), Sc = fmaf(f, c0v, omf * c1v);
+          const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
+          const float Fd = fmaf(ca_, a0 - a1, fmaf(cb_, b0 - b1, cc_ * (c0v - c1v))) + (gB - gA) * D + gm * dD;
+          const float w = gwx * gwy, qb = w * q;
+          atomicAdd(&sm.acc[0][i], w * Pv);
+          atomicAdd(&sm.acc[1][i], qb * Fd);
+          atomicAdd(&sm.acc[2][i], qb * Sa);
+          atomicAdd(&sm.acc[3][i], qb * Sb);
+          atomicAdd(&sm.acc[4][i], qb * Sc);
+          atomicAdd(&sm.acc[5 + gi][i], gwy * q * Pv);   // d/dWx_k for every member k of group gi
+          atomicAdd(&sm.acc[10 + gj][i], gwx * q * Pv);
+        } else {
+          const float G0 = Gs[m], G1 = Gs[m + 1];
+          atomicAdd(&sm.acc[0][i], fmaf(f, G0, omf * G1) + gm * D);
+          atomicAdd(&sm.acc[1][i], q * ((G0 - G1) + (gB - gA) * D + gm * dD));
+        }
       }
     }
     __syncwarp();
