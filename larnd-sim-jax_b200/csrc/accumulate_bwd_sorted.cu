@@ -100,7 +100,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   while (todo) {
     // ---- up to 4 runs: correlate, reduce, park the results in the warp's slots -------------------------------------
     int nslot = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (; nslot < BSLOTS && todo; ++nslot) {
       const int p = __ffs(todo) - 1;
       todo &= todo - 1;
