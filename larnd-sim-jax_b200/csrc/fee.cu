@@ -39,10 +39,23 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   float* c = smem + (size_t)wid * Nt;
   const float* w = F.wfs + (int64_t)row * F.stride;
   int t_first = Nt, t_last = -1;  // first / last tick with a non-zero sample
-  for (int t = lane; t < Nt; t += 32) {
-    const float qv = __fmul_rn(w[t], p.t_sampling);  // q = wfs * t_sampling
-    c[t] = qv;
-    if (qv != 0.0f) { t_first = min(t_first, t); t_last = t; }
+  // the row is streamed from HBM: 8 coalesced 128-byte loads in flight per warp (one at a time leaves the kernel latency-bound)
+  for (int t0 = 0; t0 < Nt; t0 += 256) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = t0 + 32 * k + lane;
+      v[k] = t < Nt ? __ldg(w + t) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = t0 + 32 * k + lane;
+      if (t < Nt) {
+        const float qv = __fmul_rn(v[k], p.t_sampling);  // q = wfs * t_sampling
+        c[t] = qv;
+        if (qv != 0.0f) { t_first = min(t_first, t); t_last = t; }
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
