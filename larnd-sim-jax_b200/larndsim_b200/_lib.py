@@ -80,19 +80,36 @@ def nvcc_command(out=LIB_PATH, extra=()):
 
 
 def build_library(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into liblarnd_b200.so (in-tree, next to this file)."""
+    """Compile every CUDA source for sm_100a into liblarnd_b200.so (in-tree, next to this file).  Safe to call from
+    several processes at once (torchrun ranks): the build runs under an exclusive file lock and writes to a temporary
+    name that is renamed into place."""
+    import fcntl
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(CSRC, "sorted_runs.cuh"), os.path.join(CSRC, "bwd_chain.cuh"), os.path.join(CSRC, "segment_physics.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(CSRC, "sorted_runs.cuh"), os.path.join(CSRC, "bwd_chain.cuh"),
+                   os.path.join(CSRC, "segment_physics.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
+
+    def fresh():
+        return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)
+
+    if not force and fresh():
         return LIB_PATH
-    cmd = nvcc_command()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        print(" ".join(cmd))
-        print(res.stdout)
-        print(res.stderr)
-    if res.returncode != 0:
-        raise LarndError("nvcc failed:\n" + res.stderr)
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():  # another process built it while we waited
+                return LIB_PATH
+            tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+            cmd = nvcc_command(out=tmp)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                print(" ".join(cmd))
+                print(res.stdout)
+                print(res.stderr)
+            if res.returncode != 0:
+                raise LarndError("nvcc failed:\n" + res.stderr)
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
