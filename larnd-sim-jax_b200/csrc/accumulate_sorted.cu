@@ -88,15 +88,24 @@ __device__ __forceinline__ void conv(float (&acc)[NS], const float (&Rw)[3][NS][
 // >= 2, corrections on columns >= 1; what falls below goes to the garbage column 0 (sim_jax.py:177-178,243-244).
 template <int NS>
 __device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, float* rowbase, int tmin, int nticks, int lane,
-                                            float sign, const bool (&act)[NS]) {
+                                            float sign, const bool (&act)[NS], bool last_partial) {
   if (tmin >= 2 && tmin - 2 + 32 * NS < nticks) {  // warp-uniform, the common case: whole register window inside the row
     float* dst = rowbase + (tmin - 1) + lane;
     // act[s] = this lane's tick of slot s lies inside the run window (L + 2 + span ticks, the same for every run of the
     // tile): hoisted predicates instead of a zero test per slot; zero-valued adds inside the window are harmless
-    if (act[0]) atomicAdd(dst, sign * (acc[0] + Ev));  // RED.E.ADD.F32, coalesced
+    if (last_partial) {
+      // the usual shape (the window ends inside the last slot): every lane of the other slots is active, so they need no
+      // predicate -- ptxas wraps every predicated reduction in BSSY / BRA / BSYNC
+      atomicAdd(dst, sign * (acc[0] + Ev));  // RED.E.ADD.F32, coalesced
 #pragma unroll
-    for (int s = 1; s < NS; ++s)
-      if (act[s]) atomicAdd(dst + 32 * s, sign * acc[s]);
+      for (int s = 1; s < NS - 1; ++s) atomicAdd(dst + 32 * s, sign * acc[s]);
+      if (act[NS - 1]) atomicAdd(dst + 32 * (NS - 1), sign * acc[NS - 1]);
+    } else {
+      if (act[0]) atomicAdd(dst, sign * (acc[0] + Ev));
+#pragma unroll
+      for (int s = 1; s < NS; ++s)
+        if (act[s]) atomicAdd(dst + 32 * s, sign * acc[s]);
+    }
   } else {
     float g = 0.0f;
 #pragma unroll
@@ -124,6 +133,7 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
   bool act[NS];  // window length of every run of the tile: L + 2 + span = L + NPOS ticks
 #pragma unroll
   for (int s = 0; s < NS; ++s) act[s] = 32 * s + lane < A.L + NPOS;
+  const bool lp = NS > 1 && A.L + NPOS >= 32 * (NS - 1) && A.L + NPOS < 32 * NS;  // warp-uniform, loop-invariant
   while (todo) {
     const int p0 = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -152,13 +162,13 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
     }
     const float E0 = lane < ES ? Ebuf[p0 * ES + lane] : 0.0f;
     const float E1 = lane < ES ? Ebuf[p1 * ES + lane] : 0.0f;
-    if (mode == 1) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, 1.0f, act);
-    else emit_window<NS>(a0, E0, A.wfs + (int64_t)r0 * A.nticks, t0, A.nticks, lane, 1.0f, act);
-    if (mode == 2) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, -1.0f, act);
+    if (mode == 1) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, 1.0f, act, lp);
+    else emit_window<NS>(a0, E0, A.wfs + (int64_t)r0 * A.nticks, t0, A.nticks, lane, 1.0f, act, lp);
+    if (mode == 2) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, -1.0f, act, lp);
     if (two) {
-      if (mode == 1) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, 1.0f, act);
-      else emit_window<NS>(a1, E1, A.wfs + (int64_t)r1 * A.nticks, t1, A.nticks, lane, 1.0f, act);
-      if (mode == 2) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, -1.0f, act);
+      if (mode == 1) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, 1.0f, act, lp);
+      else emit_window<NS>(a1, E1, A.wfs + (int64_t)r1 * A.nticks, t1, A.nticks, lane, 1.0f, act, lp);
+      if (mode == 2) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, -1.0f, act, lp);
     }
   }
 }

@@ -269,39 +269,72 @@ __global__ void k_compact_hits(const __grid_constant__ CompactArgs C) {
 // at step k was never clamped, so the adjoint of c^0 is supported on the <= 20 positions {e_k, e2_k}:
 //   T_k = g_k*hit_k + Sbar_k*[S_k > 0],   Sbar_k = -sum_{k' > k} T_k',
 //   cbar[e_k] += g_k*hit_k,  cbar[e2_k] += Sbar_k*[S_k > 0],   g_wfs[t] = t_sampling * sum_{t' >= t} cbar[t'].
+// The <= 20 positions are ascending in k (hit k+1 is found after the subtraction tick of hit k), so g_wfs is a step
+// function of t: on (pos[m-1], pos[m]] it equals t_sampling * (val[m] + val[m+1] + ...).  One warp per row: every lane
+// replays the ten-step recursion in registers, lane l keeps entry l, the suffix sums are formed in the same order as
+// the plain sum over k (bit-identical to it), and the warp writes the row range by range -- no per-tick loop over the
+// list.  Rows whose list is not ascending (never seen) take the plain sum.
 __global__ void __launch_bounds__(128)
 k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved, int npix, int ntw,
                const __grid_constant__ larnd_params_t p, float* __restrict__ g_wfs, int64_t g_stride) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= npix) return;
-  const int nmax = p.max_adc_values;
+  const int nmax = p.max_adc_values, nent = 2 * nmax;
   const float* sv = saved + (int64_t)row * 32;
   const unsigned hit_mask = (unsigned)__float_as_int(sv[10]);
   const unsigned spos_mask = (unsigned)__float_as_int(sv[11]);
   const unsigned slope_mask = (unsigned)__float_as_int(sv[12]);
   const float slope = p.gain * p.adc_counts / p.v_ref_minus_cm;
-  int pos[2 * LARND_MAX_ADC];
-  float val[2 * LARND_MAX_ADC];
-  float tail = 0.0f;  // sum_{k' > k} T_k'
-  for (int k = nmax - 1; k >= 0; --k) {
-    const int idx_t = (int)sv[k];
-    int e = idx_t + 1 + p.hold_interval; if (e >= ntw) e = ntw - 1;
-    int e2 = idx_t + 2 + p.hold_interval; if (e2 >= ntw) e2 = ntw - 1;
-    const float gk = ((hit_mask >> k) & 1u) && ((slope_mask >> k) & 1u) ? g_adc[(int64_t)row * nmax + k] * slope : 0.0f;
-    const float sbar = ((spos_mask >> k) & 1u) ? -tail : 0.0f;
-    pos[2 * k] = e; val[2 * k] = gk;
-    pos[2 * k + 1] = e2; val[2 * k + 1] = sbar;
-    tail += gk + sbar;
-  }
   float* out = g_wfs + (int64_t)row * g_stride;
-  const bool any = hit_mask != 0;
-  for (int t = lane; t < ntw; t += 32) {
-    float s = 0.0f;
-    if (any) {
-      for (int k = 0; k < 2 * nmax; ++k) s += (pos[k] >= t) ? val[k] : 0.0f;
+  if (hit_mask == 0u) {  // no hit: zero gradient
+    for (int t = lane; t < ntw; t += 32) out[t] = 0.0f;
+    return;
+  }
+  int mypos = -1;       // entry 2k: sampling tick e_k, entry 2k+1: subtraction tick e2_k
+  float myval = 0.0f;
+  float tail = 0.0f;    // sum_{k' > k} T_k'
+#pragma unroll
+  for (int k = LARND_MAX_ADC - 1; k >= 0; --k) {
+    if (k < nmax) {
+      const int idx_t = (int)sv[k];
+      int e = idx_t + 1 + p.hold_interval; if (e >= ntw) e = ntw - 1;
+      int e2 = idx_t + 2 + p.hold_interval; if (e2 >= ntw) e2 = ntw - 1;
+      const float gk = ((hit_mask >> k) & 1u) && ((slope_mask >> k) & 1u) ? g_adc[(int64_t)row * nmax + k] * slope : 0.0f;
+      const float sbar = ((spos_mask >> k) & 1u) ? -tail : 0.0f;
+      if (lane == 2 * k) { mypos = e; myval = gk; }
+      if (lane == 2 * k + 1) { mypos = e2; myval = sbar; }
+      tail += gk + sbar;
     }
-    out[t] = s * p.t_sampling;
+  }
+  const int nextpos = __shfl_down_sync(0xffffffffu, mypos, 1);
+  const bool ascending = __all_sync(0xffffffffu, lane >= nent - 1 || mypos <= nextpos);
+  if (ascending) {
+    float S = 0.0f;  // lane l: val[l] + val[l+1] + ... in ascending k, like the plain sum with its leading zeros
+#pragma unroll
+    for (int k = 0; k < 2 * LARND_MAX_ADC; ++k) {
+      const float v = __shfl_sync(0xffffffffu, myval, k);
+      if (k >= lane && k < nent) S += v;
+    }
+    int prev = -1;
+    for (int m = 0; m < nent; ++m) {
+      const int pm = __shfl_sync(0xffffffffu, mypos, m);
+      const float sm = __shfl_sync(0xffffffffu, S, m) * p.t_sampling;
+      for (int t = prev + 1 + lane; t <= pm; t += 32) out[t] = sm;
+      prev = max(prev, pm);
+    }
+    for (int t = prev + 1 + lane; t < ntw; t += 32) out[t] = 0.0f;
+  } else {
+    for (int t = lane; t < ntw; t += 32) {
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 2 * LARND_MAX_ADC; ++k) {
+        const int pk = __shfl_sync(0xffffffffu, mypos, k);
+        const float vk = __shfl_sync(0xffffffffu, myval, k);
+        if (k < nent) s += (pk >= t) ? vk : 0.0f;
+      }
+      out[t] = s * p.t_sampling;
+    }
   }
 }
 
