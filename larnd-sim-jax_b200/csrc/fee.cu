@@ -77,8 +77,13 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
     total = acc;
   }
   total = __shfl_sync(0xffffffffu, total, 0);
-  for (int t = max(t_last + 1, 0) + lane; t < Nt; t += 32) c[t] = total;
   __syncwarp();
+  // Outside [lo, hi] the running sum is constant (0 before the first non-zero sample, the total after the last one) and
+  // stays constant under the subtract-and-clamp of every pass: those two regions are carried as the scalars hv / tv and
+  // only the window is kept in shared memory and walked by the ten passes (~150 ticks of 2000 on a track's pixel).
+  const int lo = min(t_first, Nt), hi = t_last;  // empty row: lo = Nt, hi = -1
+  float hv = 0.0f, tv = total;
+  auto cget = [&](int t) { return t < lo ? hv : (t > hi ? tv : c[t]); };
   const float thr = p.discrimination_threshold;
   const int interval = p.hold_interval;
   const int nmax = p.max_adc_values;
@@ -103,19 +108,25 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   for (int it = 0; it < nmax; ++it) {
     // first t with q_sum[t] <= thr <= q_sum[t+1] (fee_jax.py:200-203); fill value Nt-2
     int idx_t = Nt - 2;
-    for (int t0 = 0; t0 < Nt - 1; t0 += 32) {
-      int t = t0 + lane;
-      bool hit = false;
-      if (t < Nt - 1) {
-        float a = __fadd_rn(base, c[t]), b = __fadd_rn(base, c[t + 1]);
-        hit = (b >= thr) && (a <= thr);
+    bool found = false;
+    if (lo >= 2 && __fadd_rn(base, hv) == thr) { idx_t = 0; found = true; }  // both samples in the constant head
+    if (!found) {
+      const int t_end = min(hi, Nt - 2);  // pairs (t, t+1) that touch the window
+      for (int t0 = max(lo - 1, 0); t0 <= t_end; t0 += 32) {
+        const int t = t0 + lane;
+        bool hit = false;
+        if (t <= t_end) {
+          const float a = __fadd_rn(base, cget(t)), b = __fadd_rn(base, cget(t + 1));
+          hit = (b >= thr) && (a <= thr);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) { idx_t = t0 + __ffs(m) - 1; found = true; break; }
       }
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (m) { idx_t = t0 + __ffs(m) - 1; break; }
     }
+    if (!found && hi + 1 <= Nt - 2 && __fadd_rn(base, tv) == thr) idx_t = max(hi + 1, 0);  // both samples in the constant tail
     int end = idx_t + 1 + interval;
     if (end >= Nt) end = Nt - 1;
-    const float q_nn = c[end];
+    const float q_nn = cget(end);
     const float q_vals = __fadd_rn(base, q_nn);
     const float extra = nz ? __fmul_rn(nz[np * (1 + it) + row], p.uncorrelated_noise_charge) : 0.0f;
     float adc = (q_nn != 0.0f) ? __fadd_rn(q_vals, extra) : q_nn;
@@ -127,10 +138,12 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
               : 0.0f;
     int end2 = idx_t + 1 + interval + 1;
     if (end2 >= Nt) end2 = Nt - 1;
-    const float sub = c[end2];
+    const float sub = cget(end2);
     __syncwarp();
-    float vmax = 0.0f;
-    for (int t = lane; t < Nt; t += 32) {
+    hv = __fsub_rn(hv, sub); hv = (hv < 0.0f) ? 0.0f : hv;
+    tv = __fsub_rn(tv, sub); tv = (tv < 0.0f) ? 0.0f : tv;
+    float vmax = fmaxf(lo > 0 ? hv : 0.0f, hi < Nt - 1 ? tv : 0.0f);
+    for (int t = lo + lane; t <= hi; t += 32) {
       float v = __fsub_rn(c[t], sub);
       v = (v < 0.0f) ? 0.0f : v;
       c[t] = v;
@@ -325,7 +338,8 @@ k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved,
     }
     for (int t = prev + 1 + lane; t < ntw; t += 32) out[t] = 0.0f;
   } else {
-    for (int t = lane; t < ntw; t += 32) {
+    for (int t0 = 0; t0 < ntw; t0 += 32) {  // warp-uniform trip count: the shuffles need every lane
+      const int t = t0 + lane;
       float s = 0.0f;
 #pragma unroll
       for (int k = 0; k < 2 * LARND_MAX_ADC; ++k) {
@@ -333,7 +347,7 @@ k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved,
         const float vk = __shfl_sync(0xffffffffu, myval, k);
         if (k < nent) s += (pk >= t) ? vk : 0.0f;
       }
-      out[t] = s * p.t_sampling;
+      if (t < ntw) out[t] = s * p.t_sampling;
     }
   }
 }
