@@ -55,12 +55,13 @@ def run_fit(names=("Ab", "eField"), iterations=30, n_segments=40000, lr=0.01, se
     theta = torch.ones(len(names), device=device, requires_grad=True)
     opt = torch.optim.Adam([theta], lr=lr)
     Params = lb.build_params_class(list(names))
+    p_fit = lb.load_geometry_json(Params, GEOM).replace(**base)  # the geometry file is read once, not per iteration
     reduce = parallel.allreduce_sum_differentiable if world > 1 else None
     history = []
     for it in range(iterations):
         opt.zero_grad()
         vals = {n: theta[i] * NOMINAL[n] for i, n in enumerate(names)}
-        params = lb.load_geometry_json(Params, GEOM).replace(**base, **vals)
+        params = p_fit.replace(**vals)
         wfs, upix = sim.simulate_wfs(params, bank, tracks, fields, n_events=n_events)
         adcs, x, y, z, ticks, hp, ev, _ = sim.simulate_stochastic(params, wfs, upix, 0)
         loss, aux = mse_adc(params, adc2charge(adcs, params), x, y, z, ticks, hp, ev.float(), ref_Q, tgt[1], tgt[2], tgt[3], tgt[4],

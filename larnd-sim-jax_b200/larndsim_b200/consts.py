@@ -76,9 +76,29 @@ class _ParamsBase:
         return type(self)(**d)
 
     def value(self, name):
-        """Python float value of a (possibly differentiable) scalar field."""
+        """Python float value of a (possibly differentiable) scalar field.  The tensor-valued fields of a Params object
+        are fetched together, one device-to-host copy (one synchronisation) per object, and the snapshot is kept while
+        none of the tensors is modified in place (their version counters are part of the key) -- a parameter block is
+        built several times per fit step (waveforms, front end, loss) and would otherwise synchronise per field."""
         v = getattr(self, name)
-        return float(v.detach()) if torch.is_tensor(v) else float(v)
+        if not torch.is_tensor(v):
+            return float(v)
+        tens = [(k, getattr(self, k)) for k in _DEFAULTS if torch.is_tensor(getattr(self, k))]
+        key = tuple((id(t), t._version) for _, t in tens)
+        cache = self.__dict__.get("_host_snapshot")
+        if cache is None or cache[0] != key:
+            host = {}
+            by_dev = {}
+            for k, t in tens:
+                if t.numel() != 1:
+                    continue  # array-valued tensor fields are not scalars of the parameter block
+                by_dev.setdefault(t.device, []).append((k, t))
+            for dev, items in by_dev.items():
+                vals = torch.stack([t.detach().reshape(()).to(torch.float64) for _, t in items]).cpu().tolist()
+                host.update({k: x for (k, _), x in zip(items, vals)})
+            cache = (key, host)
+            object.__setattr__(self, "_host_snapshot", cache)
+        return cache[1][name] if name in cache[1] else float(v.detach())
 
     def grad_leaves(self):
         """[(name, tensor)] of differentiable fields, in the C ABI's LARND_P_* order."""

@@ -7,8 +7,20 @@ import torch
 from .consts import get_vdrift
 
 
+_borders_cache = {}
+
+
 def _borders(params, device):
-    return torch.as_tensor(np.asarray(params.tpc_borders, dtype=np.float64), dtype=torch.float32, device=device)
+    """tpc_borders as a float32 device tensor; uploaded once per (values, device) -- a fit step asks for it every
+    iteration and a pageable host-to-device copy synchronises."""
+    b = np.asarray(params.tpc_borders, dtype=np.float64)
+    key = (b.tobytes(), b.shape, str(device))
+    t = _borders_cache.get(key)
+    if t is None:
+        if len(_borders_cache) > 16:
+            _borders_cache.clear()
+        t = _borders_cache[key] = torch.as_tensor(b, dtype=torch.float32, device=device)
+    return t
 
 
 def pixel2id(params, pixel_x, pixel_y, pixel_plane, eventID):

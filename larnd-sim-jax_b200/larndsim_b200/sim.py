@@ -451,11 +451,15 @@ def parse_output(params, adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event
     nb_valid (callers of the reference slice [:nb_valid]; here the slicing is already done)."""
     mask = (hit_prob > params.hit_prob_threshold) & (event[:, None] >= 0) & (unique_pixels[:, None] >= 0)
     k = mask.shape[1]
-    fm = mask.reshape(-1)
-    rep = lambda a: a.repeat_interleave(k)
-    out = (adcs.reshape(-1)[fm], rep(pixel_x)[fm], rep(pixel_y)[fm], pixel_z.reshape(-1)[fm], ticks.reshape(-1)[fm],
-           hit_prob.reshape(-1)[fm], rep(event)[fm], rep(unique_pixels)[fm])
-    return out + (int(fm.sum().item()),)
+    # one compaction (the only host synchronisation of this function, like the reference's [:nb_valid]); the eight
+    # outputs are gathers with the same index list -- boolean-mask indexing would synchronise once per output
+    idx = torch.nonzero(mask.reshape(-1)).squeeze(1)
+    rows = torch.div(idx, k, rounding_mode="floor")
+    slot = lambda a: a.reshape(-1).index_select(0, idx)
+    per_row = lambda a: a.index_select(0, rows)
+    out = (slot(adcs), per_row(pixel_x), per_row(pixel_y), slot(pixel_z), slot(ticks), slot(hit_prob), per_row(event),
+           per_row(unique_pixels))
+    return out + (int(idx.numel()),)
 
 
 def simulate_stochastic(params, wfs, unique_pixels, rngseed):
