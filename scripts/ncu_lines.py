@@ -2,19 +2,25 @@
 program order) with `nvdisasm --print-line-info` of the same cubin (source line of every instruction, same order).
 
 usage: python scripts/ncu_lines.py report.ncu-rep <kernel regex> <cubin name inside the .so, e.g. accumulate> [mangled filter]
+(the filter defaults to the template instantiation named in the report; the library must be the build that was profiled)
 """
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "larnd-sim-jax_b200", "larndsim_b200", "liblarnd_b200.so")
 rep, kre, cub = sys.argv[1], sys.argv[2], sys.argv[3]
-filt = sys.argv[4] if len(sys.argv) > 4 else kre
+filt = sys.argv[4] if len(sys.argv) > 4 else None
 
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
 # several launches may match: keep the first block
 blocks = out.split('"Kernel Name"')
 body = '"Kernel Name"' + blocks[1]
 lines = body.splitlines()
+if filt is None:
+    # template instantiations share the source lines: pick the .text section of the instantiation that was profiled
+    # (k_acc_tiles<4> -> mangled ...k_acc_tilesILi4E...), not the first one in the cubin
+    m = re.search(r"(%s)<(?:\(int\))?(\d+)>" % kre, out)
+    filt = "%sILi%sE" % (m.group(1), m.group(2)) if m else kre
 rows = list(csv.reader(lines[1:]))
 hdr = rows[0]
 iS, iI, iN = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
