@@ -132,10 +132,14 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
       float part[NR * NPOS];
 #pragma unroll
       for (int k = 0; k < NR * NPOS; ++k) part[k] = 0.0f;
+      if (!inside) {  // window samples live on ticks >= 2, corrections on >= 1 (only differs for runs at the low end of the readout)
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (tmin - 1 + 32 * s + lane < 2) graw[s] = 0.0f;
+      }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        // window samples live on ticks >= 2, corrections on >= 1 (only differs for runs at the low end of the readout)
-        const float gv = (inside || tmin - 1 + 32 * s + lane >= 2) ? graw[s] : 0.0f;
+        const float gv = graw[s];
 #pragma unroll
         for (int j = 0; j < NPOS; ++j)
 #pragma unroll
