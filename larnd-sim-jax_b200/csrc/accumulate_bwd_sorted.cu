@@ -41,7 +41,6 @@ constexpr int BSLOTS = 32 / MAXLEN;  // runs whose segments are processed togeth
 struct PairSlots {
   float G[BSLOTS][GSB];        // G[NR*j + r] of the run parked in the slot
   float gpos[BSLOTS][KPT + 2]; // upstream gradient at ticks tmin - 1 + j
-  float ca[BSLOTS][KPT + 2], cb[BSLOTS][KPT + 2];  // running sums of the response at ct(tmin + j), ct + 1
   int p[BSLOTS];
 };
 
@@ -121,13 +120,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
           graw[s] = (col >= 1 && col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
         }
       }
-      int ctl = nt - L - (tmin + lane);
-      ctl = max(0, min(ctl, nt - 1));
-      if (lane <= KPT) {  // lane j <-> position j: gradient at tick tmin - 1 + j, running sums at ct(tmin + j)
-        ps.gpos[nslot][lane] = graw[0];
-        ps.ca[nslot][lane] = __ldg(crow + ctl);
-        ps.cb[nslot][lane] = __ldg(crow + min(ctl + 1, nt - 1));
-      }
+      if (lane <= KPT) ps.gpos[nslot][lane] = graw[0];  // lane j <-> position j: gradient at tick tmin - 1 + j
       if (lane == 0) ps.p[nslot] = p;
       float part[NR * NPOS];
 #pragma unroll
@@ -165,7 +158,11 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
       if (m != INT32_MIN) {
         const float* Gs = ps.G[slot];
         const float gB = ps.gpos[slot][m], gA = ps.gpos[slot][m + 1];   // ticks T0 - 1 and T0
-        const float Ca = ps.ca[slot][m], Cb = ps.cb[slot][m];
+        // running sums of the response at ct(T0), ct + 1 (sim_jax.py:236-247): loaded here, once per segment, instead of
+        // per run and position in the correlation phase (where the shared-memory hand-over waited on the loads)
+        int ct = nt - L - (sm.run[p].z + m);
+        ct = max(0, min(ct, nt - 1));
+        const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1));
         const float q = sm.q[i], f = sm.f[i], omf = 1.0f - f;
         const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
         const float gm = fmaf(f, gB, omf * gA);
