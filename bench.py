@@ -380,13 +380,27 @@ def run_ours(args):
         achieved = b_seg * nseg / (k_ms[1] * 1e-3) / 1e9
         # DRAM bytes of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full`
         # capture at the 10 M-segment workload (profiles/r1_traffic_10M.json), scaled to this run's segment count
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic_10M.json")) as fh:
-                tj = json.load(fh)
-            traffic = float(tj["k_acc_tiles<4>"][0]["dram_bytes"]) * nseg / 10010184.0
-        except Exception:
-            traffic = None
+        # L2 reduction traffic (the kernel's output leaves as red.global.add.f32): lts__t_sectors_srcunit_tex_op_red x 32 B of
+        # the same capture, against the reduction throughput a pure flush kernel reaches with the same access pattern and
+        # an L2-resident target (scripts/ubench_red.cu pattern A, profiles/r1b_ubench_red.txt)
+        traffic, l2_red = None, None
+        for tname in ("r1b_traffic_10M.json", "r1_traffic_10M.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tname)) as fh:
+                    tj = json.load(fh)
+                ent = tj["k_acc_tiles<4>"][0]
+                traffic = float(ent["dram_bytes"]) * nseg / 10010184.0
+                if ent.get("l2_red_sectors"):
+                    red_bytes = float(ent["l2_red_sectors"]) * 32.0 * nseg / 10010184.0
+                    red_peak = 5170.0
+                    l2_red = {"achieved": red_bytes / (k_ms[1] * 1e-3) / 1e9, "peak": red_peak, "unit": "GB/s",
+                              "frac": red_bytes / (k_ms[1] * 1e-3) / 1e9 / red_peak, "bytes_per_launch": red_bytes,
+                              "peak_source": "scripts/ubench_red.cu, lane<->tick 128-byte reductions into an L2-resident buffer "
+                                             "(2 GB DRAM-resident target: 2080 GB/s)",
+                              "sectors_source": "profiles/" + tname}
+                break
+            except Exception:
+                continue
         line = {
             "metric": METRIC, "value": total_seg / (ms_fwd * 1e-3), "unit": "segments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_fwd, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -410,7 +424,9 @@ def run_ours(args):
             "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate incl. run sort)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_segment": b_seg,
-                         "note": "accumulate is bound by on-chip gather/FMA issue, not HBM (SURVEY §8d); contributions/s below",
+                         "note": "accumulate is bound by instruction issue and L2 reduction throughput, not HBM (SURVEY §8d): "
+                                 "see l2_red and contributions/s",
+                         "l2_red": l2_red,
                          "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3)},
             "setup_s": t_gen,
         }
