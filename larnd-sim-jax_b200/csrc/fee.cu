@@ -205,7 +205,7 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   }
 }
 
-// exclusive scan of row_counts (single CTA, looped) -> offsets, total
+// exclusive scan of row_counts (single CTA, looped, four rows per thread and iteration) -> offsets, total
 __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
                                                       int32_t* __restrict__ total) {
   __shared__ int wsum[32];
@@ -213,10 +213,13 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int b0 = 0; b0 < n; b0 += 1024) {
-    int i = b0 + threadIdx.x;
-    int v = i < n ? counts[i] : 0;
-    int inc = v;
+  for (int b0 = 0; b0 < n; b0 += 4096) {
+    const int i = b0 + 4 * threadIdx.x;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i + k < n ? counts[i + k] : 0;
+    const int tsum = v[0] + v[1] + v[2] + v[3];
+    int inc = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       int u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -234,9 +237,13 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict_
       wsum[lane] = x;
     }
     __syncthreads();
-    int off = carry + (wid > 0 ? wsum[wid - 1] : 0) + inc - v;
-    if (i < n) offsets[i] = off;
-    int blk_total = wsum[31];
+    int off = carry + (wid > 0 ? wsum[wid - 1] : 0) + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i + k < n) offsets[i + k] = off;
+      off += v[k];
+    }
+    const int blk_total = wsum[31];
     __syncthreads();
     if (threadIdx.x == 0) carry += blk_total;
     __syncthreads();
