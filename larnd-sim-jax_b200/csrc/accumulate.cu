@@ -539,7 +539,8 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
                             int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
   if (n == 0) return LARND_OK;
   const bool slow_only = (flags & LARND_ACC_SLOW_ONLY) != 0;
-  if (!slow_only && larnd_sorted_supported(p, lut)) {
+  // (the forward tile kernel addresses the waveform buffer with signed 32-bit element offsets)
+  if (!slow_only && larnd_sorted_supported(p, lut) && (int64_t)npix_capacity * p.n_ticks < ((int64_t)1 << 31)) {
     // large batches: class-sorted kernel (accumulate_sorted.cu).  LARND_ACC_IMPL = chunk | sorted overrides the size rule.
     bool sorted = n >= LARND_SORTED_MIN_SEGMENTS;
     if (const char* e = getenv("LARND_ACC_IMPL")) sorted = e[0] == 's';

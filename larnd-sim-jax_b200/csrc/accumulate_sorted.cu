@@ -42,6 +42,7 @@ struct TileSmem {
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   signed char udx[225], udy[225];  // relative pixel of every neighbour unit (P <= 15)
   int tile, next_unit, nseg;
+  int low_end;  // some run of the tile starts below tick 2 (its windows need the garbage-column handling)
 };
 
 template <int NS, int NR>
@@ -86,11 +87,12 @@ __device__ __forceinline__ void conv(float (&acc)[NS], const float (&Rw)[3][NS][
 // Adds one (run, unit) window to a waveform row: acc = window part, Ev = merged boundary correction of this lane
 // (slot 0, lanes < ES).  Column of (slot s, lane) is tmin - 1 + 32 s + lane.  Window samples are valid on columns
 // >= 2, corrections on columns >= 1; what falls below goes to the garbage column 0 (sim_jax.py:177-178,243-244).
+// dst = address of this lane's tick of slot 0 (row base + tmin - 1 + lane); fast = no run of the tile starts below tick 2
+// (the window end is inside the row for every run of the sorted path: seg_is_fast).
 template <int NS>
-__device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, float* rowbase, int tmin, int nticks, int lane,
-                                            float sign, const bool (&act)[NS], bool last_partial) {
-  if (tmin >= 2 && tmin - 2 + 32 * NS < nticks) {  // warp-uniform, the common case: whole register window inside the row
-    float* dst = rowbase + (tmin - 1) + lane;
+__device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, float* dst, int tmin, int nticks, int lane,
+                                            float sign, const bool (&act)[NS], bool last_partial, bool fast) {
+  if (fast) {  // tile-uniform, the common case: every active tick of the window is a regular column of the row
     // act[s] = this lane's tick of slot s lies inside the run window (L + 2 + span ticks, the same for every run of the
     // tile): hoisted predicates instead of a zero test per slot; zero-valued adds inside the window are harmless
     if (last_partial) {
@@ -107,6 +109,7 @@ __device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, fl
         if (act[s]) atomicAdd(dst + 32 * s, sign * acc[s]);
     }
   } else {
+    float* rowbase = dst - (tmin - 1) - lane;
     float g = 0.0f;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -130,6 +133,12 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
                                               const float* __restrict__ hbuf, int hstride, const float* __restrict__ Ebuf,
                                               float* __restrict__ row0, int mode /* 0 own row, 1 sum row -> row0, 2 own row and -row0 */,
                                               int lane) {
+  const bool fast = !sm.low_end;
+  // lane <-> run: 32-bit (signed: tmin - 1 may be negative on row 0) element offset of column tmin - 1 of the run's row
+  // inside the target buffer (the launcher keeps npix * nticks below 2^31 for this kernel); one shuffle + one wide add per
+  // window instead of 64-bit row arithmetic
+  float* const base = mode == 1 ? row0 : A.wfs;
+  const int myoff = (mode == 1 ? 0 : row * A.nticks) + (sm.run[lane].z - 1);
   bool act[NS];  // window length of every run of the tile: L + 2 + span = L + NPOS ticks
 #pragma unroll
   for (int s = 0; s < NS; ++s) act[s] = 32 * s + lane < A.L + NPOS;
@@ -140,7 +149,8 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
     const bool two = NR == 3 && todo != 0u;  // neighbour units (one template, dual flush) run one window at a time: measured faster
     const int p1 = two ? __ffs(todo) - 1 : p0;
     if (two) todo &= todo - 1;
-    const int r0 = __shfl_sync(0xffffffffu, row, p0), r1 = __shfl_sync(0xffffffffu, row, p1);
+    float* const d0 = base + (__shfl_sync(0xffffffffu, myoff, p0) + lane);
+    float* const d1 = base + (__shfl_sync(0xffffffffu, myoff, p1) + lane);
     const int t0 = sm.run[p0].z, t1 = sm.run[p1].z;
     const float* h0 = hbuf + p0 * hstride;
     const float* h1 = hbuf + p1 * hstride;
@@ -162,13 +172,11 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
     }
     const float E0 = lane < ES ? Ebuf[p0 * ES + lane] : 0.0f;
     const float E1 = lane < ES ? Ebuf[p1 * ES + lane] : 0.0f;
-    if (mode == 1) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, 1.0f, act, lp);
-    else emit_window<NS>(a0, E0, A.wfs + (int64_t)r0 * A.nticks, t0, A.nticks, lane, 1.0f, act, lp);
-    if (mode == 2) emit_window<NS>(a0, E0, row0, t0, A.nticks, lane, -1.0f, act, lp);
+    emit_window<NS>(a0, E0, d0, t0, A.nticks, lane, 1.0f, act, lp, fast);
+    if (mode == 2) emit_window<NS>(a0, E0, row0 + (t0 - 1) + lane, t0, A.nticks, lane, -1.0f, act, lp, fast);
     if (two) {
-      if (mode == 1) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, 1.0f, act, lp);
-      else emit_window<NS>(a1, E1, A.wfs + (int64_t)r1 * A.nticks, t1, A.nticks, lane, 1.0f, act, lp);
-      if (mode == 2) emit_window<NS>(a1, E1, row0, t1, A.nticks, lane, -1.0f, act, lp);
+      emit_window<NS>(a1, E1, d1, t1, A.nticks, lane, 1.0f, act, lp, fast);
+      if (mode == 2) emit_window<NS>(a1, E1, row0 + (t1 - 1) + lane, t1, A.nticks, lane, -1.0f, act, lp, fast);
     }
   }
 }
@@ -236,6 +244,8 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         sm.mpy[lane] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
         len = e.y & 0xffff;
       }
+      const unsigned low = __ballot_sync(0xffffffffu, lane < count && sm.run[lane].z < 2);
+      if (lane == 0) sm.low_end = low != 0u;
       int inc = len;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -464,6 +474,7 @@ int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut) {
   if (p.n_ticks > LARND_ROW0_TICKS_MAX) return 0;
   return 1;
 }
+
 
 int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                    int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
