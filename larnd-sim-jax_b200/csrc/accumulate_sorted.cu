@@ -89,13 +89,13 @@ __device__ __forceinline__ void conv(float (&acc)[NS], const float (&Rw)[3][NS][
 // >= 2, corrections on columns >= 1; what falls below goes to the garbage column 0 (sim_jax.py:177-178,243-244).
 // dst = address of this lane's tick of slot 0 (row base + tmin - 1 + lane); fast = no run of the tile starts below tick 2
 // (the window end is inside the row for every run of the sorted path: seg_is_fast).
-template <int NS>
+template <int NS, bool LP>
 __device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, float* dst, int tmin, int nticks, int lane,
-                                            float sign, const bool (&act)[NS], bool last_partial, bool fast) {
+                                            float sign, const bool (&act)[NS], bool fast) {
   if (fast) {  // tile-uniform, the common case: every active tick of the window is a regular column of the row
     // act[s] = this lane's tick of slot s lies inside the run window (L + 2 + span ticks, the same for every run of the
     // tile): hoisted predicates instead of a zero test per slot; zero-valued adds inside the window are harmless
-    if (last_partial) {
+    if (LP) {  // kernel-level constant: L + NPOS lies in [32 (NS - 1), 32 NS) for every NPOS
       // the usual shape (the window ends inside the last slot): every lane of the other slots is active, so they need no
       // predicate -- ptxas wraps every predicated reduction in BSSY / BRA / BSYNC
       atomicAdd(dst, sign * (acc[0] + Ev));  // RED.E.ADD.F32, coalesced
@@ -128,7 +128,7 @@ __device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, fl
 // Consume loop of one unit: every run of `todo` gets its window computed from the register-resident response and flushed.
 // Two runs are in flight per iteration (independent FFMA chains hide the 4-cycle dependency latency) and the number of
 // impulse positions is a compile-time constant (uniform per tile: the class key contains the tick span).
-template <int NS, int NR, int NPOS>
+template <int NS, int NR, int NPOS, bool LP>
 __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
                                               const float* __restrict__ hbuf, int hstride, const float* __restrict__ Ebuf,
                                               float* __restrict__ row0, int mode /* 0 own row, 1 sum row -> row0, 2 own row and -row0 */,
@@ -142,7 +142,6 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
   bool act[NS];  // window length of every run of the tile: L + 2 + span = L + NPOS ticks
 #pragma unroll
   for (int s = 0; s < NS; ++s) act[s] = 32 * s + lane < A.L + NPOS;
-  const bool lp = NS > 1 && A.L + NPOS >= 32 * (NS - 1) && A.L + NPOS < 32 * NS;  // warp-uniform, loop-invariant
   while (todo) {
     const int p0 = __ffs(todo) - 1;
     todo &= todo - 1;
@@ -172,27 +171,27 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
     }
     const float E0 = lane < ES ? Ebuf[p0 * ES + lane] : 0.0f;
     const float E1 = lane < ES ? Ebuf[p1 * ES + lane] : 0.0f;
-    emit_window<NS>(a0, E0, d0, t0, A.nticks, lane, 1.0f, act, lp, fast);
-    if (mode == 2) emit_window<NS>(a0, E0, row0 + (t0 - 1) + lane, t0, A.nticks, lane, -1.0f, act, lp, fast);
+    emit_window<NS, LP>(a0, E0, d0, t0, A.nticks, lane, 1.0f, act, fast);
+    if (mode == 2) emit_window<NS, LP>(a0, E0, row0 + (t0 - 1) + lane, t0, A.nticks, lane, -1.0f, act, fast);
     if (two) {
-      emit_window<NS>(a1, E1, d1, t1, A.nticks, lane, 1.0f, act, lp, fast);
-      if (mode == 2) emit_window<NS>(a1, E1, row0 + (t1 - 1) + lane, t1, A.nticks, lane, -1.0f, act, lp, fast);
+      emit_window<NS, LP>(a1, E1, d1, t1, A.nticks, lane, 1.0f, act, fast);
+      if (mode == 2) emit_window<NS, LP>(a1, E1, row0 + (t1 - 1) + lane, t1, A.nticks, lane, -1.0f, act, fast);
     }
   }
 }
 
-template <int NS, int NR>
+template <int NS, int NR, bool LP>
 __device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
                                                    const float* hbuf, int hstride, const float* Ebuf, float* row0, int mode, int lane, int npos) {
   if (npos <= 3) {
-    if (npos == 2) consume_pairs<NS, NR, 2>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-    else consume_pairs<NS, NR, 3>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  } else if (npos == 4) consume_pairs<NS, NR, 4>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else if (npos == 5) consume_pairs<NS, NR, 5>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else consume_pairs<NS, NR, KPT>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+    if (npos == 2) consume_pairs<NS, NR, 2, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+    else consume_pairs<NS, NR, 3, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  } else if (npos == 4) consume_pairs<NS, NR, 4, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else if (npos == 5) consume_pairs<NS, NR, 5, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else consume_pairs<NS, NR, KPT, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
 }
 
-template <int NS>
+template <int NS, bool LP>
 __global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? 2 : 1)
 k_acc_tiles(const __grid_constant__ SortArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -363,7 +362,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
                                       A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp};
         load_response<NS, 3>(Rw, rows, A.Lp, lane);
         // consume: lane <-> tick
-        consume_pairs_npos<NS, 3>(A, sm, Rw, __ballot_sync(0xffffffffu, row >= 0), row, myh, HS, myE, row0, 0, lane, npos);
+        consume_pairs_npos<NS, 3, LP>(A, sm, Rw, __ballot_sync(0xffffffffu, row >= 0), row, myh, HS, myE, row0, 0, lane, npos);
         __syncwarp();
       } else {
         // ---------------- neighbour pixels: template 0, full segment charge (sim_jax.py:197-225,250-261) ----------
@@ -427,7 +426,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         const float* const rows[1] = {rowp0};
         load_response<NS, 1>(Rw, rows, A.Lp, lane);
         const bool dual = !sum_unit && !A.skip_garbage;
-        consume_pairs_npos<NS, 1>(A, sm, Rw, owned, row, &sm.hN[0][0], KPT, myE, row0, sum_unit ? 1 : (dual ? 2 : 0), lane, npos);
+        consume_pairs_npos<NS, 1, LP>(A, sm, Rw, owned, row, &sm.hN[0][0], KPT, myE, row0, sum_unit ? 1 : (dual ? 2 : 0), lane, npos);
         __syncwarp();
       }
     }
@@ -497,14 +496,21 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
   const size_t smem = sizeof(TileSmem);
   static bool attr_done = false;
   if (!attr_done) {
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  if (need <= 32 * 4) k_acc_tiles<4><<<grid, TILE_THREADS, smem, st>>>(A);
-  else if (need <= 32 * 5) k_acc_tiles<5><<<grid, TILE_THREADS, smem, st>>>(A);
-  else k_acc_tiles<6><<<grid, TILE_THREADS, smem, st>>>(A);
+  // LP: for every number of impulse positions (2 .. KPT) the run window L + NPOS ends inside the last 32-tick slot, so
+  // all other slots are flushed without a predicate
+  const int ns = need <= 32 * 4 ? 4 : (need <= 32 * 5 ? 5 : 6);
+  const bool lp = lut->L + 2 >= 32 * (ns - 1) && lut->L + KPT < 32 * ns;
+  if (ns == 4) { if (lp) k_acc_tiles<4, true><<<grid, TILE_THREADS, smem, st>>>(A); else k_acc_tiles<4, false><<<grid, TILE_THREADS, smem, st>>>(A); }
+  else if (ns == 5) { if (lp) k_acc_tiles<5, true><<<grid, TILE_THREADS, smem, st>>>(A); else k_acc_tiles<5, false><<<grid, TILE_THREADS, smem, st>>>(A); }
+  else { if (lp) k_acc_tiles<6, true><<<grid, TILE_THREADS, smem, st>>>(A); else k_acc_tiles<6, false><<<grid, TILE_THREADS, smem, st>>>(A); }
   LARND_LAUNCH_CHECK("k_acc_tiles");
   if (!A.skip_garbage) {
     k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, grid, p.n_ticks, wfs);
