@@ -550,6 +550,8 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   bool sorted = larnd_sorted_supported(p, lut) && n >= LARND_SORTED_MIN_SEGMENTS;
   if (const char* e = getenv("LARND_BWD_IMPL")) sorted = larnd_sorted_supported(p, lut) && e[0] == 's';
   else if (const char* e2 = getenv("LARND_ACC_IMPL")) sorted = larnd_sorted_supported(p, lut) && e2[0] == 's';
+  // (the tile kernel addresses the gradient rows with signed 32-bit element offsets)
+  if ((int64_t)npix_capacity * g_stride >= ((int64_t)1 << 31)) sorted = false;
   A.sorted_active = sorted ? 1 : 0;
   prof_begin(2, st);
   if (sorted) {

@@ -58,6 +58,7 @@ struct BwdTileSmem {
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   signed char udx[225], udy[225];
   int tile, next_unit, nseg;
+  int low_end;  // some run of the tile starts below tick 2, or its 32 NS-tick register window ends beyond the row
 };
 
 __device__ __forceinline__ float warp_sum_f(float v) {
@@ -96,6 +97,10 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   const int nt = S.nt, L = S.L, nticks = S.nticks;
   const float Cl = __ldg(crow + nt - L);
   PairSlots& ps = sm.ps[warp];
+  // lane <-> run: signed 32-bit element offset of column tmin - 1 of the run's gradient row (npix * nticks < 2^31 is
+  // checked by the launcher); tile-level flag instead of a per-run test for windows at the low end of the readout
+  const int myoff = row * (int)A.g_stride + (sm.run[lane].z - 1);
+  const bool inside = !sm.low_end;
   while (todo) {
     // ---- up to 4 runs: correlate, reduce, park the results in the warp's slots -------------------------------------
     int nslot = 0;
@@ -103,17 +108,15 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
     for (; nslot < BSLOTS && todo; ++nslot) {
       const int p = __ffs(todo) - 1;
       todo &= todo - 1;
-      const int rowp = __shfl_sync(0xffffffffu, row, p);
       const int tmin = sm.run[p].z;
-      const float* grow = A.g + (int64_t)rowp * A.g_stride;
-      // upstream-gradient window (coalesced) and the running sums at the run's tick positions: all loads first
+      const float* gp = A.g + (__shfl_sync(0xffffffffu, myoff, p) + lane);
+      // upstream-gradient window (coalesced): all loads first
       float graw[NS];
-      const bool inside = tmin >= 2 && tmin - 2 + 32 * NS < nticks;  // warp-uniform, the common case: whole window inside the row
-      if (inside) {
-        const float* gp = grow + (tmin - 1 + lane);
+      if (inside) {  // tile-uniform, the common case: every register window of the tile lies inside its row
 #pragma unroll
         for (int s = 0; s < NS; ++s) graw[s] = __ldg(gp + 32 * s);
       } else {
+        const float* grow = gp - (tmin - 1) - lane;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           const int col = tmin - 1 + 32 * s + lane;
@@ -265,6 +268,8 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         sm.mpy[lane] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
         len = e.y & 0xffff;
       }
+      const unsigned low = __ballot_sync(0xffffffffu, lane < count && (sm.run[lane].z < 2 || sm.run[lane].z - 2 + 32 * NS >= S.nticks));
+      if (lane == 0) sm.low_end = low != 0u;
       int inc = len;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
