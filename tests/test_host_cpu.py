@@ -75,6 +75,25 @@ def test_params_container_mirrors_reference_semantics():
     assert abs(lb.get_vdrift(lb.load_geometry_json(lb.build_params_class([]), cm.GEOM)) - 0.159645) < 1e-6
 
 
+def test_params_host_snapshot_is_batched_and_tracks_in_place_updates():
+    """Params.value fetches every tensor-valued field in one go and keeps the snapshot until a tensor is modified in place
+    (an optimiser stepping on a leaf) -- the parameter block is built several times per fit step."""
+    import torch
+    import larndsim_b200 as lb
+    P = lb.build_params_class(["Ab", "kb", "lifetime"])
+    p = lb.load_geometry_json(P, cm.GEOM).replace(Ab=torch.tensor(0.75, requires_grad=True))
+    assert p.value("Ab") == float(np.float32(0.75)) and p.value("kb") == float(np.float32(p.kb.item()))
+    snap = p.__dict__["_host_snapshot"]
+    assert set(snap[1]) == {"Ab", "kb", "lifetime"}
+    assert p.value("lifetime") == float(p.lifetime.detach()) and p.__dict__["_host_snapshot"] is snap   # served from the snapshot
+    with torch.no_grad():
+        p.Ab.add_(0.05)                                                                                  # optimiser step in place
+    assert abs(p.value("Ab") - 0.8) < 1e-6 and p.__dict__["_host_snapshot"] is not snap
+    q = p.replace(kb=0.05)
+    assert "_host_snapshot" not in q.__dict__ and abs(q.value("kb") - 0.05) < 1e-8 and abs(q.value("Ab") - 0.8) < 1e-6
+    assert p.value("size_margin") == float(p.size_margin)                                               # plain Python fields
+
+
 def test_parameter_block_matches_oracle_constants():
     from larndsim_b200 import sim
     pp, op = cm.product_params(), cm.oracle_params()
