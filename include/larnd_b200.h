@@ -18,6 +18,12 @@
  *   larnd_mc_forward        <- simulate_drift(mc_diff) + current_mc + accumulate_signals_parametrized
  *                                                                      sim_jax.py:122-139,289-335; detsim_jax.py:207-228,618-639
  *   larnd_mc_backward       <- jax.grad through the same
+ *   larnd_tracks_stage      <- shift_tracks / quench / drift as separate stages
+ *                                                                      sim_jax.py:109-119, quenching_jax.py:38-75, drifting_jax.py:19-58
+ *   larnd_signals_stream_*  <- simulate_signals with its own (materialised-stream) argument list and its VJP
+ *                                                                      sim_jax.py:142-286
+ *   larnd_current_mc[_backward], larnd_accumulate_parametrized[_backward]
+ *                           <- current_mc, accumulate_signals_parametrized        detsim_jax.py:619-639, 209-228
  *
  * Conventions: plain pointers and sizes, no allocation and no host synchronisation inside
  * (workspace is caller-provided, its size queried with larnd_workspace_bytes); every pointer
@@ -248,6 +254,64 @@ size_t larnd_rbf_field_scratch_bytes(int32_t n_targets, int32_t n_sources);
 int larnd_rbf_field(const float* targets_d, int32_t n_targets, const float* sources_d, const float* weights_d,
                     int32_t n_sources, float sigma, float* field_d /* (n_targets, 4) */, void* scratch_d, size_t scratch_bytes,
                     void* stream);
+
+/* ---- Stream-form operators: the reference functions whose arguments are the materialised per-segment arrays.  The
+ * fused entry points above never build those arrays; these exist so that code calling the reference's stages one by one
+ * (quench -> drift -> simulate_drift_new -> simulate_signals, or simulate_drift -> current_mc ->
+ * accumulate_signals_parametrized) keeps working on the device. ---- */
+
+/* shift_tracks (sim_jax.py:109-119), quench (quenching_jax.py:38-75), drift (drifting_jax.py:19-58): tracks (n, ncols)
+ * in -> updated copy out (may alias).  stages: bit0 shift, bit1 quench, bit2 drift, applied in that order.  `cols` as for
+ * larnd_lut_forward; `oc` names the extra columns the stages read/write. */
+typedef struct larnd_track_columns {
+  int32_t x_start, x_end, y_start, y_end;                                        /* shifted with x, y (z_start/z_end: `cols`) */
+  int32_t n_electrons, long_diff, tran_diff, pixel_plane, t, t_start, t_end;    /* written by quench / drift */
+} larnd_track_columns_t;
+int larnd_tracks_stage(const float* tracks_d, int64_t n, const larnd_columns_t* cols, const larnd_track_columns_t* oc,
+                       const larnd_params_t* params, int32_t stages, float* out_d, void* stream);
+
+/* simulate_signals (sim_jax.py:142-286) with the reference's argument list:
+ *   unique_pixels (npix) int32 sorted; main entries (n_main = N*T^2): pixels int32, t0_after_diff, nelectrons, long_diff
+ *   float32, currents_idx (n_main,2) int32 in [0,5); neighbour entries: nelectrons_neigh (N), t0_neigh (N),
+ *   pix_renumbering_neigh (N*P^2) int32 rows, currents_idx_neigh (N*P^2,2) int32.
+ * wfs_d (npix, n_ticks) is zeroed and filled (garbage column 0 included).  The response values and running sums come from
+ * the larnd_lut_t tables (== response_template / jnp.cumsum(response_template)).  status_d[0]: bit0 a main response index
+ * was outside the collecting 5x5 bins, bit1 a neighbour index outside the LUT (those entries are skipped).
+ * The backward call returns the VJP w.r.t. the five float streams (g_wfs_d: (npix, n_ticks) with row stride). */
+int larnd_signals_stream_forward(const int32_t* unique_pixels_d, int32_t npix, const int32_t* pixels_d,
+                                 const float* t0_after_diff_d, const float* nelectrons_d, const float* long_diff_d,
+                                 const int32_t* currents_idx_d, int64_t n_main, const float* nelectrons_neigh_d,
+                                 const int32_t* pix_renumbering_neigh_d, const float* t0_neigh_d,
+                                 const int32_t* currents_idx_neigh_d, int64_t n_segments, const larnd_params_t* params,
+                                 const larnd_lut_t* lut, float* wfs_d, int32_t* status_d, void* stream);
+int larnd_signals_stream_backward(const int32_t* unique_pixels_d, int32_t npix, const int32_t* pixels_d,
+                                  const float* t0_after_diff_d, const float* nelectrons_d, const float* long_diff_d,
+                                  const int32_t* currents_idx_d, int64_t n_main, const float* nelectrons_neigh_d,
+                                  const int32_t* pix_renumbering_neigh_d, const float* t0_neigh_d,
+                                  const int32_t* currents_idx_neigh_d, int64_t n_segments, const larnd_params_t* params,
+                                  const larnd_lut_t* lut, const float* g_wfs_d, int64_t g_row_stride,
+                                  float* g_nelectrons_d, float* g_t0_after_diff_d, float* g_long_diff_d,
+                                  float* g_nelectrons_neigh_d, float* g_t0_neigh_d, int32_t* status_d, void* stream);
+
+/* current_mc (detsim_jax.py:619-639): electrons (n, ncols) + pixel centres (n, 2) -> t0_tick (n) int32, signals (n, 51).
+ * The backward call returns the VJP w.r.t. the electrons' x, y, z, long_diff, n_electrons columns (other columns of
+ * g_electrons_d are zeroed) and w.r.t. the pixel centres. */
+typedef struct larnd_current_columns {
+  int32_t ncols, x, y, z, long_diff, n_electrons, pixel_plane;
+} larnd_current_columns_t;
+int larnd_current_mc(const float* electrons_d, int64_t n, const larnd_current_columns_t* cols, const float* pixels_coord_d,
+                     const larnd_params_t* params, int32_t* t0_tick_d, float* signals_d, void* stream);
+int larnd_current_mc_backward(const float* electrons_d, int64_t n, const larnd_current_columns_t* cols,
+                              const float* pixels_coord_d, const larnd_params_t* params, const float* g_signals_d,
+                              float* g_electrons_d, float* g_pixels_coord_d, void* stream);
+
+/* accumulate_signals_parametrized (detsim_jax.py:209-228): wfs_d (npix, n_ticks) += signals (n, n_signal_ticks) at row
+ * pix_id, ticks start+k (< 0 or >= n_ticks-1 -> column 0, else +1).  Backward: g_signals = gather of g_wfs. */
+int larnd_accumulate_parametrized(float* wfs_d, int32_t npix, int32_t n_ticks, const float* signals_d, int32_t n_signal_ticks,
+                                  const int32_t* pix_id_d, const int32_t* start_ticks_d, int64_t n, void* stream);
+int larnd_accumulate_parametrized_backward(const float* g_wfs_d, int32_t npix, int32_t n_ticks, float* g_signals_d,
+                                           int32_t n_signal_ticks, const int32_t* pix_id_d, const int32_t* start_ticks_d,
+                                           int64_t n, void* stream);
 
 /* Optional device-side timing of the dominant kernels (used by bench.py for the roofline numbers): when
  * enabled, CUDA events are recorded on the launching stream immediately around

@@ -366,6 +366,98 @@ __global__ void __launch_bounds__(256) k_mc_reduce_partials(const float* __restr
   if (threadIdx.x == 0) grad[pidx] += (float)sm[0];
 }
 
+
+// ---- stream-form operators: current_mc (detsim_jax.py:619-639) and accumulate_signals_parametrized (:209-228) with the
+// reference's own argument lists (electrons (N, ncols) + pixel centres in, (N, 51) currents out), for code that calls
+// the stages one by one.  The fused kernels above never materialise the (N, 51) array.
+struct CurArgs {
+  const float* electrons; int64_t n; int ncols;
+  int cx, cy, cz, cld, cq, cplane;
+  const float* pixc;       // (n, 2)
+  int32_t* t0_tick;        // (n)
+  float* signals;          // (n, 51)
+  const float* g_signals;  // backward
+  float* g_electrons;      // (n, ncols), columns x, y, z, long_diff, n_electrons written
+  float* g_pixc;           // (n, 2)
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(MC_WARPS * 32)
+k_current_mc(const __grid_constant__ CurArgs A, const __grid_constant__ larnd_params_t p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
+  if (s >= A.n) return;
+  const float* el = A.electrons + s * A.ncols;
+  const float x = __ldg(el + A.cx), y = __ldg(el + A.cy), z = __ldg(el + A.cz);
+  const float q = __ldg(el + A.cq);
+  const int plane = max(0, min((int)__ldg(el + A.cplane), p.n_tpc - 1));
+  const float dxs = fsub(x, __ldg(A.pixc + 2 * s)), dys = fsub(y, __ldg(A.pixc + 2 * s + 1));
+  const float dza = fsub(z, p.tpc_borders[plane][2][0]);
+  const float t0 = fdiv(fabsf(dza), p.vdrift);
+  const int tick = (int)fadd(fdiv(t0, p.t_sampling), 0.5f);
+  const float t0f = fsub(t0, fmul((float)tick, p.t_sampling));
+  const float xd = fabsf(dxs), yd = fabsf(dys);
+  const float sig = fdiv(__ldg(el + A.cld), p.vdrift);
+  const float dtk = 5.0f / (MC_NT - 1);
+  const bool use_sig = p.diffusion_in_current_sim != 0;
+  if (!BWD) {
+    if (lane == 0) A.t0_tick[s] = tick;
+    for (int k = lane; k < MC_NT; k += 32) {
+      const float sfrac = __fdiv_rn((float)k, (float)(MC_NT - 1));
+      const float t = (k == MC_NT - 1) ? 5.0f : __fmul_rn(5.0f, sfrac);
+      A.signals[s * MC_NT + k] = current_sample<float>(t, t0f, xd, yd, sig, use_sig, dtk) * q;
+    }
+  } else {
+    float dq = 0.f, din[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < MC_NT; k += 32) {
+      const float gv = __ldg(A.g_signals + s * MC_NT + k);
+      const float sfrac = __fdiv_rn((float)k, (float)(MC_NT - 1));
+      const float t = (k == MC_NT - 1) ? 5.0f : __fmul_rn(5.0f, sfrac);
+      const D4 cur = current_sample<D4>(t, var(t0f, 0), var(xd, 1), var(yd, 2), use_sig ? var(sig, 3) : mk(sig), use_sig, dtk);
+      dq = fmaf(gv, cur.v, dq);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) din[i] = fmaf(gv * q, cur.d[i], din[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) din[i] += __shfl_xor_sync(0xffffffffu, din[i], o);
+    }
+    if (lane == 0) {
+      float* ge = A.g_electrons + s * A.ncols;
+      const float gx = din[1] * (dxs > 0.f ? 1.f : (dxs < 0.f ? -1.f : 0.f));
+      const float gy = din[2] * (dys > 0.f ? 1.f : (dys < 0.f ? -1.f : 0.f));
+      ge[A.cx] = gx;
+      ge[A.cy] = gy;
+      ge[A.cz] = din[0] * (dza > 0.f ? 1.f : (dza < 0.f ? -1.f : 0.f)) / p.vdrift;
+      ge[A.cld] = din[3] / p.vdrift;
+      ge[A.cq] = dq;
+      A.g_pixc[2 * s] = -gx;
+      A.g_pixc[2 * s + 1] = -gy;
+    }
+  }
+}
+
+// wfs.at[flat].add(signals): flat = pixID*Nticks + tick rule; negative flat ids wrap like numpy, ids past the end are dropped
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+k_accumulate_parametrized(float* __restrict__ wfs, const float* __restrict__ g_wfs, float* __restrict__ sig,
+                          const int32_t* __restrict__ pix, const int32_t* __restrict__ start, int64_t n, int nsig, int npix, int nticks) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n * nsig) return;
+  const int64_t s = i / nsig;
+  const int k = (int)(i - s * nsig);
+  int tt = __ldg(start + s) + k;
+  tt = (tt < 0 || tt >= nticks - 1) ? 0 : tt + 1;
+  const int64_t total = (int64_t)npix * nticks;
+  int64_t flat = (int64_t)__ldg(pix + s) * nticks + tt;
+  if (flat < 0) flat += total;
+  const bool ok = flat >= 0 && flat < total;
+  if (!BWD) { if (ok) atomicAdd(wfs + flat, sig[i]); }
+  else sig[i] = ok ? __ldg(g_wfs + flat) : 0.f;
+}
+
 int mc_check(const larnd_params_t* p, const larnd_columns_t* cols, const float* rnd) {
   if (!p || !cols || !rnd) { larnd_set_error("larnd_mc: null argument"); return LARND_E_ARG; }
   if (p->number_pix_neighbors != 0) {
@@ -443,5 +535,75 @@ extern "C" int larnd_mc_backward(const float* tracks_d, int64_t n, const larnd_c
   LARND_LAUNCH_CHECK("k_mc_backward");
   k_mc_reduce_partials<<<LARND_NPARAMS, 256, 0, st>>>(ws.partials, blocks, grad_params_d);
   LARND_LAUNCH_CHECK("k_mc_reduce_partials");
+  return LARND_OK;
+}
+
+static int cur_args(CurArgs& A, const float* electrons_d, int64_t n, const larnd_current_columns_t* c, const float* pixels_coord_d,
+                    const larnd_params_t* p) {
+  if (!c || !p || n < 0 || (n > 0 && (!electrons_d || !pixels_coord_d))) { larnd_set_error("larnd_current_mc: bad argument"); return LARND_E_ARG; }
+  if (p->n_tpc < 1 || p->n_tpc > LARND_MAX_TPC) { larnd_set_error("n_tpc unsupported"); return LARND_E_ARG; }
+  int nt = (int)(5.0 / (double)p->t_sampling + 1e-4) + 1;
+  if (nt != MC_NT) { larnd_set_error("current_mc is built for t_sampling = 0.1 us (51 ticks), got %d ticks", nt); return LARND_E_ARG; }
+  A.electrons = electrons_d; A.n = n; A.ncols = c->ncols;
+  A.cx = c->x; A.cy = c->y; A.cz = c->z; A.cld = c->long_diff; A.cq = c->n_electrons; A.cplane = c->pixel_plane;
+  A.pixc = pixels_coord_d; A.t0_tick = nullptr; A.signals = nullptr; A.g_signals = nullptr; A.g_electrons = nullptr; A.g_pixc = nullptr;
+  return LARND_OK;
+}
+
+extern "C" int larnd_current_mc(const float* electrons_d, int64_t n, const larnd_current_columns_t* c, const float* pixels_coord_d,
+                                const larnd_params_t* p, int32_t* t0_tick_d, float* signals_d, void* stream) {
+  CurArgs A;
+  int rc = cur_args(A, electrons_d, n, c, pixels_coord_d, p);
+  if (rc) return rc;
+  if (n == 0) return LARND_OK;
+  if (!t0_tick_d || !signals_d) { larnd_set_error("larnd_current_mc: null output"); return LARND_E_ARG; }
+  A.t0_tick = t0_tick_d; A.signals = signals_d;
+  k_current_mc<false><<<(unsigned)((n + MC_WARPS - 1) / MC_WARPS), MC_WARPS * 32, 0, (cudaStream_t)stream>>>(A, *p);
+  LARND_LAUNCH_CHECK("k_current_mc");
+  return LARND_OK;
+}
+
+extern "C" int larnd_current_mc_backward(const float* electrons_d, int64_t n, const larnd_current_columns_t* c,
+                                         const float* pixels_coord_d, const larnd_params_t* p, const float* g_signals_d,
+                                         float* g_electrons_d, float* g_pixels_coord_d, void* stream) {
+  CurArgs A;
+  int rc = cur_args(A, electrons_d, n, c, pixels_coord_d, p);
+  if (rc) return rc;
+  if (n == 0) return LARND_OK;
+  if (!g_signals_d || !g_electrons_d || !g_pixels_coord_d) { larnd_set_error("larnd_current_mc_backward: null argument"); return LARND_E_ARG; }
+  A.g_signals = g_signals_d; A.g_electrons = g_electrons_d; A.g_pixc = g_pixels_coord_d;
+  cudaStream_t st = (cudaStream_t)stream;
+  LARND_CUDA(cudaMemsetAsync(g_electrons_d, 0, (size_t)n * c->ncols * sizeof(float), st));
+  k_current_mc<true><<<(unsigned)((n + MC_WARPS - 1) / MC_WARPS), MC_WARPS * 32, 0, st>>>(A, *p);
+  LARND_LAUNCH_CHECK("k_current_mc<bwd>");
+  return LARND_OK;
+}
+
+extern "C" int larnd_accumulate_parametrized(float* wfs_d, int32_t npix, int32_t n_ticks, const float* signals_d, int32_t n_signal_ticks,
+                                             const int32_t* pix_id_d, const int32_t* start_ticks_d, int64_t n, void* stream) {
+  if (!wfs_d || npix < 1 || n_ticks < 2 || n_signal_ticks < 1 || n < 0 || (n > 0 && (!signals_d || !pix_id_d || !start_ticks_d))) {
+    larnd_set_error("larnd_accumulate_parametrized: bad argument");
+    return LARND_E_ARG;
+  }
+  if (n == 0) return LARND_OK;
+  const int64_t tot = n * n_signal_ticks;
+  k_accumulate_parametrized<false><<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      wfs_d, nullptr, const_cast<float*>(signals_d), pix_id_d, start_ticks_d, n, n_signal_ticks, npix, n_ticks);
+  LARND_LAUNCH_CHECK("k_accumulate_parametrized");
+  return LARND_OK;
+}
+
+extern "C" int larnd_accumulate_parametrized_backward(const float* g_wfs_d, int32_t npix, int32_t n_ticks, float* g_signals_d,
+                                                      int32_t n_signal_ticks, const int32_t* pix_id_d, const int32_t* start_ticks_d,
+                                                      int64_t n, void* stream) {
+  if (!g_wfs_d || npix < 1 || n_ticks < 2 || n_signal_ticks < 1 || n < 0 || (n > 0 && (!g_signals_d || !pix_id_d || !start_ticks_d))) {
+    larnd_set_error("larnd_accumulate_parametrized_backward: bad argument");
+    return LARND_E_ARG;
+  }
+  if (n == 0) return LARND_OK;
+  const int64_t tot = n * n_signal_ticks;
+  k_accumulate_parametrized<true><<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nullptr, g_wfs_d, g_signals_d, pix_id_d, start_ticks_d, n, n_signal_ticks, npix, n_ticks);
+  LARND_LAUNCH_CHECK("k_accumulate_parametrized<bwd>");
   return LARND_OK;
 }

@@ -4,6 +4,7 @@ Module map (reference module -> this package):
     larndsim.consts_jax -> larndsim_b200.consts     larndsim.sim_jax    -> larndsim_b200.sim
     larndsim.detsim_jax -> larndsim_b200.detsim     larndsim.fee_jax    -> larndsim_b200.fee
     larndsim.losses_jax -> larndsim_b200.losses (adc2charge / mmd / mse_adc / params_loss)
+    larndsim.quenching_jax -> larndsim_b200.quenching     larndsim.drifting_jax -> larndsim_b200.drifting
     optimize.dataio (chop_tracks, pad_batch) -> larndsim_b200.dataio     jax.random (key/split/normal) -> larndsim_b200.jrandom
 All heavy work is done by hand-written CUDA kernels in csrc/, reached through the C ABI of
 include/larnd_b200.h; there is no CPU fallback.

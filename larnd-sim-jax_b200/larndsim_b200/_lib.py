@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(HERE, "liblarnd_b200.so")
-SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu", "chop.cu", "rng.cu", "prob_fee.cu", "losses.cu"]
+SOURCES = ["api.cu", "prepare.cu", "lut_tables.cu", "accumulate.cu", "accumulate_sorted.cu", "accumulate_bwd.cu", "accumulate_bwd_sorted.cu", "fee.cu", "mc_current.cu", "chop.cu", "rng.cu", "prob_fee.cu", "losses.cu", "stream_ops.cu"]
 
 MAX_TPC = 8
 MAX_TEMPLATES = 128
@@ -35,6 +35,15 @@ class Columns(C.Structure):
 class ChopColumns(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ncols", "x", "y", "z", "x_start", "y_start", "z_start", "x_end", "y_end", "z_end",
                                          "dx", "dE")]
+
+
+class TrackColumns(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("x_start", "x_end", "y_start", "y_end", "n_electrons", "long_diff", "tran_diff",
+                                         "pixel_plane", "t", "t_start", "t_end")]
+
+
+class CurrentColumns(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("ncols", "x", "y", "z", "long_diff", "n_electrons", "pixel_plane")]
 
 
 class ParamsPOD(C.Structure):
@@ -160,6 +169,18 @@ def _declare(lib):
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]
     lib.larnd_chop_count.restype = C.c_int
     lib.larnd_chop_tracks.restype = C.c_int
+    lib.larnd_tracks_stage.argtypes = [vp, i64, PC, C.POINTER(TrackColumns), PP, i32, vp, vp]
+    lib.larnd_signals_stream_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, vp, vp]
+    lib.larnd_signals_stream_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, i64,
+                                                  vp, vp, vp, vp, vp, vp, vp]
+    PCU = C.POINTER(CurrentColumns)
+    lib.larnd_current_mc.argtypes = [vp, i64, PCU, vp, PP, vp, vp, vp]
+    lib.larnd_current_mc_backward.argtypes = [vp, i64, PCU, vp, PP, vp, vp, vp, vp]
+    lib.larnd_accumulate_parametrized.argtypes = [vp, i32, i32, vp, i32, vp, vp, i64, vp]
+    lib.larnd_accumulate_parametrized_backward.argtypes = [vp, i32, i32, vp, i32, vp, vp, i64, vp]
+    for name in ("larnd_tracks_stage", "larnd_signals_stream_forward", "larnd_signals_stream_backward", "larnd_current_mc",
+                 "larnd_current_mc_backward", "larnd_accumulate_parametrized", "larnd_accumulate_parametrized_backward"):
+        getattr(lib, name).restype = C.c_int
     if hasattr(lib, "larnd_mc_forward"):
         lib.larnd_mc_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, vp, vp]
         lib.larnd_mc_backward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, i64, vp, vp]

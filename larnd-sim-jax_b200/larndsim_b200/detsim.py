@@ -237,3 +237,7 @@ def apply_tran_diff(params, electrons, fields):
         raise TypeError("params.tran_diff_bin_edges is None: the non-MC transverse split is unusable in the reference as well "
                         "(every parametrized script passes --mc_diff)")
     raise NotImplementedError("apply_tran_diff with explicit bin edges is not part of the accelerated path")
+
+
+# stage-by-stage MC-current operators with the reference's argument lists (detsim_jax.py:619-639, 209-228)
+from .stream_ops import accumulate_signals_parametrized, current_mc  # noqa: E402,F401

@@ -362,6 +362,10 @@ def record_fields(st):
     return out
 
 
+# stage-by-stage operators with the reference's argument lists (sim_jax.py:142-286, 120-139, 289-335)
+from .stream_ops import simulate_drift, simulate_signals, simulate_signals_parametrized  # noqa: E402,F401
+
+
 # ------------------------------------------------------------------------------------------ front end
 class FeeState:
     __slots__ = ("adc", "ticks", "pixel_z", "pixel_x", "pixel_y", "event", "saved", "hits", "n_valid", "npix", "pod")
