@@ -17,6 +17,8 @@
 // Work whose only effect is on garbage rows is skipped: their upstream gradient is zero, checked on the device by
 // k_garbage_grad_flag.  If it is NOT zero, or for segments whose window ends beyond the readout, accumulate_bwd.cu's
 // kernel does the work instead (device-side switch, no host synchronisation).
+#include <stdlib.h>
+
 #include "bwd_chain.cuh"
 #include "sorted_runs.cuh"
 
@@ -90,8 +92,8 @@ __device__ __forceinline__ float reduce8_to_lane_s(const float (&v)[8], int lane
 // One unit of one tile: every run p of `todo` (bit mask of runs whose target row exists) is correlated with the unit's
 // response rows Rw and its segments update the shared accumulators.  NR = 3: main pixel (3-template blend, group gi/gj);
 // NR = 1: neighbour pixel (template 0, full charge).
-template <int NS, int NR, int NPOS>
-__device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
+template <int NS, int NR, int NPOS, int KP>
+__device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                            const float* __restrict__ crow, int gi, int gj, int lane, int warp) {
   const SortArgs& S = A.S;
   const int nt = S.nt, L = S.L, nticks = S.nticks;
@@ -195,33 +197,35 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   }
 }
 
-template <int NS, int NR>
-__device__ __forceinline__ void unit_pairs_npos(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
+template <int NS, int NR, int KP>
+__device__ __forceinline__ void unit_pairs_npos(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                                 const float* crow, int gi, int gj, int lane, int warp, int npos) {
   if (npos <= 3) {
-    if (npos == 2) unit_pairs<NS, NR, 2>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-    else unit_pairs<NS, NR, 3>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-  } else if (npos == 4) unit_pairs<NS, NR, 4>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-  else if (npos == 5) unit_pairs<NS, NR, 5>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-  else unit_pairs<NS, NR, KPT>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+    if (npos == 2) unit_pairs<NS, NR, 2, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+    else unit_pairs<NS, NR, 3, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  } else if (KP == 4 || npos == 4) unit_pairs<NS, NR, 4, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  else if (npos == 5) unit_pairs<NS, NR, KP >= 5 ? 5 : KP, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  else unit_pairs<NS, NR, KP, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
 }
 
-template <int NS, int NR>
-__device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KPT], const float* const (&rows)[NR], int Lp, int lane) {
+template <int NS, int NR, int KP>
+__device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const float* const (&rows)[NR], int Lp, int lane) {
 #pragma unroll
   for (int r = 0; r < NR; ++r)
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
+      for (int j = 0; j < KP; ++j) {
         const int ix = 32 * s + lane + 1 - j;  // sample k = x - 1 - j lives at row[k + 2]
         Rw[r][s][j] = ((unsigned)ix < (unsigned)Lp) ? __ldg(rows[r] + ix) : 0.0f;
       }
 }
 
-template <int NS>
-__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? 2 : 1)
-k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p) {
+// KP / part as in k_acc_tiles: the KP = KPT_SMALL kernel (48 response registers, 3 CTAs per SM) serves the tiles of runs with
+// <= KPT_SMALL impulse positions (part 1: tiles [0, split)), the KP = KPT kernel the rest (part 2) or everything (part 0).
+template <int NS, int KP>
+__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP < KPT ? 3 : 2) : 1)
+k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdTileSmem& sm = *reinterpret_cast<BwdTileSmem*>(smem_raw);
   const SortArgs& S = A.S;
@@ -242,18 +246,21 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
     sm.udx[u] = (signed char)(u / S.P - S.n_neigh);
     sm.udy[u] = (signed char)(u % S.P - S.n_neigh);
   }
-  const int ntiles = dead ? 0 : S.gcnt[1];
+  const int tile_lo = part == 2 ? S.gcnt[4] : 0;
+  const int ntiles = dead ? 0 : (part == 1 ? S.gcnt[4] : S.gcnt[1]);
+  int* const tile_counter = S.gcnt + (part == 2 ? 6 : 3);
   const int n_units = 25 + S.P * S.P;
 
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) { sm.tile = atomicAdd(S.gcnt + 3, 1); sm.next_unit = 0; }
+    if (threadIdx.x == 0) { sm.tile = tile_lo + atomicAdd(tile_counter, 1); sm.next_unit = 0; }
     __syncthreads();
     const int tile = sm.tile;
     if (tile >= ntiles) break;
     const int4 ti = S.tile_info[tile];
     const int cls = ti.x, count = ti.z;
-    const int span = cls % (SPAN_MAX_S + 1), cls_b = cls / (SPAN_MAX_S + 1);
+    const int ncb = S.ncls / (SPAN_MAX_S + 1);
+    const int span = cls / ncb, cls_b = cls % ncb;  // class = span * (ntpl * nb * nb) + (idx * nb + bxm) * nb + bym
     const int bym = cls_b % nb, bxm = (cls_b / nb) % nb, idx = cls_b / (nb * nb);
     const int npos = span + 2;
     // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
@@ -322,7 +329,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
       if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);
       unit = __shfl_sync(0xffffffffu, unit, 0);
       if (unit >= n_units) break;
-      float Rw[3][NS][KPT];
+      float Rw[3][NS][KP];
       if (unit < 25) {
         // ---------------- merged diffusion-bin group (gi, gj): 3-template blend on a main pixel ----------------
         const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
@@ -339,8 +346,8 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         if (todo == 0u) continue;
         const float* const rows[3] = {S.rm + (int64_t)((idx - 1) * 25 + bin) * S.Lp, S.rm + (int64_t)(idx * 25 + bin) * S.Lp,
                                       S.rm + (int64_t)((idx + 1) * 25 + bin) * S.Lp};
-        load_response_b<NS, 3>(Rw, rows, S.Lp, lane);
-        unit_pairs_npos<NS, 3>(sm, A, Rw, todo, row, S.cm + (int64_t)(idx * 25 + bin) * S.nt, gi, gj, lane, warp, npos);
+        load_response_b<NS, 3, KP>(Rw, rows, S.Lp, lane);
+        unit_pairs_npos<NS, 3, KP>(sm, A, Rw, todo, row, S.cm + (int64_t)(idx * 25 + bin) * S.nt, gi, gj, lane, warp, npos);
       } else {
         // ---------------- neighbour pixels that own a non-garbage waveform row: template 0, full charge -----------
         const int u = unit - 25;
@@ -357,8 +364,8 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         const int vx = 2 * bxm - S.half2 - 2 * nb * dx, vy = 2 * bym - S.half2 - 2 * nb * dy;
         const int bin = (abs(vx) >> 1) * S.ny_lut + (abs(vy) >> 1);
         const float* const rows[1] = {S.r0 + (int64_t)bin * S.Lp};
-        load_response_b<NS, 1>(Rw, rows, S.Lp, lane);
-        unit_pairs_npos<NS, 1>(sm, A, Rw, todo, row, S.c0 + (int64_t)bin * S.nt, 0, 0, lane, warp, npos);
+        load_response_b<NS, 1, KP>(Rw, rows, S.Lp, lane);
+        unit_pairs_npos<NS, 1, KP>(sm, A, Rw, todo, row, S.c0 + (int64_t)bin * S.nt, 0, 0, lane, warp, npos);
       }
     }
     __syncthreads();
@@ -414,17 +421,32 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
   const size_t smem = sizeof(BwdTileSmem);
   static bool attr_done = false;
   if (!attr_done) {
-    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<5, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<6, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, KPT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int grid = sorted_grid(2, LARND_BWD_SORTED_SLOTS);
   const int need = lut->L + 2 + SPAN_MAX_S;
-  if (need <= 32 * 4) k_bwd_tiles<4><<<grid, BT_THREADS, smem, st>>>(A, p);
-  else if (need <= 32 * 5) k_bwd_tiles<5><<<grid, BT_THREADS, smem, st>>>(A, p);
-  else k_bwd_tiles<6><<<grid, BT_THREADS, smem, st>>>(A, p);
+  static int kp4_mode = -1;  // LARND_BWD_KP4=0: one kernel for all tiles
+  if (kp4_mode < 0) {
+    const char* e = getenv("LARND_BWD_KP4");
+    kp4_mode = e ? atoi(e) : 1;
+  }
+  const bool split = need <= 32 * 4 && kp4_mode != 0;
+  const int grid2 = sorted_grid(2, LARND_BWD_SORTED_SLOTS / 2);
+  const int grid3 = split ? sorted_grid(3, LARND_BWD_SORTED_SLOTS / 2) : 0;
+  // the two kernels write disjoint slots of the per-CTA partial table: [0, grid3) and [grid3, grid3 + grid2)
+  if (split) {
+    k_bwd_tiles<4, KPT_SMALL><<<grid3, BT_THREADS, smem, st>>>(A, p, 1);
+    LARND_LAUNCH_CHECK("k_bwd_tiles<small>");
+    A.partials = sorted_partials + (int64_t)grid3 * 16;
+  }
+  const int part = split ? 2 : 0;
+  if (need <= 32 * 4) k_bwd_tiles<4, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, part);
+  else if (need <= 32 * 5) k_bwd_tiles<5, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, part);
+  else k_bwd_tiles<6, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, part);
   LARND_LAUNCH_CHECK("k_bwd_tiles");
-  *n_slots_out = grid;
+  *n_slots_out = grid2 + grid3;
   return LARND_OK;
 }

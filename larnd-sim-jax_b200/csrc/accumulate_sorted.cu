@@ -20,6 +20,8 @@
 //
 // Segments whose window touches the ends of the readout (garbage tick 0 handling, sim_jax.py:177-178,243-244)
 // are left to accumulate.cu's per-segment path (larnd_launch_accumulate with mode = slow-only).
+#include <stdlib.h>
+
 #include "sorted_runs.cuh"
 
 namespace {
@@ -45,14 +47,14 @@ struct TileSmem {
   int low_end;  // some run of the tile starts below tick 2 (its windows need the garbage-column handling)
 };
 
-template <int NS, int NR>
-__device__ __forceinline__ void load_response(float (&Rw)[3][NS][KPT], const float* const (&rows)[NR], int Lp, int lane) {
+template <int NS, int NR, int KP>
+__device__ __forceinline__ void load_response(float (&Rw)[3][NS][KP], const float* const (&rows)[NR], int Lp, int lane) {
 #pragma unroll
   for (int r = 0; r < NR; ++r)
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
+      for (int j = 0; j < KP; ++j) {
         const int ix = 32 * s + lane + 1 - j;  // sample k = x - 1 - j lives at row[k + 2]
         Rw[r][s][j] = ((unsigned)ix < (unsigned)Lp) ? __ldg(rows[r] + ix) : 0.0f;
       }
@@ -128,8 +130,8 @@ __device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, fl
 // Consume loop of one unit: every run of `todo` gets its window computed from the register-resident response and flushed.
 // Two runs are in flight per iteration (independent FFMA chains hide the 4-cycle dependency latency) and the number of
 // impulse positions is a compile-time constant (uniform per tile: the class key contains the tick span).
-template <int NS, int NR, int NPOS, bool LP>
-__device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
+template <int NS, int NR, int NPOS, bool LP, int KP, bool TWO>
+__device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                               const float* __restrict__ hbuf, int hstride, const float* __restrict__ Ebuf,
                                               float* __restrict__ row0, int mode /* 0 own row, 1 sum row -> row0, 2 own row and -row0 */,
                                               int lane) {
@@ -145,7 +147,7 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
   while (todo) {
     const int p0 = __ffs(todo) - 1;
     todo &= todo - 1;
-    const bool two = NR == 3 && todo != 0u;  // neighbour units (one template, dual flush) run one window at a time: measured faster
+    const bool two = TWO && NR == 3 && todo != 0u;  // neighbour units (one template, dual flush) run one window at a time: measured faster
     const int p1 = two ? __ffs(todo) - 1 : p0;
     if (two) todo &= todo - 1;
     float* const d0 = base + (__shfl_sync(0xffffffffu, myoff, p0) + lane);
@@ -180,20 +182,24 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
   }
 }
 
-template <int NS, int NR, bool LP>
-__device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KPT], unsigned todo, int row,
+template <int NS, int NR, bool LP, int KP, bool TWO>
+__device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                                    const float* hbuf, int hstride, const float* Ebuf, float* row0, int mode, int lane, int npos) {
   if (npos <= 3) {
-    if (npos == 2) consume_pairs<NS, NR, 2, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-    else consume_pairs<NS, NR, 3, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  } else if (npos == 4) consume_pairs<NS, NR, 4, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else if (npos == 5) consume_pairs<NS, NR, 5, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else consume_pairs<NS, NR, KPT, LP>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+    if (npos == 2) consume_pairs<NS, NR, 2, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+    else consume_pairs<NS, NR, 3, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  } else if (KP == 4 || npos == 4) consume_pairs<NS, NR, 4, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else if (npos == 5) consume_pairs<NS, NR, KP >= 5 ? 5 : KP, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else consume_pairs<NS, NR, KP, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
 }
 
-template <int NS, bool LP>
-__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? 2 : 1)
-k_acc_tiles(const __grid_constant__ SortArgs A) {
+// KP = impulse positions whose response samples are held in registers: the KP = KPT kernel serves every tile; with
+// KP = KPT_SMALL the response needs 48 instead of 72 registers, three CTAs fit on an SM (24 instead of 16 warps to hide
+// the latencies the kernel is bound by) and the kernel serves the tiles of runs with <= KPT_SMALL positions, a prefix of
+// the tile table (span-major class key).  part: 0 all tiles, 1 tiles [0, split), 2 tiles [split, ntiles).
+template <int NS, bool LP, int KP, bool TWO>
+__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? (KP < KPT ? 3 : 2) : 1)
+k_acc_tiles(const __grid_constant__ SortArgs A, const int part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
   if (A.counts[2] != 0) return;
@@ -210,7 +216,9 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
     sm.udx[u] = (signed char)(u / A.P - A.n_neigh);
     sm.udy[u] = (signed char)(u % A.P - A.n_neigh);
   }
-  const int ntiles = A.gcnt[1];
+  const int tile_lo = part == 2 ? A.gcnt[4] : 0;
+  const int ntiles = part == 1 ? A.gcnt[4] : A.gcnt[1];
+  int* const tile_counter = A.gcnt + (part == 2 ? 5 : 2);
   const int n_neigh_units = A.P * A.P;
   const int n_units = 25 + 1 + n_neigh_units;  // merged diffusion groups, neighbourhood-sum row, neighbour pixels
   float* myh = sm.ph[warp];
@@ -222,14 +230,15 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
 
   for (;;) {
     __syncthreads();  // everybody is done with the previous tile
-    if (threadIdx.x == 0) { sm.tile = atomicAdd(A.gcnt + 2, 1); sm.next_unit = 0; }
+    if (threadIdx.x == 0) { sm.tile = tile_lo + atomicAdd(tile_counter, 1); sm.next_unit = 0; }
     __syncthreads();
     const int tile = sm.tile;
     if (tile >= ntiles) break;
     const int4 ti = A.tile_info[tile];
     const int cls = ti.x, count = ti.z;
-    const int cls_b = cls / (SPAN_MAX_S + 1);  // class = ((idx * nb + bxm) * nb + bym) * (SPAN_MAX_S + 1) + span
-    const int npos = cls % (SPAN_MAX_S + 1) + 2;  // impulse positions of every run of this tile
+    const int ncb = A.ncls / (SPAN_MAX_S + 1);
+    const int cls_b = cls % ncb;     // class = span * (ntpl * nb * nb) + (idx * nb + bxm) * nb + bym
+    const int npos = cls / ncb + 2;  // impulse positions of every run of this tile
     const int bym = cls_b % nb, bxm = (cls_b / nb) % nb, idx = cls_b / (nb * nb);
     // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
     if (warp == 0) {
@@ -311,7 +320,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
       if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);
       unit = __shfl_sync(0xffffffffu, unit, 0);
       if (unit >= n_units) break;
-      float Rw[3][NS][KPT];
+      float Rw[3][NS][KP];
       if (unit < 25) {
         // ---------------- merged diffusion-bin group (gi, gj): 3-template blend on a main pixel ----------------
         const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
@@ -360,9 +369,9 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         __syncwarp();
         const float* const rows[3] = {A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp, A.rm + (int64_t)(idx * 25 + bin) * A.Lp,
                                       A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp};
-        load_response<NS, 3>(Rw, rows, A.Lp, lane);
+        load_response<NS, 3, KP>(Rw, rows, A.Lp, lane);
         // consume: lane <-> tick
-        consume_pairs_npos<NS, 3, LP>(A, sm, Rw, __ballot_sync(0xffffffffu, row >= 0), row, myh, HS, myE, row0, 0, lane, npos);
+        consume_pairs_npos<NS, 3, LP, KP, TWO>(A, sm, Rw, __ballot_sync(0xffffffffu, row >= 0), row, myh, HS, myE, row0, 0, lane, npos);
         __syncwarp();
       } else {
         // ---------------- neighbour pixels: template 0, full segment charge (sim_jax.py:197-225,250-261) ----------
@@ -424,9 +433,9 @@ k_acc_tiles(const __grid_constant__ SortArgs A) {
         }
         __syncwarp();
         const float* const rows[1] = {rowp0};
-        load_response<NS, 1>(Rw, rows, A.Lp, lane);
+        load_response<NS, 1, KP>(Rw, rows, A.Lp, lane);
         const bool dual = !sum_unit && !A.skip_garbage;
-        consume_pairs_npos<NS, 1, LP>(A, sm, Rw, owned, row, &sm.hN[0][0], KPT, myE, row0, sum_unit ? 1 : (dual ? 2 : 0), lane, npos);
+        consume_pairs_npos<NS, 1, LP, KP, TWO>(A, sm, Rw, owned, row, &sm.hN[0][0], KPT, myE, row0, sum_unit ? 1 : (dual ? 2 : 0), lane, npos);
         __syncwarp();
       }
     }
@@ -491,29 +500,47 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     if (rc0) return rc0;
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
+  const int ns = need <= 32 * 4 ? 4 : (need <= 32 * 5 ? 5 : 6);
+  // LARND_ACC_KP4: 0 = one kernel holding KPT positions for all tiles; 1 / 2 = tiles of runs with <= KPT_SMALL positions go
+  // to the 3-CTAs-per-SM kernel (1: two windows in flight for the main units, 2: one), the rest to the KPT kernel
+  static int kp4_mode = -1;
+  if (kp4_mode < 0) {
+    const char* e = getenv("LARND_ACC_KP4");
+    kp4_mode = e ? atoi(e) : 1;
+  }
+  const int split = (ns == 4) ? kp4_mode : 0;
   const int grid = sorted_grid(2, LARND_ROW0_COPIES);
-  if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)grid * p.n_ticks * sizeof(float), st));
+  const int grid_small = split ? sorted_grid(3, LARND_ROW0_COPIES) : 0;
+  const int ncopies = grid > grid_small ? grid : grid_small;
+  if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)ncopies * p.n_ticks * sizeof(float), st));
   const size_t smem = sizeof(TileSmem);
   static bool attr_done = false;
   if (!attr_done) {
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, true, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, true, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, KPT_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, KPT_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   // LP: for every number of impulse positions (2 .. KPT) the run window L + NPOS ends inside the last 32-tick slot, so
   // all other slots are flushed without a predicate
-  const int ns = need <= 32 * 4 ? 4 : (need <= 32 * 5 ? 5 : 6);
   const bool lp = lut->L + 2 >= 32 * (ns - 1) && lut->L + KPT < 32 * ns;
-  if (ns == 4) { if (lp) k_acc_tiles<4, true><<<grid, TILE_THREADS, smem, st>>>(A); else k_acc_tiles<4, false><<<grid, TILE_THREADS, smem, st>>>(A); }
-  else if (ns == 5) { if (lp) k_acc_tiles<5, true><<<grid, TILE_THREADS, smem, st>>>(A); else k_acc_tiles<5, false><<<grid, TILE_THREADS, smem, st>>>(A); }
-  else { if (lp) k_acc_tiles<6, true><<<grid, TILE_THREADS, smem, st>>>(A); else k_acc_tiles<6, false><<<grid, TILE_THREADS, smem, st>>>(A); }
+  if (split == 1) { if (lp) k_acc_tiles<4, true, KPT_SMALL, true><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); else k_acc_tiles<4, false, KPT_SMALL, true><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); }
+  else if (split) { if (lp) k_acc_tiles<4, true, KPT_SMALL, false><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); else k_acc_tiles<4, false, KPT_SMALL, false><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); }
+  if (split) LARND_LAUNCH_CHECK("k_acc_tiles<small>");
+  const int part = split ? 2 : 0;
+  if (ns == 4) { if (lp) k_acc_tiles<4, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); else k_acc_tiles<4, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); }
+  else if (ns == 5) { if (lp) k_acc_tiles<5, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); else k_acc_tiles<5, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); }
+  else { if (lp) k_acc_tiles<6, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); else k_acc_tiles<6, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); }
   LARND_LAUNCH_CHECK("k_acc_tiles");
   if (!A.skip_garbage) {
-    k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, grid, p.n_ticks, wfs);
+    k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, ncopies, p.n_ticks, wfs);
     LARND_LAUNCH_CHECK("k_reduce_row0");
   }
   // segments whose window touches the ends of the readout: per-segment path of accumulate.cu

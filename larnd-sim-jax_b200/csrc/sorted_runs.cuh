@@ -13,6 +13,7 @@ namespace {
 constexpr int TR = 32;              // runs per tile (lane <-> run in the build phases)
 constexpr int KPT = 6;              // impulse positions per run
 constexpr int SPAN_MAX_S = KPT - 2;  // max (T0max - T0min) inside a run
+constexpr int KPT_SMALL = 4;        // runs with <= KPT_SMALL positions (span <= 2) can be served by a kernel holding fewer response registers
 constexpr int MAXLEN = 8;           // segments per run (bounds the divergence of the lane <-> run build loops)
 constexpr int TILE_THREADS = 256;
 constexpr int NW = TILE_THREADS / 32;
@@ -45,7 +46,8 @@ struct SortArgs {
   int* class_start;
   int* cursor;
   int4* tile_info;
-  int* gcnt;  // [0] number of runs, [1] number of tiles, [2] tile counter
+  int* gcnt;  // [0] number of runs, [1] number of tiles, [2] forward tile counter, [3] backward tile counter,
+              // [4] first tile of a class with span > KPT_SMALL - 2, [5] forward tile counter of the large-span kernel
   int ncls;
   float* row0;  // [gridDim][nticks] per-CTA private copies of waveform row 0 (the garbage row every CTA adds to)
 };
@@ -120,7 +122,8 @@ k_build_runs(const __grid_constant__ SortArgs A) {
     }
     const int nb = A.nb;
     const int bxm = s_bx[t] - floordiv_i(s_bx[t], nb) * nb, bym = s_by[t] - floordiv_i(s_by[t], nb) * nb;
-    const int cls = ((s_idx[t] * nb + bxm) * nb + bym) * (SPAN_MAX_S + 1) + (tmax - tmin);
+    // span-major key: the tiles of runs with few impulse positions (span <= KPT_SMALL - 2) form a prefix of the tile table
+    const int cls = (tmax - tmin) * (A.ncls / (SPAN_MAX_S + 1)) + (s_idx[t] * nb + bxm) * nb + bym;
     A.runs_tmp[s_base + before] = make_int4((int)(base + t), len | ((tmax - tmin) << 16), tmin, cls);
     atomicAdd(A.class_count + cls, 1);
   }
@@ -164,6 +167,7 @@ k_class_scan(const __grid_constant__ SortArgs A) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) ex[k] = carry[k] + (wid > 0 ? s_w[k][wid - 1] : 0) + inc[k] - v[k];
     if (c < A.ncls) {
+      if (c == (KPT_SMALL - 1) * (A.ncls / (SPAN_MAX_S + 1))) A.gcnt[4] = ex[1];
       A.class_start[c] = ex[0];
       A.cursor[c] = ex[0];
       for (int i = 0; i < v[1]; ++i)  // tiles of this class
@@ -212,7 +216,7 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   A.ncls = lut->ntpl * A.nb * A.nb * (SPAN_MAX_S + 1);
   A.row0 = ws.row0;
   LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * sizeof(int), st));
-  LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 16, st));
+  LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 32, st));
   const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
   k_build_runs<<<(unsigned)chunks, LARND_CHUNK, 0, st>>>(A);
   LARND_LAUNCH_CHECK("k_build_runs");

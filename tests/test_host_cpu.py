@@ -170,6 +170,36 @@ def test_cpu_tensors_are_rejected():
         sim.simulate_wfs(cm.product_params(), torch.zeros(3, 5, 5, 10), torch.zeros(4, 26), cm.FIELDS)
 
 
+def test_stage_operators_reject_cpu_tensors_and_bad_arguments(lib):
+    """The stage-by-stage operators (quench, drift, simulate_signals, current_mc, accumulate_signals_parametrized) have no
+    CPU path either, and their C entry points validate arguments before touching the device."""
+    import torch
+    from larndsim_b200 import LarndError, _lib, detsim, drifting, quenching, sim
+    pp = cm.product_params(number_pix_neighbors=0)
+    tr = torch.zeros(4, len(cm.FIELDS))
+    for fn in (quenching.quench, drifting.drift):
+        with pytest.raises(LarndError):
+            fn(pp, tr, cm.FIELDS)
+    with pytest.raises(LarndError):
+        detsim.current_mc(pp, tr, torch.zeros(4, 2), cm.FIELDS)
+    with pytest.raises(LarndError):
+        detsim.accumulate_signals_parametrized(torch.zeros(3, 2001), torch.zeros(4, 51), torch.zeros(4, dtype=torch.int32),
+                                               torch.zeros(4, dtype=torch.int32))
+    with pytest.raises(LarndError):
+        z = torch.zeros(4)
+        sim.simulate_signals(pp, torch.zeros(3, dtype=torch.int32), z, z, torch.zeros(3, 5, 5, 10), z, z, z, z, z, z, z)
+    pod, cols = sim.make_pod(pp), sim.make_columns(cm.FIELDS)
+    assert lib.larnd_tracks_stage(None, 5, ctypes.byref(cols), None, ctypes.byref(pod), 7, None, None) == -1
+    assert lib.larnd_current_mc(None, 5, None, None, ctypes.byref(pod), None, None, None) == -1
+    assert lib.larnd_accumulate_parametrized(None, 3, 2001, None, 51, None, None, 4, None) == -1
+    assert lib.larnd_signals_stream_forward(None, 0, None, None, None, None, None, 0, None, None, None, None, 0, ctypes.byref(pod), None,
+                                            None, None, None) == -1
+    assert b"larnd_signals_stream" in lib.larnd_last_error()
+    # column tables name every column the stages touch
+    oc = _lib.TrackColumns()
+    assert {n for n, _ in oc._fields_} <= set(cm.FIELDS)
+
+
 def test_event_partition_is_balanced_and_complete():
     from larndsim_b200 import parallel
     rng = np.random.default_rng(0)
