@@ -384,14 +384,16 @@ def run_ours(args):
         # the same capture, against the reduction throughput a pure flush kernel reaches with the same access pattern and
         # an L2-resident target (scripts/ubench_red.cu pattern A, profiles/r1b_ubench_red.txt)
         traffic, l2_red = None, None
-        for tname in ("r1b_traffic_10M.json", "r1_traffic_10M.json"):
+        for tname in ("r1d_traffic_10M.json", "r1b_traffic_10M.json", "r1_traffic_10M.json"):
             try:
                 with open(os.path.join(ROOT, "profiles", tname)) as fh:
                     tj = json.load(fh)
-                ent = tj["k_acc_tiles<4>"][0]
-                traffic = float(ent["dram_bytes"]) * nseg / 10010184.0
-                if ent.get("l2_red_sectors"):
-                    red_bytes = float(ent["l2_red_sectors"]) * 32.0 * nseg / 10010184.0
+                # one forward pass launches k_acc_tiles once per kernel variant (4-position and 6-position tiles): sum them
+                ents = tj.get("k_acc_tiles") or tj["k_acc_tiles<4>"]
+                traffic = sum(float(e["dram_bytes"]) for e in ents) * nseg / 10010184.0
+                sectors = sum(float(e.get("l2_red_sectors") or 0.0) for e in ents)
+                if sectors:
+                    red_bytes = sectors * 32.0 * nseg / 10010184.0
                     red_peak = 5170.0
                     l2_red = {"achieved": red_bytes / (k_ms[1] * 1e-3) / 1e9, "peak": red_peak, "unit": "GB/s",
                               "frac": red_bytes / (k_ms[1] * 1e-3) / 1e9 / red_peak, "bytes_per_launch": red_bytes,
@@ -419,9 +421,9 @@ def run_ours(args):
                         "note": "un-chopped tracks uploaded, chop_tracks on the device (csrc/chop.cu)"},
             "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": total_seg / (ms_fg * 1e-3), "unit": "segments/s",
                          "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none"},
-            "gpu_launches": int(args.steps * 14),  # prepare 1 + unique/scan 4 + sorted accumulate 6 + FEE/compaction 3
+            "gpu_launches": int(args.steps * 15),  # prepare 1 + unique/scan 4 + sorted accumulate 7 (run sort 3, tiles 2, row 0, boundary) + FEE/compaction 3
             "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
-            "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate incl. run sort)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate: run sort + the 4- and 6-position tile kernels + row-0 reduction)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_segment": b_seg,
                          "note": "accumulate is bound by instruction issue and L2 reduction throughput, not HBM (SURVEY §8d): "

@@ -17,8 +17,6 @@
 // Work whose only effect is on garbage rows is skipped: their upstream gradient is zero, checked on the device by
 // k_garbage_grad_flag.  If it is NOT zero, or for segments whose window ends beyond the readout, accumulate_bwd.cu's
 // kernel does the work instead (device-side switch, no host synchronisation).
-#include <stdlib.h>
-
 #include "bwd_chain.cuh"
 #include "sorted_runs.cuh"
 
@@ -200,12 +198,12 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
 template <int NS, int NR, int KP>
 __device__ __forceinline__ void unit_pairs_npos(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                                 const float* crow, int gi, int gj, int lane, int warp, int npos) {
-  if (npos <= 3) {
-    if (npos == 2) unit_pairs<NS, NR, 2, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-    else unit_pairs<NS, NR, 3, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-  } else if (KP == 4 || npos == 4) unit_pairs<NS, NR, 4, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-  else if (npos == 5) unit_pairs<NS, NR, KP >= 5 ? 5 : KP, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
-  else unit_pairs<NS, NR, KP, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  constexpr int N3 = KP >= 3 ? 3 : KP, N4 = KP >= 4 ? 4 : KP, N5 = KP >= 5 ? 5 : KP;
+  if (KP >= 6 && npos >= 6) unit_pairs<NS, NR, KP, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  else if (KP >= 5 && npos == 5) unit_pairs<NS, NR, N5, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  else if (KP >= 4 && npos == 4) unit_pairs<NS, NR, N4, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  else if (KP >= 3 && npos == 3) unit_pairs<NS, NR, N3, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
+  else unit_pairs<NS, NR, 2, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
 }
 
 template <int NS, int NR, int KP>
@@ -221,11 +219,12 @@ __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const fl
       }
 }
 
-// KP / part as in k_acc_tiles: the KP = KPT_SMALL kernel (48 response registers, 3 CTAs per SM) serves the tiles of runs with
-// <= KPT_SMALL impulse positions (part 1: tiles [0, split)), the KP = KPT kernel the rest (part 2) or everything (part 0).
+// KP / span range / launch as in k_acc_tiles: the variants holding 3 / 4 response positions (36 / 48 registers, 4 / 3 CTAs
+// per SM) serve the tiles of runs with few impulse positions, the KP = KPT kernel the rest (or everything).
 template <int NS, int KP>
-__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP < KPT ? 3 : 2) : 1)
-k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int part) {
+__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : 1)
+k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int span_lo, const int span_hi,
+            const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdTileSmem& sm = *reinterpret_cast<BwdTileSmem*>(smem_raw);
   const SortArgs& S = A.S;
@@ -246,9 +245,9 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
     sm.udx[u] = (signed char)(u / S.P - S.n_neigh);
     sm.udy[u] = (signed char)(u % S.P - S.n_neigh);
   }
-  const int tile_lo = part == 2 ? S.gcnt[4] : 0;
-  const int ntiles = dead ? 0 : (part == 1 ? S.gcnt[4] : S.gcnt[1]);
-  int* const tile_counter = S.gcnt + (part == 2 ? 6 : 3);
+  const int tile_lo = S.gcnt[GC_SPAN + span_lo];
+  const int ntiles = dead ? 0 : S.gcnt[GC_SPAN + span_hi + 1];
+  int* const tile_counter = S.gcnt + GC_BWD + launch;
   const int n_units = 25 + S.P * S.P;
 
   for (;;) {
@@ -424,29 +423,34 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
     LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<5, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<6, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, KPT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
-  static int kp4_mode = -1;  // LARND_BWD_KP4=0: one kernel for all tiles
-  if (kp4_mode < 0) {
-    const char* e = getenv("LARND_BWD_KP4");
-    kp4_mode = e ? atoi(e) : 1;
+  const int split = need <= 32 * 4 ? sorted_split_mode() : 0;
+  const int cap = LARND_BWD_SORTED_SLOTS / 3;
+  const int grid2 = sorted_grid(2, cap);
+  const int grid3 = split >= 1 ? sorted_grid(3, cap) : 0;
+  const int grid4 = split >= 2 ? sorted_grid(4, cap) : 0;
+  // the kernels write disjoint slots of the per-CTA partial table
+  int big_lo = 0;
+  if (split >= 2) {
+    k_bwd_tiles<4, 3><<<grid4, BT_THREADS, smem, st>>>(A, p, 0, 1, 0);
+    LARND_LAUNCH_CHECK("k_bwd_tiles<3>");
+    A.partials += (int64_t)grid4 * 16;
+    big_lo = 2;
   }
-  const bool split = need <= 32 * 4 && kp4_mode != 0;
-  const int grid2 = sorted_grid(2, LARND_BWD_SORTED_SLOTS / 2);
-  const int grid3 = split ? sorted_grid(3, LARND_BWD_SORTED_SLOTS / 2) : 0;
-  // the two kernels write disjoint slots of the per-CTA partial table: [0, grid3) and [grid3, grid3 + grid2)
-  if (split) {
-    k_bwd_tiles<4, KPT_SMALL><<<grid3, BT_THREADS, smem, st>>>(A, p, 1);
-    LARND_LAUNCH_CHECK("k_bwd_tiles<small>");
-    A.partials = sorted_partials + (int64_t)grid3 * 16;
+  if (split >= 1) {
+    k_bwd_tiles<4, 4><<<grid3, BT_THREADS, smem, st>>>(A, p, big_lo, 2, 1);
+    LARND_LAUNCH_CHECK("k_bwd_tiles<4>");
+    A.partials += (int64_t)grid3 * 16;
+    big_lo = 3;
   }
-  const int part = split ? 2 : 0;
-  if (need <= 32 * 4) k_bwd_tiles<4, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, part);
-  else if (need <= 32 * 5) k_bwd_tiles<5, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, part);
-  else k_bwd_tiles<6, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, part);
+  if (need <= 32 * 4) k_bwd_tiles<4, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, big_lo, SPAN_MAX_S, 2);
+  else if (need <= 32 * 5) k_bwd_tiles<5, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, 0, SPAN_MAX_S, 2);
+  else k_bwd_tiles<6, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, 0, SPAN_MAX_S, 2);
   LARND_LAUNCH_CHECK("k_bwd_tiles");
-  *n_slots_out = grid2 + grid3;
+  *n_slots_out = grid2 + grid3 + grid4;
   return LARND_OK;
 }

@@ -20,8 +20,6 @@
 //
 // Segments whose window touches the ends of the readout (garbage tick 0 handling, sim_jax.py:177-178,243-244)
 // are left to accumulate.cu's per-segment path (larnd_launch_accumulate with mode = slow-only).
-#include <stdlib.h>
-
 #include "sorted_runs.cuh"
 
 namespace {
@@ -58,32 +56,6 @@ __device__ __forceinline__ void load_response(float (&Rw)[3][NS][KP], const floa
         const int ix = 32 * s + lane + 1 - j;  // sample k = x - 1 - j lives at row[k + 2]
         Rw[r][s][j] = ((unsigned)ix < (unsigned)Lp) ? __ldg(rows[r] + ix) : 0.0f;
       }
-}
-
-// acc[x] += sum_{j < NPOS} sum_r h[j*NR + r] * R_r[x - 1 - j]: pure FFMAs on the register-resident response
-template <int NS, int NR, int NPOS>
-__device__ __forceinline__ void conv_fixed(float (&acc)[NS], const float (&Rw)[3][NS][KPT], const float* __restrict__ h) {
-#pragma unroll
-  for (int j = 0; j < NPOS; ++j) {
-    float hv[NR];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) hv[r] = h[NR * j + r];
-#pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-      for (int r = 0; r < NR; ++r) acc[s] = fmaf(hv[r], Rw[r][s][j], acc[s]);
-  }
-}
-
-template <int NS, int NR>
-__device__ __forceinline__ void conv(float (&acc)[NS], const float (&Rw)[3][NS][KPT], const float* __restrict__ h, int npos) {
-  // warp-uniform: a short compare chain per (run, unit) instead of one branch per position (no jump table)
-  if (npos <= 3) {
-    if (npos == 2) conv_fixed<NS, NR, 2>(acc, Rw, h);
-    else conv_fixed<NS, NR, 3>(acc, Rw, h);
-  } else if (npos == 4) conv_fixed<NS, NR, 4>(acc, Rw, h);
-  else if (npos == 5) conv_fixed<NS, NR, 5>(acc, Rw, h);
-  else conv_fixed<NS, NR, KPT>(acc, Rw, h);
 }
 
 // Adds one (run, unit) window to a waveform row: acc = window part, Ev = merged boundary correction of this lane
@@ -185,21 +157,22 @@ __device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem&
 template <int NS, int NR, bool LP, int KP, bool TWO>
 __device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                                    const float* hbuf, int hstride, const float* Ebuf, float* row0, int mode, int lane, int npos) {
-  if (npos <= 3) {
-    if (npos == 2) consume_pairs<NS, NR, 2, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-    else consume_pairs<NS, NR, 3, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  } else if (KP == 4 || npos == 4) consume_pairs<NS, NR, 4, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else if (npos == 5) consume_pairs<NS, NR, KP >= 5 ? 5 : KP, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else consume_pairs<NS, NR, KP, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  // warp-uniform: a short compare chain per unit; only the position counts this variant can meet (2 .. KP) are instantiated
+  constexpr int N3 = KP >= 3 ? 3 : KP, N4 = KP >= 4 ? 4 : KP, N5 = KP >= 5 ? 5 : KP;
+  if (KP >= 6 && npos >= 6) consume_pairs<NS, NR, KP, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else if (KP >= 5 && npos == 5) consume_pairs<NS, NR, N5, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else if (KP >= 4 && npos == 4) consume_pairs<NS, NR, N4, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else if (KP >= 3 && npos == 3) consume_pairs<NS, NR, N3, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  else consume_pairs<NS, NR, 2, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
 }
 
-// KP = impulse positions whose response samples are held in registers: the KP = KPT kernel serves every tile; with
-// KP = KPT_SMALL the response needs 48 instead of 72 registers, three CTAs fit on an SM (24 instead of 16 warps to hide
-// the latencies the kernel is bound by) and the kernel serves the tiles of runs with <= KPT_SMALL positions, a prefix of
-// the tile table (span-major class key).  part: 0 all tiles, 1 tiles [0, split), 2 tiles [split, ntiles).
+// KP = impulse positions whose response samples are held in registers.  The KP = KPT kernel can serve every tile; with
+// KP = 4 (3) the response needs 48 (36) instead of 72 registers and three (four) CTAs fit on an SM — 24 (32) instead of 16
+// warps to hide the latencies the kernel is bound by.  A launch serves the tiles of spans span_lo .. span_hi (KP >= span_hi
+// + 2), a contiguous range of the tile table, and pulls them through its own counter gcnt[GC_FWD + launch].
 template <int NS, bool LP, int KP, bool TWO>
-__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? (KP < KPT ? 3 : 2) : 1)
-k_acc_tiles(const __grid_constant__ SortArgs A, const int part) {
+__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : 1)
+k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int span_hi, const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
   if (A.counts[2] != 0) return;
@@ -216,9 +189,9 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int part) {
     sm.udx[u] = (signed char)(u / A.P - A.n_neigh);
     sm.udy[u] = (signed char)(u % A.P - A.n_neigh);
   }
-  const int tile_lo = part == 2 ? A.gcnt[4] : 0;
-  const int ntiles = part == 1 ? A.gcnt[4] : A.gcnt[1];
-  int* const tile_counter = A.gcnt + (part == 2 ? 5 : 2);
+  const int tile_lo = A.gcnt[GC_SPAN + span_lo];
+  const int ntiles = A.gcnt[GC_SPAN + span_hi + 1];
+  int* const tile_counter = A.gcnt + GC_FWD + launch;
   const int n_neigh_units = A.P * A.P;
   const int n_units = 25 + 1 + n_neigh_units;  // merged diffusion groups, neighbourhood-sum row, neighbour pixels
   float* myh = sm.ph[warp];
@@ -501,17 +474,11 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
   const int ns = need <= 32 * 4 ? 4 : (need <= 32 * 5 ? 5 : 6);
-  // LARND_ACC_KP4: 0 = one kernel holding KPT positions for all tiles; 1 / 2 = tiles of runs with <= KPT_SMALL positions go
-  // to the 3-CTAs-per-SM kernel (1: two windows in flight for the main units, 2: one), the rest to the KPT kernel
-  static int kp4_mode = -1;
-  if (kp4_mode < 0) {
-    const char* e = getenv("LARND_ACC_KP4");
-    kp4_mode = e ? atoi(e) : 1;
-  }
-  const int split = (ns == 4) ? kp4_mode : 0;
+  const int split = (ns == 4) ? sorted_split_mode() : 0;
   const int grid = sorted_grid(2, LARND_ROW0_COPIES);
-  const int grid_small = split ? sorted_grid(3, LARND_ROW0_COPIES) : 0;
-  const int ncopies = grid > grid_small ? grid : grid_small;
+  const int grid3 = split ? sorted_grid(3, LARND_ROW0_COPIES) : 0;
+  const int grid4 = split >= 2 ? sorted_grid(4, LARND_ROW0_COPIES) : 0;
+  const int ncopies = max(grid, max(grid3, grid4));
   if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)ncopies * p.n_ticks * sizeof(float), st));
   const size_t smem = sizeof(TileSmem);
   static bool attr_done = false;
@@ -522,22 +489,29 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, KPT_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, KPT_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   // LP: for every number of impulse positions (2 .. KPT) the run window L + NPOS ends inside the last 32-tick slot, so
   // all other slots are flushed without a predicate
   const bool lp = lut->L + 2 >= 32 * (ns - 1) && lut->L + KPT < 32 * ns;
-  if (split == 1) { if (lp) k_acc_tiles<4, true, KPT_SMALL, true><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); else k_acc_tiles<4, false, KPT_SMALL, true><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); }
-  else if (split) { if (lp) k_acc_tiles<4, true, KPT_SMALL, false><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); else k_acc_tiles<4, false, KPT_SMALL, false><<<grid_small, TILE_THREADS, smem, st>>>(A, 1); }
-  if (split) LARND_LAUNCH_CHECK("k_acc_tiles<small>");
-  const int part = split ? 2 : 0;
-  if (ns == 4) { if (lp) k_acc_tiles<4, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); else k_acc_tiles<4, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); }
-  else if (ns == 5) { if (lp) k_acc_tiles<5, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); else k_acc_tiles<5, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); }
-  else { if (lp) k_acc_tiles<6, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); else k_acc_tiles<6, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, part); }
+  int big_lo = 0;  // first span left to the KPT kernel
+  if (split >= 2) {
+    if (lp) k_acc_tiles<4, true, 3, true><<<grid4, TILE_THREADS, smem, st>>>(A, 0, 1, 0); else k_acc_tiles<4, false, 3, true><<<grid4, TILE_THREADS, smem, st>>>(A, 0, 1, 0);
+    LARND_LAUNCH_CHECK("k_acc_tiles<3>");
+    big_lo = 2;
+  }
+  if (split >= 1) {
+    if (lp) k_acc_tiles<4, true, 4, true><<<grid3, TILE_THREADS, smem, st>>>(A, big_lo, 2, 1); else k_acc_tiles<4, false, 4, true><<<grid3, TILE_THREADS, smem, st>>>(A, big_lo, 2, 1);
+    LARND_LAUNCH_CHECK("k_acc_tiles<4>");
+    big_lo = 3;
+  }
+  if (ns == 4) { if (lp) k_acc_tiles<4, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); else k_acc_tiles<4, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); }
+  else if (ns == 5) { if (lp) k_acc_tiles<5, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); else k_acc_tiles<5, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); }
+  else { if (lp) k_acc_tiles<6, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); else k_acc_tiles<6, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); }
   LARND_LAUNCH_CHECK("k_acc_tiles");
   if (!A.skip_garbage) {
     k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, ncopies, p.n_ticks, wfs);

@@ -6,6 +6,8 @@
 // tick span): all runs of a class read the same response rows for the same unit and have the same number of impulse
 // positions, so a tile (<= TR runs of one class) is uniform work.
 #pragma once
+#include <stdlib.h>
+
 #include "larnd_common.cuh"
 
 namespace {
@@ -13,7 +15,12 @@ namespace {
 constexpr int TR = 32;              // runs per tile (lane <-> run in the build phases)
 constexpr int KPT = 6;              // impulse positions per run
 constexpr int SPAN_MAX_S = KPT - 2;  // max (T0max - T0min) inside a run
-constexpr int KPT_SMALL = 4;        // runs with <= KPT_SMALL positions (span <= 2) can be served by a kernel holding fewer response registers
+// Tiles are ordered by tick span (span-major class key), so runs with few impulse positions form contiguous ranges of the
+// tile table and can be served by kernel variants that hold fewer response samples in registers and fit more CTAs per SM:
+// gcnt[GC_SPAN + s] = first tile of span s (s = 0 .. SPAN_MAX_S), gcnt[GC_SPAN + SPAN_MAX_S + 1] = number of tiles.
+constexpr int GC_SPAN = 8;          // gcnt slots of the per-span tile offsets
+constexpr int GC_FWD = 16;          // gcnt slots of the forward kernels' tile counters (one per launch)
+constexpr int GC_BWD = 24;          // ... of the backward kernels'
 constexpr int MAXLEN = 8;           // segments per run (bounds the divergence of the lane <-> run build loops)
 constexpr int TILE_THREADS = 256;
 constexpr int NW = TILE_THREADS / 32;
@@ -46,8 +53,7 @@ struct SortArgs {
   int* class_start;
   int* cursor;
   int4* tile_info;
-  int* gcnt;  // [0] number of runs, [1] number of tiles, [2] forward tile counter, [3] backward tile counter,
-              // [4] first tile of a class with span > KPT_SMALL - 2, [5] forward tile counter of the large-span kernel
+  int* gcnt;  // [0] number of runs, [1] number of tiles, [GC_SPAN ..] per-span tile offsets, [GC_FWD ..] / [GC_BWD ..] tile counters
   int ncls;
   float* row0;  // [gridDim][nticks] per-CTA private copies of waveform row 0 (the garbage row every CTA adds to)
 };
@@ -122,7 +128,7 @@ k_build_runs(const __grid_constant__ SortArgs A) {
     }
     const int nb = A.nb;
     const int bxm = s_bx[t] - floordiv_i(s_bx[t], nb) * nb, bym = s_by[t] - floordiv_i(s_by[t], nb) * nb;
-    // span-major key: the tiles of runs with few impulse positions (span <= KPT_SMALL - 2) form a prefix of the tile table
+    // span-major key: the tiles of every tick span form one contiguous range of the tile table
     const int cls = (tmax - tmin) * (A.ncls / (SPAN_MAX_S + 1)) + (s_idx[t] * nb + bxm) * nb + bym;
     A.runs_tmp[s_base + before] = make_int4((int)(base + t), len | ((tmax - tmin) << 16), tmin, cls);
     atomicAdd(A.class_count + cls, 1);
@@ -167,7 +173,7 @@ k_class_scan(const __grid_constant__ SortArgs A) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) ex[k] = carry[k] + (wid > 0 ? s_w[k][wid - 1] : 0) + inc[k] - v[k];
     if (c < A.ncls) {
-      if (c == (KPT_SMALL - 1) * (A.ncls / (SPAN_MAX_S + 1))) A.gcnt[4] = ex[1];
+      if (c % (A.ncls / (SPAN_MAX_S + 1)) == 0) A.gcnt[GC_SPAN + c / (A.ncls / (SPAN_MAX_S + 1))] = ex[1];
       A.class_start[c] = ex[0];
       A.cursor[c] = ex[0];
       for (int i = 0; i < v[1]; ++i)  // tiles of this class
@@ -177,7 +183,7 @@ k_class_scan(const __grid_constant__ SortArgs A) {
     if (threadIdx.x == 0) { carry[0] += s_w[0][31]; carry[1] += s_w[1][31]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) A.gcnt[1] = carry[1];
+  if (threadIdx.x == 0) { A.gcnt[1] = carry[1]; A.gcnt[GC_SPAN + SPAN_MAX_S + 1] = carry[1]; }
 }
 
 __global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
@@ -216,7 +222,7 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   A.ncls = lut->ntpl * A.nb * A.nb * (SPAN_MAX_S + 1);
   A.row0 = ws.row0;
   LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * sizeof(int), st));
-  LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 32, st));
+  LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 256, st));
   const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
   k_build_runs<<<(unsigned)chunks, LARND_CHUNK, 0, st>>>(A);
   LARND_LAUNCH_CHECK("k_build_runs");
@@ -227,6 +233,18 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   k_scatter_runs<<<(unsigned)blocks, 256, 0, st>>>(A);
   LARND_LAUNCH_CHECK("k_scatter_runs");
   return LARND_OK;
+}
+
+// How the tile table is split over kernel variants (LARND_SORTED_SPLIT): 0 = one kernel holding KPT positions for all
+// tiles, 1 = spans 0-2 on the 4-position kernel (3 CTAs/SM) + the rest, 2 = spans 0-1 on the 3-position kernel (4 CTAs/SM),
+// span 2 on the 4-position kernel, the rest on the KPT kernel.
+inline int sorted_split_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LARND_SORTED_SPLIT");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
 }
 
 inline int sorted_grid(int per_sm, int cap) {

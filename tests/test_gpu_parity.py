@@ -427,6 +427,51 @@ def test_spill_sized_batch_properties(torch_dev, monkeypatch):
     assert float(((sp.wfs_full[real][:, 1:] - ws[real][:, 1:]).abs() / (scale + 1e-30)).max()) < 2 * WFS_RTOL
 
 
+_SPLIT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/larnd-sim-jax_b200"); sys.path.insert(0, sys.argv[1] + "/tests")
+import common as cm
+from larndsim_b200 import sim, synthetic, dataio
+from larndsim_b200.consts import build_response_template
+dev = torch.device("cuda", 0)
+params = cm.product_params(number_pix_neighbors=4, signal_length=100, electron_sampling_resolution=0.01)
+raw, nev = synthetic.synthetic_raw_tracks(400_000, seed=5, precision=0.01)
+tracks = dataio.chop_tracks(torch.from_numpy(raw).to(dev), synthetic.FIELDS, 0.01)
+bank = build_response_template(synthetic.synthetic_response(), params, device=dev)
+st = sim.lut_forward(params, bank, tracks, synthetic.FIELDS, n_events=nev)
+fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True)
+g = sim.fee_backward(fs, fs.adc * (st.unique_pixels >= 0).unsqueeze(1))
+grad = sim.lut_backward(st, g)
+np.savez(sys.argv[2], wfs=st.wfs_full.cpu().numpy(), uniq=st.unique_pixels.cpu().numpy(), grad=grad.double().cpu().numpy(),
+         ticks=fs.ticks.cpu().numpy())
+"""
+
+
+def test_sorted_kernel_variants_agree(torch_dev, tmp_path):
+    """The class-sorted kernels serve the tile table with one, two or three register-footprint variants (LARND_SORTED_SPLIT =
+    0 / 1 / 2, read once per process): same runs, same per-window arithmetic, different launch partition — the waveforms
+    must agree to the float32 reduction-order tolerance, the hit ticks exactly, the gradients to GRAD_RTOL."""
+    import os
+    import subprocess
+    import sys
+    res = {}
+    for mode in ("0", "1", "2"):
+        out = str(tmp_path / ("split%s.npz" % mode))
+        env = dict(os.environ, LARND_SORTED_SPLIT=mode, LARND_ACC_IMPL="sorted", LARND_BWD_IMPL="sorted")
+        subprocess.run([sys.executable, "-c", _SPLIT_SCRIPT, cm.ROOT, out], check=True, env=env, timeout=600)
+        res[mode] = np.load(out)
+    ref = res["0"]
+    real = ref["uniq"] >= 0
+    scale = np.abs(ref["wfs"][real]).max(axis=1, keepdims=True)
+    for mode in ("1", "2"):
+        r = res[mode]
+        assert np.array_equal(r["uniq"], ref["uniq"])
+        assert (np.abs(r["wfs"][real][:, 1:] - ref["wfs"][real][:, 1:]) <= 2 * WFS_RTOL * scale + 1e-3).all()
+        assert (r["ticks"][real] != ref["ticks"][real]).sum() <= 3
+        nz = np.abs(ref["grad"]) > 0
+        assert (np.abs(r["grad"][nz] / ref["grad"][nz] - 1) < GRAD_RTOL).all()
+
+
 def test_fit_and_scan_drivers(torch_dev):
     """The reference's convergence criterion (tests/test_fit_convergence.py:21-45): no NaN and the mean of the last 5
     losses is below the mean of the first 5; plus a 3x3 likelihood scan whose minimum sits at the nominal point."""
