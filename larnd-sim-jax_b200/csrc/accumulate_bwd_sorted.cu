@@ -222,7 +222,7 @@ __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const fl
 // KP / span range / launch as in k_acc_tiles: the variants holding 3 / 4 response positions (36 / 48 registers, 4 / 3 CTAs
 // per SM) serve the tiles of runs with few impulse positions, the KP = KPT kernel the rest (or everything).
 template <int NS, int KP>
-__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : 1)
+__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1))
 k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int span_lo, const int span_hi,
             const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -425,6 +425,7 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
     LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<6, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<5, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
@@ -448,7 +449,20 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
     big_lo = 3;
   }
   if (need <= 32 * 4) k_bwd_tiles<4, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, big_lo, SPAN_MAX_S, 2);
-  else if (need <= 32 * 5) k_bwd_tiles<5, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, 0, SPAN_MAX_S, 2);
+  else if (need <= 32 * 5) {
+    int n5 = 0;
+    if (sorted_split_mode() >= 1) {  // 150-tick windows: 60 response registers, 2 CTAs/SM instead of 1
+      k_bwd_tiles<5, 4><<<grid2, BT_THREADS, smem, st>>>(A, p, 0, 2, 1);
+      LARND_LAUNCH_CHECK("k_bwd_tiles<5,4>");
+      A.partials += (int64_t)grid2 * 16;
+      big_lo = 3;
+      n5 = grid2;
+    }
+    k_bwd_tiles<5, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, big_lo, SPAN_MAX_S, 2);
+    LARND_LAUNCH_CHECK("k_bwd_tiles");
+    *n_slots_out = grid2 + n5;
+    return LARND_OK;
+  }
   else k_bwd_tiles<6, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, 0, SPAN_MAX_S, 2);
   LARND_LAUNCH_CHECK("k_bwd_tiles");
   *n_slots_out = grid2 + grid3 + grid4;

@@ -171,7 +171,7 @@ __device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const Tile
 // warps to hide the latencies the kernel is bound by.  A launch serves the tiles of spans span_lo .. span_hi (KP >= span_hi
 // + 2), a contiguous range of the tile table, and pulls them through its own counter gcnt[GC_FWD + launch].
 template <int NS, bool LP, int KP, bool TWO>
-__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : 1)
+__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1))
 k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int span_hi, const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
@@ -475,6 +475,7 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
   const int need = lut->L + 2 + SPAN_MAX_S;
   const int ns = need <= 32 * 4 ? 4 : (need <= 32 * 5 ? 5 : 6);
   const int split = (ns == 4) ? sorted_split_mode() : 0;
+  const bool split5 = ns == 5 && sorted_split_mode() >= 1;  // 150-tick windows: 60 response registers, 2 CTAs/SM instead of 1
   const int grid = sorted_grid(2, LARND_ROW0_COPIES);
   const int grid3 = split ? sorted_grid(3, LARND_ROW0_COPIES) : 0;
   const int grid4 = split >= 2 ? sorted_grid(4, LARND_ROW0_COPIES) : 0;
@@ -492,6 +493,8 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
@@ -510,7 +513,14 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     big_lo = 3;
   }
   if (ns == 4) { if (lp) k_acc_tiles<4, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); else k_acc_tiles<4, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); }
-  else if (ns == 5) { if (lp) k_acc_tiles<5, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); else k_acc_tiles<5, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); }
+  else if (ns == 5) {
+    if (split5) {
+      if (lp) k_acc_tiles<5, true, 4, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, 2, 1); else k_acc_tiles<5, false, 4, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, 2, 1);
+      LARND_LAUNCH_CHECK("k_acc_tiles<5,4>");
+      big_lo = 3;
+    }
+    if (lp) k_acc_tiles<5, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); else k_acc_tiles<5, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2);
+  }
   else { if (lp) k_acc_tiles<6, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); else k_acc_tiles<6, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); }
   LARND_LAUNCH_CHECK("k_acc_tiles");
   if (!A.skip_garbage) {
