@@ -34,6 +34,9 @@ NEIGH, SIGLEN, PRECISION = 4, 100, 0.01
 GEOM = os.path.join(ROOT, "larnd-sim-jax_b200", "larndsim_b200", "data", "module0_geometry.json")
 
 
+MC_SEGMENTS = 2_000_000  # size of the MC-current-mode side measurement
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -356,6 +359,23 @@ def run_ours(args):
         ms_skip, _ = timed(lambda: fwd(flags=1), args.steps, 1)
         fwd()
 
+    # MC-current mode (BASELINE config 3: simulate_parametrized, mc_diff, diffusion in the current model, n = 0, L = 150 as in
+    # optimize/fit_test.sh:95-102) on the first MC_SEGMENTS segments of the same batch: prepare + unique + analytic current +
+    # scatter + FEE, random numbers from the device Threefry stream (drawn once, outside the timed region)
+    n_mc = min(nseg, MC_SEGMENTS)
+    p_mc = params.replace(number_pix_neighbors=0, signal_length=150, mc_diff=True, diffusion_in_current_sim=True)
+    tr_mc = tracks[:n_mc].contiguous()
+    rnd_mc = sim.mc_normals(n_mc, 0, dev)
+    st_mc = sim.mc_forward(p_mc, tr_mc, fields, rnd_mc, n_events=n_events)
+    npix_mc, pod_mc = st_mc.npix, st_mc.pod
+    del st_mc
+
+    def mc_fwd():
+        stm = sim.mc_forward(p_mc, tr_mc, fields, rnd_mc, npix_capacity=npix_mc, n_events=n_events)
+        return sim.fee_forward(p_mc, stm.wfs_full[:, 1:], stm.unique_pixels, None, compact=True, pod=pod_mc)
+
+    ms_mc, _ = timed(mc_fwd, args.steps, max(1, args.warmup // 3))
+
     # per-kernel device times of the dominant kernels, same launches as above
     lib.larnd_profile_enable(1)
     import ctypes as C
@@ -421,6 +441,8 @@ def run_ours(args):
                         "note": "un-chopped tracks uploaded, chop_tracks on the device (csrc/chop.cu)"},
             "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": total_seg / (ms_fg * 1e-3), "unit": "segments/s",
                          "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none"},
+            "mc_mode": {"metric": "segments/s fwd (MC-current mode, n=0, mc_diff, diffusion in the current model)",
+                        "value": n_mc * world / (ms_mc * 1e-3), "unit": "segments/s", "ms_per_step": ms_mc, "segments_per_gpu": n_mc},
             "gpu_launches": int(args.steps * 15),  # prepare 1 + unique/scan 4 + sorted accumulate 7 (run sort 3, tiles 2, row 0, boundary) + FEE/compaction 3
             "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
             "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate: run sort + the 4- and 6-position tile kernels + row-0 reduction)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

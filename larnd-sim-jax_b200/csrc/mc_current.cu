@@ -209,41 +209,75 @@ struct McArgs {
 };
 
 constexpr int MC_WARPS = 8;
+constexpr int MC_SEGS = 5;                  // segments per CTA of k_mc_accumulate: 5 x 51 = 255 of 256 threads busy
+constexpr int MC_ACC_THREADS = 256;
 
-// accumulate_signals_parametrized (detsim_jax.py:207-228): tick = t0_tick - 51 + k; <0 or >= Nticks-1 -> column 0, else +1
-__global__ void __launch_bounds__(MC_WARPS * 32)
+// current_mc + accumulate_signals_parametrized (detsim_jax.py:618-639, 207-228): thread <-> (segment, tick).  tick = t0_tick -
+// 51 + k; < 0 or >= Nticks-1 -> column 0, else +1.  The row normalisation of the diffusion variant (lower edge of the first
+// bin minus upper edge of the last one, detsim_jax.py:470-473) does not depend on the tick: threads k = 0 / 1 of every
+// segment evaluate it once for the two exponential components and hand it over in shared memory, which halves the
+// erf / erfc / exp work per sample.
+__global__ void __launch_bounds__(MC_ACC_THREADS)
 k_mc_accumulate(const __grid_constant__ McArgs A, const __grid_constant__ larnd_params_t p) {
-  if (A.counts[2] != 0) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
-  if (s >= A.n) return;
-  RowLookup lk = A.lk;
-  lk.n_unique = A.counts[0];
-  lk.n_neg = A.counts[1];
-  const int* irec = reinterpret_cast<const int*>(A.rec);
-  const int64_t n = A.n;
-  const float q = A.rec[(int64_t)M_Q * n + s];
-  const int pid = irec[(int64_t)M_PID * n + s];
-  const int row = lookup_row(lk, pid);
-  if (row < 0) return;  // cannot happen: every id was inserted by k_mc_prepare
-  const float t0f = A.rec[(int64_t)M_T0F * n + s], xd = A.rec[(int64_t)M_XD * n + s], yd = A.rec[(int64_t)M_YD * n + s];
-  const float sig = A.rec[(int64_t)M_SIG * n + s];
-  const int start = irec[(int64_t)M_TICK * n + s] - MC_NT;
+  __shared__ float s_den[MC_SEGS][2];
+  __shared__ float s_garbage[MC_SEGS];
+  const int sl = threadIdx.x / MC_NT, k = threadIdx.x - sl * MC_NT;
+  const int64_t s = (int64_t)blockIdx.x * MC_SEGS + sl;
+  const bool diffusion = p.diffusion_in_current_sim != 0;
   const float dtk = 5.0f / (MC_NT - 1);
-  float* base = A.wfs + (int64_t)row * A.nticks;
-  float garbage = 0.f;
-  for (int k = lane; k < MC_NT; k += 32) {
+  bool live = A.counts[2] == 0 && sl < MC_SEGS && s < A.n;
+  int row = -1, start = 0;
+  float q = 0.f, t0f = 0.f, xd = 0.f, yd = 0.f, sig = 1.f;
+  if (live) {
+    RowLookup lk = A.lk;
+    lk.n_unique = A.counts[0];
+    lk.n_neg = A.counts[1];
+    const int* irec = reinterpret_cast<const int*>(A.rec);
+    const int64_t n = A.n;
+    row = lookup_row(lk, irec[(int64_t)M_PID * n + s]);
+    live = row >= 0;  // cannot fail: every id was inserted by k_mc_prepare
+    q = A.rec[(int64_t)M_Q * n + s];
+    t0f = A.rec[(int64_t)M_T0F * n + s]; xd = A.rec[(int64_t)M_XD * n + s]; yd = A.rec[(int64_t)M_YD * n + s];
+    sig = A.rec[(int64_t)M_SIG * n + s];
+    start = irec[(int64_t)M_TICK * n + s] - MC_NT;
+  }
+  if (threadIdx.x < MC_SEGS) s_garbage[threadIdx.x] = 0.f;
+  const float Bp[6] = {1.060f, -0.909f, -0.909f, 5.856f, 0.207f, 0.207f};
+  const float Cp[6] = {0.679f, -1.083f, -1.083f, 8.772f, -5.521f, -5.521f};
+  const float Dp[6] = {2.644f, -9.174f, -9.174f, 13.483f, 45.887f, 45.887f};
+  const float Tp[6] = {2.948f, -2.705f, -2.705f, 4.825f, 20.814f, 20.814f};
+  const float a = g_min1(quad(Bp, xd, yd));
+  const float b = quad(Cp, xd, yd), c = quad(Dp, xd, yd);
+  const float loc = -(t0f + quad(Tp, xd, yd));
+  const float half = 0.5f * dtk;
+  if (diffusion && live && k < 2) {
+    const float lam = 1.0f / (k == 0 ? b : c);
+    const float lo_first = expon_diff_edge(0.0f - half, loc, lam, sig);
+    const float up_last = expon_diff_edge(-(dtk * (MC_NT - 1)) + half, loc, lam, sig);
+    s_den[sl][k] = lo_first - up_last;
+  }
+  __syncthreads();
+  if (live) {
     // jnp.linspace(0, 5, 51)[k] = 0*(1-s) + 5*s with s = k/50 (exact end point)
     const float sfrac = __fdiv_rn((float)k, (float)(MC_NT - 1));
     const float t = (k == MC_NT - 1) ? 5.0f : __fmul_rn(5.0f, sfrac);
-    const float cur = current_sample<float>(t, t0f, xd, yd, sig, p.diffusion_in_current_sim != 0, dtk) * q;
+    float cur;
+    if (diffusion) {
+      const float x = -t, lb = 1.0f / b, lc = 1.0f / c;
+      const float nb = expon_diff_edge(x + half, loc, lb, sig) - expon_diff_edge(x - half, loc, lb, sig);
+      const float nc = expon_diff_edge(x + half, loc, lc, sig) - expon_diff_edge(x - half, loc, lc, sig);
+      cur = a * ((nb / s_den[sl][0]) / dtk) + (1.0f - a) * ((nc / s_den[sl][1]) / dtk);
+    } else {
+      cur = current_sample<float>(t, t0f, xd, yd, sig, false, dtk);
+    }
+    cur *= q;
+    float* base = A.wfs + (int64_t)row * A.nticks;
     const int tick = start + k;
-    if (tick < 0 || tick >= A.nticks - 1) garbage += cur;
+    if (tick < 0 || tick >= A.nticks - 1) atomicAdd(&s_garbage[sl], cur);  // rare: windows sticking out of the readout
     else atomicAdd(base + tick + 1, cur);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) garbage += __shfl_xor_sync(0xffffffffu, garbage, o);
-  if (lane == 0 && garbage != 0.f) atomicAdd(base, garbage);
+  __syncthreads();
+  if (live && k == 0 && s_garbage[sl] != 0.f) atomicAdd(A.wfs + (int64_t)row * A.nticks, s_garbage[sl]);
 }
 
 __global__ void __launch_bounds__(MC_WARPS * 32)
@@ -502,7 +536,7 @@ extern "C" int larnd_mc_forward(const float* tracks_d, int64_t n, const larnd_co
     A.lk.bitmap = ws.bitmap; A.lk.wprefix = ws.wprefix; A.lk.n_words = ws.n_words; A.lk.pid_offset = ws.pid_offset;
     A.lk.n_unique = 0; A.lk.n_neg = 0; A.lk.npix = npix_capacity;
     A.counts = counts_d; A.nticks = p->n_ticks; A.wfs = wfs_d; A.g = nullptr; A.g_stride = 0; A.partials = nullptr;
-    k_mc_accumulate<<<(unsigned)((n + MC_WARPS - 1) / MC_WARPS), MC_WARPS * 32, 0, st>>>(A, *p);
+    k_mc_accumulate<<<(unsigned)((n + MC_SEGS - 1) / MC_SEGS), MC_ACC_THREADS, 0, st>>>(A, *p);
     LARND_LAUNCH_CHECK("k_mc_accumulate");
   }
   return LARND_OK;
