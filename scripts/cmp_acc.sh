@@ -1,7 +1,8 @@
 #!/bin/bash
-# Compare the accumulate variants on the bench workload: scripts/cmp_acc.sh "<impl list>" "<segment counts>"
+# Compare the accumulate kernels (LARND_ACC_IMPL = sorted / chunk) on the bench workload: scripts/cmp_acc.sh "<impl list>" "<segment counts>"
+# (LARND_SORTED_SPLIT = 0 / 1 / 2 selects how the class-sorted kernels split the tile table over register-footprint variants)
 for n in ${2:-10000000}; do
-  for impl in ${1:-sorted mma}; do
+  for impl in ${1:-sorted chunk}; do
     LARND_ACC_IMPL=$impl python bench.py --no-cpu-baseline --segments $n > gpurun_out/bench_${impl}_$n.json 2> gpurun_out/bench_${impl}_$n.err
     python - <<PY
 import json
