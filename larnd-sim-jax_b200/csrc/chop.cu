@@ -84,6 +84,11 @@ __global__ void __launch_bounds__(1024) k_chop_scan(int64_t* __restrict__ counts
   if (threadIdx.x == 0) counts[m] = carry;
 }
 
+constexpr int CHOP_ROWS = 32;  // output rows per warp task
+
+// One warp per chunk of CHOP_ROWS consecutive OUTPUT rows (lanes <-> columns, every output row one coalesced store), the raw
+// row of the chunk's first piece found by binary search in the prefix table: the work is balanced over the pieces, not over
+// the raw rows (a raw row expands into ~2 000 pieces at 0.01 cm, and a batch has only a few thousand raw rows).
 __global__ void __launch_bounds__(256)
 k_chop_expand(const float* __restrict__ raw, int64_t m, const __grid_constant__ larnd_chop_columns_t c, double precision,
               float prec32, const int64_t* __restrict__ offsets, float* __restrict__ out, int64_t capacity) {
@@ -91,43 +96,56 @@ k_chop_expand(const float* __restrict__ raw, int64_t m, const __grid_constant__ 
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int ncols = c.ncols;
-  if (offsets[m] > capacity) return;  // caller checks counts[m] against its capacity
-  for (int64_t i = warp; i < m; i += nwarps) {
-    const float* tr = raw + i * ncols;
-    const ChopGeom g = chop_geom(tr, c);
-    const long long n = chop_nsteps(g.len, prec32);
-    const int64_t o0 = offsets[i];
-    // which role this lane's column plays (lanes >= ncols idle; rows wider than 32 columns loop)
-    for (int col0 = 0; col0 < ncols; col0 += 32) {
-      const int col = col0 + lane;
-      if (col >= ncols) continue;
-      const float base = tr[col];
-      int axis = -1, kind = 0;  // kind: 1 start, 2 end, 3 mid, 4 dx, 5 dE
-      if (col == c.x_start) { axis = 0; kind = 1; } else if (col == c.y_start) { axis = 1; kind = 1; } else if (col == c.z_start) { axis = 2; kind = 1; }
-      else if (col == c.x_end) { axis = 0; kind = 2; } else if (col == c.y_end) { axis = 1; kind = 2; } else if (col == c.z_end) { axis = 2; kind = 2; }
-      else if (col == c.x) { axis = 0; kind = 3; } else if (col == c.y) { axis = 1; kind = 3; } else if (col == c.z) { axis = 2; kind = 3; }
-      else if (col == c.dx) kind = 4;
-      else if (col == c.dE) kind = 5;
-      const int cs = axis == 0 ? c.x_start : (axis == 1 ? c.y_start : c.z_start);
-      const int ce = axis == 0 ? c.x_end : (axis == 1 ? c.y_end : c.z_end);
-      const double s0 = axis >= 0 ? (double)tr[cs] : 0.0, d = axis >= 0 ? (double)g.dir[axis] : 0.0;
-      const float e_last = axis >= 0 ? tr[ce] : 0.0f;
-      const float len_eps = __fadd_rn(g.len, 1e-10f);            // np.float32 + weak Python float
-      const float dE_in = __fdiv_rn(__fmul_rn(base, prec32), len_eps);
-      for (long long k = 0; k < n; ++k) {
-        const bool last = k == n - 1;
-        float v = base;
-        if (kind == 1 || kind == 2 || kind == 3) {
-          const float vs = (float)(s0 + __dmul_rn(__dmul_rn((double)k, precision), d));
-          const float ve = last ? e_last : (float)(s0 + __dmul_rn(__dmul_rn(precision, (double)(k + 1)), d));
-          v = kind == 1 ? vs : (kind == 2 ? ve : __fmul_rn(0.5f, __fadd_rn(vs, ve)));
-        } else if (kind == 4) {
-          v = last ? (float)((double)g.len - __dmul_rn(precision, (double)(n - 1))) : prec32;
-        } else if (kind == 5) {
-          v = last ? (float)__dmul_rn((double)base, 1.0 - __ddiv_rn(__dmul_rn(precision, (double)(n - 1)), (double)len_eps)) : dE_in;
+  const int64_t total = offsets[m];
+  if (total > capacity) return;  // caller checks counts[m] against its capacity
+  const int64_t nchunks = (total + CHOP_ROWS - 1) / CHOP_ROWS;
+  for (int64_t chunk = warp; chunk < nchunks; chunk += nwarps) {
+    int64_t o = chunk * CHOP_ROWS;
+    const int64_t o_end = min(total, o + CHOP_ROWS);
+    int64_t lo = 0, hi = m - 1;  // largest i with offsets[i] <= o (every raw row has at least one piece)
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (offsets[mid] <= o) lo = mid; else hi = mid - 1;
+    }
+    for (int64_t i = lo; o < o_end; ++i) {
+      const float* tr = raw + i * ncols;
+      const ChopGeom g = chop_geom(tr, c);
+      const long long n = chop_nsteps(g.len, prec32);
+      const int64_t o0 = offsets[i];
+      const long long k0 = o - o0, k1 = min((long long)n, k0 + (long long)(o_end - o));
+      // which role this lane's column plays (lanes >= ncols idle; rows wider than 32 columns loop)
+      for (int col0 = 0; col0 < ncols; col0 += 32) {
+        const int col = col0 + lane;
+        if (col >= ncols) continue;
+        const float base = tr[col];
+        int axis = -1, kind = 0;  // kind: 1 start, 2 end, 3 mid, 4 dx, 5 dE
+        if (col == c.x_start) { axis = 0; kind = 1; } else if (col == c.y_start) { axis = 1; kind = 1; } else if (col == c.z_start) { axis = 2; kind = 1; }
+        else if (col == c.x_end) { axis = 0; kind = 2; } else if (col == c.y_end) { axis = 1; kind = 2; } else if (col == c.z_end) { axis = 2; kind = 2; }
+        else if (col == c.x) { axis = 0; kind = 3; } else if (col == c.y) { axis = 1; kind = 3; } else if (col == c.z) { axis = 2; kind = 3; }
+        else if (col == c.dx) kind = 4;
+        else if (col == c.dE) kind = 5;
+        const int cs = axis == 0 ? c.x_start : (axis == 1 ? c.y_start : c.z_start);
+        const int ce = axis == 0 ? c.x_end : (axis == 1 ? c.y_end : c.z_end);
+        const double s0 = axis >= 0 ? (double)tr[cs] : 0.0, d = axis >= 0 ? (double)g.dir[axis] : 0.0;
+        const float e_last = axis >= 0 ? tr[ce] : 0.0f;
+        const float len_eps = __fadd_rn(g.len, 1e-10f);            // np.float32 + weak Python float
+        const float dE_in = __fdiv_rn(__fmul_rn(base, prec32), len_eps);
+        for (long long k = k0; k < k1; ++k) {
+          const bool last = k == n - 1;
+          float v = base;
+          if (kind == 1 || kind == 2 || kind == 3) {
+            const float vs = (float)(s0 + __dmul_rn(__dmul_rn((double)k, precision), d));
+            const float ve = last ? e_last : (float)(s0 + __dmul_rn(__dmul_rn(precision, (double)(k + 1)), d));
+            v = kind == 1 ? vs : (kind == 2 ? ve : __fmul_rn(0.5f, __fadd_rn(vs, ve)));
+          } else if (kind == 4) {
+            v = last ? (float)((double)g.len - __dmul_rn(precision, (double)(n - 1))) : prec32;
+          } else if (kind == 5) {
+            v = last ? (float)__dmul_rn((double)base, 1.0 - __ddiv_rn(__dmul_rn(precision, (double)(n - 1)), (double)len_eps)) : dE_in;
+          }
+          out[(o0 + k) * ncols + col] = v;
         }
-        out[(o0 + k) * ncols + col] = v;
       }
+      o += k1 - k0;
     }
   }
 }
@@ -155,8 +173,7 @@ extern "C" int larnd_chop_tracks(const float* raw_d, int64_t m, const larnd_chop
   }
   if (m == 0) return LARND_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = (m * 32 + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  const int64_t blocks = 148 * 16;  // persistent warps striding over the chunks of output rows
   k_chop_expand<<<(unsigned)blocks, 256, 0, st>>>(raw_d, m, *cols, precision, (float)precision, offsets_d, out_d, capacity);
   LARND_LAUNCH_CHECK("k_chop_expand");
   return LARND_OK;
