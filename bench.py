@@ -199,6 +199,11 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: keep this rank's pinned host buffers and copy threads on the GPU's own NUMA node
+        from larndsim_b200 import parallel
+        numa_cpus = parallel.bind_to_gpu_numa_node(local) if os.environ.get("LARND_NO_NUMA_BIND") is None else None
+    else:
+        numa_cpus = None
     lb.build_library()
     lib = lb.get_lib()
 
@@ -453,6 +458,7 @@ def run_ours(args):
                          "l2_red": l2_red,
                          "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3)},
             "setup_s": t_gen,
+            "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
         }
         if ms_skip is not None:
             line["value_skip_garbage_row"] = total_seg / (ms_skip * 1e-3)

@@ -12,6 +12,37 @@ import torch
 import torch.distributed as dist
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index, sysfs="/sys/bus/pci/devices"):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, BEFORE it allocates pinned host buffers
+    (first touch places them on that node).  With one process per GPU, every rank's host-to-device stream then stays on its
+    own socket's memory controllers and PCIe root instead of crossing the inter-socket link.  Returns the CPU set used, or
+    None when the topology is unknown (no sysfs entry, a single node, or a cpuset that excludes those CPUs) — never raises."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(os.path.join(sysfs, bdf, "local_cpulist")) as fh:
+            local = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def event_partition(event_ids, world_size):
     """Contiguous event ranges balanced by segment count.  ``event_ids``: per-row local event id (>= 0; padding rows
     with -1 are ignored).  Returns a list of (first_event, last_event_exclusive) per rank."""

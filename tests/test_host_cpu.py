@@ -200,6 +200,17 @@ def test_stage_operators_reject_cpu_tensors_and_bad_arguments(lib):
     assert {n for n, _ in oc._fields_} <= set(cm.FIELDS)
 
 
+def test_numa_binding_helper_is_safe_without_topology(tmp_path):
+    """bind_to_gpu_numa_node never raises: unknown topology (no GPU / no sysfs entry) -> None and the affinity is untouched."""
+    import os
+    from larndsim_b200 import parallel
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before
+
+
 def test_event_partition_is_balanced_and_complete():
     from larndsim_b200 import parallel
     rng = np.random.default_rng(0)
