@@ -9,7 +9,6 @@ csrc/mc_current.cu) and differentiable w.r.t. its float tensor arguments; gradie
 through the fused entry points, not through these."""
 import ctypes as C
 
-import numpy as np
 import torch
 
 from . import _lib
