@@ -87,6 +87,22 @@ __device__ __forceinline__ float reduce8_to_lane_s(const float (&v)[8], int lane
   return __shfl_sync(0xffffffffu, y, (lane & 7) * 4);
 }
 
+// sums 4 lane-partial values over the warp with 7 shuffles; the total of v[j] is returned in lane j (j < 4)
+__device__ __forceinline__ float reduce4_to_lane_s(const float (&v)[4], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8;
+  float w[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b4 ? v[i] : v[i + 2], keep = b4 ? v[i + 2] : v[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float x = (b3 ? w[1] : w[0]) + __shfl_xor_sync(0xffffffffu, b3 ? w[0] : w[1], 8);
+  x += __shfl_xor_sync(0xffffffffu, x, 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return __shfl_sync(0xffffffffu, x, ((lane & 2) << 3) | ((lane & 1) << 3));  // value j lives in lanes with (b4, b3) = (j >> 1, j & 1)
+}
+
 // One unit of one tile: every run p of `todo` (bit mask of runs whose target row exists) is correlated with the unit's
 // response rows Rw and its segments update the shared accumulators.  NR = 3: main pixel (3-template blend, group gi/gj);
 // NR = 1: neighbour pixel (template 0, full charge).
@@ -141,13 +157,32 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
 #pragma unroll
           for (int r = 0; r < NR; ++r) part[NR * j + r] = fmaf(gv, Rw[r][s][j], part[NR * j + r]);
       }
+      // full groups of 8 partials with the 10-shuffle butterfly; the remainder with the cheapest one that fits
+      // (<= 4 values: 7 shuffles, a single value: plain warp sum)
+      constexpr int V = NR * NPOS, V8 = V / 8 * 8, REM = V - V8;
 #pragma unroll
-      for (int c0 = 0; c0 < NR * NPOS; c0 += 8) {
+      for (int c0 = 0; c0 < V8; c0 += 8) {
         float v8[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v8[k] = (c0 + k < NR * NPOS) ? part[(c0 + k < NR * NPOS) ? c0 + k : 0] : 0.0f;
+        for (int k = 0; k < 8; ++k) v8[k] = part[c0 + k];
         const float tot = reduce8_to_lane_s(v8, lane);
         if (lane < 8) ps.G[nslot][c0 + lane] = tot;  // G[NR*j + r]
+      }
+      if (REM > 4) {
+        float v8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v8[k] = (k < REM) ? part[(k < REM) ? V8 + k : 0] : 0.0f;
+        const float tot = reduce8_to_lane_s(v8, lane);
+        if (lane < 8) ps.G[nslot][V8 + lane] = tot;
+      } else if (REM > 1) {
+        float v4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v4[k] = (k < REM) ? part[(k < REM) ? V8 + k : 0] : 0.0f;
+        const float tot = reduce4_to_lane_s(v4, lane);
+        if (lane < 4) ps.G[nslot][V8 + lane] = tot;
+      } else if (REM == 1) {
+        const float tot = warp_sum_f(part[V8 < V ? V8 : 0]);
+        if (lane == 0) ps.G[nslot][V8] = tot;
       }
     }
     __syncwarp();
