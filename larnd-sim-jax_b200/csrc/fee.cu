@@ -15,6 +15,7 @@ namespace {
 
 constexpr int FEE_WARPS = 4;
 constexpr int FEE_THREADS = FEE_WARPS * 32;
+#define FEE_ROW_STRIDE(nt) ((((nt) + 3) & ~3) + 4)  // floats per warp: the row, rounded up to whole vectors, + the alignment shift
 
 struct FeeArgs {
   const float* wfs;
@@ -31,29 +32,49 @@ __device__ __forceinline__ int floordiv_pos(int a, int b) { return floordiv_i(a,
 
 __global__ void __launch_bounds__(FEE_THREADS)
 k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_params_t p) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row = blockIdx.x * FEE_WARPS + wid;
   if (row >= F.npix) return;
   const int Nt = F.ntw;
-  float* c = smem + (size_t)wid * Nt;
   const float* w = F.wfs + (int64_t)row * F.stride;
-  int t_first = Nt, t_last = -1;  // first / last tick with a non-zero sample
-  // the row is streamed from HBM: 8 coalesced 128-byte loads in flight per warp (one at a time leaves the kernel latency-bound)
-  for (int t0 = 0; t0 < Nt; t0 += 256) {
-    float v[8];
+  // The row base is only 4-byte aligned (simulate_wfs hands out wfs[:, 1:] of a 2001-float row): `head` floats up to the
+  // next 16-byte boundary and `tail` floats after the last whole vector are read by six lanes, the body with 128-bit
+  // loads.  The copy in shared memory is shifted by `shift` floats so that the vector stores are aligned as well.
+  const int head = min((int)(((16u - (unsigned)((uintptr_t)w & 15u)) & 15u) >> 2), Nt);
+  const int nvec = (Nt - head) >> 2, tail = Nt - head - 4 * nvec;
+  const int shift = (4 - head) & 3;
+  float* c = smem + (size_t)wid * FEE_ROW_STRIDE(Nt) + shift;
+  int t_first = Nt, t_last = -1;  // bounds of the non-zero samples (vector granularity: a superset is enough, zeros inside
+                                  // the window do not change any running sum)
+  if (lane < head + tail) {
+    const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
+    const float qv = __fmul_rn(__ldg(w + t), p.t_sampling);  // q = wfs * t_sampling
+    c[t] = qv;
+    if (qv != 0.0f) { t_first = t; t_last = t; }
+  }
+  const float4* w4 = reinterpret_cast<const float4*>(w + head);
+  float4* c4 = reinterpret_cast<float4*>(c + head);
+  for (int v0 = 0; v0 < nvec; v0 += 128) {
+    float4 x[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int t = t0 + 32 * k + lane;
-      v[k] = t < Nt ? __ldg(w + t) : 0.0f;
+    for (int k = 0; k < 4; ++k) {  // four 512-byte warp loads in flight
+      const int v = v0 + 32 * k + lane;
+      x[k] = v < nvec ? __ldg(w4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int t = t0 + 32 * k + lane;
-      if (t < Nt) {
-        const float qv = __fmul_rn(v[k], p.t_sampling);  // q = wfs * t_sampling
-        c[t] = qv;
-        if (qv != 0.0f) { t_first = min(t_first, t); t_last = t; }
+    for (int k = 0; k < 4; ++k) {
+      const int v = v0 + 32 * k + lane;
+      if (v < nvec) {
+        float4 q;
+        q.x = __fmul_rn(x[k].x, p.t_sampling); q.y = __fmul_rn(x[k].y, p.t_sampling);
+        q.z = __fmul_rn(x[k].z, p.t_sampling); q.w = __fmul_rn(x[k].w, p.t_sampling);
+        c4[v] = q;
+        if (q.x != 0.0f || q.y != 0.0f || q.z != 0.0f || q.w != 0.0f) {
+          const int t = head + 4 * v;
+          t_first = min(t_first, t);
+          t_last = max(t_last, t + 3);
+        }
       }
     }
   }
@@ -391,7 +412,7 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
   F.event = event_d; F.saved = saved_d;
   F.row_counts = reinterpret_cast<int32_t*>(scratch_d);
   int32_t* offsets = F.row_counts + npix;
-  size_t smem = (size_t)FEE_WARPS * ntw * sizeof(float);
+  size_t smem = (size_t)FEE_WARPS * FEE_ROW_STRIDE(ntw) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     LARND_CUDA(cudaFuncSetAttribute(k_fee_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
