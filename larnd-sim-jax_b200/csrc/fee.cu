@@ -89,11 +89,29 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   // constant tail is filled in parallel.
   float total = 0.0f;
   if (lane == 0) {
+    // scalar head (t < head), whole vectors of the body (the window bounds sit on vector boundaries there; samples of a
+    // vector outside the window are zeros), scalar tail: one 128-bit load and store per four dependent adds
     float acc = 0.0f;
-#pragma unroll 8
-    for (int t = t_first; t <= t_last; ++t) {
+    int t = t_first;
+    for (; t <= t_last && t < head; ++t) {
       acc = __fadd_rn(acc, c[t]);
       c[t] = acc;
+    }
+    if (t <= t_last) {
+      const int vend = min(nvec - 1, (t_last - head) >> 2);
+#pragma unroll 4
+      for (int v = (t - head) >> 2; v <= vend; ++v) {
+        float4 q = c4[v];
+        acc = __fadd_rn(acc, q.x); q.x = acc;
+        acc = __fadd_rn(acc, q.y); q.y = acc;
+        acc = __fadd_rn(acc, q.z); q.z = acc;
+        acc = __fadd_rn(acc, q.w); q.w = acc;
+        c4[v] = q;
+      }
+      for (int t2 = max(t, head + 4 * nvec); t2 <= t_last; ++t2) {
+        acc = __fadd_rn(acc, c[t2]);
+        c[t2] = acc;
+      }
     }
     total = acc;
   }
