@@ -456,7 +456,15 @@ def run_ours(args):
                          "note": "accumulate is bound by instruction issue and L2 reduction throughput, not HBM (SURVEY §8d): "
                                  "see l2_red and contributions/s",
                          "l2_red": l2_red,
-                         "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3)},
+                         "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3),
+                         # the two streaming kernels of the step, which ARE HBM-bound (algorithmic bytes / measured time):
+                         # prepare reads the 104-byte record and writes the 31-word segment record; the front end reads
+                         # every waveform row once
+                         "hbm_kernels": {
+                             "k_prepare": {"achieved": nseg * (104 + 4 * 31) / (k_ms[0] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                           "frac": nseg * (104 + 4 * 31) / (k_ms[0] * 1e-3) / 1e9 / peak},
+                             "k_fee_forward": {"achieved": npix * (nticks - 1) * 4.0 / (k_ms[3] * 1e-3) / 1e9, "peak": peak,
+                                               "unit": "GB/s", "frac": npix * (nticks - 1) * 4.0 / (k_ms[3] * 1e-3) / 1e9 / peak}}},
             "setup_s": t_gen,
             "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
         }
