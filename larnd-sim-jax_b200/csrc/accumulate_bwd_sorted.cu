@@ -465,10 +465,11 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
   const int split = need <= 32 * 4 ? sorted_split_mode() : 0;
-  const int cap = LARND_BWD_SORTED_SLOTS / 3;
-  const int grid2 = sorted_grid(2, cap);
-  const int grid3 = split >= 1 ? sorted_grid(3, cap) : 0;
-  const int grid4 = split >= 2 ? sorted_grid(4, cap) : 0;
+  // every launch gets its full residency (2 / 3 / 4 CTAs per SM); only the optional third variant is capped by what is left
+  // of the per-CTA partial table
+  const int grid2 = sorted_grid(2, LARND_BWD_SORTED_SLOTS / 3);
+  const int grid3 = split >= 1 ? sorted_grid(3, LARND_BWD_SORTED_SLOTS / 2 - grid2 / 2) : 0;
+  const int grid4 = split >= 2 ? sorted_grid(4, LARND_BWD_SORTED_SLOTS - grid2 - grid3) : 0;
   // the kernels write disjoint slots of the per-CTA partial table
   int big_lo = 0;
   if (split >= 2) {
