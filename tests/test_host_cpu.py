@@ -352,3 +352,15 @@ def test_event_id_validators_have_the_reference_error_behaviour():
     bid = detsim.bin2id(p, bx, by, pl, ev)
     assert [t.tolist() for t in detsim.id2bin(p, bid)] == [bx.tolist(), by.tolist(), pl.tolist(), ev.tolist()]
     assert detsim.bin2id(p, torch.tensor([1400]), torch.tensor([0]), torch.tensor([0]), torch.tensor([0])).item() == -1
+
+
+def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) needs no GPU: one JSON line with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "segments/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["steps"] == 1 and "workload" in line["config"]
