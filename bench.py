@@ -232,7 +232,7 @@ def run_ours(args):
     st0 = sim.lut_forward(params, bank, tracks, fields, n_events=n_events)
     n_unique = int(st0.counts[0].item())
     npix = st0.npix
-    out = (st0.unique_pixels, st0.wfs_full)
+    out = (st0.unique_pixels, st0.wfs_buf)
     pod = st0.pod
     del st0
 

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define LARND_ABI_VERSION 1
+#define LARND_ABI_VERSION 2
 #define LARND_MAX_TPC 8
 #define LARND_MAX_TEMPLATES 128
 #define LARND_NB_TRAN_BINS 5   /* params.nb_tran_diff_bins, consts_jax.py:158,294 */
@@ -53,6 +53,14 @@ enum {
   LARND_E_CUDA = -2,      /* CUDA runtime error (message has the detail) */
   LARND_E_CAPACITY = -3   /* caller-provided capacity too small (host-side check) */
 };
+
+/* `flags` of larnd_lut_forward / _accumulate / _backward (every behaviour switch is an explicit argument: the library
+ * reads no environment variable). */
+#define LARND_FLAG_SKIP_GARBAGE 0x1  /* drop what the reference routes to the garbage row 0 (NOT reference-identical for wfs[0]) */
+#define LARND_FLAG_IMPL_CHUNK   0x2  /* force the chunk kernels (default: by batch size)            */
+#define LARND_FLAG_IMPL_SORTED  0x4  /* force the class-sorted tile kernels where they are supported  */
+#define LARND_FLAG_NO_SPLIT     0x8  /* class-sorted kernels: serve every tile with the 6-position variant */
+#define LARND_FLAG_PUBLIC_MASK  0xf
 
 /* Differentiable parameters (optimize/ranges.py:7-21).  Gradients are returned in this order. */
 enum {
@@ -122,6 +130,13 @@ int larnd_build_bank(const float* response_d, int nx, int ny, int nt, const floa
  * it is only read during this call. */
 int larnd_lut_create(const float* bank_d, int n_templates, int nx, int ny, int nt, int signal_length,
                      void* stream, larnd_lut_t** out);
+/* Second half of the table build, needed before any accumulate / backward call: the neighbourhood-sum rows for
+ * (nb_sampling_bins_per_pixel, number_pix_neighbors) — everything a segment deposits on neighbour pixels that are not main
+ * pixels lands in waveform row 0 (sim_jax.py:724-725), by linearity (sum over the whole neighbourhood) - (owned ones).
+ * This is the only call that allocates / mutates a LUT after creation; the per-batch entry points take a const handle,
+ * never allocate, and fail with LARND_E_ARG when the tables do not match their parameters.  Not concurrent with
+ * per-batch calls on the same handle. */
+int larnd_lut_prepare_neighbours(larnd_lut_t* lut, int nb_sampling_bins_per_pixel, int number_pix_neighbors, void* stream);
 void larnd_lut_destroy(larnd_lut_t* lut);
 
 /* Workspace (device) size for a batch of n_segments whose local event ids are < n_events
@@ -132,15 +147,19 @@ size_t larnd_workspace_bytes(int64_t n_segments, int32_t n_events, int32_t n_tpc
  *   unique_pixels_d (npix_capacity) int32 : sorted unique main-pixel ids, front-padded with -1 exactly
  *                                           like sim_jax.py:717-721 for a padded size of npix_capacity
  *   wfs_d (npix_capacity, n_ticks) float32: FULL waveform rows including garbage column 0
- *                                           (simulate_signals' return; simulate_wfs is wfs[:,1:])
+ *                                           (simulate_signals' return; simulate_wfs is wfs[:,1:]), row stride
+ *                                           wfs_row_stride floats (>= n_ticks).  With a 16-byte aligned base and a
+ *                                           stride that is a multiple of 4 and >= n_ticks + 3 (2004 for 2001 ticks) the
+ *                                           tile kernel flushes whole frames with red.global.add.v4.f32; any other
+ *                                           stride (e.g. n_ticks itself) is served with scalar reductions.  The
+ *                                           padding columns are zeroed.
  *   counts_d[4] int32                     : {n_unique_main_pixels, n_negative_ids, overflow_flag, n_chunks}
  * overflow_flag != 0 means npix_capacity < n_unique+1: outputs are then invalid.
- * flags: bit0 = skip the garbage row (contributions the reference routes to row 0 are dropped;
- *        NOT reference-identical for wfs[0]). */
+ * flags: LARND_FLAG_* above. */
 int larnd_lut_forward(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
                       const larnd_params_t* params, const larnd_lut_t* lut, int32_t n_events,
                       int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
-                      int32_t* unique_pixels_d, float* wfs_d, int32_t* counts_d, void* stream);
+                      int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream);
 
 /* Only the drift/pixelisation stage + unique/renumber (simulate_drift_new + sim_jax.py:717-725):
  * fills the workspace segment records and unique_pixels_d/counts_d.  Lets a caller size wfs exactly
@@ -150,8 +169,8 @@ int larnd_lut_prepare(const float* tracks_d, int64_t n_segments, const larnd_col
                       void* workspace_d, size_t workspace_bytes, int32_t* counts_d, void* stream);
 int larnd_lut_accumulate(int64_t n_segments, const larnd_params_t* params, const larnd_lut_t* lut,
                          int32_t n_events, int32_t npix_capacity, int32_t flags, void* workspace_d,
-                         size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d, int32_t* counts_d,
-                         void* stream);
+                         size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride,
+                         int32_t* counts_d, void* stream);
 
 /* VJP of simulate_wfs w.r.t. the LARND_NPARAMS fitted parameters.  Must follow a forward/prepare call
  * on the same workspace.  g_wfs_d is (npix_capacity, n_ticks) with row stride g_row_stride floats

@@ -35,6 +35,7 @@ struct AccArgs {
   const float* sc;
   int nt, L, Lp, ny_lut, nx_lut;
   int nticks;
+  int64_t wstride;  // row stride of wfs in floats
   int nb, half2;  // bins per pixel; 2*(nb/2) - 1
   int n_neigh, P;
   int nxp, nyp;   // pixels per plane
@@ -87,7 +88,7 @@ template <int NS>
 __device__ __forceinline__ void flush_row(float (&acc)[NS], float& g0, bool& g0_used, int row, int tbase,
                                           const AccArgs& A, int lane) {
   if (row >= 0) {
-    float* base = A.wfs + (int64_t)row * A.nticks;
+    float* base = A.wfs + (int64_t)row * A.wstride;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
       int col = tbase + 32 * j + lane;
@@ -536,25 +537,28 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
 }  // namespace
 
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                            int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
+                            int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts, cudaStream_t st) {
   if (n == 0) return LARND_OK;
   const bool slow_only = (flags & LARND_ACC_SLOW_ONLY) != 0;
   // (the forward tile kernel addresses the waveform buffer with signed 32-bit element offsets)
-  if (!slow_only && larnd_sorted_supported(p, lut) && (int64_t)npix_capacity * p.n_ticks < ((int64_t)1 << 31)) {
-    // large batches: class-sorted kernel (accumulate_sorted.cu).  LARND_ACC_IMPL = chunk | sorted overrides the size rule.
+  {
+    int rc0 = larnd_lut_check_neighbours(lut, p.nb_sampling_bins_per_pixel, p.number_pix_neighbors);
+    if (rc0) return rc0;
+  }
+  // (the tile kernel addresses the waveform buffer with signed 32-bit element offsets)
+  if (!slow_only && larnd_sorted_supported(p, lut) && (int64_t)npix_capacity * wfs_stride < ((int64_t)1 << 31)) {
+    // large batches: class-sorted kernel (accumulate_sorted.cu); LARND_FLAG_IMPL_CHUNK / _SORTED override the size rule
     bool sorted = n >= LARND_SORTED_MIN_SEGMENTS;
-    if (const char* e = getenv("LARND_ACC_IMPL")) sorted = e[0] == 's';
-    if (sorted) return larnd_launch_accumulate_sorted(n, p, lut, ws, npix_capacity, flags, wfs, counts, st);
+    if (flags & LARND_FLAG_IMPL_SORTED) sorted = true;
+    if (flags & LARND_FLAG_IMPL_CHUNK) sorted = false;
+    if (sorted) return larnd_launch_accumulate_sorted(n, p, lut, ws, npix_capacity, flags, wfs, wfs_stride, counts, st);
   }
   AccArgs A;
   A.rec = ws.rec; A.n = n;
-  {
-    int rc0 = larnd_lut_ensure_neighbour_sums(const_cast<larnd_lut*>(lut), p.nb_sampling_bins_per_pixel, p.number_pix_neighbors, st);
-    if (rc0) return rc0;
-  }
   A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm; A.sr = lut->sr; A.sc = lut->sc;
   A.nt = lut->nt; A.L = lut->L; A.Lp = lut->Lp; A.ny_lut = lut->ny; A.nx_lut = lut->nx;
   A.nticks = p.n_ticks;
+  A.wstride = wfs_stride;
   A.nb = p.nb_sampling_bins_per_pixel;
   A.half2 = 2 * (A.nb / 2) - 1;
   A.n_neigh = p.number_pix_neighbors;
@@ -564,11 +568,11 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.lk.n_unique = 0; A.lk.n_neg = 0; A.lk.npix = npix_capacity;
   A.counts = counts;
   A.wfs = wfs;
-  A.skip_garbage = flags & 1;
+  A.skip_garbage = flags & LARND_FLAG_SKIP_GARBAGE;
   A.slow_only = slow_only ? 1 : 0;
   const int64_t chunks = (n + S - 1) / S;
   // register window = run window (L + 2 + span) + slack for the tick drift between consecutive runs of a track;
-  // more slack = fewer flushes but more predicated-off slots in the inner loop.  LARND_ACC_NS overrides (tuning).
+  // more slack = fewer flushes but more predicated-off slots in the inner loop.
   int need = lut->L + 2 + SPAN_MAX;  // measured on B200: the tightest window wins (4 slots vs 6 at L=100: -15 % time)
   const size_t smem = sizeof(ChunkSmem);
   static bool attr_done = false;
@@ -581,11 +585,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
     LARND_CUDA(cudaFuncSetAttribute(k_lut_accumulate<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  int ns_sel = (need + 31) / 32;
-  if (const char* e = getenv("LARND_ACC_NS")) {
-    int v = atoi(e);
-    if (32 * v >= lut->L + 2 + SPAN_MAX) ns_sel = v;
-  }
+  const int ns_sel = (need + 31) / 32;
   if (!slow_only) prof_begin(1, st);
   if (ns_sel <= 4) k_lut_accumulate<4><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);
   else if (ns_sel <= 5) k_lut_accumulate<5><<<(unsigned)chunks, ACC_THREADS, smem, st>>>(A);

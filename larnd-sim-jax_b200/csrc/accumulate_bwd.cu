@@ -545,11 +545,11 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   k_garbage_grad_flag<<<32, 256, 0, st>>>(g_wfs, g_stride, p.n_ticks, counts, gflag);
   LARND_LAUNCH_CHECK("k_garbage_grad_flag");
   A.garbage_grad_nonzero = gflag;
-  // large batches: the class-sorted kernel (accumulate_bwd_sorted.cu) does the bulk.  LARND_BWD_IMPL / LARND_ACC_IMPL =
-  // chunk | sorted override the size rule (the tests force both paths on small batches).
+  // large batches: the class-sorted kernel (accumulate_bwd_sorted.cu) does the bulk.  LARND_FLAG_IMPL_CHUNK / _SORTED
+  // override the size rule (the tests force both paths on small batches).
   bool sorted = larnd_sorted_supported(p, lut) && n >= LARND_SORTED_MIN_SEGMENTS;
-  if (const char* e = getenv("LARND_BWD_IMPL")) sorted = larnd_sorted_supported(p, lut) && e[0] == 's';
-  else if (const char* e2 = getenv("LARND_ACC_IMPL")) sorted = larnd_sorted_supported(p, lut) && e2[0] == 's';
+  if (flags & LARND_FLAG_IMPL_SORTED) sorted = larnd_sorted_supported(p, lut) != 0;
+  if (flags & LARND_FLAG_IMPL_CHUNK) sorted = false;
   // (the tile kernel addresses the gradient rows with signed 32-bit element offsets)
   if ((int64_t)npix_capacity * g_stride >= ((int64_t)1 << 31)) sorted = false;
   A.sorted_active = sorted ? 1 : 0;

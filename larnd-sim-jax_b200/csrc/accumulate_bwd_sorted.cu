@@ -464,7 +464,7 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
     attr_done = true;
   }
   const int need = lut->L + 2 + SPAN_MAX_S;
-  const int split = need <= 32 * 4 ? sorted_split_mode() : 0;
+  const int split = need <= 32 * 4 ? sorted_split_mode(flags) : 0;
   // every launch gets its full residency (2 / 3 / 4 CTAs per SM); only the optional third variant is capped by what is left
   // of the per-CTA partial table
   const int grid2 = sorted_grid(2, LARND_BWD_SORTED_SLOTS / 3);
@@ -487,7 +487,7 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
   if (need <= 32 * 4) k_bwd_tiles<4, KPT><<<grid2, BT_THREADS, smem, st>>>(A, p, big_lo, SPAN_MAX_S, 2);
   else if (need <= 32 * 5) {
     int n5 = 0;
-    if (sorted_split_mode() >= 1) {  // 150-tick windows: 60 response registers, 2 CTAs/SM instead of 1
+    if (sorted_split_mode(flags) >= 1) {  // 150-tick windows: 60 response registers, 2 CTAs/SM instead of 1
       k_bwd_tiles<5, 4><<<grid2, BT_THREADS, smem, st>>>(A, p, 0, 2, 1);
       LARND_LAUNCH_CHECK("k_bwd_tiles<5,4>");
       A.partials += (int64_t)grid2 * 16;

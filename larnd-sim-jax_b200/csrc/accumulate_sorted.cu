@@ -1,180 +1,375 @@
-// K3' class-sorted lut_accumulate (forward), sm_100a — the large-batch path of simulate_signals
+// K3s class-sorted lut_accumulate (forward), sm_100a — the large-batch path of simulate_signals
 // (reference sim_jax.py:142-286; same arithmetic as accumulate.cu, different work decomposition).
 //
-// accumulate.cu walks a chunk of consecutive segments and re-reads the response rows from L1/L2 for every
-// (run, unit) pair: ~75 % of its instructions are gather/bookkeeping around the multiply-adds.  Here the runs of
-// the whole batch are first SORTED BY RESPONSE CLASS (longitudinal template index, sub-pixel bin inside the pixel):
-// every run of a class reads the same response rows for the same unit, so a warp loads the rows of its unit ONCE
-// into registers — for every tick of its 32*NS-tick window and every impulse position j < KPT the sample
-// R[x - 1 - j] — and then streams the runs of the class through pure FFMAs:
+// The runs of the whole batch are SORTED BY RESPONSE CLASS (longitudinal template index, sub-pixel bin inside the pixel,
+// tick span; sorted_runs.cuh) and cut into tiles of <= 32 runs.  A persistent CTA pulls a tile, stages its segments in
+// shared memory and then works in two phases that overlap freely between its 8 warps:
 //
-//   k_build_runs     chunk of 128 segments -> runs (same definition as accumulate.cu, only "fast" segments whose
-//                    whole window lies inside the readout), class histogram                          [global atomics]
-//   k_class_scan     exclusive scan of the histogram -> class offsets, tile table (<= 32 runs of one class)
-//   k_scatter_runs   counting-sort scatter of the run records
-//   k_acc_tiles      persistent CTAs pull tiles; per tile 8 warps pull units (merged diffusion-bin groups,
-//                    the neighbourhood-sum row, neighbour pixels that own a waveform row).  Per (unit, tile):
-//                    lane <-> run builds the impulse trains + boundary corrections in shared memory, then
-//                    lane <-> tick applies them from the register-resident response and flushes every
-//                    (run, unit) window with coalesced red.global.add.f32.
+//   phase A  main pixels (3-template blend on the <= 3x3 pixels the diffusion stencil reaches): warp <-> merged
+//            diffusion-bin group.  Every run of the tile reads the same three response rows for a group, so the warp
+//            holds them in REGISTERS and streams the runs through pure FFMAs.
+//   phase B  neighbour pixels (template 0, full segment charge): warp <-> run.  A run owns a waveform row for only
+//            ~15 % of its (2n+1)^2 neighbours; everything else lands in the garbage row 0 (sim_jax.py:724-725), which by
+//            linearity is (neighbourhood-sum response) - (owned neighbours).  The warp keeps that row-0 frame in registers
+//            while it walks the owned neighbours of its run and flushes it ONCE (the round-1 kernel flushed every owned
+//            window twice: +own row, -row 0).
 //
-// Segments whose window touches the ends of the readout (garbage tick 0 handling, sim_jax.py:177-178,243-244)
-// are left to accumulate.cu's per-segment path (larnd_launch_accumulate with mode = slow-only).
+// Output layout: lane <-> 4 consecutive ticks.  A run's frame starts at B = (tmin - 1) & ~3, so with a waveform row
+// stride that is a multiple of 4 every lane's float4 is 16-byte aligned and a 128-tick frame leaves as ONE
+// red.global.add.v4.f32 per lane (round 1: lane <-> tick, four scalar reductions).  The alignment shift s = (tmin-1) & 3
+// is absorbed by four pre-shifted copies of the response tables (lut_tables.cu::k_shift_rows): a lane reads the
+// NPOS + 3 samples its four ticks need with two or three aligned 128-bit loads, whatever s is.  Runs are ordered by s
+// inside a tile, so phase A reloads its registers at most four times per (tile, group).
+//
+// Segments whose window ends beyond the readout are left to accumulate.cu's per-segment path
+// (larnd_launch_accumulate with LARND_ACC_SLOW_ONLY); windows sticking out at the LOW end (garbage column 0,
+// sim_jax.py:177-178,243-244) are handled here by the generic flush.
 #include "sorted_runs.cuh"
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------ tile consumer
 constexpr int SEGMAX = TR * MAXLEN;  // segments per tile
+#ifndef LARND_KP4_CTAS
+#define LARND_KP4_CTAS 4
+#endif
+// Boundary corrections of a (run, unit) frame live at frame positions j + s <= KP + 2; a lane reads the four positions of
+// its ticks, lanes whose ticks lie beyond read the always-zero rows KP + 3 .. KP + 6 (no branch in the consume loops).
+// Row stride TRE = 33: a lane-dependent ROW with a uniform column must not land in one bank.
+constexpr int TRE = TR + 1;
+template <int KP> struct ECfg { static constexpr int USED = KP + 3, EK = KP + 7; };
+// per-warp train buffer: built as [run][3 j + template] (stride HS, conflict-free read-modify-write), then re-laid in place
+// as float4 [j][run] = (3 templates, 0) so that the consume loop fetches a position with ONE broadcast 128-bit load
+template <int KP> struct HCfg { static constexpr int FLOATS = (TR * HS > KP * TR * 4) ? TR * HS : KP * TR * 4; };
 
+template <int KP>
 struct TileSmem {
   int4 run[TR];                 // start, len | span << 16, tmin, class
   int ep[TR], mpx[TR], mpy[TR], soff[TR];
-  // per-segment data of the tile, staged once (thread <-> segment) and read by every unit's build phase
+  // per-segment data of the tile, staged once (thread <-> segment) and read by every group's build phase
   float qf[SEGMAX], qo[SEGMAX], ca[SEGMAX], cb[SEGMAX], cc[SEGMAX], fr[SEGMAX];
   int m[SEGMAX];                // T0 - tmin of the run
   float wxg[5][SEGMAX], wyg[5][SEGMAX];  // transverse weights merged per group of the class
   unsigned char owner[SEGMAX];
   float hN[TR][KPT];            // neighbour impulse train (full segment charge)
   float mom[TR][MS];            // neighbour correction moments A1,A2,A3,B1,B3 per position
-  float ph[NW][TR * HS];        // per-warp trains of the current unit: [run][3*j + template]
-  float pE[NW][TR * ES];        // per-warp merged boundary corrections: [run][position]
+  __align__(16) float ph[NW][HCfg<KP>::FLOATS];  // per-warp trains of the current group (see HCfg)
+  float pE[NW][ECfg<KP>::EK * TRE];               // per-warp boundary corrections: [frame position][run or unit]
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   signed char udx[225], udy[225];  // relative pixel of every neighbour unit (P <= 15)
-  int tile, next_unit, nseg;
-  int low_end;  // some run of the tile starts below tick 2 (its windows need the garbage-column handling)
+  int ubin[96];                 // neighbour unit -> response row (template 0 bin; entry P*P: the neighbourhood-sum row)
+  float ucl[96];                // ... and its running sum at Nt - L
+  unsigned smask[4];            // runs of the tile per alignment shift
+  int tile, next_unit, next_run, nseg;
+  int low_end;  // some run of the tile starts below tick 2 (its frames need the garbage-column handling)
 };
 
-template <int NS, int NR, int KP>
-__device__ __forceinline__ void load_response(float (&Rw)[3][NS][KP], const float* const (&rows)[NR], int Lp, int lane) {
+// KP = impulse positions whose response samples are held in registers: a lane's four ticks need samples
+// 4x + c + 7 - j (c < 4, j < KP) of the shifted row, i.e. floats [4x + WOFF, 4x + WOFF + WN)
+template <int KP> struct WCfg { static constexpr int WN = KP <= 4 ? 8 : 12, WOFF = KP <= 4 ? 4 : 0; };
+
+// [region: load_w]
+template <int NSV, int NR, int KP>
+__device__ __forceinline__ void load_w(float (&W)[3][NSV][WCfg<KP>::WN], const float* const (&rows)[NR], int lane) {
 #pragma unroll
   for (int r = 0; r < NR; ++r)
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
+    for (int v = 0; v < NSV; ++v)
 #pragma unroll
-      for (int j = 0; j < KP; ++j) {
-        const int ix = 32 * s + lane + 1 - j;  // sample k = x - 1 - j lives at row[k + 2]
-        Rw[r][s][j] = ((unsigned)ix < (unsigned)Lp) ? __ldg(rows[r] + ix) : 0.0f;
+      for (int q = 0; q < WCfg<KP>::WN / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(rows[r] + 128 * v + 4 * lane + WCfg<KP>::WOFF + 4 * q));
+        W[r][v][4 * q + 0] = t.x; W[r][v][4 * q + 1] = t.y; W[r][v][4 * q + 2] = t.z; W[r][v][4 * q + 3] = t.w;
       }
 }
 
-// Adds one (run, unit) window to a waveform row: acc = window part, Ev = merged boundary correction of this lane
-// (slot 0, lanes < ES).  Column of (slot s, lane) is tmin - 1 + 32 s + lane.  Window samples are valid on columns
-// >= 2, corrections on columns >= 1; what falls below goes to the garbage column 0 (sim_jax.py:177-178,243-244).
-// dst = address of this lane's tick of slot 0 (row base + tmin - 1 + lane); fast = no run of the tile starts below tick 2
-// (the window end is inside the row for every run of the sorted path: seg_is_fast).
-template <int NS, bool LP>
-__device__ __forceinline__ void emit_window(const float (&acc)[NS], float Ev, float* dst, int tmin, int nticks, int lane,
-                                            float sign, const bool (&act)[NS], bool fast) {
-  if (fast) {  // tile-uniform, the common case: every active tick of the window is a regular column of the row
-    // act[s] = this lane's tick of slot s lies inside the run window (L + 2 + span ticks, the same for every run of the
-    // tile): hoisted predicates instead of a zero test per slot; zero-valued adds inside the window are harmless
-    if (LP) {  // kernel-level constant: L + NPOS lies in [32 (NS - 1), 32 NS) for every NPOS
-      // the usual shape (the window ends inside the last slot): every lane of the other slots is active, so they need no
-      // predicate -- ptxas wraps every predicated reduction in BSSY / BRA / BSYNC
-      atomicAdd(dst, sign * (acc[0] + Ev));  // RED.E.ADD.F32, coalesced
+// [region: emit]
+__device__ __forceinline__ void red_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Frame of one (run, target row): lane holds columns B + 128 v + 4 lane + c; acc = window part (boundary corrections of
+// slot 0 already added by the caller on the fast paths).  d = address of this lane's first column.  v4: aligned rows, one
+// vector reduction per active slot; otherwise scalar reductions.
+template <int NSV>
+__device__ __forceinline__ void emit_fast(const float (&acc)[NSV][4], float* d, const bool (&act)[NSV], bool v4) {
+  if (v4) {
 #pragma unroll
-      for (int s = 1; s < NS - 1; ++s) atomicAdd(dst + 32 * s, sign * acc[s]);
-      if (act[NS - 1]) atomicAdd(dst + 32 * (NS - 1), sign * acc[NS - 1]);
-    } else {
-      if (act[0]) atomicAdd(dst, sign * (acc[0] + Ev));
-#pragma unroll
-      for (int s = 1; s < NS; ++s)
-        if (act[s]) atomicAdd(dst + 32 * s, sign * acc[s]);
-    }
+    for (int v = 0; v < NSV; ++v)
+      if (act[v]) red_v4(d + 128 * v, acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
   } else {
-    float* rowbase = dst - (tmin - 1) - lane;
-    float g = 0.0f;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      const int col = tmin - 1 + 32 * s + lane;
-      const float w = acc[s], e = (s == 0) ? Ev : 0.0f;
-      const float v = (col >= 2 ? w : 0.0f) + (col >= 1 ? e : 0.0f);
-      g += (col < 2 ? w : 0.0f) + (col < 1 ? e : 0.0f);
-      if (v != 0.0f && col < nticks) atomicAdd(rowbase + col, sign * v);
-    }
+    for (int v = 0; v < NSV; ++v)
+      if (act[v]) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-    if (lane == 0 && g != 0.0f) atomicAdd(rowbase, sign * g);
+        for (int c = 0; c < 4; ++c)
+          if (acc[v][c] != 0.0f) atomicAdd(d + 128 * v + c, acc[v][c]);
+      }
   }
 }
 
-// Consume loop of one unit: every run of `todo` gets its window computed from the register-resident response and flushed.
-// Two runs are in flight per iteration (independent FFMA chains hide the 4-cycle dependency latency) and the number of
-// impulse positions is a compile-time constant (uniform per tile: the class key contains the tick span).
-template <int NS, int NR, int NPOS, bool LP, int KP, bool TWO>
-__device__ __forceinline__ void consume_pairs(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KP], unsigned todo, int row,
-                                              const float* __restrict__ hbuf, int hstride, const float* __restrict__ Ebuf,
-                                              float* __restrict__ row0, int mode /* 0 own row, 1 sum row -> row0, 2 own row and -row0 */,
-                                              int lane) {
-  const bool fast = !sm.low_end;
-  // lane <-> run: 32-bit (signed: tmin - 1 may be negative on row 0) element offset of column tmin - 1 of the run's row
-  // inside the target buffer (the launcher keeps npix * nticks below 2^31 for this kernel); one shuffle + one wide add per
-  // window instead of 64-bit row arithmetic
-  float* const base = mode == 1 ? row0 : A.wfs;
-  const int myoff = (mode == 1 ? 0 : row * A.nticks) + (sm.run[lane].z - 1);
-  bool act[NS];  // window length of every run of the tile: L + 2 + span = L + NPOS ticks
+// Frames of runs that start below tick 2: window samples are valid on columns >= 2, corrections (e: this lane's four
+// ticks of slot 0) on columns >= 1, what falls below goes to the garbage column 0 (sim_jax.py:177-178,243-244).
+template <int NSV>
+__device__ __forceinline__ void emit_generic(const float (&acc)[NSV][4], const float (&e)[4], float* rowbase, int B, int nticks,
+                                             int lane, float sign) {
+  float g = 0.0f;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) act[s] = 32 * s + lane < A.L + NPOS;
+  for (int v = 0; v < NSV; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = B + 128 * v + 4 * lane + c;
+      const float w = acc[v][c], ee = (v == 0) ? e[c] : 0.0f;
+      const float val = (col >= 2 ? w : 0.0f) + (col >= 1 ? ee : 0.0f);
+      g += (col < 2 ? w : 0.0f) + (col < 1 ? ee : 0.0f);
+      if (val != 0.0f && col < nticks) atomicAdd(rowbase + col, sign * val);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  if (lane == 0 && g != 0.0f) atomicAdd(rowbase, sign * g);
+}
+
+// [region: conv_frame]
+// window part of a frame: acc[v][c] += sum_j sum_r h[NR j + r] W[r][v][c + 7 - j - WOFF]
+template <int NSV, int NR, int NPOS, int KP>
+__device__ __forceinline__ void conv_frame(float (&acc)[NSV][4], const float (&W)[3][NSV][WCfg<KP>::WN], const float* __restrict__ h) {
+#pragma unroll
+  for (int j = 0; j < NPOS; ++j) {
+    float u[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) u[r] = h[NR * j + r];
+#pragma unroll
+    for (int v = 0; v < NSV; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[v][c] = fmaf(u[r], W[r][v][c + 7 - j - WCfg<KP>::WOFF], acc[v][c]);
+  }
+}
+
+// [region: consume_main]
+// Phase A consume loop of one (group, shift): every run of `todo` gets its frame computed from the register-resident
+// response and flushed.  Two runs are in flight per iteration (independent FFMA chains) and the number of impulse
+// positions is a compile-time constant (uniform per tile: the class key contains the tick span).
+// myoff (lane <-> run) = element offset of the run's frame start (row * stride + B) inside the waveform buffer.
+template <int NSV, int NPOS, int KP>
+__device__ __forceinline__ void consume_main(const SortArgs& A, const TileSmem<KP>& sm, const float (&W)[3][NSV][WCfg<KP>::WN], unsigned todo,
+                                             int myoff, const float* __restrict__ hbuf, const float* __restrict__ Ebuf, int s, int lane,
+                                             int path) {
+  bool act[NSV];
+#pragma unroll
+  for (int v = 0; v < NSV; ++v) act[v] = 128 * v + 4 * lane - s < A.L + NPOS;
+  const float* const Elane = Ebuf + (4 * lane < ECfg<KP>::USED ? 4 * lane : ECfg<KP>::USED) * TRE;
+  const float4* const h4 = reinterpret_cast<const float4*>(hbuf);
+  float* const wl = A.wfs + 4 * lane;
   while (todo) {
     const int p0 = __ffs(todo) - 1;
     todo &= todo - 1;
-    const bool two = TWO && NR == 3 && todo != 0u;  // neighbour units (one template, dual flush) run one window at a time: measured faster
+    const bool two = todo != 0u;
     const int p1 = two ? __ffs(todo) - 1 : p0;
     if (two) todo &= todo - 1;
-    float* const d0 = base + (__shfl_sync(0xffffffffu, myoff, p0) + lane);
-    float* const d1 = base + (__shfl_sync(0xffffffffu, myoff, p1) + lane);
-    const int t0 = sm.run[p0].z, t1 = sm.run[p1].z;
-    const float* h0 = hbuf + p0 * hstride;
-    const float* h1 = hbuf + p1 * hstride;
-    float a0[NS], a1[NS];
+    const int off0 = __shfl_sync(0xffffffffu, myoff, p0), off1 = __shfl_sync(0xffffffffu, myoff, p1);
+    float a0[NSV][4], a1[NSV][4], e0[4], e1[4];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) { a0[s] = 0.0f; a1[s] = 0.0f; }
+    for (int c = 0; c < 4; ++c) { e0[c] = Elane[c * TRE + p0]; e1[c] = Elane[c * TRE + p1]; }
+#pragma unroll
+    for (int v = 0; v < NSV; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { a0[v][c] = v == 0 ? e0[c] : 0.0f; a1[v][c] = v == 0 ? e1[c] : 0.0f; }
 #pragma unroll
     for (int j = 0; j < NPOS; ++j) {
-      float u[NR], v[NR];
+      const float4 u4 = h4[j * TR + p0], w4 = h4[j * TR + p1];
+      const float u[3] = {u4.x, u4.y, u4.z}, w[3] = {w4.x, w4.y, w4.z};
 #pragma unroll
-      for (int r = 0; r < NR; ++r) { u[r] = h0[NR * j + r]; v[r] = h1[NR * j + r]; }
+      for (int v = 0; v < NSV; ++v)
 #pragma unroll
-      for (int s = 0; s < NS; ++s)
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          a0[s] = fmaf(u[r], Rw[r][s][j], a0[s]);
-          a1[s] = fmaf(v[r], Rw[r][s][j], a1[s]);
-        }
+          for (int r = 0; r < 3; ++r) {
+            a0[v][c] = fmaf(u[r], W[r][v][c + 7 - j - WCfg<KP>::WOFF], a0[v][c]);
+            a1[v][c] = fmaf(w[r], W[r][v][c + 7 - j - WCfg<KP>::WOFF], a1[v][c]);
+          }
     }
-    const float E0 = lane < ES ? Ebuf[p0 * ES + lane] : 0.0f;
-    const float E1 = lane < ES ? Ebuf[p1 * ES + lane] : 0.0f;
-    emit_window<NS, LP>(a0, E0, d0, t0, A.nticks, lane, 1.0f, act, fast);
-    if (mode == 2) emit_window<NS, LP>(a0, E0, row0 + (t0 - 1) + lane, t0, A.nticks, lane, -1.0f, act, fast);
-    if (two) {
-      emit_window<NS, LP>(a1, E1, d1, t1, A.nticks, lane, 1.0f, act, fast);
-      if (mode == 2) emit_window<NS, LP>(a1, E1, row0 + (t1 - 1) + lane, t1, A.nticks, lane, -1.0f, act, fast);
+    if (path < 2) {
+      emit_fast<NSV>(a0, wl + off0, act, path == 0);
+      if (two) emit_fast<NSV>(a1, wl + off1, act, path == 0);
+    } else {  // myoff = row * stride here (the frame start may lie below the row); window and corrections go separately
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { a0[0][c] -= e0[c]; a1[0][c] -= e1[c]; }
+      emit_generic<NSV>(a0, e0, A.wfs + off0, (sm.run[p0].z - 1) & ~3, A.nticks, lane, 1.0f);
+      if (two) emit_generic<NSV>(a1, e1, A.wfs + off1, (sm.run[p1].z - 1) & ~3, A.nticks, lane, 1.0f);
     }
   }
 }
 
-template <int NS, int NR, bool LP, int KP, bool TWO>
-__device__ __forceinline__ void consume_pairs_npos(const SortArgs& A, const TileSmem& sm, const float (&Rw)[3][NS][KP], unsigned todo, int row,
-                                                   const float* hbuf, int hstride, const float* Ebuf, float* row0, int mode, int lane, int npos) {
-  // warp-uniform: a short compare chain per unit; only the position counts this variant can meet (2 .. KP) are instantiated
+// [region: dispatch]
+template <int NSV, int KP>
+__device__ __forceinline__ void consume_main_npos(const SortArgs& A, const TileSmem<KP>& sm, const float (&W)[3][NSV][WCfg<KP>::WN], unsigned todo,
+                                                  int myoff, const float* hbuf, const float* Ebuf, int s, int lane, int path, int npos) {
+  // warp-uniform: only the position counts this variant can meet (2 .. KP) are instantiated
   constexpr int N3 = KP >= 3 ? 3 : KP, N4 = KP >= 4 ? 4 : KP, N5 = KP >= 5 ? 5 : KP;
-  if (KP >= 6 && npos >= 6) consume_pairs<NS, NR, KP, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else if (KP >= 5 && npos == 5) consume_pairs<NS, NR, N5, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else if (KP >= 4 && npos == 4) consume_pairs<NS, NR, N4, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else if (KP >= 3 && npos == 3) consume_pairs<NS, NR, N3, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
-  else consume_pairs<NS, NR, 2, LP, KP, TWO>(A, sm, Rw, todo, row, hbuf, hstride, Ebuf, row0, mode, lane);
+  if (KP >= 6 && npos >= 6) consume_main<NSV, KP, KP>(A, sm, W, todo, myoff, hbuf, Ebuf, s, lane, path);
+  else if (KP >= 5 && npos == 5) consume_main<NSV, N5, KP>(A, sm, W, todo, myoff, hbuf, Ebuf, s, lane, path);
+  else if (KP >= 4 && npos == 4) consume_main<NSV, N4, KP>(A, sm, W, todo, myoff, hbuf, Ebuf, s, lane, path);
+  else if (KP >= 3 && npos == 3) consume_main<NSV, N3, KP>(A, sm, W, todo, myoff, hbuf, Ebuf, s, lane, path);
+  else consume_main<NSV, 2, KP>(A, sm, W, todo, myoff, hbuf, Ebuf, s, lane, path);
 }
 
-// KP = impulse positions whose response samples are held in registers.  The KP = KPT kernel can serve every tile; with
-// KP = 4 (3) the response needs 48 (36) instead of 72 registers and three (four) CTAs fit on an SM — 24 (32) instead of 16
-// warps to hide the latencies the kernel is bound by.  A launch serves the tiles of spans span_lo .. span_hi (KP >= span_hi
-// + 2), a contiguous range of the tile table, and pulls them through its own counter gcnt[GC_FWD + launch].
-template <int NS, bool LP, int KP, bool TWO>
-__global__ void __launch_bounds__(TILE_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1))
+// [region: neigh_frame]
+// Phase B helpers.
+template <int NSV, int NPOS, int KP>
+__device__ __forceinline__ void neigh_frame(float (&acc)[NSV][4], const float (&e4)[4], const float* __restrict__ trow4 /* row + 4 lane */,
+                                            const float (&hreg)[KPT]) {
+  float W[NSV][WCfg<KP>::WN];
+#pragma unroll
+  for (int v = 0; v < NSV; ++v)
+#pragma unroll
+    for (int q = 0; q < WCfg<KP>::WN / 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(trow4 + 128 * v + WCfg<KP>::WOFF + 4 * q));
+      W[v][4 * q + 0] = t.x; W[v][4 * q + 1] = t.y; W[v][4 * q + 2] = t.z; W[v][4 * q + 3] = t.w;
+    }
+#pragma unroll
+  for (int v = 0; v < NSV; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[v][c] = v == 0 ? e4[c] : 0.0f;
+#pragma unroll
+  for (int j = 0; j < NPOS; ++j)
+#pragma unroll
+    for (int v = 0; v < NSV; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[v][c] = fmaf(hreg[j], W[v][c + 7 - j - WCfg<KP>::WOFF], acc[v][c]);
+}
+
+// [region: neigh_run setup]
+// One run of phase B (NPOS = span + 2 impulse positions, compile-time).  Units = the (2n+1)^2 neighbour pixels plus, as
+// unit P*P, the neighbourhood-sum row (row n0 + in-pixel bin of the shifted template-0 table); lane <-> unit (three words
+// of 32) for the row lookups and for the boundary corrections (every lane walks the <= NPOS positions of ITS unit: full
+// SIMD width), then the warp walks the owned units of the word with lane <-> 4 ticks.
+template <int NSV, int NPOS, int KP>
+__device__ __forceinline__ void neigh_run(const SortArgs& A, const TileSmem<KP>& sm, const RowLookup& lk, int p, float* __restrict__ myE,
+                                          float* row0, int lane, int basepath) {
+  const int4 e = sm.run[p];
+  const int tmin = e.z;
+  const int s = (tmin - 1) & 3, B = (tmin - 1) & ~3;
+  const int path = tmin < 2 ? 2 : basepath;
+  const int nu = A.P * A.P;
+  const int mpx = sm.mpx[p], mpy = sm.mpy[p], ep = sm.ep[p];
+  float hreg[KPT];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) hreg[j] = j < NPOS ? sm.hN[p][j] : 0.0f;
+  bool act[NSV];
+#pragma unroll
+  for (int v = 0; v < NSV; ++v) act[v] = 128 * v + 4 * lane - s < A.L + NPOS;
+  const float* const t4 = A.t0s + ((int64_t)s * A.n0rows * A.lps + 4 * lane);  // shifted copy s, this lane's ticks
+  float* const wl = A.wfs + 4 * lane;
+  const float* const Elane = myE + (4 * lane < ECfg<KP>::USED ? 4 * lane : ECfg<KP>::USED) * TRE;
+  const float* const mom = sm.mom[p];
+  const int ctbase = A.nt - A.L - tmin;
+  float acc0[NSV][4];  // frame of the garbage row: neighbourhood sum minus the neighbours that own a row
+#pragma unroll
+  for (int v = 0; v < NSV; ++v)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc0[v][c] = 0.0f;
+#pragma unroll 1
+  for (int k = 0; 32 * k <= nu; ++k) {
+    const int u = lane + 32 * k;
+    // [region: neigh lookups]
+    // ---- which units of this word own a waveform row ----
+    int row = -1;
+    if (u < nu) {
+      const int dx = sm.udx[u], dy = sm.udy[u];
+      if (dx != 0 || dy != 0) {  // the centre id is -999: row 0 only (inside the sum row)
+        const int pid = pixel2id_dev(mpx + dx, mpy + dy, ep, A.nxp, A.nyp);
+        row = lookup_row(lk, pid);
+        if (row <= 0) row = -1;
+        else if (A.skip_garbage && pid < 0) row = -1;
+      }
+    } else if (u == nu && !A.skip_garbage) row = 0;  // the neighbourhood-sum unit
+    unsigned m = __ballot_sync(0xffffffffu, row >= 0);
+    if (m == 0u) continue;
+    // [region: neigh corrections]
+    // ---- boundary corrections of the owned units (lane <-> unit): E_j = e0_j + e1_{j-1} at frame position j + s ----
+    int woff = 0, toff = 0;  // element offsets of the unit's frame start in wfs and of its response row in the table
+    if (row >= 0) {
+      const int bin = sm.ubin[u];
+      woff = (int)((int64_t)row * A.wstride) + (path < 2 ? B : 0);
+      toff = bin * A.lps;
+#pragma unroll
+      for (int q = 0; q < ECfg<KP>::USED; ++q) myE[q * TRE + lane] = 0.0f;
+      const float* crow = u == nu ? A.sc + (int64_t)(bin - A.n0) * A.nt : A.c0 + (int64_t)bin * A.nt;
+      const float Cl = sm.ucl[u];
+      float e1prev = 0.0f;
+      float* E = myE + s * TRE + lane;
+#pragma unroll
+      for (int j = 0; j < NPOS - 1; ++j) {  // positions 0 .. span
+        int ct = ctbase - j;
+        ct = max(0, min(ct, A.nt - 1));
+        const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
+        const float* mo = mom + 5 * j;
+        const float e1 = Cl * mo[0] - Ca * mo[1] - Cb * mo[2];
+        const float e0 = Cl * mo[3] - Ca * mo[2] - Cb * mo[4];
+        E[j * TRE] = e0 + e1prev;
+        e1prev = e1;
+      }
+      E[(NPOS - 1) * TRE] = e1prev;
+    }
+    __syncwarp();
+    // [region: neigh owned loop]
+    // ---- frames of the owned units ----
+    const int sumbit = (nu >> 5) == k ? (nu & 31) : -1;  // lane of the neighbourhood-sum unit in this word
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int wo = __shfl_sync(0xffffffffu, woff, b), to = __shfl_sync(0xffffffffu, toff, b);
+      float acc[NSV][4], e4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) e4[c] = Elane[c * TRE + b];
+      neigh_frame<NSV, NPOS, KP>(acc, e4, t4 + to, hreg);
+      if (path == 2) {  // low end: window and corrections follow different garbage rules, no register merging
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[0][c] -= e4[c];
+        if (b == sumbit) emit_generic<NSV>(acc, e4, row0, B, A.nticks, lane, 1.0f);
+        else {
+          emit_generic<NSV>(acc, e4, A.wfs + wo, B, A.nticks, lane, 1.0f);
+          if (!A.skip_garbage) emit_generic<NSV>(acc, e4, row0, B, A.nticks, lane, -1.0f);
+        }
+      } else if (b == sumbit) {
+#pragma unroll
+        for (int v = 0; v < NSV; ++v)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc0[v][c] += acc[v][c];
+      } else {
+        emit_fast<NSV>(acc, wl + wo, act, path == 0);
+#pragma unroll
+        for (int v = 0; v < NSV; ++v)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc0[v][c] -= acc[v][c];
+      }
+    }
+    __syncwarp();
+  }
+  if (!A.skip_garbage && path != 2) emit_fast<NSV>(acc0, row0 + B + 4 * lane, act, true);  // private copies are aligned
+}
+
+// [region: dispatch]
+template <int NSV, int KP>
+__device__ __forceinline__ void neigh_run_npos(const SortArgs& A, const TileSmem<KP>& sm, const RowLookup& lk, int p, float* myE, float* row0,
+                                               int lane, int basepath, int npos) {
+  constexpr int N3 = KP >= 3 ? 3 : KP, N4 = KP >= 4 ? 4 : KP, N5 = KP >= 5 ? 5 : KP;
+  if (KP >= 6 && npos >= 6) neigh_run<NSV, KP, KP>(A, sm, lk, p, myE, row0, lane, basepath);
+  else if (KP >= 5 && npos == 5) neigh_run<NSV, N5, KP>(A, sm, lk, p, myE, row0, lane, basepath);
+  else if (KP >= 4 && npos == 4) neigh_run<NSV, N4, KP>(A, sm, lk, p, myE, row0, lane, basepath);
+  else if (KP >= 3 && npos == 3) neigh_run<NSV, N3, KP>(A, sm, lk, p, myE, row0, lane, basepath);
+  else neigh_run<NSV, 2, KP>(A, sm, lk, p, myE, row0, lane, basepath);
+}
+
+// [region: kernel prologue]
+// A launch serves the tiles of spans span_lo .. span_hi (KP >= span_hi + 2), a contiguous range of the tile table, and
+// pulls them through its own counter gcnt[GC_FWD + launch].
+template <int NSV, int KP>
+__global__ void __launch_bounds__(TILE_THREADS, NSV == 1 ? (KP <= 4 ? LARND_KP4_CTAS : 3) : 2)
 k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int span_hi, const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_raw);
+  TileSmem<KP>& sm = *reinterpret_cast<TileSmem<KP>*>(smem_raw);
   if (A.counts[2] != 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nb = A.nb, L = A.L;
@@ -189,21 +384,21 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
     sm.udx[u] = (signed char)(u / A.P - A.n_neigh);
     sm.udy[u] = (signed char)(u % A.P - A.n_neigh);
   }
+  for (int i = threadIdx.x; i < NW * ECfg<KP>::EK * TRE; i += TILE_THREADS) (&sm.pE[0][0])[i] = 0.0f;  // incl. the always-zero rows
   const int tile_lo = A.gcnt[GC_SPAN + span_lo];
   const int ntiles = A.gcnt[GC_SPAN + span_hi + 1];
   int* const tile_counter = A.gcnt + GC_FWD + launch;
-  const int n_neigh_units = A.P * A.P;
-  const int n_units = 25 + 1 + n_neigh_units;  // merged diffusion groups, neighbourhood-sum row, neighbour pixels
   float* myh = sm.ph[warp];
   float* myE = sm.pE[warp];
-  // Waveform row 0 collects the neighbourhood sum of EVERY run (sim_jax.py:724-725): ~13 windows per run from all CTAs
-  // onto the same 8 KB would serialise in the L2 atomic units, so each CTA reduces into a private copy (summed by
-  // k_reduce_row0 afterwards).
-  float* row0 = A.row0 + (int64_t)blockIdx.x * A.nticks;
+  // Waveform row 0 collects the garbage of EVERY run (sim_jax.py:724-725): one frame per run from all CTAs onto the same
+  // 8 KB would serialise in the L2 atomic units, so each CTA reduces into a private copy (summed by k_reduce_row0).
+  float* row0 = A.row0 + (int64_t)blockIdx.x * A.r0stride;
+  const int basepath = A.v4ok ? 0 : 1;
 
   for (;;) {
+    // [region: tile pull]
     __syncthreads();  // everybody is done with the previous tile
-    if (threadIdx.x == 0) { sm.tile = tile_lo + atomicAdd(tile_counter, 1); sm.next_unit = 0; }
+    if (threadIdx.x == 0) { sm.tile = tile_lo + atomicAdd(tile_counter, 1); sm.next_unit = 0; sm.next_run = 0; }
     __syncthreads();
     const int tile = sm.tile;
     if (tile >= ntiles) break;
@@ -213,9 +408,10 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
     const int cls_b = cls % ncb;     // class = span * (ntpl * nb * nb) + (idx * nb + bxm) * nb + bym
     const int npos = cls / ncb + 2;  // impulse positions of every run of this tile
     const int bym = cls_b % nb, bxm = (cls_b / nb) % nb, idx = cls_b / (nb * nb);
+    // [region: stage runs]
     // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
     if (warp == 0) {
-      int len = 0;
+      int len = 0, tm = 2, sh = -1;
       if (lane < count) {
         const int4 e = A.runs[ti.y + lane];
         sm.run[lane] = e;
@@ -224,9 +420,16 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
         sm.mpx[lane] = floordiv_i(irec[(int64_t)LARND_I_BX * n + s0], nb);
         sm.mpy[lane] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
         len = e.y & 0xffff;
+        tm = e.z;
+        sh = (e.z - 1) & 3;
       }
-      const unsigned low = __ballot_sync(0xffffffffu, lane < count && sm.run[lane].z < 2);
+      const unsigned low = __ballot_sync(0xffffffffu, tm < 2);
       if (lane == 0) sm.low_end = low != 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned mq = __ballot_sync(0xffffffffu, sh == q);
+        if (lane == 0) sm.smask[q] = mq;
+      }
       int inc = len;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -238,7 +441,25 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
       for (int t = 0; t < len; ++t) sm.owner[off + t] = (unsigned char)lane;
       if (lane == 31) sm.nseg = inc;
     }
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + 96) {  // per-unit response rows of this class (warps 1-3)
+      const int u = threadIdx.x - 32, nu = A.P * A.P;
+      int bin = 0;
+      float cl = 0.0f;
+      if (u < nu) {
+        const int dx = u / A.P - A.n_neigh, dy = u % A.P - A.n_neigh;
+        const int vx = 2 * bxm - A.half2 - 2 * nb * dx, vy = 2 * bym - A.half2 - 2 * nb * dy;
+        bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
+        cl = __ldg(A.c0 + (int64_t)bin * A.nt + A.nt - L);
+      } else if (u == nu) {  // the neighbourhood-sum rows follow the nx * ny bins in the shifted table
+        const int sb = bxm * nb + bym;
+        bin = A.n0 + sb;
+        cl = __ldg(A.sc + (int64_t)sb * A.nt + A.nt - L);
+      }
+      sm.ubin[u] = bin;
+      sm.ucl[u] = cl;
+    }
     __syncthreads();
+    // [region: stage segments]
     // ---- stage the segments (thread <-> segment): products, Lagrange weights, group-merged transverse weights ---
     for (int i = threadIdx.x; i < sm.nseg; i += TILE_THREADS) {
       const int r = sm.owner[i];
@@ -269,6 +490,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
       }
     }
     __syncthreads();
+    // [region: moments]
     // ---- neighbour impulse train + correction moments (thread <-> run) -------------------------------------------
     if (threadIdx.x < count) {
       const int r = threadIdx.x;
@@ -287,141 +509,111 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
       }
     }
     __syncthreads();
+    const int pathA = sm.low_end ? 2 : basepath;
 
+    // [region: phaseA unit setup]
+    // ================= phase A: merged diffusion-bin groups (gi, gj), 3-template blend on a main pixel =================
     for (;;) {
       int unit = 0;
       if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);
       unit = __shfl_sync(0xffffffffu, unit, 0);
-      if (unit >= n_units) break;
-      float Rw[3][NS][KP];
-      if (unit < 25) {
-        // ---------------- merged diffusion-bin group (gi, gj): 3-template blend on a main pixel ----------------
-        const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
-        if (gi >= sm.g_n[bxm] || gj >= sm.g_n[bym]) continue;
-        const int bin = (int)sm.g_ci[bxm][gi] * 5 + (int)sm.g_ci[bym][gj];
-        const int ox = (int)sm.g_ox[bxm][gi] - 1, oy = (int)sm.g_ox[bym][gj] - 1;
-        int row = -1;
-        if (lane < count) {
-          const int pid = pixel2id_dev(sm.mpx[lane] + ox, sm.mpy[lane] + oy, sm.ep[lane], A.nxp, A.nyp);
-          row = lookup_row(lk, pid);  // not in the list -> dropped (sim_jax.py:152-154)
-          if (A.skip_garbage && pid < 0) row = -1;
-        }
-        if (__ballot_sync(0xffffffffu, row >= 0) == 0u) continue;
-        // build: lane <-> run
-        if (row >= 0) {
-          float* h = myh + lane * HS;
-          float* E = myE + lane * ES;
-#pragma unroll
-          for (int k = 0; k < 3 * KPT; ++k) h[k] = 0.0f;
-#pragma unroll
-          for (int k = 0; k < ES; ++k) E[k] = 0.0f;
-          const int4 e = sm.run[lane];
-          const int len = e.y & 0xffff, tmin = e.z, so = sm.soff[lane];
-          const float* crow = A.cm + (int64_t)(idx * 25 + bin) * A.nt;
-          const float Cl = __ldg(crow + A.nt - L);
-          const float* wxp = sm.wxg[gi];
-          const float* wyp = sm.wyg[gj];
-          for (int t = 0; t < len; ++t) {
-            const int i = so + t;
-            const int m = sm.m[i];
-            // boundary correction of this segment (sim_jax.py:236-247): D lands on tick T0 (weight 1-f) and T0-1 (f)
-            int ct = A.nt - L - (tmin + m);
-            ct = max(0, min(ct, A.nt - 1));
-            const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
-            const float w = wxp[i] * wyp[i];
-            const float qf = w * sm.qf[i], qo = w * sm.qo[i], f = sm.fr[i];
-            const float ca = sm.ca[i], cb = sm.cb[i], cc = sm.cc[i];
-            float* hm = h + 3 * m;
-            hm[0] = fmaf(qf, ca, hm[0]); hm[1] = fmaf(qf, cb, hm[1]); hm[2] = fmaf(qf, cc, hm[2]);
-            hm[3] = fmaf(qo, ca, hm[3]); hm[4] = fmaf(qo, cb, hm[4]); hm[5] = fmaf(qo, cc, hm[5]);
-            const float D = Cl - (Ca * (1.0f - f) + Cb * f);
-            E[m] = fmaf(qf, D, E[m]);
-            E[m + 1] = fmaf(qo, D, E[m + 1]);
-          }
-        }
-        __syncwarp();
-        const float* const rows[3] = {A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp, A.rm + (int64_t)(idx * 25 + bin) * A.Lp,
-                                      A.rm + (int64_t)((idx + 1) * 25 + bin) * A.Lp};
-        load_response<NS, 3, KP>(Rw, rows, A.Lp, lane);
-        // consume: lane <-> tick
-        consume_pairs_npos<NS, 3, LP, KP, TWO>(A, sm, Rw, __ballot_sync(0xffffffffu, row >= 0), row, myh, HS, myE, row0, 0, lane, npos);
-        __syncwarp();
-      } else {
-        // ---------------- neighbour pixels: template 0, full segment charge (sim_jax.py:197-225,250-261) ----------
-        // unit 25 = the neighbourhood-sum row into waveform row 0; the others add to the neighbour's own row (if it
-        // is a main pixel of the batch) and take the same deposit back out of row 0 (see accumulate.cu)
-        const bool sum_unit = unit == 25;
-        if (sum_unit && A.skip_garbage) continue;
-        const int u = unit - 26;
-        const int dx = sum_unit ? 0 : (int)sm.udx[u], dy = sum_unit ? 0 : (int)sm.udy[u];
-        if (!sum_unit && dx == 0 && dy == 0) continue;  // the centre id is -999: row 0 only (inside the sum row)
-        int row = -1;
-        if (lane < count) {
-          if (sum_unit) row = 0;
-          else {
-            const int pid = pixel2id_dev(sm.mpx[lane] + dx, sm.mpy[lane] + dy, sm.ep[lane], A.nxp, A.nyp);
-            row = lookup_row(lk, pid);
-            if (row <= 0) row = -1;
-            else if (A.skip_garbage && pid < 0) row = -1;
-          }
-        }
-        unsigned owned = __ballot_sync(0xffffffffu, row >= 0);
-        if (owned == 0u) continue;
-        const float* rowp0;
-        const float* crow;
-        if (sum_unit) {
-          const int sb = bxm * nb + bym;
-          rowp0 = A.sr + (int64_t)sb * A.Lp;
-          crow = A.sc + (int64_t)sb * A.nt;
-        } else {
-          const int vx = 2 * bxm - A.half2 - 2 * nb * dx, vy = 2 * bym - A.half2 - 2 * nb * dy;
-          const int bin = (abs(vx) >> 1) * A.ny_lut + (abs(vy) >> 1);
-          rowp0 = A.r0 + (int64_t)bin * A.Lp;
-          crow = A.c0 + (int64_t)bin * A.nt;
-        }
-        if (row >= 0) {  // merged corrections from the run's moments: E_j = e0_j + e1_{j-1}
-          const int4 e = sm.run[lane];
-          const int span = e.y >> 16, tmin = e.z;
-          const float Cl = __ldg(crow + A.nt - L);
-          float e1prev = 0.0f;
-          float* E = myE + lane * ES;
-#pragma unroll
-          for (int j = 0; j < ES; ++j) {
-            float Ej = 0.0f;
-            if (j <= span + 1) {
-              float e1 = 0.0f, e0 = 0.0f;
-              if (j <= span) {
-                int ct = A.nt - L - (tmin + j);
-                ct = max(0, min(ct, A.nt - 1));
-                const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
-                const float* mo = sm.mom[lane] + 5 * j;
-                e1 = Cl * mo[0] - Ca * mo[1] - Cb * mo[2];
-                e0 = Cl * mo[3] - Ca * mo[2] - Cb * mo[4];
-              }
-              Ej = e0 + e1prev;
-              e1prev = e1;
-            }
-            E[j] = Ej;
-          }
-        }
-        __syncwarp();
-        const float* const rows[1] = {rowp0};
-        load_response<NS, 1, KP>(Rw, rows, A.Lp, lane);
-        const bool dual = !sum_unit && !A.skip_garbage;
-        consume_pairs_npos<NS, 1, LP, KP, TWO>(A, sm, Rw, owned, row, &sm.hN[0][0], KPT, myE, row0, sum_unit ? 1 : (dual ? 2 : 0), lane, npos);
-        __syncwarp();
+      if (unit >= 25) break;
+      const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
+      if (gi >= sm.g_n[bxm] || gj >= sm.g_n[bym]) continue;
+      const int bin = (int)sm.g_ci[bxm][gi] * 5 + (int)sm.g_ci[bym][gj];
+      const int ox = (int)sm.g_ox[bxm][gi] - 1, oy = (int)sm.g_ox[bym][gj] - 1;
+      int row = -1;
+      if (lane < count) {
+        const int pid = pixel2id_dev(sm.mpx[lane] + ox, sm.mpy[lane] + oy, sm.ep[lane], A.nxp, A.nyp);
+        row = lookup_row(lk, pid);  // not in the list -> dropped (sim_jax.py:152-154)
+        if (A.skip_garbage && pid < 0) row = -1;
       }
+      const unsigned owned = __ballot_sync(0xffffffffu, row >= 0);
+      if (owned == 0u) continue;
+      // [region: phaseA build]
+      // build: lane <-> run
+      if (row >= 0) {
+        float* h = myh + lane * HS;
+#pragma unroll
+        for (int k = 0; k < 3 * KP; ++k) h[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ECfg<KP>::USED; ++k) myE[k * TRE + lane] = 0.0f;
+        const int4 e = sm.run[lane];
+        const int len = e.y & 0xffff, tmin = e.z, so = sm.soff[lane];
+        float* E = myE + ((tmin - 1) & 3) * TRE + lane;  // correction of position j sits at frame position j + s
+        const float* crow = A.cm + (int64_t)(idx * 25 + bin) * A.nt;
+        const float Cl = __ldg(crow + A.nt - L);
+        const float* wxp = sm.wxg[gi];
+        const float* wyp = sm.wyg[gj];
+        for (int t = 0; t < len; ++t) {
+          const int i = so + t;
+          const int m = sm.m[i];
+          // boundary correction of this segment (sim_jax.py:236-247): D lands on tick T0 (weight 1-f) and T0-1 (f)
+          int ct = A.nt - L - (tmin + m);
+          ct = max(0, min(ct, A.nt - 1));
+          const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, A.nt - 1));
+          const float w = wxp[i] * wyp[i];
+          const float qf = w * sm.qf[i], qo = w * sm.qo[i], f = sm.fr[i];
+          const float ca = sm.ca[i], cb = sm.cb[i], cc = sm.cc[i];
+          float* hm = h + 3 * m;
+          hm[0] = fmaf(qf, ca, hm[0]); hm[1] = fmaf(qf, cb, hm[1]); hm[2] = fmaf(qf, cc, hm[2]);
+          hm[3] = fmaf(qo, ca, hm[3]); hm[4] = fmaf(qo, cb, hm[4]); hm[5] = fmaf(qo, cc, hm[5]);
+          const float D = Cl - (Ca * (1.0f - f) + Cb * f);
+          E[m * TRE] = fmaf(qf, D, E[m * TRE]);
+          E[(m + 1) * TRE] = fmaf(qo, D, E[(m + 1) * TRE]);
+        }
+      }
+      {  // re-lay the trains in place: [run][3 j + template] -> float4 [j][run]
+        __syncwarp();
+        float hv[3 * KP];
+        if (row >= 0) {
+#pragma unroll
+          for (int k = 0; k < 3 * KP; ++k) hv[k] = myh[lane * HS + k];
+        }
+        __syncwarp();
+        if (row >= 0) {
+#pragma unroll
+          for (int j = 0; j < KP; ++j) reinterpret_cast<float4*>(myh)[j * TR + lane] = make_float4(hv[3 * j], hv[3 * j + 1], hv[3 * j + 2], 0.0f);
+        }
+      }
+      __syncwarp();
+      // [region: phaseA shift loop]
+      // element offset of the run's frame start (fast paths) / of its row (low-end tiles)
+      const int myoff = row >= 0 ? (int)((int64_t)row * A.wstride) + (pathA < 2 ? ((sm.run[lane].z - 1) & ~3) : 0) : 0;
+#pragma unroll 1
+      for (int s = 0; s < 4; ++s) {
+        const unsigned todo = owned & sm.smask[s];
+        if (todo == 0u) continue;
+        const float* const tb = A.tms + (int64_t)s * A.nmrows * A.lps;
+        const float* const rows[3] = {tb + (int64_t)((idx - 1) * 25 + bin) * A.lps, tb + (int64_t)(idx * 25 + bin) * A.lps,
+                                      tb + (int64_t)((idx + 1) * 25 + bin) * A.lps};
+        float W[3][NSV][WCfg<KP>::WN];
+        load_w<NSV, 3, KP>(W, rows, lane);
+        consume_main_npos<NSV, KP>(A, sm, W, todo, myoff, myh, myE, s, lane, pathA, npos);
+      }
+      __syncwarp();
+    }
+    // [region: phaseB pull]
+    // ================= phase B: neighbour pixels, template 0, full segment charge (sim_jax.py:197-225,250-261) =========
+    for (;;) {
+      int p = 0;
+      if (lane == 0) p = atomicAdd(&sm.next_run, 1);
+      p = __shfl_sync(0xffffffffu, p, 0);
+      if (p >= count) break;
+      neigh_run_npos<NSV, KP>(A, sm, lk, p, myE, row0, lane, basepath, npos);
     }
   }
 }
 
-__global__ void k_reduce_row0(const float* __restrict__ row0, int ncopies, int nticks, float* __restrict__ wfs) {
+__global__ void k_reduce_row0(const float* __restrict__ row0, int ncopies, int r0stride, int nticks, float* __restrict__ wfs) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nticks) return;
   float acc = 0.0f;
-  for (int k = 0; k < ncopies; ++k) acc += row0[(int64_t)k * nticks + c];
+  for (int k = 0; k < ncopies; ++k) acc += row0[(int64_t)k * r0stride + c];
   if (acc != 0.0f) atomicAdd(wfs + c, acc);
 }
+
+static_assert(sizeof(TileSmem<4>) <= 56 * 1024, "the 4-position tile kernel is sized for four CTAs per SM");
 
 }  // namespace
 
@@ -429,7 +621,8 @@ size_t larnd_sorted_workspace_bytes(int64_t n) {
   size_t b = 0;
   const size_t nn = (size_t)(n > 0 ? n : 1);
   b += align_up(nn * sizeof(int4), 256) * 2;                                       // runs_tmp, runs
-  b += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256) * 3;                    // class_count, class_start, cursor
+  b += align_up((size_t)LARND_NCLS_MAX * 4 * sizeof(int), 256) * 2;                // class_count, cursor (4 shift sub-buckets)
+  b += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);                        // class_start
   b += align_up((nn / TR + LARND_NCLS_MAX + 1) * sizeof(int4), 256);               // tile_info
   b += 256;                                                                        // counters
   b += align_up((size_t)LARND_ROW0_COPIES * LARND_ROW0_TICKS_MAX * sizeof(float), 256);  // private garbage rows
@@ -440,9 +633,9 @@ void larnd_carve_sorted(char* p, int64_t n, Workspace* ws) {
   const size_t nn = (size_t)(n > 0 ? n : 1);
   ws->runs_tmp = p; p += align_up(nn * sizeof(int4), 256);
   ws->runs = p; p += align_up(nn * sizeof(int4), 256);
-  ws->class_count = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
+  ws->class_count = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * 4 * sizeof(int), 256);
+  ws->cursor = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * 4 * sizeof(int), 256);
   ws->class_start = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
-  ws->cursor = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
   ws->tile_info = p; p += align_up((nn / TR + LARND_NCLS_MAX + 1) * sizeof(int4), 256);
   ws->gcnt = reinterpret_cast<int*>(p); p += 256;
   ws->row0 = reinterpret_cast<float*>(p);
@@ -451,84 +644,59 @@ void larnd_carve_sorted(char* p, int64_t n, Workspace* ws) {
 int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut) {
   const int nb = p.nb_sampling_bins_per_pixel;
   if (lut->ntpl * nb * nb * (SPAN_MAX_S + 1) > LARND_NCLS_MAX) return 0;
-  if (lut->L + 2 + SPAN_MAX_S > 32 * 6) return 0;
-  if (p.n_ticks > LARND_ROW0_TICKS_MAX) return 0;
+  if (lut->nsv == 0) return 0;                       // forward: frames of <= 256 ticks
+  if (lut->L + 2 + SPAN_MAX_S > 32 * 6) return 0;    // backward kernel: 6 slots of 32 ticks
+  if (p.n_ticks + 3 > LARND_ROW0_TICKS_MAX) return 0;
+  if (p.number_pix_neighbors > 4) return 0;          // phase B: three neighbour units per lane
   return 1;
 }
 
-
 int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                                   int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st) {
+                                   int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts,
+                                   cudaStream_t st) {
   if (n == 0) return LARND_OK;
   SortArgs A;
-  {
-    int rc0 = larnd_lut_ensure_neighbour_sums(const_cast<larnd_lut*>(lut), p.nb_sampling_bins_per_pixel, p.number_pix_neighbors, st);
-    if (rc0) return rc0;
-  }
   A.wfs = wfs;
-  A.skip_garbage = flags & 1;
+  A.wstride = wfs_stride;
+  A.v4ok = (reinterpret_cast<uintptr_t>(wfs) % 16 == 0) && wfs_stride % 4 == 0 && wfs_stride >= p.n_ticks + 3;
+  A.r0stride = (p.n_ticks + 3 + 3) & ~3;
+  A.skip_garbage = flags & LARND_FLAG_SKIP_GARBAGE;
   prof_begin(1, st);
   {
     int rc0 = sorted_fill_and_build(A, n, p, lut, ws, npix_capacity, counts, st);
     if (rc0) return rc0;
   }
-  const int need = lut->L + 2 + SPAN_MAX_S;
-  const int ns = need <= 32 * 4 ? 4 : (need <= 32 * 5 ? 5 : 6);
-  const int split = (ns == 4) ? sorted_split_mode() : 0;
-  const bool split5 = ns == 5 && sorted_split_mode() >= 1;  // 150-tick windows: 60 response registers, 2 CTAs/SM instead of 1
-  const int grid = sorted_grid(2, LARND_ROW0_COPIES);
-  const int grid3 = split ? sorted_grid(3, LARND_ROW0_COPIES) : 0;
-  const int grid4 = split >= 2 ? sorted_grid(4, LARND_ROW0_COPIES) : 0;
-  const int ncopies = max(grid, max(grid3, grid4));
-  if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)ncopies * p.n_ticks * sizeof(float), st));
-  const size_t smem = sizeof(TileSmem);
+  const int nsv = lut->nsv;
+  const int split = sorted_split_mode(flags);
+  const size_t smem4 = sizeof(TileSmem<4>), smem6 = sizeof(TileSmem<KPT>);
   static bool attr_done = false;
   if (!attr_done) {
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, true, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, true, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<6, false, KPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<5, false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<4, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<1, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<2, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
     attr_done = true;
   }
-  // LP: for every number of impulse positions (2 .. KPT) the run window L + NPOS ends inside the last 32-tick slot, so
-  // all other slots are flushed without a predicate
-  const bool lp = lut->L + 2 >= 32 * (ns - 1) && lut->L + KPT < 32 * ns;
+  const int grid_small = sorted_grid(nsv == 1 ? LARND_KP4_CTAS : 2, LARND_ROW0_COPIES);  // KP = 4 variant
+  const int grid_big = sorted_grid(nsv == 1 ? 3 : 2, LARND_ROW0_COPIES);
+  const int ncopies = max(grid_small, grid_big);
+  if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)ncopies * A.r0stride * sizeof(float), st));
   int big_lo = 0;  // first span left to the KPT kernel
-  if (split >= 2) {
-    if (lp) k_acc_tiles<4, true, 3, true><<<grid4, TILE_THREADS, smem, st>>>(A, 0, 1, 0); else k_acc_tiles<4, false, 3, true><<<grid4, TILE_THREADS, smem, st>>>(A, 0, 1, 0);
-    LARND_LAUNCH_CHECK("k_acc_tiles<3>");
-    big_lo = 2;
-  }
   if (split >= 1) {
-    if (lp) k_acc_tiles<4, true, 4, true><<<grid3, TILE_THREADS, smem, st>>>(A, big_lo, 2, 1); else k_acc_tiles<4, false, 4, true><<<grid3, TILE_THREADS, smem, st>>>(A, big_lo, 2, 1);
+    if (nsv == 1) k_acc_tiles<1, 4><<<grid_small, TILE_THREADS, smem4, st>>>(A, 0, 2, 1);
+    else k_acc_tiles<2, 4><<<grid_small, TILE_THREADS, smem4, st>>>(A, 0, 2, 1);
     LARND_LAUNCH_CHECK("k_acc_tiles<4>");
     big_lo = 3;
   }
-  if (ns == 4) { if (lp) k_acc_tiles<4, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); else k_acc_tiles<4, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); }
-  else if (ns == 5) {
-    if (split5) {
-      if (lp) k_acc_tiles<5, true, 4, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, 2, 1); else k_acc_tiles<5, false, 4, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, 2, 1);
-      LARND_LAUNCH_CHECK("k_acc_tiles<5,4>");
-      big_lo = 3;
-    }
-    if (lp) k_acc_tiles<5, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2); else k_acc_tiles<5, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, big_lo, SPAN_MAX_S, 2);
-  }
-  else { if (lp) k_acc_tiles<6, true, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); else k_acc_tiles<6, false, KPT, true><<<grid, TILE_THREADS, smem, st>>>(A, 0, SPAN_MAX_S, 2); }
+  if (nsv == 1) k_acc_tiles<1, KPT><<<grid_big, TILE_THREADS, smem6, st>>>(A, big_lo, SPAN_MAX_S, 2);
+  else k_acc_tiles<2, KPT><<<grid_big, TILE_THREADS, smem6, st>>>(A, big_lo, SPAN_MAX_S, 2);
   LARND_LAUNCH_CHECK("k_acc_tiles");
   if (!A.skip_garbage) {
-    k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, ncopies, p.n_ticks, wfs);
+    k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, ncopies, A.r0stride, p.n_ticks, wfs);
     LARND_LAUNCH_CHECK("k_reduce_row0");
   }
-  // segments whose window touches the ends of the readout: per-segment path of accumulate.cu
-  int rc = larnd_launch_accumulate(n, p, lut, ws, npix_capacity, flags | LARND_ACC_SLOW_ONLY, wfs, counts, st);
+  // segments whose window ends beyond the readout: per-segment path of accumulate.cu
+  int rc = larnd_launch_accumulate(n, p, lut, ws, npix_capacity, flags | LARND_ACC_SLOW_ONLY, wfs, wfs_stride, counts, st);
   prof_end(1, st);
   return rc;
 }

@@ -106,7 +106,8 @@ static int check_common(const larnd_params_t* p, const larnd_lut_t* lut, bool ne
   if (need_lut) {
     if (!lut) { larnd_set_error("lut is null"); return LARND_E_ARG; }
     if (lut->L != p->signal_length) { larnd_set_error("LUT was built for signal_length %d, params say %d", lut->L, p->signal_length); return LARND_E_ARG; }
-    if (lut->ntpl != p->n_templates) { larnd_set_error("LUT has %d templates, params say %d", lut->ntpl, p->n_templates); return LARND_E_ARG; }
+    // fewer bank rows than long_diff_template entries = a truncated bank: allowed, overflow is flagged on the device
+    if (lut->ntpl > p->n_templates) { larnd_set_error("LUT has %d templates, long_diff_template only %d", lut->ntpl, p->n_templates); return LARND_E_ARG; }
     int need = p->nb_sampling_bins_per_pixel * p->number_pix_neighbors + p->nb_sampling_bins_per_pixel / 2;
     if (need > lut->nx || need > lut->ny) {
       // the reference would index past the LUT (take(mode='fill') -> NaN), sim_jax.py:221-222,443
@@ -136,29 +137,32 @@ extern "C" int larnd_lut_prepare(const float* tracks_d, int64_t n, const larnd_c
 
 extern "C" int larnd_lut_accumulate(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
                                     int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
-                                    int32_t* unique_pixels_d, float* wfs_d, int32_t* counts_d, void* stream) {
+                                    int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream) {
   int rc = check_common(p, lut, true);
   if (rc) return rc;
-  if (!unique_pixels_d || !wfs_d || !counts_d || npix_capacity < 1) { larnd_set_error("larnd_lut_accumulate: bad argument"); return LARND_E_ARG; }
+  if (!unique_pixels_d || !wfs_d || !counts_d || npix_capacity < 1 || wfs_row_stride < p->n_ticks) {
+    larnd_set_error("larnd_lut_accumulate: bad argument (null pointer, capacity < 1 or row stride < n_ticks)");
+    return LARND_E_ARG;
+  }
   Workspace ws;
   if (!larnd_carve_workspace(workspace_d, workspace_bytes, n, n_events, p->n_tpc, p->n_pixels_x, p->n_pixels_y, &ws)) {
     larnd_set_error("workspace too small");
     return LARND_E_CAPACITY;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * p->n_ticks * sizeof(float), st));
+  LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * wfs_row_stride * sizeof(float), st));
   if ((rc = larnd_launch_unique(ws, *p, npix_capacity, /*extra=*/1, unique_pixels_d, counts_d, st))) return rc;
-  return larnd_launch_accumulate(n, *p, lut, ws, npix_capacity, flags, wfs_d, counts_d, st);
+  return larnd_launch_accumulate(n, *p, lut, ws, npix_capacity, flags & LARND_FLAG_PUBLIC_MASK, wfs_d, wfs_row_stride, counts_d, st);
 }
 
 extern "C" int larnd_lut_forward(const float* tracks_d, int64_t n, const larnd_columns_t* cols, const larnd_params_t* p,
                                  const larnd_lut_t* lut, int32_t n_events, int32_t npix_capacity, int32_t flags,
                                  void* workspace_d, size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d,
-                                 int32_t* counts_d, void* stream) {
+                                 int64_t wfs_row_stride, int32_t* counts_d, void* stream) {
   int rc = larnd_lut_prepare(tracks_d, n, cols, p, lut, n_events, workspace_d, workspace_bytes, counts_d, stream);
   if (rc) return rc;
   return larnd_lut_accumulate(n, p, lut, n_events, npix_capacity, flags, workspace_d, workspace_bytes, unique_pixels_d,
-                              wfs_d, counts_d, stream);
+                              wfs_d, wfs_row_stride, counts_d, stream);
 }
 
 extern "C" int larnd_lut_backward(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
@@ -173,6 +177,6 @@ extern "C" int larnd_lut_backward(int64_t n, const larnd_params_t* p, const larn
     larnd_set_error("workspace too small");
     return LARND_E_CAPACITY;
   }
-  return larnd_launch_accumulate_bwd(n, *p, lut, ws, npix_capacity, flags, g_wfs_d, g_row_stride, grad_params_d,
+  return larnd_launch_accumulate_bwd(n, *p, lut, ws, npix_capacity, flags & LARND_FLAG_PUBLIC_MASK, g_wfs_d, g_row_stride, grad_params_d,
                                      counts_d, (cudaStream_t)stream);
 }

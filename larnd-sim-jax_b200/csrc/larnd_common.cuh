@@ -23,8 +23,13 @@ struct larnd_lut {
   int sum_nb, sum_n;
   float* sr;  // [nb*nb][Lp]
   float* sc;  // [nb*nb][nt]
+  // Shifted copies for the lane <-> 4-ticks tile kernels (lut_tables.cu::k_shift_rows): T[s][row][i] = R_row[i - s - 8],
+  // s = 0..3, rows of lps = 128 * nsv + 8 floats (nsv = 128-tick slots of a run frame; 0 = L too long for those kernels).
+  int nsv, lps;
+  float* t0s;  // [4][nx*ny + nb*nb][lps]: template 0, then the neighbourhood-sum rows (built by larnd_lut_prepare_neighbours)
+  float* tms;  // [4][ntpl*25][lps]
 };
-int larnd_lut_ensure_neighbour_sums(larnd_lut* lut, int nb, int n, cudaStream_t st);
+int larnd_lut_check_neighbours(const larnd_lut* lut, int nb, int n);
 
 // Views into the caller-provided workspace.
 struct Workspace {
@@ -50,7 +55,7 @@ struct Workspace {
   float* row0;
 };
 
-#define LARND_NCLS_MAX (LARND_MAX_TEMPLATES * 11 * 11 * 5)  // response classes: template index x in-pixel bin x tick span
+#define LARND_NCLS_MAX (LARND_MAX_TEMPLATES * 11 * 11 * 5)  // response classes: template index x in-pixel bin x tick span (x 4 alignment-shift sub-buckets in the sort)
 #define LARND_ROW0_COPIES 512                            // private garbage-row copies (>= CTAs of k_acc_tiles)
 #define LARND_ROW0_TICKS_MAX 8192
 #define LARND_BWD_SORTED_SLOTS 1280                      // per-warp gradient partials of the class-sorted backward kernel
@@ -150,9 +155,10 @@ int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t np
                         int32_t* counts, cudaStream_t st);
 int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                            int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
+                            int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                                   int32_t npix_capacity, int32_t flags, float* wfs, const int32_t* counts, cudaStream_t st);
+                                   int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts,
+                                   cudaStream_t st);
 int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                        int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride,
                                        float* sorted_partials, int* n_slots_out, const int* gflag, const int32_t* counts,

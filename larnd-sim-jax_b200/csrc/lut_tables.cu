@@ -30,6 +30,22 @@ __global__ void k_compact_rows(const float* __restrict__ bank, int nx, int ny, i
   }
 }
 
+// Shifted copies for the lane <-> 4-ticks tile kernels (accumulate_sorted.cu): dst[s][r][i] = R_r[i - s - 8] (0 outside
+// [0, L)), s = 0..3, so that a lane whose four output ticks start at frame position 4x reads its response samples with
+// aligned 128-bit loads whatever the run's start tick modulo 4 is.  src rows are the compact rows (sample k at k + 2).
+// dst holds dst_rows rows per shift copy; the nrows source rows land at rows dst_row0 .. dst_row0 + nrows - 1 of every copy.
+__global__ void k_shift_rows(const float* __restrict__ src, int nrows, int L, int Lp, int lps, float* __restrict__ dst, int dst_rows,
+                             int dst_row0) {
+  const int64_t total = (int64_t)4 * nrows * lps;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % lps);
+    const int64_t rr = e / lps;
+    const int r = (int)(rr % nrows), s = (int)(rr / nrows);
+    const int k = i - s - 8;
+    dst[((int64_t)s * dst_rows + dst_row0 + r) * lps + i] = (k >= 0 && k < L) ? src[(int64_t)r * Lp + k + 2] : 0.0f;
+  }
+}
+
 // float32 running sum along time, strictly left to right (bit-identical to a sequential cumsum)
 __global__ void k_cumsum_rows(const float* __restrict__ bank, int nx, int ny, int nt, int ntpl,
                               float* __restrict__ c0, float* __restrict__ cm) {
@@ -76,18 +92,44 @@ __global__ void k_neighbour_sums(const float* __restrict__ r0, const float* __re
 
 }  // namespace
 
-int larnd_lut_ensure_neighbour_sums(larnd_lut* lut, int nb, int n, cudaStream_t st) {
+// Neighbourhood-sum rows for (nb, n): explicit, mutating call made once after larnd_lut_create (never from a per-batch
+// entry point: those take a const handle and only CHECK that the tables match their parameters).
+extern "C" int larnd_lut_prepare_neighbours(larnd_lut_t* lut, int nb, int n, void* stream) {
+  if (!lut || nb < 2 || n < 0 || n > 7) { larnd_set_error("larnd_lut_prepare_neighbours: invalid argument"); return LARND_E_ARG; }
   if (lut->sr && lut->sum_nb == nb && lut->sum_n == n) return LARND_OK;
-  if (lut->sr && lut->sum_nb != nb) { cudaFree(lut->sr); cudaFree(lut->sc); lut->sr = lut->sc = nullptr; }
+  if (nb * n + nb / 2 > lut->nx || nb * n + nb / 2 > lut->ny) {
+    larnd_set_error("number_pix_neighbors=%d needs %d response bins per axis, LUT has %dx%d", n, nb * n + nb / 2, lut->nx, lut->ny);
+    return LARND_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lut->sr && lut->sum_nb != nb) {
+    LARND_CUDA(cudaStreamSynchronize(st));
+    cudaFree(lut->sr); cudaFree(lut->sc); cudaFree(lut->t0s);
+    lut->sr = lut->sc = lut->t0s = nullptr;
+  }
   if (!lut->sr) {
     LARND_CUDA(cudaMalloc(&lut->sr, (size_t)nb * nb * lut->Lp * sizeof(float)));
     LARND_CUDA(cudaMalloc(&lut->sc, (size_t)nb * nb * lut->nt * sizeof(float)));
+    if (lut->nsv) LARND_CUDA(cudaMalloc(&lut->t0s, (size_t)4 * (lut->nx * lut->ny + nb * nb) * lut->lps * sizeof(float)));
   }
   k_neighbour_sums<<<nb * nb, 256, 0, st>>>(lut->r0, lut->c0, lut->ny, lut->nt, lut->Lp, nb, n, lut->sr, lut->sc);
   LARND_LAUNCH_CHECK("k_neighbour_sums");
+  if (lut->nsv) {  // shifted template-0 rows followed by the shifted neighbourhood-sum rows, one table per shift
+    const int n0 = lut->nx * lut->ny;
+    k_shift_rows<<<148 * 4, 256, 0, st>>>(lut->r0, n0, lut->L, lut->Lp, lut->lps, lut->t0s, n0 + nb * nb, 0);
+    k_shift_rows<<<64, 256, 0, st>>>(lut->sr, nb * nb, lut->L, lut->Lp, lut->lps, lut->t0s, n0 + nb * nb, n0);
+    LARND_LAUNCH_CHECK("k_shift_rows(t0s)");
+  }
   lut->sum_nb = nb;
   lut->sum_n = n;
   return LARND_OK;
+}
+
+int larnd_lut_check_neighbours(const larnd_lut* lut, int nb, int n) {
+  if (lut->sr && lut->sum_nb == nb && lut->sum_n == n) return LARND_OK;
+  larnd_set_error("LUT neighbour tables were not prepared for nb_sampling_bins_per_pixel=%d, number_pix_neighbors=%d: call "
+                  "larnd_lut_prepare_neighbours() after larnd_lut_create()", nb, n);
+  return LARND_E_ARG;
 }
 
 extern "C" int larnd_lut_create(const float* bank_d, int n_templates, int nx, int ny, int nt, int signal_length,
@@ -105,7 +147,12 @@ extern "C" int larnd_lut_create(const float* bank_d, int n_templates, int nx, in
   size_t n0 = (size_t)nx * ny, nm = (size_t)n_templates * 25;
   lut->r0 = lut->rm = lut->c0 = lut->cm = nullptr;
   lut->sr = lut->sc = nullptr;
+  lut->t0s = lut->tms = nullptr;
   lut->sum_nb = lut->sum_n = -1;
+  // frames of the tile kernels: run window (L + up to 6 impulse positions) + alignment shift (<= 3) in 128-tick slots
+  const int frame = signal_length + 6 + 3;
+  lut->nsv = frame <= 128 ? 1 : (frame <= 256 ? 2 : 0);
+  lut->lps = 128 * lut->nsv + 8;
   int rc = LARND_OK;
   auto fail = [&](int code) { larnd_lut_destroy(lut); return code; };
   if ((rc = larnd_check_cuda(cudaMalloc(&lut->r0, n0 * lut->Lp * sizeof(float)), "cudaMalloc r0"))) return fail(rc);
@@ -117,6 +164,11 @@ extern "C" int larnd_lut_create(const float* bank_d, int n_templates, int nx, in
   if ((rc = larnd_check_cuda(cudaGetLastError(), "k_compact_rows"))) return fail(rc);
   k_cumsum_rows<<<(nrows + 63) / 64, 64, 0, st>>>(bank_d, nx, ny, nt, n_templates, lut->c0, lut->cm);
   if ((rc = larnd_check_cuda(cudaGetLastError(), "k_cumsum_rows"))) return fail(rc);
+  if (lut->nsv) {
+    if ((rc = larnd_check_cuda(cudaMalloc(&lut->tms, 4 * nm * lut->lps * sizeof(float)), "cudaMalloc tms"))) return fail(rc);
+    k_shift_rows<<<148 * 4, 256, 0, st>>>(lut->rm, (int)nm, signal_length, lut->Lp, lut->lps, lut->tms, (int)nm, 0);
+    if ((rc = larnd_check_cuda(cudaGetLastError(), "k_shift_rows"))) return fail(rc);
+  }
   *out = lut;
   return LARND_OK;
 }
@@ -129,6 +181,8 @@ extern "C" void larnd_lut_destroy(larnd_lut_t* lut) {
   cudaFree(lut->cm);
   cudaFree(lut->sr);
   cudaFree(lut->sc);
+  cudaFree(lut->t0s);
+  cudaFree(lut->tms);
   delete lut;
 }
 

@@ -17,7 +17,7 @@ constexpr int PREP_THREADS = 128;
 
 __global__ void __launch_bounds__(PREP_THREADS)
 k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ larnd_columns_t cols,
-          const __grid_constant__ larnd_params_t p, int nt, float* __restrict__ rec, uint32_t* __restrict__ bitmap,
+          const __grid_constant__ larnd_params_t p, int nt, int bank_ntpl, float* __restrict__ rec, uint32_t* __restrict__ bitmap,
           int64_t n_words, int pid_offset, int32_t* __restrict__ counts) {
   extern __shared__ float srow[];
   const int ncols = cols.ncols;
@@ -79,6 +79,9 @@ k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ l
       if (p.long_diff_template[mid] < sl) lo = mid + 1; else hi = mid;
     }
     int idx = max(1, min(lo, p.n_templates - 2));
+    // a bank truncated to fewer rows than long_diff_template (tests bound memory that way) is valid as long as no segment
+    // needs a missing row; one that does is flagged (bit 2 of counts[2]) and clamped so that nothing reads out of bounds
+    if (idx + 1 >= bank_ntpl) { if (q != 0.0f) atomicOr(counts + 2, 4); idx = max(1, bank_ntpl - 2); }
     float t0v = p.long_diff_template[idx - 1], t1v = p.long_diff_template[idx], t2v = p.long_diff_template[idx + 1];
     float a = fdiv(fmul(fsub(sl, t1v), fsub(sl, t2v)), fmul(fsub(t0v, t1v), fsub(t0v, t2v)));
     float b = fdiv(fmul(fsub(sl, t0v), fsub(sl, t2v)), fmul(fsub(t1v, t0v), fsub(t1v, t2v)));
@@ -255,7 +258,7 @@ int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& 
   size_t smem = (size_t)PREP_THREADS * stride * sizeof(float);
   int64_t blocks = (n + PREP_THREADS - 1) / PREP_THREADS;
   prof_begin(0, st);
-  k_prepare<<<(unsigned)blocks, PREP_THREADS, smem, st>>>(tracks, n, cols, p, lut ? lut->nt : 0, ws.rec, ws.bitmap,
+  k_prepare<<<(unsigned)blocks, PREP_THREADS, smem, st>>>(tracks, n, cols, p, lut ? lut->nt : 0, lut ? lut->ntpl : p.n_templates, ws.rec, ws.bitmap,
                                                          ws.n_words, ws.pid_offset, counts);
   prof_end(0, st);
   LARND_LAUNCH_CHECK("k_prepare");

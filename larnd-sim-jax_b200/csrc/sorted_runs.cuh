@@ -4,10 +4,10 @@
 // A *run* = consecutive segments with the same (event, plane, sub-pixel bin, template index) whose start ticks lie
 // within SPAN_MAX_S of each other (at most MAXLEN segments).  Its *class* = (template index, bin inside the pixel,
 // tick span): all runs of a class read the same response rows for the same unit and have the same number of impulse
-// positions, so a tile (<= TR runs of one class) is uniform work.
+// positions, so a tile (<= TR runs of one class) is uniform work.  Inside a class the runs are ordered by the alignment
+// shift s = (tmin - 1) mod 4 of their tick frame (four sub-buckets of the counting sort), so the runs of a tile that share
+// a shift form a contiguous lane range and can share the register copy of the response rows (accumulate_sorted.cu).
 #pragma once
-#include <stdlib.h>
-
 #include "larnd_common.cuh"
 
 namespace {
@@ -46,6 +46,11 @@ struct SortArgs {
   RowLookup lk;
   const int32_t* counts;
   float* wfs;
+  int64_t wstride;  // row stride of wfs in floats
+  int v4ok;         // wfs is 16-byte aligned, wstride % 4 == 0 and >= nticks + 3: frames can be flushed with red.global.add.v4.f32
+  int r0stride;     // row stride of the private row-0 copies
+  const float* t0s; const float* tms;  // shifted response tables (larnd_lut)
+  int lps, n0 /* nx * ny */, n0rows /* rows per shift copy of t0s: n0 + nb * nb */, nmrows;
   int skip_garbage;
   int4* runs_tmp;
   int4* runs;
@@ -131,7 +136,7 @@ k_build_runs(const __grid_constant__ SortArgs A) {
     // span-major key: the tiles of every tick span form one contiguous range of the tile table
     const int cls = (tmax - tmin) * (A.ncls / (SPAN_MAX_S + 1)) + (s_idx[t] * nb + bxm) * nb + bym;
     A.runs_tmp[s_base + before] = make_int4((int)(base + t), len | ((tmax - tmin) << 16), tmin, cls);
-    atomicAdd(A.class_count + cls, 1);
+    atomicAdd(A.class_count + 4 * cls + ((tmin - 1) & 3), 1);
   }
 }
 
@@ -146,7 +151,8 @@ k_class_scan(const __grid_constant__ SortArgs A) {
   __syncthreads();
   for (int c0 = 0; c0 < A.ncls; c0 += 1024) {
     const int c = c0 + threadIdx.x;
-    const int cnt = c < A.ncls ? A.class_count[c] : 0;
+    const int4 sub = c < A.ncls ? reinterpret_cast<const int4*>(A.class_count)[c] : make_int4(0, 0, 0, 0);
+    const int cnt = sub.x + sub.y + sub.z + sub.w;
     int v[2] = {cnt, (cnt + TR - 1) / TR};
     int inc[2] = {v[0], v[1]};
 #pragma unroll
@@ -175,7 +181,7 @@ k_class_scan(const __grid_constant__ SortArgs A) {
     if (c < A.ncls) {
       if (c % (A.ncls / (SPAN_MAX_S + 1)) == 0) A.gcnt[GC_SPAN + c / (A.ncls / (SPAN_MAX_S + 1))] = ex[1];
       A.class_start[c] = ex[0];
-      A.cursor[c] = ex[0];
+      reinterpret_cast<int4*>(A.cursor)[c] = make_int4(ex[0], ex[0] + sub.x, ex[0] + sub.x + sub.y, ex[0] + sub.x + sub.y + sub.z);
       for (int i = 0; i < v[1]; ++i)  // tiles of this class
         A.tile_info[ex[1] + i] = make_int4(c, ex[0] + i * TR, min(TR, cnt - i * TR), 0);
     }
@@ -191,7 +197,7 @@ __global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
   const int nruns = A.gcnt[0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nruns; i += gridDim.x * blockDim.x) {
     const int4 e = A.runs_tmp[i];
-    const int pos = atomicAdd(A.cursor + e.w, 1);
+    const int pos = atomicAdd(A.cursor + 4 * e.w + ((e.z - 1) & 3), 1);
     A.runs[pos] = e;
   }
 }
@@ -204,6 +210,8 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   A.rec = ws.rec; A.n = n;
   A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm; A.sr = lut->sr; A.sc = lut->sc;
   A.nt = lut->nt; A.L = lut->L; A.Lp = lut->Lp; A.ny_lut = lut->ny;
+  A.t0s = lut->t0s; A.tms = lut->tms; A.lps = lut->lps;
+  A.n0 = lut->nx * lut->ny; A.n0rows = A.n0 + p.nb_sampling_bins_per_pixel * p.nb_sampling_bins_per_pixel; A.nmrows = lut->ntpl * 25;
   A.nticks = p.n_ticks;
   A.nb = p.nb_sampling_bins_per_pixel;
   A.half2 = 2 * (A.nb / 2) - 1;
@@ -221,7 +229,7 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   A.gcnt = ws.gcnt;
   A.ncls = lut->ntpl * A.nb * A.nb * (SPAN_MAX_S + 1);
   A.row0 = ws.row0;
-  LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * sizeof(int), st));
+  LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * 4 * sizeof(int), st));
   LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 256, st));
   const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
   k_build_runs<<<(unsigned)chunks, LARND_CHUNK, 0, st>>>(A);
@@ -235,17 +243,10 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   return LARND_OK;
 }
 
-// How the tile table is split over kernel variants (LARND_SORTED_SPLIT): 0 = one kernel holding KPT positions for all
-// tiles, 1 = spans 0-2 on the 4-position kernel (3 CTAs/SM) + the rest, 2 = spans 0-1 on the 3-position kernel (4 CTAs/SM),
-// span 2 on the 4-position kernel, the rest on the KPT kernel.
-inline int sorted_split_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("LARND_SORTED_SPLIT");
-    mode = e ? atoi(e) : 1;
-  }
-  return mode;
-}
+// How the tile table is split over kernel variants: by default the tiles of spans 0-2 go to the variant that holds 4 impulse
+// positions in registers (more CTAs per SM) and the rest to the KPT-position variant; LARND_FLAG_NO_SPLIT sends everything to
+// the latter.
+inline int sorted_split_mode(int flags) { return (flags & LARND_FLAG_NO_SPLIT) ? 0 : 1; }
 
 inline int sorted_grid(int per_sm, int cap) {
   int nsm = 148, dev = 0;

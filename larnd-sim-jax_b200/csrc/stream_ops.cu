@@ -149,6 +149,7 @@ __device__ __forceinline__ bool load_entry(const StreamArgs& A, const larnd_para
       if (p.long_diff_template[mid] < E.ld) l2 = mid + 1; else h2 = mid;
     }
     const int idx = max(1, min(l2, p.n_templates - 2));
+    if (idx + 1 >= lut.ntpl) { atomicOr(A.status, 4); E.row = -1; return false; }  // truncated bank: row missing (status bit2)
     E.x0 = p.long_diff_template[idx - 1]; E.x1 = p.long_diff_template[idx]; E.x2 = p.long_diff_template[idx + 1];
     E.a = (E.ld - E.x1) * (E.ld - E.x2) / ((E.x0 - E.x1) * (E.x0 - E.x2));
     E.b = (E.ld - E.x0) * (E.ld - E.x2) / ((E.x1 - E.x0) * (E.x1 - E.x2));
@@ -270,7 +271,7 @@ int stream_check(const larnd_params_t* p, const larnd_lut* lut, int64_t n_main, 
   if (!p || !lut) { larnd_set_error("larnd_signals_stream: null argument"); return LARND_E_ARG; }
   if (n_main < 0 || n_seg < 0) { larnd_set_error("larnd_signals_stream: negative size"); return LARND_E_ARG; }
   if (lut->L != p->signal_length) { larnd_set_error("LUT tables were built for signal_length %d, params say %d", lut->L, p->signal_length); return LARND_E_ARG; }
-  if (lut->ntpl != p->n_templates || p->n_templates < 3) { larnd_set_error("template count mismatch (%d vs %d)", lut->ntpl, p->n_templates); return LARND_E_ARG; }
+  if (lut->ntpl > p->n_templates || lut->ntpl < 3) { larnd_set_error("template count mismatch (bank %d vs long_diff_template %d)", lut->ntpl, p->n_templates); return LARND_E_ARG; }
   return LARND_OK;
 }
 

@@ -22,6 +22,9 @@ NPARAMS = 15
 PARAM_ORDER = ("Ab", "kb", "eField", "lifetime", "long_diff", "tran_diff", "shift_x", "shift_y", "shift_z",
                "alpha", "beta", "R_param", "lArDensity", "MeVToElectrons", "vdrift")
 
+# flags of larnd_lut_forward / _accumulate / _backward (include/larnd_b200.h)
+FLAG_SKIP_GARBAGE, FLAG_IMPL_CHUNK, FLAG_IMPL_SORTED, FLAG_NO_SPLIT = 1, 2, 4, 8
+
 # record fields inside the workspace (enum in larnd_b200.h)
 REC_FIELDS = ("Q", "FRAC", "SL", "A", "B", "C", "WX0", "WX1", "WX2", "WX3", "WX4", "WY0", "WY1", "WY2", "WY3", "WY4",
               "TD", "X0", "Y0", "ST", "REC", "FT", "XI", "COS2", "T0", "IDX", "BX", "BY", "EP", "FLAGS", "MAINPIX")
@@ -82,23 +85,29 @@ class LarndError(RuntimeError):
 _lib = None
 
 
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(os.path.dirname(HERE), "build")
+HEADERS = ["larnd_common.cuh", "sorted_runs.cuh", "bwd_chain.cuh", "segment_physics.cuh"]
+
+
 def nvcc_command(out=LIB_PATH, extra=()):
+    """The one-shot form of the build (all sources in one nvcc call); build_library compiles per file in parallel."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    return (["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-             "-Xcompiler", "-fPIC", "-shared", "-I" + INCLUDE, "-o", out] + list(extra) + srcs)
+    return ["nvcc"] + NVCC_FLAGS + ["-shared", "-I" + INCLUDE, "-o", out] + list(extra) + srcs
 
 
 def build_library(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into liblarnd_b200.so (in-tree, next to this file).  Safe to call from
-    several processes at once (torchrun ranks): the build runs under an exclusive file lock and writes to a temporary
-    name that is renamed into place."""
+    """Compile every CUDA source for sm_100a (one nvcc per translation unit, in parallel, objects cached under
+    larnd-sim-jax_b200/build/) and link liblarnd_b200.so in-tree, next to this file.  Safe to call from several processes
+    at once (torchrun ranks): the build runs under an exclusive file lock and the link writes to a temporary name that is
+    renamed into place."""
     import fcntl
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "larnd_common.cuh"), os.path.join(CSRC, "sorted_runs.cuh"), os.path.join(CSRC, "bwd_chain.cuh"),
-                   os.path.join(CSRC, "segment_physics.cuh"), os.path.join(INCLUDE, "larnd_b200.h")]
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "larnd_b200.h")]
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
 
     def fresh():
-        return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)
+        return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in srcs + hdrs)
 
     if not force and fresh():
         return LIB_PATH
@@ -107,15 +116,33 @@ def build_library(force=False, verbose=False):
         try:
             if not force and fresh():  # another process built it while we waited
                 return LIB_PATH
+            os.makedirs(BUILD_DIR, exist_ok=True)
+            jobs, objs = [], []
+            for src in srcs:
+                obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
+                objs.append(obj)
+                if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_time):
+                    continue
+                cmd = ["nvcc"] + NVCC_FLAGS + ["-I" + INCLUDE, "-c", src, "-o", obj]
+                jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            failed = []
+            for cmd, proc in jobs:
+                out, _ = proc.communicate()
+                if verbose or proc.returncode != 0:
+                    print(" ".join(cmd))
+                    print(out)
+                if proc.returncode != 0:
+                    failed.append(out)
+            if failed:
+                raise LarndError("nvcc failed:\n" + "\n".join(failed))
             tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-            cmd = nvcc_command(out=tmp)
+            cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs
             res = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or res.returncode != 0:
                 print(" ".join(cmd))
-                print(res.stdout)
-                print(res.stderr)
+                print(res.stdout + res.stderr)
             if res.returncode != 0:
-                raise LarndError("nvcc failed:\n" + res.stderr)
+                raise LarndError("link failed:\n" + res.stderr)
             os.replace(tmp, LIB_PATH)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
@@ -132,9 +159,10 @@ def _declare(lib):
     lib.larnd_lut_destroy.restype = None
     lib.larnd_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
     lib.larnd_workspace_bytes.restype = sz
-    lib.larnd_lut_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp]
+    lib.larnd_lut_prepare_neighbours.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.larnd_lut_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     lib.larnd_lut_prepare.argtypes = [vp, i64, PC, PP, vp, i32, vp, sz, vp, vp]
-    lib.larnd_lut_accumulate.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, vp, vp]
+    lib.larnd_lut_accumulate.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     lib.larnd_lut_backward.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     lib.larnd_fee_forward.argtypes = [vp, i64, vp, i32, PP, vp] + [vp] * 16 + [vp, sz, vp]
     lib.larnd_profile_enable.argtypes = [C.c_int]
@@ -185,7 +213,7 @@ def _declare(lib):
         lib.larnd_mc_forward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, vp, vp]
         lib.larnd_mc_backward.argtypes = [vp, i64, PC, PP, vp, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     for name in ("larnd_lut_create", "larnd_lut_forward", "larnd_lut_prepare", "larnd_lut_accumulate", "larnd_lut_backward",
-                 "larnd_fee_forward", "larnd_fee_backward", "larnd_mc_forward", "larnd_mc_backward"):
+                 "larnd_fee_forward", "larnd_fee_backward", "larnd_mc_forward", "larnd_mc_backward", "larnd_lut_prepare_neighbours"):
         if hasattr(lib, name):
             getattr(lib, name).restype = C.c_int
 
@@ -197,7 +225,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise LarndError("liblarnd_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                              "(the CUDA extension is mandatory, there is no CPU fallback)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(os.environ.get("LARND_B200_LIB", LIB_PATH))  # override: A/B timing of alternative builds (scripts/)
         _declare(lib)
         _lib = lib
     return _lib

@@ -8,6 +8,7 @@ wrapped in ``torch.autograd.Function`` (the role ``jax.custom_vjp`` plays for th
 INTEGRATION.md).  There is no CPU path: a missing library or a CPU tensor raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -98,7 +99,11 @@ def make_pod(params, lut_shape=None):
     tpl = np.asarray(params.long_diff_template, dtype=np.float32)
     if tpl.shape[0] > _lib.MAX_TEMPLATES:
         raise ValueError("too many longitudinal-diffusion templates")
-    P.n_templates = tpl.shape[0] if lut_shape is None else int(lut_shape[0])
+    if lut_shape is not None and int(lut_shape[0]) > tpl.shape[0]:
+        raise ValueError("response_template has %d templates, params.long_diff_template only %d" % (int(lut_shape[0]), tpl.shape[0]))
+    # the reference searches / clips with long_diff_template.shape[0] (sim_jax.py:163-164).  A bank with FEWER rows (tests
+    # truncate it to bound memory) is accepted; a segment that needs a missing row is flagged on the device (check_state)
+    P.n_templates = tpl.shape[0]
     for i, t in enumerate(tpl):
         P.long_diff_template[i] = t
     P.discrimination_threshold = params.DISCRIMINATION_THRESHOLD
@@ -142,14 +147,17 @@ def _check_cuda(t, name):
 
 # ------------------------------------------------------------------------------------------ LUT handle cache
 class _LutHandle:
-    def __init__(self, bank, L):
+    def __init__(self, bank, L, nb, n_neigh):
         self.bank = bank  # keeps the pointer alive / unique
         self.L = L
         self.shape = tuple(bank.shape)
         h = C.c_void_p()
         ntpl, nx, ny, nt = self.shape
-        _lib.check(_lib.get_lib().larnd_lut_create(_ptr(bank), ntpl, nx, ny, nt, L, _stream(), C.byref(h)))
+        lib = _lib.get_lib()
+        _lib.check(lib.larnd_lut_create(_ptr(bank), ntpl, nx, ny, nt, L, _stream(), C.byref(h)))
         self.handle = h
+        # the neighbourhood-sum tables belong to the table build, not to the per-batch calls (which take a const handle)
+        _lib.check(lib.larnd_lut_prepare_neighbours(h, int(nb), int(n_neigh), _stream()))
 
     def __del__(self):
         try:
@@ -162,18 +170,19 @@ class _LutHandle:
 _lut_cache = {}
 
 
-def get_lut(response_template, signal_length):
-    """Device tables (compacted response rows + running sums) for (response_template, signal_length); built
-    once and cached — the reference recomputes cumsum(response_template) on every call (sim_jax.py:228)."""
+def get_lut(response_template, signal_length, nb=10, n_neigh=0):
+    """Device tables (compacted response rows + running sums + neighbourhood sums) for (response_template, signal_length,
+    nb_sampling_bins_per_pixel, number_pix_neighbors); built once and cached — the reference recomputes
+    cumsum(response_template) on every call (sim_jax.py:228)."""
     _check_cuda(response_template, "response_template")
     if response_template.dtype != torch.float32 or response_template.dim() != 4:
         raise ValueError("response_template must be a float32 (n_templates, Nx, Ny, Nt) tensor")
     rt = response_template.contiguous()
-    key = (rt.data_ptr(), tuple(rt.shape), int(signal_length), rt.device.index, rt._version)
+    key = (rt.data_ptr(), tuple(rt.shape), int(signal_length), rt.device.index, rt._version, int(nb), int(n_neigh))
     h = _lut_cache.get(key)
     if h is None:
         with torch.cuda.device(rt.device):
-            h = _LutHandle(rt, int(signal_length))
+            h = _LutHandle(rt, int(signal_length), nb, n_neigh)
         if len(_lut_cache) > 8:
             _lut_cache.pop(next(iter(_lut_cache)))
         _lut_cache[key] = h
@@ -183,7 +192,7 @@ def get_lut(response_template, signal_length):
 # ------------------------------------------------------------------------------------------ LUT waveform simulation
 class LutState:
     """Everything a backward pass (or a kernel-level test) needs from one forward call."""
-    __slots__ = ("workspace", "counts", "n", "n_events", "npix", "pod", "lut", "unique_pixels", "wfs_full", "flags")
+    __slots__ = ("workspace", "counts", "n", "n_events", "npix", "pod", "lut", "unique_pixels", "wfs_full", "wfs_buf", "flags")
 
 
 def n_events_of(tracks, fields):
@@ -203,12 +212,13 @@ def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n
     tracks = tracks.contiguous()
     lib = _lib.get_lib()
     with torch.cuda.device(tracks.device):
-        lut = get_lut(response_template, params.signal_length)
+        lut = get_lut(response_template, params.signal_length, params.nb_sampling_bins_per_pixel, params.number_pix_neighbors)
         pod = make_pod(params, lut.shape)
         cols = make_columns(fields)
         n = tracks.shape[0]
         if n_events is None:
             n_events = n_events_of(tracks, fields)
+        flags = int(flags) | env_flags()
         ws_bytes = lib.larnd_workspace_bytes(n, n_events, pod.n_tpc, pod.n_pixels_x, pod.n_pixels_y)
         st = LutState()
         st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=tracks.device)
@@ -218,17 +228,63 @@ def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n
                                          _ptr(st.workspace), ws_bytes, _ptr(st.counts), _stream()))
         if npix_capacity is None:
             cnt = st.counts.cpu()
+            if int(cnt[2]) & 4:
+                raise ValueError("a segment's longitudinal diffusion needs a template row beyond the (truncated) response_template bank")
             if int(cnt[2]) != 0:
                 raise ValueError("eventID outside [-1, n_events) found in tracks")
             npix_capacity = pad_size(int(cnt[0]) + 1, "unique_pixels", 0.2)
         st.npix = int(npix_capacity)
         if out is None:
-            st.unique_pixels = torch.empty(st.npix, dtype=torch.int32, device=tracks.device)
-            st.wfs_full = torch.empty((st.npix, pod.n_ticks), dtype=torch.float32, device=tracks.device)
+            # -1 everywhere: if the device-side capacity / event-id check trips (counts[2] != 0) the kernels bail out and
+            # the caller still sees a well-defined "no pixel" list and all-zero waveforms (see check_state)
+            st.unique_pixels = torch.full((st.npix,), -1, dtype=torch.int32, device=tracks.device)
+            st.wfs_buf = alloc_wfs(st.npix, pod.n_ticks, tracks.device)
         else:
-            st.unique_pixels, st.wfs_full = out
+            st.unique_pixels, st.wfs_buf = out
+        if st.wfs_buf.dim() != 2 or st.wfs_buf.shape[0] != st.npix or st.wfs_buf.shape[1] < pod.n_ticks or st.wfs_buf.stride(1) != 1:
+            raise ValueError("waveform buffer must be (npix_capacity, >= n_ticks) float32 with unit column stride")
+        st.wfs_full = st.wfs_buf[:, :pod.n_ticks]
         _lib.check(lib.larnd_lut_accumulate(n, C.byref(pod), lut.handle, n_events, st.npix, st.flags, _ptr(st.workspace),
-                                            ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_full), _ptr(st.counts), _stream()))
+                                            ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_buf), st.wfs_buf.stride(0),
+                                            _ptr(st.counts), _stream()))
+    return st
+
+
+def wfs_row_stride(n_ticks):
+    """Row stride (floats) of the internal waveform buffer: a multiple of 4 that leaves three padding columns, so that the
+    tile kernel can flush whole 4-tick groups with one 16-byte reduction (include/larnd_b200.h, larnd_lut_forward)."""
+    return (int(n_ticks) + 3 + 3) // 4 * 4
+
+
+def alloc_wfs(npix, n_ticks, device):
+    return torch.empty((int(npix), wfs_row_stride(n_ticks)), dtype=torch.float32, device=device)
+
+
+def env_flags():
+    """Kernel-selection switches for tests and tuning, read HERE on the host and passed as explicit LARND_FLAG_* bits (the
+    library itself reads no environment variable): LARND_ACC_IMPL = chunk | sorted, LARND_SORTED_SPLIT = 0 (one kernel variant)."""
+    f = 0
+    impl = os.environ.get("LARND_ACC_IMPL", "")
+    if impl.startswith("c"):
+        f |= _lib.FLAG_IMPL_CHUNK
+    elif impl.startswith("s"):
+        f |= _lib.FLAG_IMPL_SORTED
+    if os.environ.get("LARND_SORTED_SPLIT", "") == "0":
+        f |= _lib.FLAG_NO_SPLIT
+    return f
+
+
+def check_state(st):
+    """Raises if the device-side checks of the forward call tripped: bit0 of counts[2] = npix_capacity < n_unique + 1,
+    bit1 = an eventID outside [-1, n_events).  With an explicit npix_capacity the forward call is fully asynchronous and
+    this check (one 16-byte D2H read) is the caller's; simulate_stochastic / the backward pass run it at their own sync."""
+    cnt = st.counts.cpu()
+    if int(cnt[2]) & 2:
+        raise ValueError("eventID outside [-1, n_events) found in tracks")
+    if int(cnt[2]) & 4:
+        raise ValueError("a segment's longitudinal diffusion needs a template row beyond the (truncated) response_template bank")
+    if int(cnt[2]) != 0:
+        raise _lib.LarndError("npix_capacity=%d is too small for %d unique pixels (+1 padding entry)" % (st.npix, int(cnt[0])))
     return st
 
 
@@ -243,8 +299,12 @@ def lut_backward(st, g_wfs, skip_garbage=False):
     grad = torch.zeros(_lib.NPARAMS, dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device):
         # column c of the full row (c >= 1) is g[:, c-1]: pass g - 1 element with stride Nticks-1
+        bflags = (1 if skip_garbage else 0) | (st.flags & ~1) | env_flags()
+        impl = os.environ.get("LARND_BWD_IMPL", "")
+        if impl:
+            bflags = (bflags & ~(_lib.FLAG_IMPL_CHUNK | _lib.FLAG_IMPL_SORTED)) | (_lib.FLAG_IMPL_SORTED if impl.startswith("s") else _lib.FLAG_IMPL_CHUNK)
         _lib.check(lib.larnd_lut_backward(st.n, C.byref(st.pod), st.lut.handle, st.n_events, st.npix,
-                                          1 if skip_garbage else 0, _ptr(st.workspace), st.workspace.numel(),
+                                          bflags, _ptr(st.workspace), st.workspace.numel(),
                                           _ptr(st.counts), C.c_void_p(g.data_ptr() - 4), nt1, _ptr(grad), _stream()))
     return grad
 
@@ -297,11 +357,12 @@ def simulate_drift_new(params, tracks, fields, response_template=None, n_events=
         n_events = n_events_of(tracks, fields)
     with torch.cuda.device(tracks.device):
         if response_template is not None:
-            lut = get_lut(response_template, params.signal_length)
+            lut = get_lut(response_template, params.signal_length, params.nb_sampling_bins_per_pixel, params.number_pix_neighbors)
             pod = make_pod(params, lut.shape)
         else:
             fake = _FakeLut(params)
-            lut, pod = fake, make_pod(params, fake.shape)
+            lut, pod = fake, make_pod(params)
+            pod.n_templates = fake.shape[0]  # only the template index record depends on it, which is not one of the outputs
         st = LutState()
         ws_bytes = lib.larnd_workspace_bytes(n, n_events, pod.n_tpc, pod.n_pixels_x, pod.n_pixels_y)
         st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=tracks.device)
@@ -344,10 +405,13 @@ class _FakeLut:
     def __init__(self, params, nt=1950):
         need = int(params.nb_sampling_bins_per_pixel) * int(params.number_pix_neighbors) + int(params.nb_sampling_bins_per_pixel) // 2
         need = max(need, 5)
-        key = (need, int(params.signal_length), nt, torch.cuda.current_device())
+        ntpl = 3
+        key = (need, int(params.signal_length), nt, torch.cuda.current_device(), ntpl, int(params.nb_sampling_bins_per_pixel),
+               int(params.number_pix_neighbors))
         h = _FakeLut._cache.get(key)
         if h is None:
-            h = _LutHandle(torch.zeros((3, need, need, nt), dtype=torch.float32, device="cuda"), int(params.signal_length))
+            h = _LutHandle(torch.zeros((ntpl, need, need, nt), dtype=torch.float32, device="cuda"), int(params.signal_length),
+                           params.nb_sampling_bins_per_pixel, params.number_pix_neighbors)
             _FakeLut._cache[key] = h
         self.handle, self.shape = h.handle, h.shape
 

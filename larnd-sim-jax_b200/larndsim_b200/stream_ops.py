@@ -61,7 +61,7 @@ class _SimulateSignals(torch.autograd.Function):
         dev = unique_pixels.device
         f32 = lambda a: a.detach().to(dev, torch.float32).contiguous().reshape(-1)
         i32 = lambda a: a.detach().to(dev, torch.int32).contiguous()
-        lut = sim.get_lut(response_template, params.signal_length)
+        lut = sim.get_lut(response_template, params.signal_length, params.nb_sampling_bins_per_pixel, params.number_pix_neighbors)
         pod = sim.make_pod(params, lut.shape)
         args = dict(up=i32(unique_pixels), pix=i32(pixels).reshape(-1), t0=f32(t0_after_diff), q=f32(nelectrons), ld=f32(long_diff),
                     ci=i32(currents_idx).reshape(-1, 2), qn=f32(nelectrons_neigh), rn=i32(pix_renumbering_neigh).reshape(-1),
@@ -83,7 +83,9 @@ class _SimulateSignals(torch.autograd.Function):
         st = int(status.item())
         if st:
             raise ValueError("simulate_signals: response index outside the LUT (%s)" %
-                             ("main bins must be < 5" if st & 1 else "number_pix_neighbors too large for this LUT"))
+                             ("main bins must be < 5" if st & 1 else
+                              "template row beyond the truncated response_template bank" if st & 4 else
+                              "number_pix_neighbors too large for this LUT"))
         ctx.args, ctx.pod, ctx.lut, ctx.shapes = args, pod, lut, (t0_after_diff.shape, nelectrons.shape, long_diff.shape,
                                                                 nelectrons_neigh.shape, t0_neigh.shape)
         return wfs

@@ -66,5 +66,12 @@ def srcline(loc):
                 srcs[p] = open(p).read().splitlines()
             return srcs[p][ln - 1].strip()[:100] if ln - 1 < len(srcs[p]) else ""
     return ""
-for loc, (ni, ns) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+TOP = int(os.environ.get("NCU_LINES_TOP", "45"))
+ops = collections.Counter()
+for (src, ni, ns), (loc, txt) in zip(prof[:n], insts[:n]):
+    t = txt.split()
+    op = t[1] if t and t[0].startswith("@") and len(t) > 1 else (t[0] if t else "?")
+    ops[op.split(".")[0]] += ni
+print("opcode mix: " + ", ".join("%s %.1f%%" % (k, 100.0 * v / tot) for k, v in ops.most_common(24)))
+for loc, (ni, ns) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:TOP]:
     print("%5.1f%% (smp %4.1f%%) %s:%d  %s" % (100.0 * ni / tot, 100.0 * ns / tots, loc[0], loc[1], srcline(loc)))

@@ -3,6 +3,8 @@
 Bars (north star): pixel ids, tick indices, template indices and hit sets bit-exact; waveforms within
 WFS_RTOL of the row maximum (float32 accumulation order differs from the oracle's float64 scatter-add);
 ADC values within ADC_ATOL counts; gradients within GRAD_RTOL of float64 central differences."""
+import os
+
 import numpy as np
 import pytest
 
@@ -181,6 +183,31 @@ def test_skip_garbage_flag_only_changes_garbage_rows(torch_dev, acc_impl):
     assert np.abs(s[~valid]).max() == 0.0
 
 
+def test_waveform_row_stride_variants_agree(torch_dev, acc_impl):
+    """The C ABI takes a waveform row stride: the padded stride (multiple of 4, n_ticks + 3: frames leave as 16-byte vector
+    reductions in the tile kernel), the bare n_ticks stride (scalar reductions) and a misaligned base must give the same
+    rows; padding columns stay zero."""
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = cm.synthetic_bank(32, 25, 25, 1950)
+    pp = cm.product_params(**kw)
+    tr = cm.small_batch(3000, pad=16, precision=0.01)
+    b, t = torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev)
+    ref = sim.lut_forward(pp, b, t, cm.FIELDS)
+    npix, nt = ref.npix, ref.pod.n_ticks
+    assert ref.wfs_buf.shape[1] % 4 == 0 and ref.wfs_buf.shape[1] >= nt + 3
+    assert float(ref.wfs_buf[:, nt:].abs().max()) == 0.0
+    a = ref.wfs_full.cpu().numpy()
+    scale = np.abs(a).max(axis=1, keepdims=True) + 1e-30
+    for buf in (torch.empty((npix, nt), device=torch_dev),                                  # reference layout, stride 2001
+                torch.empty(npix * (nt + 7) + 1, device=torch_dev)[1:].view(npix, nt + 7)):   # base not 16-byte aligned
+        st = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=npix, out=(torch.empty(npix, dtype=torch.int32, device=torch_dev), buf))
+        assert np.array_equal(st.unique_pixels.cpu().numpy(), ref.unique_pixels.cpu().numpy())
+        w = st.wfs_full.cpu().numpy()
+        assert (np.abs(w - a)[:, 1:] <= 2 * WFS_RTOL * scale + 1e-4).all()
+
+
 def test_empty_and_all_padding_batches(torch_dev):
     import torch
     from larndsim_b200 import sim
@@ -212,8 +239,15 @@ def test_capacity_overflow_and_bad_event_ids_are_flagged(torch_dev):
     b, t = torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev)
     st = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=2)
     assert st.counts.cpu().numpy()[2] & 1
+    # nothing was written: the caller sees "no pixel" and zero waveforms, and check_state turns the flag into an exception
+    assert (st.unique_pixels.cpu().numpy() == -1).all() and float(st.wfs_full.abs().max()) == 0.0
+    from larndsim_b200 import LarndError
+    with pytest.raises(LarndError):
+        sim.check_state(st)
     st = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=64, n_events=1)   # events 1.. are out of the declared range
     assert st.counts.cpu().numpy()[2] & 2
+    with pytest.raises(ValueError):
+        sim.check_state(st)
     with pytest.raises(ValueError):
         sim.lut_forward(pp, b, t, cm.FIELDS, n_events=1)
     from larndsim_b200 import LarndError
@@ -272,6 +306,55 @@ def test_lut_gradients_match_float64_finite_differences(torch_dev, acc_impl):
     assert grad[_lib.PARAM_ORDER.index("vdrift")] == 0.0   # params.vdrift is never read by the reference
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])   # BOX, BIRKS, ELLIPSOID (consts_jax.py:20-23)
+def test_all_fitted_leaves_in_every_recombination_model(torch_dev, mode, acc_impl):
+    """Forward parity of the FUSED prepare/accumulate kernels in the Box and Ellipsoid models (quenching_jax.py:18-35) and
+    finite-difference checks of every leaf of LARND_P_* the model reads: the Birks pair (Ab, kb) or the Box/Ellipsoid set
+    (alpha, beta, R_param), lArDensity, MeVToElectrons, eField, lifetime, the two diffusion coefficients and all three
+    shifts — 15/15 leaves over the three modes (vdrift is identically zero: params.vdrift has no reader)."""
+    import torch
+    import larndsim_b200 as lb
+    from larndsim_b200 import _lib, sim
+    kw = dict(number_pix_neighbors=1, signal_length=100)
+    extra = dict(recombination_mode=mode, shift_x=0.013, shift_y=-0.021, shift_z=0.017)
+    op = cm.oracle_params(**kw).replace(**extra)
+    pp = cm.product_params(**kw).replace(**dict(extra, recombination_mode=lb.RecombinationMode(mode)))
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    tr = cm.small_batch(300, ibatch=2, pad=4, precision=0.01)
+    # forward: records of the fused prepare kernel + waveforms + hit set against the float32 oracle
+    wfs_o, uniq_o, d_o, full_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={}, return_aux=True)
+    b, t = torch.as_tensor(bank, device=torch_dev), torch.as_tensor(tr, device=torch_dev)
+    st = sim.lut_forward(pp, b, t, cm.FIELDS, npix_capacity=len(uniq_o))
+    assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o)
+    _check_records(st, d_o, op, kw["signal_length"])
+    _check_wfs(st.wfs_full.cpu().numpy(), full_o)
+    _hits_equal(lo.simulate_stochastic(op, wfs_o, uniq_o), sim.simulate_stochastic(pp, st.wfs_full[:, 1:], st.unique_pixels, 0))
+    # gradients against float64 central differences of the oracle
+    npix = len(uniq_o)
+    rng = np.random.default_rng(11 + mode)
+    tt = np.arange(2000)
+    G = (rng.uniform(0.5, 1.5, (npix, 1)) * (1 + 0.5 * np.sin(tt[None, :] / 41.0 + rng.uniform(0, 6, (npix, 1))))).astype(np.float32)
+
+    def L(p):
+        w, _ = lo.simulate_wfs(p, bank, tr, cm.FIELDS, dt=np.float64, pad_to=npix)
+        return float((w * G.astype(np.float64)).sum())
+
+    grad = sim.lut_backward(st, torch.as_tensor(G, device=torch_dev)).cpu().numpy()
+    steps = dict(eField=1e-7, lifetime=1e-2, long_diff=1e-11, tran_diff=1e-11, shift_x=1e-6, shift_y=1e-6, shift_z=1e-6,
+                 MeVToElectrons=1e-1, lArDensity=1e-6)
+    steps.update(dict(Ab=1e-6, kb=1e-7) if mode == 2 else dict(alpha=1e-6, beta=1e-6))
+    if mode == 3:
+        steps["R_param"] = 1e-5
+    for name, h in steps.items():
+        base = getattr(op, name)
+        fd = (L(op.replace(**{name: base + h})) - L(op.replace(**{name: base - h}))) / (2 * h)
+        g = grad[_lib.PARAM_ORDER.index(name)]
+        assert abs(g - fd) <= GRAD_RTOL * abs(fd) + 1e-6 * abs(grad).max(), (mode, name, g, fd)
+    unused = {1: ("Ab", "kb", "R_param"), 2: ("alpha", "beta", "R_param"), 3: ("Ab", "kb")}[mode] + ("vdrift",)
+    for name in unused:   # leaves the model does not read
+        assert grad[_lib.PARAM_ORDER.index(name)] == 0.0, name
+
+
 def test_autograd_end_to_end(torch_dev, acc_impl):
     """build_params_class leaves get gradients through simulate_wfs + simulate_stochastic, like jax.grad in the reference."""
     import torch
@@ -323,9 +406,16 @@ def test_mc_mode_matches_oracle(torch_dev):
         assert len(got[0]) == len(out_o[0])
         assert np.array_equal(got[4], out_o[4]) and np.array_equal(got[7], out_o[7])
         assert np.abs(got[0] - out_o[0]).max() <= ADC_ATOL
-    # gradients of the diffusion-in-current variant
-    op = cm.oracle_params(**kw)
-    pp = cm.product_params(**kw)
+    # gradients of both current models (diffusion inside the current model / plain exponentials + smeared z)
+    for diff_in_current in (True, False):
+        _mc_gradient_check(torch_dev, kw, diff_in_current, rng)
+
+
+def _mc_gradient_check(torch_dev, kw, diff_in_current, rng):
+    import torch
+    from larndsim_b200 import _lib, sim
+    op = cm.oracle_params(**kw).replace(diffusion_in_current_sim=diff_in_current)
+    pp = cm.product_params(**kw).replace(diffusion_in_current_sim=diff_in_current)
     tr = cm.small_batch(300, ibatch=1, pad=0, precision=0.01)
     rnd = rng.normal(size=(tr.shape[0], 3)).astype(np.float32)
     _, wfull, uniq = lo.simulate_parametrized(op, tr, cm.FIELDS, rnd, history={}, return_wfs=True)
@@ -376,6 +466,47 @@ def test_full_fixture_batch_and_size_independent_properties(torch_dev, acc_impl)
         for p, w in zip(part.unique_pixels.cpu().numpy(), part.wfs_full.cpu().numpy()):
             if p >= 0:
                 _check_wfs(w[None, 1:], tot[int(p)][None, 1:])
+
+
+def _oracle_batch(job):
+    """Worker of test_all_prepared_inputs_forward_matches_oracle (module level: picklable for the process pool)."""
+    ifile, ib = job
+    arr, _ = cm.fixture_batches(ifile, 0.005)[ib]
+    op = cm.oracle_params()
+    bank = cm.synthetic_bank(32, 45, 45, 1950)
+    wfs_o, uniq_o = lo.simulate_wfs(op, bank, arr, cm.FIELDS, history={})
+    hits = lo.simulate_stochastic(op, wfs_o, uniq_o)
+    real = uniq_o >= 0
+    return ifile, ib, uniq_o, [np.asarray(h) for h in hits], wfs_o[real].astype(np.float32)
+
+
+def test_all_prepared_inputs_forward_matches_oracle(torch_dev):
+    """BASELINE config 2: every batch of all 22 un-shifted prepared_data inputs (optimize/simulate_test.sh settings: 0.005 cm,
+    n = 4, L = 100, max_batch_len 50, no noise; ~0.84 M chopped segments) through simulate_wfs + simulate_stochastic, against
+    the oracle evaluated in a process pool on the host cores: unique-pixel lists and hit sets (pixel, tick, event) bit for
+    bit, ADCs to ADC_ATOL, waveform rows of real pixels to WFS_RTOL of the row maximum."""
+    import concurrent.futures as cf
+    import multiprocessing as mp
+    import torch
+    from larndsim_b200 import sim
+    jobs = [(f, ib) for f in range(22) for ib in range(len(cm.fixture_batches(f, 0.005)))]
+    cm.synthetic_bank(32, 45, 45, 1950)   # built once here, inherited by the forked workers
+    pp = cm.product_params()
+    bank_d = torch.as_tensor(cm.synthetic_bank(32, 45, 45, 1950), device=torch_dev)
+    nseg = nhits = 0
+    with cf.ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1), mp_context=mp.get_context("fork")) as pool:
+        for ifile, ib, uniq_o, hits_o, wreal_o in pool.map(_oracle_batch, jobs, chunksize=1):
+            arr, _ = cm.fixture_batches(ifile, 0.005)[ib]
+            st = sim.lut_forward(pp, bank_d, torch.as_tensor(arr, device=torch_dev), cm.FIELDS, npix_capacity=len(uniq_o))
+            sim.check_state(st)
+            assert np.array_equal(st.unique_pixels.cpu().numpy(), uniq_o), (ifile, ib)
+            w = st.wfs_full[:, 1:].cpu().numpy()[uniq_o >= 0]
+            scale = np.abs(wreal_o).max(axis=1, keepdims=True)
+            assert (np.abs(w - wreal_o) <= WFS_RTOL * scale + 1e-3).all(), (ifile, ib)
+            _hits_equal(hits_o, sim.simulate_stochastic(pp, st.wfs_full[:, 1:], st.unique_pixels, 0))
+            nseg += arr.shape[0]
+            nhits += len(hits_o[0])
+    assert nseg > 700000 and nhits > 10000, (nseg, nhits)
 
 
 def test_spill_sized_batch_properties(torch_dev, monkeypatch):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
             "larnd_mc_backward", "larnd_lut_create", "larnd_workspace_bytes", "larnd_last_error"} <= names
     for n in names:
         assert hasattr(lib, n), "symbol %s declared in include/larnd_b200.h is not exported" % n
-    assert lib.larnd_abi_version() == 1
+    assert lib.larnd_abi_version() == 2
 
 
 def test_params_pod_layout_matches_the_header(lib, tmp_path):
