@@ -316,15 +316,15 @@ __device__ __forceinline__ void neigh_run(const SortArgs& A, const TileSmem<KP>&
     // [region: neigh owned loop]
     // ---- frames of the owned units ----
     const int sumbit = (nu >> 5) == k ? (nu & 31) : -1;  // lane of the neighbourhood-sum unit in this word
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const int wo = __shfl_sync(0xffffffffu, woff, b), to = __shfl_sync(0xffffffffu, toff, b);
-      float acc[NSV][4], e4[4];
+    if (path == 2) {  // low end: window and corrections follow different garbage rules, no register merging
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int wo = __shfl_sync(0xffffffffu, woff, b), to = __shfl_sync(0xffffffffu, toff, b);
+        float acc[NSV][4], e4[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) e4[c] = Elane[c * TRE + b];
-      neigh_frame<NSV, NPOS, KP>(acc, e4, t4 + to, hreg);
-      if (path == 2) {  // low end: window and corrections follow different garbage rules, no register merging
+        for (int c = 0; c < 4; ++c) e4[c] = Elane[c * TRE + b];
+        neigh_frame<NSV, NPOS, KP>(acc, e4, t4 + to, hreg);
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[0][c] -= e4[c];
         if (b == sumbit) emit_generic<NSV>(acc, e4, row0, B, A.nticks, lane, 1.0f);
@@ -332,17 +332,63 @@ __device__ __forceinline__ void neigh_run(const SortArgs& A, const TileSmem<KP>&
           emit_generic<NSV>(acc, e4, A.wfs + wo, B, A.nticks, lane, 1.0f);
           if (!A.skip_garbage) emit_generic<NSV>(acc, e4, row0, B, A.nticks, lane, -1.0f);
         }
-      } else if (b == sumbit) {
+      }
+    } else {
+      if (sumbit >= 0 && (m >> sumbit & 1u)) {  // the neighbourhood-sum frame seeds the garbage-row accumulator
+        m &= ~(1u << sumbit);
+        const int to = __shfl_sync(0xffffffffu, toff, sumbit);
+        float acc[NSV][4], e4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e4[c] = Elane[c * TRE + sumbit];
+        neigh_frame<NSV, NPOS, KP>(acc, e4, t4 + to, hreg);
 #pragma unroll
         for (int v = 0; v < NSV; ++v)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc0[v][c] += acc[v][c];
-      } else {
-        emit_fast<NSV>(acc, wl + wo, act, path == 0);
+      }
+      // two owned units in flight: their response / correction loads are issued together (the kernel is bound by the
+      // latency of these L2 loads, not by issue slots)
+      while (m) {
+        const int b0 = __ffs(m) - 1;
+        m &= m - 1;
+        const bool two = m != 0u;
+        const int b1 = two ? __ffs(m) - 1 : b0;
+        if (two) m &= m - 1;
+        const int wo0 = __shfl_sync(0xffffffffu, woff, b0), to0 = __shfl_sync(0xffffffffu, toff, b0);
+        const int wo1 = __shfl_sync(0xffffffffu, woff, b1), to1 = __shfl_sync(0xffffffffu, toff, b1);
+        float W0[NSV][WCfg<KP>::WN], W1[NSV][WCfg<KP>::WN];
 #pragma unroll
         for (int v = 0; v < NSV; ++v)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc0[v][c] -= acc[v][c];
+          for (int q = 0; q < WCfg<KP>::WN / 4; ++q) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(t4 + to0 + 128 * v + WCfg<KP>::WOFF + 4 * q));
+            const float4 y = __ldg(reinterpret_cast<const float4*>(t4 + to1 + 128 * v + WCfg<KP>::WOFF + 4 * q));
+            W0[v][4 * q + 0] = x.x; W0[v][4 * q + 1] = x.y; W0[v][4 * q + 2] = x.z; W0[v][4 * q + 3] = x.w;
+            W1[v][4 * q + 0] = y.x; W1[v][4 * q + 1] = y.y; W1[v][4 * q + 2] = y.z; W1[v][4 * q + 3] = y.w;
+          }
+        float a0[NSV][4], a1[NSV][4];
+#pragma unroll
+        for (int v = 0; v < NSV; ++v)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            a0[v][c] = v == 0 ? Elane[c * TRE + b0] : 0.0f;
+            a1[v][c] = v == 0 ? Elane[c * TRE + b1] : 0.0f;
+          }
+#pragma unroll
+        for (int j = 0; j < NPOS; ++j)
+#pragma unroll
+          for (int v = 0; v < NSV; ++v)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              a0[v][c] = fmaf(hreg[j], W0[v][c + 7 - j - WCfg<KP>::WOFF], a0[v][c]);
+              a1[v][c] = fmaf(hreg[j], W1[v][c + 7 - j - WCfg<KP>::WOFF], a1[v][c]);
+            }
+        emit_fast<NSV>(a0, wl + wo0, act, path == 0);
+        if (two) emit_fast<NSV>(a1, wl + wo1, act, path == 0);
+#pragma unroll
+        for (int v = 0; v < NSV; ++v)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc0[v][c] -= two ? a0[v][c] + a1[v][c] : a0[v][c];
       }
     }
     __syncwarp();
