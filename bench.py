@@ -5,15 +5,24 @@
 
 One *step* = one pass of the hot path over one synthetic spill batch of the prepared_data shape
 (SURVEY.md §8d config 5): prepare -> unique/renumber -> LUT accumulate -> fused FEE/ADC (+ hit compaction).
-`value`     : forward segments/s with the batch already resident in HBM (CUDA events, max over ranks).
-`e2e`       : the same through the public API with the batch in pinned HOST memory: H2D copy of the tracks and
-              D2H read-back of the hit list inside the timed region.
-`fwd_grad`  : forward + loss + backward (FEE VJP -> accumulate VJP -> 15 parameter gradients, all-reduced over ranks).
-`roofline`  : dominant kernel (k_lut_accumulate), algorithmic HBM bytes / CUDA-event kernel time vs the measured peak.
-`cpu_baseline`: the numpy oracle (a port of the reference algorithm; JAX is not installable here) on host cores.
---impl reference times that oracle port on all host cores (the reference itself needs jax, absent from the image).
-Multi-GPU: events are independent, so every rank simulates its own batch (weak scaling); the only collective is the
-16-float all-reduce of (loss, gradients) in the fwd+grad step.
+`value`      : forward segments/s with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`        : the same through the reference-facing entry (dataio.simulate_from_raw's path): the RAW, un-chopped rows
+               of the batch are copied from pinned host memory, chopped on the device, simulated, and the hit list is
+               read back — all inside the timed region.  `e2e_chopped` / `e2e_packed`: a caller that holds CHOPPED
+               batches on the host uploads all 26 columns (104 B/segment) / the 10 columns the simulation reads (40 B).
+`fwd_grad`   : forward + loss + backward (FEE VJP -> accumulate VJP -> 15 parameter gradients, all-reduced over ranks).
+`mc_mode`    : BASELINE config 3 (MC-current mode) forward and forward+grad.
+`fit_step`   : BASELINE config 4: one Adam step of the reference's --lut fit (n = 2, L = 150, ~19.8 k segments per rank,
+               mse_adc, six fitted parameters), events sharded over the ranks, steps/s.
+`scan_2d`    : BASELINE config 5b: 16 x 16 likelihood scan (loss + 2 gradients per point), grid points x event shards
+               distributed over the ranks, wall time.
+`roofline`   : dominant kernels (forward and backward tile kernels): algorithmic HBM bytes / CUDA-event kernel time vs the
+               measured peak, DRAM traffic from the committed ncu capture.
+`cpu_baseline`: the numpy oracle (a port of the reference algorithm; JAX is absent from this image AND from the GPU box,
+               profiles/r2_probe_jax.txt) on host cores.
+--impl reference times that oracle port on all host cores on a bounded sample of the SAME workload and config.
+Multi-GPU: events are independent, so every rank simulates its own batch (weak scaling); the only collectives are the
+16-float all-reduce of (loss, gradients) in fwd_grad, two small all-reduces per fit step and one all-gather per scan.
 """
 import argparse
 import json
@@ -35,6 +44,29 @@ GEOM = os.path.join(ROOT, "larnd-sim-jax_b200", "larndsim_b200", "data", "module
 
 
 MC_SEGMENTS = 2_000_000  # size of the MC-current-mode side measurement
+FIT_SEGMENTS = 19_800    # optimize/fit_test.sh --lut: 200 cm of track at 0.01 cm per batch
+FIT_NAMES = ("Ab", "kb", "eField", "lifetime", "tran_diff", "long_diff")
+FIT_NOMINAL = dict(Ab=0.8, kb=0.0486, eField=0.5, lifetime=2.2e3, long_diff=4.0e-6, tran_diff=8.8e-6)
+FIT_TARGET = dict(Ab=0.83, kb=0.055, eField=0.52, lifetime=1.8e3, long_diff=5.0e-6, tran_diff=10e-6)
+SCAN_GRID = 16
+SCAN_RANGES = {"eField": (0.45, 0.55), "lifetime": (500.0, 5000.0)}  # optimize/ranges.py down/up
+
+
+def workload_config(nseg, n_events):
+    """`config` of the JSON line: a function of the generator arguments only, so that both arms print the same dict."""
+    return {"workload": "synthetic_spill: %d segments/GPU (straight tracks chopped at %.2f cm, %d events), LUT mode, "
+                        "synthetic (45,45,1950) response x 100 templates" % (nseg, PRECISION, n_events),
+            "number_pix_neighbors": NEIGH, "signal_length": SIGLEN,
+            "l2": "inputs (%.0f MB tracks + waveforms > 1 GB) exceed the 126 MB L2" % (nseg * 104 / 1e6),
+            "garbage_row": "computed (reference-identical)"}
+
+
+def chopped_count(raw, fields):
+    """Number of rows chop_tracks(raw, fields, PRECISION) produces (float32 length, as numpy evaluates the reference)."""
+    c = lambda n: fields.index(n)
+    seg = np.stack([raw[:, c(a + "_end")] - raw[:, c(a + "_start")] for a in "xyz"], axis=1).astype(np.float32)
+    length = np.sqrt(np.sum(seg ** 2, axis=1))
+    return int(np.maximum(np.ceil(length / PRECISION), 1).astype(np.int64).sum())
 
 
 def parse_args():
@@ -47,6 +79,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=12_000, help="segments of the workload timed on the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-garbage", action="store_true", help="also report the variant that drops the garbage row")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fit-step / scan / MC-mode side measurements")
     return ap.parse_args()
 
 
@@ -151,17 +184,28 @@ def cpu_oracle_rate(tracks, bank32, fields, nproc, per_proc):
 
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores.  jax is installed neither in this image nor on
+    the GPU box (profiles/r2_probe_jax.txt), so this is the numpy oracle port (kind "port"), on all host cores, each step a
+    bounded sample of OUR arm's workload (same generator, same seed, same chopping, same physics configuration)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from larndsim_b200 import synthetic
     from oracle import consts as oc
+    from oracle import larnd_oracle as lo
     cores = os.cpu_count() or 1
     per_proc = 2500
-    tracks, _ = synthetic.synthetic_tracks(per_proc * cores, seed=1234, precision=PRECISION)
+    fields = synthetic.FIELDS
+    raw, n_events = synthetic.synthetic_raw_tracks(args.segments, seed=1234, precision=PRECISION)
+    nseg_full = chopped_count(raw, fields)
+    # the first raw tracks of the workload, chopped like the reference does, until the sample holds per_proc * cores segments
+    need, rows, k = per_proc * cores, [], 0
+    while sum(len(r) for r in rows) < need and k < raw.shape[0]:
+        rows.append(lo.chop_tracks(raw[k:k + 8], fields, PRECISION))
+        k += 8
+    tracks = np.concatenate(rows, axis=0)[:need]
     p = oracle_params()
     bank32 = oc.build_response_template(synthetic.synthetic_response(), p, n_templates=32)
-    fields = synthetic.FIELDS
     rates = []
     for i in range(args.warmup + args.steps):
         r, nseg = cpu_oracle_rate(tracks, bank32, fields, cores, per_proc)
@@ -172,11 +216,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "segments/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * nseg / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic_spill (straight tracks chopped at 0.01 cm), LUT mode n=4 L=100, bounded sample of %d segments/step" % nseg,
-                   "number_pix_neighbors": NEIGH, "signal_length": SIGLEN},
+        "config": workload_config(nseg_full, n_events),
         "cpu_baseline": {"value": val, "unit": "segments/s", "cores": cores, "kind": "port",
-                         "sample": "%d segments/step, %d processes x %d segments, numpy oracle port of the reference algorithm "
-                                   "(the reference needs jax, not installable in this image)" % (nseg, cores, per_proc)},
+                         "sample": "the first %d segments of the workload per step (%d processes x %d segments; only the first 32 of "
+                                   "the 100 templates are built: none of the sample's segments needs a later one), numpy oracle port of "
+                                   "the reference algorithm (the reference needs jax: absent from the image and from the GPU box)"
+                                   % (nseg, cores, per_proc)},
         "e2e": {"value": val, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -188,7 +233,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import larndsim_b200 as lb
-    from larndsim_b200 import _lib, sim, synthetic
+    from larndsim_b200 import _lib, dataio, fit, parallel, sim, synthetic
+    from larndsim_b200.consts import build_response_template
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,7 +246,6 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         # one process per GPU: keep this rank's pinned host buffers and copy threads on the GPU's own NUMA node
-        from larndsim_b200 import parallel
         numa_cpus = parallel.bind_to_gpu_numa_node(local) if os.environ.get("LARND_NO_NUMA_BIND") is None else None
     else:
         numa_cpus = None
@@ -214,17 +259,18 @@ def run_ours(args):
                                                           UNCORRELATED_NOISE_CHARGE=0, time_window=SIGLEN)
     t_gen = time.time()
     # raw tracks (one row per track, the prepared_data shape) -> chopped on the DEVICE (csrc/chop.cu, bit-identical to the
-    # reference's host-side chop_tracks); the chopped batch is the input of `value` and of `e2e`, the raw rows of `e2e_raw`
-    from larndsim_b200 import dataio
+    # reference's host-side chop_tracks); the chopped batch is the resident input of `value`, the raw rows the input of `e2e`
     raw_np, n_events = synthetic.synthetic_raw_tracks(args.segments, seed=1234 + rank, precision=PRECISION)
     raw_host = torch.from_numpy(raw_np).pin_memory()
     tracks = dataio.chop_tracks(raw_host.to(dev), fields, PRECISION)
     nseg = tracks.shape[0]
+    assert rank != 0 or nseg == chopped_count(raw_np, fields)
     tracks_host = tracks.cpu().pin_memory()
+    packed_dev, pfields = dataio.pack_columns(tracks, fields)
+    packed_host = packed_dev.cpu().pin_memory()
+    del packed_dev
     tracks_np = tracks_host.numpy()
-    resp = synthetic.synthetic_response()
-    from larndsim_b200.consts import build_response_template
-    bank = build_response_template(resp, params, device=dev)
+    bank = build_response_template(synthetic.synthetic_response(), params, device=dev)
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
 
@@ -236,8 +282,8 @@ def run_ours(args):
     pod = st0.pod
     del st0
 
-    def fwd(flags=0, src=tracks):
-        st = sim.lut_forward(params, bank, src, fields, npix_capacity=npix, n_events=n_events, flags=flags, out=out)
+    def fwd(flags=0, src=tracks, flds=fields):
+        st = sim.lut_forward(params, bank, src, flds, npix_capacity=npix, n_events=n_events, flags=flags, out=out)
         fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True, pod=pod)
         return st, fs
 
@@ -262,67 +308,66 @@ def run_ours(args):
 
     hit_host = torch.empty((8, npix * pod.max_adc_values // 4 + 1024), dtype=torch.float32).pin_memory()
     nv_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-
-    # End-to-end step: every step copies ITS batch host->device (pinned, 104 B/segment) and reads its hit list back.
-    # The copies run on a second stream and are double-buffered, so the H2D of step i+1 and the D2H of step i-1 overlap
-    # the kernels of step i (what a production loop over batches does); all copies are inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    dev_bufs = [torch.empty_like(tracks), torch.empty_like(tracks)]
-    h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-    buf_free = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"i": 0, "primed": False}
 
-    def issue_h2d(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(buf_free[slot])          # the kernels that last read this buffer are done
-            dev_bufs[slot].copy_(tracks_host, non_blocking=True)
-            h2d_done[slot].record(copy_stream)
-
-    def e2e_step():
+    def read_back_hits(fs):
+        """D2H of the compacted hit list on the copy stream (overlaps the next step's kernels)."""
         main = torch.cuda.current_stream()
-        slot = state["i"] & 1
-        if not state["primed"]:
-            buf_free[0].record(main); buf_free[1].record(main)
-            issue_h2d(slot)
-            state["primed"] = True
-        issue_h2d(slot ^ 1)                                   # prefetch the next step's batch while this one computes
-        main.wait_event(h2d_done[slot])
-        st, fs = fwd(src=dev_bufs[slot])
-        buf_free[slot].record(main)
         done = torch.cuda.Event()
         done.record(main)
         hf, hi = fs.hits
         cap = hit_host.shape[1]
-        with torch.cuda.stream(copy_stream):                  # D2H of the compacted hit list, overlapping the next step
+        with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done)
             nv_host.copy_(fs.n_valid, non_blocking=True)
             hit_host[:6].copy_(hf[:, :cap], non_blocking=True)
             hit_host[6:8].copy_(hi[:, :cap].view(torch.float32), non_blocking=True)
             hf.record_stream(copy_stream); hi.record_stream(copy_stream); fs.n_valid.record_stream(copy_stream)
-        state["i"] += 1
-        return fs
 
-    # End-to-end from the RAW rows: H2D of the un-chopped tracks (a few hundred KB), chop on the device,
-    # forward, D2H of the hit list — the reference chops on the host and ships 104 B per chopped segment.
+    # HEADLINE end-to-end step, the reference-facing entry for production batches (dataio.simulate_from_raw's path with
+    # preallocated buffers): H2D of the RAW, un-chopped rows (what the input file holds), chop on the device, forward, D2H
+    # of the hit list.  The reference chops on the host and ships 104 B per chopped segment.
     raw_dev = torch.empty(raw_host.shape, dtype=torch.float32, device=dev)
     chop_buf = torch.empty_like(tracks)
 
-    def e2e_raw_step():
-        main = torch.cuda.current_stream()
+    def e2e_step():
         raw_dev.copy_(raw_host, non_blocking=True)
         dataio.chop_tracks(raw_dev, fields, PRECISION, out=chop_buf)
         st, fs = fwd(src=chop_buf)
-        done = torch.cuda.Event()
-        done.record(main)
-        hf, hi = fs.hits
-        cap = hit_host.shape[1]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
-            nv_host.copy_(fs.n_valid, non_blocking=True)
-            hit_host[:6].copy_(hf[:, :cap], non_blocking=True)
-            hit_host[6:8].copy_(hi[:, :cap].view(torch.float32), non_blocking=True)
-            hf.record_stream(copy_stream); hi.record_stream(copy_stream); fs.n_valid.record_stream(copy_stream)
+        read_back_hits(fs)
         return fs
+
+    # Callers that hold CHOPPED batches on the host: every step copies ITS batch host->device and reads its hits back.  The
+    # copies run on a second stream and are double-buffered (H2D of step i+1 and D2H of step i-1 overlap the kernels of step
+    # i); `packed` uploads only the ten columns the simulation reads (`fields` is an argument of the API: a 10-column batch
+    # is a valid input as it is).
+    def make_chopped_step(host, flds):
+        bufs = [torch.empty(host.shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
+        buf_free = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"i": 0, "primed": False}
+
+        def issue_h2d(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(buf_free[slot])          # the kernels that last read this buffer are done
+                bufs[slot].copy_(host, non_blocking=True)
+                h2d_done[slot].record(copy_stream)
+
+        def step():
+            main = torch.cuda.current_stream()
+            slot = state["i"] & 1
+            if not state["primed"]:
+                buf_free[0].record(main); buf_free[1].record(main)
+                issue_h2d(slot)
+                state["primed"] = True
+            issue_h2d(slot ^ 1)                                   # prefetch the next step's batch while this one computes
+            main.wait_event(h2d_done[slot])
+            st, fs = fwd(src=bufs[slot], flds=flds)
+            buf_free[slot].record(main)
+            read_back_hits(fs)
+            state["i"] += 1
+            return fs
+        return step, bufs
 
     def timed(fn, steps, warmup, sampler=None, join=None):
         if sampler:
@@ -335,6 +380,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         if sampler:
             sampler.mark()           # only samples taken from here on (timed region, GPU under load) are summarised
+        l0 = lib.larnd_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -343,43 +389,128 @@ def run_ours(args):
             torch.cuda.current_stream().wait_stream(join)   # the timed region ends after the last copy of the last step
         e1.record()
         torch.cuda.synchronize()
+        launches = lib.larnd_launch_count() - l0
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps, clocks
+        return float(ms.item()) / steps, int(launches)
 
-    # the clock sampler covers all four timed regions (value, e2e, e2e_raw, fwd_grad): ~100 ms nvidia-smi period
+    # the clock sampler covers the timed regions value .. fwd_grad: ~100 ms nvidia-smi period
+    w3 = max(2, args.warmup // 3)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_fwd, _ = timed(fwd, args.steps, args.warmup, sampler)
-    ms_e2e, _ = timed(e2e_step, args.steps, max(2, args.warmup // 3), join=copy_stream)
-    ms_e2e_raw, _ = timed(e2e_raw_step, args.steps, max(2, args.warmup // 3), join=copy_stream)
-    ms_fg, _ = timed(fwd_grad, args.steps, max(1, args.warmup // 3))
+    ms_fwd, launches = timed(fwd, args.steps, args.warmup, sampler)
+    ms_e2e, _ = timed(e2e_step, args.steps, w3, join=copy_stream)
+    step_c, bufs_c = make_chopped_step(tracks_host, fields)
+    ms_e2e_c, _ = timed(step_c, args.steps, w3, join=copy_stream)
+    del step_c, bufs_c
+    step_p, bufs_p = make_chopped_step(packed_host, pfields)
+    ms_e2e_p, _ = timed(step_p, args.steps, w3, join=copy_stream)
+    del step_p, bufs_p
+    ms_fg, launches_fg = timed(fwd_grad, args.steps, max(1, args.warmup // 3))
     clocks = sampler.stop() if sampler else None
     ms_skip = None
     if args.skip_garbage:
         ms_skip, _ = timed(lambda: fwd(flags=1), args.steps, 1)
         fwd()
 
-    # MC-current mode (BASELINE config 3: simulate_parametrized, mc_diff, diffusion in the current model, n = 0, L = 150 as in
-    # optimize/fit_test.sh:95-102) on the first MC_SEGMENTS segments of the same batch: prepare + unique + analytic current +
-    # scatter + FEE, random numbers from the device Threefry stream (drawn once, outside the timed region)
-    n_mc = min(nseg, MC_SEGMENTS)
-    p_mc = params.replace(number_pix_neighbors=0, signal_length=150, mc_diff=True, diffusion_in_current_sim=True)
-    tr_mc = tracks[:n_mc].contiguous()
-    rnd_mc = sim.mc_normals(n_mc, 0, dev)
-    st_mc = sim.mc_forward(p_mc, tr_mc, fields, rnd_mc, n_events=n_events)
-    npix_mc, pod_mc = st_mc.npix, st_mc.pod
-    del st_mc
+    extras = {}
+    if not args.no_extras:
+        # ---- BASELINE config 3: MC-current mode (simulate_parametrized, mc_diff, diffusion in the current model, n = 0, L = 150
+        # as in optimize/fit_test.sh:95-102) on the first MC_SEGMENTS segments of the same batch: prepare + unique + analytic
+        # current + scatter + FEE, random numbers from the device Threefry stream (drawn once, outside the timed region)
+        n_mc = min(nseg, MC_SEGMENTS)
+        p_mc = params.replace(number_pix_neighbors=0, signal_length=150, mc_diff=True, diffusion_in_current_sim=True)
+        tr_mc = tracks[:n_mc].contiguous()
+        rnd_mc = sim.mc_normals(n_mc, 0, dev)
+        st_mc = sim.mc_forward(p_mc, tr_mc, fields, rnd_mc, n_events=n_events)
+        npix_mc, pod_mc = st_mc.npix, st_mc.pod
+        fs_mc = sim.fee_forward(p_mc, st_mc.wfs_full[:, 1:], st_mc.unique_pixels, None, compact=False, pod=pod_mc)
+        adc_mc_target = (fs_mc.adc * 0.9).clone()
+        del st_mc, fs_mc
 
-    def mc_fwd():
-        stm = sim.mc_forward(p_mc, tr_mc, fields, rnd_mc, npix_capacity=npix_mc, n_events=n_events)
-        return sim.fee_forward(p_mc, stm.wfs_full[:, 1:], stm.unique_pixels, None, compact=True, pod=pod_mc)
+        def mc_fwd():
+            stm = sim.mc_forward(p_mc, tr_mc, fields, rnd_mc, npix_capacity=npix_mc, n_events=n_events)
+            return stm, sim.fee_forward(p_mc, stm.wfs_full[:, 1:], stm.unique_pixels, None, compact=True, pod=pod_mc)
 
-    ms_mc, _ = timed(mc_fwd, args.steps, max(1, args.warmup // 3))
+        def mc_fwd_grad():
+            stm, fsm = mc_fwd()
+            diff = (fsm.adc - adc_mc_target) * (stm.unique_pixels >= 0).unsqueeze(1)
+            g_wfs = sim.fee_backward(fsm, 2.0 * diff)
+            red = torch.cat([(diff * diff).sum().reshape(1), sim.mc_backward(stm, tr_mc, g_wfs)])
+            if world > 1:
+                dist.all_reduce(red)
+            return red
+
+        ms_mc, _ = timed(mc_fwd, args.steps, w3)
+        ms_mc_fg, _ = timed(mc_fwd_grad, args.steps, 1)
+        extras["mc_mode"] = {"metric": "segments/s (MC-current mode, n=0, L=150, mc_diff, diffusion in the current model; BASELINE config 3)",
+                             "value": n_mc * world / (ms_mc * 1e-3), "unit": "segments/s", "ms_per_step": ms_mc,
+                             "fwd_grad": n_mc * world / (ms_mc_fg * 1e-3), "fwd_grad_ms_per_step": ms_mc_fg, "segments_per_gpu": n_mc}
+        del tr_mc, rnd_mc, adc_mc_target
+
+        # ---- BASELINE config 4: one Adam step of the --lut fit (optimize/fit_test.sh: 0.01 cm, n = 2, L = 150, ~19.8 k segments,
+        # mse_adc, six fitted parameters); every rank holds ITS events, the loss sums and the gradients are all-reduced
+        base4 = dict(number_pix_neighbors=2, signal_length=150, electron_sampling_resolution=PRECISION, RESET_NOISE_CHARGE=0,
+                     UNCORRELATED_NOISE_CHARGE=0)
+        fit_np, fit_events = synthetic.synthetic_tracks(FIT_SEGMENTS, seed=500 + rank, precision=PRECISION)
+        fit_tracks = torch.as_tensor(fit_np, device=dev)
+        p4 = lb.load_geometry_json(lb.build_params_class(list(FIT_NAMES)), GEOM).replace(**base4)
+        bank4 = build_response_template(synthetic.synthetic_response(25, 25, 1950), p4, device=dev)
+        prob = fit.FitProblem.from_target_params(FIT_NAMES, p4, FIT_TARGET, bank4, fit_tracks, fields, fit_events)
+        adam = fit.AdamFit(prob, FIT_NOMINAL, lr=0.01)
+        for _ in range(10):
+            adam.step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_fit = 50
+        t0 = time.perf_counter()
+        l0 = lib.larnd_launch_count()
+        for _ in range(n_fit):
+            adam.step()
+        torch.cuda.synchronize()
+        wall = torch.tensor([time.perf_counter() - t0], device=dev)
+        fit_launches = (lib.larnd_launch_count() - l0) / n_fit
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        extras["fit_step"] = {"metric": "fit steps/s (BASELINE config 4: fwd + mse_adc + grads of 6 parameters + Adam, events sharded)",
+                              "value": n_fit / float(wall.item()), "unit": "steps/s", "ms_per_step": 1e3 * float(wall.item()) / n_fit,
+                              "segments_per_step": int(fit_tracks.shape[0]) * world, "segments_per_gpu": int(fit_tracks.shape[0]),
+                              "our_kernel_launches_per_step": fit_launches, "timing": "host wall clock around 50 steps (the step is "
+                              "host-bound at this size), max over ranks", "collectives": "2 all-reduces (7 loss sums, 6 gradients)" if world > 1 else "none"}
+
+        # ---- BASELINE config 5b: 16 x 16 likelihood scan over (eField, lifetime): loss + 2 gradients per point; the grid points
+        # are dealt to point groups, the events of a point are sharded over the ranks of its group
+        event_shards = 2 if world >= 4 else 1
+        scan_names = ("eField", "lifetime")
+        p5 = lb.load_geometry_json(lb.build_params_class(list(scan_names)), GEOM).replace(**base4)
+        scan_np, scan_events = synthetic.synthetic_tracks(FIT_SEGMENTS * event_shards, seed=77, precision=PRECISION)
+
+        def make_problem(es, n_es, group):
+            loc, nev, _ = parallel.shard_tracks(scan_np, fields, es, n_es)
+            return fit.FitProblem.from_target_params(scan_names, p5, {}, bank4, torch.as_tensor(loc, device=dev), fields, nev, group=group)
+
+        a1, a2 = np.linspace(*SCAN_RANGES["eField"], SCAN_GRID), np.linspace(*SCAN_RANGES["lifetime"], SCAN_GRID)
+        fit.scan_2d(make_problem, "eField", a1[:2], "lifetime", a2[:2], event_shards=event_shards)   # warm-up (sizing, caches)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        table = fit.scan_2d(make_problem, "eField", a1, "lifetime", a2, event_shards=event_shards)
+        torch.cuda.synchronize()
+        wall = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        imin = np.unravel_index(np.nanargmin(table[..., 0]), table.shape[:2])
+        extras["scan_2d"] = {"metric": "wall seconds of a %dx%d likelihood scan (BASELINE config 5b)" % (SCAN_GRID, SCAN_GRID),
+                             "value": float(wall.item()), "unit": "s", "points": SCAN_GRID * SCAN_GRID, "points_per_s": SCAN_GRID * SCAN_GRID / float(wall.item()),
+                             "segments_per_point": int(scan_np.shape[0]), "layout": "%d point groups x %d event shards" % (world // event_shards, event_shards),
+                             "argmin": [float(a1[imin[0]]), float(a2[imin[1]])], "nominal": [0.5, 2200.0],
+                             "finite_points": int(np.isfinite(table[..., 0]).sum())}
+        del prob, adam, fit_tracks, bank4
 
     # per-kernel device times of the dominant kernels, same launches as above
     lib.larnd_profile_enable(1)
@@ -398,65 +529,67 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         nticks, L = pod.n_ticks, SIGLEN
-        # algorithmic (compulsory) HBM bytes of the forward path per segment, SURVEY.md §8d:
+        # algorithmic (compulsory) HBM bytes per segment, SURVEY.md §8d: forward = record + one write of every touched waveform
+        # row + the LUT window; backward = re-read of the segment records (31 words) + one read of every gradient row
         lut_window = 4 * L * (25 * 3 + (10 * NEIGH + 5) ** 2)
         b_seg = 104 + 4.0 * (n_unique + 1) * nticks / nseg + lut_window / nseg
+        b_seg_bwd = 4 * 31 + 4.0 * (n_unique + 1) * nticks / nseg + lut_window / nseg
         c_seg = (25 + (2 * NEIGH + 1) ** 2) * (2 * L + 2)
         achieved = b_seg * nseg / (k_ms[1] * 1e-3) / 1e9
-        # DRAM bytes of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full`
-        # capture at the 10 M-segment workload (profiles/r1_traffic_10M.json), scaled to this run's segment count
-        # L2 reduction traffic (the kernel's output leaves as red.global.add.f32): lts__t_sectors_srcunit_tex_op_red x 32 B of
-        # the same capture, against the reduction throughput a pure flush kernel reaches with the same access pattern and
-        # an L2-resident target (scripts/ubench_red.cu pattern A, profiles/r1b_ubench_red.txt)
-        traffic, l2_red = None, None
-        for tname in ("r1d_traffic_10M.json", "r1b_traffic_10M.json", "r1_traffic_10M.json"):
-            try:
-                with open(os.path.join(ROOT, "profiles", tname)) as fh:
-                    tj = json.load(fh)
-                # one forward pass launches k_acc_tiles once per kernel variant (4-position and 6-position tiles): sum them
-                ents = tj.get("k_acc_tiles") or tj["k_acc_tiles<4>"]
-                traffic = sum(float(e["dram_bytes"]) for e in ents) * nseg / 10010184.0
-                sectors = sum(float(e.get("l2_red_sectors") or 0.0) for e in ents)
-                if sectors:
-                    red_bytes = sectors * 32.0 * nseg / 10010184.0
-                    red_peak = 5170.0
-                    l2_red = {"achieved": red_bytes / (k_ms[1] * 1e-3) / 1e9, "peak": red_peak, "unit": "GB/s",
-                              "frac": red_bytes / (k_ms[1] * 1e-3) / 1e9 / red_peak, "bytes_per_launch": red_bytes,
-                              "peak_source": "scripts/ubench_red.cu, lane<->tick 128-byte reductions into an L2-resident buffer "
-                                             "(2 GB DRAM-resident target: 2080 GB/s)",
-                              "sectors_source": "profiles/" + tname}
-                break
-            except Exception:
-                continue
+        achieved_bwd = b_seg_bwd * nseg / (k_ms[2] * 1e-3) / 1e9
+        # DRAM bytes and L2 reduction sectors of the dominant kernels per launch come from ONE `ncu --set full` capture of this
+        # workload (profiles/r2_traffic_10M.json, written by scripts/ncu_traffic.py), scaled to this run's segment count
+        traffic = traffic_bwd = l2_red = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic_10M.json")) as fh:
+                tj = json.load(fh)
+            scale = nseg / float(tj.get("segments", 10010184))
+            traffic = sum(float(e["dram_bytes"]) for e in tj["k_acc_tiles"]) * scale
+            traffic_bwd = sum(float(e["dram_bytes"]) for e in tj["k_bwd_tiles"]) * scale
+            sectors = sum(float(e.get("l2_red_sectors") or 0.0) for e in tj["k_acc_tiles"])
+            if sectors:
+                red_bytes = sectors * 32.0 * scale
+                l2_red = {"achieved": red_bytes / (k_ms[1] * 1e-3) / 1e9, "peak": 5800.0, "unit": "GB/s",
+                          "frac": red_bytes / (k_ms[1] * 1e-3) / 1e9 / 5800.0, "bytes_per_launch": red_bytes,
+                          "peak_source": "scripts/ubench_red.cu, lane<->4 ticks red.global.add.v4.f32 into an L2-resident buffer "
+                                         "(profiles/r1b_ubench_red.txt)", "sectors_source": "profiles/r2_traffic_10M.json"}
+        except Exception:
+            pass
+        hits_bytes = int(hit_host.numel() * 4 + 4)
+        seg_s = lambda ms: total_seg / (ms * 1e-3)
         line = {
-            "metric": METRIC, "value": total_seg / (ms_fwd * 1e-3), "unit": "segments/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": seg_s(ms_fwd), "unit": "segments/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_fwd, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic_spill: %d segments/GPU (straight tracks chopped at %.2f cm, %d events), LUT mode, "
-                                   "synthetic (45,45,1950) response x 100 templates" % (nseg, PRECISION, n_events),
-                       "number_pix_neighbors": NEIGH, "signal_length": SIGLEN, "n_unique_pixels": n_unique, "npix_padded": npix,
-                       "hits": n_valid, "l2": "inputs (%.0f MB tracks + %.0f MB waveforms) exceed the 126 MB L2" %
-                                              (nseg * 104 / 1e6, npix * nticks * 4 / 1e6),
-                       "garbage_row": "computed (reference-identical)"},
+            "config": workload_config(nseg, n_events),
+            "workload_stats": {"n_unique_pixels": n_unique, "npix_padded": npix, "hits": n_valid,
+                               "waveform_buffer_mb": npix * sim.wfs_row_stride(nticks) * 4 / 1e6},
             "clocks": clocks,
-            "e2e": {"value": total_seg / (ms_e2e * 1e-3), "unit": "segments/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(tracks_host.numel() * 4), "d2h_bytes_per_step": int(hit_host.numel() * 4 + 4)},
-            "e2e_raw": {"value": total_seg / (ms_e2e_raw * 1e-3), "unit": "segments/s", "ms_per_step": ms_e2e_raw,
-                        "h2d_bytes_per_step": int(raw_host.numel() * 4), "d2h_bytes_per_step": int(hit_host.numel() * 4 + 4),
-                        "note": "un-chopped tracks uploaded, chop_tracks on the device (csrc/chop.cu)"},
-            "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": total_seg / (ms_fg * 1e-3), "unit": "segments/s",
-                         "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none"},
-            "mc_mode": {"metric": "segments/s fwd (MC-current mode, n=0, mc_diff, diffusion in the current model)",
-                        "value": n_mc * world / (ms_mc * 1e-3), "unit": "segments/s", "ms_per_step": ms_mc, "segments_per_gpu": n_mc},
-            "gpu_launches": int(args.steps * 15),  # prepare 1 + unique/scan 4 + sorted accumulate 7 (run sort 3, tiles 2, row 0, boundary) + FEE/compaction 3
+            "e2e": {"value": seg_s(ms_e2e), "unit": "segments/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(raw_host.numel() * 4), "d2h_bytes_per_step": hits_bytes,
+                    "entry": "dataio.simulate_from_raw path: raw (un-chopped) rows uploaded from pinned memory, chop_tracks on the "
+                             "device (csrc/chop.cu), simulate_wfs + simulate_stochastic, hit list read back"},
+            "e2e_chopped": {"value": seg_s(ms_e2e_c), "unit": "segments/s", "ms_per_step": ms_e2e_c,
+                            "h2d_bytes_per_step": int(tracks_host.numel() * 4), "d2h_bytes_per_step": hits_bytes,
+                            "note": "host-chopped batch, all 26 columns uploaded (104 B/segment), double-buffered"},
+            "e2e_packed": {"value": seg_s(ms_e2e_p), "unit": "segments/s", "ms_per_step": ms_e2e_p,
+                           "h2d_bytes_per_step": int(packed_host.numel() * 4), "d2h_bytes_per_step": hits_bytes,
+                           "note": "host-chopped batch, the 10 columns the simulation reads (dataio.pack_columns, 40 B/segment)"},
+            "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": seg_s(ms_fg), "unit": "segments/s",
+                         "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none",
+                         "gpu_launches": launches_fg},
+            "gpu_launches": launches,  # kernels of liblarnd_b200.so launched inside the timed region of `value` (larnd_launch_count)
             "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
-            "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate: run sort + the 4- and 6-position tile kernels + row-0 reduction)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_segment": b_seg,
-                         "note": "accumulate is bound by instruction issue and L2 reduction throughput, not HBM (SURVEY §8d): "
-                                 "see l2_red and contributions/s",
+            "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate: run sort + the 4- and 6-position tile kernels + row-0 reduction)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_segment": b_seg,
+                         "note": "accumulate is bound by instruction issue and L1/L2 traffic of its FMA/reduction stream, not by HBM "
+                                 "(SURVEY §8d): see l2_red, contributions/s and DESIGN.md §4",
                          "l2_red": l2_red,
                          "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3),
+                         "backward": {"kernel": "k_bwd_tiles (class-sorted VJP of lut_accumulate + chain rule)", "bound": "hbm",
+                                      "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
+                                      "traffic": traffic_bwd, "algorithmic_bytes_per_segment": b_seg_bwd},
                          # the two streaming kernels of the step, which ARE HBM-bound (algorithmic bytes / measured time):
                          # prepare reads the 104-byte record and writes the 31-word segment record; the front end reads
                          # every waveform row once
@@ -468,13 +601,12 @@ def run_ours(args):
             "setup_s": t_gen,
             "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
         }
+        line.update(extras)
         if ms_skip is not None:
-            line["value_skip_garbage_row"] = total_seg / (ms_skip * 1e-3)
+            line["value_skip_garbage_row"] = seg_s(ms_skip)
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import consts as oc
             sample = tracks_np[: args.cpu_sample]
             bank32 = bank[:32].cpu().numpy()
-            _ = oc
             rate, ns = cpu_oracle_rate(sample, bank32, fields, 1, len(sample))
             line["cpu_baseline"] = {"value": rate, "unit": "segments/s", "cores": 1, "kind": "port",
                                     "sample": "first %d segments of the same workload, numpy oracle port, 1 process" % ns}

@@ -190,7 +190,9 @@ int larnd_lut_backward(int64_t n_segments, const larnd_params_t* params, const l
  * Per-pixel outputs (npix): pixel_x_d, pixel_y_d, event_d (int32).
  * Compacted outputs (capacity npix*10, first n_valid entries meaningful, parse_output order):
  *   hit_adc_d, hit_x_d, hit_y_d, hit_z_d, hit_ticks_d, hit_prob_d (float), hit_event_d, hit_pixel_d (int32),
- *   n_valid_d[1].  saved_d (npix, 32) float: per-row state needed by larnd_fee_backward. */
+ *   n_valid_d[1].  saved_d (npix, 32) float: per-row state needed by larnd_fee_backward ([0..9] crossing ticks, [10..12]
+ *   hit / subtraction / digitiser-slope masks, [13..22] the integrated charge of every hit BEFORE the digitiser = the
+ *   `adc` array get_adc_values itself returns, fee_jax.py:170-279). */
 int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
                       const larnd_params_t* params, const float* noise_d,
                       float* adc_d, float* ticks_d, float* pixel_z_d, float* pixel_x_d, float* pixel_y_d,
@@ -200,9 +202,11 @@ int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t*
                       void* scratch_d, size_t scratch_bytes, void* stream);
 size_t larnd_fee_scratch_bytes(int32_t npix);
 
-/* VJP of get_adc_values+digitize: g_adc_d (npix,10) -> g_wfs_d (npix, n_ticks-1) with row stride. */
+/* VJP of get_adc_values+digitize: g_adc_d (npix,10) -> g_wfs_d (npix, n_ticks-1) with row stride.
+ * raw_charge != 0: g_adc_d is the gradient w.r.t. the INTEGRATED CHARGE get_adc_values returns (saved_d[row*32 + 13 + k],
+ * fee_jax.py:229-265) instead of the digitised ADC, i.e. the digitiser slope and its clipping are left out. */
 int larnd_fee_backward(const float* g_adc_d, const float* ticks_d, const float* saved_d, int32_t npix,
-                       const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, void* stream);
+                       const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, int32_t raw_charge, void* stream);
 
 /* Noise-averaged ("probabilistic") front end, forward: get_adc_values_average_noise_vmap (fee_jax.py:390-461).
  * wfs_d: (npix, n_ticks) waveforms (row stride in floats).  Outputs (npix, MAX_ADC_VALUES, n_ticks-1) each:
@@ -337,6 +341,10 @@ int larnd_accumulate_parametrized_backward(const float* g_wfs_d, int32_t npix, i
  *   slot 0: k_prepare   slot 1: k_lut_accumulate   slot 2: k_lut_backward   slot 3: k_fee_forward
  * larnd_profile_read synchronises on those events and returns the elapsed milliseconds of the LAST launch of
  * each kernel (-1 if it has not run since larnd_profile_enable(1)). */
+/* Number of kernels this library has launched in this process so far (every launch site counts itself): lets a caller
+ * report how many of OUR kernels ran inside a timed region instead of asserting a constant. */
+uint64_t larnd_launch_count(void);
+
 #define LARND_PROF_SLOTS 4
 int larnd_profile_enable(int on);
 int larnd_profile_read(float* ms_out /* [LARND_PROF_SLOTS] */);

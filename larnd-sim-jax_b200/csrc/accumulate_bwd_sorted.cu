@@ -61,7 +61,7 @@ struct BwdTileSmem {
   int low_end;  // some run of the tile starts below tick 2, or its 32 NS-tick register window ends beyond the row
 };
 
-__device__ __forceinline__ float warp_sum_f(float v) {
+__device__ __forceinline__ float warp_sum_f(float v) {  // [region: reduce helpers]
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -107,7 +107,7 @@ __device__ __forceinline__ float reduce4_to_lane_s(const float (&v)[4], int lane
 // response rows Rw and its segments update the shared accumulators.  NR = 3: main pixel (3-template blend, group gi/gj);
 // NR = 1: neighbour pixel (template 0, full charge).
 template <int NS, int NR, int NPOS, int KP>
-__device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,
+__device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,  // [region: unit_pairs setup]
                                            const float* __restrict__ crow, int gi, int gj, int lane, int warp) {
   const SortArgs& S = A.S;
   const int nt = S.nt, L = S.L, nticks = S.nticks;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   const int myoff = row * (int)A.g_stride + (sm.run[lane].z - 1);
   const bool inside = !sm.low_end;
   while (todo) {
-    // ---- up to 4 runs: correlate, reduce, park the results in the warp's slots -------------------------------------
+    // ---- up to 4 runs: correlate, reduce, park the results in the warp's slots -------------------------------------  // [region: corr: pick run + g loads]
     int nslot = 0;
 #pragma unroll 2
     for (; nslot < BSLOTS && todo; ++nslot) {
@@ -141,7 +141,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
       }
       if (lane <= KPT) ps.gpos[nslot][lane] = graw[0];  // lane j <-> position j: gradient at tick tmin - 1 + j
       if (lane == 0) ps.p[nslot] = p;
-      float part[NR * NPOS];
+      float part[NR * NPOS];  // [region: corr: FMAs]
 #pragma unroll
       for (int k = 0; k < NR * NPOS; ++k) part[k] = 0.0f;
       if (!inside) {  // window samples live on ticks >= 2, corrections on >= 1 (only differs for runs at the low end of the readout)
@@ -157,7 +157,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
 #pragma unroll
           for (int r = 0; r < NR; ++r) part[NR * j + r] = fmaf(gv, Rw[r][s][j], part[NR * j + r]);
       }
-      // full groups of 8 partials with the 10-shuffle butterfly; the remainder with the cheapest one that fits
+      // full groups of 8 partials with the 10-shuffle butterfly; the remainder with the cheapest one that fits  // [region: corr: reduce+park]
       // (<= 4 values: 7 shuffles, a single value: plain warp sum)
       constexpr int V = NR * NPOS, V8 = V / 8 * 8, REM = V - V8;
 #pragma unroll
@@ -186,7 +186,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
       }
     }
     __syncwarp();
-    // ---- lanes <-> (slot, segment): 4 runs x up to 8 segments in one pass --------------------------------------------
+    // ---- lanes <-> (slot, segment): 4 runs x up to 8 segments in one pass --------------------------------------------  // [region: segment phase]
     const int slot = lane >> 3, t = lane & 7;
     if (slot < nslot) {
       const int p = ps.p[slot];
@@ -230,7 +230,7 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   }
 }
 
-template <int NS, int NR, int KP>
+template <int NS, int NR, int KP>  // [region: dispatch]
 __device__ __forceinline__ void unit_pairs_npos(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                                 const float* crow, int gi, int gj, int lane, int warp, int npos) {
   constexpr int N3 = KP >= 3 ? 3 : KP, N4 = KP >= 4 ? 4 : KP, N5 = KP >= 5 ? 5 : KP;
@@ -241,7 +241,7 @@ __device__ __forceinline__ void unit_pairs_npos(BwdTileSmem& sm, const BwdSortAr
   else unit_pairs<NS, NR, 2, KP>(sm, A, Rw, todo, row, crow, gi, gj, lane, warp);
 }
 
-template <int NS, int NR, int KP>
+template <int NS, int NR, int KP>  // [region: load_response]
 __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const float* const (&rows)[NR], int Lp, int lane) {
 #pragma unroll
   for (int r = 0; r < NR; ++r)
@@ -256,7 +256,7 @@ __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const fl
 
 // KP / span range / launch as in k_acc_tiles: the variants holding 3 / 4 response positions (36 / 48 registers, 4 / 3 CTAs
 // per SM) serve the tiles of runs with few impulse positions, the KP = KPT kernel the rest (or everything).
-template <int NS, int KP>
+template <int NS, int KP>  // [region: kernel prologue]
 __global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1))
 k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int span_lo, const int span_hi,
             const int launch) {
@@ -285,7 +285,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
   int* const tile_counter = S.gcnt + GC_BWD + launch;
   const int n_units = 25 + S.P * S.P;
 
-  for (;;) {
+  for (;;) {  // [region: tile pull]
     __syncthreads();
     if (threadIdx.x == 0) { sm.tile = tile_lo + atomicAdd(tile_counter, 1); sm.next_unit = 0; }
     __syncthreads();
@@ -297,7 +297,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
     const int span = cls / ncb, cls_b = cls % ncb;  // class = span * (ntpl * nb * nb) + (idx * nb + bxm) * nb + bym
     const int bym = cls_b % nb, bxm = (cls_b / nb) % nb, idx = cls_b / (nb * nb);
     const int npos = span + 2;
-    // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------
+    // ---- stage the runs (warp 0: lane <-> run) ---------------------------------------------------------------  // [region: stage runs]
     if (warp == 0) {
       int len = 0;
       if (lane < count) {
@@ -323,7 +323,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
       if (lane == 31) sm.nseg = inc;
     }
     __syncthreads();
-    // ---- stage the segments (thread <-> segment) -----------------------------------------------------------------
+    // ---- stage the segments (thread <-> segment) -----------------------------------------------------------------  // [region: stage segments]
     const int nseg = sm.nseg;
     for (int i = threadIdx.x; i < nseg; i += BT_THREADS) {
       const int r = sm.owner[i];
@@ -358,13 +358,13 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
     }
     __syncthreads();
 
-    for (;;) {
+    for (;;) {  // [region: unit pull]
       int unit = 0;
       if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);
       unit = __shfl_sync(0xffffffffu, unit, 0);
       if (unit >= n_units) break;
       float Rw[3][NS][KP];
-      if (unit < 25) {
+      if (unit < 25) {  // [region: main unit setup]
         // ---------------- merged diffusion-bin group (gi, gj): 3-template blend on a main pixel ----------------
         const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
         if (gi >= sm.g_n[bxm] || gj >= sm.g_n[bym]) continue;
@@ -382,7 +382,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
                                       S.rm + (int64_t)((idx + 1) * 25 + bin) * S.Lp};
         load_response_b<NS, 3, KP>(Rw, rows, S.Lp, lane);
         unit_pairs_npos<NS, 3, KP>(sm, A, Rw, todo, row, S.cm + (int64_t)(idx * 25 + bin) * S.nt, gi, gj, lane, warp, npos);
-      } else {
+      } else {  // [region: neigh unit setup]
         // ---------------- neighbour pixels that own a non-garbage waveform row: template 0, full charge -----------
         const int u = unit - 25;
         const int dx = sm.udx[u], dy = sm.udy[u];
@@ -402,7 +402,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         unit_pairs_npos<NS, 1, KP>(sm, A, Rw, todo, row, S.c0 + (int64_t)bin * S.nt, 0, 0, lane, warp, npos);
       }
     }
-    __syncthreads();
+    __syncthreads();  // [region: chain rule]
     // ---- K1b: chain rule through the per-segment preparation, thread <-> segment -------------------------------------
     int gmapx[5], gmapy[5];  // group of every transverse bin (uniform per class)
 #pragma unroll
@@ -422,7 +422,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
       chain_rule_segment(p, S.rec, n, s, idx, q, dq, df, da, db, dc, dwx, dwy, [&](int k, float v) { GACC(k) += v; });
     }
   }
-  // ---- warp + block reduction -> per-CTA partials ------------------------------------------------------------------
+  // ---- warp + block reduction -> per-CTA partials ------------------------------------------------------------------  // [region: final reduce]
 #pragma unroll
   for (int k = 0; k < LARND_NPARAMS; ++k) {
     const float v = warp_sum_f(GACC(k));

@@ -19,6 +19,9 @@ int larnd_check_cuda(cudaError_t e, const char* what) {
   return LARND_E_CUDA;
 }
 
+unsigned long long g_launch_count = 0;
+extern "C" uint64_t larnd_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
+
 bool g_prof_on = false;
 ProfSlot g_prof[LARND_PROF_SLOTS];
 

@@ -205,7 +205,10 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
       F.adc[(int64_t)row * nmax + it] = dig;
       F.ticks[(int64_t)row * nmax + it] = ic;
       F.pixel_z[(int64_t)row * nmax + it] = pz;
-      if (F.saved) F.saved[(int64_t)row * 32 + it] = (float)idx_t;
+      if (F.saved) {
+        F.saved[(int64_t)row * 32 + it] = (float)idx_t;
+        F.saved[(int64_t)row * 32 + 13 + it] = adc;  // integrated charge before the digitiser = get_adc_values' own output
+      }
     }
     // Early exit (noise-free only): after the clamp the row is >= 0, so every later subtraction is >= 0 and the row can only
     // shrink; once its maximum is below the threshold no later pass can find a crossing.  The remaining passes of the
@@ -223,7 +226,7 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
           F.adc[(int64_t)row * nmax + k] = dig0;
           F.ticks[(int64_t)row * nmax + k] = ic0;
           F.pixel_z[(int64_t)row * nmax + k] = pz0;
-          if (F.saved) F.saved[(int64_t)row * 32 + k] = ic0;
+          if (F.saved) { F.saved[(int64_t)row * 32 + k] = ic0; F.saved[(int64_t)row * 32 + 13 + k] = 0.0f; }
         }
         if (counts_valid) n_valid += nmax - it - 1;
         break;
@@ -335,7 +338,7 @@ __global__ void k_compact_hits(const __grid_constant__ CompactArgs C) {
 // list.  Rows whose list is not ascending (never seen) take the plain sum.
 __global__ void __launch_bounds__(128)
 k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved, int npix, int ntw,
-               const __grid_constant__ larnd_params_t p, float* __restrict__ g_wfs, int64_t g_stride) {
+               const __grid_constant__ larnd_params_t p, float* __restrict__ g_wfs, int64_t g_stride, const int raw_charge) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= npix) return;
@@ -359,7 +362,9 @@ k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved,
       const int idx_t = (int)sv[k];
       int e = idx_t + 1 + p.hold_interval; if (e >= ntw) e = ntw - 1;
       int e2 = idx_t + 2 + p.hold_interval; if (e2 >= ntw) e2 = ntw - 1;
-      const float gk = ((hit_mask >> k) & 1u) && ((slope_mask >> k) & 1u) ? g_adc[(int64_t)row * nmax + k] * slope : 0.0f;
+      // raw_charge: the upstream gradient is w.r.t. the integrated charge (get_adc_values), not the digitised ADC
+      const bool live = ((hit_mask >> k) & 1u) && (raw_charge || ((slope_mask >> k) & 1u));
+      const float gk = live ? g_adc[(int64_t)row * nmax + k] * (raw_charge ? 1.0f : slope) : 0.0f;
       const float sbar = ((spos_mask >> k) & 1u) ? -tail : 0.0f;
       if (lane == 2 * k) { mypos = e; myval = gk; }
       if (lane == 2 * k + 1) { mypos = e2; myval = sbar; }
@@ -457,12 +462,13 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
 }
 
 extern "C" int larnd_fee_backward(const float* g_adc_d, const float* ticks_d, const float* saved_d, int32_t npix,
-                                  const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, void* stream) {
+                                  const larnd_params_t* params, float* g_wfs_d, int64_t g_row_stride, int32_t raw_charge,
+                                  void* stream) {
   (void)ticks_d;
   if (!g_adc_d || !saved_d || !params || !g_wfs_d) { larnd_set_error("larnd_fee_backward: null argument"); return LARND_E_ARG; }
   if (npix == 0) return LARND_OK;
   k_fee_backward<<<(npix + 3) / 4, 128, 0, (cudaStream_t)stream>>>(g_adc_d, saved_d, npix, params->n_ticks - 1, *params,
-                                                                 g_wfs_d, g_row_stride);
+                                                                 g_wfs_d, g_row_stride, raw_charge != 0);
   LARND_LAUNCH_CHECK("k_fee_backward");
   return LARND_OK;
 }

@@ -79,7 +79,13 @@ int larnd_check_cuda(cudaError_t e, const char* what);
     int _rc = larnd_check_cuda((call), #call);             \
     if (_rc != 0) return _rc;                              \
   } while (0)
-#define LARND_LAUNCH_CHECK(name) LARND_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it also feeds larnd_launch_count()
+extern unsigned long long g_launch_count;
+#define LARND_LAUNCH_CHECK(name)                                      \
+  do {                                                               \
+    __atomic_add_fetch(&g_launch_count, 1ull, __ATOMIC_RELAXED);     \
+    LARND_CUDA(cudaGetLastError());                                  \
+  } while (0)
 
 // optional event timing around the dominant kernels (larnd_profile_enable / larnd_profile_read)
 struct ProfSlot { cudaEvent_t start, stop; bool used; };

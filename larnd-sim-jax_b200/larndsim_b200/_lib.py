@@ -154,6 +154,7 @@ def _declare(lib):
     PP, PC = C.POINTER(ParamsPOD), C.POINTER(Columns)
     lib.larnd_last_error.restype = C.c_char_p
     lib.larnd_abi_version.restype = C.c_int
+    lib.larnd_launch_count.restype = C.c_uint64
     lib.larnd_lut_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(vp)]
     lib.larnd_lut_destroy.argtypes = [vp]
     lib.larnd_lut_destroy.restype = None
@@ -171,7 +172,7 @@ def _declare(lib):
     lib.larnd_profile_read.restype = C.c_int
     lib.larnd_fee_scratch_bytes.argtypes = [i32]
     lib.larnd_fee_scratch_bytes.restype = sz
-    lib.larnd_fee_backward.argtypes = [vp, vp, vp, i32, PP, vp, i64, vp]
+    lib.larnd_fee_backward.argtypes = [vp, vp, vp, i32, PP, vp, i64, i32, vp]
     lib.larnd_build_bank.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp]
     lib.larnd_build_bank.restype = C.c_int
     U2 = C.POINTER(C.c_uint32)

@@ -132,12 +132,34 @@ def get_vdrift(params):
     return _mobility(e, params.temperature, params.ELECTRON_MOBILITY_PARAMS) * e
 
 
+def _vdrift_f32(e, temperature, mob):
+    """get_vdrift evaluated op by op in float32, the way the reference's jitted function runs when eField is a traced
+    float32 leaf (consts_jax.py:208-216; Python-float constants are weak-typed and rounded to float32)."""
+    f = np.float32
+    a0, a1, a2, a3, a4, a5 = (f(a) for a in mob)
+    e = f(e)
+    num = a0 + a1 * e + a2 * np.power(e, f(1.5)) + a3 * np.power(e, f(2.5))
+    den = f(1) + f(mob[1] / mob[0]) * e + a4 * np.power(e, f(2)) + a5 * np.power(e, f(3))
+    mu = num / den * f((temperature / 89) ** -1.5) / f(1000)
+    return float(f(mu * e))
+
+
 def vdrift_and_derivative(params):
-    """(v, dv/dE) in double precision for the kernels' parameter block."""
+    """(v, dv/dE) for the kernels' parameter block.  v follows the reference's arithmetic: Python doubles rounded once when
+    eField is static, float32 op by op when it is a fitted leaf (a traced float32 scalar in the reference) — the tick,
+    fraction and template-index boundaries depend on the last bit of v.  dv/dE is the closed form, in double."""
     e = params.value("eField")
-    f = lambda x: _mobility(x, params.temperature, params.ELECTRON_MOBILITY_PARAMS) * x
-    h = 1e-6 * max(abs(e), 1.0)
-    return f(e), (f(e + h) - f(e - h)) / (2 * h)
+    a0, a1, a2, a3, a4, a5 = params.ELECTRON_MOBILITY_PARAMS
+    tc = (params.temperature / 89) ** -1.5 / 1000
+    num = a0 + a1 * e + a2 * e ** 1.5 + a3 * e ** 2.5
+    den = 1 + (a1 / a0) * e + a4 * e ** 2 + a5 * e ** 3
+    dnum = a1 + 1.5 * a2 * e ** 0.5 + 2.5 * a3 * e ** 1.5
+    dden = a1 / a0 + 2 * a4 * e + 3 * a5 * e ** 2
+    mu, dmu = num / den * tc, (dnum * den - num * dden) / den ** 2 * tc
+    v = mu * e
+    if "eField" in getattr(params, "_grad_fields", ()):
+        v = _vdrift_f32(e, params.temperature, params.ELECTRON_MOBILITY_PARAMS)
+    return v, mu + e * dmu
 
 
 def _geometry_from_yaml(detprop_file, pixel_file):

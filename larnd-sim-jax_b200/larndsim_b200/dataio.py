@@ -72,3 +72,40 @@ def pad_batch(batch, target_len, fields):
         if name in fields:
             out[n:, fields.index(name)] = -1
     return out
+
+
+# The ten columns the simulation reads (include/larnd_b200.h, larnd_columns_t); everything else in the 26-column file
+# layout is bookkeeping the hot path never touches.
+PACKED_FIELDS = ("eventID", "x", "y", "z", "z_start", "z_end", "dx", "dEdx", "dE", "t0")
+
+
+def pack_columns(tracks, fields):
+    """(packed (N, 10) array, PACKED_FIELDS): the columns the simulation reads, in the ABI's order.  ``fields`` is an
+    argument of every simulate_* entry point, so a packed batch is a valid input as it is: a loader that holds chopped
+    batches on the host uploads 40 instead of 104 bytes per segment.  Works on numpy arrays and torch tensors."""
+    idx = [tuple(fields).index(n) for n in PACKED_FIELDS]
+    if torch.is_tensor(tracks):
+        return tracks[:, idx].contiguous(), PACKED_FIELDS
+    import numpy as np
+    return np.ascontiguousarray(tracks[:, idx]), PACKED_FIELDS
+
+
+def simulate_from_raw(params, response_template, raw_tracks, fields, precision=None, rngseed=0, device=None,
+                      npix_capacity=None, n_events=None):
+    """The reference-facing entry for production batches: RAW (un-chopped) segment rows as they come out of the input file
+    (optimize/dataio.py:133-141) -> hits.  The reference chops on the host (a Python loop per raw row, :63-106) and uploads
+    104 B per CHOPPED segment; here the raw rows are uploaded (100-700x fewer) and expanded on the device by the chop
+    kernels, then simulate_wfs + simulate_stochastic run as usual.  ``raw_tracks``: (M, n_fields) float32, a pinned host
+    tensor / numpy array (uploaded here) or a CUDA tensor; event ids must be batch-local.  Returns the 8-tuple of
+    simulate_stochastic."""
+    from . import sim
+    if precision is None:
+        precision = float(params.electron_sampling_resolution)
+    if not torch.is_tensor(raw_tracks):
+        raw_tracks = torch.from_numpy(raw_tracks)
+    if not raw_tracks.is_cuda:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        raw_tracks = raw_tracks.to(dev, non_blocking=True)
+    chopped = chop_tracks(raw_tracks, fields, precision)
+    wfs, upix = sim.simulate_wfs(params, response_template, chopped, fields, npix_capacity=npix_capacity, n_events=n_events)
+    return sim.simulate_stochastic(params, wfs, upix, rngseed)

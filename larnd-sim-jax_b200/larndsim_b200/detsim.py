@@ -67,6 +67,7 @@ def get_hit_z(params, ticks, plane, fixed_v=False):
 # ------------------------------------------------------------------------------------------ id packing limits / validators
 # Host-side guards the reference runs on every batch before simulating (detsim_jax.py:26-152, called from
 # optimize/simulate.py:111-113 and dataio): same names, same exceptions (ValueError / OverflowError).
+_I32_MAX = 2 ** 31 - 1
 _I64_MAX = np.iinfo(np.int64).max
 
 
@@ -129,6 +130,11 @@ def validate_event_ids_for_packing(params, event_ids, kind="pixel", context=""):
         raise OverflowError("%s eventID %d exceeds the int64-safe limit %d for %s packing" % (context, top, limit, kind))
     if biggest > _I64_MAX:
         raise OverflowError("%s maximum packed %s id %d exceeds int64 max" % (context, kind, biggest))
+    if kind == "pixel" and biggest > _I32_MAX:
+        # the kernels pack pixel ids in int32 — and so does the reference as it is run (jax_enable_x64 is never set, so its
+        # astype(jnp.int64) yields int32 and larger ids wrap silently, detsim_jax.py:241-244); wrapping is refused here
+        raise OverflowError("%s maximum packed pixel id %d exceeds the int32 range ids are packed in (eventID must stay <= %d)"
+                            % (context, biggest, (_I32_MAX + 1) // _pixel_id_stride(params) - 1))
 
 
 def validate_packed_ids_for_decoding(params, packed_ids, kind="pixel", context=""):

@@ -12,18 +12,29 @@ def digitize(params, integral_list):
     return torch.clamp(v * params.ADC_COUNTS / (params.V_REF - params.V_CM), max=params.ADC_COUNTS)
 
 
-def undigitize(params, adcs):
-    return (adcs * (params.V_REF - params.V_CM) / params.ADC_COUNTS + params.V_CM - params.V_PEDESTAL) / params.GAIN
+class _AdcValues(torch.autograd.Function):
+    """get_adc_values as one kernel launch: the FEE kernel's integrated charge (before the digitiser) and its VJP."""
+
+    @staticmethod
+    def forward(ctx, wfs, params, noise):
+        upix = torch.zeros(wfs.shape[0], dtype=torch.int32, device=wfs.device)
+        fs = _sim.fee_forward(params, wfs, upix, noise, compact=False)
+        ctx.fs = fs
+        ctx.mark_non_differentiable(fs.ticks)
+        return fs.saved[:, 13:13 + fs.pod.max_adc_values].contiguous(), fs.ticks
+
+    @staticmethod
+    def backward(ctx, g_q, _g_ticks):
+        return _sim.fee_backward(ctx.fs, g_q, raw_charge=True), None, None
 
 
 def get_adc_values(params, pixels_signals, noise_rng_key=None):
-    """(adc (Npix,10) integrated charge, ticks (Npix,10)) like the reference (fee_jax.py:170-279).  The kernel
-    returns digitised ADC; the integral is recovered where the digitiser is invertible (unclipped hits)."""
+    """(adc (Npix,10) integrated charge in the reference's units, ticks (Npix,10) float, integer valued) — reference:
+    fee_jax.py:170-279.  The values are the kernel's own pre-digitiser integrals (bit-identical to what it digitises, also
+    for saturated hits) and differentiable w.r.t. pixels_signals like the reference's; digitize() maps them to ADC."""
+    _sim._check_cuda(pixels_signals, "pixels_signals")
     noise = _sim.make_noise(params, pixels_signals.shape[0], noise_rng_key, pixels_signals.device)
-    upix = torch.zeros(pixels_signals.shape[0], dtype=torch.int32, device=pixels_signals.device)
-    fs = _sim.fee_forward(params, pixels_signals, upix, noise, compact=False)
-    integral = torch.where(fs.ticks < pixels_signals.shape[1] - 2, undigitize(params, fs.adc), torch.zeros_like(fs.adc))
-    return integral, fs.ticks
+    return _AdcValues.apply(pixels_signals, params, noise)
 
 
 def _prob_forward(params, w, stop_threshold, want_state):

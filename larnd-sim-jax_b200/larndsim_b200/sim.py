@@ -292,8 +292,10 @@ def lut_backward(st, g_wfs, skip_garbage=False):
     """VJP of simulate_wfs: g_wfs is the gradient of the (Npix, Nticks-1) output.  Returns a float32 tensor of
     LARND_NPARAMS parameter gradients (order _lib.PARAM_ORDER)."""
     lib = _lib.get_lib()
-    g = g_wfs.contiguous()
     nt1 = st.pod.n_ticks - 1
+    g = g_wfs
+    if g.dtype != torch.float32 or g.dim() != 2 or g.stride(1) != 1 or g.stride(0) < nt1:
+        g = g.contiguous().float()   # fee_backward's strided view of a padded full-row buffer is taken as it is
     if tuple(g.shape) != (st.npix, nt1):
         raise ValueError("gradient shape %s != %s" % (tuple(g.shape), (st.npix, nt1)))
     grad = torch.zeros(_lib.NPARAMS, dtype=torch.float32, device=g.device)
@@ -305,24 +307,26 @@ def lut_backward(st, g_wfs, skip_garbage=False):
             bflags = (bflags & ~(_lib.FLAG_IMPL_CHUNK | _lib.FLAG_IMPL_SORTED)) | (_lib.FLAG_IMPL_SORTED if impl.startswith("s") else _lib.FLAG_IMPL_CHUNK)
         _lib.check(lib.larnd_lut_backward(st.n, C.byref(st.pod), st.lut.handle, st.n_events, st.npix,
                                           bflags, _ptr(st.workspace), st.workspace.numel(),
-                                          _ptr(st.counts), C.c_void_p(g.data_ptr() - 4), nt1, _ptr(grad), _stream()))
+                                          _ptr(st.counts), C.c_void_p(g.data_ptr() - 4), g.stride(0), _ptr(grad), _stream()))
     return grad
 
 
 class _SimulateWfs(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, theta, params, response_template, tracks, fields, names, npix_capacity, n_events):
+    def forward(ctx, theta, params, response_template, tracks, fields, names, npix_capacity, n_events, holder=None):
         st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
         ctx.st = st
         ctx.names = names
         ctx.mark_non_differentiable(st.unique_pixels)
+        if holder is not None:
+            holder.append(st.counts)
         return st.wfs_full[:, 1:], st.unique_pixels
 
     @staticmethod
     def backward(ctx, g_wfs, _g_pix):
         grad_all = lut_backward(ctx.st, g_wfs)
         idx = torch.tensor([_lib.PARAM_ORDER.index(n) for n in ctx.names], device=grad_all.device)
-        return (grad_all[idx],) + (None,) * 7
+        return (grad_all[idx],) + (None,) * 8
 
 
 def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, n_events=None):
@@ -332,9 +336,32 @@ def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, 
     if leaves and torch.is_grad_enabled():
         names = tuple(n for n, _ in leaves)
         theta = torch.stack([t.to(tracks.device, torch.float32) for _, t in leaves])
-        return _SimulateWfs.apply(theta, params, response_template, tracks, tuple(fields), names, npix_capacity, n_events)
-    st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
-    return st.wfs_full[:, 1:], st.unique_pixels
+        holder = []
+        wfs, upix = _SimulateWfs.apply(theta, params, response_template, tracks, tuple(fields), names, npix_capacity, n_events, holder)
+        counts = holder[0]
+    else:
+        st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
+        wfs, upix, counts = st.wfs_full[:, 1:], st.unique_pixels, st.counts
+    # With an explicit npix_capacity the call is asynchronous and a capacity overflow / bad event id is only flagged on the
+    # device: the flag travels with the outputs and is checked at the consumer's own synchronisation point
+    # (simulate_stochastic), so a public-API user cannot silently get all-zero waveforms.
+    wfs._larnd_state = upix._larnd_state = (counts, int(upix.shape[0]))
+    return wfs, upix
+
+
+def check_outputs(*tensors):
+    """Raises if the forward call that produced any of ``tensors`` tripped its device-side checks (see check_state)."""
+    for t in tensors:
+        stt = getattr(t, "_larnd_state", None)
+        if stt is not None:
+            cnt = stt[0].cpu()
+            if int(cnt[2]) & 2:
+                raise ValueError("eventID outside [-1, n_events) found in tracks")
+            if int(cnt[2]) & 4:
+                raise ValueError("a segment's longitudinal diffusion needs a template row beyond the (truncated) response_template bank")
+            if int(cnt[2]) != 0:
+                raise _lib.LarndError("npix_capacity=%d is too small for %d unique pixels (+1 padding entry)" % (stt[1], int(cnt[0])))
+            return
 
 
 def simulate_signals_state(params, response_template, tracks, fields, **kw):
@@ -480,13 +507,21 @@ def fee_forward(params, wfs, unique_pixels, noise=None, compact=True, pod=None):
     return fs
 
 
-def fee_backward(fs, g_adc):
+def fee_backward(fs, g_adc, raw_charge=False):
+    """VJP of the front end w.r.t. the (Npix, Nticks-1) waveforms.  The result is a view into a padded full-row buffer
+    (wfs_row_stride columns: garbage column 0 and the padding are zero), i.e. exactly the layout lut_backward's tile
+    kernel reads with aligned 16-byte loads — no copy between the two VJPs.  raw_charge: g_adc is the gradient w.r.t.
+    get_adc_values' integrated charge (no digitiser slope)."""
     lib = _lib.get_lib()
     g = g_adc.contiguous().float()
-    ntw = fs.pod.n_ticks - 1
-    out = torch.empty((fs.npix, ntw), dtype=torch.float32, device=g.device)
+    nt = fs.pod.n_ticks
+    buf = torch.empty((fs.npix, wfs_row_stride(nt)), dtype=torch.float32, device=g.device)
+    buf[:, 0] = 0      # the kernel writes columns 1 .. nt-1 of every row; the garbage column and the padding are zeroed here
+    buf[:, nt:] = 0
+    out = buf[:, 1:nt]
     with torch.cuda.device(g.device):
-        _lib.check(lib.larnd_fee_backward(_ptr(g), _ptr(fs.ticks), _ptr(fs.saved), fs.npix, C.byref(fs.pod), _ptr(out), ntw, _stream()))
+        _lib.check(lib.larnd_fee_backward(_ptr(g), _ptr(fs.ticks), _ptr(fs.saved), fs.npix, C.byref(fs.pod), _ptr(out), buf.stride(0),
+                                          1 if raw_charge else 0, _stream()))
     return out
 
 
@@ -539,9 +574,11 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
     if not need_grad:
         fs = fee_forward(params, wfs, unique_pixels, noise, compact=True)
         nv = int(fs.n_valid.item())
+        check_outputs(wfs, unique_pixels)   # same synchronisation point: the forward call's device-side flags
         hf, hi = fs.hits
         return hf[0, :nv], hf[1, :nv], hf[2, :nv], hf[3, :nv], hf[4, :nv], hf[5, :nv], hi[0, :nv], hi[1, :nv]
     adcs, ticks, pixel_x, pixel_y, event = _FeeAdc.apply(wfs, params, unique_pixels, noise)
+    check_outputs(wfs, unique_pixels)       # parse_output below synchronises anyway
     hit_prob = torch.where(ticks < wfs.shape[1] - 3, 1.0, 0.0)
     plane = torch.div(unique_pixels, params.n_pixels_x * params.n_pixels_y, rounding_mode="floor") % np.asarray(params.tpc_borders).shape[0]
     pixel_z = get_hit_z(params, ticks.reshape(-1), plane.repeat_interleave(ticks.shape[1])).reshape(ticks.shape)

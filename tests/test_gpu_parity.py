@@ -208,6 +208,35 @@ def test_waveform_row_stride_variants_agree(torch_dev, acc_impl):
         assert (np.abs(w - a)[:, 1:] <= 2 * WFS_RTOL * scale + 1e-4).all()
 
 
+def test_packed_columns_and_raw_entry_match_the_full_batch(torch_dev):
+    """`fields` is an argument of the API: a batch reduced to the ten columns the simulation reads (dataio.pack_columns,
+    40 instead of 104 bytes per segment on the host-to-device link) must give bit-identical pixel lists, waveforms and hits;
+    and dataio.simulate_from_raw (raw rows uploaded, chopped on the device) must reproduce the hits of the host-chopped batch."""
+    import torch
+    from larndsim_b200 import dataio, sim
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = torch.as_tensor(cm.synthetic_bank(32, 25, 25, 1950), device=torch_dev)
+    pp = cm.product_params(**kw).replace(electron_sampling_resolution=0.01)
+    seg = lo.swap_xz_structured(np.load(os.path.join(cm.GOLD, "segments_input_2.npz"))["segments"])
+    rows, gids = lo.make_batches(seg, 50.0)[0]
+    raw = lo.batch_array(seg, rows, gids, cm.FIELDS, False, 0.01)          # un-chopped rows of the first batch, local event ids
+    chopped = lo.chop_tracks(raw, cm.FIELDS, 0.01)
+    t = torch.as_tensor(chopped, device=torch_dev)
+    ref = sim.lut_forward(pp, bank, t, cm.FIELDS)
+    packed, pfields = dataio.pack_columns(chopped, cm.FIELDS)
+    assert packed.shape == (chopped.shape[0], 10) and pfields == dataio.PACKED_FIELDS
+    st = sim.lut_forward(pp, bank, torch.as_tensor(packed, device=torch_dev), pfields, npix_capacity=ref.npix)
+    assert torch.equal(st.unique_pixels, ref.unique_pixels)
+    scale = ref.wfs_full.abs().amax(dim=1, keepdim=True) + 1e-30
+    assert bool(((st.wfs_full - ref.wfs_full).abs() <= 2 * WFS_RTOL * scale + 1e-3).all())   # float atomics: order differs
+    hits_ref = sim.simulate_stochastic(pp, ref.wfs_full[:, 1:], ref.unique_pixels, 0)
+    hits_raw = dataio.simulate_from_raw(pp, bank, raw, cm.FIELDS, precision=0.01)
+    assert len(hits_raw[0]) == len(hits_ref[0]) > 0
+    for k in (4, 6, 7):
+        assert torch.equal(hits_raw[k], hits_ref[k])
+    assert float((hits_raw[0] - hits_ref[0]).abs().max()) <= ADC_ATOL
+
+
 def test_empty_and_all_padding_batches(torch_dev):
     import torch
     from larndsim_b200 import sim
@@ -275,6 +304,46 @@ def test_fee_with_injected_noise_matches_oracle(torch_dev):
                          torch.as_tensor(z.reshape(-1), device=torch_dev), compact=False)
     assert np.array_equal(fs.ticks.cpu().numpy(), ticks_o)
     assert np.array_equal(fs.adc.cpu().numpy(), lo.digitize(op, adc_o))
+
+
+def test_get_adc_values_returns_the_integrated_charge_and_its_gradient(torch_dev):
+    """fee.get_adc_values (fee_jax.py:170-279) returns the charge integrals themselves — also for hits the digitiser
+    clips (ADC 0 or 256), where un-digitising the ADC would be wrong — and is differentiable w.r.t. the waveforms:
+    d adc_k / d wfs[t] = t_sampling on the hit's integration interval, checked against central differences
+    of the float64 oracle."""
+    import torch
+    from larndsim_b200 import fee
+    kw = dict(number_pix_neighbors=1, signal_length=100)
+    bank = cm.synthetic_bank(32, 15, 15, 1950)
+    tr = cm.small_batch(1200, ibatch=1, pad=0, precision=0.01)
+    op, pp = cm.oracle_params(**kw), cm.product_params(**kw)
+    wfs_o, uniq_o = lo.simulate_wfs(op, bank, tr, cm.FIELDS, history={})
+    wfs_o = wfs_o.copy()
+    big = int(np.argmax(lo.get_adc_values(op, wfs_o)[0].max(axis=1)))
+    wfs_o[big] *= 300.0   # one fired row far beyond the ADC range: its hits saturate at ADC_COUNTS
+    q_o, ticks_o = lo.get_adc_values(op, wfs_o)
+    assert (lo.digitize(op, q_o) >= op.ADC_COUNTS).any()
+    w = torch.as_tensor(wfs_o, device=torch_dev).requires_grad_(True)
+    q, ticks = fee.get_adc_values(pp, w)
+    assert np.array_equal(ticks.cpu().numpy(), ticks_o)
+    assert np.array_equal(q.detach().cpu().numpy(), q_o)                       # bit for bit, saturated hits included
+    assert np.array_equal(fee.digitize(pp, q.detach()).cpu().numpy(), lo.digitize(op, q_o))
+    rng = np.random.default_rng(3)
+    G = rng.uniform(0.5, 1.5, q_o.shape).astype(np.float32)
+    (q * torch.as_tensor(G, device=torch_dev)).sum().backward()
+    g = w.grad.cpu().numpy()
+    rows = np.where((q_o != 0).any(axis=1))[0][:3]
+    for r in rows:                                                              # finite differences on a few fired rows
+        for t in (int(ticks_o[r, 0]) - 5, int(ticks_o[r, 0]) + 10, 1500):
+            if not 0 <= t < wfs_o.shape[1]:
+                continue
+            h = 1e-3 * max(abs(float(wfs_o[r, t])), 1.0)
+            wp, wm = wfs_o[r:r + 1].astype(np.float64), wfs_o[r:r + 1].astype(np.float64)
+            wp, wm = wp.copy(), wm.copy()
+            wp[0, t] += h
+            wm[0, t] -= h
+            fd = ((lo.get_adc_values(op, wp, dt=np.float64)[0] - lo.get_adc_values(op, wm, dt=np.float64)[0]) * G[r:r + 1]).sum() / (2 * h)
+            assert abs(g[r, t] - fd) <= 1e-3 * abs(fd) + 1e-6, (r, t, g[r, t], fd)
 
 
 def test_lut_gradients_match_float64_finite_differences(torch_dev, acc_impl):
@@ -601,6 +670,69 @@ def test_sorted_kernel_variants_agree(torch_dev, tmp_path):
         assert (r["ticks"][real] != ref["ticks"][real]).sum() <= 3
         nz = np.abs(ref["grad"]) > 0
         assert (np.abs(r["grad"][nz] / ref["grad"][nz] - 1) < GRAD_RTOL).all()
+
+
+_SHARD_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "larnd-sim-jax_b200"))
+import numpy as np, torch, torch.distributed as dist
+import larndsim_b200 as lb
+from larndsim_b200 import fit, parallel, synthetic
+from larndsim_b200.consts import build_response_template
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+ngpu = torch.cuda.device_count()
+dev = torch.device("cuda", rank if ngpu >= world else 0)
+torch.cuda.set_device(dev)
+# one rank per GPU over NCCL when the box has two GPUs; on a one-GPU box both ranks share cuda:0 and the two small
+# collectives go through gloo (NCCL refuses two ranks on one device) - the kernels and the two-phase reduction are the same
+dist.init_process_group("nccl" if ngpu >= world else "gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
+                        rank=rank, world_size=world)
+GEOM = os.path.join(sys.argv[1], "larnd-sim-jax_b200", "larndsim_b200", "data", "module0_geometry.json")
+names = ("Ab", "kb", "eField", "lifetime", "tran_diff", "long_diff")
+base = dict(number_pix_neighbors=2, signal_length=150, electron_sampling_resolution=0.01, RESET_NOISE_CHARGE=0, UNCORRELATED_NOISE_CHARGE=0)
+fields = synthetic.FIELDS
+tracks_all, nev_all = synthetic.synthetic_tracks(19800, seed=5, precision=0.01)
+p = lb.load_geometry_json(lb.build_params_class(list(names)), GEOM).replace(**base)
+bank = build_response_template(synthetic.synthetic_response(25, 25, 1950), p, device=dev)
+target = dict(Ab=0.83, kb=0.055, eField=0.52, lifetime=1.8e3, long_diff=5.0e-6, tran_diff=10e-6)
+nominal = dict(Ab=0.8, kb=0.0486, eField=0.5, lifetime=2.2e3, long_diff=4.0e-6, tran_diff=8.8e-6)
+loc, nev, _ = parallel.shard_tracks(tracks_all, fields, rank, world)
+prob = fit.FitProblem.from_target_params(names, p, target, bank, torch.as_tensor(loc, device=dev), fields, nev)
+loss, g = prob.loss_and_grads(nominal)
+if rank == 0:
+    single = fit.FitProblem.from_target_params(names, p, target, bank, torch.as_tensor(tracks_all, device=dev), fields, nev_all, distributed=False)
+    loss1, g1 = single.loss_and_grads(nominal)
+    np.savez(sys.argv[2], loss=float(loss), g=g.cpu().numpy(), loss1=float(loss1), g1=g1.cpu().numpy(), nseg=len(tracks_all),
+             nloc=len(loc), backend=dist.get_backend())
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_fit_step_equals_single_gpu(torch_dev, tmp_path):
+    """BASELINE config 4 on hardware: the fit step of optimize/fit_test.sh --lut (n = 2, L = 150, ~19.8 k segments, mse_adc,
+    six leaves) with the events sharded over two ranks must give the single-GPU loss and gradients: the MMD and charge
+    terms are normalised by GLOBAL sums, so this holds only if the two-phase reduction (7 loss sums, then 6 gradients) is
+    right.  Two ranks on two GPUs over NCCL when the box has them, else both on cuda:0 with the collectives over gloo."""
+    import socket
+    import subprocess
+    import sys
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "shard.npz")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, "-c", _SHARD_SCRIPT, cm.ROOT, out], env=env))
+    for pr in procs:
+        assert pr.wait(timeout=900) == 0
+    r = np.load(out)
+    assert 0 < r["nloc"] < r["nseg"]
+    assert abs(r["loss"] - r["loss1"]) <= 1e-4 * abs(r["loss1"]), (r["loss"], r["loss1"])
+    scale = np.abs(r["g1"]).max()
+    assert (np.abs(r["g"] - r["g1"]) <= 2e-3 * np.abs(r["g1"]) + 1e-5 * scale).all(), (r["g"], r["g1"])
+    assert (r["g1"] != 0).all()
 
 
 def test_fit_and_scan_drivers(torch_dev):

@@ -364,3 +364,30 @@ def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["steps"] == 1 and "workload" in line["config"]
+
+
+def test_packing_validator_uses_the_int32_range_ids_are_packed_in():
+    """pixel2id and the kernels pack ids in int32 (the reference never enables x64, so its astype(int64) is
+    int32 too): an eventID whose packed id would wrap must be refused, not accepted against the int64 limit."""
+    from larndsim_b200 import detsim
+    p = cm.product_params()
+    stride = 2 * p.n_pixels_x * p.n_pixels_y
+    top_ok = (2 ** 31) // stride - 1
+    detsim.validate_event_ids_for_packing(p, np.array([0, top_ok]), kind="pixel", context="test")
+    with pytest.raises(OverflowError):
+        detsim.validate_event_ids_for_packing(p, np.array([0, top_ok + 1]), kind="pixel", context="test")
+
+
+def test_vdrift_follows_the_reference_arithmetic_for_static_and_fitted_efield():
+    """Static eField: Python doubles rounded once; fitted eField (a traced float32 leaf in the reference): float32 op by
+    op.  The derivative handed to the backward kernels is the closed form."""
+    from larndsim_b200.consts import vdrift_and_derivative
+    from oracle import consts as oc
+    v_static, dv = vdrift_and_derivative(cm.product_params())
+    v_leaf, dv2 = vdrift_and_derivative(cm.product_params(grad=("eField",)))
+    assert v_static == oc.get_vdrift(cm.oracle_params())
+    assert v_leaf == float(oc.get_vdrift(cm.oracle_params(), traced=True)) and v_leaf != v_static
+    op = cm.oracle_params()
+    h = 1e-6
+    fd = (oc.get_vdrift(op.replace(eField=op.eField + h)) - oc.get_vdrift(op.replace(eField=op.eField - h))) / (2 * h)
+    assert abs(dv - fd) < 1e-8 and dv == dv2
