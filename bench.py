@@ -460,27 +460,36 @@ def run_ours(args):
         p4 = lb.load_geometry_json(lb.build_params_class(list(FIT_NAMES)), GEOM).replace(**base4)
         bank4 = build_response_template(synthetic.synthetic_response(25, 25, 1950), p4, device=dev)
         prob = fit.FitProblem.from_target_params(FIT_NAMES, p4, FIT_TARGET, bank4, fit_tracks, fields, fit_events)
-        adam = fit.AdamFit(prob, FIT_NOMINAL, lr=0.01)
-        for _ in range(10):
-            adam.step()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        n_fit = 50
-        t0 = time.perf_counter()
-        l0 = lib.larnd_launch_count()
-        for _ in range(n_fit):
-            adam.step()
-        torch.cuda.synchronize()
-        wall = torch.tensor([time.perf_counter() - t0], device=dev)
-        fit_launches = (lib.larnd_launch_count() - l0) / n_fit
-        if world > 1:
-            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        def time_fit(adam, n_fit=50):
+            for _ in range(10):
+                adam.step()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            l0 = lib.larnd_launch_count()
+            for _ in range(n_fit):
+                adam.step()
+            torch.cuda.synchronize()
+            wall = torch.tensor([time.perf_counter() - t0], device=dev)
+            nl = (lib.larnd_launch_count() - l0) / n_fit
+            if world > 1:
+                dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+            return float(wall.item()) / n_fit, nl
+
+        adam = fit.FusedAdamFit(prob, FIT_NOMINAL, lr=0.01)
+        s_fused, nl_fused = time_fit(adam)
+        s_auto, nl_auto = time_fit(fit.AdamFit(prob, FIT_NOMINAL, lr=0.01))
         extras["fit_step"] = {"metric": "fit steps/s (BASELINE config 4: fwd + mse_adc + grads of 6 parameters + Adam, events sharded)",
-                              "value": n_fit / float(wall.item()), "unit": "steps/s", "ms_per_step": 1e3 * float(wall.item()) / n_fit,
+                              "value": 1.0 / s_fused, "unit": "steps/s", "ms_per_step": 1e3 * s_fused,
                               "segments_per_step": int(fit_tracks.shape[0]) * world, "segments_per_gpu": int(fit_tracks.shape[0]),
-                              "our_kernel_launches_per_step": fit_launches, "timing": "host wall clock around 50 steps (the step is "
-                              "host-bound at this size), max over ranks", "collectives": "2 all-reduces (7 loss sums, 6 gradients)" if world > 1 else "none"}
+                              "our_kernel_launches_per_step": nl_fused,
+                              "path": "fit.FusedAdamFit: one asynchronous chain of C-ABI calls (dense mse_adc operator, no hit compaction, "
+                                      "no autograd graph), one host synchronisation per step",
+                              "autograd_path": {"ms_per_step": 1e3 * s_auto, "steps_per_s": 1.0 / s_auto, "our_kernel_launches_per_step": nl_auto,
+                                                "path": "fit.AdamFit: simulate_wfs + simulate_stochastic + losses.mse_adc under torch.autograd"},
+                              "timing": "host wall clock around 50 steps (the step is host-bound at this size), max over ranks",
+                              "collectives": "2 all-reduces (5 loss sums, 15 gradients)" if world > 1 else "none"}
 
         # ---- BASELINE config 5b: 16 x 16 likelihood scan over (eField, lifetime): loss + 2 gradients per point; the grid points
         # are dealt to point groups, the events of a point are sharded over the ranks of its group

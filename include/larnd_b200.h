@@ -278,6 +278,26 @@ int larnd_rbf_field(const float* targets_d, int32_t n_targets, const float* sour
                     int32_t n_sources, float sigma, float* field_d /* (n_targets, 4) */, void* scratch_d, size_t scratch_bytes,
                     void* stream);
 
+/* Dense mse_adc (losses_jax.py:58-82 on the hits of simulate_stochastic, sim_jax.py:738-769) WITHOUT hit compaction: the
+ * inputs are larnd_fee_forward's dense (npix, MAX_ADC_VALUES) outputs, every slot parse_output would drop enters with weight
+ * 0.  Lets a fit step (optimize/fit_params.py:731) run forward + loss + backward without a host synchronisation.
+ *   larnd_mse_adc_sums     -> sums_d[0..2] = {Kxx, Kxy, Sx} of THIS rank's events (sums_d[3..4] = {Kyy, Sy} of the target are
+ *                             written by the caller; all five are all-reduced by the caller when events are sharded)
+ *   larnd_mse_adc_backward -> loss_d[4] = {loss, mmd term, charge term, Sx}, g_adc_d (npix, MAX_ADC_VALUES) = dL/d adc and
+ *                             grad_params_d[LARND_P_EFIELD] += dL/d(hit z) * d(hit z)/d eField (detsim_jax.py:318)
+ * ref_points_d (n_ref, 3) = (x + event * 1e5, y, z) and ref_weights_d = Q * hit_prob of the target hits.  The same
+ * scratch_d (larnd_mse_adc_scratch_bytes) must be passed to both calls: it carries the kernel fields between them. */
+size_t larnd_mse_adc_scratch_bytes(int32_t npix, int32_t max_adc_values, int32_t n_ref);
+int larnd_mse_adc_sums(const float* adc_d, const float* ticks_d, const float* pixel_z_d, const float* pixel_x_d,
+                       const float* pixel_y_d, const int32_t* event_d, const int32_t* unique_pixels_d, int32_t npix,
+                       const larnd_params_t* params, const float* ref_points_d, const float* ref_weights_d, int32_t n_ref,
+                       float sigma, float* sums_d, void* scratch_d, size_t scratch_bytes, void* stream);
+int larnd_mse_adc_backward(const float* sums_d, const float* adc_d, const float* ticks_d, const float* pixel_z_d,
+                           const float* pixel_x_d, const float* pixel_y_d, const int32_t* event_d,
+                           const int32_t* unique_pixels_d, int32_t npix, const larnd_params_t* params, int32_t n_ref,
+                           float sigma, float lambda_q, float* loss_d, float* g_adc_d, float* grad_params_d,
+                           void* scratch_d, size_t scratch_bytes, void* stream);
+
 /* ---- Stream-form operators: the reference functions whose arguments are the materialised per-segment arrays.  The
  * fused entry points above never build those arrays; these exist so that code calling the reference's stages one by one
  * (quench -> drift -> simulate_drift_new -> simulate_signals, or simulate_drift -> current_mc ->

@@ -108,3 +108,206 @@ extern "C" int larnd_rbf_field(const float* targets_d, int32_t n_targets, const 
   LARND_LAUNCH_CHECK("k_rbf_field");
   return LARND_OK;
 }
+
+// ---- Dense mse_adc on the front end's (npix, 10) outputs ------------------------------------------------------------
+// The reference's fit step compacts the hits (parse_output, a host synchronisation) and evaluates mse_adc
+// (losses_jax.py:58-82) on the ragged list.  A hit slot that parse_output would drop (hit_prob == 0, event < 0 or
+// pixel < 0) contributes weight 0 to every sum of the loss, so the same number comes out of the DENSE arrays with the mask
+// folded into the weight: no compaction, no host round trip, fixed shapes — the whole step stays asynchronous.
+//   point_i  = (pixel_x + event * 1e5, pixel_y, pixel_z),   w_i = adc2charge(adc_i) * hit_prob_i * [event >= 0, pixel >= 0]
+//   L = Kxx / Sx^2 + Kyy / Sy^2 - 2 Kxy / (Sx Sy) + lambda_Q ((Sx - Sy) / (Sy + 1e-6))^2,   Kab = sum_ij wa_i wb_j K(a_i, b_j)
+// sums_d = {Kxx, Kxy, Sx, Kyy, Sy}: the first three are produced here, Kyy / Sy (target only) are the caller's; with events
+// sharded over ranks the caller all-reduces the five numbers between larnd_mse_adc_sums and larnd_mse_adc_backward.
+namespace {
+
+struct HitsArgs {
+  const float* adc; const float* ticks; const float* pz; const float* px; const float* py; const int32_t* event; const int32_t* upix;
+  int npix, nmax, n;  // n = npix * nmax points
+  float* pts; float* w;
+};
+
+__device__ __forceinline__ float adc_to_charge(float adc, const larnd_params_t& p) {
+  // losses_jax.py:380-383, evaluated in double and rounded once (what reproduces the goldens' Q column)
+  const double v = ((double)adc / (double)p.adc_counts * (double)p.v_ref_minus_cm + (double)p.v_cm - (double)p.v_pedestal) / (double)p.gain * 1e-3;
+  return (float)v;
+}
+
+__global__ void __launch_bounds__(RT)
+k_hits_points(const __grid_constant__ HitsArgs H, const __grid_constant__ larnd_params_t p, float* __restrict__ sums) {
+  __shared__ float s_part[RT / 32];
+  const int i = blockIdx.x * RT + threadIdx.x;
+  float w = 0.0f;
+  if (i < H.n) {
+    const int row = i / H.nmax;
+    const int ev = H.event[row];
+    const bool valid = ev >= 0 && H.upix[row] >= 0;
+    const float hp = H.ticks[i] < (float)(p.n_ticks - 1 - 3) ? 1.0f : 0.0f;
+    w = (valid && hp > p.hit_prob_threshold) ? adc_to_charge(H.adc[i], p) * hp : 0.0f;
+    H.pts[(int64_t)i * 3] = __fadd_rn(H.px[row], __fmul_rn((float)ev, 1e5f));
+    H.pts[(int64_t)i * 3 + 1] = H.py[row];
+    H.pts[(int64_t)i * 3 + 2] = H.pz[i];
+    H.w[i] = w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < RT / 32; ++k) t += s_part[k];
+    if (t != 0.0f) atomicAdd(sums + 2, t);
+  }
+}
+
+__global__ void __launch_bounds__(RT)
+k_hits_ksums(const float* __restrict__ w, const float4* __restrict__ fxx, const float4* __restrict__ fxy, int n, float* __restrict__ sums) {
+  __shared__ float s_part[2][RT / 32];
+  const int i = blockIdx.x * RT + threadIdx.x;
+  float a = 0.0f, b = 0.0f;
+  if (i < n) { const float wi = w[i]; a = wi * fxx[i].x; b = wi * fxy[i].x; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { s_part[0][threadIdx.x >> 5] = a; s_part[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.0f, tb = 0.0f;
+    for (int k = 0; k < RT / 32; ++k) { ta += s_part[0][k]; tb += s_part[1][k]; }
+    if (ta != 0.0f) atomicAdd(sums, ta);
+    if (tb != 0.0f) atomicAdd(sums + 1, tb);
+  }
+}
+
+__global__ void __launch_bounds__(RT)
+k_hits_backward(const __grid_constant__ HitsArgs H, const __grid_constant__ larnd_params_t p, const float4* __restrict__ fxx,
+                const float4* __restrict__ fxy, const float* __restrict__ sums, float sigma, float lambda_q, float* __restrict__ loss,
+                float* __restrict__ g_adc, float* __restrict__ g_params) {
+  __shared__ float s_part[RT / 32];
+  const float Kxx = sums[0], Kxy = sums[1], Sx = sums[2], Kyy = sums[3], Sy = sums[4];
+  const float isx = Sx != 0.0f ? 1.0f / Sx : 0.0f, isy = Sy != 0.0f ? 1.0f / Sy : 0.0f;
+  const float dq = (Sx - Sy) / (Sy + 1e-6f);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float mmd = Kxx * isx * isx + Kyy * isy * isy - 2.0f * Kxy * isx * isy;
+    loss[0] = mmd + lambda_q * dq * dq;
+    loss[1] = mmd;
+    loss[2] = dq * dq;
+    loss[3] = Sx;
+  }
+  const int i = blockIdx.x * RT + threadIdx.x;
+  float gE = 0.0f;
+  if (i < H.n) {
+    const float wi = H.w[i];
+    float ga = 0.0f;
+    if (wi != 0.0f || true) {
+      const float4 a = fxx[i], b = fxy[i];
+      // d L / d w_i
+      const float dLdw = 2.0f * a.x * isx * isx - 2.0f * Kxx * isx * isx * isx - 2.0f * b.x * isx * isy + 2.0f * Kxy * isx * isx * isy +
+                         2.0f * lambda_q * dq / (Sy + 1e-6f);
+      const int row = i / H.nmax;
+      const bool valid = H.event[row] >= 0 && H.upix[row] >= 0;
+      const float hp = H.ticks[i] < (float)(p.n_ticks - 1 - 3) ? 1.0f : 0.0f;
+      // w = adc2charge(adc) * hp: linear in adc with slope (V_REF - V_CM) / (ADC_COUNTS * GAIN) * 1e-3
+      if (valid && hp > p.hit_prob_threshold) ga = dLdw * hp * (p.v_ref_minus_cm / (p.adc_counts * p.gain) * 1e-3f);
+      // d L / d z_i, and z_i = z_anode + tick * t_sampling * v(eField) * sign (detsim_jax.py:318): the drift velocity is the only
+      // parameter the hit position depends on
+      const float dLdz = (2.0f * wi * a.w * isx * isx - 2.0f * wi * b.w * isx * isy) / (sigma * sigma);
+      const int plane = (H.upix[row] >= 0) ? (H.upix[row] / (p.n_pixels_x * p.n_pixels_y)) % p.n_tpc : 0;
+      const float sgn = p.tpc_borders[plane][2][1] > p.tpc_borders[plane][2][0] ? 1.0f : -1.0f;
+      gE = dLdz * H.ticks[i] * p.t_sampling * sgn * p.dvdrift_dEfield;
+    }
+    g_adc[i] = ga;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gE += __shfl_xor_sync(0xffffffffu, gE, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = gE;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int k = 0; k < RT / 32; ++k) t += s_part[k];
+    if (t != 0.0f) atomicAdd(g_params + LARND_P_EFIELD, t);
+  }
+}
+
+struct HitsScratch { float* pts; float* w; float* fxx; float* fxy; float* tbox; float* rbox; };
+
+inline size_t hits_scratch_layout(int n, int n_ref, char* base, HitsScratch* hs) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+  const int ntt = (n + RT - 1) / RT, nrt = (n_ref + RT - 1) / RT;
+  char* a = take((size_t)n * 3 * sizeof(float));
+  char* b = take((size_t)n * sizeof(float));
+  char* c = take((size_t)n * 4 * sizeof(float));
+  char* d = take((size_t)n * 4 * sizeof(float));
+  char* e = take((size_t)(ntt + 1) * 6 * sizeof(float));
+  char* f = take((size_t)(nrt + 1) * 6 * sizeof(float));
+  if (hs) { hs->pts = (float*)a; hs->w = (float*)b; hs->fxx = (float*)c; hs->fxy = (float*)d; hs->tbox = (float*)e; hs->rbox = (float*)f; }
+  return off;
+}
+
+inline int hits_check(const float* adc, const float* ticks, const float* pz, const float* px, const float* py, const int32_t* ev,
+                      const int32_t* up, int32_t npix, const larnd_params_t* p, int32_t n_ref, const void* scratch, size_t bytes) {
+  if (!adc || !ticks || !pz || !px || !py || !ev || !up || !p || npix < 0 || n_ref < 0 || !scratch ||
+      bytes < hits_scratch_layout(npix * p->max_adc_values, n_ref, nullptr, nullptr)) {
+    larnd_set_error("larnd_mse_adc: bad argument or scratch too small");
+    return LARND_E_ARG;
+  }
+  return LARND_OK;
+}
+
+}  // namespace
+
+extern "C" size_t larnd_mse_adc_scratch_bytes(int32_t npix, int32_t max_adc_values, int32_t n_ref) {
+  return hits_scratch_layout(npix * max_adc_values, n_ref, nullptr, nullptr);
+}
+
+extern "C" int larnd_mse_adc_sums(const float* adc_d, const float* ticks_d, const float* pixel_z_d, const float* pixel_x_d,
+                                  const float* pixel_y_d, const int32_t* event_d, const int32_t* unique_pixels_d, int32_t npix,
+                                  const larnd_params_t* params, const float* ref_points_d, const float* ref_weights_d, int32_t n_ref,
+                                  float sigma, float* sums_d, void* scratch_d, size_t scratch_bytes, void* stream) {
+  int rc = hits_check(adc_d, ticks_d, pixel_z_d, pixel_x_d, pixel_y_d, event_d, unique_pixels_d, npix, params, n_ref, scratch_d, scratch_bytes);
+  if (rc) return rc;
+  if (!sums_d || !(sigma > 0) || (n_ref > 0 && (!ref_points_d || !ref_weights_d))) { larnd_set_error("larnd_mse_adc_sums: bad argument"); return LARND_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HitsScratch hs;
+  const int n = npix * params->max_adc_values;
+  hits_scratch_layout(n, n_ref, reinterpret_cast<char*>(scratch_d), &hs);
+  LARND_CUDA(cudaMemsetAsync(sums_d, 0, 3 * sizeof(float), st));   // Kxx, Kxy, Sx; [3], [4] = Kyy, Sy are the caller's
+  if (n == 0) return LARND_OK;
+  HitsArgs H{adc_d, ticks_d, pixel_z_d, pixel_x_d, pixel_y_d, event_d, unique_pixels_d, npix, params->max_adc_values, n, hs.pts, hs.w};
+  const int ntt = (n + RT - 1) / RT, nrt = (n_ref + RT - 1) / RT;
+  k_hits_points<<<ntt, RT, 0, st>>>(H, *params, sums_d);
+  LARND_LAUNCH_CHECK("k_hits_points");
+  k_rbf_bbox<<<ntt, RT, 0, st>>>(hs.pts, n, hs.tbox);
+  LARND_LAUNCH_CHECK("k_rbf_bbox");
+  const float inv2s2 = 0.5f / (sigma * sigma), cutoff = 15.0f * sigma;
+  k_rbf_field<<<ntt, RT, 0, st>>>(hs.pts, n, hs.tbox, hs.pts, hs.w, n, hs.tbox, ntt, inv2s2, cutoff, hs.fxx);
+  LARND_LAUNCH_CHECK("k_rbf_field(xx)");
+  if (nrt > 0) {
+    k_rbf_bbox<<<nrt, RT, 0, st>>>(ref_points_d, n_ref, hs.rbox);
+    LARND_LAUNCH_CHECK("k_rbf_bbox(ref)");
+  }
+  k_rbf_field<<<ntt, RT, 0, st>>>(hs.pts, n, hs.tbox, ref_points_d, ref_weights_d, n_ref, hs.rbox, nrt, inv2s2, cutoff, hs.fxy);
+  LARND_LAUNCH_CHECK("k_rbf_field(xy)");
+  k_hits_ksums<<<ntt, RT, 0, st>>>(hs.w, reinterpret_cast<const float4*>(hs.fxx), reinterpret_cast<const float4*>(hs.fxy), n, sums_d);
+  LARND_LAUNCH_CHECK("k_hits_ksums");
+  return LARND_OK;
+}
+
+extern "C" int larnd_mse_adc_backward(const float* sums_d, const float* adc_d, const float* ticks_d, const float* pixel_z_d,
+                                      const float* pixel_x_d, const float* pixel_y_d, const int32_t* event_d,
+                                      const int32_t* unique_pixels_d, int32_t npix, const larnd_params_t* params, int32_t n_ref,
+                                      float sigma, float lambda_q, float* loss_d, float* g_adc_d, float* grad_params_d,
+                                      void* scratch_d, size_t scratch_bytes, void* stream) {
+  int rc = hits_check(adc_d, ticks_d, pixel_z_d, pixel_x_d, pixel_y_d, event_d, unique_pixels_d, npix, params, n_ref, scratch_d, scratch_bytes);
+  if (rc) return rc;
+  if (!sums_d || !loss_d || !g_adc_d || !grad_params_d) { larnd_set_error("larnd_mse_adc_backward: null argument"); return LARND_E_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  HitsScratch hs;
+  const int n = npix * params->max_adc_values;
+  hits_scratch_layout(n, n_ref, reinterpret_cast<char*>(scratch_d), &hs);
+  HitsArgs H{adc_d, ticks_d, pixel_z_d, pixel_x_d, pixel_y_d, event_d, unique_pixels_d, npix, params->max_adc_values, n, hs.pts, hs.w};
+  k_hits_backward<<<max((n + RT - 1) / RT, 1), RT, 0, st>>>(H, *params, reinterpret_cast<const float4*>(hs.fxx),
+                                                           reinterpret_cast<const float4*>(hs.fxy), sums_d, sigma, lambda_q, loss_d, g_adc_d,
+                                                           grad_params_d);
+  LARND_LAUNCH_CHECK("k_hits_backward");
+  return LARND_OK;
+}

@@ -193,6 +193,12 @@ def _declare(lib):
     lib.larnd_rbf_field_scratch_bytes.restype = sz
     lib.larnd_rbf_field.argtypes = [vp, i32, vp, vp, i32, C.c_float, vp, vp, sz, vp]
     lib.larnd_rbf_field.restype = C.c_int
+    lib.larnd_mse_adc_scratch_bytes.argtypes = [i32, i32, i32]
+    lib.larnd_mse_adc_scratch_bytes.restype = sz
+    lib.larnd_mse_adc_sums.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, PP, vp, vp, i32, C.c_float, vp, vp, sz, vp]
+    lib.larnd_mse_adc_sums.restype = C.c_int
+    lib.larnd_mse_adc_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, PP, i32, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp]
+    lib.larnd_mse_adc_backward.restype = C.c_int
     PCC = C.POINTER(ChopColumns)
     lib.larnd_chop_count.argtypes = [vp, i64, PCC, C.c_double, vp, vp]
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]

@@ -9,7 +9,10 @@ def digitize(params, integral_list):
     """ADC counts from integrated charge — no rounding, ADC stays float (reference: fee_jax.py:57-71)."""
     x = integral_list if torch.is_tensor(integral_list) else torch.as_tensor(integral_list, dtype=torch.float32)
     v = torch.clamp(x * params.GAIN + params.V_PEDESTAL - params.V_CM, min=0)
-    return torch.clamp(v * params.ADC_COUNTS / (params.V_REF - params.V_CM), max=params.ADC_COUNTS)
+    # a true float32 division like XLA's: torch turns `tensor / python_scalar` into a multiplication by the reciprocal on
+    # CUDA, which is off by an ulp now and then — divide by a 0-d DEVICE tensor instead
+    den = torch.tensor(params.V_REF - params.V_CM, dtype=v.dtype, device=v.device)
+    return torch.clamp(v * params.ADC_COUNTS / den, max=params.ADC_COUNTS)
 
 
 class _AdcValues(torch.autograd.Function):

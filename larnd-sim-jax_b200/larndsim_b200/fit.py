@@ -170,3 +170,141 @@ def scan_2d(make_problem, p1, a1, p2, a2, fixed=None, event_shards=1):
         if ipt >= 0:
             out[int(ipt) // n2, int(ipt) % n2] = (l, g1, g2)
     return out
+
+
+class FusedFitStep:
+    """The same loss + gradients as FitProblem.loss_and_grads, as ONE asynchronous chain of kernel launches through the C ABI:
+    prepare -> unique -> accumulate -> front end (dense, no hit compaction) -> dense mse_adc sums -> [all-reduce 5 floats]
+    -> mse_adc VJP -> front-end VJP -> accumulate VJP + chain rule -> [all-reduce 15 floats] -> one 80-byte read-back.
+    Every buffer is allocated once; no autograd graph, no torch glue kernels, a single host synchronisation per step (the
+    read of loss + gradients the optimiser needs anyway).  This is the regime every optimize/ fit of the reference runs in
+    (~20 k segments per batch, optimize/fit_test.sh), where a step is bound by host work, not by the kernels."""
+
+    def __init__(self, problem, capacity_margin=1.1):
+        import ctypes as C
+        from . import _lib
+        self.C, self._lib, self.lib = C, _lib, _lib.get_lib()
+        pr = self.problem = problem
+        dev = self.dev = pr.tracks.device
+        lib = self.lib
+        # static configuration: a Params object WITHOUT tensor leaves (values are plain floats here)
+        self.params = pr.params
+        with torch.cuda.device(dev):
+            self.lut = sim.get_lut(pr.bank, pr.params.signal_length, pr.params.nb_sampling_bins_per_pixel, pr.params.number_pix_neighbors)
+            self.pod = sim.make_pod(self._with_values({}), self.lut.shape)
+            self.cols = sim.make_columns(pr.fields)
+            n = self.n = pr.tracks.shape[0]
+            self.tracks = pr.tracks.contiguous()
+            self.ws_bytes = lib.larnd_workspace_bytes(n, pr.n_events, self.pod.n_tpc, self.pod.n_pixels_x, self.pod.n_pixels_y)
+            self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+            self.counts = torch.zeros(4, dtype=torch.int32, device=dev)
+            st = sim.lut_forward(self._with_values({}), pr.bank, self.tracks, pr.fields, n_events=pr.n_events)
+            self.npix = sim.pad_size(int(st.npix * capacity_margin) + 8, "fused_fit_unique_pixels", 0.2)
+            del st
+            nt, k = self.pod.n_ticks, self.pod.max_adc_values
+            npix = self.npix
+            self.upix = torch.empty(npix, dtype=torch.int32, device=dev)
+            self.wfs = sim.alloc_wfs(npix, nt, dev)
+            f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+            self.adc, self.ticks, self.pz = f32(npix, k), f32(npix, k), f32(npix, k)
+            self.px, self.py = f32(npix), f32(npix)
+            self.event = torch.empty(npix, dtype=torch.int32, device=dev)
+            self.saved = torch.zeros((npix, 32), dtype=torch.float32, device=dev)
+            self.n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.fee_scratch = torch.empty(lib.larnd_fee_scratch_bytes(npix), dtype=torch.uint8, device=dev)
+            self.g_adc = f32(npix, k)
+            self.g_wfs = torch.zeros((npix, self.wfs.shape[1]), dtype=torch.float32, device=dev)   # padding / column 0 stay zero
+            # target side of the loss: points, weights, Kyy, Sy (constants of the fit)
+            rq, rx, ry, rz, _rt, rhp, rev = pr.ref
+            self.ref_pts = torch.stack((rx + rev * 1e5, ry, rz), dim=-1).contiguous().float()
+            self.ref_w = (rq * rhp).contiguous().float()
+            self.n_ref = int(self.ref_w.shape[0])
+            from .losses import rbf_field
+            fyy = rbf_field(self.ref_pts, self.ref_pts, self.ref_w, pr.sigma) if self.n_ref else torch.zeros((0, 4), device=dev)
+            self.out = torch.zeros(8 + 4 + _lib.NPARAMS + 4, dtype=torch.float32, device=dev)   # sums | loss | grads | counts (as float)
+            self.sums, self.loss, self.grad = self.out[0:8], self.out[8:12], self.out[12:12 + _lib.NPARAMS]
+            self.kyy_sy = torch.stack([(self.ref_w * fyy[:, 0]).sum(), self.ref_w.sum()]) if self.n_ref else torch.zeros(2, device=dev)
+            self.loss_scratch = torch.empty(max(lib.larnd_mse_adc_scratch_bytes(npix, k, self.n_ref), 256), dtype=torch.uint8, device=dev)
+            self.host = torch.zeros(self.out.shape[0], dtype=torch.float32).pin_memory()
+        self.idx = [_lib.PARAM_ORDER.index(nm) for nm in pr.names]
+
+    def _with_values(self, values):
+        vals = {nm: float(v) for nm, v in values.items()}
+        base = {nm: float(self.problem.params.value(nm)) for nm in self.problem.names if nm not in vals}
+        return self.problem.params.replace(**dict(base, **vals))
+
+    def __call__(self, values):
+        """(loss, gradients w.r.t. problem.names as a numpy array) for plain-float parameter values."""
+        C, lib, pr = self.C, self.lib, self.problem
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        check = self._lib.check
+        with torch.cuda.device(self.dev):
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            pod = sim.fill_pod_leaves(self.pod, self._with_values(values))
+            P = C.byref(pod)
+            npix, nt = self.npix, pod.n_ticks
+            self.out[:12 + self._lib.NPARAMS].zero_()
+            self.sums[3:5].copy_(self.kyy_sy)
+            self.counts.zero_()
+            check(lib.larnd_lut_forward(ptr(self.tracks), self.n, C.byref(self.cols), P, self.lut.handle, pr.n_events, npix, 0,
+                                        ptr(self.workspace), self.ws_bytes, ptr(self.upix), ptr(self.wfs), self.wfs.stride(0),
+                                        ptr(self.counts), stream))
+            wfs1 = C.c_void_p(self.wfs.data_ptr() + 4)          # simulate_wfs' view [:, 1:]
+            null = C.c_void_p(0)
+            check(lib.larnd_fee_forward(wfs1, self.wfs.stride(0), ptr(self.upix), npix, P, null, ptr(self.adc), ptr(self.ticks),
+                                        ptr(self.pz), ptr(self.px), ptr(self.py), ptr(self.event), ptr(self.saved),
+                                        null, null, null, null, null, null, null, null, ptr(self.n_valid),
+                                        ptr(self.fee_scratch), self.fee_scratch.numel(), stream))
+            fee_out = (ptr(self.adc), ptr(self.ticks), ptr(self.pz), ptr(self.px), ptr(self.py), ptr(self.event), ptr(self.upix))
+            check(lib.larnd_mse_adc_sums(*fee_out, npix, P, ptr(self.ref_pts), ptr(self.ref_w), self.n_ref, float(pr.sigma),
+                                         ptr(self.sums), ptr(self.loss_scratch), self.loss_scratch.numel(), stream))
+            if pr.distributed:
+                dist.all_reduce(self.sums[:5], group=pr.group)
+            check(lib.larnd_mse_adc_backward(ptr(self.sums), *fee_out, npix, P, self.n_ref, float(pr.sigma), float(pr.lambda_Q),
+                                             ptr(self.loss), ptr(self.g_adc), ptr(self.grad), ptr(self.loss_scratch),
+                                             self.loss_scratch.numel(), stream))
+            g1 = C.c_void_p(self.g_wfs.data_ptr() + 4)
+            check(lib.larnd_fee_backward(ptr(self.g_adc), ptr(self.ticks), ptr(self.saved), npix, P, g1, self.g_wfs.stride(0), 0, stream))
+            check(lib.larnd_lut_backward(self.n, P, self.lut.handle, pr.n_events, npix, 1, ptr(self.workspace), self.ws_bytes,
+                                         ptr(self.counts), ptr(self.g_wfs), self.g_wfs.stride(0), ptr(self.grad), stream))
+            if pr.distributed:
+                dist.all_reduce(self.grad, group=pr.group)
+            self.out[12 + self._lib.NPARAMS:].copy_(self.counts)   # device-side flags travel with the results
+            self.host.copy_(self.out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h = self.host.numpy()
+        flags = int(h[12 + self._lib.NPARAMS + 2])
+        if flags:
+            raise self._lib.LarndError("fit step: device-side check failed (flags %d: 1 = pixel capacity %d too small, 2 = event id "
+                                       "out of range, 4 = template row beyond the bank)" % (flags, self.npix))
+        return float(h[8]), h[12:12 + self._lib.NPARAMS][self.idx].astype(np.float64)
+
+
+class FusedAdamFit:
+    """AdamFit with FusedFitStep: parameters live on the host (six floats), Adam runs on the host, one synchronisation per
+    step.  Same update rule as torch.optim.Adam (bias-corrected first / second moments, eps outside the square root)."""
+
+    def __init__(self, problem, nominal, lr=0.01, betas=(0.9, 0.999), eps=1e-8):
+        self.step_fn = FusedFitStep(problem)
+        self.names = problem.names
+        self.nominal = np.array([float(nominal[n]) for n in self.names])
+        self.theta = np.ones(len(self.names))
+        self.lr, self.b1, self.b2, self.eps = lr, betas[0], betas[1], eps
+        self.m, self.v, self.t = np.zeros_like(self.theta), np.zeros_like(self.theta), 0
+
+    def step(self):
+        vals = {n: float(t * s) for n, t, s in zip(self.names, self.theta, self.nominal)}
+        loss, g = self.step_fn(vals)
+        g = g * self.nominal                       # d loss / d theta (theta = value / nominal)
+        self.t += 1
+        self.m = self.b1 * self.m + (1 - self.b1) * g
+        self.v = self.b2 * self.v + (1 - self.b2) * g * g
+        mh, vh = self.m / (1 - self.b1 ** self.t), self.v / (1 - self.b2 ** self.t)
+        self.theta = self.theta - self.lr * mh / (np.sqrt(vh) + self.eps)
+        return loss
+
+    def values(self):
+        return {n: float(t * s) for n, t, s in zip(self.names, self.theta, self.nominal)}
+
+
+FastAdamFit = FusedAdamFit

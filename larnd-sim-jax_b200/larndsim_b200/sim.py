@@ -57,12 +57,8 @@ def _f(params, name):
     return params.value(name)
 
 
-def make_pod(params, lut_shape=None):
-    """Fill the C parameter block.  Python-float constant expressions are evaluated in double and rounded to
-    float32 once, which is what the reference's weak-typed constants do under jit."""
-    P = _lib.ParamsPOD()
-    mode = params.recombination_mode
-    P.recombination_mode = mode.value if isinstance(mode, RecombinationMode) else int(mode)
+def fill_pod_leaves(P, params):
+    """The fields of the C parameter block that depend on fittable Params fields (everything a fit step changes)."""
     P.Ab, P.kb, P.alpha, P.beta = _f(params, "Ab"), _f(params, "kb"), _f(params, "alpha"), _f(params, "beta")
     P.inv_R2 = 1.0 / _f(params, "R_param") ** 2
     P.efield_rho = _f(params, "eField") * _f(params, "lArDensity")
@@ -70,8 +66,20 @@ def make_pod(params, lut_shape=None):
     v, dv = vdrift_and_derivative(params)
     P.vdrift, P.dvdrift_dEfield = v, dv
     P.lifetime, P.long_diff, P.tran_diff = _f(params, "lifetime"), _f(params, "long_diff"), _f(params, "tran_diff")
-    P.size_margin = params.size_margin
     P.shift_x, P.shift_y, P.shift_z = _f(params, "shift_x"), _f(params, "shift_y"), _f(params, "shift_z")
+    P.eField, P.lArDensity, P.R_param = _f(params, "eField"), _f(params, "lArDensity"), _f(params, "R_param")
+    P.ts_vdrift = float(np.float32(params.t_sampling) * np.float32(v))
+    return P
+
+
+def make_pod(params, lut_shape=None):
+    """Fill the C parameter block.  Python-float constant expressions are evaluated in double and rounded to
+    float32 once, which is what the reference's weak-typed constants do under jit."""
+    P = _lib.ParamsPOD()
+    mode = params.recombination_mode
+    P.recombination_mode = mode.value if isinstance(mode, RecombinationMode) else int(mode)
+    fill_pod_leaves(P, params)
+    P.size_margin = params.size_margin
     borders = np.asarray(params.tpc_borders, dtype=np.float64)
     if borders.ndim != 3 or borders.shape[0] > _lib.MAX_TPC:
         raise ValueError("tpc_borders must have shape (n_tpc<=%d, 3, 2)" % _lib.MAX_TPC)
@@ -116,8 +124,6 @@ def make_pod(params, lut_shape=None):
     P.hold_interval = round((3 * params.CLOCK_CYCLE + params.ADC_HOLD_DELAY * params.CLOCK_CYCLE) / params.t_sampling)
     P.max_adc_values = int(params.MAX_ADC_VALUES)
     P.diffusion_in_current_sim = int(bool(params.diffusion_in_current_sim))
-    P.eField, P.lArDensity, P.R_param = _f(params, "eField"), _f(params, "lArDensity"), _f(params, "R_param")
-    P.ts_vdrift = float(np.float32(params.t_sampling) * np.float32(v))
     return P
 
 

@@ -699,11 +699,13 @@ nominal = dict(Ab=0.8, kb=0.0486, eField=0.5, lifetime=2.2e3, long_diff=4.0e-6, 
 loc, nev, _ = parallel.shard_tracks(tracks_all, fields, rank, world)
 prob = fit.FitProblem.from_target_params(names, p, target, bank, torch.as_tensor(loc, device=dev), fields, nev)
 loss, g = prob.loss_and_grads(nominal)
+floss, fg = fit.FusedFitStep(prob)(nominal)          # the autograd-free chain, same sharding and collectives
 if rank == 0:
     single = fit.FitProblem.from_target_params(names, p, target, bank, torch.as_tensor(tracks_all, device=dev), fields, nev_all, distributed=False)
     loss1, g1 = single.loss_and_grads(nominal)
+    floss1, fg1 = fit.FusedFitStep(single)(nominal)
     np.savez(sys.argv[2], loss=float(loss), g=g.cpu().numpy(), loss1=float(loss1), g1=g1.cpu().numpy(), nseg=len(tracks_all),
-             nloc=len(loc), backend=dist.get_backend())
+             nloc=len(loc), backend=dist.get_backend(), floss=floss, fg=fg, floss1=floss1, fg1=fg1)
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -733,6 +735,10 @@ def test_sharded_fit_step_equals_single_gpu(torch_dev, tmp_path):
     scale = np.abs(r["g1"]).max()
     assert (np.abs(r["g"] - r["g1"]) <= 2e-3 * np.abs(r["g1"]) + 1e-5 * scale).all(), (r["g"], r["g1"])
     assert (r["g1"] != 0).all()
+    # the fused (autograd-free, dense-loss) step: same loss and gradients, sharded and not
+    for lf, gf in ((r["floss1"], r["fg1"]), (r["floss"], r["fg"])):
+        assert abs(lf - r["loss1"]) <= 2e-4 * abs(r["loss1"]), (lf, r["loss1"])
+        assert (np.abs(gf - r["g1"]) <= 3e-3 * np.abs(r["g1"]) + 1e-5 * scale).all(), (gf, r["g1"])
 
 
 def test_fit_and_scan_drivers(torch_dev):
