@@ -166,27 +166,31 @@ def get_vdrift(params, traced=False):
     return num / den * tc / f(1000) * e
 
 
-def gaussian_taps(params):
+def gaussian_taps(params, dtype=np.float32):
     """Normalised Gaussian kernels, one per long_diff_template entry (consts_jax.py:427-428)."""
+    dt = np.dtype(dtype).type
     ext = int(params.long_diff_extent)
-    x = np.arange(-ext, ext + 1, 1).astype(np.float32)
-    sig = np.asarray(params.long_diff_template, dtype=np.float32)[:, None]
-    g = np.exp(-0.5 * (x[None, :] / sig) ** 2) / (sig * np.float32(math.sqrt(2 * math.pi)))
-    g = g.astype(np.float32)
-    return (g / g.sum(axis=1, keepdims=True)).astype(np.float32)
+    x = np.arange(-ext, ext + 1, 1).astype(dtype)
+    sig = np.asarray(params.long_diff_template, dtype=dtype)[:, None]
+    # jax.scipy.stats.norm.pdf = exp(logpdf), logpdf = (log(2 pi scale^2) + (x - loc)^2 / scale^2) / -2
+    # (jax/_src/scipy/stats/norm.py), evaluated operation by operation in the working precision
+    s2 = (sig * sig).astype(dtype)
+    g = np.exp(((np.log((dt(2 * math.pi) * s2).astype(dtype)).astype(dtype) + ((x[None, :] * x[None, :]).astype(dtype) / s2).astype(dtype)) / dt(-2)).astype(dtype))
+    g = g.astype(dtype)
+    return (g / g.sum(axis=1, keepdims=True)).astype(dtype)
 
 
-def build_response_template(response, params, n_templates=None):
+def build_response_template(response, params, n_templates=None, dtype=np.float32):
     """Template bank of load_lut (consts_jax.py:427-447): row t = response (*) Gaussian_t
     with numpy 'same' convolution along time, row 0 overwritten by the raw response.
     ``n_templates`` truncates the bank (tests use < 100 rows to bound memory; valid as long
     as every used template index + 1 stays below it)."""
     from scipy.ndimage import convolve1d
 
-    response = np.asarray(response, dtype=np.float32)
-    g = gaussian_taps(params)
+    response = np.asarray(response, dtype=dtype)
+    g = gaussian_taps(params, dtype)
     nt = g.shape[0] if n_templates is None else int(n_templates)
-    bank = np.empty((nt,) + response.shape, dtype=np.float32)
+    bank = np.empty((nt,) + response.shape, dtype=dtype)
     for t in range(nt):
         # symmetric odd-length kernel + zero padding == np.convolve(x, k, mode='same')
         bank[t] = convolve1d(response, g[t], axis=-1, mode="constant", cval=0.0)

@@ -9,9 +9,14 @@ constants rounded to f32 once, dropped negative scatter ids, garbage tick 0).  P
 finite-difference gradient checks).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
-import this module.  PARITY STATUS: "parity unpinned" for waveform arithmetic (JAX cannot be
-run here and the response LUT blob is missing); pinned against the reference goldens for
-geometry / id packing / coordinate and ADC maps (tests/test_oracle_golden.py).
+import this module.  PARITY STATUS: pinned in two ways.  (1) Against the reference-held goldens
+(output/jax_ref, produced by real JAX) for geometry / id packing / coordinate and ADC maps
+(tests/test_oracle_golden.py).  (2) Against outputs of the reference's own source, imported unmodified and
+executed on a numpy stand-in for jax (tests/golden/jaxshim, fixtures tests/golden/refshim_*.npz,
+tests/test_refshim_golden.py): drift-stage arrays, unique pixels, waveforms, self-trigger ticks, hit lists,
+MC-current mode, probabilistic front end, losses and double-precision finite-difference gradients agree to
+~1e-9 in double and to float32 rounding in single precision.  NOT pinned: XLA's own float32 code
+generation beyond the three facts the JAX goldens expose (real JAX is not installable here).
 """
 import math
 
@@ -57,6 +62,11 @@ def _erf(x, dt):
 
 def _erfc(x, dt):
     return sps.erfc(np.asarray(x, dtype=np.float64)).astype(dt)
+
+
+def _sqrt2(dt):
+    """jnp.sqrt(2): a weak-typed scalar, i.e. rounded to the working precision."""
+    return dt(np.sqrt(dt(2.0)))
 
 
 def _col(fields, name):
@@ -318,7 +328,7 @@ def diffusion_weights_1d(bins, x0, sigma, dt):
     e = np.ones_like(edges)
     e[:, 0] = -1
     with np.errstate(divide="ignore", invalid="ignore"):
-        e[:, 1:-1] = _erf(edges[:, 1:-1] / (dt(np.float32(math.sqrt(2.0))) * sigma[:, None]), dt)
+        e[:, 1:-1] = _erf(edges[:, 1:-1] / (_sqrt2(dt) * sigma[:, None]), dt)
     return (dt(0.5) * (e[:, 1:] - e[:, :-1])).astype(dt)
 
 
@@ -424,7 +434,7 @@ def simulate_signals(params, unique_pixels, d, pix_renumbering_neigh, response_t
     T2 = int(params.nb_tran_diff_bins) ** 2
     P2 = (2 * int(params.number_pix_neighbors) + 1) ** 2
     ts = dt(params.t_sampling)
-    tv = np.asarray(params.long_diff_template, dtype=np.float32).astype(dt)
+    tv = np.asarray(params.long_diff_template, dtype=dt)   # float32 values in the default mode (consts_jax.py:259)
     wfs = np.zeros(Npix * Nticks, dtype=acc_dtype)
     Nseg = d["nelectrons_neigh"].shape[0]
     ar = np.arange(L)
@@ -637,7 +647,7 @@ def emg_pdf(x, mu, sigma, lambd, dt):
     """detsim_jax.py:440-458."""
     coeff = lambd / dt(2)
     expo = coeff * (dt(2) * mu + lambd * sigma ** 2 - dt(2) * x)
-    er = _erfc((mu + lambd * sigma ** 2 - x) / (dt(np.float32(math.sqrt(2.0))) * sigma), dt)
+    er = _erfc((mu + lambd * sigma ** 2 - x) / (_sqrt2(dt) * sigma), dt)
     return coeff * np.exp(expo) * er
 
 
@@ -646,7 +656,7 @@ def integrated_expon_diff(x, loc, scale, diff, dtk, dt):
     lambd = dt(1) / scale
     a = x - dt(dtk / 2)
     b = x + dt(dtk / 2)
-    s2 = dt(np.float32(math.sqrt(2.0)))
+    s2 = _sqrt2(dt)
     up = dt(0.5) * _erf((b - loc) / (s2 * diff), dt) - emg_pdf(b, loc, diff, lambd, dt) / lambd
     lo = dt(0.5) * _erf((a - loc) / (s2 * diff), dt) - emg_pdf(a, loc, diff, lambd, dt) / lambd
     tv = up - lo
