@@ -336,6 +336,27 @@ int larnd_signals_stream_backward(const int32_t* unique_pixels_d, int32_t npix, 
                                   float* g_nelectrons_d, float* g_t0_after_diff_d, float* g_long_diff_d,
                                   float* g_nelectrons_neigh_d, float* g_t0_neigh_d, int32_t* status_d, void* stream);
 
+/* Legacy entry points the reference keeps beside simulate_signals (no caller in the reference itself; signatures kept):
+ *   simulate_signals_new   sim_jax.py:456-617      main entries (n_main = Nseg * 25) + neighbour ENTRIES
+ *   accumulate_signals     detsim_jax.py:157-205   n_main = 0, entries = (currents_idx, charge, pixID, cathode_ticks)
+ * Truncating tick (t0 / t_sampling).astype(int), no sub-tick split, bare searchsorted for the main pixels, boundary
+ * correction of the main entries from the running sum of template 0 (the reference's response_cum.take without template
+ * offset), .at[] index semantics (negative flat index wraps once, out of range dropped).  The per-entry arrays are the
+ * reference's own: charge / pixID / cathode_ticks per (segment, neighbour pixel).  wfs_d (npix, n_ticks) is ACCUMULATED
+ * INTO.  status_d[0]: bits 0-2 as larnd_signals_stream_forward, bit 3 a tick outside [0, Nt) (clamped for the correction). */
+int larnd_signals_legacy_forward(const int32_t* unique_pixels_d, int32_t npix, const int32_t* pixels_d,
+                                 const float* t0_after_diff_d, const float* nelectrons_d, const float* long_diff_d,
+                                 const int32_t* currents_idx_d, int64_t n_main, const float* charge_entries_d,
+                                 const int32_t* pix_id_entries_d, const int32_t* cathode_ticks_entries_d,
+                                 const int32_t* currents_idx_entries_d, int64_t n_entries, const larnd_params_t* params,
+                                 const larnd_lut_t* lut, float* wfs_d, int32_t* status_d, void* stream);
+
+/* current_lut (detsim_jax.py:642-660): t0 = response_full_drift_t - electrons[:, t]; currents_idx = clip(int(|x - px| /
+ * response_bin_size), 0, nx-1), likewise y.  electrons (n, ncols), pixels_coord (n, 2) -> t0 (n), currents_idx (n, 2). */
+int larnd_current_lut(const float* electrons_d, int64_t n, int32_t ncols, int32_t col_x, int32_t col_y, int32_t col_t,
+                      const float* pixels_coord_d, float response_full_drift_t, float response_bin_size, int32_t nx,
+                      int32_t ny, float* t0_d, int32_t* currents_idx_d, void* stream);
+
 /* current_mc (detsim_jax.py:619-639): electrons (n, ncols) + pixel centres (n, 2) -> t0_tick (n) int32, signals (n, 51).
  * The backward call returns the VJP w.r.t. the electrons' x, y, z, long_diff, n_electrons columns (other columns of
  * g_electrons_d are zeroed) and w.r.t. the pixel centres. */

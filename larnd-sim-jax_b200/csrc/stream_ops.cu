@@ -267,6 +267,103 @@ k_signals_stream_bwd(const __grid_constant__ StreamArgs A, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------- legacy entry points
+// simulate_signals_new (sim_jax.py:456-617) and accumulate_signals (detsim_jax.py:157-205): the pre-"sub-tick split" form
+// the reference keeps beside simulate_signals.  Differences, reproduced as written:
+//   * the tick is (t0 / t_sampling).astype(int): truncation, no clip, no fractional split — one placement per sample;
+//   * main pixels are renumbered with a bare searchsorted (no equality mask): a pixel id absent from unique_pixels lands on
+//     the row of the next larger id, id > every entry -> row Npix -> flat index out of range -> dropped by .at[].add;
+//   * the boundary correction of the MAIN entries reads response_cum.take(base + ...) WITHOUT the template offset, i.e.
+//     the running sum of template 0 (sim_jax.py:593-596), also when the values were blended from templates idx-1..idx+1;
+//   * flat indices go through .at[]: negative ones wrap once by Npix*Nticks, the rest out of range is dropped.
+// One warp per entry; wfs is accumulated INTO (accumulate_signals adds onto its argument).
+struct LegacyArgs {
+  const int32_t* unique_pixels; int npix;
+  const int32_t* pixels; const float* t0; const float* q; const float* ld; const int32_t* cidx; int64_t n_main;
+  const float* qe; const int32_t* rowe; const int32_t* cte; const int32_t* cidxe; int64_t n_entries;
+  larnd_lut lut;
+  float* wfs;
+  int32_t* status;   // bit0 / bit1 / bit2 as above, bit3: tick outside [0, Nt) (the reference would read a neighbouring LUT row)
+};
+
+__device__ __forceinline__ void legacy_add(float* wfs, int64_t size, int64_t flat, float v) {
+  if (flat < 0) flat += size;
+  if (flat >= 0 && flat < size) atomicAdd(wfs + flat, v);
+}
+
+__global__ void __launch_bounds__(SG_WARPS * 32)
+k_signals_legacy(const __grid_constant__ LegacyArgs A, const __grid_constant__ larnd_params_t p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * SG_WARPS + (threadIdx.x >> 5);
+  if (e >= A.n_main + A.n_entries) return;
+  const larnd_lut& lut = A.lut;
+  const int Nt = lut.nt, L = lut.L, nticks = p.n_ticks;
+  const int64_t size = (int64_t)A.npix * nticks;
+  const bool main = e < A.n_main;
+  int row, ct;
+  float q, a = 0.f, b = 1.f, c = 0.f;
+  const float *Ri, *Ra, *Rc, *C0;
+  if (main) {
+    const int pix = __ldg(A.pixels + e);
+    int lo = 0, hi = A.npix;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(A.unique_pixels + mid) < pix) lo = mid + 1; else hi = mid;
+    }
+    row = lo;                                                    // no equality mask (sim_jax.py:533)
+    q = __ldg(A.q + e);
+    const float ld = __ldg(A.ld + e);
+    ct = (int)__fdiv_rn(__ldg(A.t0 + e), p.t_sampling);         // astype(int): truncation
+    const int ci = __ldg(A.cidx + 2 * e), cj = __ldg(A.cidx + 2 * e + 1);
+    if (ci < 0 || cj < 0 || ci >= 5 || cj >= 5) { if (lane == 0) atomicOr(A.status, 1); return; }
+    int l2 = 0, h2 = p.n_templates;
+    while (l2 < h2) {
+      const int mid = (l2 + h2) >> 1;
+      if (p.long_diff_template[mid] < ld) l2 = mid + 1; else h2 = mid;
+    }
+    const int idx = max(1, min(l2, p.n_templates - 2));
+    if (idx + 1 >= lut.ntpl) { if (lane == 0) atomicOr(A.status, 4); return; }
+    const float x0 = p.long_diff_template[idx - 1], x1 = p.long_diff_template[idx], x2 = p.long_diff_template[idx + 1];
+    a = (ld - x1) * (ld - x2) / ((x0 - x1) * (x0 - x2));
+    b = (ld - x0) * (ld - x2) / ((x1 - x0) * (x1 - x2));
+    c = (ld - x0) * (ld - x1) / ((x2 - x0) * (x2 - x1));
+    const int64_t r = (int64_t)idx * 25 + ci * 5 + cj;
+    Ri = lut.rm + r * lut.Lp + 2;
+    Ra = lut.rm + (r - 25) * lut.Lp + 2;
+    Rc = lut.rm + (r + 25) * lut.Lp + 2;
+    C0 = lut.c0 + ((int64_t)ci * lut.ny + cj) * Nt;              // template 0 (no template offset in the reference)
+  } else {
+    const int64_t j = e - A.n_main;
+    row = __ldg(A.rowe + j);
+    q = __ldg(A.qe + j);
+    ct = __ldg(A.cte + j);
+    const int ci = __ldg(A.cidxe + 2 * j), cj = __ldg(A.cidxe + 2 * j + 1);
+    if (ci < 0 || cj < 0 || ci >= lut.nx || cj >= lut.ny) { if (lane == 0) atomicOr(A.status, 2); return; }
+    const int64_t r = (int64_t)ci * lut.ny + cj;
+    Ri = Ra = Rc = lut.r0 + r * lut.Lp + 2;
+    C0 = lut.c0 + r * Nt;
+  }
+  const int st0 = Nt - L - ct;
+  const int64_t base = (int64_t)row * nticks;
+  float garbage = 0.f;   // column 0 of this row collects every out-of-window sample
+  for (int k = lane; k < L; k += 32) {
+    // three separate .at[].add in the reference (b, a, c order); one rounded sum here
+    const float v = main ? (__ldg(Ri + k) * q * b + __ldg(Ra + k) * q * a + __ldg(Rc + k) * q * c) : __ldg(Ri + k) * q;
+    const int tk = tick_rule(st0 + k, nticks);
+    if (tk == 0) garbage += v; else legacy_add(A.wfs, size, base + tk, v);
+  }
+  if (lane == 0) {
+    int ctc = ct;
+    if (ct < 0 || ct >= Nt) { atomicOr(A.status, 8); ctc = max(0, min(ct, Nt - 1)); }
+    const float d = (__ldg(C0 + Nt - L) - __ldg(C0 + ctc)) * q;
+    const int s0 = start_rule(st0, nticks);
+    if (s0 == 0) garbage += d; else legacy_add(A.wfs, size, base + s0, d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) garbage += __shfl_xor_sync(0xffffffffu, garbage, o);
+  if (lane == 0 && garbage != 0.f) legacy_add(A.wfs, size, base, garbage);
+}
+
 int stream_check(const larnd_params_t* p, const larnd_lut* lut, int64_t n_main, int64_t n_seg) {
   if (!p || !lut) { larnd_set_error("larnd_signals_stream: null argument"); return LARND_E_ARG; }
   if (n_main < 0 || n_seg < 0) { larnd_set_error("larnd_signals_stream: negative size"); return LARND_E_ARG; }
@@ -359,5 +456,58 @@ extern "C" int larnd_signals_stream_backward(const int32_t* unique_pixels_d, int
   if (entries == 0) return LARND_OK;
   k_signals_stream_bwd<<<(unsigned)((entries + SG_WARPS - 1) / SG_WARPS), SG_WARPS * 32, 0, st>>>(A, *p);
   LARND_LAUNCH_CHECK("k_signals_stream_bwd");
+  return LARND_OK;
+}
+
+extern "C" int larnd_signals_legacy_forward(const int32_t* unique_pixels_d, int32_t npix, const int32_t* pixels_d,
+                                            const float* t0_after_diff_d, const float* nelectrons_d, const float* long_diff_d,
+                                            const int32_t* currents_idx_d, int64_t n_main, const float* charge_entries_d,
+                                            const int32_t* pix_id_entries_d, const int32_t* cathode_ticks_entries_d,
+                                            const int32_t* currents_idx_entries_d, int64_t n_entries, const larnd_params_t* p,
+                                            const larnd_lut_t* lut, float* wfs_d, int32_t* status_d, void* stream) {
+  int rc = stream_check(p, lut, n_main, n_entries);
+  if (rc) return rc;
+  if (npix < 1 || !wfs_d || !status_d || (n_main > 0 && (!unique_pixels_d || !pixels_d || !t0_after_diff_d || !nelectrons_d || !long_diff_d || !currents_idx_d)) ||
+      (n_entries > 0 && (!charge_entries_d || !pix_id_entries_d || !cathode_ticks_entries_d || !currents_idx_entries_d))) {
+    larnd_set_error("larnd_signals_legacy_forward: bad argument");
+    return LARND_E_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  LARND_CUDA(cudaMemsetAsync(status_d, 0, sizeof(int32_t), st));
+  LegacyArgs A{unique_pixels_d, npix, pixels_d, t0_after_diff_d, nelectrons_d, long_diff_d, currents_idx_d, n_main,
+               charge_entries_d, pix_id_entries_d, cathode_ticks_entries_d, currents_idx_entries_d, n_entries, *lut, wfs_d, status_d};
+  const int64_t entries = n_main + n_entries;
+  if (entries == 0) return LARND_OK;
+  k_signals_legacy<<<(unsigned)((entries + SG_WARPS - 1) / SG_WARPS), SG_WARPS * 32, 0, st>>>(A, *p);
+  LARND_LAUNCH_CHECK("k_signals_legacy");
+  return LARND_OK;
+}
+
+// current_lut (detsim_jax.py:642-660): t0 = response_full_drift_t - t, response bin of |electron - pixel centre|.
+namespace {
+__global__ void k_current_lut(const float* __restrict__ el, int64_t n, int ncols, int cx, int cy, int ctm, const float* __restrict__ pc,
+                              float full_drift_t, float bin_size, int nx, int ny, float* __restrict__ t0, int32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = el + i * ncols;
+  const float xd = fabsf(__fsub_rn(r[cx], pc[2 * i])), yd = fabsf(__fsub_rn(r[cy], pc[2 * i + 1]));
+  t0[i] = __fsub_rn(full_drift_t, r[ctm]);
+  idx[2 * i] = max(0, min((int)__fdiv_rn(xd, bin_size), nx - 1));
+  idx[2 * i + 1] = max(0, min((int)__fdiv_rn(yd, bin_size), ny - 1));
+}
+}  // namespace
+
+extern "C" int larnd_current_lut(const float* electrons_d, int64_t n, int32_t ncols, int32_t col_x, int32_t col_y, int32_t col_t,
+                                 const float* pixels_coord_d, float response_full_drift_t, float response_bin_size, int32_t nx,
+                                 int32_t ny, float* t0_d, int32_t* currents_idx_d, void* stream) {
+  if (n < 0 || ncols < 1 || col_x < 0 || col_y < 0 || col_t < 0 || col_x >= ncols || col_y >= ncols || col_t >= ncols || nx < 1 || ny < 1 ||
+      !(response_bin_size > 0) || (n > 0 && (!electrons_d || !pixels_coord_d || !t0_d || !currents_idx_d))) {
+    larnd_set_error("larnd_current_lut: bad argument");
+    return LARND_E_ARG;
+  }
+  if (n == 0) return LARND_OK;
+  k_current_lut<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(electrons_d, n, ncols, col_x, col_y, col_t, pixels_coord_d,
+                                                                             response_full_drift_t, response_bin_size, nx, ny, t0_d, currents_idx_d);
+  LARND_LAUNCH_CHECK("k_current_lut");
   return LARND_OK;
 }

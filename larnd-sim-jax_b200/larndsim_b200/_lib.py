@@ -208,6 +208,10 @@ def _declare(lib):
     lib.larnd_signals_stream_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, vp, vp]
     lib.larnd_signals_stream_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, i64,
                                                   vp, vp, vp, vp, vp, vp, vp]
+    lib.larnd_signals_legacy_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, vp, vp]
+    lib.larnd_signals_legacy_forward.restype = C.c_int
+    lib.larnd_current_lut.argtypes = [vp, i64, i32, i32, i32, i32, vp, C.c_float, C.c_float, i32, i32, vp, vp, vp]
+    lib.larnd_current_lut.restype = C.c_int
     PCU = C.POINTER(CurrentColumns)
     lib.larnd_current_mc.argtypes = [vp, i64, PCU, vp, PP, vp, vp, vp]
     lib.larnd_current_mc_backward.argtypes = [vp, i64, PCU, vp, PP, vp, vp, vp, vp]

@@ -246,4 +246,4 @@ def apply_tran_diff(params, electrons, fields):
 
 
 # stage-by-stage MC-current operators with the reference's argument lists (detsim_jax.py:619-639, 209-228)
-from .stream_ops import accumulate_signals_parametrized, current_mc  # noqa: E402,F401
+from .stream_ops import accumulate_signals, accumulate_signals_parametrized, current_lut, current_mc  # noqa: E402,F401

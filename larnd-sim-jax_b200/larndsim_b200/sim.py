@@ -460,7 +460,7 @@ def record_fields(st):
 
 
 # stage-by-stage operators with the reference's argument lists (sim_jax.py:142-286, 120-139, 289-335)
-from .stream_ops import simulate_drift, simulate_signals, simulate_signals_parametrized  # noqa: E402,F401
+from .stream_ops import simulate_drift, simulate_signals, simulate_signals_new, simulate_signals_parametrized  # noqa: E402,F401
 
 
 # ------------------------------------------------------------------------------------------ front end

@@ -123,6 +123,113 @@ def simulate_signals(params, unique_pixels, pixels, t0_after_diff, response_temp
     return _SimulateSignals.apply(t0_after_diff, nelectrons, long_diff, nelectrons_neigh, t0_neigh, ints, params, response_template)
 
 
+# ------------------------------------------------------------------------------------------ legacy entry points
+def _legacy_status(st, who):
+    if st & 7:
+        raise ValueError("%s: response index outside the LUT (%s)" % (who, "main bins must be < 5" if st & 1 else
+                         "template row beyond the truncated response_template bank" if st & 4 else
+                         "neighbour bin outside the response"))
+    if st & 8:
+        raise ValueError("%s: a drift tick lies outside the response time axis [0, Nt) — the reference would read a neighbouring "
+                         "LUT row there" % who)
+
+
+def simulate_signals_new(params, unique_pixels, pixels, t0_after_diff, response_template, nelectrons, long_diff, currents_idx,
+                         nelectrons_neigh, pix_renumbering_neigh, t0_neigh, currents_idx_neigh):
+    """The reference's earlier form of ``simulate_signals`` (sim_jax.py:456-617), kept there beside the current one and kept
+    here with the same argument list: truncating tick, no sub-tick split, bare ``searchsorted`` for the main pixels,
+    boundary correction of the main entries from the running sum of template 0.  Returns (Npix, Nticks) waveforms including
+    the garbage column 0.  Forward only (no caller in the reference; gradients flow through ``simulate_signals``)."""
+    sim = _sim()
+    sim._check_cuda(unique_pixels, "unique_pixels")
+    sim._check_cuda(response_template, "response_template")
+    dev = unique_pixels.device
+    f32 = lambda a: a.detach().to(dev, torch.float32).contiguous().reshape(-1)
+    i32 = lambda a: a.detach().to(dev, torch.int32).contiguous()
+    lut = sim.get_lut(response_template, params.signal_length, params.nb_sampling_bins_per_pixel, params.number_pix_neighbors)
+    pod = sim.make_pod(params, lut.shape)
+    up, pix, ci = i32(unique_pixels), i32(pixels).reshape(-1), i32(currents_idx).reshape(-1, 2)
+    t0, q, ld = f32(t0_after_diff), f32(nelectrons), f32(long_diff)
+    n_main = pix.numel()
+    if not (t0.numel() == q.numel() == ld.numel() == ci.shape[0] == n_main):
+        raise ValueError("simulate_signals_new: main-pixel streams have different lengths")
+    rn, cin = i32(pix_renumbering_neigh).reshape(-1), i32(currents_idx_neigh).reshape(-1, 2)
+    npix_n = (2 * pod.number_pix_neighbors + 1) ** 2
+    n_ent = rn.numel()
+    # jnp.take(nelectrons_neigh, arange(n) // npix, mode='fill', fill_value=0); cathode tick = (t0 / t_sampling).astype(int)
+    elec = torch.arange(n_ent, device=dev) // npix_n
+    qn_seg, t0n_seg = f32(nelectrons_neigh), f32(t0_neigh)
+    ok = elec < qn_seg.numel()
+    safe = elec.clamp(max=max(qn_seg.numel() - 1, 0))
+    qe = torch.where(ok, qn_seg[safe], torch.zeros((), device=dev)) if n_ent else qn_seg[:0]
+    t0e = torch.where(ok, t0n_seg[safe], torch.zeros((), device=dev)) if n_ent else t0n_seg[:0]
+    cte = torch.div(t0e, torch.tensor(params.t_sampling, dtype=torch.float32, device=dev)).to(torch.int32)
+    npix = up.numel()
+    wfs = torch.zeros((npix, pod.n_ticks), dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.get_lib().larnd_signals_legacy_forward(
+            sim._ptr(up), npix, sim._ptr(pix), sim._ptr(t0), sim._ptr(q), sim._ptr(ld), sim._ptr(ci), n_main, sim._ptr(qe.contiguous()),
+            sim._ptr(rn), sim._ptr(cte.contiguous()), sim._ptr(cin), n_ent, C.byref(pod), lut.handle, sim._ptr(wfs), sim._ptr(status),
+            sim._stream()))
+    _legacy_status(int(status.item()), "simulate_signals_new")
+    return wfs
+
+
+def accumulate_signals(wfs, currents_idx, charge, response, response_cum, pixID, cathode_ticks, signal_length):
+    """``wfs`` + the template-0 response of every (currents_idx, charge, pixID, cathode_ticks) entry, with the boundary
+    correction from ``response_cum`` — the reference's ``accumulate_signals`` (detsim_jax.py:157-205), same argument list.
+    ``response`` is the (Nx, Ny, Nt) template-0 response; ``response_cum`` is accepted for signature compatibility (its
+    template-0 block is the running sum the kernel's tables hold; it is recomputed from ``response``)."""
+    sim = _sim()
+    sim._check_cuda(wfs, "wfs")
+    sim._check_cuda(response, "response")
+    if response.dim() != 3:
+        raise ValueError("accumulate_signals: response must be (Nx, Ny, Nt)")
+    dev = wfs.device
+    bank = response.detach().to(torch.float32)[None].expand(3, -1, -1, -1).contiguous()   # the table builder wants >= 3 templates
+    with torch.cuda.device(dev):
+        lut = sim._LutHandle(bank, int(signal_length), 10, 0)
+    pod = _lib.ParamsPOD()
+    pod.n_ticks, pod.signal_length, pod.n_templates, pod.t_sampling = int(wfs.shape[1]), int(signal_length), 3, 1.0
+    i32 = lambda a: a.detach().to(dev, torch.int32).contiguous()
+    ci, pid, ct = i32(currents_idx).reshape(-1, 2), i32(pixID).reshape(-1), i32(cathode_ticks).reshape(-1)
+    q = charge.detach().to(dev, torch.float32).contiguous().reshape(-1)
+    n = pid.numel()
+    if not (ci.shape[0] == ct.numel() == q.numel() == n):
+        raise ValueError("accumulate_signals: entry arrays have different lengths")
+    out = wfs.detach().to(torch.float32).clone().contiguous()
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    null = C.c_void_p(0)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.get_lib().larnd_signals_legacy_forward(
+            null, int(out.shape[0]), null, null, null, null, null, 0, sim._ptr(q), sim._ptr(pid), sim._ptr(ct), sim._ptr(ci), n,
+            C.byref(pod), lut.handle, sim._ptr(out), sim._ptr(status), sim._stream()))
+    _legacy_status(int(status.item()), "accumulate_signals")
+    return out
+
+
+def current_lut(params, response, electrons, pixels_coord, fields):
+    """(t0, currents_idx): drift time left on the response axis and the response bin of |electron - pixel centre| —
+    the reference's ``current_lut`` (detsim_jax.py:642-660)."""
+    sim = _sim()
+    sim._check_cuda(electrons, "electrons")
+    f = tuple(fields)
+    el = electrons.detach().to(torch.float32).contiguous()
+    pc = pixels_coord.detach().to(el.device, torch.float32).contiguous().reshape(-1, 2)
+    n = el.shape[0]
+    if pc.shape[0] != n:
+        raise ValueError("current_lut: one pixel centre per electron expected")
+    t0 = torch.empty(n, dtype=torch.float32, device=el.device)
+    idx = torch.empty((n, 2), dtype=torch.int32, device=el.device)
+    with torch.cuda.device(el.device):
+        _lib.check(_lib.get_lib().larnd_current_lut(sim._ptr(el), n, el.shape[1], f.index("x"), f.index("y"), f.index("t"), sim._ptr(pc),
+                                                    float(params.response_full_drift_t), float(params.response_bin_size),
+                                                    int(response.shape[0]), int(response.shape[1]), sim._ptr(t0), sim._ptr(idx),
+                                                    sim._stream()))
+    return t0, idx
+
+
 # ------------------------------------------------------------------------------------------ MC-current stages
 def _current_columns(fields):
     f = tuple(fields)

@@ -518,6 +518,91 @@ def simulate_signals(params, unique_pixels, d, pix_renumbering_neigh, response_t
     return wfs.reshape(Npix, Nticks).astype(dt)
 
 
+# --------------------------------------------------------------------------- legacy entry points (kept by the reference)
+def _at_add(wfs_flat, idx, val):
+    """``wfs.at[idx].add(val)``: negative indices wrap once, out-of-range ones are dropped; exactly rounded sums."""
+    idx = np.asarray(idx, dtype=np.int64).ravel()
+    val = np.asarray(val).ravel()
+    size = wfs_flat.shape[0]
+    idx = np.where(idx < 0, idx + size, idx)
+    keep = (idx >= 0) & (idx < size)
+    wfs_flat += np.bincount(idx[keep], weights=val[keep].astype(np.float64), minlength=size)
+
+
+def accumulate_signals(wfs, currents_idx, charge, response, response_cum, pixID, cathode_ticks, signal_length, dt=np.float32):
+    """detsim_jax.py:157-205: template-0 response rows scattered at truncated ticks + boundary correction read from the
+    FLATTENED ``response_cum`` without a template offset (i.e. its template-0 block)."""
+    Npix, Nticks = wfs.shape
+    R = np.asarray(response, dtype=dt)
+    Nx, Ny, Nt = R.shape
+    L = int(signal_length)
+    ct = np.asarray(cathode_ticks, dtype=np.int64)
+    pid = np.asarray(pixID, dtype=np.int64)
+    q = np.asarray(charge, dtype=dt)
+    ci = np.asarray(currents_idx, dtype=np.int64).reshape(-1, 2)
+    st = Nt - L - ct
+    tt = st[:, None] + np.arange(L)
+    tt = np.where((tt <= 0) | (tt >= Nticks - 1), 0, tt + 1)
+    out = np.asarray(wfs, dtype=np.float64).ravel().copy()
+    vals = R[ci[:, 0, None], ci[:, 1, None], np.arange(Nt - L, Nt)[None, :]] * q[:, None]
+    _at_add(out, pid[:, None] * Nticks + tt, vals)
+    cum_flat = np.asarray(response_cum, dtype=dt).reshape(-1)
+    base = (ci[:, 0] * Ny + ci[:, 1]) * Nt
+    diff = (cum_flat[base + Nt - L] - cum_flat[base + ct]) * q
+    _at_add(out, np.where((st <= 0) | (st >= Nticks - 1), 0, st) + pid * Nticks, diff)
+    return out.reshape(Npix, Nticks).astype(dt)
+
+
+def simulate_signals_new(params, unique_pixels, d, pix_renumbering_neigh, response_template, dt=np.float32):
+    """sim_jax.py:456-617 on the arrays of simulate_drift_new (``d``): truncating tick, no sub-tick split, bare
+    searchsorted for the main pixels, main boundary correction from the template-0 running sum."""
+    R = np.asarray(response_template, dtype=dt)
+    C = response_cumsum(R)
+    Npix = unique_pixels.shape[0]
+    Nticks = int(params.time_interval[1] / params.t_sampling) + 1
+    Ntpl, Nx, Ny, Nt = R.shape
+    L = int(params.signal_length)
+    ts = dt(params.t_sampling)
+    tv = np.asarray(params.long_diff_template, dtype=dt)
+    ren = np.searchsorted(unique_pixels, d["pixels"].reshape(-1)).astype(np.int64)
+    ct = (d["t0_after_diff"] / ts).astype(np.int32).astype(np.int64)
+    st = Nt - L - ct
+    tt = st[:, None] + np.arange(L)
+    tt = np.where((tt <= 0) | (tt >= Nticks - 1), 0, tt + 1)
+    ld, q = d["long_diff"], d["nelectrons"]
+    idx = np.clip(np.searchsorted(tv, ld), 1, tv.shape[0] - 2)
+    x0, x1, x2 = tv[idx - 1], tv[idx], tv[idx + 1]
+    a = (ld - x1) * (ld - x2) / ((x0 - x1) * (x0 - x2))
+    b = (ld - x0) * (ld - x2) / ((x1 - x0) * (x1 - x2))
+    c = (ld - x0) * (ld - x1) / ((x2 - x0) * (x2 - x1))
+    ci = d["currents_idx"].astype(np.int64)
+    lt = np.arange(Nt - L, Nt)[None, :]
+    out = np.zeros(Npix * Nticks, dtype=np.float64)
+    flat = ren[:, None] * Nticks + tt
+    for coef, off in ((b, 0), (a, -1), (c, 1)):
+        _at_add(out, flat, R[(idx + off)[:, None], ci[:, 0, None], ci[:, 1, None], lt] * q[:, None] * coef[:, None])
+    cum_flat = C.reshape(-1)
+    base = (ci[:, 0] * Ny + ci[:, 1]) * Nt
+    diff = (cum_flat[base + Nt - L] - cum_flat[base + ct]) * q
+    _at_add(out, np.where((st <= 0) | (st >= Nticks - 1), 0, st) + ren * Nticks, diff)
+    wfs = out.reshape(Npix, Nticks).astype(dt)
+    P2 = (2 * int(params.number_pix_neighbors) + 1) ** 2
+    qn = np.repeat(d["nelectrons_neigh"], P2)
+    ctn = (np.repeat(d["t0_neigh"], P2) / ts).astype(np.int32)
+    return accumulate_signals(wfs, d["currents_idx_neigh"], qn, R[0], C, pix_renumbering_neigh, ctn, L, dt)
+
+
+def current_lut(params, response, electrons, pixels_coord, fields, dt=np.float32):
+    """detsim_jax.py:642-660."""
+    e = np.asarray(electrons, dtype=dt)
+    xd = np.abs(e[:, _col(fields, "x")] - pixels_coord[..., 0])
+    yd = np.abs(e[:, _col(fields, "y")] - pixels_coord[..., 1])
+    t0 = dt(params.response_full_drift_t) - e[:, _col(fields, "t")]
+    i = np.clip((xd / dt(params.response_bin_size)).astype(np.int32), 0, response.shape[0] - 1)
+    j = np.clip((yd / dt(params.response_bin_size)).astype(np.int32), 0, response.shape[1] - 1)
+    return t0, np.stack([i, j], axis=-1)
+
+
 def simulate_wfs(params, response_template, tracks, fields, dt=np.float32, pad_to=None, history=None,
                  response_cum=None, traced_efield=False, return_aux=False):
     """sim_jax.py:689-736: (wfs[:, 1:], unique_pixels)."""

@@ -199,6 +199,34 @@ def test_oracle_probabilistic_front_end_equals_reference_source(prec):
         assert np.allclose(np.asarray(out[k], dtype=np.float64), z["probabilistic/%d" % k], rtol=2e-6, atol=1e-6), k
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_oracle_legacy_entry_points_equal_reference_source(prec):
+    """simulate_signals_new (sim_jax.py:456-617), accumulate_signals (detsim_jax.py:157-205), current_lut (:642-660)."""
+    z = _load("refshim_lut_%s.npz" % prec)
+    dt = np.float64 if prec == "f64" else np.float32
+    for name in ("n2_L100_birks", "n1_L150_box_shift", "n0_L100_ellipsoid"):
+        tr, op, bshape = _case(name)
+        bank, op = _bank(bshape, op, dt)
+        d = lo.simulate_drift_new(op, tr.astype(dt), cm.FIELDS, dt=dt)
+        upix = z[name + "/unique_pixels"]
+        _, ren = lo.unique_and_renumber(d, pad_to=len(upix))
+        w = lo.simulate_signals_new(op, upix, d, ren, bank, dt=dt)
+        ref = z[name + "/legacy_wfs"]
+        assert w.shape == ref.shape and np.abs(w - ref).max() <= (1e-9 if prec == "f64" else 1e-5) * np.abs(ref).max()
+        if name == "n2_L100_birks":
+            P2 = 25
+            ct = (np.repeat(d["t0_neigh"], P2) / dt(op.t_sampling)).astype(np.int32)
+            acc = lo.accumulate_signals(np.zeros_like(ref), d["currents_idx_neigh"], np.repeat(d["nelectrons_neigh"], P2), bank[0],
+                                        lo.response_cumsum(bank), ren, ct, 100, dt)
+            ra = z[name + "/accumulate_signals"]
+            assert np.abs(acc - ra).max() <= (1e-9 if prec == "f64" else 1e-5) * np.abs(ra).max()
+            px, py, plane, _ = lo.id2pixel(op, d["main_pixels"])
+            t0, cidx = lo.current_lut(op, bank[0], tr.astype(dt), lo.get_pixel_coordinates(op, px, py, plane, dt), cm.FIELDS, dt)
+            ok = d["main_pixels"] >= 0             # padding rows (pixel id -1) sit exactly on a bin edge: 1 ulp decides
+            assert np.array_equal(cidx[ok], z[name + "/current_lut_idx"][ok]) and ok.sum() >= 590
+            assert np.abs(t0 - z[name + "/current_lut_t0"]).max() <= 1e-4
+
+
 def _fd(L, p, names):
     return np.array([(L(p.replace(**{n: getattr(p, n) + GRAD_STEPS[n]})) - L(p.replace(**{n: getattr(p, n) - GRAD_STEPS[n]}))) /
                      (2 * GRAD_STEPS[n]) for n in names])
@@ -465,3 +493,40 @@ def test_cuda_probabilistic_front_end_equals_reference_source(torch_dev):
     assert np.abs(out[0].cpu().numpy() - z32["probabilistic/0"]).max() < 2e-3
     for k in (1, 2, 4):
         assert np.allclose(out[k].cpu().numpy().astype(np.float64), z32["probabilistic/%d" % k], rtol=2e-6, atol=1e-6), k
+
+
+@pytest.mark.gpu
+def test_cuda_legacy_entry_points_equal_reference_source(torch_dev):
+    """sim.simulate_signals_new, detsim.accumulate_signals, detsim.current_lut (kept with the reference's argument lists)."""
+    import torch
+    from larndsim_b200 import detsim, sim
+    z32 = _load("refshim_lut_f32.npz")
+    T = lambda a, **k: torch.as_tensor(np.ascontiguousarray(a), device=torch_dev, **k)
+    for name in ("n2_L100_birks", "n1_L150_box_shift", "n0_L100_ellipsoid"):
+        tr, pp, bshape = _case(name, product=True)
+        bank = T(cm.synthetic_bank(*bshape))
+        d = {k: z32["%s/drift/%s" % (name, k)] for k in DRIFT_KEYS}
+        upix = z32[name + "/unique_pixels"]
+        ren = np.searchsorted(upix, d["pIDs_neigh"].ravel())
+        ren = np.where((ren < len(upix)) & (upix[np.minimum(ren, len(upix) - 1)] == d["pIDs_neigh"].ravel()), ren, 0)
+        w = sim.simulate_signals_new(pp, T(upix), T(d["pixels"]), T(d["t0_after_diff"]), bank, T(d["nelectrons"]), T(d["long_diff"]),
+                                     T(d["currents_idx"]), T(d["nelectrons_neigh"]), T(ren.astype(np.int32)), T(d["t0_neigh"]),
+                                     T(d["currents_idx_neigh"])).cpu().numpy()
+        ref = z32[name + "/legacy_wfs"]
+        scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1.0)
+        real = upix >= 0
+        assert w.shape == ref.shape and (np.abs(w - ref)[real][:, 1:] <= 1e-5 * scale[real] + 1e-3).all()
+        assert (np.abs(w - ref)[:, 0] <= 1e-3 * np.maximum(np.abs(ref[:, 0]), scale[:, 0]) + 1e-3).all()     # garbage column
+        if name == "n2_L100_birks":
+            ts = np.float32(pp.t_sampling)
+            ct = (np.repeat(d["t0_neigh"], 25) / ts).astype(np.int32)
+            acc = detsim.accumulate_signals(torch.zeros(ref.shape, device=torch_dev), T(d["currents_idx_neigh"]),
+                                            T(np.repeat(d["nelectrons_neigh"], 25)), bank[0], None, T(ren.astype(np.int32)), T(ct), 100)
+            ra = z32[name + "/accumulate_signals"]
+            sc = np.maximum(np.abs(ra).max(axis=1, keepdims=True), 1.0)
+            assert (np.abs(acc.cpu().numpy() - ra)[:, 1:] <= 1e-5 * sc + 1e-3).all()
+            px, py, plane, _ = detsim.id2pixel(pp, T(d["main_pixels"]))
+            t0, cidx = detsim.current_lut(pp, bank[0], T(z32[name + "/tracks"]), detsim.get_pixel_coordinates(pp, px, py, plane), cm.FIELDS)
+            ok = d["main_pixels"] >= 0             # padding rows (pixel id -1) sit exactly on a bin edge: 1 ulp decides
+            assert np.array_equal(cidx.cpu().numpy()[ok], z32[name + "/current_lut_idx"][ok])
+            assert np.abs(t0.cpu().numpy() - z32[name + "/current_lut_t0"]).max() <= 1e-4
