@@ -258,6 +258,20 @@ int larnd_chop_count(const float* raw_d, int64_t m, const larnd_chop_columns_t* 
 int larnd_chop_tracks(const float* raw_d, int64_t m, const larnd_chop_columns_t* cols, double precision,
                       const int64_t* offsets_d, float* out_d, int64_t capacity, void* stream);
 
+/* Batch assembly around the chop (TracksDataset.__getitem__ / pad_batch, optimize/dataio.py:340-406, :47-61): the file's
+ * rows stay on the device; a batch is a list of row indices with the batch-local event id of every row.
+ *   larnd_batch_gather: out_d (m, ncols) = raw_d[rows_d[i]] with column event_col replaced by local_event_d[i]
+ *   larnd_pad_rows    : rows [*n_valid_d, capacity) of batch_d become invalid rows — eventID / trackID / pixel_plane -1,
+ *                       every other column 0 (np.pad + _invalidate_rows); n_valid_d is a DEVICE scalar (e.g. the total
+ *                       larnd_chop_count left in offsets_d[m]), so the batch is produced without a host synchronisation */
+typedef struct larnd_pad_columns {
+  int32_t eventID, trackID, pixel_plane;   /* column indices; -1 = column absent */
+} larnd_pad_columns_t;
+int larnd_batch_gather(const float* raw_d, int32_t ncols, const int64_t* rows_d, const int32_t* local_event_d, int64_t m,
+                       int32_t event_col, float* out_d, void* stream);
+int larnd_pad_rows(float* batch_d, int32_t ncols, const int64_t* n_valid_d, int64_t capacity, const larnd_pad_columns_t* cols,
+                   void* stream);
+
 /* jax.random-compatible random numbers (Threefry-2x32; replaces jax.random.key/split/normal at fee_jax.py:186,237-255,271,
  * detsim_jax.py:393, sim_jax.py:359-360,757).  key = the two uint32 words of jax.random.key(seed) = {seed >> 32, seed};
  * partitionable = 1 follows jax_threefry_partitionable (default since JAX 0.5.0), 0 the original counter layout.

@@ -178,3 +178,50 @@ extern "C" int larnd_chop_tracks(const float* raw_d, int64_t m, const larnd_chop
   LARND_LAUNCH_CHECK("k_chop_expand");
   return LARND_OK;
 }
+
+// ---- batch assembly in front of the chop (TracksDataset.__getitem__ / pad_batch, optimize/dataio.py:340-406) -----------
+// The reference builds every batch on the host: gather the rows of the batch's trajectories from the structured file
+// array, convert to float32, remap global event ids to batch-local ones (remap_event_ids_to_local :47-61), chop, pad
+// with invalid rows.  Here the file's rows live on the device once; a batch is a list of row indices + local ids.
+namespace {
+__global__ void k_batch_gather(const float* __restrict__ raw, int ncols, const int64_t* __restrict__ rows, const int32_t* __restrict__ local_event,
+                               int64_t m, int event_col, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m * ncols) return;
+  const int64_t r = i / ncols;
+  const int c = (int)(i - r * ncols);
+  out[i] = (c == event_col) ? (float)local_event[r] : raw[rows[r] * ncols + c];
+}
+
+__global__ void k_pad_rows(float* __restrict__ batch, int ncols, const int64_t* __restrict__ n_valid, int64_t capacity,
+                           const __grid_constant__ larnd_pad_columns_t pc) {
+  const int64_t first = min(max(*n_valid, (int64_t)0), capacity);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + first * ncols;
+  if (i >= capacity * ncols) return;
+  const int c = (int)(i % ncols);
+  batch[i] = (c == pc.eventID || c == pc.trackID || c == pc.pixel_plane) ? -1.0f : 0.0f;
+}
+}  // namespace
+
+extern "C" int larnd_batch_gather(const float* raw_d, int32_t ncols, const int64_t* rows_d, const int32_t* local_event_d, int64_t m,
+                                  int32_t event_col, float* out_d, void* stream) {
+  if (m < 0 || ncols < 1 || event_col < 0 || event_col >= ncols || (m > 0 && (!raw_d || !rows_d || !local_event_d || !out_d))) {
+    larnd_set_error("larnd_batch_gather: bad argument");
+    return LARND_E_ARG;
+  }
+  if (m == 0) return LARND_OK;
+  const int64_t n = m * ncols;
+  k_batch_gather<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw_d, ncols, rows_d, local_event_d, m, event_col, out_d);
+  LARND_LAUNCH_CHECK("k_batch_gather");
+  return LARND_OK;
+}
+
+extern "C" int larnd_pad_rows(float* batch_d, int32_t ncols, const int64_t* n_valid_d, int64_t capacity, const larnd_pad_columns_t* cols,
+                              void* stream) {
+  if (capacity < 0 || ncols < 1 || !cols || !n_valid_d || (capacity > 0 && !batch_d)) { larnd_set_error("larnd_pad_rows: bad argument"); return LARND_E_ARG; }
+  if (capacity == 0) return LARND_OK;
+  const int64_t n = capacity * ncols;   // the grid covers the worst case (n_valid = 0); threads beyond the tail exit
+  k_pad_rows<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(batch_d, ncols, n_valid_d, capacity, *cols);
+  LARND_LAUNCH_CHECK("k_pad_rows");
+  return LARND_OK;
+}

@@ -35,6 +35,10 @@ class Columns(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ncols", "eventID", "x", "y", "z", "z_start", "z_end", "dx", "dEdx", "dE", "t0")]
 
 
+class PadColumns(C.Structure):
+    _fields_ = [("eventID", C.c_int32), ("trackID", C.c_int32), ("pixel_plane", C.c_int32)]
+
+
 class ChopColumns(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ncols", "x", "y", "z", "x_start", "y_start", "z_start", "x_end", "y_end", "z_end",
                                          "dx", "dE")]
@@ -204,6 +208,10 @@ def _declare(lib):
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]
     lib.larnd_chop_count.restype = C.c_int
     lib.larnd_chop_tracks.restype = C.c_int
+    lib.larnd_batch_gather.argtypes = [vp, i32, vp, vp, i64, i32, vp, vp]
+    lib.larnd_batch_gather.restype = C.c_int
+    lib.larnd_pad_rows.argtypes = [vp, i32, vp, i64, C.POINTER(PadColumns), vp]
+    lib.larnd_pad_rows.restype = C.c_int
     lib.larnd_tracks_stage.argtypes = [vp, i64, PC, C.POINTER(TrackColumns), PP, i32, vp, vp]
     lib.larnd_signals_stream_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, vp, vp]
     lib.larnd_signals_stream_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, PP, vp, vp, i64,

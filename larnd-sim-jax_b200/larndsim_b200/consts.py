@@ -227,7 +227,9 @@ def gaussian_bank_kernels(params):
     ext = int(params.long_diff_extent)
     x = np.arange(-ext, ext + 1, dtype=np.float32)
     sig = np.asarray(params.long_diff_template, dtype=np.float32)[:, None]
-    g = (np.exp(-0.5 * (x[None, :] / sig) ** 2) / (sig * np.float32(math.sqrt(2 * math.pi)))).astype(np.float32)
+    # jax.scipy.stats.norm.pdf = exp(logpdf), logpdf = (log(2 pi scale^2) + x^2 / scale^2) / -2, float32 operation by operation
+    s2 = (sig * sig).astype(np.float32)
+    g = np.exp(((np.log(np.float32(2 * math.pi) * s2) + (x[None, :] * x[None, :]) / s2) / np.float32(-2)).astype(np.float32)).astype(np.float32)
     return (g / g.sum(axis=1, keepdims=True)).astype(np.float32)
 
 
@@ -254,8 +256,22 @@ def build_response_template(response, params, device="cuda"):
     return bank
 
 
-def load_lut(lut_file, params, device="cuda"):
-    """(response_template, params') from a .npy/.npz response file (reference: consts_jax.py:387-449)."""
+def _bank_cache_key(resp, params):
+    import hashlib
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(resp, dtype=np.float32).tobytes())
+    h.update(np.asarray(params.long_diff_template, dtype=np.float32).tobytes())
+    h.update(("extent=%d;v=2" % int(params.long_diff_extent)).encode())
+    return h.hexdigest()
+
+
+def load_lut(lut_file, params, device="cuda", cache_dir=None):
+    """(response_template, params') from a .npy/.npz response file (reference: consts_jax.py:387-449).
+
+    ``cache_dir``: on-disk cache of the convolved bank, keyed by a hash of (response samples, template grid, extent).  The
+    reference rebuilds the bank on every start (100 x 2025 ``jnp.convolve`` calls); here the build is one ~2 ms kernel, so
+    the cache only saves the host-side read of the response — it exists for drivers that share one bank between many
+    processes (e.g. one per GPU) and is validated by shape on load (a stale or truncated file is rebuilt)."""
     resp = np.load(lut_file)
     new_params = params.replace()
     if isinstance(resp, np.lib.npyio.NpzFile):
@@ -267,4 +283,21 @@ def load_lut(lut_file, params, device="cuda"):
         resp = data
     elif not isinstance(resp, np.ndarray):
         raise ValueError("Unsupported response format. Expected npz or numpy array.")
-    return build_response_template(resp, params, device), new_params
+    if cache_dir is None:
+        return build_response_template(resp, params, device), new_params
+    import os
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, "bank_%s.npy" % _bank_cache_key(resp, params))
+    want = (len(params.long_diff_template),) + tuple(resp.shape)
+    if os.path.exists(path):
+        try:
+            cached = np.load(path, mmap_mode="r")
+            if tuple(cached.shape) == want and cached.dtype == np.float32:
+                return torch.from_numpy(np.array(cached)).to(device), new_params
+        except (ValueError, OSError):
+            pass
+    bank = build_response_template(resp, params, device)
+    tmp = path + ".tmp.%d" % os.getpid()
+    np.save(tmp, bank.cpu().numpy())
+    os.replace(tmp + ".npy" if not tmp.endswith(".npy") else tmp, path)      # atomic: concurrent ranks see a complete file or none
+    return bank, new_params

@@ -109,3 +109,199 @@ def simulate_from_raw(params, response_template, raw_tracks, fields, precision=N
     chopped = chop_tracks(raw_tracks, fields, precision)
     wfs, upix = sim.simulate_wfs(params, response_template, chopped, fields, npix_capacity=npix_capacity, n_events=n_events)
     return sim.simulate_stochastic(params, wfs, upix, rngseed)
+
+
+# ------------------------------------------------------------------------------------------ event-aligned batching
+class TracksDataset:
+    """Device-resident counterpart of the reference's ``TracksDataset`` (optimize/dataio.py:107-418), same constructor
+    arguments and accessors.  The bookkeeping — trajectories = unique (eventID, trackID), trajectories longer than
+    ``max_batch_len`` dropped, WHOLE events packed into batches by floor-divide of the cumulative event length, per-batch
+    global event ids — is a few thousand raw rows and stays on the host (numpy, vectorised; the reference loops in
+    Python).  The rows themselves are uploaded ONCE; ``dataset[i]`` assembles batch i on the device: gather + event-id
+    remap (k_batch_gather), chop (k_chop_*), padding with invalid rows to the largest batch (k_pad_rows, driven by the
+    device-side row count — no host synchronisation).  Returns CUDA float32 tensors of shape (rows, n_fields).
+
+    ``source``: path of an HDF5 file with a ``segments`` table (read with larndsim_b200.h5io) or the structured array."""
+
+    def __init__(self, filename, nevents=None, max_nbatch=None, swap_xz=True, random_nevents=False, data_seed=42, track_len_sel=2.,
+                 max_abs_costheta_sel=0.966, min_abs_segz_sel=15., track_z_bound=28., max_batch_len=50, print_input=False,
+                 chopped=True, pad=True, electron_sampling_resolution=0.1, live_selection=False, device=None):
+        import numpy as np
+        from numpy.lib import recfunctions as rfn
+        if isinstance(filename, str):
+            from .h5io import read_dataset
+            tracks = read_dataset(filename, "segments")
+        else:
+            tracks = np.array(filename, copy=True)
+        if swap_xz:                                   # the drift axis is z in the simulation (dataio.py:117-128)
+            for a, b in (("x_start", "z_start"), ("x_end", "z_end"), ("x", "z")):
+                tmp = tracks[a].copy()
+                tracks[a] = tracks[b]
+                tracks[b] = tmp
+        if "t0" not in tracks.dtype.names:
+            tracks = rfn.append_fields(tracks, "t0", np.zeros(tracks.shape[0]), usemask=False)
+        rename = {"event_id": "eventID", "traj_id": "trackID"}
+        self.track_fields = tuple(rename.get(f, f) for f in tracks.dtype.names)
+        tracks.dtype.names = self.track_fields
+        if max_batch_len is not None and max_nbatch is not None and max_nbatch > 0:
+            # load only what max_nbatch batches can need, cut at an event boundary (dataio.py:147-157)
+            cutoff = int(np.searchsorted(np.cumsum(tracks["dx"]), max_batch_len * (max_nbatch + 2), side="left"))
+            if cutoff < len(tracks):
+                other = np.nonzero(tracks["eventID"][:cutoff + 1] != tracks["eventID"][cutoff])[0]
+                if other.size:
+                    tracks = tracks[:int(other[-1]) + 1]
+        self.tracks_struct = tracks
+        ev, trk = tracks["eventID"].astype(np.int64), tracks["trackID"].astype(np.int64)
+        if live_selection:                            # dataio.py:162-186
+            sel_rows = np.nonzero(np.abs(tracks["z"]) < min_abs_segz_sel)[0]
+            sel = tracks[sel_rows]
+            _, first = np.unique(sel[["eventID", "trackID"]], return_index=True)
+            first = np.sort(first)
+            last = np.r_[first[1:] - 1, len(sel) - 1]
+            a, b = sel[first], sel[last]
+            d = np.column_stack((a["x_start"] - b["x_end"], a["y_start"] - b["y_end"], a["z_start"] - b["z_end"]))
+            cos_theta = np.abs(d[:, 2]) / (np.linalg.norm(d, axis=1) + 1e-10)
+            ok = (np.sqrt((d ** 2).sum(axis=1)) > track_len_sel) & (cos_theta < max_abs_costheta_sel) & \
+                 (np.maximum(np.abs(a["z"]), np.abs(b["z"])) < track_z_bound)
+            key_rows = sel_rows[np.repeat(ok, last - first + 1)]
+        else:
+            key_rows = np.arange(len(tracks))
+        # trajectories: rows grouped by (eventID, trackID) in key order, rows in file order inside a trajectory.
+        # NOTE (reference quirk, kept): with live_selection the inverse index is over the SELECTED rows but is used to
+        # address rows of the full table (dataio.py:189-207); without it (every production script) they coincide.
+        keys = np.ascontiguousarray(tracks[key_rows][["eventID", "trackID"]])
+        self.traj_keys, inverse = np.unique(keys, return_inverse=True)
+        order = np.argsort(inverse, kind="stable")
+        starts = np.r_[0, np.nonzero(np.diff(inverse[order]))[0] + 1, len(order)]
+        traj_rows = [order[s:e] for s, e in zip(starts[:-1], starts[1:])] if len(order) else []
+        traj_event = np.array([ev[r[0]] for r in traj_rows], dtype=np.int64)
+        uniq_ev, first_ev = np.unique(traj_event, return_index=True)
+        ordered_events = uniq_ev[np.argsort(first_ev)]
+        if nevents is not None and nevents > 0:
+            if random_nevents and nevents < len(ordered_events):
+                chosen = np.random.default_rng(seed=data_seed).choice(ordered_events, size=nevents, replace=False)
+            else:
+                chosen = ordered_events if random_nevents else ordered_events[:nevents]
+            keep = np.nonzero(np.isin(traj_event, chosen))[0]
+            traj_rows = [traj_rows[i] for i in keep]
+        self.trajectory_row_indices = traj_rows
+        if max_batch_len is not None:
+            traj_len = np.array([tracks["dx"][r].sum() for r in traj_rows])
+            valid = np.nonzero(traj_len <= max_batch_len)[0]
+            if valid.size == 0:
+                raise ValueError("All tracks are longer than the batch size! Please check.")
+            uev, inv = np.unique(np.array([ev[traj_rows[v][0]] for v in valid]), return_inverse=True)
+            ev_len = np.zeros(len(uev))
+            np.add.at(ev_len, inv, traj_len[valid])            # same accumulation order as the reference's loop
+            cum = np.cumsum(ev_len)
+            split = np.nonzero(np.diff(np.floor_divide(cum, max_batch_len)) > 0)[0] + 1
+            split = np.r_[0, split, len(cum)]
+            if max_nbatch and max_nbatch > 0:
+                split = split[:max_nbatch + 1]
+            by_event = [valid[inv == e] for e in range(len(uev))]
+            self.batch_traj_indices = [[int(t) for e in range(split[i], split[i + 1]) for t in by_event[e]] for i in range(len(split) - 1)]
+            self.tot_data_length = cum[split[-1] - 1]
+        else:
+            self.batch_traj_indices = [[i] for i in range(len(traj_rows))]
+            self.tot_data_length = float(sum(tracks["dx"][r].sum() for r in traj_rows))
+        if min(len(b) for b in self.batch_traj_indices) == 0:
+            raise ValueError("There exist some empty batch in the simulation input!")
+        self.batch_row_indices, self.batch_event_global_ids, self.batch_row_keys, self.batch_nsteps = [], [], [], []
+        for trajs in self.batch_traj_indices:
+            rows = np.concatenate([traj_rows[t] for t in trajs]).astype(np.int64)
+            self.batch_row_indices.append(rows)
+            self.batch_row_keys.append(np.ascontiguousarray(np.unique(tracks[rows][["eventID", "trackID"]])))
+            self.batch_event_global_ids.append(np.unique(ev[rows]))
+            self.batch_nsteps.append(int(np.maximum(np.ceil(tracks["dx"][rows] / electron_sampling_resolution), 1).astype(int).sum()))
+        self.max_batch_nsteps = max(self.batch_nsteps) if self.batch_nsteps else 0
+        self.chopped, self.pad, self.print_input = chopped, pad, print_input
+        self.electron_sampling_resolution = electron_sampling_resolution
+        # ---- device side (uploaded on first use): the float32 rows once, per batch the row list and the local event id of
+        # every row (remap_event_ids_to_local, dataio.py:47-61)
+        self.device = device
+        self._host_rows = np.stack([tracks[n].astype(np.float32) for n in self.track_fields], axis=1)   # structured_to_unstructured
+        self.batch_local_event_ids = [np.searchsorted(g, ev[r]).astype(np.int32)
+                                      for r, g in zip(self.batch_row_indices, self.batch_event_global_ids)]
+        self._raw = None
+        f = self.track_fields
+        self._pad_cols = _lib.PadColumns(f.index("eventID"), f.index("trackID") if "trackID" in f else -1,
+                                         f.index("pixel_plane") if "pixel_plane" in f else -1)
+
+    def _upload(self):
+        if self._raw is None:
+            if not torch.cuda.is_available():
+                raise _lib.LarndError("TracksDataset batches are assembled on the GPU (larndsim_b200 has no CPU path)")
+            self.device = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+            self._raw = torch.from_numpy(self._host_rows).to(self.device)
+            self._rows_d = [torch.from_numpy(r).to(self.device) for r in self.batch_row_indices]
+            self._local_d = [torch.from_numpy(l).to(self.device) for l in self.batch_local_event_ids]
+
+    def __len__(self):
+        return len(self.batch_traj_indices)
+
+    def get_track_fields(self):
+        return self.track_fields
+
+    def get_batch_global_event_ids(self, idx=None):
+        return self.batch_event_global_ids if idx is None else self.batch_event_global_ids[idx]
+
+    def get_batch_row_keys(self):
+        return self.batch_row_keys
+
+    def get_batch_row_indices(self, idx=None):
+        return self.batch_row_indices if idx is None else self.batch_row_indices[idx]
+
+    def raw_batch(self, idx):
+        """Un-chopped rows of batch idx with batch-local event ids, on the device."""
+        self._upload()
+        rows, local = self._rows_d[idx], self._local_d[idx]
+        out = torch.empty((rows.numel(), self._raw.shape[1]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.get_lib().larnd_batch_gather(C.c_void_p(self._raw.data_ptr()), self._raw.shape[1], C.c_void_p(rows.data_ptr()),
+                                                         C.c_void_p(local.data_ptr()), rows.numel(), self.track_fields.index("eventID"),
+                                                         C.c_void_p(out.data_ptr()), st))
+        return out
+
+    def device_batch(self, idx, capacity=None):
+        """Batch idx chopped and padded to ``capacity`` rows (default: its own size with pad=False, the largest batch with
+        pad=True) without a host synchronisation: the row counts come from the host-side bookkeeping (batch_nsteps, exact
+        by construction) and the padding kernel reads the chop's device-side total."""
+        if idx < 0 or idx >= len(self):
+            raise IndexError("Batch index out of range")
+        raw = self.raw_batch(idx)
+        if not self.chopped:
+            return raw if capacity is None or capacity <= raw.shape[0] else pad_batch(raw, capacity, self.track_fields)
+        if capacity is None:
+            capacity = self.max_batch_nsteps if self.pad else self.batch_nsteps[idx]
+        capacity = max(int(capacity), self.batch_nsteps[idx])
+        off = chop_offsets(raw, self.track_fields, self.electron_sampling_resolution)
+        out = torch.empty((capacity, raw.shape[1]), dtype=torch.float32, device=self.device)
+        chop_tracks(raw, self.track_fields, self.electron_sampling_resolution, out=out, offsets=off)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.get_lib().larnd_pad_rows(C.c_void_p(out.data_ptr()), out.shape[1], C.c_void_p(off[-1:].data_ptr()), capacity,
+                                                     C.byref(self._pad_cols), st))
+        return out
+
+    def __getitem__(self, idx):
+        return self.device_batch(idx)
+
+    def pad_batch(self, batch_arr, target_len, idx=None):
+        """TracksDataset.pad_batch (dataio.py:351-368) on a device batch: invalid rows up to target_len; rows whose local event
+        id is not one of the batch's events are invalidated too."""
+        out = pad_batch(batch_arr, target_len, self.track_fields)
+        if idx is not None:
+            f = self.track_fields
+            evc = out[:, f.index("eventID")]
+            bad = (evc >= 0) & (evc >= len(self.batch_event_global_ids[idx]))
+            if bool(bad.any()):
+                out = out.clone()
+                out[bad, f.index("eventID")] = -1
+                for name in ("n_electrons", "dE", "dEdx", "dx", "long_diff", "tran_diff"):
+                    if name in f:
+                        out[bad, f.index(name)] = 0
+                for name in ("trackID", "pixel_plane"):
+                    if name in f:
+                        out[bad, f.index(name)] = -1
+        return out

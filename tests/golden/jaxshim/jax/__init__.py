@@ -72,3 +72,16 @@ def devices(*a):
 
 def default_backend():
     return "cpu"
+
+
+def device_put(x, device=None, **kw):
+    from ._core import asarray
+    return asarray(x)
+
+
+def device_get(x):
+    return x
+
+
+def block_until_ready(x):
+    return x

@@ -218,6 +218,14 @@ class _AtHelper:
         return _AtRef(self.arr, idx)
 
 
+def _canon_method(name):
+    """ndarray methods that do not dispatch through __array_ufunc__ and would hand back 64-bit results."""
+    def method(self, *a, **k):
+        return wrap(getattr(self.view(np.ndarray), name)(*a, **k))
+    method.__name__ = name
+    return method
+
+
 class Array(np.ndarray):
     """jax.Array stand-in: immutable-style `.at[]` updates, clamped gathers, canonical dtypes."""
     __array_priority__ = 100.0
@@ -240,11 +248,18 @@ class Array(np.ndarray):
         return wrap(getattr(ufunc, method)(*ins, **kwargs))
 
     def __array_function__(self, func, types, args, kwargs):
-        args = tuple(_plain(a) for a in args)
-        kwargs = {k: _plain(v) for k, v in kwargs.items()}
-        if "dtype" in kwargs and kwargs["dtype"] is not None:
-            kwargs["dtype"] = canon_dtype(kwargs["dtype"])
-        return wrap(func(*args, **kwargs))
+        # numpy.<function>(jax array): numpy converts the operand (np.asarray) and applies ITS OWN semantics, returning
+        # numpy arrays — e.g. np.unique(event[mask]) in optimize/simulate.py:139 yields hashable numpy integers
+        def plain(a):
+            if isinstance(a, np.ndarray):
+                return a.view(np.ndarray)
+            if isinstance(a, (list, tuple)):
+                return type(a)(plain(e) for e in a)
+            return a
+        return func(*plain(args), **{k: plain(v) for k, v in kwargs.items()})
+
+    argmax, argmin, cumsum, cumprod, nonzero, argsort, searchsorted = [_canon_method(_n) for _n in (
+        "argmax", "argmin", "cumsum", "cumprod", "nonzero", "argsort", "searchsorted")]
 
     @property
     def at(self):

@@ -280,8 +280,46 @@ def worker():
     raw = lo.structured_to_f32(lo.swap_xz_structured(seg))[:40]
     chopped = dataio.chop_tracks(raw.copy(), cm.FIELDS, 0.05)
     out["chop_in"], out["chop_out"] = raw, np.asarray(chopped)
+    # TracksDataset bookkeeping (optimize/dataio.py:107-418) on three prepared inputs, production settings + a cut variant
+    for ifile, kw in ((0, {}), (1, {}), (7, {}), (7, dict(nevents=5, max_nbatch=2, max_batch_len=30))):
+        ds = dataio.TracksDataset(filename=os.path.join(REF, "prepared_data/input_%d.h5" % ifile), **dict(dict(
+            nevents=None, max_nbatch=None, swap_xz=True, random_nevents=False, data_seed=42, max_batch_len=50, chopped=True, pad=False,
+            electron_sampling_resolution=0.005, live_selection=False), **kw))
+        pre = "dataset_%d%s" % (ifile, "_cut" if kw else "")
+        out[pre + "/nsteps"] = np.array(ds.batch_nsteps)
+        out[pre + "/tot_len"] = np.float64(ds.tot_data_length)
+        for b in range(len(ds)):
+            out["%s/rows_%d" % (pre, b)] = np.sort(ds.get_batch_row_indices(b))     # the order inside a trajectory comes from an
+            out["%s/events_%d" % (pre, b)] = ds.get_batch_global_event_ids(b)       # unstable argsort in the reference: set only
+            if b == 0 and not kw:
+                arr = ds[b]
+                padded = ds.pad_batch(arr, arr.shape[0] + 7, b)
+                order = np.lexsort(arr.T[::-1])                                     # row order normalised for the comparison
+                out[pre + "/batch0_sorted"], out[pre + "/batch0_pad_tail"] = arr[order], padded[-7:]
     np.savez_compressed(os.path.join(HERE, "refshim_misc.npz"), **out)
     print(tag, "misc:", len(out), "arrays")
+
+    # ------------------------------------------------------------------ the production driver, end to end
+    # python -m optimize.simulate with the settings of optimize/simulate_test.sh on prepared_data/input_0.h5 and the synthetic
+    # response; what it writes through h5py is captured by the stand-in (tests/golden/jaxshim/h5py.py)
+    import argparse
+    import h5py
+    from optimize import simulate as ref_simulate
+    sim_jax.size_history_dict.clear()
+    lut_path = os.path.join(tmp, "response_synthetic.npy")
+    np.save(lut_path, oc.synthetic_response(45, 45, 1950))
+    cfg = argparse.Namespace(
+        input_file=os.path.join(REF, "prepared_data/input_0.h5"), output_file=os.path.join(tmp, "out_0.h5"),
+        detector_props=os.path.join(REF, "src/larndsim/detector_properties/module0.yaml"),
+        pixel_layouts=os.path.join(REF, "src/larndsim/pixel_layouts/multi_tile_layout-2.4.16_v4.yaml"), mode="lut",
+        electron_sampling_resolution=0.005, number_pix_neighbors=4, signal_length=100, lut_file=lut_path, noise=False, seed=None,
+        diffusion_in_current_sim=False, batch_size=500, gpu=False, jac=False, mc_diff=False, save_wfs=False, n_events=-1, out_np=False,
+        max_batch_len=50., chop=True)
+    rc, msg = ref_simulate.main(cfg)
+    assert rc == 0, msg
+    written = h5py.WRITTEN[cfg.output_file]
+    np.savez_compressed(os.path.join(HERE, "refshim_simulate_0.npz"), **written)
+    print(tag, "simulate:", len(written), "datasets,", sum(len(v) for k, v in written.items() if k.endswith("/adc")), "hits")
 
 
 if __name__ == "__main__":
