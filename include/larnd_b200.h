@@ -161,6 +161,23 @@ int larnd_lut_forward(const float* tracks_d, int64_t n_segments, const larnd_col
                       int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
                       int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream);
 
+/* Deterministic simulate_wfs (the counterpart of running the reference with --xla_gpu_deterministic_ops,
+ * optimize/example_run.py:44-47): same outputs as larnd_lut_forward, but bitwise reproducible from run to run.  The default
+ * kernels add float32 window sums with red.global.add in arrival order (low bits vary, ~1e-7 relative); here every window
+ * sum — a fixed function of its chunk of segments — is added as a 64-bit fixed-point integer (2^-20 resolution), which is
+ * order-independent, and converted to float32 once.  Uses the chunk kernels for every batch size (slower at spill size)
+ * and a caller-provided scratch of larnd_deterministic_scratch_bytes(npix_capacity, n_ticks) bytes. */
+size_t larnd_deterministic_scratch_bytes(int32_t npix_capacity, int32_t n_ticks);
+int larnd_lut_accumulate_deterministic(int64_t n_segments, const larnd_params_t* params, const larnd_lut_t* lut,
+                                       int32_t n_events, int32_t npix_capacity, int32_t flags, void* workspace_d,
+                                       size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride,
+                                       int32_t* counts_d, void* det_scratch_d, size_t det_scratch_bytes, void* stream);
+int larnd_lut_forward_deterministic(const float* tracks_d, int64_t n_segments, const larnd_columns_t* cols,
+                                    const larnd_params_t* params, const larnd_lut_t* lut, int32_t n_events,
+                                    int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                                    int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d,
+                                    void* det_scratch_d, size_t det_scratch_bytes, void* stream);
+
 /* Only the drift/pixelisation stage + unique/renumber (simulate_drift_new + sim_jax.py:717-725):
  * fills the workspace segment records and unique_pixels_d/counts_d.  Lets a caller size wfs exactly
  * (the reference's pad_size(n_unique+1)) before calling larnd_lut_accumulate. */

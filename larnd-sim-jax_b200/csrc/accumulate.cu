@@ -42,6 +42,7 @@ struct AccArgs {
   RowLookup lk;
   const int32_t* counts;
   float* wfs;
+  unsigned long long* wfs64;  // deterministic mode: (npix, nticks) 64-bit fixed-point accumulators instead of wfs (else nullptr)
   int skip_garbage;
   int slow_only;  // 1: only segments whose window touches the ends of the readout (the rest is done by accumulate_sorted.cu)
 };
@@ -84,10 +85,36 @@ struct ChunkSmem {
   int next_unit;
 };
 
+// 2^-20 electrons-per-tick resolution, +-8.8e12 range: far below float32 resolution of any waveform sample that matters
+constexpr double DET_SCALE = 1048576.0;
+__device__ __forceinline__ unsigned long long det_fixed(float v) { return (unsigned long long)__double2ll_rn((double)v * DET_SCALE); }
+
+__global__ void k_det_convert(const unsigned long long* __restrict__ acc, float* __restrict__ wfs, int64_t npix, int nticks, int64_t stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * nticks) return;
+  const int64_t r = i / nticks;
+  wfs[r * stride + (i - r * nticks)] = (float)((double)(long long)acc[i] * (1.0 / DET_SCALE));
+}
+
 template <int NS>
 __device__ __forceinline__ void flush_row(float (&acc)[NS], float& g0, bool& g0_used, int row, int tbase,
                                           const AccArgs& A, int lane) {
-  if (row >= 0) {
+  if (row >= 0 && A.wfs64) {
+    // deterministic mode: every flushed window value is a fixed function of the chunk's segments; adding it as a 64-bit
+    // fixed-point integer makes the total independent of the order in which warps and CTAs arrive
+    unsigned long long* base = A.wfs64 + (int64_t)row * A.nticks;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      int col = tbase + 32 * j + lane;
+      if (acc[j] != 0.0f && col >= 1 && col < A.nticks) atomicAdd(base + col, det_fixed(acc[j]));
+    }
+    if (g0_used) {
+      float g = g0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+      if (lane == 0 && g != 0.0f) atomicAdd(base, det_fixed(g));
+    }
+  } else if (row >= 0) {
     float* base = A.wfs + (int64_t)row * A.wstride;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
@@ -537,8 +564,13 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
 }  // namespace
 
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                            int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts, cudaStream_t st) {
+                            int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts, cudaStream_t st,
+                            unsigned long long* det_acc) {
   if (n == 0) return LARND_OK;
+  if (det_acc) {   // deterministic mode: chunk kernel only, 64-bit fixed-point accumulators, converted at the end
+    flags = (flags | LARND_FLAG_IMPL_CHUNK) & ~LARND_FLAG_IMPL_SORTED;
+    LARND_CUDA(cudaMemsetAsync(det_acc, 0, (size_t)npix_capacity * p.n_ticks * sizeof(unsigned long long), st));
+  }
   const bool slow_only = (flags & LARND_ACC_SLOW_ONLY) != 0;
   // (the forward tile kernel addresses the waveform buffer with signed 32-bit element offsets)
   {
@@ -568,6 +600,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.lk.n_unique = 0; A.lk.n_neg = 0; A.lk.npix = npix_capacity;
   A.counts = counts;
   A.wfs = wfs;
+  A.wfs64 = det_acc;
   A.skip_garbage = flags & LARND_FLAG_SKIP_GARBAGE;
   A.slow_only = slow_only ? 1 : 0;
   const int64_t chunks = (n + S - 1) / S;
@@ -599,5 +632,10 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   }
   if (!slow_only) prof_end(1, st);
   LARND_LAUNCH_CHECK("k_lut_accumulate");
+  if (det_acc) {
+    const int64_t tot = (int64_t)npix_capacity * p.n_ticks;
+    k_det_convert<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(det_acc, wfs, npix_capacity, p.n_ticks, wfs_stride);
+    LARND_LAUNCH_CHECK("k_det_convert");
+  }
   return LARND_OK;
 }

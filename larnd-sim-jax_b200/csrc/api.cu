@@ -138,9 +138,10 @@ extern "C" int larnd_lut_prepare(const float* tracks_d, int64_t n, const larnd_c
   return larnd_launch_scan(ws, *p, counts_d, st);
 }
 
-extern "C" int larnd_lut_accumulate(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
-                                    int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
-                                    int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream) {
+static int lut_accumulate_impl(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
+                               int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                               int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream,
+                               unsigned long long* det_acc) {
   int rc = check_common(p, lut, true);
   if (rc) return rc;
   if (!unique_pixels_d || !wfs_d || !counts_d || npix_capacity < 1 || wfs_row_stride < p->n_ticks) {
@@ -155,7 +156,41 @@ extern "C" int larnd_lut_accumulate(int64_t n, const larnd_params_t* p, const la
   cudaStream_t st = (cudaStream_t)stream;
   LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * wfs_row_stride * sizeof(float), st));
   if ((rc = larnd_launch_unique(ws, *p, npix_capacity, /*extra=*/1, unique_pixels_d, counts_d, st))) return rc;
-  return larnd_launch_accumulate(n, *p, lut, ws, npix_capacity, flags & LARND_FLAG_PUBLIC_MASK, wfs_d, wfs_row_stride, counts_d, st);
+  return larnd_launch_accumulate(n, *p, lut, ws, npix_capacity, flags & LARND_FLAG_PUBLIC_MASK, wfs_d, wfs_row_stride, counts_d, st, det_acc);
+}
+
+extern "C" int larnd_lut_accumulate(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
+                                    int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                                    int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream) {
+  return lut_accumulate_impl(n, p, lut, n_events, npix_capacity, flags, workspace_d, workspace_bytes, unique_pixels_d, wfs_d, wfs_row_stride,
+                             counts_d, stream, nullptr);
+}
+
+extern "C" size_t larnd_deterministic_scratch_bytes(int32_t npix_capacity, int32_t n_ticks) {
+  return (size_t)(npix_capacity > 0 ? npix_capacity : 0) * (size_t)(n_ticks > 0 ? n_ticks : 0) * sizeof(unsigned long long);
+}
+
+extern "C" int larnd_lut_accumulate_deterministic(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
+                                                  int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                                                  int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d,
+                                                  void* det_scratch_d, size_t det_scratch_bytes, void* stream) {
+  if (!p || !det_scratch_d || det_scratch_bytes < larnd_deterministic_scratch_bytes(npix_capacity, p->n_ticks)) {
+    larnd_set_error("larnd_lut_accumulate_deterministic: scratch missing or smaller than larnd_deterministic_scratch_bytes()");
+    return LARND_E_ARG;
+  }
+  return lut_accumulate_impl(n, p, lut, n_events, npix_capacity, flags, workspace_d, workspace_bytes, unique_pixels_d, wfs_d, wfs_row_stride,
+                             counts_d, stream, reinterpret_cast<unsigned long long*>(det_scratch_d));
+}
+
+extern "C" int larnd_lut_forward_deterministic(const float* tracks_d, int64_t n, const larnd_columns_t* cols, const larnd_params_t* p,
+                                               const larnd_lut_t* lut, int32_t n_events, int32_t npix_capacity, int32_t flags,
+                                               void* workspace_d, size_t workspace_bytes, int32_t* unique_pixels_d, float* wfs_d,
+                                               int64_t wfs_row_stride, int32_t* counts_d, void* det_scratch_d, size_t det_scratch_bytes,
+                                               void* stream) {
+  int rc = larnd_lut_prepare(tracks_d, n, cols, p, lut, n_events, workspace_d, workspace_bytes, counts_d, stream);
+  if (rc) return rc;
+  return larnd_lut_accumulate_deterministic(n, p, lut, n_events, npix_capacity, flags, workspace_d, workspace_bytes, unique_pixels_d, wfs_d,
+                                            wfs_row_stride, counts_d, det_scratch_d, det_scratch_bytes, stream);
 }
 
 extern "C" int larnd_lut_forward(const float* tracks_d, int64_t n, const larnd_columns_t* cols, const larnd_params_t* p,

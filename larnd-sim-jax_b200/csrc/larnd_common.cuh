@@ -161,7 +161,8 @@ int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t np
                         int32_t* counts, cudaStream_t st);
 int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st);
 int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                            int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts, cudaStream_t st);
+                            int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts, cudaStream_t st,
+                            unsigned long long* det_acc = nullptr);
 int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                    int32_t npix_capacity, int32_t flags, float* wfs, int64_t wfs_stride, const int32_t* counts,
                                    cudaStream_t st);

@@ -208,6 +208,12 @@ def _declare(lib):
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]
     lib.larnd_chop_count.restype = C.c_int
     lib.larnd_chop_tracks.restype = C.c_int
+    lib.larnd_deterministic_scratch_bytes.argtypes = [i32, i32]
+    lib.larnd_deterministic_scratch_bytes.restype = sz
+    lib.larnd_lut_accumulate_deterministic.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp, sz, vp]
+    lib.larnd_lut_accumulate_deterministic.restype = C.c_int
+    lib.larnd_lut_forward_deterministic.argtypes = [vp, i64, PC, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp, sz, vp]
+    lib.larnd_lut_forward_deterministic.restype = C.c_int
     lib.larnd_batch_gather.argtypes = [vp, i32, vp, vp, i64, i32, vp, vp]
     lib.larnd_batch_gather.restype = C.c_int
     lib.larnd_pad_rows.argtypes = [vp, i32, vp, i64, C.POINTER(PadColumns), vp]

@@ -208,7 +208,20 @@ def n_events_of(tracks, fields):
     return max(int(ev.max().item()) + 1, 0) if ev.numel() else 0
 
 
-def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n_events=None, flags=0, out=None):
+_deterministic = False
+
+
+def set_deterministic(on=True):
+    """Process-wide switch for bitwise reproducible waveforms and hit lists — the counterpart of running the reference with
+    XLA_FLAGS=--xla_gpu_deterministic_ops (optimize/example_run.py:44-47).  The default kernels add float32 window sums with
+    red.global.add in arrival order (the low bits vary from run to run, ~1e-7 relative); with this switch simulate_wfs
+    accumulates 64-bit fixed-point integers (order-independent) through the chunk kernels.  Slower at spill-sized batches
+    and needs 8 more bytes per waveform sample.  Gradients are not covered (the backward kernels reduce with float atomics)."""
+    global _deterministic
+    _deterministic = bool(on)
+
+
+def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n_events=None, flags=0, out=None, deterministic=None):
     """prepare -> unique/renumber -> accumulate.  ``npix_capacity=None`` reproduces the reference's padded size
     pad_size(n_unique+1,'unique_pixels',0.2) (one 16-byte D2H read, like jnp.unique's sync); an explicit
     capacity keeps the whole call asynchronous.  Returns a LutState."""
@@ -250,9 +263,15 @@ def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n
         if st.wfs_buf.dim() != 2 or st.wfs_buf.shape[0] != st.npix or st.wfs_buf.shape[1] < pod.n_ticks or st.wfs_buf.stride(1) != 1:
             raise ValueError("waveform buffer must be (npix_capacity, >= n_ticks) float32 with unit column stride")
         st.wfs_full = st.wfs_buf[:, :pod.n_ticks]
-        _lib.check(lib.larnd_lut_accumulate(n, C.byref(pod), lut.handle, n_events, st.npix, st.flags, _ptr(st.workspace),
-                                            ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_buf), st.wfs_buf.stride(0),
-                                            _ptr(st.counts), _stream()))
+        if _deterministic if deterministic is None else deterministic:
+            scratch = torch.empty(lib.larnd_deterministic_scratch_bytes(st.npix, pod.n_ticks), dtype=torch.uint8, device=tracks.device)
+            _lib.check(lib.larnd_lut_accumulate_deterministic(n, C.byref(pod), lut.handle, n_events, st.npix, st.flags, _ptr(st.workspace),
+                                                              ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_buf), st.wfs_buf.stride(0),
+                                                              _ptr(st.counts), _ptr(scratch), scratch.numel(), _stream()))
+        else:
+            _lib.check(lib.larnd_lut_accumulate(n, C.byref(pod), lut.handle, n_events, st.npix, st.flags, _ptr(st.workspace),
+                                                ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_buf), st.wfs_buf.stride(0),
+                                                _ptr(st.counts), _stream()))
     return st
 
 

@@ -990,3 +990,46 @@ def test_simulate_drift_new_view_and_mirror_helpers(torch_dev):
     c = cm.FIELDS.index
     assert np.allclose(el[:, c("x")], d["tracks"][:, c("x")] + rnd[:, 0] * d["tracks"][:, c("tran_diff")], atol=1e-5)
     assert np.array_equal(el[:, c("z")], d["tracks"][:, c("z")])
+
+
+def test_deterministic_mode_is_bitwise_reproducible_and_reference_accurate(torch_dev):
+    """sim.set_deterministic / lut_forward(deterministic=True): the counterpart of --xla_gpu_deterministic_ops
+    (optimize/example_run.py:44-47).  Five runs of a 60 k-segment batch (where the default kernels' float reductions do
+    reorder) give bit-identical waveforms and hit lists; the result meets the same bars against the oracle."""
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=4, signal_length=100)
+    bank = torch.as_tensor(cm.synthetic_bank(32, 45, 45, 1950), device=torch_dev)
+    # event ids stay local per source batch: offset them so that the concatenation is one batch of distinct events
+    off, parts = 0, []
+    for i, src in enumerate([cm.fixture_batches(0, 0.005)[j][0] for j in range(4)] + [cm.fixture_batches(1, 0.005)[j][0] for j in range(2)]):
+        p = src.copy()
+        p[:, 0] += off
+        off = int(p[:, 0].max()) + 1
+        parts.append(p)
+    tr = torch.as_tensor(np.concatenate(parts), device=torch_dev)
+    assert tr.shape[0] > 50000
+    pp = cm.product_params(**kw)
+    ref = None
+    for rep in range(5):
+        st = sim.lut_forward(pp, bank, tr, cm.FIELDS, deterministic=True)
+        hits = sim.simulate_stochastic(pp, st.wfs_full[:, 1:], st.unique_pixels, 0)
+        cur = [st.wfs_full.clone()] + [h.clone() for h in hits]
+        if ref is None:
+            ref = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(ref, cur)), rep
+    # accuracy: the deterministic waveforms against the default kernels (both within the oracle bar of each other)
+    st0 = sim.lut_forward(pp, bank, tr, cm.FIELDS, npix_capacity=st.npix)
+    w, w0 = ref[0].cpu().numpy(), st0.wfs_full.cpu().numpy()
+    real = st.unique_pixels.cpu().numpy() >= 0
+    scale = np.abs(w0[real]).max(axis=1, keepdims=True)
+    assert (np.abs(w - w0)[real][:, 1:] <= WFS_RTOL * scale + 1e-3).all()
+    _hits_equal([h.cpu().numpy() for h in sim.simulate_stochastic(pp, st0.wfs_full[:, 1:], st0.unique_pixels, 0)], ref[1:])
+    # ... and against the oracle on a small batch through the same path
+    small = cm.small_batch(600, pad=8, precision=0.01)
+    op = cm.oracle_params(**kw)
+    wo, uo = lo.simulate_wfs(op, cm.synthetic_bank(32, 45, 45, 1950), small, cm.FIELDS, history={})
+    sd = sim.lut_forward(pp, bank, torch.as_tensor(small, device=torch_dev), cm.FIELDS, npix_capacity=len(uo), deterministic=True)
+    assert np.array_equal(sd.unique_pixels.cpu().numpy(), uo)
+    _check_wfs(sd.wfs_full[:, 1:].cpu().numpy(), wo, uniq=uo)
