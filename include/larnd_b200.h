@@ -209,7 +209,12 @@ int larnd_lut_backward(int64_t n_segments, const larnd_params_t* params, const l
  *   hit_adc_d, hit_x_d, hit_y_d, hit_z_d, hit_ticks_d, hit_prob_d (float), hit_event_d, hit_pixel_d (int32),
  *   n_valid_d[1].  saved_d (npix, 32) float: per-row state needed by larnd_fee_backward ([0..9] crossing ticks, [10..12]
  *   hit / subtraction / digitiser-slope masks, [13..22] the integrated charge of every hit BEFORE the digitiser = the
- *   `adc` array get_adc_values itself returns, fee_jax.py:170-279). */
+ *   `adc` array get_adc_values itself returns, fee_jax.py:170-279).
+ * Row loads: when the row stride is a multiple of four floats, the rows are fetched with one cp.async.bulk (TMA) each from
+ * the 16-byte aligned address at or below the row start; if wfs_d itself is k = (wfs_d mod 16) / 4 floats past a 16-byte
+ * boundary (k = 1 for simulate_wfs' view [:, 1:] of the padded buffer) the k floats in front of every row and the round-up
+ * to a whole vector behind it are READ as well (never used) and must belong to the caller's buffer — true for any row
+ * stride >= round_up(k + n_ticks - 1, 4).  Other layouts take the vector-load path. */
 int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
                       const larnd_params_t* params, const float* noise_d,
                       float* adc_d, float* ticks_d, float* pixel_z_d, float* pixel_x_d, float* pixel_y_d,

@@ -26,6 +26,7 @@ struct FeeArgs {
   const float* noise;
   float* adc; float* ticks; float* pixel_z; float* pixel_x; float* pixel_y; int32_t* event; float* saved;
   int32_t* row_counts;
+  int bulk;  // rows are loaded with cp.async.bulk (layout contract checked by larnd_fee_forward)
 };
 
 __device__ __forceinline__ int floordiv_pos(int a, int b) { return floordiv_i(a, b); }
@@ -47,14 +48,56 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   float* c = smem + (size_t)wid * FEE_ROW_STRIDE(Nt) + shift;
   int t_first = Nt, t_last = -1;  // bounds of the non-zero samples (vector granularity: a superset is enough, zeros inside
                                   // the window do not change any running sum)
+  const float4* w4 = reinterpret_cast<const float4*>(w + head);
+  float4* c4 = reinterpret_cast<float4*>(c + head);
+  if (F.bulk) {
+    // Row load by the TMA engine: ONE cp.async.bulk per row (the whole 8 KB in flight per warp instead of four 512-byte
+    // warp loads at a time), completion on a per-warp mbarrier.  Layout contract (checked on the host): rows start `shift`
+    // (0 or 1) floats past a 16-byte boundary and the stride is a multiple of four floats — simulate_wfs' view [:, 1:] of
+    // the padded waveform buffer — so the copy starts at the aligned address below the row (its garbage column) and lands at
+    // the start of this warp's buffer; c = buffer + shift is the same shifted copy the vector path builds.
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)FEE_WARPS * FEE_ROW_STRIDE(Nt)) + wid;
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(c - shift);
+    const unsigned bytes = (unsigned)(((shift + Nt + 3) >> 2) << 4);
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst_s), "l"(w - shift), "r"(bytes), "r"(bar_s) : "memory");
+    }
+    __syncwarp();
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar_s) : "memory");
+    }
+    // q = wfs * t_sampling in place + bounds of the non-zero samples
+    if (lane < head + tail) {
+      const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
+      const float qv = __fmul_rn(c[t], p.t_sampling);
+      c[t] = qv;
+      if (qv != 0.0f) { t_first = t; t_last = t; }
+    }
+    for (int v = lane; v < nvec; v += 32) {
+      float4 q = c4[v];
+      q.x = __fmul_rn(q.x, p.t_sampling); q.y = __fmul_rn(q.y, p.t_sampling);
+      q.z = __fmul_rn(q.z, p.t_sampling); q.w = __fmul_rn(q.w, p.t_sampling);
+      if (q.x != 0.0f || q.y != 0.0f || q.z != 0.0f || q.w != 0.0f) {
+        c4[v] = q;   // all-zero vectors stay as they are (0 * t_sampling = 0)
+        const int t = head + 4 * v;
+        t_first = min(t_first, t);
+        t_last = max(t_last, t + 3);
+      }
+    }
+  } else {
   if (lane < head + tail) {
     const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
     const float qv = __fmul_rn(__ldg(w + t), p.t_sampling);  // q = wfs * t_sampling
     c[t] = qv;
     if (qv != 0.0f) { t_first = t; t_last = t; }
   }
-  const float4* w4 = reinterpret_cast<const float4*>(w + head);
-  float4* c4 = reinterpret_cast<float4*>(c + head);
   for (int v0 = 0; v0 < nvec; v0 += 128) {
     float4 x[4];
 #pragma unroll
@@ -77,6 +120,7 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
         }
       }
     }
+  }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -435,7 +479,13 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
   F.event = event_d; F.saved = saved_d;
   F.row_counts = reinterpret_cast<int32_t*>(scratch_d);
   int32_t* offsets = F.row_counts + npix;
-  size_t smem = (size_t)FEE_WARPS * FEE_ROW_STRIDE(ntw) * sizeof(float);
+  size_t smem = (size_t)FEE_WARPS * FEE_ROW_STRIDE(ntw) * sizeof(float) + FEE_WARPS * sizeof(uint64_t);  // rows + one mbarrier per warp
+  {
+    // TMA row loads need 16-byte aligned sources: rows whose start is `sh` floats past a 16-byte boundary are copied from
+    // the aligned address below (see the header: those floats and the round-up at the end must be readable)
+    const int sh = (int)(((uintptr_t)wfs_d & 15u) >> 2);
+    F.bulk = (((uintptr_t)wfs_d & 3u) == 0 && wfs_row_stride % 4 == 0 && ((sh + ntw + 3) & ~3) <= wfs_row_stride) ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     LARND_CUDA(cudaFuncSetAttribute(k_fee_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
