@@ -14,6 +14,7 @@ One *step* = one pass of the hot path over one synthetic spill batch of the prep
 `mc_mode`    : BASELINE config 3 (MC-current mode) forward and forward+grad.
 `fit_step`   : BASELINE config 4: one Adam step of the reference's --lut fit (n = 2, L = 150, ~19.8 k segments per rank,
                mse_adc, six fitted parameters), events sharded over the ranks, steps/s.
+`prepared_inputs`: BASELINE config 2: all 22 prepared inputs through the production-driver loop (N = 1 only).
 `scan_2d`    : BASELINE config 5b: 16 x 16 likelihood scan (loss + 2 gradients per point), grid points x event shards
                distributed over the ranks, wall time.
 `roofline`   : dominant kernels (forward and backward tile kernels): algorithmic HBM bytes / CUDA-event kernel time vs the
@@ -520,6 +521,42 @@ def run_ours(args):
                              "argmin": [float(a1[imin[0]]), float(a2[imin[1]])], "nominal": [0.5, 2200.0],
                              "finite_points": int(np.isfinite(table[..., 0]).sum())}
         del prob, adam, fit_tracks, bank4
+
+    if not args.no_extras:
+        # ---- BASELINE config 2: forward over ALL 22 prepared inputs (prepared_data/input_*.h5, committed as tests/golden/
+        # segments_input_*.npz), settings of optimize/simulate_test.sh (0.005 cm, n = 4, L = 100, --chop, 50 cm batches): the
+        # production driver's loop — TracksDataset batches assembled / chopped / padded on the device, simulate_wfs +
+        # simulate_stochastic, hits read back per batch.  ~90 batches of ~10 k segments: the small-batch regime.
+        import glob
+        from larndsim_b200 import dataio as _dio
+        files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "segments_input_*.npz")))
+        if files and world == 1:
+            p2 = params.replace(electron_sampling_resolution=0.005)
+            dsets = [_dio.TracksDataset(np.load(f)["segments"], nevents=None, max_nbatch=None, swap_xz=True, max_batch_len=50, chopped=True,
+                                        pad=False, electron_sampling_resolution=0.005, device=dev) for f in files]
+
+            def run_all():
+                nh = 0
+                for ds in dsets:
+                    f2 = ds.get_track_fields()
+                    for ib in range(len(ds)):
+                        cap = sim.pad_size(ds.batch_nsteps[ib], "batch_size", 0.5)
+                        tr = ds.device_batch(ib, capacity=cap)
+                        w, u = sim.simulate_wfs(p2, bank, tr, f2, n_events=len(ds.get_batch_global_event_ids(ib)))
+                        nh += int(sim.simulate_stochastic(p2, w, u, rngseed=ib)[0].shape[0])
+                return nh
+            run_all()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nhits2 = run_all()
+            torch.cuda.synchronize()
+            wall2 = time.perf_counter() - t0
+            nseg2 = sum(sum(ds.batch_nsteps) for ds in dsets)
+            nb2 = sum(len(ds) for ds in dsets)
+            extras["prepared_inputs"] = {"metric": "segments/s over all 22 prepared inputs (BASELINE config 2, production-driver loop)",
+                                         "value": nseg2 / wall2, "unit": "segments/s", "wall_s": wall2, "files": len(files), "batches": nb2,
+                                         "segments": int(nseg2), "hits": int(nhits2), "ms_per_batch": 1e3 * wall2 / nb2,
+                                         "timing": "host wall clock, one pass after a warm-up pass (the loop is launch/sync-bound at ~10 k segments per batch)"}
 
     # per-kernel device times of the dominant kernels, same launches as above
     lib.larnd_profile_enable(1)
