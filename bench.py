@@ -296,12 +296,16 @@ def run_ours(args):
     adc_target = fs_t.adc.clone()
     del st_t, fs_t
 
-    def fwd_grad():
+    steps_buf = torch.empty(lib.larnd_fee_steps_bytes(npix), dtype=torch.uint8, device=dev)
+
+    def fwd_grad(dense=False):
         st, fs = fwd(flags=0)
         diff = (fs.adc - adc_target) * (st.unique_pixels >= 0).unsqueeze(1)  # only real pixels enter the loss (parse_output)
         loss = (diff * diff).sum()
-        g_wfs = sim.fee_backward(fs, 2.0 * diff)
-        grad = sim.lut_backward(st, g_wfs)  # rows of ids < 0 carry zero gradient: detected on the device, their work is skipped
+        if dense:   # the two VJPs through the dense (npix, n_ticks) waveform gradient (what an arbitrary loss on the waveforms needs)
+            grad = sim.lut_backward(st, sim.fee_backward(fs, 2.0 * diff))
+        else:       # front-end VJP as a step list per pixel row -> accumulate VJP from running-sum differences (no dense gradient)
+            grad = sim.hits_backward(st, fs, 2.0 * diff, steps=steps_buf)
         red = torch.cat([loss.reshape(1), grad])
         if world > 1:
             dist.all_reduce(red)
@@ -411,6 +415,8 @@ def run_ours(args):
     ms_e2e_p, _ = timed(step_p, args.steps, w3, join=copy_stream)
     del step_p, bufs_p
     ms_fg, launches_fg = timed(fwd_grad, args.steps, max(1, args.warmup // 3))
+    ms_fg_dense, _ = timed(lambda: fwd_grad(dense=True), max(2, args.steps // 2), 1)
+    g_check = [fwd_grad(dense=d)[1:].double().cpu().numpy() for d in (False, True)]   # the two backward paths agree (reported below)
     clocks = sampler.stop() if sampler else None
     ms_skip = None
     if args.skip_garbage:
@@ -579,7 +585,8 @@ def run_ours(args):
         # row + the LUT window; backward = re-read of the segment records (31 words) + one read of every gradient row
         lut_window = 4 * L * (25 * 3 + (10 * NEIGH + 5) ** 2)
         b_seg = 104 + 4.0 * (n_unique + 1) * nticks / nseg + lut_window / nseg
-        b_seg_bwd = 4 * 31 + 4.0 * (n_unique + 1) * nticks / nseg + lut_window / nseg
+        # (steps form: 168 bytes of step events per pixel row instead of one read of the n_ticks-float gradient row)
+        b_seg_bwd = 4 * 31 + 168.0 * (n_unique + 1) / nseg + lut_window / nseg
         c_seg = (25 + (2 * NEIGH + 1) ** 2) * (2 * L + 2)
         achieved = b_seg * nseg / (k_ms[1] * 1e-3) / 1e9
         achieved_bwd = b_seg_bwd * nseg / (k_ms[2] * 1e-3) / 1e9
@@ -623,7 +630,13 @@ def run_ours(args):
                            "note": "host-chopped batch, the 10 columns the simulation reads (dataio.pack_columns, 40 B/segment)"},
             "fwd_grad": {"metric": "segments/s fwd+grad (LUT mode)", "value": seg_s(ms_fg), "unit": "segments/s",
                          "ms_per_step": ms_fg, "collective": "all_reduce(16 floats)" if world > 1 else "none",
-                         "gpu_launches": launches_fg},
+                         "gpu_launches": launches_fg,
+                         "backward": "sim.hits_backward: front-end VJP as <= 20 steps per pixel row, accumulate VJP from running-sum "
+                                     "differences (no dense waveform gradient)",
+                         "dense_gradient_path": {"value": seg_s(ms_fg_dense), "ms_per_step": ms_fg_dense,
+                                                 "backward": "sim.fee_backward + sim.lut_backward through the dense (npix, n_ticks) gradient"},
+                         "max_rel_diff_between_paths": float(np.max(np.abs(g_check[0] - g_check[1])[np.abs(g_check[1]) > 0] /
+                                                                    np.abs(g_check[1])[np.abs(g_check[1]) > 0]))},
             "gpu_launches": launches,  # kernels of liblarnd_b200.so launched inside the timed region of `value` (larnd_launch_count)
             "kernels_ms": {"k_prepare": k_ms[0], "k_lut_accumulate": k_ms[1], "k_lut_backward": k_ms[2], "k_fee_forward": k_ms[3]},
             "roofline": {"kernel": "k_acc_tiles (class-sorted lut_accumulate: run sort + the 4- and 6-position tile kernels + row-0 reduction)",
@@ -633,7 +646,7 @@ def run_ours(args):
                                  "(SURVEY §8d): see l2_red, contributions/s and DESIGN.md §4",
                          "l2_red": l2_red,
                          "contributions_per_s": c_seg * nseg / (k_ms[1] * 1e-3),
-                         "backward": {"kernel": "k_bwd_tiles (class-sorted VJP of lut_accumulate + chain rule)", "bound": "hbm",
+                         "backward": {"kernel": "k_bwd_tiles<steps> (class-sorted VJP of lut_accumulate from the front end's step events + chain rule)", "bound": "hbm",
                                       "achieved": achieved_bwd, "peak": peak, "unit": "GB/s", "frac": achieved_bwd / peak,
                                       "traffic": traffic_bwd, "algorithmic_bytes_per_segment": b_seg_bwd},
                          # the two streaming kernels of the step, which ARE HBM-bound (algorithmic bytes / measured time):

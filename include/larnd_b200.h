@@ -200,6 +200,20 @@ int larnd_lut_backward(int64_t n_segments, const larnd_params_t* params, const l
                        size_t workspace_bytes, const int32_t* counts_d, const float* g_wfs_d, int64_t g_row_stride,
                        float* grad_params_d, void* stream);
 
+/* The two VJPs above chained WITHOUT the dense waveform gradient.  The VJP of get_adc_values is a step function of the tick
+ * (at most 2 * MAX_ADC_VALUES steps per pixel row: a hit's integral reaches back to the previous subtraction), so
+ * larnd_fee_backward_steps emits the (last column, coefficient) list of every row — 168 bytes instead of n_ticks floats —
+ * and larnd_lut_backward_steps turns every correlation sum_k g[t + k] R[k] into differences of the response's running sum at
+ * the step positions.  Same gradients as larnd_fee_backward + larnd_lut_backward (rows of pixel ids < 0 carry no gradient, as
+ * for every loss built on parse_output's hits); the 2 GB gradient array of a spill-sized batch is neither written nor read.
+ * steps_d: larnd_fee_steps_bytes(npix) bytes, npix = the npix_capacity of the forward call. */
+size_t larnd_fee_steps_bytes(int32_t npix);
+int larnd_fee_backward_steps(const float* g_adc_d, const float* saved_d, const int32_t* unique_pixels_d, int32_t npix,
+                             const larnd_params_t* params, void* steps_d, size_t steps_bytes, int32_t raw_charge, void* stream);
+int larnd_lut_backward_steps(int64_t n_segments, const larnd_params_t* params, const larnd_lut_t* lut, int32_t n_events,
+                             int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                             const int32_t* counts_d, const void* steps_d, size_t steps_bytes, float* grad_params_d, void* stream);
+
 /* simulate_stochastic on (npix, n_ticks-1) waveforms (row stride wfs_row_stride floats, first column =
  * reference tick index 0 of wfs[:,1:]).  noise_d: NULL (noise-free) or standard normals laid out as
  * [base(npix) | extra(10,npix) | pass(10,npix) | fail(10,npix)].

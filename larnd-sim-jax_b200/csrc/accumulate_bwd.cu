@@ -45,6 +45,8 @@ struct BwdArgs {
   float* partials;
   int skip_garbage;
   const int* garbage_grad_nonzero;  // device flag written by k_garbage_grad_flag
+  StepsView steps;   // compact upstream gradient (larnd_fee_backward_steps) used instead of g when use_steps != 0
+  int use_steps;
   int sorted_active;  // the class-sorted kernel (accumulate_bwd_sorted.cu) runs too and takes every segment it can handle
 };
 
@@ -104,13 +106,31 @@ __device__ __forceinline__ float reduce8_to_lane(const float (&v)[8], int lane) 
   return __shfl_sync(0xffffffffu, y, (lane & 7) * 4);
 }
 
+// One row of the upstream gradient: either a pointer into the dense (npix, n_ticks) array or the row's step events
+// (larnd_fee_backward_steps), from which any column is synthesised in registers — no gradient traffic at all.
+struct GRow {
+  const float* grow;
+  RowSteps ev;
+  bool steps;
+  __device__ __forceinline__ void open(const BwdArgs& A, int row, int lane) {
+    steps = A.use_steps != 0;
+    if (steps) { ev.load(A.steps, row, lane); ev.fix(lane); }
+    else grow = A.g + (int64_t)row * A.g_stride;
+  }
+  // value at this lane's column (warp-collective in the steps form); `ok` masks lanes whose column must read as zero
+  __device__ __forceinline__ float at(int col, bool ok) const {
+    if (steps) { const float v = ev.value(col); return ok ? v : 0.0f; }
+    return ok ? __ldg(grow + col) : 0.0f;
+  }
+};
+
 // gradient window registers: gr[i] = g[row, tmin + lane + 32 i]; ticks beyond the readout read as zero
 template <int NG>
-__device__ __forceinline__ void load_gwin(float (&gr)[NG], const float* grow, int tmin, int nticks, int lane) {
+__device__ __forceinline__ void load_gwin(float (&gr)[NG], const GRow& G, int tmin, int nticks, int lane) {
 #pragma unroll
   for (int i = 0; i < NG; ++i) {
     const int col = tmin + lane + 32 * i;
-    gr[i] = (col <= nticks - 1) ? __ldg(grow + col) : 0.0f;
+    gr[i] = G.at(col, col <= nticks - 1);
   }
 }
 
@@ -136,15 +156,17 @@ __device__ __forceinline__ float correlate(const float (&gr)[NG], const float* r
 
 // per-segment (slow path, runs touching the ends of the readout): lane-partial sums of one (segment, row) pair.
 template <int NR>
-__device__ __forceinline__ void slow_sums(const float* grow, const float* const (&rows)[NR], int T0, int L, int nticks, int lane,
+__device__ __forceinline__ void slow_sums(const GRow& G, const float* const (&rows)[NR], int T0, int L, int nticks, int lane,
                                           float (&G0)[NR], float (&G1)[NR], float& gB, float& gA) {
 #pragma unroll
   for (int r = 0; r < NR; ++r) { G0[r] = 0.f; G1[r] = 0.f; }
   gB = 0.f; gA = 0.f;
-  for (int x = -1 + lane; x <= L; x += 32) {
+  for (int x0 = -1; x0 <= L; x0 += 32) {   // warp-uniform trip count (the steps form of G.at is warp-collective)
+    const int x = x0 + lane;
     const int col = T0 + x;
-    const bool inb = col >= 1 && col <= nticks - 1;
-    const float gv = inb ? __ldg(grow + col) : 0.0f;
+    const bool inb = x <= L && col >= 1 && col <= nticks - 1;
+    const float gv = G.at(col, inb);
+    if (x > L) continue;
     const float gw = (col >= 2) ? gv : 0.0f;               // window deposits are valid for ticks 2 .. nticks-1
     const float gc = (col <= nticks - 2) ? gv : 0.0f;      // boundary deposits are valid for ticks 1 .. nticks-2
 #pragma unroll
@@ -347,7 +369,8 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
 #pragma unroll
         for (int j = 0; j < 5; ++j) gwy += (my >> j & 1) ? sm.wy[j][tl] : 0.f;
         const float w = gwx * gwy;
-        const float* grow = A.g + (int64_t)row * A.g_stride;
+        GRow grow;
+        grow.open(A, row, lane);
         const int bin = cix * 5 + ciy;
         const float* ra = A.rm + (int64_t)((idx - 1) * 25 + bin) * A.Lp;
         const float* rb = A.rm + (int64_t)(idx * 25 + bin) * A.Lp;
@@ -360,7 +383,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
           const float Gla = correlate<NG>(gr, ra, npos, L, lane);
           const float Glb = correlate<NG>(gr, rb, npos, L, lane);
           const float Glc = correlate<NG>(gr, rc, npos, L, lane);
-          const float gC = __ldg(grow + R.tmin - 1 + min(lane, npos));
+          const float gC = grow.at(R.tmin - 1 + min(lane, npos), true);
           const float Cav = __ldg(crow + ctl), Cbv = __ldg(crow + ctl1), Cl = __ldg(crow + nt - L);
           const float a0 = __shfl_sync(0xffffffffu, Gla, m), a1 = __shfl_sync(0xffffffffu, Gla, m + 1);
           const float b0 = __shfl_sync(0xffffffffu, Glb, m), b1 = __shfl_sync(0xffffffffu, Glb, m + 1);
@@ -426,7 +449,8 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         if (skip_garbage && garbage) continue;
         row = raw < 0 ? 0 : (raw & ~(1 << 30));               // absent / centre -> waveform row 0 (sim_jax.py:724-725)
       }
-      const float* grow = A.g + (int64_t)row * A.g_stride;
+      GRow grow;
+      grow.open(A, row, lane);
       const int ci = abs(2 * bxm - A.half2 - 2 * nb * dx) >> 1, cj = abs(2 * bym - A.half2 - 2 * nb * dy) >> 1;
       const int bin = ci * A.ny_lut + cj;
       const float* rowp = A.r0 + (int64_t)bin * A.Lp;
@@ -435,7 +459,7 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
         float gr[NG];
         load_gwin<NG>(gr, grow, R.tmin, A.nticks, lane);
         const float Gl = correlate<NG>(gr, rowp, npos, L, lane);
-        const float gC = __ldg(grow + R.tmin - 1 + min(lane, npos));       // tick tmin - 1 + lane
+        const float gC = grow.at(R.tmin - 1 + min(lane, npos), true);       // tick tmin - 1 + lane
         const float Cav = __ldg(crow + ctl), Cbv = __ldg(crow + ctl1), Cl = __ldg(crow + nt - L);
         const float G0 = __shfl_sync(0xffffffffu, Gl, m), G1 = __shfl_sync(0xffffffffu, Gl, m + 1);
         const float gB = __shfl_sync(0xffffffffu, gC, m), gA = __shfl_sync(0xffffffffu, gC, m + 1);
@@ -520,7 +544,7 @@ int launch_bwd(const BwdArgs& A, const larnd_params_t& p, int64_t chunks, cudaSt
 
 int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                 int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride,
-                                float* grad_params, const int32_t* counts, cudaStream_t st) {
+                                float* grad_params, const int32_t* counts, cudaStream_t st, const StepsView* steps) {
   if (n == 0) return LARND_OK;
   if (p.number_pix_neighbors > 7) { larnd_set_error("number_pix_neighbors > 7 unsupported"); return LARND_E_ARG; }
   BwdArgs A;
@@ -542,8 +566,15 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   const int64_t chunks = (n + S - 1) / S;
   int* gflag = reinterpret_cast<int*>(ws.partials + (size_t)ws.n_chunks_max * 16) - 4;  // last 16 bytes of the partials area
   LARND_CUDA(cudaMemsetAsync(gflag, 0, sizeof(int), st));
-  k_garbage_grad_flag<<<32, 256, 0, st>>>(g_wfs, g_stride, p.n_ticks, counts, gflag);
-  LARND_LAUNCH_CHECK("k_garbage_grad_flag");
+  A.use_steps = steps ? 1 : 0;
+  if (steps) {
+    A.steps = *steps;          // rows of pixel ids < 0 carry no event by construction: the garbage flag stays 0
+    A.skip_garbage = 1;
+  } else {
+    A.steps = StepsView{nullptr};
+    k_garbage_grad_flag<<<32, 256, 0, st>>>(g_wfs, g_stride, p.n_ticks, counts, gflag);
+    LARND_LAUNCH_CHECK("k_garbage_grad_flag");
+  }
   A.garbage_grad_nonzero = gflag;
   // large batches: the class-sorted kernel (accumulate_bwd_sorted.cu) does the bulk.  LARND_FLAG_IMPL_CHUNK / _SORTED
   // override the size rule (the tests force both paths on small batches).
@@ -551,14 +582,15 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   if (flags & LARND_FLAG_IMPL_SORTED) sorted = larnd_sorted_supported(p, lut) != 0;
   if (flags & LARND_FLAG_IMPL_CHUNK) sorted = false;
   // (the tile kernel addresses the gradient rows with signed 32-bit element offsets)
-  if ((int64_t)npix_capacity * g_stride >= ((int64_t)1 << 31)) sorted = false;
+  if (!steps && (int64_t)npix_capacity * g_stride >= ((int64_t)1 << 31)) sorted = false;
+  if (steps && lut->nt - lut->L < 1) sorted = false;   // the running-sum form needs one sample in front of the response window
   A.sorted_active = sorted ? 1 : 0;
   prof_begin(2, st);
   if (sorted) {
     float* sorted_partials = ws.partials + (size_t)ws.n_chunks_max * 16;
     int n_slots = 0;
     int rc0 = larnd_launch_accumulate_bwd_sorted(n, p, lut, ws, npix_capacity, flags, g_wfs, g_stride, sorted_partials, &n_slots,
-                                                 gflag, counts, st);
+                                                 gflag, counts, st, steps);
     if (rc0) return rc0;
     k_reduce_partials<<<LARND_NPARAMS, 256, 0, st>>>(sorted_partials, n_slots, grad_params);
     LARND_LAUNCH_CHECK("k_reduce_partials");

@@ -35,6 +35,7 @@ struct BwdSortArgs {
   float* partials;   // [gridDim][16]
   int force_skip;    // caller promises zero gradients on garbage rows
   const int* garbage_grad_nonzero;
+  StepsView steps;   // compact upstream gradient (STEPS kernels): g / g_stride are unused then
 };
 
 constexpr int BSLOTS = 32 / MAXLEN;  // runs whose segments are processed together (lanes <-> (slot, segment))
@@ -42,6 +43,8 @@ struct PairSlots {
   float G[BSLOTS][GSB];        // G[NR*j + r] of the run parked in the slot
   float gpos[BSLOTS][KPT + 2]; // upstream gradient at ticks tmin - 1 + j
   int p[BSLOTS];
+  int evp[BSLOTS][LARND_STEPS_MAX];    // STEPS kernels: step events of the slot's target row (position -1 / value 0 beyond the count)
+  float evv[BSLOTS][LARND_STEPS_MAX];
 };
 
 struct BwdTileSmem {
@@ -230,6 +233,133 @@ __device__ __forceinline__ void unit_pairs(BwdTileSmem& sm, const BwdSortArgs& A
   }
 }
 
+// The same (unit, runs) work when the upstream gradient is the front end's step function (StepsView): the correlation
+//       G_r[j] = sum_k g[row, tmin + j + k] R_r[k]          (k = sample of the L-sample response window)
+// with g[col] = sum_{e: pos_e >= col} val_e collapses to one difference of the response's RUNNING SUM per event,
+//       G_r[j] = sum_e val_e (C_r[min(khi, pos_e - tmin - j)] - C_r[klo - 1]),      C_r = cumulative response (lut cm / c0),
+// so lane <-> (j, r) owns its G entry outright: no gradient loads, no FFMA sweep over the window, no butterfly reduction,
+// no register-resident response.  klo / khi carry the readout limits (window deposits live on columns 2 .. n_ticks - 1).
+template <int NR>
+__device__ __forceinline__ void unit_pairs_steps(BwdTileSmem& sm, const BwdSortArgs& A, const float* const (&crows)[NR], unsigned todo, int row,
+                                                 const float* __restrict__ crow, int gi, int gj, int lane, int warp, int npos) {
+  const SortArgs& S = A.S;
+  const int nt = S.nt, L = S.L, nticks = S.nticks, ntL = nt - L;
+  const float Cl = __ldg(crow + ntL);
+  PairSlots& ps = sm.ps[warp];
+  const int V = NR * npos;
+  // crr[k] below = running sum up to sample k of the response window, crr[-1] = everything before it
+  // Several runs share the warp: a run needs V = NR * npos lanes for its G entries (and npos + 1 <= KPT + 1 lanes for the
+  // boundary-deposit columns), so a main unit (NR = 3, V <= 15 for npos <= 5) takes a half warp and a neighbour unit (NR = 1)
+  // a quarter; the events of the parked runs sit in shared memory and are read as broadcasts.
+  constexpr int LPR = (NR == 3) ? 16 : 8, RPP = 32 / LPR;
+  const bool narrow = V <= LPR;                  // warp-uniform (npos = 6 main units use the whole warp per run)
+  const int sub = narrow ? lane / LPR : 0, ll = narrow ? lane % LPR : lane;
+  const int jj = (NR == 3) ? ll / 3 : ll, rr = (NR == 3) ? ll - 3 * jj : 0;
+  const float* crr = crows[0];
+  if (NR == 3) crr = (rr == 0) ? crows[0] : ((rr == 1) ? crows[NR - 2] : crows[NR - 1]);
+  crr += ntL;
+  const bool mine2 = ll < V;
+  const float cbase2 = mine2 ? __ldg(crr - 1) : 0.0f;
+  while (todo) {
+    // up to BSLOTS runs per pass: all event records are requested first (independent loads), staged, then consumed
+    int nslot = 0;
+    int nev[BSLOTS];
+    {
+      int pr[BSLOTS];
+      RowSteps ev[BSLOTS];
+#pragma unroll
+      for (int s = 0; s < BSLOTS; ++s) {
+        pr[s] = -1;
+        nev[s] = 0;
+        if (todo) {
+          pr[s] = __ffs(todo) - 1;
+          todo &= todo - 1;
+          ev[s].load(A.steps, __shfl_sync(0xffffffffu, row, pr[s]), lane);
+          nslot = s + 1;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < BSLOTS; ++s) {
+        if (s < nslot) {
+          ev[s].fix(lane);
+          nev[s] = ev[s].n;
+          if (lane < LARND_STEPS_MAX) { ps.evp[s][lane] = ev[s].pos; ps.evv[s][lane] = ev[s].val; }
+          if (lane == 0) ps.p[s] = pr[s];
+        }
+      }
+    }
+    __syncwarp();
+    const int npass = narrow ? (nslot + RPP - 1) / RPP : nslot;
+    for (int pass = 0; pass < npass; ++pass) {
+      const int s = narrow ? pass * RPP + sub : pass;
+      const bool act = s < nslot;
+      const int sx = act ? s : 0;
+      int nemax = 0;
+#pragma unroll
+      for (int k = 0; k < BSLOTS; ++k)
+        if (narrow ? (k / RPP == pass) : (k == pass)) nemax = max(nemax, nev[k]);
+      const int tmin = sm.run[ps.p[sx]].z;
+      const int klo = max(0, 2 - tmin - jj), kcap = min(L - 1, nticks - 1 - tmin - jj);
+      const float clo = (klo > 0 && mine2) ? __ldg(crr + klo - 1) : cbase2;
+      const int colp = tmin - 1 + ll;            // ll <-> position: gradient at column tmin - 1 + ll (boundary deposits)
+      const bool colok = colp >= 1 && colp <= nticks - 1 && ll <= KPT;
+      const int base = tmin + jj;
+      float acc = 0.0f, gp = 0.0f;
+      const int* evp = ps.evp[sx];
+      const float* evv = ps.evv[sx];
+#pragma unroll 2
+      for (int e = 0; e < nemax; ++e) {
+        const int pe = evp[e];
+        const float ve = evv[e];
+        const int khi = min(kcap, pe - base);
+        if (mine2 && khi >= klo) acc = fmaf(ve, __ldg(crr + khi) - clo, acc);
+        gp += (colok && pe >= colp) ? ve : 0.0f;
+      }
+      if (act && mine2) ps.G[s][ll] = acc;       // G[NR * j + r]
+      if (act && ll <= KPT) ps.gpos[s][ll] = gp;
+    }
+    __syncwarp();
+    const int slot = lane >> 3, t = lane & 7;
+    if (slot < nslot) {
+      const int p = ps.p[slot];
+      const int len = sm.run[p].y & 0xffff;
+      const int i = sm.soff[p] + t;
+      const int m = t < len ? sm.m[i] : INT32_MIN;
+      if (m != INT32_MIN) {
+        const float* Gs = ps.G[slot];
+        const float gB = ps.gpos[slot][m], gA = ps.gpos[slot][m + 1];
+        int ct = nt - L - (sm.run[p].z + m);
+        ct = max(0, min(ct, nt - 1));
+        const float Ca = __ldg(crow + ct), Cb = __ldg(crow + min(ct + 1, nt - 1));
+        const float q = sm.q[i], f = sm.f[i], omf = 1.0f - f;
+        const float D = Cl - (Ca * omf + Cb * f), dD = -(Cb - Ca);
+        const float gm = fmaf(f, gB, omf * gA);
+        if (NR == 3) {
+          const float a0 = Gs[3 * m], b0 = Gs[3 * m + 1], c0v = Gs[3 * m + 2], a1 = Gs[3 * m + 3], b1 = Gs[3 * m + 4], c1v = Gs[3 * m + 5];
+          const float ca_ = sm.ca[i], cb_ = sm.cb[i], cc_ = sm.cc[i];
+          const float gwx = sm.wxg[gi][i], gwy = sm.wyg[gj][i];
+          const float Sa = fmaf(f, a0, omf * a1), Sb = fmaf(f, b0, omf * b1), Sc = fmaf(f, c0v, omf * c1v);
+          const float Pv = fmaf(ca_, Sa, fmaf(cb_, Sb, cc_ * Sc)) + gm * D;
+          const float Fd = fmaf(ca_, a0 - a1, fmaf(cb_, b0 - b1, cc_ * (c0v - c1v))) + (gB - gA) * D + gm * dD;
+          const float w = gwx * gwy, qb = w * q;
+          atomicAdd(&sm.acc[0][i], w * Pv);
+          atomicAdd(&sm.acc[1][i], qb * Fd);
+          atomicAdd(&sm.acc[2][i], qb * Sa);
+          atomicAdd(&sm.acc[3][i], qb * Sb);
+          atomicAdd(&sm.acc[4][i], qb * Sc);
+          atomicAdd(&sm.acc[5 + gi][i], gwy * q * Pv);
+          atomicAdd(&sm.acc[10 + gj][i], gwx * q * Pv);
+        } else {
+          const float G0 = Gs[m], G1 = Gs[m + 1];
+          atomicAdd(&sm.acc[0][i], fmaf(f, G0, omf * G1) + gm * D);
+          atomicAdd(&sm.acc[1][i], q * ((G0 - G1) + (gB - gA) * D + gm * dD));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int NS, int NR, int KP>  // [region: dispatch]
 __device__ __forceinline__ void unit_pairs_npos(BwdTileSmem& sm, const BwdSortArgs& A, const float (&Rw)[3][NS][KP], unsigned todo, int row,
                                                 const float* crow, int gi, int gj, int lane, int warp, int npos) {
@@ -256,8 +386,8 @@ __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const fl
 
 // KP / span range / launch as in k_acc_tiles: the variants holding 3 / 4 response positions (36 / 48 registers, 4 / 3 CTAs
 // per SM) serve the tiles of runs with few impulse positions, the KP = KPT kernel the rest (or everything).
-template <int NS, int KP>  // [region: kernel prologue]
-__global__ void __launch_bounds__(BT_THREADS, NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1))
+template <int NS, int KP, bool STEPS = false>  // [region: kernel prologue]
+__global__ void __launch_bounds__(BT_THREADS, STEPS ? 3 : (NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1)))
 k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int span_lo, const int span_hi,
             const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,7 +397,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
 #define GACC(k) sm.gl[k][threadIdx.x]
 #pragma unroll
   for (int k = 0; k < LARND_NPARAMS; ++k) GACC(k) = 0.0f;
-  const bool garbage_needed = !A.force_skip && (*A.garbage_grad_nonzero != 0);
+  const bool garbage_needed = !STEPS && !A.force_skip && (*A.garbage_grad_nonzero != 0);
   const bool dead = S.counts[2] != 0 || garbage_needed;  // accumulate_bwd.cu's kernel takes over
   const int nb = S.nb;
   const int64_t n = S.n;
@@ -309,7 +439,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         sm.mpy[lane] = floordiv_i(irec[(int64_t)LARND_I_BY * n + s0], nb);
         len = e.y & 0xffff;
       }
-      const unsigned low = __ballot_sync(0xffffffffu, lane < count && (sm.run[lane].z < 2 || sm.run[lane].z - 2 + 32 * NS >= S.nticks));
+      const unsigned low = STEPS ? 0u : __ballot_sync(0xffffffffu, lane < count && (sm.run[lane].z < 2 || sm.run[lane].z - 2 + 32 * NS >= S.nticks));
       if (lane == 0) sm.low_end = low != 0u;
       int inc = len;
 #pragma unroll
@@ -363,7 +493,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
       if (lane == 0) unit = atomicAdd(&sm.next_unit, 1);
       unit = __shfl_sync(0xffffffffu, unit, 0);
       if (unit >= n_units) break;
-      float Rw[3][NS][KP];
+      float Rw[STEPS ? 1 : 3][STEPS ? 1 : NS][STEPS ? 1 : KP];
       if (unit < 25) {  // [region: main unit setup]
         // ---------------- merged diffusion-bin group (gi, gj): 3-template blend on a main pixel ----------------
         const int gi = unit / LARND_NB_TRAN_BINS, gj = unit % LARND_NB_TRAN_BINS;
@@ -378,10 +508,16 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         }
         const unsigned todo = __ballot_sync(0xffffffffu, row >= 0);
         if (todo == 0u) continue;
-        const float* const rows[3] = {S.rm + (int64_t)((idx - 1) * 25 + bin) * S.Lp, S.rm + (int64_t)(idx * 25 + bin) * S.Lp,
-                                      S.rm + (int64_t)((idx + 1) * 25 + bin) * S.Lp};
-        load_response_b<NS, 3, KP>(Rw, rows, S.Lp, lane);
-        unit_pairs_npos<NS, 3, KP>(sm, A, Rw, todo, row, S.cm + (int64_t)(idx * 25 + bin) * S.nt, gi, gj, lane, warp, npos);
+        if constexpr (STEPS) {
+          const float* const crows[3] = {S.cm + (int64_t)((idx - 1) * 25 + bin) * S.nt, S.cm + (int64_t)(idx * 25 + bin) * S.nt,
+                                         S.cm + (int64_t)((idx + 1) * 25 + bin) * S.nt};
+          unit_pairs_steps<3>(sm, A, crows, todo, row, crows[1], gi, gj, lane, warp, npos);
+        } else {
+          const float* const rows[3] = {S.rm + (int64_t)((idx - 1) * 25 + bin) * S.Lp, S.rm + (int64_t)(idx * 25 + bin) * S.Lp,
+                                        S.rm + (int64_t)((idx + 1) * 25 + bin) * S.Lp};
+          load_response_b<NS, 3, KP>(Rw, rows, S.Lp, lane);
+          unit_pairs_npos<NS, 3, KP>(sm, A, Rw, todo, row, S.cm + (int64_t)(idx * 25 + bin) * S.nt, gi, gj, lane, warp, npos);
+        }
       } else {  // [region: neigh unit setup]
         // ---------------- neighbour pixels that own a non-garbage waveform row: template 0, full charge -----------
         const int u = unit - 25;
@@ -397,9 +533,14 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
         if (todo == 0u) continue;
         const int vx = 2 * bxm - S.half2 - 2 * nb * dx, vy = 2 * bym - S.half2 - 2 * nb * dy;
         const int bin = (abs(vx) >> 1) * S.ny_lut + (abs(vy) >> 1);
-        const float* const rows[1] = {S.r0 + (int64_t)bin * S.Lp};
-        load_response_b<NS, 1, KP>(Rw, rows, S.Lp, lane);
-        unit_pairs_npos<NS, 1, KP>(sm, A, Rw, todo, row, S.c0 + (int64_t)bin * S.nt, 0, 0, lane, warp, npos);
+        if constexpr (STEPS) {
+          const float* const crows[1] = {S.c0 + (int64_t)bin * S.nt};
+          unit_pairs_steps<1>(sm, A, crows, todo, row, crows[0], 0, 0, lane, warp, npos);
+        } else {
+          const float* const rows[1] = {S.r0 + (int64_t)bin * S.Lp};
+          load_response_b<NS, 1, KP>(Rw, rows, S.Lp, lane);
+          unit_pairs_npos<NS, 1, KP>(sm, A, Rw, todo, row, S.c0 + (int64_t)bin * S.nt, 0, 0, lane, warp, npos);
+        }
       }
     }
     __syncthreads();  // [region: chain rule]
@@ -442,10 +583,31 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
 int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                        int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride,
                                        float* sorted_partials, int* n_slots_out, const int* gflag, const int32_t* counts,
-                                       cudaStream_t st) {
+                                       cudaStream_t st, const StepsView* steps) {
   BwdSortArgs A;
   int rc = sorted_fill_and_build(A.S, n, p, lut, ws, npix_capacity, counts, st);
   if (rc) return rc;
+  if (steps) {
+    // compact upstream gradient: one kernel for every tick span (no register-resident response, so no KP variants)
+    A.S.wfs = nullptr;
+    A.S.skip_garbage = 1;
+    A.g = nullptr; A.g_stride = 0;
+    A.partials = sorted_partials;
+    A.force_skip = 1;
+    A.garbage_grad_nonzero = gflag;
+    A.steps = *steps;
+    const size_t smem_s = sizeof(BwdTileSmem);
+    static bool attr_steps = false;
+    if (!attr_steps) {
+      LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+      attr_steps = true;
+    }
+    const int grid = sorted_grid(3, LARND_BWD_SORTED_SLOTS);
+    k_bwd_tiles<4, 2, true><<<grid, BT_THREADS, smem_s, st>>>(A, p, 0, SPAN_MAX_S, 2);
+    LARND_LAUNCH_CHECK("k_bwd_tiles<steps>");
+    *n_slots_out = grid;
+    return LARND_OK;
+  }
   A.S.wfs = nullptr;
   A.S.skip_garbage = 1;
   A.g = g_wfs; A.g_stride = g_stride;

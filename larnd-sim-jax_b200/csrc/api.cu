@@ -218,3 +218,24 @@ extern "C" int larnd_lut_backward(int64_t n, const larnd_params_t* p, const larn
   return larnd_launch_accumulate_bwd(n, *p, lut, ws, npix_capacity, flags & LARND_FLAG_PUBLIC_MASK, g_wfs_d, g_row_stride, grad_params_d,
                                      counts_d, (cudaStream_t)stream);
 }
+
+extern "C" int larnd_lut_backward_steps(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
+                                        int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
+                                        const int32_t* counts_d, const void* steps_d, size_t steps_bytes, float* grad_params_d,
+                                        void* stream) {
+  int rc = check_common(p, lut, true);
+  if (rc) return rc;
+  if (!steps_d || !grad_params_d || !counts_d || steps_bytes < larnd_steps_layout(npix_capacity, nullptr, nullptr)) {
+    larnd_set_error("larnd_lut_backward_steps: null argument or steps buffer smaller than larnd_fee_steps_bytes(npix_capacity)");
+    return LARND_E_ARG;
+  }
+  Workspace ws;
+  if (!larnd_carve_workspace(workspace_d, workspace_bytes, n, n_events, p->n_tpc, p->n_pixels_x, p->n_pixels_y, &ws)) {
+    larnd_set_error("workspace too small");
+    return LARND_E_CAPACITY;
+  }
+  StepsView v;
+  larnd_steps_layout(npix_capacity, const_cast<void*>(steps_d), &v);
+  return larnd_launch_accumulate_bwd(n, *p, lut, ws, npix_capacity, (flags & LARND_FLAG_PUBLIC_MASK) | 1, nullptr, 0, grad_params_d, counts_d,
+                                     (cudaStream_t)stream, &v);
+}

@@ -447,7 +447,62 @@ k_fee_backward(const float* __restrict__ g_adc, const float* __restrict__ saved,
   }
 }
 
+// The same VJP as k_fee_backward in its COMPACT form: the (position, coefficient) list itself, consumed directly by
+// larnd_lut_backward_steps — the dense (npix, n_ticks) gradient (2 GB at spill size) is never written or read.
+// thread <-> row; events with a zero coefficient are dropped; rows of pixel ids < 0 get no event (parse_output drops
+// their hits, sim_jax.py:621, so no loss built on hits reaches them).
+__global__ void __launch_bounds__(128)
+k_fee_backward_steps(const float* __restrict__ g_adc, const float* __restrict__ saved, const int32_t* __restrict__ unique_pixels,
+                     int npix, int ntw, const __grid_constant__ larnd_params_t p, int32_t* __restrict__ rec, const int raw_charge) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= npix) return;
+  const int nmax = p.max_adc_values;
+  const float* sv = saved + (int64_t)row * 32;
+  const unsigned hit_mask = (unsigned)__float_as_int(sv[10]);
+  int count = 0;
+  if (hit_mask != 0u && unique_pixels[row] >= 0) {
+    const unsigned spos_mask = (unsigned)__float_as_int(sv[11]);
+    const unsigned slope_mask = (unsigned)__float_as_int(sv[12]);
+    const float slope = p.gain * p.adc_counts / p.v_ref_minus_cm;
+    int32_t* pos = rec + (int64_t)row * LARND_STEPS_WORDS;
+    float* val = reinterpret_cast<float*>(pos + LARND_STEPS_MAX);
+    float tail = 0.0f;   // sum_{k' > k} T_k' (same recursion and order as k_fee_backward)
+    for (int k = nmax - 1; k >= 0; --k) {
+      const int idx_t = (int)sv[k];
+      int e = idx_t + 1 + p.hold_interval; if (e >= ntw) e = ntw - 1;
+      int e2 = idx_t + 2 + p.hold_interval; if (e2 >= ntw) e2 = ntw - 1;
+      const bool live = ((hit_mask >> k) & 1u) && (raw_charge || ((slope_mask >> k) & 1u));
+      const float gk = live ? g_adc[(int64_t)row * nmax + k] * (raw_charge ? 1.0f : slope) : 0.0f;
+      const float sbar = ((spos_mask >> k) & 1u) ? -tail : 0.0f;
+      // full-row column of FEE tick t is t + 1 (simulate_wfs returns wfs[:, 1:])
+      if (sbar != 0.0f) { pos[count] = e2 + 1; val[count] = sbar * p.t_sampling; ++count; }
+      if (gk != 0.0f) { pos[count] = e + 1; val[count] = gk * p.t_sampling; ++count; }
+      tail += gk + sbar;
+    }
+  }
+  rec[(int64_t)row * LARND_STEPS_WORDS + 2 * LARND_STEPS_MAX] = count;
+}
+
 }  // namespace
+
+extern "C" size_t larnd_fee_steps_bytes(int32_t npix) { return larnd_steps_layout(npix > 0 ? npix : 0, nullptr, nullptr); }
+
+extern "C" int larnd_fee_backward_steps(const float* g_adc_d, const float* saved_d, const int32_t* unique_pixels_d, int32_t npix,
+                                        const larnd_params_t* params, void* steps_d, size_t steps_bytes, int32_t raw_charge,
+                                        void* stream) {
+  if (!g_adc_d || !saved_d || !unique_pixels_d || !params || !steps_d || npix < 0 || steps_bytes < larnd_fee_steps_bytes(npix)) {
+    larnd_set_error("larnd_fee_backward_steps: null argument or steps buffer smaller than larnd_fee_steps_bytes()");
+    return LARND_E_ARG;
+  }
+  if (params->max_adc_values > LARND_MAX_ADC) { larnd_set_error("MAX_ADC_VALUES > %d unsupported", LARND_MAX_ADC); return LARND_E_ARG; }
+  if (npix == 0) return LARND_OK;
+  StepsView v;
+  larnd_steps_layout(npix, steps_d, &v);
+  k_fee_backward_steps<<<(npix + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      g_adc_d, saved_d, unique_pixels_d, npix, params->n_ticks - 1, *params, const_cast<int32_t*>(v.rec), raw_charge != 0);
+  LARND_LAUNCH_CHECK("k_fee_backward_steps");
+  return LARND_OK;
+}
 
 extern "C" size_t larnd_fee_scratch_bytes(int32_t npix) { return align_up((size_t)npix * 2 * sizeof(int32_t) + 64, 256); }
 

@@ -70,6 +70,49 @@ int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Compact upstream gradient of the waveforms when it comes from the front end (larnd_fee_backward_steps): for every waveform
+// row the VJP of get_adc_values is a step function of the tick, dL/dwfs_full[row, col] = sum over the row's events e with
+// pos[e] >= col of val[e] (col >= 1; zero for col 0), with at most 2 * MAX_ADC_VALUES events (fee.cu).  168 bytes per row
+// instead of n_ticks floats.
+constexpr int LARND_STEPS_MAX = 2 * LARND_MAX_ADC;
+constexpr int LARND_STEPS_WORDS = 48;   // one 192-byte record per row: pos[0..19] | val[20..39] | n[40] | padding
+struct StepsView {
+  const int32_t* rec;   // [npix][LARND_STEPS_WORDS]
+};
+inline size_t larnd_steps_layout(int32_t npix, void* base, StepsView* v) {
+  if (v) v->rec = reinterpret_cast<const int32_t*>(base);
+  return align_up((size_t)npix * LARND_STEPS_WORDS * sizeof(int32_t), 256);
+}
+#ifdef __CUDACC__
+// The events of one row spread over the lanes of a warp (lane e <-> event e); value(col) is a warp-collective call.
+struct RowSteps {
+  int n, pos;
+  float val;
+  // three independent loads (one record, two cache lines): issue them for several rows before using any (fix())
+  __device__ __forceinline__ void load(const StepsView& s, int row, int lane) {
+    const int32_t* r = s.rec + (int64_t)row * LARND_STEPS_WORDS;
+    const int l = min(lane, LARND_STEPS_MAX - 1);
+    n = __ldg(r + 2 * LARND_STEPS_MAX);
+    pos = __ldg(r + l);
+    val = __int_as_float(__ldg(r + LARND_STEPS_MAX + l));
+  }
+  __device__ __forceinline__ void fix(int lane) {
+    if (lane >= n) { pos = -1; val = 0.0f; }
+  }
+  // dL/dwfs_full[row, col] for this lane's col (every lane of the warp must call)
+  __device__ __forceinline__ float value(int col) const {
+    float g = 0.0f;
+    for (int e = 0; e < n; ++e) {
+      const int pe = __shfl_sync(0xffffffffu, pos, e);
+      const float ve = __shfl_sync(0xffffffffu, val, e);
+      g += (pe >= col && col >= 1) ? ve : 0.0f;
+    }
+    return g;
+  }
+};
+#endif
+
+
 bool larnd_carve_workspace(void* base, size_t bytes, int64_t n, int32_t n_events, int32_t ntpc, int32_t nx,
                            int32_t ny, Workspace* ws);
 void larnd_set_error(const char* fmt, ...);
@@ -169,7 +212,7 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
 int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                        int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride,
                                        float* sorted_partials, int* n_slots_out, const int* gflag, const int32_t* counts,
-                                       cudaStream_t st);
+                                       cudaStream_t st, const StepsView* steps = nullptr);
 int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
                                 int32_t npix_capacity, int32_t flags, const float* g_wfs, int64_t g_stride, float* grad_params,
-                                const int32_t* counts, cudaStream_t st);
+                                const int32_t* counts, cudaStream_t st, const StepsView* steps = nullptr);

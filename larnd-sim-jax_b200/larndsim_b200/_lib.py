@@ -208,6 +208,12 @@ def _declare(lib):
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]
     lib.larnd_chop_count.restype = C.c_int
     lib.larnd_chop_tracks.restype = C.c_int
+    lib.larnd_fee_steps_bytes.argtypes = [i32]
+    lib.larnd_fee_steps_bytes.restype = sz
+    lib.larnd_fee_backward_steps.argtypes = [vp, vp, vp, i32, PP, vp, sz, i32, vp]
+    lib.larnd_fee_backward_steps.restype = C.c_int
+    lib.larnd_lut_backward_steps.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, sz, vp, vp]
+    lib.larnd_lut_backward_steps.restype = C.c_int
     lib.larnd_deterministic_scratch_bytes.argtypes = [i32, i32]
     lib.larnd_deterministic_scratch_bytes.restype = sz
     lib.larnd_lut_accumulate_deterministic.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp, sz, vp]

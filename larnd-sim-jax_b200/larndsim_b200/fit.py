@@ -175,7 +175,7 @@ def scan_2d(make_problem, p1, a1, p2, a2, fixed=None, event_shards=1):
 class FusedFitStep:
     """The same loss + gradients as FitProblem.loss_and_grads, as ONE asynchronous chain of kernel launches through the C ABI:
     prepare -> unique -> accumulate -> front end (dense, no hit compaction) -> dense mse_adc sums -> [all-reduce 5 floats]
-    -> mse_adc VJP -> front-end VJP -> accumulate VJP + chain rule -> [all-reduce 15 floats] -> one 80-byte read-back.
+    -> mse_adc VJP -> front-end VJP (step events) -> accumulate VJP + chain rule -> [all-reduce 15 floats] -> one read-back.
     Every buffer is allocated once; no autograd graph, no torch glue kernels, a single host synchronisation per step (the
     read of loss + gradients the optimiser needs anyway).  This is the regime every optimize/ fit of the reference runs in
     (~20 k segments per batch, optimize/fit_test.sh), where a step is bound by host work, not by the kernels."""
@@ -213,7 +213,7 @@ class FusedFitStep:
             self.n_valid = torch.zeros(1, dtype=torch.int32, device=dev)
             self.fee_scratch = torch.empty(lib.larnd_fee_scratch_bytes(npix), dtype=torch.uint8, device=dev)
             self.g_adc = f32(npix, k)
-            self.g_wfs = torch.zeros((npix, self.wfs.shape[1]), dtype=torch.float32, device=dev)   # padding / column 0 stay zero
+            self.steps = torch.empty(lib.larnd_fee_steps_bytes(npix), dtype=torch.uint8, device=dev)   # front-end VJP as step lists
             # target side of the loss: points, weights, Kyy, Sy (constants of the fit)
             rq, rx, ry, rz, _rt, rhp, rev = pr.ref
             self.ref_pts = torch.stack((rx + rev * 1e5, ry, rz), dim=-1).contiguous().float()
@@ -263,10 +263,11 @@ class FusedFitStep:
             check(lib.larnd_mse_adc_backward(ptr(self.sums), *fee_out, npix, P, self.n_ref, float(pr.sigma), float(pr.lambda_Q),
                                              ptr(self.loss), ptr(self.g_adc), ptr(self.grad), ptr(self.loss_scratch),
                                              self.loss_scratch.numel(), stream))
-            g1 = C.c_void_p(self.g_wfs.data_ptr() + 4)
-            check(lib.larnd_fee_backward(ptr(self.g_adc), ptr(self.ticks), ptr(self.saved), npix, P, g1, self.g_wfs.stride(0), 0, stream))
-            check(lib.larnd_lut_backward(self.n, P, self.lut.handle, pr.n_events, npix, 1, ptr(self.workspace), self.ws_bytes,
-                                         ptr(self.counts), ptr(self.g_wfs), self.g_wfs.stride(0), ptr(self.grad), stream))
+            # the two VJPs without the dense (npix, n_ticks) waveform gradient: step events per pixel row
+            check(lib.larnd_fee_backward_steps(ptr(self.g_adc), ptr(self.saved), ptr(self.upix), npix, P, ptr(self.steps),
+                                               self.steps.numel(), 0, stream))
+            check(lib.larnd_lut_backward_steps(self.n, P, self.lut.handle, pr.n_events, npix, 0, ptr(self.workspace), self.ws_bytes,
+                                               ptr(self.counts), ptr(self.steps), self.steps.numel(), ptr(self.grad), stream))
             if pr.distributed:
                 dist.all_reduce(self.grad, group=pr.group)
             self.out[12 + self._lib.NPARAMS:].copy_(self.counts)   # device-side flags travel with the results

@@ -550,6 +550,31 @@ def fee_backward(fs, g_adc, raw_charge=False):
     return out
 
 
+def hits_backward(st, fs, g_adc, raw_charge=False, steps=None):
+    """fee_backward followed by lut_backward WITHOUT the dense (Npix, Nticks) waveform gradient: the front end's VJP is a step
+    function per pixel row (<= 20 steps), handed to the accumulate VJP as a 168-byte list per row (larnd_fee_backward_steps ->
+    larnd_lut_backward_steps).  ``st``: LutState of the forward, ``fs``: FeeState of fee_forward on st's waveforms, ``g_adc``:
+    gradient w.r.t. the dense (Npix, 10) ADC array.  Returns the LARND_NPARAMS parameter gradients like lut_backward."""
+    lib = _lib.get_lib()
+    g = g_adc.contiguous().float()
+    if tuple(g.shape) != (st.npix, fs.pod.max_adc_values) or fs.npix != st.npix:
+        raise ValueError("g_adc must be (npix, MAX_ADC_VALUES) of the forward's pixel capacity")
+    nbytes = lib.larnd_fee_steps_bytes(st.npix)
+    if steps is None:
+        steps = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
+    grad = torch.zeros(_lib.NPARAMS, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(lib.larnd_fee_backward_steps(_ptr(g), _ptr(fs.saved), _ptr(st.unique_pixels), st.npix, C.byref(fs.pod), _ptr(steps),
+                                                steps.numel(), 1 if raw_charge else 0, _stream()))
+        bflags = (st.flags & ~1) | env_flags()
+        impl = os.environ.get("LARND_BWD_IMPL", "")
+        if impl:
+            bflags = (bflags & ~(_lib.FLAG_IMPL_CHUNK | _lib.FLAG_IMPL_SORTED)) | (_lib.FLAG_IMPL_SORTED if impl.startswith("s") else _lib.FLAG_IMPL_CHUNK)
+        _lib.check(lib.larnd_lut_backward_steps(st.n, C.byref(st.pod), st.lut.handle, st.n_events, st.npix, bflags, _ptr(st.workspace),
+                                                st.workspace.numel(), _ptr(st.counts), _ptr(steps), steps.numel(), _ptr(grad), _stream()))
+    return grad
+
+
 class _FeeAdc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wfs, params, unique_pixels, noise):

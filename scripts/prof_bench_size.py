@@ -7,7 +7,8 @@ import larndsim_b200 as lb
 from larndsim_b200 import sim, synthetic, dataio
 from larndsim_b200.consts import build_response_template
 nseg = int(sys.argv[1]) if len(sys.argv) > 1 else 10000000
-bwd = len(sys.argv) > 2 and sys.argv[2] == "bwd"
+bwd = len(sys.argv) > 2 and sys.argv[2] in ("bwd", "steps")
+steps = len(sys.argv) > 2 and sys.argv[2] == "steps"
 dev = torch.device("cuda", 0)
 GEOM = os.path.join(ROOT, "larnd-sim-jax_b200", "larndsim_b200", "data", "module0_geometry.json")
 P = lb.build_params_class([])
@@ -20,7 +21,9 @@ npix = st.npix
 for i in range(2):
     st = sim.lut_forward(params, bank, tracks, synthetic.FIELDS, npix_capacity=npix, n_events=nev)
     fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True)
-    if bwd:
+    if steps:
+        sim.hits_backward(st, fs, fs.adc * (st.unique_pixels >= 0).unsqueeze(1))
+    elif bwd:
         g = sim.fee_backward(fs, fs.adc * (st.unique_pixels >= 0).unsqueeze(1))
         sim.lut_backward(st, g)
 torch.cuda.synchronize()

@@ -1033,3 +1033,43 @@ def test_deterministic_mode_is_bitwise_reproducible_and_reference_accurate(torch
     sd = sim.lut_forward(pp, bank, torch.as_tensor(small, device=torch_dev), cm.FIELDS, npix_capacity=len(uo), deterministic=True)
     assert np.array_equal(sd.unique_pixels.cpu().numpy(), uo)
     _check_wfs(sd.wfs_full[:, 1:].cpu().numpy(), wo, uniq=uo)
+
+
+@pytest.mark.parametrize("cfg", [dict(number_pix_neighbors=4, signal_length=100), dict(number_pix_neighbors=2, signal_length=150)])
+@pytest.mark.parametrize("bwd", ["chunk", "sorted"])
+def test_steps_backward_equals_dense_backward(torch_dev, cfg, bwd, monkeypatch):
+    """sim.hits_backward (larnd_fee_backward_steps -> larnd_lut_backward_steps: the front end's VJP as a step list per row, the
+    correlations as running-sum differences) against fee_backward + lut_backward (dense gradient array) for the same upstream
+    gradient, on a batch with segments next to the anode (windows sticking out at the low end) and outside every TPC; all 15
+    leaves, both kernel families."""
+    import torch
+    from larndsim_b200 import _lib, sim
+    monkeypatch.setenv("LARND_BWD_IMPL", bwd)
+    rng = np.random.default_rng(5)
+    tr = cm.small_batch(1500, ibatch=1, pad=0, precision=0.01)
+    c = cm.FIELDS.index
+    near = tr[:300].copy()
+    shift = 30.45 - np.abs(near[:, c("z")]).max()
+    for col in ("z", "z_start", "z_end"):
+        near[:, c(col)] += np.sign(near[:, c(col)]) * shift
+    far = tr[300:330].copy()
+    far[:, c("x")] += 100.0
+    allr = np.concatenate([tr, near, far, cm.small_batch(1200, ifile=1, ibatch=0, pad=6, precision=0.01)])
+    pp = cm.product_params(**cfg)
+    nbins = 10 * cfg["number_pix_neighbors"] + 5
+    bank = torch.as_tensor(cm.synthetic_bank(48, nbins, nbins, 1950), device=torch_dev)
+    st = sim.lut_forward(pp, bank, torch.as_tensor(allr, device=torch_dev), cm.FIELDS)
+    fs = sim.fee_forward(pp, st.wfs_full[:, 1:], st.unique_pixels, None, compact=False)
+    assert int((fs.ticks < 1997).sum()) > 80
+    g_adc = torch.as_tensor(rng.normal(size=tuple(fs.adc.shape)).astype(np.float32), device=torch_dev)
+    g_adc = g_adc * (st.unique_pixels >= 0).unsqueeze(1)          # hits of invalid rows never reach a loss (parse_output)
+    dense = sim.lut_backward(st, sim.fee_backward(fs, g_adc)).cpu().numpy().astype(np.float64)
+    steps = sim.hits_backward(st, fs, g_adc).cpu().numpy().astype(np.float64)
+    used = [i for i, n in enumerate(_lib.PARAM_ORDER) if n not in ("alpha", "beta", "R_param", "vdrift")]   # Birks model
+    assert (dense[used] != 0).all()
+    err = np.abs(steps - dense) / np.maximum(np.abs(dense), 1e-30)
+    assert (err[used] <= 1e-3).all(), dict(zip(_lib.PARAM_ORDER, zip(steps, dense)))
+    # raw-charge form (gradient w.r.t. get_adc_values' integrated charge)
+    dense_q = sim.lut_backward(st, sim.fee_backward(fs, g_adc, raw_charge=True)).cpu().numpy().astype(np.float64)
+    steps_q = sim.hits_backward(st, fs, g_adc, raw_charge=True).cpu().numpy().astype(np.float64)
+    assert (np.abs(steps_q - dense_q)[used] <= 1e-3 * np.abs(dense_q)[used]).all()
