@@ -34,9 +34,15 @@ k_mc_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant_
   const int rows_here = (int)min((int64_t)MCP_THREADS, n - base);
   const int total = rows_here * ncols;
   const float* src = tracks + base * ncols;
-  for (int i = threadIdx.x; i < total; i += MCP_THREADS) {
-    int r = i / ncols, c = i - r * ncols;
-    srow[r * stride + c] = __ldg(src + i);
+  {
+    const int dr = MCP_THREADS / ncols, dc = MCP_THREADS - dr * ncols;   // incremental (row, column): no division per element
+    int r = threadIdx.x / ncols, c = threadIdx.x - r * ncols;
+    for (int i = threadIdx.x; i < total; i += MCP_THREADS) {
+      srow[r * stride + c] = __ldg(src + i);
+      r += dr;
+      c += dc;
+      if (c >= ncols) { c -= ncols; ++r; }
+    }
   }
   __syncthreads();
   const int t = threadIdx.x;
