@@ -56,8 +56,7 @@ struct BwdTileSmem {
   unsigned char owner[SEGMAX_B];
   float acc[NACC][SEGMAX_B];
   PairSlots ps[BT_WARPS];
-  float gl[LARND_NPARAMS][BT_THREADS];       // per-thread parameter-gradient accumulators (kept out of the register file)
-  float red[BT_WARPS][16];
+  float red[BT_WARPS][16];                   // per-warp parameter-gradient accumulators (warp-reduced once per tile)
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   signed char udx[225], udy[225];
   int tile, next_unit, nseg;
@@ -387,16 +386,14 @@ __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const fl
 // KP / span range / launch as in k_acc_tiles: the variants holding 3 / 4 response positions (36 / 48 registers, 4 / 3 CTAs
 // per SM) serve the tiles of runs with few impulse positions, the KP = KPT kernel the rest (or everything).
 template <int NS, int KP, bool STEPS = false>  // [region: kernel prologue]
-__global__ void __launch_bounds__(BT_THREADS, STEPS ? 3 : (NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1)))
+__global__ void __launch_bounds__(BT_THREADS, STEPS ? 4 : (NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1)))
 k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int span_lo, const int span_hi,
             const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdTileSmem& sm = *reinterpret_cast<BwdTileSmem*>(smem_raw);
   const SortArgs& S = A.S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#define GACC(k) sm.gl[k][threadIdx.x]
-#pragma unroll
-  for (int k = 0; k < LARND_NPARAMS; ++k) GACC(k) = 0.0f;
+  if (lane < 16) sm.red[warp][lane] = 0.0f;
   const bool garbage_needed = !STEPS && !A.force_skip && (*A.garbage_grad_nonzero != 0);
   const bool dead = S.counts[2] != 0 || garbage_needed;  // accumulate_bwd.cu's kernel takes over
   const int nb = S.nb;
@@ -552,6 +549,9 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
       for (int g = 0; g < sm.g_n[bxm]; ++g) if (sm.g_mask[bxm][g] >> k & 1) gmapx[k] = g;
       for (int g = 0; g < sm.g_n[bym]; ++g) if (sm.g_mask[bym][g] >> k & 1) gmapy[k] = g;
     }
+    float gacc[LARND_NPARAMS];   // this thread's parameter gradients of the tile; live only during the chain-rule phase
+#pragma unroll
+    for (int k = 0; k < LARND_NPARAMS; ++k) gacc[k] = 0.0f;
     for (int i = threadIdx.x; i < nseg; i += BT_THREADS) {
       if (sm.m[i] == INT32_MIN) continue;
       const int64_t s = sm.sid[i];
@@ -560,16 +560,17 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
       float dwx[5], dwy[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) { dwx[k] = sm.acc[5 + gmapx[k]][i]; dwy[k] = sm.acc[10 + gmapy[k]][i]; }
-      chain_rule_segment(p, S.rec, n, s, idx, q, dq, df, da, db, dc, dwx, dwy, [&](int k, float v) { GACC(k) += v; });
+      chain_rule_segment(p, S.rec, n, s, idx, q, dq, df, da, db, dc, dwx, dwy, [&](int k, float v) { gacc[k] += v; });
+    }
+    if (warp * 32 < nseg) {      // warps without a segment of this tile have nothing to add (warp-uniform)
+#pragma unroll
+      for (int k = 0; k < LARND_NPARAMS; ++k) {
+        const float v = warp_sum_f(gacc[k]);
+        if (lane == 0) sm.red[warp][k] += v;
+      }
     }
   }
-  // ---- warp + block reduction -> per-CTA partials ------------------------------------------------------------------  // [region: final reduce]
-#pragma unroll
-  for (int k = 0; k < LARND_NPARAMS; ++k) {
-    const float v = warp_sum_f(GACC(k));
-    if (lane == 0) sm.red[warp][k] = v;
-  }
-#undef GACC
+  // ---- block reduction -> per-CTA partials -------------------------------------------------------------------------  // [region: final reduce]
   __syncthreads();
   if (threadIdx.x < LARND_NPARAMS) {
     float v = 0.f;
@@ -602,7 +603,7 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
       LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
       attr_steps = true;
     }
-    const int grid = sorted_grid(3, LARND_BWD_SORTED_SLOTS);
+    const int grid = sorted_grid(4, LARND_BWD_SORTED_SLOTS);
     k_bwd_tiles<4, 2, true><<<grid, BT_THREADS, smem_s, st>>>(A, p, 0, SPAN_MAX_S, 2);
     LARND_LAUNCH_CHECK("k_bwd_tiles<steps>");
     *n_slots_out = grid;
