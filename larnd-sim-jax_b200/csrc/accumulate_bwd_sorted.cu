@@ -43,8 +43,7 @@ struct PairSlots {
   float G[BSLOTS][GSB];        // G[NR*j + r] of the run parked in the slot
   float gpos[BSLOTS][KPT + 2]; // upstream gradient at ticks tmin - 1 + j
   int p[BSLOTS];
-  int evp[BSLOTS][LARND_STEPS_MAX];    // STEPS kernels: step events of the slot's target row (position -1 / value 0 beyond the count)
-  float evv[BSLOTS][LARND_STEPS_MAX];
+  __align__(16) int ev[BSLOTS][LARND_STEPS_WORDS];   // STEPS kernels: the step-event record of the slot's target row (cp.async)
 };
 
 struct BwdTileSmem {
@@ -260,33 +259,30 @@ __device__ __forceinline__ void unit_pairs_steps(BwdTileSmem& sm, const BwdSortA
   const bool mine2 = ll < V;
   const float cbase2 = mine2 ? __ldg(crr - 1) : 0.0f;
   while (todo) {
-    // up to BSLOTS runs per pass: all event records are requested first (independent loads), staged, then consumed
+    // up to BSLOTS runs per pass: their event records (192 bytes each) go straight from global to shared memory with
+    // cp.async (twelve 16-byte copies per record, no register staging), then the slots are consumed
     int nslot = 0;
     int nev[BSLOTS];
-    {
-      int pr[BSLOTS];
-      RowSteps ev[BSLOTS];
 #pragma unroll
-      for (int s = 0; s < BSLOTS; ++s) {
-        pr[s] = -1;
-        nev[s] = 0;
-        if (todo) {
-          pr[s] = __ffs(todo) - 1;
-          todo &= todo - 1;
-          ev[s].load(A.steps, __shfl_sync(0xffffffffu, row, pr[s]), lane);
-          nslot = s + 1;
+    for (int s = 0; s < BSLOTS; ++s) {
+      if (todo) {
+        const int pp = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int rowp = __shfl_sync(0xffffffffu, row, pp);
+        if (lane < LARND_STEPS_WORDS / 4) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(&ps.ev[s][4 * lane]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(A.steps.rec + (int64_t)rowp * LARND_STEPS_WORDS + 4 * lane)
+                       : "memory");
         }
-      }
-#pragma unroll
-      for (int s = 0; s < BSLOTS; ++s) {
-        if (s < nslot) {
-          ev[s].fix(lane);
-          nev[s] = ev[s].n;
-          if (lane < LARND_STEPS_MAX) { ps.evp[s][lane] = ev[s].pos; ps.evv[s][lane] = ev[s].val; }
-          if (lane == 0) ps.p[s] = pr[s];
-        }
+        if (lane == 0) ps.p[s] = pp;
+        nslot = s + 1;
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < BSLOTS; ++s) nev[s] = (s < nslot) ? ps.ev[s][2 * LARND_STEPS_MAX] : 0;
     __syncwarp();
     const int npass = narrow ? (nslot + RPP - 1) / RPP : nslot;
     for (int pass = 0; pass < npass; ++pass) {
@@ -304,8 +300,8 @@ __device__ __forceinline__ void unit_pairs_steps(BwdTileSmem& sm, const BwdSortA
       const bool colok = colp >= 1 && colp <= nticks - 1 && ll <= KPT;
       const int base = tmin + jj;
       float acc = 0.0f, gp = 0.0f;
-      const int* evp = ps.evp[sx];
-      const float* evv = ps.evv[sx];
+      const int* evp = ps.ev[sx];
+      const float* evv = reinterpret_cast<const float*>(ps.ev[sx] + LARND_STEPS_MAX);
 #pragma unroll 2
       for (int e = 0; e < nemax; ++e) {
         const int pe = evp[e];

@@ -460,6 +460,12 @@ k_fee_backward_steps(const float* __restrict__ g_adc, const float* __restrict__ 
   const float* sv = saved + (int64_t)row * 32;
   const unsigned hit_mask = (unsigned)__float_as_int(sv[10]);
   int count = 0;
+  {
+    // unused entries read as "no event" (position -1, coefficient 0): consumers may walk a record without masking by its count
+    int32_t* r = rec + (int64_t)row * LARND_STEPS_WORDS;
+#pragma unroll
+    for (int k = 0; k < LARND_STEPS_MAX; ++k) { r[k] = -1; r[LARND_STEPS_MAX + k] = 0; }
+  }
   if (hit_mask != 0u && unique_pixels[row] >= 0) {
     const unsigned spos_mask = (unsigned)__float_as_int(sv[11]);
     const unsigned slope_mask = (unsigned)__float_as_int(sv[12]);
