@@ -46,6 +46,7 @@ template <int KP>
 struct TileSmem {
   int4 run[TR];                 // start, len | span << 16, tmin, class
   int ep[TR], mpx[TR], mpy[TR], soff[TR];
+  int prow[9][TR];              // waveform row of the 3x3 pixels around every run's main pixel (-1: not in the list)
   // per-segment data of the tile, staged once (thread <-> segment) and read by every group's build phase
   float qf[SEGMAX], qo[SEGMAX], ca[SEGMAX], cb[SEGMAX], cc[SEGMAX], fr[SEGMAX];
   int m[SEGMAX];                // T0 - tmin of the run
@@ -269,11 +270,13 @@ __device__ __forceinline__ void neigh_run(const SortArgs& A, const TileSmem<KP>&
   for (int v = 0; v < NSV; ++v)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc0[v][c] = 0.0f;
-#pragma unroll 1
-  for (int k = 0; 32 * k <= nu; ++k) {
+  // [region: neigh lookups]
+  // ---- which units own a waveform row: the lookups of all (<= 3) words are issued together, so their two dependent L2
+  // loads overlap instead of heading every word of the loop below ----
+  int rows3[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
     const int u = lane + 32 * k;
-    // [region: neigh lookups]
-    // ---- which units of this word own a waveform row ----
     int row = -1;
     if (u < nu) {
       const int dx = sm.udx[u], dy = sm.udy[u];
@@ -284,6 +287,12 @@ __device__ __forceinline__ void neigh_run(const SortArgs& A, const TileSmem<KP>&
         else if (A.skip_garbage && pid < 0) row = -1;
       }
     } else if (u == nu && !A.skip_garbage) row = 0;  // the neighbourhood-sum unit
+    rows3[k] = row;
+  }
+#pragma unroll 1
+  for (int k = 0; 32 * k <= nu; ++k) {
+    const int u = lane + 32 * k;
+    const int row = k == 0 ? rows3[0] : (k == 1 ? rows3[1] : rows3[2]);
     unsigned m = __ballot_sync(0xffffffffu, row >= 0);
     if (m == 0u) continue;
     // [region: neigh corrections]
@@ -505,6 +514,18 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
       sm.ucl[u] = cl;
     }
     __syncthreads();
+    // rows of the 3x3 main pixels, looked up ONCE per (run, pixel) for all diffusion-bin groups of phase A: the two dependent
+    // L2 loads of a lookup used to head every (group, tile) unit
+    for (int i = threadIdx.x; i < 9 * TR; i += TILE_THREADS) {
+      const int o = i / TR, r = i - o * TR;
+      int row = -1;
+      if (r < count) {
+        const int pid = pixel2id_dev(sm.mpx[r] + o / 3 - 1, sm.mpy[r] + o % 3 - 1, sm.ep[r], A.nxp, A.nyp);
+        row = lookup_row(lk, pid);  // not in the list -> dropped (sim_jax.py:152-154)
+        if (A.skip_garbage && pid < 0) row = -1;
+      }
+      sm.prow[o][r] = row;
+    }
     // [region: stage segments]
     // ---- stage the segments (thread <-> segment): products, Lagrange weights, group-merged transverse weights ---
     for (int i = threadIdx.x; i < sm.nseg; i += TILE_THREADS) {
@@ -568,12 +589,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
       if (gi >= sm.g_n[bxm] || gj >= sm.g_n[bym]) continue;
       const int bin = (int)sm.g_ci[bxm][gi] * 5 + (int)sm.g_ci[bym][gj];
       const int ox = (int)sm.g_ox[bxm][gi] - 1, oy = (int)sm.g_ox[bym][gj] - 1;
-      int row = -1;
-      if (lane < count) {
-        const int pid = pixel2id_dev(sm.mpx[lane] + ox, sm.mpy[lane] + oy, sm.ep[lane], A.nxp, A.nyp);
-        row = lookup_row(lk, pid);  // not in the list -> dropped (sim_jax.py:152-154)
-        if (A.skip_garbage && pid < 0) row = -1;
-      }
+      const int row = sm.prow[(ox + 1) * 3 + (oy + 1)][lane];
       const unsigned owned = __ballot_sync(0xffffffffu, row >= 0);
       if (owned == 0u) continue;
       // [region: phaseA build]

@@ -13,8 +13,9 @@
 
 namespace {
 
-constexpr int FEE_WARPS = 4;
-constexpr int FEE_THREADS = FEE_WARPS * 32;
+#ifndef LARND_FEE_WARPS
+#define LARND_FEE_WARPS 4
+#endif
 #define FEE_ROW_STRIDE(nt) ((((nt) + 3) & ~3) + 4)  // floats per warp: the row, rounded up to whole vectors, + the alignment shift
 
 struct FeeArgs {
@@ -31,136 +32,170 @@ struct FeeArgs {
 
 __device__ __forceinline__ int floordiv_pos(int a, int b) { return floordiv_i(a, b); }
 
-__global__ void __launch_bounds__(FEE_THREADS)
+// Sequential float32 running sum (fee_jax.py:193) of one row's window [t_first, t_last], strictly left to right, in place.
+// Scalar head (t < head), whole vectors of the body (the window bounds sit on vector boundaries there; samples of a vector
+// outside the window are zeros), scalar tail: one 128-bit load and store per four dependent adds.  Returns the row total.
+__device__ __forceinline__ float fee_serial_sum(float* c, int head, int nvec, int t_first, int t_last) {
+  float4* c4 = reinterpret_cast<float4*>(c + head);
+  float acc = 0.0f;
+  int t = t_first;
+  for (; t <= t_last && t < head; ++t) {
+    acc = __fadd_rn(acc, c[t]);
+    c[t] = acc;
+  }
+  if (t <= t_last) {
+    const int vend = min(nvec - 1, (t_last - head) >> 2);
+#pragma unroll 4
+    for (int v = (t - head) >> 2; v <= vend; ++v) {
+      float4 q = c4[v];
+      acc = __fadd_rn(acc, q.x); q.x = acc;
+      acc = __fadd_rn(acc, q.y); q.y = acc;
+      acc = __fadd_rn(acc, q.z); q.z = acc;
+      acc = __fadd_rn(acc, q.w); q.w = acc;
+      c4[v] = q;
+    }
+    for (int t2 = max(t, head + 4 * nvec); t2 <= t_last; ++t2) {
+      acc = __fadd_rn(acc, c[t2]);
+      c[t2] = acc;
+    }
+  }
+  return acc;
+}
+
+// Three phases per CTA of FEE_WARPS rows:
+//   1. warp <-> row: the row is fetched into shared memory (TMA), the bounds of its non-zero samples are found with an
+//      integer OR over 128-bit vectors (no arithmetic on the ~1850 zero samples of a track's pixel) and only the window is
+//      scaled by t_sampling;
+//   2. lane <-> row: lanes 0 .. FEE_WARPS-1 of warp 0 form the sequential running sums of ALL rows of the CTA at once — the
+//      dependent-add chain is the one part of the algorithm that has no parallelism inside a row (it was 21 % of the
+//      kernel's instructions with one useful lane of 32 per row);
+//   3. warp <-> row: the ten discriminator passes as ballot scans over the window.
+template <int FEE_WARPS>
+__global__ void __launch_bounds__(FEE_WARPS * 32)
 k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_params_t p) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int row = blockIdx.x * FEE_WARPS + wid;
-  if (row >= F.npix) return;
+  const bool live = row < F.npix;
   const int Nt = F.ntw;
-  const float* w = F.wfs + (int64_t)row * F.stride;
+  const int rstride = FEE_ROW_STRIDE(Nt);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + (size_t)FEE_WARPS * rstride);
+  int* const s_first = reinterpret_cast<int*>(bars + FEE_WARPS);
+  int* const s_last = s_first + FEE_WARPS;
+  float* const s_total = reinterpret_cast<float*>(s_last + FEE_WARPS);
+  const float* w = F.wfs + (int64_t)(live ? row : 0) * F.stride;
   // The row base is only 4-byte aligned (simulate_wfs hands out wfs[:, 1:] of a 2001-float row): `head` floats up to the
-  // next 16-byte boundary and `tail` floats after the last whole vector are read by six lanes, the body with 128-bit
-  // loads.  The copy in shared memory is shifted by `shift` floats so that the vector stores are aligned as well.
+  // next 16-byte boundary and `tail` floats after the last whole vector are handled by six lanes, the body as 128-bit
+  // vectors.  The copy in shared memory is shifted by `shift` floats so that the vectors are aligned there as well.
   const int head = min((int)(((16u - (unsigned)((uintptr_t)w & 15u)) & 15u) >> 2), Nt);
   const int nvec = (Nt - head) >> 2, tail = Nt - head - 4 * nvec;
   const int shift = (4 - head) & 3;
-  float* c = smem + (size_t)wid * FEE_ROW_STRIDE(Nt) + shift;
+  float* c = smem + (size_t)wid * rstride + shift;
   int t_first = Nt, t_last = -1;  // bounds of the non-zero samples (vector granularity: a superset is enough, zeros inside
                                   // the window do not change any running sum)
   const float4* w4 = reinterpret_cast<const float4*>(w + head);
   float4* c4 = reinterpret_cast<float4*>(c + head);
-  if (F.bulk) {
-    // Row load by the TMA engine: ONE cp.async.bulk per row (the whole 8 KB in flight per warp instead of four 512-byte
-    // warp loads at a time), completion on a per-warp mbarrier.  Layout contract (checked on the host): rows start `shift`
-    // (0 or 1) floats past a 16-byte boundary and the stride is a multiple of four floats — simulate_wfs' view [:, 1:] of
-    // the padded waveform buffer — so the copy starts at the aligned address below the row (its garbage column) and lands at
-    // the start of this warp's buffer; c = buffer + shift is the same shifted copy the vector path builds.
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)FEE_WARPS * FEE_ROW_STRIDE(Nt)) + wid;
-    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
-    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(c - shift);
-    const unsigned bytes = (unsigned)(((shift + Nt + 3) >> 2) << 4);
-    if (lane == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst_s), "l"(w - shift), "r"(bytes), "r"(bar_s) : "memory");
-    }
-    __syncwarp();
-    unsigned done = 0;
-    while (!done) {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done) : "r"(bar_s) : "memory");
-    }
-    // q = wfs * t_sampling in place + bounds of the non-zero samples
-    if (lane < head + tail) {
-      const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
-      const float qv = __fmul_rn(c[t], p.t_sampling);
-      c[t] = qv;
-      if (qv != 0.0f) { t_first = t; t_last = t; }
-    }
-    for (int v = lane; v < nvec; v += 32) {
-      float4 q = c4[v];
-      q.x = __fmul_rn(q.x, p.t_sampling); q.y = __fmul_rn(q.y, p.t_sampling);
-      q.z = __fmul_rn(q.z, p.t_sampling); q.w = __fmul_rn(q.w, p.t_sampling);
-      if (q.x != 0.0f || q.y != 0.0f || q.z != 0.0f || q.w != 0.0f) {
-        c4[v] = q;   // all-zero vectors stay as they are (0 * t_sampling = 0)
-        const int t = head + 4 * v;
-        t_first = min(t_first, t);
-        t_last = max(t_last, t + 3);
+  if (live) {
+    if (F.bulk) {
+      // Row load by the TMA engine: ONE cp.async.bulk per row (the whole 8 KB in flight per warp instead of four 512-byte
+      // warp loads at a time), completion on a per-warp mbarrier.  Layout contract (checked on the host): rows start `shift`
+      // (0 or 1) floats past a 16-byte boundary and the stride is a multiple of four floats — simulate_wfs' view [:, 1:] of
+      // the padded waveform buffer — so the copy starts at the aligned address below the row (its garbage column) and lands at
+      // the start of this warp's buffer; c = buffer + shift is the same shifted copy the vector path builds.
+      const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bars + wid);
+      const unsigned dst_s = (unsigned)__cvta_generic_to_shared(c - shift);
+      const unsigned bytes = (unsigned)(((shift + Nt + 3) >> 2) << 4);
+      if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_s), "l"(w - shift), "r"(bytes), "r"(bar_s) : "memory");
       }
-    }
-  } else {
-  if (lane < head + tail) {
-    const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
-    const float qv = __fmul_rn(__ldg(w + t), p.t_sampling);  // q = wfs * t_sampling
-    c[t] = qv;
-    if (qv != 0.0f) { t_first = t; t_last = t; }
-  }
-  for (int v0 = 0; v0 < nvec; v0 += 128) {
-    float4 x[4];
+      __syncwarp();
+      unsigned done = 0;
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_s) : "memory");
+      }
+    } else {
+      if (lane < head + tail) {
+        const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
+        c[t] = __ldg(w + t);
+      }
+      for (int v0 = 0; v0 < nvec; v0 += 128) {
+        float4 x[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {  // four 512-byte warp loads in flight
-      const int v = v0 + 32 * k + lane;
-      x[k] = v < nvec ? __ldg(w4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+        for (int k = 0; k < 4; ++k) {  // four 512-byte warp loads in flight
+          const int v = v0 + 32 * k + lane;
+          x[k] = v < nvec ? __ldg(w4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int v = v0 + 32 * k + lane;
-      if (v < nvec) {
-        float4 q;
-        q.x = __fmul_rn(x[k].x, p.t_sampling); q.y = __fmul_rn(x[k].y, p.t_sampling);
-        q.z = __fmul_rn(x[k].z, p.t_sampling); q.w = __fmul_rn(x[k].w, p.t_sampling);
-        c4[v] = q;
-        if (q.x != 0.0f || q.y != 0.0f || q.z != 0.0f || q.w != 0.0f) {
-          const int t = head + 4 * v;
-          t_first = min(t_first, t);
-          t_last = max(t_last, t + 3);
+        for (int k = 0; k < 4; ++k) {
+          const int v = v0 + 32 * k + lane;
+          if (v < nvec) c4[v] = x[k];
         }
       }
+      __syncwarp();
     }
-  }
-  }
+    // bounds of the non-zero samples: bitwise OR of whole vectors (-0.0 counts as non-zero: a superset), two vectors per trip
+    if (lane < head + tail) {
+      const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
+      if (__float_as_uint(c[t]) != 0u) { t_first = t; t_last = t; }
+    }
+    {
+      const uint4* u4 = reinterpret_cast<const uint4*>(c4);
+      int vf = 0x3fffffff, vl = -1;
+      for (int v = lane; v < nvec; v += 64) {
+        const uint4 a = u4[v];
+        const bool has_b = v + 32 < nvec;
+        const uint4 b = has_b ? u4[v + 32] : make_uint4(0u, 0u, 0u, 0u);
+        const unsigned oa = a.x | a.y | a.z | a.w, ob = b.x | b.y | b.z | b.w;
+        if (oa) { vf = min(vf, v); vl = v; }
+        if (ob) { vf = min(vf, v + 32); vl = v + 32; }
+      }
+      if (vl >= 0) {
+        t_first = min(t_first, head + 4 * vf);
+        t_last = max(t_last, head + 4 * vl + 3);
+      }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, o));
-    t_last = max(t_last, __shfl_xor_sync(0xffffffffu, t_last, o));
-  }
-  __syncwarp();
-  // sequential float32 running sum (fee_jax.py:193), strictly left to right.  Adding the zero samples before the first
-  // and after the last non-zero tick does not change a float32 sum, so only [t_first, t_last] is walked serially and the
-  // constant tail is filled in parallel.
-  float total = 0.0f;
-  if (lane == 0) {
-    // scalar head (t < head), whole vectors of the body (the window bounds sit on vector boundaries there; samples of a
-    // vector outside the window are zeros), scalar tail: one 128-bit load and store per four dependent adds
-    float acc = 0.0f;
-    int t = t_first;
-    for (; t <= t_last && t < head; ++t) {
-      acc = __fadd_rn(acc, c[t]);
-      c[t] = acc;
+    for (int o = 16; o > 0; o >>= 1) {
+      t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, o));
+      t_last = max(t_last, __shfl_xor_sync(0xffffffffu, t_last, o));
     }
-    if (t <= t_last) {
-      const int vend = min(nvec - 1, (t_last - head) >> 2);
-#pragma unroll 4
-      for (int v = (t - head) >> 2; v <= vend; ++v) {
+    // q = wfs * t_sampling, on the window only (0 * t_sampling = 0 elsewhere)
+    if (t_last >= t_first) {
+      if (lane < head + tail) {
+        const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
+        c[t] = __fmul_rn(c[t], p.t_sampling);
+      }
+      const int v0 = max(0, (t_first - head) >> 2), v1 = min(nvec - 1, (t_last - head) >> 2);
+      for (int v = v0 + lane; v <= v1; v += 32) {
         float4 q = c4[v];
-        acc = __fadd_rn(acc, q.x); q.x = acc;
-        acc = __fadd_rn(acc, q.y); q.y = acc;
-        acc = __fadd_rn(acc, q.z); q.z = acc;
-        acc = __fadd_rn(acc, q.w); q.w = acc;
+        q.x = __fmul_rn(q.x, p.t_sampling); q.y = __fmul_rn(q.y, p.t_sampling);
+        q.z = __fmul_rn(q.z, p.t_sampling); q.w = __fmul_rn(q.w, p.t_sampling);
         c4[v] = q;
       }
-      for (int t2 = max(t, head + 4 * nvec); t2 <= t_last; ++t2) {
-        acc = __fadd_rn(acc, c[t2]);
-        c[t2] = acc;
-      }
     }
-    total = acc;
   }
-  total = __shfl_sync(0xffffffffu, total, 0);
-  __syncwarp();
+  if (lane == 0) { s_first[wid] = t_first; s_last[wid] = t_last; }
+  __syncthreads();
+  // sequential running sums of the CTA's rows, lane <-> row.  Adding the zero samples before the first and after the last
+  // non-zero tick does not change a float32 sum, so only [t_first, t_last] is walked.
+  if (wid == 0 && lane < FEE_WARPS) {
+    float tot = 0.0f;
+    const int rl = blockIdx.x * FEE_WARPS + lane;
+    if (rl < F.npix) {
+      const float* wl = F.wfs + (int64_t)rl * F.stride;
+      const int hl = min((int)(((16u - (unsigned)((uintptr_t)wl & 15u)) & 15u) >> 2), Nt);
+      tot = fee_serial_sum(smem + (size_t)lane * rstride + ((4 - hl) & 3), hl, (Nt - hl) >> 2, s_first[lane], s_last[lane]);
+    }
+    s_total[lane] = tot;
+  }
+  __syncthreads();
+  if (!live) return;
+  const float total = s_total[wid];
   // Outside [lo, hi] the running sum is constant (0 before the first non-zero sample, the total after the last one) and
   // stays constant under the subtract-and-clamp of every pass: those two regions are carried as the scalars hv / tv and
   // only the window is kept in shared memory and walked by the ten passes (~150 ticks of 2000 on a track's pixel).
@@ -176,18 +211,27 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   // pixel geometry (id2pixel with Python floor semantics; negative ids give event < 0)
   const int pid = F.unique_pixels[row];
   const int nx = p.n_pixels_x, ny = p.n_pixels_y, ntpc = p.n_tpc;
-  const int xp = pid - floordiv_pos(pid, nx) * nx;
+  // three floor divisions instead of five: floor(floor(a / b) / c) == floor(a / (b c)) for positive b, c
   const int t1 = floordiv_pos(pid, nx);
-  const int yp = t1 - floordiv_pos(t1, ny) * ny;
-  const int t2 = floordiv_pos(pid, nx * ny);
-  const int plane = t2 - floordiv_pos(t2, ntpc) * ntpc;
-  const int ev = floordiv_pos(pid, nx * ny * ntpc);
+  const int xp = pid - t1 * nx;
+  const int t2 = floordiv_pos(t1, ny);      // == floordiv(pid, nx * ny)
+  const int yp = t1 - t2 * ny;
+  const int ev = floordiv_pos(t2, ntpc);    // == floordiv(pid, nx * ny * ntpc)
+  const int plane = t2 - ev * ntpc;
   const float z_anode = p.tpc_borders[plane][2][0], z_high = p.tpc_borders[plane][2][1];
   const float dz = __fsub_rn(z_high, z_anode);
   const float sgn = dz > 0.0f ? 1.0f : (dz < 0.0f ? -1.0f : 0.0f);
   const float adc_scale_den = p.v_ref_minus_cm;
   unsigned hit_mask = 0, spos_mask = 0, slope_mask = 0;
   int n_valid = 0;
+  // The crossing scan reads pairs (t, t+1) that touch the window, i.e. ticks lo-1 .. hi+1: the two constant regions are
+  // mirrored into the zero samples next to the window (c[lo-1] = hv, c[hi+1] = tv, refreshed after every pass) so that the
+  // scan loads shared memory without a bounds select per sample.
+  if (lane == 0) {
+    if (lo >= 1 && lo <= Nt) c[lo - 1] = hv;
+    if (hi >= 0 && hi + 1 < Nt) c[hi + 1] = tv;
+  }
+  __syncwarp();
   for (int it = 0; it < nmax; ++it) {
     // first t with q_sum[t] <= thr <= q_sum[t+1] (fee_jax.py:200-203); fill value Nt-2
     int idx_t = Nt - 2;
@@ -199,7 +243,7 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
         const int t = t0 + lane;
         bool hit = false;
         if (t <= t_end) {
-          const float a = __fadd_rn(base, cget(t)), b = __fadd_rn(base, cget(t + 1));
+          const float a = __fadd_rn(base, c[t]), b = __fadd_rn(base, c[t + 1]);
           hit = (b >= thr) && (a <= thr);
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -231,6 +275,10 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
       v = (v < 0.0f) ? 0.0f : v;
       c[t] = v;
       vmax = fmaxf(vmax, v);
+    }
+    if (lane == 0) {
+      if (lo >= 1 && lo <= Nt) c[lo - 1] = hv;
+      if (hi >= 0 && hi + 1 < Nt) c[hi + 1] = tv;
     }
     __syncwarp();
     // digitize (fee_jax.py:68-69)
@@ -540,7 +588,17 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
   F.event = event_d; F.saved = saved_d;
   F.row_counts = reinterpret_cast<int32_t*>(scratch_d);
   int32_t* offsets = F.row_counts + npix;
-  size_t smem = (size_t)FEE_WARPS * FEE_ROW_STRIDE(ntw) * sizeof(float) + FEE_WARPS * sizeof(uint64_t);  // rows + one mbarrier per warp
+  // rows per CTA (= warps): LARND_FEE_WARPS at build time, overridable for experiments with the environment variable of the
+  // same name (read once)
+  static int fee_warps = 0;
+  if (fee_warps == 0) {
+    const char* e = getenv("LARND_FEE_WARPS");
+    const int v = e ? atoi(e) : LARND_FEE_WARPS;
+    fee_warps = (v == 1 || v == 2 || v == 4 || v == 8) ? v : LARND_FEE_WARPS;
+  }
+  int nw = fee_warps;
+  // rows + one mbarrier per warp + window bounds and total per row
+  size_t smem = (size_t)nw * FEE_ROW_STRIDE(ntw) * sizeof(float) + nw * (sizeof(uint64_t) + 2 * sizeof(int) + sizeof(float));
   {
     // TMA row loads need 16-byte aligned sources: rows whose start is `sh` floats past a 16-byte boundary are copied from
     // the aligned address below (see the header: those floats and the round-up at the end must be readable)
@@ -549,12 +607,23 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
   }
   static bool attr_set = false;
   if (!attr_set) {
-    LARND_CUDA(cudaFuncSetAttribute(k_fee_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LARND_CUDA(cudaFuncSetAttribute(k_fee_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LARND_CUDA(cudaFuncSetAttribute(k_fee_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LARND_CUDA(cudaFuncSetAttribute(k_fee_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LARND_CUDA(cudaFuncSetAttribute(k_fee_forward<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
+  }
+  while (smem > 200 * 1024 && nw > 1) {  // very long readouts: fewer rows per CTA
+    nw >>= 1;
+    smem = (size_t)nw * FEE_ROW_STRIDE(ntw) * sizeof(float) + nw * (sizeof(uint64_t) + 2 * sizeof(int) + sizeof(float));
   }
   if (smem > 200 * 1024) { larnd_set_error("larnd_fee_forward: n_ticks too large for shared memory"); return LARND_E_ARG; }
   prof_begin(3, st);
-  k_fee_forward<<<(npix + FEE_WARPS - 1) / FEE_WARPS, FEE_THREADS, smem, st>>>(F, *params);
+  const unsigned grid = (unsigned)((npix + nw - 1) / nw);
+  if (nw == 8) k_fee_forward<8><<<grid, 256, smem, st>>>(F, *params);
+  else if (nw == 4) k_fee_forward<4><<<grid, 128, smem, st>>>(F, *params);
+  else if (nw == 2) k_fee_forward<2><<<grid, 64, smem, st>>>(F, *params);
+  else k_fee_forward<1><<<grid, 32, smem, st>>>(F, *params);
   prof_end(3, st);
   LARND_LAUNCH_CHECK("k_fee_forward");
   k_scan_counts<<<1, 1024, 0, st>>>(F.row_counts, npix, offsets, n_valid_d);

@@ -31,7 +31,22 @@ k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ l
     // instructions, ncu line profile profiles/r2y_k_prepare_lines.txt)
     const int dr = PREP_THREADS / ncols, dc = PREP_THREADS - dr * ncols;
     int r = threadIdx.x / ncols, c = threadIdx.x - r * ncols;
-    for (int i = threadIdx.x; i < total; i += PREP_THREADS) {
+    int i = threadIdx.x;
+    // eight coalesced loads in flight per thread before the first store (the kernel's top stall was the load -> store
+    // dependency of a one-element loop body: long-scoreboard 5 warps per issue, profiles/r2_final_kernels_ncu_summary.txt)
+    for (; i + 7 * PREP_THREADS < total; i += 8 * PREP_THREADS) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(src + i + k * PREP_THREADS);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        srow[r * stride + c] = v[k];
+        r += dr;
+        c += dc;
+        if (c >= ncols) { c -= ncols; ++r; }
+      }
+    }
+    for (; i < total; i += PREP_THREADS) {
       srow[r * stride + c] = __ldg(src + i);  // coalesced stream of the 104-byte records
       r += dr;
       c += dc;

@@ -336,6 +336,24 @@ def lut_backward(st, g_wfs, skip_garbage=False):
     return grad
 
 
+# Batches from this size on hand the front end's VJP to the accumulate VJP as step events (hits_backward) instead of a dense
+# (Npix, Nticks) gradient when simulate_wfs -> simulate_stochastic are chained under torch.autograd; below it the chunk kernel
+# on dense gradient rows is faster.
+STEPS_AUTOGRAD_MIN_SEGMENTS = 200000
+
+
+class _StepsLink:
+    """Shared by the autograd nodes of simulate_wfs and simulate_stochastic when the second consumes the first's output
+    directly.  The front end's VJP is a step function per pixel row; its node parks (FeeState, g_adc) here and returns a
+    zero-stride all-zero placeholder for d loss / d wfs.  If that placeholder reaches simulate_wfs' node untouched, the
+    accumulate VJP runs from the step events (no 2 GB gradient written or read); if autograd added other gradients to it
+    (the waveforms had a second consumer), the sum is a fresh tensor and the dense front-end gradient is added to it."""
+    __slots__ = ("st", "pending", "placeholder")
+
+    def __init__(self):
+        self.st, self.pending, self.placeholder = None, None, None
+
+
 class _SimulateWfs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, theta, params, response_template, tracks, fields, names, npix_capacity, n_events, holder=None):
@@ -343,13 +361,28 @@ class _SimulateWfs(torch.autograd.Function):
         ctx.st = st
         ctx.names = names
         ctx.mark_non_differentiable(st.unique_pixels)
+        ctx.link = None
         if holder is not None:
             holder.append(st.counts)
+            if st.n >= STEPS_AUTOGRAD_MIN_SEGMENTS and not os.environ.get("LARND_NO_STEPS_AUTOGRAD"):
+                ctx.link = _StepsLink()
+                ctx.link.st = st
+            holder.append(ctx.link)
         return st.wfs_full[:, 1:], st.unique_pixels
 
     @staticmethod
     def backward(ctx, g_wfs, _g_pix):
-        grad_all = lut_backward(ctx.st, g_wfs)
+        link = ctx.link
+        if link is not None and link.pending is not None:
+            fs, g_adc = link.pending
+            ph = link.placeholder
+            link.pending = link.placeholder = None
+            if g_wfs.data_ptr() == ph.data_ptr() and g_wfs.stride() == ph.stride():
+                grad_all = hits_backward(ctx.st, fs, g_adc)
+            else:  # the waveforms had other consumers: their gradients + the dense front-end gradient
+                grad_all = lut_backward(ctx.st, g_wfs + fee_backward(fs, g_adc))
+        else:
+            grad_all = lut_backward(ctx.st, g_wfs)
         idx = torch.tensor([_lib.PARAM_ORDER.index(n) for n in ctx.names], device=grad_all.device)
         return (grad_all[idx],) + (None,) * 8
 
@@ -364,6 +397,8 @@ def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, 
         holder = []
         wfs, upix = _SimulateWfs.apply(theta, params, response_template, tracks, tuple(fields), names, npix_capacity, n_events, holder)
         counts = holder[0]
+        if holder[1] is not None:
+            wfs._larnd_steps_link = holder[1]
     else:
         st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
         wfs, upix, counts = st.wfs_full[:, 1:], st.unique_pixels, st.counts
@@ -577,15 +612,22 @@ def hits_backward(st, fs, g_adc, raw_charge=False, steps=None):
 
 class _FeeAdc(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, wfs, params, unique_pixels, noise):
+    def forward(ctx, wfs, params, unique_pixels, noise, link=None):
         fs = fee_forward(params, wfs, unique_pixels, noise, compact=False)
         ctx.fs = fs
+        ctx.link = link
         ctx.mark_non_differentiable(fs.ticks, fs.pixel_x, fs.pixel_y, fs.event)
         return fs.adc, fs.ticks, fs.pixel_x, fs.pixel_y, fs.event
 
     @staticmethod
     def backward(ctx, g_adc, *_unused):
-        return fee_backward(ctx.fs, g_adc), None, None, None
+        link = ctx.link
+        if link is not None and link.pending is None and link.st.npix == ctx.fs.npix:
+            # step-event hand-over to simulate_wfs' node (see _StepsLink): nothing dense is written here
+            link.pending = (ctx.fs, g_adc)
+            link.placeholder = torch.zeros(1, dtype=torch.float32, device=g_adc.device).expand(ctx.fs.npix, ctx.fs.pod.n_ticks - 1)
+            return link.placeholder, None, None, None, None
+        return fee_backward(ctx.fs, g_adc), None, None, None, None
 
 
 def make_noise(params, npix, rngseed, device):
@@ -627,7 +669,7 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
         check_outputs(wfs, unique_pixels)   # same synchronisation point: the forward call's device-side flags
         hf, hi = fs.hits
         return hf[0, :nv], hf[1, :nv], hf[2, :nv], hf[3, :nv], hf[4, :nv], hf[5, :nv], hi[0, :nv], hi[1, :nv]
-    adcs, ticks, pixel_x, pixel_y, event = _FeeAdc.apply(wfs, params, unique_pixels, noise)
+    adcs, ticks, pixel_x, pixel_y, event = _FeeAdc.apply(wfs, params, unique_pixels, noise, getattr(wfs, "_larnd_steps_link", None))
     check_outputs(wfs, unique_pixels)       # parse_output below synchronises anyway
     hit_prob = torch.where(ticks < wfs.shape[1] - 3, 1.0, 0.0)
     plane = torch.div(unique_pixels, params.n_pixels_x * params.n_pixels_y, rounding_mode="floor") % np.asarray(params.tpc_borders).shape[0]
