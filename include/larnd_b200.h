@@ -60,7 +60,11 @@ enum {
 #define LARND_FLAG_IMPL_CHUNK   0x2  /* force the chunk kernels (default: by batch size)            */
 #define LARND_FLAG_IMPL_SORTED  0x4  /* force the class-sorted tile kernels where they are supported  */
 #define LARND_FLAG_NO_SPLIT     0x8  /* class-sorted kernels: serve every tile with the 6-position variant */
-#define LARND_FLAG_PUBLIC_MASK  0xf
+#define LARND_FLAG_REUSE_RUNS   0x10 /* larnd_lut_backward / _backward_steps: the workspace still holds the sorted run / tile tables the
+                                      * forward call (larnd_lut_accumulate / _forward) built from the same records, on the same
+                                      * stream or synchronised with it; the library checks (workspace, n, lut, n_ticks) against its
+                                      * record of the last build and rebuilds when they do not match */
+#define LARND_FLAG_PUBLIC_MASK  0x1f
 
 /* Differentiable parameters (optimize/ranges.py:7-21).  Gradients are returned in this order. */
 enum {

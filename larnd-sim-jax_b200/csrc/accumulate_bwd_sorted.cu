@@ -582,7 +582,7 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
                                        float* sorted_partials, int* n_slots_out, const int* gflag, const int32_t* counts,
                                        cudaStream_t st, const StepsView* steps) {
   BwdSortArgs A;
-  int rc = sorted_fill_and_build(A.S, n, p, lut, ws, npix_capacity, counts, st);
+  int rc = sorted_fill_and_build(A.S, n, p, lut, ws, npix_capacity, counts, st, (flags & LARND_FLAG_REUSE_RUNS) != 0);
   if (rc) return rc;
   if (steps) {
     // compact upstream gradient: one kernel for every tick span (no register-resident response, so no KP variants)

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "larnd_common.cuh"
+#include <mutex>
 
 static thread_local char g_err[512] = "";
 
@@ -71,6 +72,36 @@ extern "C" size_t larnd_workspace_bytes(int64_t n, int32_t n_events, int32_t ntp
   b += align_up((size_t)(nchunks + LARND_BWD_SORTED_SLOTS) * 16 * sizeof(float), 256);
   b += larnd_sorted_workspace_bytes(n);
   return b;
+}
+
+namespace {
+struct RunsCacheEntry { const void* rec; int64_t n; const void* lut; int n_ticks; };
+constexpr int RUNS_CACHE_N = 16;
+RunsCacheEntry g_runs_cache[RUNS_CACHE_N];
+int g_runs_cache_next = 0;
+std::mutex g_runs_cache_mu;
+}  // namespace
+
+void larnd_runs_cache_drop(const void* rec) {
+  std::lock_guard<std::mutex> lock(g_runs_cache_mu);
+  for (auto& e : g_runs_cache)
+    if (e.rec == rec) e.rec = nullptr;
+}
+
+void larnd_runs_cache_set(const void* rec, int64_t n, const void* lut, int n_ticks) {
+  std::lock_guard<std::mutex> lock(g_runs_cache_mu);
+  RunsCacheEntry* slot = nullptr;
+  for (auto& e : g_runs_cache)
+    if (e.rec == rec) slot = &e;
+  if (!slot) { slot = &g_runs_cache[g_runs_cache_next]; g_runs_cache_next = (g_runs_cache_next + 1) % RUNS_CACHE_N; }
+  *slot = RunsCacheEntry{rec, n, lut, n_ticks};
+}
+
+bool larnd_runs_cache_valid(const void* rec, int64_t n, const void* lut, int n_ticks) {
+  std::lock_guard<std::mutex> lock(g_runs_cache_mu);
+  for (auto& e : g_runs_cache)
+    if (e.rec == rec && rec) return e.n == n && e.lut == lut && e.n_ticks == n_ticks;
+  return false;
 }
 
 bool larnd_carve_workspace(void* base, size_t bytes, int64_t n, int32_t n_events, int32_t ntpc, int32_t nx, int32_t ny,

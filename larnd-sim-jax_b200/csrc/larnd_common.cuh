@@ -197,6 +197,12 @@ __device__ __forceinline__ int lookup_row(const RowLookup& lk, int pid) {
   return pid < 0 ? rank : lk.npix - lk.n_unique + rank;
 }
 
+// Host-side record of which workspaces hold valid sorted run / tile tables (sorted_runs.cuh), keyed on the record base
+// pointer: set by a build, dropped by whatever rewrites the records (prepare kernels).  LARND_FLAG_REUSE_RUNS consults it.
+void larnd_runs_cache_set(const void* rec, int64_t n, const void* lut, int n_ticks);
+void larnd_runs_cache_drop(const void* rec);
+bool larnd_runs_cache_valid(const void* rec, int64_t n, const void* lut, int n_ticks);
+
 // kernels / launchers implemented in the .cu files
 int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& cols, const larnd_params_t& p,
                          const larnd_lut* lut, const Workspace& ws, int32_t* counts, cudaStream_t st);

@@ -530,6 +530,7 @@ extern "C" int larnd_mc_forward(const float* tracks_d, int64_t n, const larnd_co
   LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * p->n_ticks * sizeof(float), st));
   if (n > 0) {
     size_t smem = (size_t)MCP_THREADS * (cols->ncols | 1) * sizeof(float);
+    larnd_runs_cache_drop(ws.rec);
     k_mc_prepare<<<(unsigned)((n + MCP_THREADS - 1) / MCP_THREADS), MCP_THREADS, smem, st>>>(
         tracks_d, n, *cols, *p, rnd_d, ws.rec, ws.bitmap, ws.n_words, ws.pid_offset, counts_d);
     LARND_LAUNCH_CHECK("k_mc_prepare");

@@ -281,6 +281,7 @@ int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& 
   size_t smem = (size_t)PREP_THREADS * stride * sizeof(float);
   int64_t blocks = (n + PREP_THREADS - 1) / PREP_THREADS;
   prof_begin(0, st);
+  larnd_runs_cache_drop(ws.rec);  // the records change: sorted run tables built from the old ones are stale
   k_prepare<<<(unsigned)blocks, PREP_THREADS, smem, st>>>(tracks, n, cols, p, lut ? lut->nt : 0, lut ? lut->ntpl : p.n_templates, ws.rec, ws.bitmap,
                                                          ws.n_words, ws.pid_offset, counts);
   prof_end(0, st);

@@ -204,8 +204,10 @@ __global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
 
 
 // fills the fields every sorted kernel needs and (re)builds the sorted run table + tile table on `st`
+// reuse: LARND_FLAG_REUSE_RUNS was given — when the library's record says this workspace still holds the tables of these
+// records, only the tile counters are reset (the three kernels below cost 0.36 ms per 10 M segments).
 inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
-                                 int32_t npix_capacity, const int32_t* counts, cudaStream_t st) {
+                                 int32_t npix_capacity, const int32_t* counts, cudaStream_t st, bool reuse = false) {
   if (n >= (int64_t)1 << 31) { larnd_set_error("sorted accumulate: n must be < 2^31"); return LARND_E_ARG; }
   A.rec = ws.rec; A.n = n;
   A.r0 = lut->r0; A.rm = lut->rm; A.c0 = lut->c0; A.cm = lut->cm; A.sr = lut->sr; A.sc = lut->sc;
@@ -229,6 +231,10 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   A.gcnt = ws.gcnt;
   A.ncls = lut->ntpl * A.nb * A.nb * (SPAN_MAX_S + 1);
   A.row0 = ws.row0;
+  if (reuse && larnd_runs_cache_valid(ws.rec, n, lut, p.n_ticks)) {
+    LARND_CUDA(cudaMemsetAsync(ws.gcnt + GC_FWD, 0, 16 * sizeof(int), st));  // tile counters of the forward and backward launches
+    return LARND_OK;
+  }
   LARND_CUDA(cudaMemsetAsync(ws.class_count, 0, (size_t)A.ncls * 4 * sizeof(int), st));
   LARND_CUDA(cudaMemsetAsync(ws.gcnt, 0, 256, st));
   const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
@@ -240,6 +246,7 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   if (blocks > 148 * 32) blocks = 148 * 32;
   k_scatter_runs<<<(unsigned)blocks, 256, 0, st>>>(A);
   LARND_LAUNCH_CHECK("k_scatter_runs");
+  larnd_runs_cache_set(ws.rec, n, lut, p.n_ticks);
   return LARND_OK;
 }
 

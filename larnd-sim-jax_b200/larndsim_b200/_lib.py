@@ -23,7 +23,7 @@ PARAM_ORDER = ("Ab", "kb", "eField", "lifetime", "long_diff", "tran_diff", "shif
                "alpha", "beta", "R_param", "lArDensity", "MeVToElectrons", "vdrift")
 
 # flags of larnd_lut_forward / _accumulate / _backward (include/larnd_b200.h)
-FLAG_SKIP_GARBAGE, FLAG_IMPL_CHUNK, FLAG_IMPL_SORTED, FLAG_NO_SPLIT = 1, 2, 4, 8
+FLAG_SKIP_GARBAGE, FLAG_IMPL_CHUNK, FLAG_IMPL_SORTED, FLAG_NO_SPLIT, FLAG_REUSE_RUNS = 1, 2, 4, 8, 16
 
 # record fields inside the workspace (enum in larnd_b200.h)
 REC_FIELDS = ("Q", "FRAC", "SL", "A", "B", "C", "WX0", "WX1", "WX2", "WX3", "WX4", "WY0", "WY1", "WY2", "WY3", "WY4",

@@ -272,12 +272,12 @@ class FusedFitStep:
             if self.use_steps:   # the two VJPs without the dense (npix, n_ticks) waveform gradient: step events per pixel row
                 check(lib.larnd_fee_backward_steps(ptr(self.g_adc), ptr(self.saved), ptr(self.upix), npix, P, ptr(self.steps),
                                                    self.steps.numel(), 0, stream))
-                check(lib.larnd_lut_backward_steps(self.n, P, self.lut.handle, pr.n_events, npix, 0, ptr(self.workspace), self.ws_bytes,
+                check(lib.larnd_lut_backward_steps(self.n, P, self.lut.handle, pr.n_events, npix, self._lib.FLAG_REUSE_RUNS, ptr(self.workspace), self.ws_bytes,
                                                    ptr(self.counts), ptr(self.steps), self.steps.numel(), ptr(self.grad), stream))
             else:
                 g1 = C.c_void_p(self.g_wfs.data_ptr() + 4)
                 check(lib.larnd_fee_backward(ptr(self.g_adc), ptr(self.ticks), ptr(self.saved), npix, P, g1, self.g_wfs.stride(0), 0, stream))
-                check(lib.larnd_lut_backward(self.n, P, self.lut.handle, pr.n_events, npix, 1, ptr(self.workspace), self.ws_bytes,
+                check(lib.larnd_lut_backward(self.n, P, self.lut.handle, pr.n_events, npix, 1 | self._lib.FLAG_REUSE_RUNS, ptr(self.workspace), self.ws_bytes,
                                              ptr(self.counts), ptr(self.g_wfs), self.g_wfs.stride(0), ptr(self.grad), stream))
             if pr.distributed:
                 dist.all_reduce(self.grad, group=pr.group)

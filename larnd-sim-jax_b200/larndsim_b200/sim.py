@@ -326,7 +326,8 @@ def lut_backward(st, g_wfs, skip_garbage=False):
     grad = torch.zeros(_lib.NPARAMS, dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device):
         # column c of the full row (c >= 1) is g[:, c-1]: pass g - 1 element with stride Nticks-1
-        bflags = (1 if skip_garbage else 0) | (st.flags & ~1) | env_flags()
+        # the LutState's workspace is written by lut_forward only, so the run / tile tables it built are the ones to reuse
+        bflags = (1 if skip_garbage else 0) | (st.flags & ~1) | env_flags() | _lib.FLAG_REUSE_RUNS
         impl = os.environ.get("LARND_BWD_IMPL", "")
         if impl:
             bflags = (bflags & ~(_lib.FLAG_IMPL_CHUNK | _lib.FLAG_IMPL_SORTED)) | (_lib.FLAG_IMPL_SORTED if impl.startswith("s") else _lib.FLAG_IMPL_CHUNK)
@@ -601,7 +602,7 @@ def hits_backward(st, fs, g_adc, raw_charge=False, steps=None):
     with torch.cuda.device(g.device):
         _lib.check(lib.larnd_fee_backward_steps(_ptr(g), _ptr(fs.saved), _ptr(st.unique_pixels), st.npix, C.byref(fs.pod), _ptr(steps),
                                                 steps.numel(), 1 if raw_charge else 0, _stream()))
-        bflags = (st.flags & ~1) | env_flags()
+        bflags = (st.flags & ~1) | env_flags() | _lib.FLAG_REUSE_RUNS
         impl = os.environ.get("LARND_BWD_IMPL", "")
         if impl:
             bflags = (bflags & ~(_lib.FLAG_IMPL_CHUNK | _lib.FLAG_IMPL_SORTED)) | (_lib.FLAG_IMPL_SORTED if impl.startswith("s") else _lib.FLAG_IMPL_CHUNK)

@@ -1075,3 +1075,43 @@ def test_steps_backward_equals_dense_backward(torch_dev, cfg, bwd, monkeypatch):
     dense_q = sim.lut_backward(st, sim.fee_backward(fs, g_adc, raw_charge=True)).cpu().numpy().astype(np.float64)
     steps_q = sim.hits_backward(st, fs, g_adc, raw_charge=True).cpu().numpy().astype(np.float64)
     assert (np.abs(steps_q - dense_q)[used] <= 1e-3 * np.abs(dense_q)[used]).all()
+
+
+@pytest.mark.gpu
+def test_autograd_hands_the_front_end_vjp_over_as_step_events(torch_dev, monkeypatch):
+    """simulate_wfs -> simulate_stochastic chained under torch.autograd: from STEPS_AUTOGRAD_MIN_SEGMENTS on, the front end's
+    node hands its VJP to simulate_wfs' node as step events (sim._StepsLink) instead of a dense (Npix, Nticks) gradient.  Same
+    gradients as the dense route; with a second consumer of the waveforms the placeholder is summed away by autograd and the
+    dense front-end gradient is added back."""
+    import torch
+    from larndsim_b200 import sim
+    kw = dict(number_pix_neighbors=2, signal_length=150)
+    names = ("Ab", "kb", "eField", "lifetime", "tran_diff", "long_diff")
+    bank = torch.as_tensor(cm.synthetic_bank(32, 25, 25, 1950), device=torch_dev)
+    tr = torch.as_tensor(cm.small_batch(1200, ibatch=1, pad=0, precision=0.01), device=torch_dev)
+
+    def grads(min_segments, second_consumer):
+        monkeypatch.setattr(sim, "STEPS_AUTOGRAD_MIN_SEGMENTS", min_segments)
+        P = cm.product_params(grad=names, **kw)
+        calls = {"steps": 0, "dense": 0}
+        hb, lb_ = sim.hits_backward, sim.lut_backward
+        monkeypatch.setattr(sim, "hits_backward", lambda *a, **k: (calls.__setitem__("steps", calls["steps"] + 1), hb(*a, **k))[1])
+        monkeypatch.setattr(sim, "lut_backward", lambda *a, **k: (calls.__setitem__("dense", calls["dense"] + 1), lb_(*a, **k))[1])
+        wfs, upix = sim.simulate_wfs(P, bank, tr, cm.FIELDS)
+        out = sim.simulate_stochastic(P, wfs, upix, 0)
+        loss = (out[0] ** 2).sum() * 1e-4 + (out[3] ** 2).sum() * 1e-3
+        if second_consumer:
+            loss = loss + (wfs[1:] ** 2).sum() * 1e-6
+        loss.backward()
+        monkeypatch.setattr(sim, "hits_backward", hb)
+        monkeypatch.setattr(sim, "lut_backward", lb_)
+        return np.array([float(getattr(P, n).grad) for n in names]), calls, float(loss)
+
+    for second in (False, True):
+        g_dense, c_dense, l_dense = grads(1 << 40, second)
+        g_steps, c_steps, l_steps = grads(0, second)
+        assert c_dense == {"steps": 0, "dense": 1}
+        assert c_steps == ({"steps": 0, "dense": 1} if second else {"steps": 1, "dense": 0})
+        assert abs(l_dense - l_steps) <= 1e-5 * abs(l_dense)
+        tol = np.where(np.array(names) == "long_diff", 5e-3, 1e-3)   # cancelling template sums in float32 (see above)
+        assert (np.abs(g_steps - g_dense) <= tol * np.abs(g_dense) + 1e-12).all(), (second, g_steps, g_dense)
