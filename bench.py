@@ -7,8 +7,8 @@ One *step* = one pass of the hot path over one synthetic spill batch of the prep
 (SURVEY.md §8d config 5): prepare -> unique/renumber -> LUT accumulate -> fused FEE/ADC (+ hit compaction).
 `value`      : forward segments/s with the batch already resident in HBM (CUDA events, max over ranks).
 `e2e`        : the same through the reference-facing entry (dataio.simulate_from_raw's path): the RAW, un-chopped rows
-               of the batch are copied from pinned host memory, chopped on the device, simulated, and the hit list is
-               read back — all inside the timed region.  `e2e_chopped` / `e2e_packed`: a caller that holds CHOPPED
+               of the batch are copied from pinned host memory, chopped on the device (inside the prepare kernel),
+               simulated, and the hit list is read back — all inside the timed region.  `e2e_chopped` / `e2e_packed`: a caller that holds CHOPPED
                batches on the host uploads all 26 columns (104 B/segment) / the 10 columns the simulation reads (40 B).
 `fwd_grad`   : forward + loss + backward (FEE VJP -> accumulate VJP -> 15 parameter gradients, all-reduced over ranks).
 `mc_mode`    : BASELINE config 3 (MC-current mode) forward and forward+grad.
@@ -283,8 +283,8 @@ def run_ours(args):
     pod = st0.pod
     del st0
 
-    def fwd(flags=0, src=tracks, flds=fields):
-        st = sim.lut_forward(params, bank, src, flds, npix_capacity=npix, n_events=n_events, flags=flags, out=out)
+    def fwd(flags=0, src=tracks, flds=fields, raw=None):
+        st = sim.lut_forward(params, bank, src, flds, npix_capacity=npix, n_events=n_events, flags=flags, out=out, raw=raw)
         fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True, pod=pod)
         return st, fs
 
@@ -333,9 +333,17 @@ def run_ours(args):
     # preallocated buffers): H2D of the RAW, un-chopped rows (what the input file holds), chop on the device, forward, D2H
     # of the hit list.  The reference chops on the host and ships 104 B per chopped segment.
     raw_dev = torch.empty(raw_host.shape, dtype=torch.float32, device=dev)
-    chop_buf = torch.empty_like(tracks)
 
     def e2e_step():
+        raw_dev.copy_(raw_host, non_blocking=True)
+        # chop_tracks fused into the prepare kernel (larnd_lut_prepare_raw): the chopped (n, 26) batch is never written
+        st, fs = fwd(src=raw_dev, raw=(PRECISION, nseg))
+        read_back_hits(fs)
+        return fs
+
+    chop_buf = torch.empty_like(tracks)
+
+    def e2e_step_unfused():   # the same entry with a separate chop kernel (round-2 path), reported as e2e_chop_first
         raw_dev.copy_(raw_host, non_blocking=True)
         dataio.chop_tracks(raw_dev, fields, PRECISION, out=chop_buf)
         st, fs = fwd(src=chop_buf)
@@ -408,6 +416,8 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_fwd, launches = timed(fwd, args.steps, args.warmup, sampler)
     ms_e2e, _ = timed(e2e_step, args.steps, w3, join=copy_stream)
+    ms_e2e_u, _ = timed(e2e_step_unfused, args.steps, w3, join=copy_stream)
+    del chop_buf
     step_c, bufs_c = make_chopped_step(tracks_host, fields)
     ms_e2e_c, _ = timed(step_c, args.steps, w3, join=copy_stream)
     del step_c, bufs_c
@@ -620,8 +630,12 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": seg_s(ms_e2e), "unit": "segments/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(raw_host.numel() * 4), "d2h_bytes_per_step": hits_bytes,
-                    "entry": "dataio.simulate_from_raw path: raw (un-chopped) rows uploaded from pinned memory, chop_tracks on the "
-                             "device (csrc/chop.cu), simulate_wfs + simulate_stochastic, hit list read back"},
+                    "entry": "dataio.simulate_from_raw path: raw (un-chopped) rows uploaded from pinned memory, chop_tracks fused into "
+                             "the prepare kernel (larnd_lut_prepare_raw: the chopped batch is never written), simulate_wfs + "
+                             "simulate_stochastic, hit list read back"},
+            "e2e_chop_first": {"value": seg_s(ms_e2e_u), "unit": "segments/s", "ms_per_step": ms_e2e_u,
+                               "note": "same entry with the separate chop kernel (csrc/chop.cu writes the chopped (n, 26) batch, "
+                                       "larnd_lut_prepare reads it back): the round-2 path"},
             "e2e_chopped": {"value": seg_s(ms_e2e_c), "unit": "segments/s", "ms_per_step": ms_e2e_c,
                             "h2d_bytes_per_step": int(tracks_host.numel() * 4), "d2h_bytes_per_step": hits_bytes,
                             "note": "host-chopped batch, all 26 columns uploaded (104 B/segment), double-buffered"},

@@ -298,6 +298,18 @@ int larnd_chop_count(const float* raw_d, int64_t m, const larnd_chop_columns_t* 
 int larnd_chop_tracks(const float* raw_d, int64_t m, const larnd_chop_columns_t* cols, double precision,
                       const int64_t* offsets_d, float* out_d, int64_t capacity, void* stream);
 
+/* larnd_lut_prepare for RAW (un-chopped) rows: chop_tracks fused into the drift / pixelisation stage.  Segment s of the batch
+ * (0 <= s < n_segments, the caller's capacity; workspace sized for n_segments) is piece s - offsets_d[i] of raw row i, its
+ * ten simulation columns formed in registers with chop_tracks' arithmetic (bit-identical to larnd_chop_tracks), so the
+ * chopped (n, ncols) batch of optimize/dataio.py:63-106 — 104 B per segment written and read back — never exists.
+ * Segments beyond offsets_d[m] are the invalid rows pad_batch appends (:340-373).  offsets_d: larnd_chop_count's output for
+ * the same rows and precision.  offsets_d[m] > n_segments sets bit 3 of counts_d[2] (outputs invalid, kernels bail out).
+ * Follow with larnd_lut_accumulate(n_segments, ...) / the backward entry points as after larnd_lut_prepare. */
+int larnd_lut_prepare_raw(const float* raw_d, int64_t m, const larnd_chop_columns_t* chop_cols, const larnd_columns_t* cols,
+                          double precision, const int64_t* offsets_d, int64_t n_segments, const larnd_params_t* params,
+                          const larnd_lut_t* lut, int32_t n_events, void* workspace_d, size_t workspace_bytes,
+                          int32_t* counts_d, void* stream);
+
 /* Batch assembly around the chop (TracksDataset.__getitem__ / pad_batch, optimize/dataio.py:340-406, :47-61): the file's
  * rows stay on the device; a batch is a list of row indices with the batch-local event id of every row.
  *   larnd_batch_gather: out_d (m, ncols) = raw_d[rows_d[i]] with column event_col replaced by local_event_d[i]

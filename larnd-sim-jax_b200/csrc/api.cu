@@ -169,6 +169,32 @@ extern "C" int larnd_lut_prepare(const float* tracks_d, int64_t n, const larnd_c
   return larnd_launch_scan(ws, *p, counts_d, st);
 }
 
+extern "C" int larnd_lut_prepare_raw(const float* raw_d, int64_t m, const larnd_chop_columns_t* chop_cols, const larnd_columns_t* cols,
+                                     double precision, const int64_t* offsets_d, int64_t n, const larnd_params_t* p,
+                                     const larnd_lut_t* lut, int32_t n_events, void* workspace_d, size_t workspace_bytes,
+                                     int32_t* counts_d, void* stream) {
+  int rc = check_common(p, lut, true);
+  if (rc) return rc;
+  if ((!raw_d && m > 0) || !chop_cols || !cols || !offsets_d || !counts_d || n < 0 || m < 0 || !(precision > 0)) {
+    larnd_set_error("larnd_lut_prepare_raw: bad argument");
+    return LARND_E_ARG;
+  }
+  // both column maps describe the same raw row: the chopped columns the simulation reads must be the ones the chop produces
+  if (chop_cols->ncols != cols->ncols || chop_cols->x != cols->x || chop_cols->y != cols->y || chop_cols->z != cols->z ||
+      chop_cols->z_start != cols->z_start || chop_cols->z_end != cols->z_end || chop_cols->dx != cols->dx || chop_cols->dE != cols->dE) {
+    larnd_set_error("larnd_lut_prepare_raw: chop_cols and cols disagree about the row layout");
+    return LARND_E_ARG;
+  }
+  Workspace ws;
+  if (!larnd_carve_workspace(workspace_d, workspace_bytes, n, n_events, p->n_tpc, p->n_pixels_x, p->n_pixels_y, &ws)) {
+    larnd_set_error("workspace too small: need %zu bytes", larnd_workspace_bytes(n, n_events, p->n_tpc, p->n_pixels_x, p->n_pixels_y));
+    return LARND_E_CAPACITY;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = larnd_launch_prepare_raw(raw_d, m, *chop_cols, *cols, precision, offsets_d, n, *p, lut, ws, counts_d, st))) return rc;
+  return larnd_launch_scan(ws, *p, counts_d, st);
+}
+
 static int lut_accumulate_impl(int64_t n, const larnd_params_t* p, const larnd_lut_t* lut, int32_t n_events,
                                int32_t npix_capacity, int32_t flags, void* workspace_d, size_t workspace_bytes,
                                int32_t* unique_pixels_d, float* wfs_d, int64_t wfs_row_stride, int32_t* counts_d, void* stream,

@@ -10,34 +10,9 @@
 // float64 (int64 array * Python float * float32 scalar), rounded to float32 on assignment; dE of the inner pieces is
 // float32 (float32 array * weak Python float / float32 scalar); the last piece is computed in float64 and rounded.
 #include "larnd_common.cuh"
+#include "chop_math.cuh"
 
 namespace {
-
-struct ChopGeom {
-  float len;       // float32 sqrt(sum(seg**2))
-  float dir[3];    // float32 seg / (len + 1e-10)
-};
-
-__device__ __forceinline__ ChopGeom chop_geom(const float* tr, const larnd_chop_columns_t& c) {
-  ChopGeom g;
-  const float sx = __fsub_rn(tr[c.x_end], tr[c.x_start]);
-  const float sy = __fsub_rn(tr[c.y_end], tr[c.y_start]);
-  const float sz = __fsub_rn(tr[c.z_end], tr[c.z_start]);
-  // np.sum over 3 float32 elements: sequential adds, no FMA contraction
-  const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fmul_rn(sz, sz));
-  g.len = __fsqrt_rn(s2);
-  const float den = __fadd_rn(g.len, 1e-10f);
-  g.dir[0] = __fdiv_rn(sx, den);
-  g.dir[1] = __fdiv_rn(sy, den);
-  g.dir[2] = __fdiv_rn(sz, den);
-  return g;
-}
-
-__device__ __forceinline__ long long chop_nsteps(float len, float prec32) {
-  // np.maximum(np.ceil(length / precision), 1).astype(int): float32 array / weak Python float -> float32
-  const float q = ceilf(__fdiv_rn(len, prec32));
-  return (long long)fmaxf(q, 1.0f);
-}
 
 __global__ void k_chop_count(const float* __restrict__ raw, int64_t m, const __grid_constant__ larnd_chop_columns_t c,
                              float prec32, int64_t* __restrict__ counts) {

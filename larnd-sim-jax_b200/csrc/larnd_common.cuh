@@ -206,6 +206,9 @@ bool larnd_runs_cache_valid(const void* rec, int64_t n, const void* lut, int n_t
 // kernels / launchers implemented in the .cu files
 int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& cols, const larnd_params_t& p,
                          const larnd_lut* lut, const Workspace& ws, int32_t* counts, cudaStream_t st);
+int larnd_launch_prepare_raw(const float* raw, int64_t m, const larnd_chop_columns_t& cc, const larnd_columns_t& cols, double precision,
+                             const int64_t* offsets, int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                             int32_t* counts, cudaStream_t st);
 int larnd_launch_unique(const Workspace& ws, const larnd_params_t& p, int32_t npix_capacity, int32_t extra, int32_t* unique_pixels,
                         int32_t* counts, cudaStream_t st);
 int larnd_launch_scan(const Workspace& ws, const larnd_params_t& p, int32_t* counts, cudaStream_t st);

@@ -10,10 +10,111 @@
 // evaluates these op by op in float32 and the ids must match bit for bit.
 #include "larnd_common.cuh"
 #include "segment_physics.cuh"
+#include "chop_math.cuh"
 
 namespace {
 
 constexpr int PREP_THREADS = 128;
+
+// One segment: physics, bins, diffusion weights, tick / template records (tr: its row, cols: where the ten columns sit in it).
+// Returns the main-pixel id.
+__device__ __forceinline__ int prepare_segment(const float* tr, const larnd_columns_t& cols, const larnd_params_t& p, int nt, int bank_ntpl,
+                                               float* __restrict__ rec, int64_t n, int64_t s, int32_t* __restrict__ counts) {
+  const SegPhys ph = segment_physics(tr, cols, p);
+  const float x = ph.x, y = ph.y, z = ph.z, q = ph.q, td = ph.td, sl_cm = ph.sl_cm, sT = ph.sT;
+  const float recomb = ph.recomb, xi = ph.xi, cos2 = ph.cos2, z_anode = ph.z_anode, z_cath = ph.z_cath;
+  const int plane = ph.plane;
+  const bool inside = ph.inside;
+  // sub-pixel bins and in-bin position
+  float xr = fsub(x, p.tpc_borders[plane][0][0]);
+  float yr = fsub(y, p.tpc_borders[plane][1][0]);
+  int bx = (int)floor_divide_f(xr, p.bin_width);
+  int by = (int)floor_divide_f(yr, p.bin_width);
+  float x0 = remainder_f(xr, p.bin_width);
+  float y0 = remainder_f(yr, p.bin_width);
+  // transverse diffusion weights: 5 bin integrals per axis, outer edges forced to -1/+1
+  const float s2sig = fmul(1.41421354f, sT);
+  float ex[LARND_NB_TRAN_BINS + 1], ey[LARND_NB_TRAN_BINS + 1];
+  ex[0] = ey[0] = -1.0f;
+  ex[LARND_NB_TRAN_BINS] = ey[LARND_NB_TRAN_BINS] = 1.0f;
+#pragma unroll
+  for (int k = 1; k < LARND_NB_TRAN_BINS; ++k) {
+    ex[k] = erff(fdiv(fsub(p.tran_bin_edges[k], x0), s2sig));
+    ey[k] = erff(fdiv(fsub(p.tran_bin_edges[k], y0), s2sig));
+  }
+#pragma unroll
+  for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
+    rec[(int64_t)(LARND_F_WX0 + k) * n + s] = fmul(0.5f, fsub(ex[k + 1], ex[k]));
+    rec[(int64_t)(LARND_F_WY0 + k) * n + s] = fmul(0.5f, fsub(ey[k + 1], ey[k]));
+  }
+  // time to the cathode -> tick + fraction (sim_jax.py:418-420,157-159)
+  float t0 = fdiv(fabsf(fsub(z, z_cath)), p.vdrift);
+  float ft = fdiv(t0, p.t_sampling);
+  int ct = (int)floorf(ft);
+  ct = max(0, min(ct, nt - 1));
+  float frac = fsub(ft, (float)ct);
+  // longitudinal diffusion in ticks -> template index + Lagrange weights (sim_jax.py:423,162-168)
+  float sl = fdiv(fdiv(sl_cm, p.vdrift), p.t_sampling);
+  int lo = 0, hi = p.n_templates;  // searchsorted side='left': number of template values < sl
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (p.long_diff_template[mid] < sl) lo = mid + 1; else hi = mid;
+  }
+  int idx = max(1, min(lo, p.n_templates - 2));
+  // a bank truncated to fewer rows than long_diff_template (tests bound memory that way) is valid as long as no segment
+  // needs a missing row; one that does is flagged (bit 2 of counts[2]) and clamped so that nothing reads out of bounds
+  if (idx + 1 >= bank_ntpl) { if (q != 0.0f) atomicOr(counts + 2, 4); idx = max(1, bank_ntpl - 2); }
+  float t0v = p.long_diff_template[idx - 1], t1v = p.long_diff_template[idx], t2v = p.long_diff_template[idx + 1];
+  float a = fdiv(fmul(fsub(sl, t1v), fsub(sl, t2v)), fmul(fsub(t0v, t1v), fsub(t0v, t2v)));
+  float b = fdiv(fmul(fsub(sl, t0v), fsub(sl, t2v)), fmul(fsub(t1v, t0v), fsub(t1v, t2v)));
+  float c = fdiv(fmul(fsub(sl, t0v), fsub(sl, t1v)), fmul(fsub(t2v, t0v), fsub(t2v, t1v)));
+  int ev = (int)tr[cols.eventID];
+  int ep = ev * p.n_tpc + plane;
+  const int nb = p.nb_sampling_bins_per_pixel;
+  const int pid = pixel2id_dev(floordiv_i(bx, nb), floordiv_i(by, nb), ep, p.n_pixels_x, p.n_pixels_y);
+  int flags = (inside ? 1 : 0) | (fsub(z, z_anode) > 0.0f ? 2 : 0) | (fsub(z, z_cath) > 0.0f ? 4 : 0);
+  rec[(int64_t)LARND_F_Q * n + s] = q;
+  rec[(int64_t)LARND_F_FRAC * n + s] = frac;
+  rec[(int64_t)LARND_F_SL * n + s] = sl;
+  rec[(int64_t)LARND_F_A * n + s] = a;
+  rec[(int64_t)LARND_F_B * n + s] = b;
+  rec[(int64_t)LARND_F_C * n + s] = c;
+  rec[(int64_t)LARND_F_TD * n + s] = td;
+  rec[(int64_t)LARND_F_X0 * n + s] = x0;
+  rec[(int64_t)LARND_F_Y0 * n + s] = y0;
+  rec[(int64_t)LARND_F_ST * n + s] = sT;
+  rec[(int64_t)LARND_F_REC * n + s] = recomb;
+  rec[(int64_t)LARND_F_FT * n + s] = ft;
+  rec[(int64_t)LARND_F_XI * n + s] = xi;
+  rec[(int64_t)LARND_F_COS2 * n + s] = cos2;
+  int* irec = reinterpret_cast<int*>(rec);
+  irec[(int64_t)LARND_I_T0 * n + s] = nt - p.signal_length - ct;
+  irec[(int64_t)LARND_I_IDX * n + s] = idx;
+  irec[(int64_t)LARND_I_BX * n + s] = bx;
+  irec[(int64_t)LARND_I_BY * n + s] = by;
+  irec[(int64_t)LARND_I_EP * n + s] = ep;
+  irec[(int64_t)LARND_I_FLAGS * n + s] = flags;
+  irec[(int64_t)LARND_I_MAINPIX * n + s] = pid;
+  return pid;
+}
+
+// mark the main pixels of a warp's segments in the bitmap: one atomic per distinct id per warp
+__device__ __forceinline__ void mark_main_pixel(bool pid_ok, int pid, uint32_t* __restrict__ bitmap, int64_t n_words, int pid_offset,
+                                                int32_t* __restrict__ counts) {
+  unsigned live = __ballot_sync(0xffffffffu, pid_ok);
+  if (pid_ok) {
+    unsigned peers = __match_any_sync(live, pid);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      long long bidx = (long long)pid + pid_offset;
+      if (bidx < 0 || (bidx >> 5) >= n_words) {
+        atomicOr(counts + 2, 2);  // event id outside the declared [-1, n_events) range
+      } else {
+        uint32_t bit = 1u << (bidx & 31);
+        if (!(__ldg(bitmap + (bidx >> 5)) & bit)) atomicOr(bitmap + (bidx >> 5), bit);
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(PREP_THREADS)
 k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ larnd_columns_t cols,
@@ -57,101 +158,71 @@ k_prepare(const float* __restrict__ tracks, int64_t n, const __grid_constant__ l
   const int t = threadIdx.x;
   const bool active = t < rows_here;
   int pid = 0;
-  bool pid_ok = false;
-  if (active) {
-    const float* tr = srow + t * stride;
-    const int64_t s = base + t;
-    const SegPhys ph = segment_physics(tr, cols, p);
-    const float x = ph.x, y = ph.y, z = ph.z, q = ph.q, td = ph.td, sl_cm = ph.sl_cm, sT = ph.sT;
-    const float recomb = ph.recomb, xi = ph.xi, cos2 = ph.cos2, z_anode = ph.z_anode, z_cath = ph.z_cath;
-    const int plane = ph.plane;
-    const bool inside = ph.inside;
-    // sub-pixel bins and in-bin position
-    float xr = fsub(x, p.tpc_borders[plane][0][0]);
-    float yr = fsub(y, p.tpc_borders[plane][1][0]);
-    int bx = (int)floor_divide_f(xr, p.bin_width);
-    int by = (int)floor_divide_f(yr, p.bin_width);
-    float x0 = remainder_f(xr, p.bin_width);
-    float y0 = remainder_f(yr, p.bin_width);
-    // transverse diffusion weights: 5 bin integrals per axis, outer edges forced to -1/+1
-    const float s2sig = fmul(1.41421354f, sT);
-    float ex[LARND_NB_TRAN_BINS + 1], ey[LARND_NB_TRAN_BINS + 1];
-    ex[0] = ey[0] = -1.0f;
-    ex[LARND_NB_TRAN_BINS] = ey[LARND_NB_TRAN_BINS] = 1.0f;
-#pragma unroll
-    for (int k = 1; k < LARND_NB_TRAN_BINS; ++k) {
-      ex[k] = erff(fdiv(fsub(p.tran_bin_edges[k], x0), s2sig));
-      ey[k] = erff(fdiv(fsub(p.tran_bin_edges[k], y0), s2sig));
-    }
-#pragma unroll
-    for (int k = 0; k < LARND_NB_TRAN_BINS; ++k) {
-      rec[(int64_t)(LARND_F_WX0 + k) * n + s] = fmul(0.5f, fsub(ex[k + 1], ex[k]));
-      rec[(int64_t)(LARND_F_WY0 + k) * n + s] = fmul(0.5f, fsub(ey[k + 1], ey[k]));
-    }
-    // time to the cathode -> tick + fraction (sim_jax.py:418-420,157-159)
-    float t0 = fdiv(fabsf(fsub(z, z_cath)), p.vdrift);
-    float ft = fdiv(t0, p.t_sampling);
-    int ct = (int)floorf(ft);
-    ct = max(0, min(ct, nt - 1));
-    float frac = fsub(ft, (float)ct);
-    // longitudinal diffusion in ticks -> template index + Lagrange weights (sim_jax.py:423,162-168)
-    float sl = fdiv(fdiv(sl_cm, p.vdrift), p.t_sampling);
-    int lo = 0, hi = p.n_templates;  // searchsorted side='left': number of template values < sl
+  if (active) pid = prepare_segment(srow + t * stride, cols, p, nt, bank_ntpl, rec, n, base + t, counts);
+  mark_main_pixel(active, pid, bitmap, n_words, pid_offset, counts);
+}
+
+// The same records straight from the RAW (un-chopped) rows: thread <-> chopped segment s of the batch.  The piece (raw row i,
+// index k) is found in the prefix table of larnd_chop_count, its ten simulation columns are formed in registers with
+// chop_tracks' arithmetic (chop_math.cuh: bit-identical to k_chop_expand) and handed to prepare_segment — the chopped
+// (n, 26) batch (104 B per segment written by the chop kernel and read back here) never exists.  Segments s >= total
+// (the batch is sized for `n` slots) are the invalid rows pad_batch appends: eventID -1, everything else 0.
+__global__ void __launch_bounds__(PREP_THREADS)
+k_prepare_raw(const float* __restrict__ raw, int64_t m, const __grid_constant__ larnd_chop_columns_t cc,
+              const __grid_constant__ larnd_columns_t cols, double precision, float prec32, const int64_t* __restrict__ offsets,
+              int64_t n, const __grid_constant__ larnd_params_t p, int nt, int bank_ntpl, float* __restrict__ rec,
+              uint32_t* __restrict__ bitmap, int64_t n_words, int pid_offset, int32_t* __restrict__ counts) {
+  __shared__ int64_t s_i0;
+  const int64_t base = (int64_t)blockIdx.x * PREP_THREADS;
+  const int64_t total = offsets[m];
+  if (total > n) {  // more pieces than segment slots: flagged, the accumulate kernels bail out on counts[2] != 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(counts + 2, 8);
+    return;
+  }
+  if (threadIdx.x == 0) {
+    int64_t lo = 0, hi = m > 0 ? m - 1 : 0;  // largest i with offsets[i] <= base (every raw row has at least one piece)
     while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (p.long_diff_template[mid] < sl) lo = mid + 1; else hi = mid;
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (offsets[mid] <= base) lo = mid; else hi = mid - 1;
     }
-    int idx = max(1, min(lo, p.n_templates - 2));
-    // a bank truncated to fewer rows than long_diff_template (tests bound memory that way) is valid as long as no segment
-    // needs a missing row; one that does is flagged (bit 2 of counts[2]) and clamped so that nothing reads out of bounds
-    if (idx + 1 >= bank_ntpl) { if (q != 0.0f) atomicOr(counts + 2, 4); idx = max(1, bank_ntpl - 2); }
-    float t0v = p.long_diff_template[idx - 1], t1v = p.long_diff_template[idx], t2v = p.long_diff_template[idx + 1];
-    float a = fdiv(fmul(fsub(sl, t1v), fsub(sl, t2v)), fmul(fsub(t0v, t1v), fsub(t0v, t2v)));
-    float b = fdiv(fmul(fsub(sl, t0v), fsub(sl, t2v)), fmul(fsub(t1v, t0v), fsub(t1v, t2v)));
-    float c = fdiv(fmul(fsub(sl, t0v), fsub(sl, t1v)), fmul(fsub(t2v, t0v), fsub(t2v, t1v)));
-    int ev = (int)tr[cols.eventID];
-    int ep = ev * p.n_tpc + plane;
-    const int nb = p.nb_sampling_bins_per_pixel;
-    pid = pixel2id_dev(floordiv_i(bx, nb), floordiv_i(by, nb), ep, p.n_pixels_x, p.n_pixels_y);
-    pid_ok = true;
-    int flags = (inside ? 1 : 0) | (fsub(z, z_anode) > 0.0f ? 2 : 0) | (fsub(z, z_cath) > 0.0f ? 4 : 0);
-    rec[(int64_t)LARND_F_Q * n + s] = q;
-    rec[(int64_t)LARND_F_FRAC * n + s] = frac;
-    rec[(int64_t)LARND_F_SL * n + s] = sl;
-    rec[(int64_t)LARND_F_A * n + s] = a;
-    rec[(int64_t)LARND_F_B * n + s] = b;
-    rec[(int64_t)LARND_F_C * n + s] = c;
-    rec[(int64_t)LARND_F_TD * n + s] = td;
-    rec[(int64_t)LARND_F_X0 * n + s] = x0;
-    rec[(int64_t)LARND_F_Y0 * n + s] = y0;
-    rec[(int64_t)LARND_F_ST * n + s] = sT;
-    rec[(int64_t)LARND_F_REC * n + s] = recomb;
-    rec[(int64_t)LARND_F_FT * n + s] = ft;
-    rec[(int64_t)LARND_F_XI * n + s] = xi;
-    rec[(int64_t)LARND_F_COS2 * n + s] = cos2;
-    int* irec = reinterpret_cast<int*>(rec);
-    irec[(int64_t)LARND_I_T0 * n + s] = nt - p.signal_length - ct;
-    irec[(int64_t)LARND_I_IDX * n + s] = idx;
-    irec[(int64_t)LARND_I_BX * n + s] = bx;
-    irec[(int64_t)LARND_I_BY * n + s] = by;
-    irec[(int64_t)LARND_I_EP * n + s] = ep;
-    irec[(int64_t)LARND_I_FLAGS * n + s] = flags;
-    irec[(int64_t)LARND_I_MAINPIX * n + s] = pid;
+    s_i0 = lo;
   }
-  // mark the main pixel in the bitmap: one atomic per distinct id per warp
-  unsigned live = __ballot_sync(0xffffffffu, pid_ok);
-  if (pid_ok) {
-    unsigned peers = __match_any_sync(live, pid);
-    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-      long long bidx = (long long)pid + pid_offset;
-      if (bidx < 0 || (bidx >> 5) >= n_words) {
-        atomicOr(counts + 2, 2);  // event id outside the declared [-1, n_events) range
-      } else {
-        uint32_t bit = 1u << (bidx & 31);
-        if (!(__ldg(bitmap + (bidx >> 5)) & bit)) atomicOr(bitmap + (bidx >> 5), bit);
+  __syncthreads();
+  const int64_t s = base + threadIdx.x;
+  const bool active = s < n;
+  int pid = 0;
+  if (active) {
+    // ten columns in the ABI's order: eventID, x, y, z, z_start, z_end, dx, dEdx, dE, t0
+    float loc[10] = {-1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (s < total) {
+      int64_t i = s_i0;
+      while (i + 1 < m && offsets[i + 1] <= s) ++i;
+      const float* tr = raw + i * cc.ncols;
+      const ChopGeom g = chop_geom(tr, cc);
+      const long long np = chop_nsteps(g.len, prec32), k = s - offsets[i];
+      float mid[3], zs = 0.0f, ze = 0.0f;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const int cs = ax == 0 ? cc.x_start : (ax == 1 ? cc.y_start : cc.z_start);
+        const int ce = ax == 0 ? cc.x_end : (ax == 1 ? cc.y_end : cc.z_end);
+        const double s0 = (double)tr[cs], d = (double)g.dir[ax];
+        const float vs = chop_start(s0, d, k, precision), ve = chop_end(s0, d, tr[ce], k, np, precision);
+        mid[ax] = __fmul_rn(0.5f, __fadd_rn(vs, ve));
+        if (ax == 2) { zs = vs; ze = ve; }
       }
+      loc[0] = tr[cols.eventID];
+      loc[1] = mid[0]; loc[2] = mid[1]; loc[3] = mid[2];
+      loc[4] = zs; loc[5] = ze;
+      loc[6] = chop_dx(g, k, np, precision, prec32);
+      loc[7] = tr[cols.dEdx];
+      loc[8] = chop_dE(tr[cc.dE], g, k, np, precision, prec32);
+      loc[9] = tr[cols.t0];
     }
+    larnd_columns_t lc;
+    lc.ncols = 10; lc.eventID = 0; lc.x = 1; lc.y = 2; lc.z = 3; lc.z_start = 4; lc.z_end = 5; lc.dx = 6; lc.dEdx = 7; lc.dE = 8; lc.t0 = 9;
+    pid = prepare_segment(loc, lc, p, nt, bank_ntpl, rec, n, s, counts);
   }
+  mark_main_pixel(active, pid, bitmap, n_words, pid_offset, counts);
 }
 
 // ---- popcount scan over the bitmap -------------------------------------------------------------------
@@ -286,6 +357,22 @@ int larnd_launch_prepare(const float* tracks, int64_t n, const larnd_columns_t& 
                                                          ws.n_words, ws.pid_offset, counts);
   prof_end(0, st);
   LARND_LAUNCH_CHECK("k_prepare");
+  return LARND_OK;
+}
+
+int larnd_launch_prepare_raw(const float* raw, int64_t m, const larnd_chop_columns_t& cc, const larnd_columns_t& cols, double precision,
+                             const int64_t* offsets, int64_t n, const larnd_params_t& p, const larnd_lut* lut, const Workspace& ws,
+                             int32_t* counts, cudaStream_t st) {
+  LARND_CUDA(cudaMemsetAsync(ws.bitmap, 0, ws.n_words * sizeof(uint32_t), st));
+  LARND_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
+  if (n == 0) return LARND_OK;
+  const int64_t blocks = (n + PREP_THREADS - 1) / PREP_THREADS;
+  prof_begin(0, st);
+  larnd_runs_cache_drop(ws.rec);
+  k_prepare_raw<<<(unsigned)blocks, PREP_THREADS, 0, st>>>(raw, m, cc, cols, precision, (float)precision, offsets, n, p, lut ? lut->nt : 0,
+                                                          lut ? lut->ntpl : p.n_templates, ws.rec, ws.bitmap, ws.n_words, ws.pid_offset, counts);
+  prof_end(0, st);
+  LARND_LAUNCH_CHECK("k_prepare_raw");
   return LARND_OK;
 }
 

@@ -91,7 +91,7 @@ _lib = None
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 BUILD_DIR = os.path.join(os.path.dirname(HERE), "build")
-HEADERS = ["larnd_common.cuh", "sorted_runs.cuh", "bwd_chain.cuh", "segment_physics.cuh"]
+HEADERS = ["larnd_common.cuh", "sorted_runs.cuh", "bwd_chain.cuh", "segment_physics.cuh", "chop_math.cuh"]
 
 
 def nvcc_command(out=LIB_PATH, extra=()):
@@ -207,6 +207,8 @@ def _declare(lib):
     lib.larnd_chop_count.argtypes = [vp, i64, PCC, C.c_double, vp, vp]
     lib.larnd_chop_tracks.argtypes = [vp, i64, PCC, C.c_double, vp, vp, i64, vp]
     lib.larnd_chop_count.restype = C.c_int
+    lib.larnd_lut_prepare_raw.argtypes = [vp, i64, PCC, PC, C.c_double, vp, i64, PP, vp, i32, vp, sz, vp, vp]
+    lib.larnd_lut_prepare_raw.restype = C.c_int
     lib.larnd_chop_tracks.restype = C.c_int
     lib.larnd_fee_steps_bytes.argtypes = [i32]
     lib.larnd_fee_steps_bytes.restype = sz

@@ -91,13 +91,14 @@ def pack_columns(tracks, fields):
 
 
 def simulate_from_raw(params, response_template, raw_tracks, fields, precision=None, rngseed=0, device=None,
-                      npix_capacity=None, n_events=None):
+                      npix_capacity=None, n_events=None, n_segments=None, fused=True):
     """The reference-facing entry for production batches: RAW (un-chopped) segment rows as they come out of the input file
     (optimize/dataio.py:133-141) -> hits.  The reference chops on the host (a Python loop per raw row, :63-106) and uploads
     104 B per CHOPPED segment; here the raw rows are uploaded (100-700x fewer) and expanded on the device by the chop
     kernels, then simulate_wfs + simulate_stochastic run as usual.  ``raw_tracks``: (M, n_fields) float32, a pinned host
-    tensor / numpy array (uploaded here) or a CUDA tensor; event ids must be batch-local.  Returns the 8-tuple of
-    simulate_stochastic."""
+    tensor / numpy array (uploaded here) or a CUDA tensor; event ids must be batch-local.  ``fused`` (default): the chop runs
+    INSIDE the prepare kernel, piece by piece in registers; ``n_segments`` = segment slots of the batch (None: the piece count is
+    read back once).  Returns the 8-tuple of simulate_stochastic."""
     from . import sim
     if precision is None:
         precision = float(params.electron_sampling_resolution)
@@ -106,8 +107,14 @@ def simulate_from_raw(params, response_template, raw_tracks, fields, precision=N
     if not raw_tracks.is_cuda:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         raw_tracks = raw_tracks.to(dev, non_blocking=True)
-    chopped = chop_tracks(raw_tracks, fields, precision)
-    wfs, upix = sim.simulate_wfs(params, response_template, chopped, fields, npix_capacity=npix_capacity, n_events=n_events)
+    if n_events is None:
+        n_events = sim.n_events_of(raw_tracks, fields)
+    if fused:   # chop_tracks inside the prepare kernel: the chopped (n, 26) batch is never written (larnd_lut_prepare_raw)
+        wfs, upix = sim.simulate_wfs(params, response_template, raw_tracks.contiguous(), fields, npix_capacity=npix_capacity,
+                                     n_events=n_events, raw=(precision, n_segments))
+    else:
+        chopped = chop_tracks(raw_tracks, fields, precision)
+        wfs, upix = sim.simulate_wfs(params, response_template, chopped, fields, npix_capacity=npix_capacity, n_events=n_events)
     return sim.simulate_stochastic(params, wfs, upix, rngseed)
 
 

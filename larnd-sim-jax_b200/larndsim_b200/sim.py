@@ -221,10 +221,16 @@ def set_deterministic(on=True):
     _deterministic = bool(on)
 
 
-def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n_events=None, flags=0, out=None, deterministic=None):
+def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n_events=None, flags=0, out=None, deterministic=None,
+                raw=None):
     """prepare -> unique/renumber -> accumulate.  ``npix_capacity=None`` reproduces the reference's padded size
     pad_size(n_unique+1,'unique_pixels',0.2) (one 16-byte D2H read, like jnp.unique's sync); an explicit
-    capacity keeps the whole call asynchronous.  Returns a LutState."""
+    capacity keeps the whole call asynchronous.  Returns a LutState.
+
+    ``raw=(precision, n_segments)``: ``tracks`` are RAW (un-chopped) rows; chop_tracks(tracks, fields, precision) is fused into
+    the prepare kernel (larnd_lut_prepare_raw) for a batch of ``n_segments`` segment slots (>= the number of pieces; the
+    rest are pad_batch's invalid rows) — same records, waveforms and gradients as chopping first, without the chopped
+    (n, 26) batch ever being written.  ``n_segments=None`` reads the piece count back once (8-byte D2H)."""
     _check_cuda(tracks, "tracks")
     if tracks.dtype != torch.float32 or tracks.dim() != 2:
         raise ValueError("tracks must be a float32 (N, n_fields) tensor")
@@ -238,17 +244,31 @@ def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n
         if n_events is None:
             n_events = n_events_of(tracks, fields)
         flags = int(flags) | env_flags()
+        offsets = None
+        if raw is not None:
+            from . import dataio
+            precision, n_seg = raw
+            offsets = dataio.chop_offsets(tracks, fields, precision)
+            n = int(offsets[-1].item()) if n_seg is None else int(n_seg)
         ws_bytes = lib.larnd_workspace_bytes(n, n_events, pod.n_tpc, pod.n_pixels_x, pod.n_pixels_y)
         st = LutState()
         st.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=tracks.device)
         st.counts = torch.zeros(4, dtype=torch.int32, device=tracks.device)
         st.n, st.n_events, st.pod, st.lut, st.flags = n, n_events, pod, lut, int(flags)
-        _lib.check(lib.larnd_lut_prepare(_ptr(tracks), n, C.byref(cols), C.byref(pod), lut.handle, n_events,
-                                         _ptr(st.workspace), ws_bytes, _ptr(st.counts), _stream()))
+        if raw is not None:
+            ccols = dataio.make_chop_columns(fields)
+            _lib.check(lib.larnd_lut_prepare_raw(_ptr(tracks), tracks.shape[0], C.byref(ccols), C.byref(cols), float(precision),
+                                                 _ptr(offsets), n, C.byref(pod), lut.handle, n_events, _ptr(st.workspace), ws_bytes,
+                                                 _ptr(st.counts), _stream()))
+        else:
+            _lib.check(lib.larnd_lut_prepare(_ptr(tracks), n, C.byref(cols), C.byref(pod), lut.handle, n_events,
+                                             _ptr(st.workspace), ws_bytes, _ptr(st.counts), _stream()))
         if npix_capacity is None:
             cnt = st.counts.cpu()
             if int(cnt[2]) & 4:
                 raise ValueError("a segment's longitudinal diffusion needs a template row beyond the (truncated) response_template bank")
+            if int(cnt[2]) & 8:
+                raise _lib.LarndError("the raw rows chop into more pieces than the batch's n_segments slots")
             if int(cnt[2]) != 0:
                 raise ValueError("eventID outside [-1, n_events) found in tracks")
             npix_capacity = pad_size(int(cnt[0]) + 1, "unique_pixels", 0.2)
@@ -308,6 +328,8 @@ def check_state(st):
         raise ValueError("eventID outside [-1, n_events) found in tracks")
     if int(cnt[2]) & 4:
         raise ValueError("a segment's longitudinal diffusion needs a template row beyond the (truncated) response_template bank")
+    if int(cnt[2]) & 8:
+        raise _lib.LarndError("the raw rows chop into more pieces than the batch's n_segments slots")
     if int(cnt[2]) != 0:
         raise _lib.LarndError("npix_capacity=%d is too small for %d unique pixels (+1 padding entry)" % (st.npix, int(cnt[0])))
     return st
@@ -357,8 +379,8 @@ class _StepsLink:
 
 class _SimulateWfs(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, theta, params, response_template, tracks, fields, names, npix_capacity, n_events, holder=None):
-        st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
+    def forward(ctx, theta, params, response_template, tracks, fields, names, npix_capacity, n_events, holder=None, raw=None):
+        st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events, raw=raw)
         ctx.st = st
         ctx.names = names
         ctx.mark_non_differentiable(st.unique_pixels)
@@ -385,23 +407,24 @@ class _SimulateWfs(torch.autograd.Function):
         else:
             grad_all = lut_backward(ctx.st, g_wfs)
         idx = torch.tensor([_lib.PARAM_ORDER.index(n) for n in ctx.names], device=grad_all.device)
-        return (grad_all[idx],) + (None,) * 8
+        return (grad_all[idx],) + (None,) * 9
 
 
-def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, n_events=None):
+def simulate_wfs(params, response_template, tracks, fields, npix_capacity=None, n_events=None, raw=None):
     """(wfs (Npix, Nticks-1) float32, unique_pixels (Npix,) int32 sorted, -1 padded at the front).
-    Reference: sim_jax.py:689-736.  Differentiable w.r.t. the Params fields built with build_params_class."""
+    Reference: sim_jax.py:689-736.  Differentiable w.r.t. the Params fields built with build_params_class.
+    ``raw=(precision, n_segments)``: ``tracks`` are un-chopped rows, chopped inside the prepare kernel (see lut_forward)."""
     leaves = params.grad_leaves()
     if leaves and torch.is_grad_enabled():
         names = tuple(n for n, _ in leaves)
         theta = torch.stack([t.to(tracks.device, torch.float32) for _, t in leaves])
         holder = []
-        wfs, upix = _SimulateWfs.apply(theta, params, response_template, tracks, tuple(fields), names, npix_capacity, n_events, holder)
+        wfs, upix = _SimulateWfs.apply(theta, params, response_template, tracks, tuple(fields), names, npix_capacity, n_events, holder, raw)
         counts = holder[0]
         if holder[1] is not None:
             wfs._larnd_steps_link = holder[1]
     else:
-        st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events)
+        st = lut_forward(params, response_template, tracks, fields, npix_capacity, n_events, raw=raw)
         wfs, upix, counts = st.wfs_full[:, 1:], st.unique_pixels, st.counts
     # With an explicit npix_capacity the call is asynchronous and a capacity overflow / bad event id is only flagged on the
     # device: the flag travels with the outputs and is checked at the consumer's own synchronisation point
@@ -420,6 +443,8 @@ def check_outputs(*tensors):
                 raise ValueError("eventID outside [-1, n_events) found in tracks")
             if int(cnt[2]) & 4:
                 raise ValueError("a segment's longitudinal diffusion needs a template row beyond the (truncated) response_template bank")
+            if int(cnt[2]) & 8:
+                raise _lib.LarndError("the raw rows chop into more pieces than the batch's n_segments slots")
             if int(cnt[2]) != 0:
                 raise _lib.LarndError("npix_capacity=%d is too small for %d unique pixels (+1 padding entry)" % (stt[1], int(cnt[0])))
             return

@@ -1115,3 +1115,61 @@ def test_autograd_hands_the_front_end_vjp_over_as_step_events(torch_dev, monkeyp
         assert abs(l_dense - l_steps) <= 1e-5 * abs(l_dense)
         tol = np.where(np.array(names) == "long_diff", 5e-3, 1e-3)   # cancelling template sums in float32 (see above)
         assert (np.abs(g_steps - g_dense) <= tol * np.abs(g_dense) + 1e-12).all(), (second, g_steps, g_dense)
+
+
+def test_fused_raw_prepare_is_bit_identical_to_chop_then_prepare(torch_dev):
+    """larnd_lut_prepare_raw (chop_tracks fused into the prepare kernel: the chopped batch is never written) against
+    chop_tracks -> pad_batch -> larnd_lut_prepare: every per-segment record bit for bit (including the invalid rows of the
+    padded slots), the same pixel list and hits, the same gradients through the step-event backward; degenerate raw rows
+    (zero length, exactly two pieces); too few segment slots are flagged on the device."""
+    import torch
+    from larndsim_b200 import _lib, dataio, sim
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = torch.as_tensor(cm.synthetic_bank(32, 25, 25, 1950), device=torch_dev)
+    pp = cm.product_params(**kw).replace(electron_sampling_resolution=0.01)
+    seg = lo.swap_xz_structured(np.load(os.path.join(cm.GOLD, "segments_input_2.npz"))["segments"])
+    rows, gids = lo.make_batches(seg, 50.0)[0]
+    raw = lo.batch_array(seg, rows, gids, cm.FIELDS, False, 0.01)
+    raw = np.concatenate([raw, raw[:2]])
+    c = cm.FIELDS.index
+    for ax in "xyz":
+        raw[-1, c(ax + "_end")] = raw[-1, c(ax + "_start")]
+    raw[-2, c("x_end")] = raw[-2, c("x_start")] + np.float32(0.02)
+    raw[-2, c("y_end")] = raw[-2, c("y_start")]
+    raw[-2, c("z_end")] = raw[-2, c("z_start")]
+    rt = torch.as_tensor(raw, device=torch_dev)
+    for prec in (0.01, 0.05):
+        chopped = dataio.chop_tracks(rt, cm.FIELDS, prec)
+        total = chopped.shape[0]
+        for n_seg in (total, total + 37):
+            padded = dataio.pad_batch(chopped, n_seg, cm.FIELDS)
+            nev = sim.n_events_of(rt, cm.FIELDS)
+            ref = sim.lut_forward(pp, bank, padded, cm.FIELDS, n_events=nev)
+            got = sim.lut_forward(pp, bank, rt, cm.FIELDS, n_events=nev, npix_capacity=ref.npix, raw=(prec, n_seg))
+            assert got.n == ref.n == n_seg
+            assert int(got.counts[2].item()) == 0
+            ra, rb = sim.record_fields(ref), sim.record_fields(got)
+            for name in ra:
+                assert torch.equal(ra[name].view(torch.int32), rb[name].view(torch.int32)), (prec, n_seg, name)
+            assert torch.equal(got.unique_pixels, ref.unique_pixels)
+            scale = ref.wfs_full.abs().amax(dim=1, keepdim=True) + 1e-30
+            assert bool(((got.wfs_full - ref.wfs_full).abs() <= 2 * WFS_RTOL * scale + 1e-3).all())
+            fa = sim.fee_forward(pp, ref.wfs_full[:, 1:], ref.unique_pixels, None, compact=False)
+            fb = sim.fee_forward(pp, got.wfs_full[:, 1:], got.unique_pixels, None, compact=False)
+            assert torch.equal(fa.ticks, fb.ticks)
+            g_adc = fa.adc * (ref.unique_pixels >= 0).unsqueeze(1)
+            ga = sim.hits_backward(ref, fa, g_adc).cpu().numpy().astype(np.float64)
+            gb = sim.hits_backward(got, fb, g_adc).cpu().numpy().astype(np.float64)
+            assert (np.abs(ga - gb) <= 1e-4 * np.abs(ga) + 1e-12).all(), (ga, gb)
+    # the reference-facing entry: hits of the fused path == hits of the chop-first path
+    ha = dataio.simulate_from_raw(pp, bank, raw, cm.FIELDS, precision=0.01, fused=False)
+    hb = dataio.simulate_from_raw(pp, bank, raw, cm.FIELDS, precision=0.01, fused=True)
+    assert len(ha[0]) == len(hb[0]) > 0
+    for k in (4, 6, 7):
+        assert torch.equal(ha[k], hb[k])
+    assert float((ha[0] - hb[0]).abs().max()) <= ADC_ATOL
+    # fewer slots than pieces: flagged, nothing simulated
+    st = sim.lut_forward(pp, bank, rt, cm.FIELDS, n_events=nev, npix_capacity=ref.npix, raw=(0.01, 100))
+    assert int(st.counts[2].item()) & 8
+    with pytest.raises(_lib.LarndError):
+        sim.check_state(st)
