@@ -283,9 +283,16 @@ def run_ours(args):
     pod = st0.pod
     del st0
 
+    # hits-only pipeline (sim.simulate_hits' kernels with preallocated outputs): the waveform buffer is scratch, the front-end
+    # kernel zeroes what it has read (LARND_FEE_CLEAR_WFS) and the next accumulate skips the 2 GB memset (LARND_FLAG_WFS_ZERO)
+    arena_clean = {"ok": False}
+
     def fwd(flags=0, src=tracks, flds=fields, raw=None):
-        st = sim.lut_forward(params, bank, src, flds, npix_capacity=npix, n_events=n_events, flags=flags, out=out, raw=raw)
-        fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True, pod=pod)
+        was_clean, arena_clean["ok"] = arena_clean["ok"], False
+        st = sim.lut_forward(params, bank, src, flds, npix_capacity=npix, n_events=n_events, flags=flags, out=out, raw=raw,
+                             wfs_zero=was_clean)
+        fs = sim.fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, None, compact=True, pod=pod, clear_wfs=True)
+        arena_clean["ok"] = True
         return st, fs
 
     # target for the fit-style loss: the ADCs of a slightly different detector (lifetime -10 %)

@@ -64,7 +64,9 @@ enum {
                                       * forward call (larnd_lut_accumulate / _forward) built from the same records, on the same
                                       * stream or synchronised with it; the library checks (workspace, n, lut, n_ticks) against its
                                       * record of the last build and rebuilds when they do not match */
-#define LARND_FLAG_PUBLIC_MASK  0x1f
+#define LARND_FLAG_WFS_ZERO     0x20 /* larnd_lut_accumulate / _forward: wfs_d is already all-zero (fresh cudaMemset, or cleaned by
+                                      * larnd_fee_forward_ex(LARND_FEE_CLEAR_WFS)): skip the memset of the waveform buffer */
+#define LARND_FLAG_PUBLIC_MASK  0x3f
 
 /* Differentiable parameters (optimize/ranges.py:7-21).  Gradients are returned in this order. */
 enum {
@@ -240,6 +242,18 @@ int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t*
                       float* hit_adc_d, float* hit_x_d, float* hit_y_d, float* hit_z_d, float* hit_ticks_d,
                       float* hit_prob_d, int32_t* hit_event_d, int32_t* hit_pixel_d, int32_t* n_valid_d,
                       void* scratch_d, size_t scratch_bytes, void* stream);
+/* larnd_fee_forward with flags.  LARND_FEE_CLEAR_WFS: the waveform buffer is scratch of a hits-only pipeline — every row's
+ * non-zero samples (and its garbage column) are zeroed as soon as the row has been read, so the buffer is all-zero again when
+ * the call completes and the next larnd_lut_accumulate on it may pass LARND_FLAG_WFS_ZERO instead of paying its 2 GB memset
+ * (8 KB per row written vs ~0.6 KB).  Needs the TMA row layout described above. */
+#define LARND_FEE_CLEAR_WFS 0x1
+int larnd_fee_forward_ex(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
+                      const larnd_params_t* params, const float* noise_d,
+                      float* adc_d, float* ticks_d, float* pixel_z_d, float* pixel_x_d, float* pixel_y_d,
+                      int32_t* event_d, float* saved_d,
+                      float* hit_adc_d, float* hit_x_d, float* hit_y_d, float* hit_z_d, float* hit_ticks_d,
+                      float* hit_prob_d, int32_t* hit_event_d, int32_t* hit_pixel_d, int32_t* n_valid_d,
+                      void* scratch_d, size_t scratch_bytes, int32_t fee_flags, void* stream);
 size_t larnd_fee_scratch_bytes(int32_t npix);
 
 /* VJP of get_adc_values+digitize: g_adc_d (npix,10) -> g_wfs_d (npix, n_ticks-1) with row stride.

@@ -211,7 +211,7 @@ static int lut_accumulate_impl(int64_t n, const larnd_params_t* p, const larnd_l
     return LARND_E_CAPACITY;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * wfs_row_stride * sizeof(float), st));
+  if (!(flags & LARND_FLAG_WFS_ZERO)) LARND_CUDA(cudaMemsetAsync(wfs_d, 0, (size_t)npix_capacity * wfs_row_stride * sizeof(float), st));
   if ((rc = larnd_launch_unique(ws, *p, npix_capacity, /*extra=*/1, unique_pixels_d, counts_d, st))) return rc;
   return larnd_launch_accumulate(n, *p, lut, ws, npix_capacity, flags & LARND_FLAG_PUBLIC_MASK, wfs_d, wfs_row_stride, counts_d, st, det_acc);
 }

@@ -28,6 +28,7 @@ struct FeeArgs {
   float* adc; float* ticks; float* pixel_z; float* pixel_x; float* pixel_y; int32_t* event; float* saved;
   int32_t* row_counts;
   int bulk;  // rows are loaded with cp.async.bulk (layout contract checked by larnd_fee_forward)
+  int clear; // LARND_FEE_CLEAR_WFS: every non-zero sample of the waveform buffer is zeroed once it has been read (bulk layout only)
 };
 
 __device__ __forceinline__ int floordiv_pos(int a, int b) { return floordiv_i(a, b); }
@@ -163,6 +164,26 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
     for (int o = 16; o > 0; o >>= 1) {
       t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, o));
       t_last = max(t_last, __shfl_xor_sync(0xffffffffu, t_last, o));
+    }
+    // Self-cleaning waveform buffer: the row now lives in shared memory, and everything non-zero in global memory lies inside
+    // [t_first, t_last] (plus, possibly, the garbage column in front of the row, which came along with the TMA copy): zero
+    // exactly that — ~150 floats per row instead of the 2 GB memset the next accumulate call would otherwise need.
+    if (F.clear) {
+      float* wz = const_cast<float*>(w);
+      if (lane == 0 && shift > 0) {
+        bool nz0 = false;
+        for (int k = 1; k <= shift; ++k) nz0 |= __float_as_uint(c[-k]) != 0u;
+        if (nz0) for (int k = 1; k <= shift; ++k) wz[-k] = 0.0f;
+      }
+      if (t_last >= t_first) {
+        if (lane < head + tail) {
+          const int t = lane < head ? lane : head + 4 * nvec + (lane - head);
+          wz[t] = 0.0f;
+        }
+        float4* wz4 = reinterpret_cast<float4*>(wz + head);
+        const int v0 = max(0, (t_first - head) >> 2), v1 = min(nvec - 1, (t_last - head) >> 2);
+        for (int v = v0 + lane; v <= v1; v += 32) wz4[v] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
     }
     // q = wfs * t_sampling, on the window only (0 * t_sampling = 0 elsewhere)
     if (t_last >= t_first) {
@@ -566,6 +587,17 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
                                  float* hit_adc_d, float* hit_x_d, float* hit_y_d, float* hit_z_d, float* hit_ticks_d,
                                  float* hit_prob_d, int32_t* hit_event_d, int32_t* hit_pixel_d, int32_t* n_valid_d,
                                  void* scratch_d, size_t scratch_bytes, void* stream) {
+  return larnd_fee_forward_ex(wfs_d, wfs_row_stride, unique_pixels_d, npix, params, noise_d, adc_d, ticks_d, pixel_z_d, pixel_x_d,
+                              pixel_y_d, event_d, saved_d, hit_adc_d, hit_x_d, hit_y_d, hit_z_d, hit_ticks_d, hit_prob_d, hit_event_d,
+                              hit_pixel_d, n_valid_d, scratch_d, scratch_bytes, 0, stream);
+}
+
+extern "C" int larnd_fee_forward_ex(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
+                                    const larnd_params_t* params, const float* noise_d, float* adc_d, float* ticks_d,
+                                    float* pixel_z_d, float* pixel_x_d, float* pixel_y_d, int32_t* event_d, float* saved_d,
+                                    float* hit_adc_d, float* hit_x_d, float* hit_y_d, float* hit_z_d, float* hit_ticks_d,
+                                    float* hit_prob_d, int32_t* hit_event_d, int32_t* hit_pixel_d, int32_t* n_valid_d,
+                                    void* scratch_d, size_t scratch_bytes, int32_t fee_flags, void* stream) {
   if (!wfs_d || !unique_pixels_d || !params || !adc_d || !ticks_d || !pixel_z_d || !pixel_x_d || !pixel_y_d || !event_d ||
       !n_valid_d || !scratch_d) {
     larnd_set_error("larnd_fee_forward: null argument");
@@ -597,6 +629,12 @@ extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, con
     // the aligned address below (see the header: those floats and the round-up at the end must be readable)
     const int sh = (int)(((uintptr_t)wfs_d & 15u) >> 2);
     F.bulk = (((uintptr_t)wfs_d & 3u) == 0 && wfs_row_stride % 4 == 0 && ((sh + ntw + 3) & ~3) <= wfs_row_stride) ? 1 : 0;
+  }
+  F.clear = (fee_flags & LARND_FEE_CLEAR_WFS) ? 1 : 0;
+  if (F.clear && !F.bulk) {
+    larnd_set_error("larnd_fee_forward_ex: LARND_FEE_CLEAR_WFS needs the padded waveform layout (16-byte aligned buffer, row stride a "
+                    "multiple of four floats)");
+    return LARND_E_ARG;
   }
   static bool attr_set = false;
   if (!attr_set) {

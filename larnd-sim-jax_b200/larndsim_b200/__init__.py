@@ -12,5 +12,5 @@ include/larnd_b200.h; there is no CPU fallback.
 from ._lib import LarndError, build_library, get_lib  # noqa: F401
 from .consts import (RecombinationMode, build_params_class, get_vdrift, load_detector_properties,  # noqa: F401
                      load_geometry_json, load_lut)
-from .sim import (pad_size, shift_tracks, simulate_parametrized, simulate_probabilistic, simulate_stochastic,  # noqa: F401
-                  simulate_wfs)
+from .sim import (pad_size, shift_tracks, simulate_hits, simulate_parametrized, simulate_probabilistic,  # noqa: F401
+                  simulate_stochastic, simulate_wfs)

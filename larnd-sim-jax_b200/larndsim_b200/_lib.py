@@ -23,7 +23,8 @@ PARAM_ORDER = ("Ab", "kb", "eField", "lifetime", "long_diff", "tran_diff", "shif
                "alpha", "beta", "R_param", "lArDensity", "MeVToElectrons", "vdrift")
 
 # flags of larnd_lut_forward / _accumulate / _backward (include/larnd_b200.h)
-FLAG_SKIP_GARBAGE, FLAG_IMPL_CHUNK, FLAG_IMPL_SORTED, FLAG_NO_SPLIT, FLAG_REUSE_RUNS = 1, 2, 4, 8, 16
+FLAG_SKIP_GARBAGE, FLAG_IMPL_CHUNK, FLAG_IMPL_SORTED, FLAG_NO_SPLIT, FLAG_REUSE_RUNS, FLAG_WFS_ZERO = 1, 2, 4, 8, 16, 32
+FEE_CLEAR_WFS = 1
 
 # record fields inside the workspace (enum in larnd_b200.h)
 REC_FIELDS = ("Q", "FRAC", "SL", "A", "B", "C", "WX0", "WX1", "WX2", "WX3", "WX4", "WY0", "WY1", "WY2", "WY3", "WY4",
@@ -170,6 +171,8 @@ def _declare(lib):
     lib.larnd_lut_accumulate.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     lib.larnd_lut_backward.argtypes = [i64, PP, vp, i32, i32, i32, vp, sz, vp, vp, i64, vp, vp]
     lib.larnd_fee_forward.argtypes = [vp, i64, vp, i32, PP, vp] + [vp] * 16 + [vp, sz, vp]
+    lib.larnd_fee_forward_ex.argtypes = [vp, i64, vp, i32, PP, vp] + [vp] * 16 + [vp, sz, i32, vp]
+    lib.larnd_fee_forward_ex.restype = C.c_int
     lib.larnd_profile_enable.argtypes = [C.c_int]
     lib.larnd_profile_enable.restype = C.c_int
     lib.larnd_profile_read.argtypes = [C.POINTER(C.c_float)]

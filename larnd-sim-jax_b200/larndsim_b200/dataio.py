@@ -110,8 +110,8 @@ def simulate_from_raw(params, response_template, raw_tracks, fields, precision=N
     if n_events is None:
         n_events = sim.n_events_of(raw_tracks, fields)
     if fused:   # chop_tracks inside the prepare kernel: the chopped (n, 26) batch is never written (larnd_lut_prepare_raw)
-        wfs, upix = sim.simulate_wfs(params, response_template, raw_tracks.contiguous(), fields, npix_capacity=npix_capacity,
-                                     n_events=n_events, raw=(precision, n_segments))
+        return sim.simulate_hits(params, response_template, raw_tracks.contiguous(), fields, rngseed=rngseed,
+                                 npix_capacity=npix_capacity, n_events=n_events, raw=(precision, n_segments))
     else:
         chopped = chop_tracks(raw_tracks, fields, precision)
         wfs, upix = sim.simulate_wfs(params, response_template, chopped, fields, npix_capacity=npix_capacity, n_events=n_events)

@@ -222,7 +222,7 @@ def set_deterministic(on=True):
 
 
 def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n_events=None, flags=0, out=None, deterministic=None,
-                raw=None):
+                raw=None, wfs_zero=False):
     """prepare -> unique/renumber -> accumulate.  ``npix_capacity=None`` reproduces the reference's padded size
     pad_size(n_unique+1,'unique_pixels',0.2) (one 16-byte D2H read, like jnp.unique's sync); an explicit
     capacity keeps the whole call asynchronous.  Returns a LutState.
@@ -230,7 +230,10 @@ def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n
     ``raw=(precision, n_segments)``: ``tracks`` are RAW (un-chopped) rows; chop_tracks(tracks, fields, precision) is fused into
     the prepare kernel (larnd_lut_prepare_raw) for a batch of ``n_segments`` segment slots (>= the number of pieces; the
     rest are pad_batch's invalid rows) — same records, waveforms and gradients as chopping first, without the chopped
-    (n, 26) batch ever being written.  ``n_segments=None`` reads the piece count back once (8-byte D2H)."""
+    (n, 26) batch ever being written.  ``n_segments=None`` reads the piece count back once (8-byte D2H).
+
+    ``wfs_zero``: the caller's ``out`` waveform buffer is already all-zero (fresh torch.zeros, or cleaned by
+    fee_forward(clear_wfs=True)): the 8 KB-per-row memset is skipped (LARND_FLAG_WFS_ZERO)."""
     _check_cuda(tracks, "tracks")
     if tracks.dtype != torch.float32 or tracks.dim() != 2:
         raise ValueError("tracks must be a float32 (N, n_fields) tensor")
@@ -289,7 +292,10 @@ def lut_forward(params, response_template, tracks, fields, npix_capacity=None, n
                                                               ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_buf), st.wfs_buf.stride(0),
                                                               _ptr(st.counts), _ptr(scratch), scratch.numel(), _stream()))
         else:
-            _lib.check(lib.larnd_lut_accumulate(n, C.byref(pod), lut.handle, n_events, st.npix, st.flags, _ptr(st.workspace),
+            if wfs_zero and out is None:
+                raise ValueError("wfs_zero describes a caller-provided `out` buffer")
+            _lib.check(lib.larnd_lut_accumulate(n, C.byref(pod), lut.handle, n_events, st.npix,
+                                                st.flags | (_lib.FLAG_WFS_ZERO if wfs_zero else 0), _ptr(st.workspace),
                                                 ws_bytes, _ptr(st.unique_pixels), _ptr(st.wfs_buf), st.wfs_buf.stride(0),
                                                 _ptr(st.counts), _stream()))
     return st
@@ -548,12 +554,16 @@ class FeeState:
     __slots__ = ("adc", "ticks", "pixel_z", "pixel_x", "pixel_y", "event", "saved", "hits", "n_valid", "npix", "pod")
 
 
-def fee_forward(params, wfs, unique_pixels, noise=None, compact=True, pod=None):
-    """Runs the fused FEE kernel on (Npix, Nticks-1) waveforms (any row stride)."""
+def fee_forward(params, wfs, unique_pixels, noise=None, compact=True, pod=None, clear_wfs=False):
+    """Runs the fused FEE kernel on (Npix, Nticks-1) waveforms (any row stride).  ``clear_wfs``: the waveform buffer is
+    scratch of a hits-only pipeline — the kernel zeroes every non-zero sample it has read (LARND_FEE_CLEAR_WFS), leaving the
+    padded buffer all-zero for the next lut_forward(out=..., wfs_zero=True)."""
     _check_cuda(wfs, "wfs")
     _check_cuda(unique_pixels, "unique_pixels")
     lib = _lib.get_lib()
     if wfs.dtype != torch.float32 or wfs.dim() != 2 or wfs.stride(1) != 1:
+        if clear_wfs:
+            raise ValueError("clear_wfs needs the float32 waveform buffer itself (lut_forward's wfs_full[:, 1:]), not a copy")
         wfs = wfs.contiguous().float()
     unique_pixels = unique_pixels.to(torch.int32).contiguous()
     pod = make_pod(params) if pod is None else pod
@@ -586,10 +596,10 @@ def fee_forward(params, wfs, unique_pixels, noise=None, compact=True, pod=None):
             noise = noise.to(dev, torch.float32).contiguous()
             if noise.numel() != npix * (1 + 3 * k):
                 raise ValueError("noise must hold npix*(1+3*MAX_ADC_VALUES) standard normals")
-        _lib.check(lib.larnd_fee_forward(_ptr(wfs), wfs.stride(0), _ptr(unique_pixels), npix, C.byref(pod), _ptr(noise),
-                                         _ptr(fs.adc), _ptr(fs.ticks), _ptr(fs.pixel_z), _ptr(fs.pixel_x), _ptr(fs.pixel_y),
-                                         _ptr(fs.event), _ptr(fs.saved), *hp, _ptr(fs.n_valid),
-                                         _ptr(scratch), scratch.numel(), _stream()))
+        _lib.check(lib.larnd_fee_forward_ex(_ptr(wfs), wfs.stride(0), _ptr(unique_pixels), npix, C.byref(pod), _ptr(noise),
+                                            _ptr(fs.adc), _ptr(fs.ticks), _ptr(fs.pixel_z), _ptr(fs.pixel_x), _ptr(fs.pixel_y),
+                                            _ptr(fs.event), _ptr(fs.saved), *hp, _ptr(fs.n_valid),
+                                            _ptr(scratch), scratch.numel(), _lib.FEE_CLEAR_WFS if clear_wfs else 0, _stream()))
     return fs
 
 
@@ -702,6 +712,55 @@ def simulate_stochastic(params, wfs, unique_pixels, rngseed):
     pixel_z = get_hit_z(params, ticks.reshape(-1), plane.repeat_interleave(ticks.shape[1])).reshape(ticks.shape)
     out = parse_output(params, adcs, pixel_x, pixel_y, pixel_z, ticks, hit_prob, event, unique_pixels.to(torch.int32))
     return out[:8]
+
+
+class HitsArena:
+    """Persistent scratch of the hits-only pipeline (simulate_hits): pixel list + padded waveform buffer of one
+    (npix_capacity, n_ticks) shape.  The front-end kernel zeroes what it has read (fee_forward(clear_wfs=True)), so after the
+    first call the 8 KB-per-row memset of the waveform buffer is never paid again; ``clean`` tracks whether that invariant
+    holds (an exception between the two kernels simply costs one memset on the next call)."""
+    __slots__ = ("unique_pixels", "wfs", "clean")
+
+    def __init__(self):
+        self.unique_pixels = self.wfs = None
+        self.clean = False
+
+    def fit(self, npix, n_ticks, device):
+        shape = (int(npix), wfs_row_stride(n_ticks))
+        if self.wfs is None or tuple(self.wfs.shape) != shape or self.wfs.device != device:
+            self.wfs = torch.zeros(shape, dtype=torch.float32, device=device)
+            self.unique_pixels = torch.full((int(npix),), -1, dtype=torch.int32, device=device)
+            self.clean = True
+
+
+_default_arenas = {}
+
+
+def simulate_hits(params, response_template, tracks, fields, rngseed=0, npix_capacity=None, n_events=None, raw=None, arena=None):
+    """simulate_wfs + simulate_stochastic (sim_jax.py:689-769) as ONE hits-only call: the same 8-tuple of hits, the
+    waveforms stay internal scratch (no gradients, nothing to return), which lets the buffer be reused and cleaned by the
+    front-end kernel instead of being allocated and memset per batch.  Needs an explicit ``npix_capacity`` (production loops
+    size it once); without it, or under autograd, the two-call path runs.  ``raw``: see lut_forward."""
+    need_grad = torch.is_grad_enabled() and bool(params.grad_leaves())
+    if npix_capacity is None or need_grad:
+        wfs, upix = simulate_wfs(params, response_template, tracks, fields, npix_capacity=npix_capacity, n_events=n_events, raw=raw)
+        return simulate_stochastic(params, wfs, upix, rngseed)
+    _check_cuda(tracks, "tracks")
+    dev = tracks.device
+    if arena is None:
+        arena = _default_arenas.setdefault((dev.type, dev.index), HitsArena())
+    n_ticks = int(make_pod(params).n_ticks)
+    arena.fit(npix_capacity, n_ticks, dev)
+    was_clean, arena.clean = arena.clean, False
+    st = lut_forward(params, response_template, tracks, fields, npix_capacity=npix_capacity, n_events=n_events, raw=raw,
+                     out=(arena.unique_pixels, arena.wfs), wfs_zero=was_clean)
+    noise = make_noise(params, st.npix, rngseed, dev)
+    fs = fee_forward(params, st.wfs_full[:, 1:], st.unique_pixels, noise, compact=True, pod=st.pod, clear_wfs=True)
+    arena.clean = True
+    nv = int(fs.n_valid.item())
+    check_state(st)
+    hf, hi = fs.hits
+    return hf[0, :nv], hf[1, :nv], hf[2, :nv], hf[3, :nv], hf[4, :nv], hf[5, :nv], hi[0, :nv], hi[1, :nv]
 
 
 def simulate_probabilistic(params, wfs, unique_pixels):

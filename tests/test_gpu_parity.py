@@ -627,6 +627,15 @@ def test_spill_sized_batch_properties(torch_dev, monkeypatch):
     sp = sim.lut_forward(params, bank, tracks[perm], synthetic.FIELDS, npix_capacity=npix, n_events=nev)
     assert torch.equal(sp.unique_pixels, us)
     assert float(((sp.wfs_full[real][:, 1:] - ws[real][:, 1:]).abs() / (scale + 1e-30)).max()) < 2 * WFS_RTOL
+    # self-cleaning front end at spill size (tile kernels, garbage row 0 fed by every CTA): after fee_forward(clear_wfs=True)
+    # the whole padded buffer is bitwise zero, and a forward pass into it without the memset reproduces the waveforms
+    fz = sim.fee_forward(params, sp.wfs_full[:, 1:], sp.unique_pixels, None, compact=True, clear_wfs=True)
+    assert int(torch.count_nonzero(sp.wfs_buf.view(torch.int32))) == 0
+    s2 = sim.lut_forward(params, bank, tracks[perm], synthetic.FIELDS, npix_capacity=npix, n_events=nev,
+                         out=(sp.unique_pixels, sp.wfs_buf), wfs_zero=True)
+    assert float(((s2.wfs_full[real][:, 1:] - ws[real][:, 1:]).abs() / (scale + 1e-30)).max()) < 2 * WFS_RTOL
+    f2 = sim.fee_forward(params, s2.wfs_full[:, 1:], s2.unique_pixels, None, compact=True)
+    assert abs(int(f2.n_valid.item()) - int(fz.n_valid.item())) <= 3
 
 
 _SPLIT_SCRIPT = r"""
@@ -1173,3 +1182,42 @@ def test_fused_raw_prepare_is_bit_identical_to_chop_then_prepare(torch_dev):
     assert int(st.counts[2].item()) & 8
     with pytest.raises(_lib.LarndError):
         sim.check_state(st)
+
+
+def test_hits_only_pipeline_cleans_its_waveform_buffer(torch_dev):
+    """sim.simulate_hits: simulate_wfs + simulate_stochastic over a persistent arena.  The front-end kernel zeroes every sample
+    it has read (LARND_FEE_CLEAR_WFS), so (a) the padded waveform buffer is bitwise all-zero after every call — including the
+    garbage row 0, the garbage column and the padding columns — and the next accumulate may skip its memset
+    (LARND_FLAG_WFS_ZERO); (b) repeated calls on different batches return exactly the hits of the two-call API; (c) FEE
+    outputs with and without cleaning are identical."""
+    import torch
+    from larndsim_b200 import dataio, sim
+    kw = dict(number_pix_neighbors=2, signal_length=100)
+    bank = torch.as_tensor(cm.synthetic_bank(32, 25, 25, 1950), device=torch_dev)
+    pp = cm.product_params(**kw)
+    batches = [cm.small_batch(900, ifile=0, ibatch=0, pad=5, precision=0.01), cm.small_batch(1300, ifile=1, ibatch=1, pad=0, precision=0.01),
+               cm.small_batch(700, ifile=2, ibatch=0, pad=9, precision=0.01)]
+    arena = sim.HitsArena()
+    npix = 1024
+    for rep in range(2):
+        for ib, tr in enumerate(batches):
+            t = torch.as_tensor(tr, device=torch_dev)
+            nev = sim.n_events_of(t, cm.FIELDS)
+            wfs, upix = sim.simulate_wfs(pp, bank, t, cm.FIELDS, npix_capacity=npix, n_events=nev)
+            ref = sim.simulate_stochastic(pp, wfs, upix, ib)
+            got = sim.simulate_hits(pp, bank, t, cm.FIELDS, rngseed=ib, npix_capacity=npix, n_events=nev, arena=arena)
+            assert arena.clean and int(torch.count_nonzero(arena.wfs.view(torch.int32))) == 0, (rep, ib)
+            assert len(got[0]) == len(ref[0]) > 0
+            for k in (4, 6, 7):
+                assert torch.equal(got[k], ref[k])
+            assert float((got[0] - ref[0]).abs().max()) <= ADC_ATOL
+    # same FEE outputs with and without the cleaning stores
+    st = sim.lut_forward(pp, bank, torch.as_tensor(batches[0], device=torch_dev), cm.FIELDS, npix_capacity=npix)
+    keep = st.wfs_buf.clone()
+    fa = sim.fee_forward(pp, st.wfs_full[:, 1:], st.unique_pixels, None, compact=False)
+    assert torch.equal(st.wfs_buf, keep)
+    fb = sim.fee_forward(pp, st.wfs_full[:, 1:], st.unique_pixels, None, compact=False, clear_wfs=True)
+    assert int(torch.count_nonzero(st.wfs_buf.view(torch.int32))) == 0
+    assert torch.equal(fa.adc, fb.adc) and torch.equal(fa.ticks, fb.ticks) and torch.equal(fa.saved, fb.saved)
+    with pytest.raises(ValueError):
+        sim.fee_forward(pp, keep[:, 1:1950].double(), st.unique_pixels, None, clear_wfs=True)
