@@ -45,6 +45,7 @@ struct AccArgs {
   unsigned long long* wfs64;  // deterministic mode: (npix, nticks) 64-bit fixed-point accumulators instead of wfs (else nullptr)
   int skip_garbage;
   int slow_only;  // 1: only segments whose window touches the ends of the readout (the rest is done by accumulate_sorted.cu)
+  const int* n_slow;  // slow_only: device count of such segments (k_build_runs), 0 = nothing to do
 };
 
 constexpr int KP = 8;            // tick positions per run (impulse train length)
@@ -290,6 +291,7 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
   const int nb = A.nb;
   const int L = A.L;
   if (A.slow_only) {  // nothing to do for a chunk without boundary segments (the common case)
+    if (A.n_slow && *A.n_slow == 0) return;  // ... nor for a batch without any (counted by k_build_runs): no record is read
     int slow = 0;
     if ((int)threadIdx.x < ns)
       slow = !seg_is_fast(reinterpret_cast<const int*>(A.rec)[(int64_t)LARND_I_T0 * A.n + s_base + threadIdx.x], L, A.nticks);
@@ -603,6 +605,7 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.wfs64 = det_acc;
   A.skip_garbage = flags & LARND_FLAG_SKIP_GARBAGE;
   A.slow_only = slow_only ? 1 : 0;
+  A.n_slow = slow_only ? ws.gcnt + 3 /* GC_SLOW, sorted_runs.cuh */ : nullptr;
   const int64_t chunks = (n + S - 1) / S;
   // register window = run window (L + 2 + span) + slack for the tick drift between consecutive runs of a track;
   // more slack = fewer flushes but more predicated-off slots in the inner loop.

@@ -48,6 +48,7 @@ struct BwdArgs {
   StepsView steps;   // compact upstream gradient (larnd_fee_backward_steps) used instead of g when use_steps != 0
   int use_steps;
   int sorted_active;  // the class-sorted kernel (accumulate_bwd_sorted.cu) runs too and takes every segment it can handle
+  const int* n_slow;  // sorted_active: device count of the segments it leaves to this kernel (k_build_runs)
 };
 
 constexpr int MAXK = 16;        // distinct main pixels per chunk served from the shared row table
@@ -223,8 +224,9 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
   const bool slow_only = A.sorted_active && skip_garbage;
   if (slow_only) {
     int slow = 0;
-    if ((int)threadIdx.x < ns) slow = !seg_is_fast(irec[(int64_t)LARND_I_T0 * n + s_base + threadIdx.x], L, A.nticks);
-    if (!__syncthreads_or(slow)) {
+    const bool none = A.n_slow && *A.n_slow == 0;   // block-uniform: no boundary segment in the whole batch
+    if (!none && (int)threadIdx.x < ns) slow = !seg_is_fast(irec[(int64_t)LARND_I_T0 * n + s_base + threadIdx.x], L, A.nticks);
+    if (none || !__syncthreads_or(slow)) {
       if (threadIdx.x < LARND_NPARAMS) A.partials[(int64_t)blockIdx.x * 16 + threadIdx.x] = 0.0f;
       return;
     }
@@ -585,6 +587,7 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   if (!steps && (int64_t)npix_capacity * g_stride >= ((int64_t)1 << 31)) sorted = false;
   if (steps && lut->nt - lut->L < 1) sorted = false;   // the running-sum form needs one sample in front of the response window
   A.sorted_active = sorted ? 1 : 0;
+  A.n_slow = sorted ? ws.gcnt + 3 /* GC_SLOW, sorted_runs.cuh */ : nullptr;
   prof_begin(2, st);
   if (sorted) {
     float* sorted_partials = ws.partials + (size_t)ws.n_chunks_max * 16;

@@ -686,7 +686,7 @@ size_t larnd_sorted_workspace_bytes(int64_t n) {
   b += align_up((size_t)LARND_NCLS_MAX * 4 * sizeof(int), 256) * 2;                // class_count, cursor (4 shift sub-buckets)
   b += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);                        // class_start
   b += align_up((nn / TR + LARND_NCLS_MAX + 1) * sizeof(int4), 256);               // tile_info
-  b += 256;                                                                        // counters
+  b += 256 + 1024;                                                                 // counters + per-class-block totals (sorted_runs.cuh)
   b += align_up((size_t)LARND_ROW0_COPIES * LARND_ROW0_TICKS_MAX * sizeof(float), 256);  // private garbage rows
   return b;
 }
@@ -699,7 +699,7 @@ void larnd_carve_sorted(char* p, int64_t n, Workspace* ws) {
   ws->cursor = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * 4 * sizeof(int), 256);
   ws->class_start = reinterpret_cast<int*>(p); p += align_up((size_t)LARND_NCLS_MAX * sizeof(int), 256);
   ws->tile_info = p; p += align_up((nn / TR + LARND_NCLS_MAX + 1) * sizeof(int4), 256);
-  ws->gcnt = reinterpret_cast<int*>(p); p += 256;
+  ws->gcnt = reinterpret_cast<int*>(p); p += 256 + 1024;
   ws->row0 = reinterpret_cast<float*>(p);
 }
 

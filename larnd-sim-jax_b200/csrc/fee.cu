@@ -360,50 +360,71 @@ k_fee_forward(const __grid_constant__ FeeArgs F, const __grid_constant__ larnd_p
   }
 }
 
-// exclusive scan of row_counts (single CTA, looped, four rows per thread and iteration) -> offsets, total
-__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ offsets,
-                                                      int32_t* __restrict__ total) {
-  __shared__ int wsum[32];
-  __shared__ int carry;
+// exclusive scan of row_counts -> offsets, total.  Two launches over blocks of 4096 rows (1024 threads x 4 rows): per-block
+// totals, then every block adds the totals in front of it (a few dozen values) to its own in-block scan — the single looped
+// CTA this replaces took 0.07-0.14 ms for the 268 k rows of a spill.
+constexpr int SCAN_ROWS = 4096;
+
+__device__ __forceinline__ int block_sum_1024(int v, int* wsum) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < n; b0 += 4096) {
-    const int i = b0 + 4 * threadIdx.x;
-    int v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = i + k < n ? counts[i + k] : 0;
-    const int tsum = v[0] + v[1] + v[2] + v[3];
-    int inc = tsum;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) wsum[wid] = v;
+  __syncthreads();
+  int t = wsum[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(1024) k_count_block_sums(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ bsum) {
+  __shared__ int wsum[32];
+  const int i = blockIdx.x * SCAN_ROWS + 4 * threadIdx.x;
+  int v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v += i + k < n ? counts[i + k] : 0;
+  const int tot = block_sum_1024(v, wsum);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ counts, int n, const int32_t* __restrict__ bsum,
+                                                      int32_t* __restrict__ offsets, int32_t* __restrict__ total) {
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int before = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) before += bsum[b];
+  const int carry = block_sum_1024(before, wsum);
+  const int i = blockIdx.x * SCAN_ROWS + 4 * threadIdx.x;
+  int v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = i + k < n ? counts[i + k] : 0;
+  const int tsum = v[0] + v[1] + v[2] + v[3];
+  int inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int x = wsum[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int u = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += u;
+      int u = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += u;
     }
-    if (lane == 31) wsum[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      int x = wsum[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int u = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += u;
-      }
-      wsum[lane] = x;
-    }
-    __syncthreads();
-    int off = carry + (wid > 0 ? wsum[wid - 1] : 0) + inc - tsum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i + k < n) offsets[i + k] = off;
-      off += v[k];
-    }
-    const int blk_total = wsum[31];
-    __syncthreads();
-    if (threadIdx.x == 0) carry += blk_total;
-    __syncthreads();
+    wsum[lane] = x;
   }
-  if (threadIdx.x == 0) *total = carry;
+  __syncthreads();
+  int off = carry + (wid > 0 ? wsum[wid - 1] : 0) + inc - tsum;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (i + k < n) offsets[i + k] = off;
+    off += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = carry + wsum[31];
 }
 
 struct CompactArgs {
@@ -579,7 +600,10 @@ extern "C" int larnd_fee_backward_steps(const float* g_adc_d, const float* saved
   return LARND_OK;
 }
 
-extern "C" size_t larnd_fee_scratch_bytes(int32_t npix) { return align_up((size_t)npix * 2 * sizeof(int32_t) + 64, 256); }
+// row counts | offsets | per-block totals of the hit-offset scan
+extern "C" size_t larnd_fee_scratch_bytes(int32_t npix) {
+  return align_up(((size_t)npix * 2 + (size_t)npix / SCAN_ROWS + 1) * sizeof(int32_t) + 64, 256);
+}
 
 extern "C" int larnd_fee_forward(const float* wfs_d, int64_t wfs_row_stride, const int32_t* unique_pixels_d, int32_t npix,
                                  const larnd_params_t* params, const float* noise_d, float* adc_d, float* ticks_d,
@@ -657,8 +681,14 @@ extern "C" int larnd_fee_forward_ex(const float* wfs_d, int64_t wfs_row_stride, 
   else k_fee_forward<1><<<grid, 32, smem, st>>>(F, *params);
   prof_end(3, st);
   LARND_LAUNCH_CHECK("k_fee_forward");
-  k_scan_counts<<<1, 1024, 0, st>>>(F.row_counts, npix, offsets, n_valid_d);
-  LARND_LAUNCH_CHECK("k_scan_counts");
+  {
+    int32_t* bsum = offsets + npix;
+    const int nblk = (npix + SCAN_ROWS - 1) / SCAN_ROWS;
+    k_count_block_sums<<<nblk, 1024, 0, st>>>(F.row_counts, npix, bsum);
+    LARND_LAUNCH_CHECK("k_count_block_sums");
+    k_scan_counts<<<nblk, 1024, 0, st>>>(F.row_counts, npix, bsum, offsets, n_valid_d);
+    LARND_LAUNCH_CHECK("k_scan_counts");
+  }
   if (hit_adc_d) {
     CompactArgs C;
     C.adc = adc_d; C.ticks = ticks_d; C.pixel_z = pixel_z_d; C.pixel_x = pixel_x_d; C.pixel_y = pixel_y_d; C.event = event_d;

@@ -18,6 +18,7 @@ constexpr int SPAN_MAX_S = KPT - 2;  // max (T0max - T0min) inside a run
 // Tiles are ordered by tick span (span-major class key), so runs with few impulse positions form contiguous ranges of the
 // tile table and can be served by kernel variants that hold fewer response samples in registers and fit more CTAs per SM:
 // gcnt[GC_SPAN + s] = first tile of span s (s = 0 .. SPAN_MAX_S), gcnt[GC_SPAN + SPAN_MAX_S + 1] = number of tiles.
+constexpr int GC_SLOW = 3;          // gcnt slot: number of segments the tile kernels leave to the chunk kernels (window ends beyond the readout)
 constexpr int GC_SPAN = 8;          // gcnt slots of the per-span tile offsets
 constexpr int GC_FWD = 16;          // gcnt slots of the forward kernels' tile counters (one per launch)
 constexpr int GC_BWD = 24;          // ... of the backward kernels'
@@ -85,7 +86,9 @@ k_build_runs(const __grid_constant__ SortArgs A) {
     s_fast[t] = seg_is_fast(T0, A.L, A.nticks);
   }
   s_head[t] = 0;
-  __syncthreads();
+  // segments left to the chunk kernels' boundary pass: counted here so that pass can return at once when there are none
+  const int nslow = __syncthreads_count(t < ns && !s_fast[t]);
+  if (t == 0 && nslow) atomicAdd(A.gcnt + GC_SLOW, nslow);
   bool kh = false;
   if (t < ns) {
     kh = t == 0 || s_ep[t] != s_ep[t - 1] || s_bx[t] != s_bx[t - 1] || s_by[t] != s_by[t - 1] || s_idx[t] != s_idx[t - 1] ||
@@ -140,17 +143,52 @@ k_build_runs(const __grid_constant__ SortArgs A) {
   }
 }
 
-// exclusive scans over the class histogram: run offsets and tile offsets; then the tile table
+// exclusive scans over the class histogram: run offsets and tile offsets; then the tile table.  Two launches over blocks of
+// 1024 classes: per-block totals (runs, tiles), then every block adds the totals in front of it to its in-block scans (the
+// single looped CTA this replaces took ~0.12 ms for the 50 k classes of a 100-template bank).
+constexpr int GC_BSUM = 64;         // gcnt[GC_BSUM + 2 b], [.. + 1]: runs / tiles of class block b (the counter area holds 64 + 2 * 128 ints)
+constexpr int CLASS_BLOCKS_MAX = 128;
+
+__global__ void __launch_bounds__(1024)
+k_class_sums(const __grid_constant__ SortArgs A) {
+  __shared__ int s_w[2][32];
+  if (A.counts[2] != 0) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 1024 + threadIdx.x;
+  const int4 sub = c < A.ncls ? reinterpret_cast<const int4*>(A.class_count)[c] : make_int4(0, 0, 0, 0);
+  const int cnt = sub.x + sub.y + sub.z + sub.w;
+  int v[2] = {cnt, (cnt + TR - 1) / TR};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) s_w[k][wid] = v[k];
+  }
+  __syncthreads();
+  if (wid < 2) {
+    int t = s_w[wid][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) A.gcnt[GC_BSUM + 2 * blockIdx.x + wid] = t;
+  }
+}
+
 __global__ void __launch_bounds__(1024)
 k_class_scan(const __grid_constant__ SortArgs A) {
   __shared__ int s_w[2][32];
   __shared__ int carry[2];
   if (A.counts[2] != 0) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
+  if (wid < 2) {  // totals of the class blocks in front of this one (<= CLASS_BLOCKS_MAX values per quantity)
+    int t = 0;
+    for (int b = lane; b < (int)blockIdx.x; b += 32) t += A.gcnt[GC_BSUM + 2 * b + wid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) carry[wid] = t;
+  }
   __syncthreads();
-  for (int c0 = 0; c0 < A.ncls; c0 += 1024) {
-    const int c = c0 + threadIdx.x;
+  {
+    const int c = blockIdx.x * 1024 + threadIdx.x;
     const int4 sub = c < A.ncls ? reinterpret_cast<const int4*>(A.class_count)[c] : make_int4(0, 0, 0, 0);
     const int cnt = sub.x + sub.y + sub.z + sub.w;
     int v[2] = {cnt, (cnt + TR - 1) / TR};
@@ -185,11 +223,12 @@ k_class_scan(const __grid_constant__ SortArgs A) {
       for (int i = 0; i < v[1]; ++i)  // tiles of this class
         A.tile_info[ex[1] + i] = make_int4(c, ex[0] + i * TR, min(TR, cnt - i * TR), 0);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) { carry[0] += s_w[0][31]; carry[1] += s_w[1][31]; }
-    __syncthreads();
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+      const int ntiles = carry[1] + s_w[1][31];
+      A.gcnt[1] = ntiles;
+      A.gcnt[GC_SPAN + SPAN_MAX_S + 1] = ntiles;
+    }
   }
-  if (threadIdx.x == 0) { A.gcnt[1] = carry[1]; A.gcnt[GC_SPAN + SPAN_MAX_S + 1] = carry[1]; }
 }
 
 __global__ void k_scatter_runs(const __grid_constant__ SortArgs A) {
@@ -240,7 +279,11 @@ inline int sorted_fill_and_build(SortArgs& A, int64_t n, const larnd_params_t& p
   const int64_t chunks = (n + LARND_CHUNK - 1) / LARND_CHUNK;
   k_build_runs<<<(unsigned)chunks, LARND_CHUNK, 0, st>>>(A);
   LARND_LAUNCH_CHECK("k_build_runs");
-  k_class_scan<<<1, 1024, 0, st>>>(A);
+  const int class_blocks = (A.ncls + 1023) / 1024;
+  if (class_blocks > CLASS_BLOCKS_MAX) { larnd_set_error("sorted accumulate: too many response classes"); return LARND_E_ARG; }
+  k_class_sums<<<class_blocks, 1024, 0, st>>>(A);
+  LARND_LAUNCH_CHECK("k_class_sums");
+  k_class_scan<<<class_blocks, 1024, 0, st>>>(A);
   LARND_LAUNCH_CHECK("k_class_scan");
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
