@@ -558,27 +558,43 @@ def run_ours(args):
             dsets = [_dio.TracksDataset(np.load(f)["segments"], nevents=None, max_nbatch=None, swap_xz=True, max_batch_len=50, chopped=True,
                                         pad=False, electron_sampling_resolution=0.005, device=dev) for f in files]
 
-            def run_all():
+            cap2 = {"npix": 0}
+
+            def run_all(hits_only):
                 nh = 0
                 for ds in dsets:
                     f2 = ds.get_track_fields()
                     for ib in range(len(ds)):
                         cap = sim.pad_size(ds.batch_nsteps[ib], "batch_size", 0.5)
                         tr = ds.device_batch(ib, capacity=cap)
-                        w, u = sim.simulate_wfs(p2, bank, tr, f2, n_events=len(ds.get_batch_global_event_ids(ib)))
-                        nh += int(sim.simulate_stochastic(p2, w, u, rngseed=ib)[0].shape[0])
+                        nev2 = len(ds.get_batch_global_event_ids(ib))
+                        if hits_only:   # the driver's path after its first batch: one call over the self-cleaning arena
+                            nh += int(sim.simulate_hits(p2, bank, tr, f2, rngseed=ib, npix_capacity=cap2["npix"], n_events=nev2)[0].shape[0])
+                        else:           # reference-shaped two-call path (pad_size buckets of the pixel list, waveforms returned)
+                            w, u = sim.simulate_wfs(p2, bank, tr, f2, n_events=nev2)
+                            cap2["npix"] = max(cap2["npix"], int(u.shape[0]))
+                            nh += int(sim.simulate_stochastic(p2, w, u, rngseed=ib)[0].shape[0])
                 return nh
-            run_all()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            nhits2 = run_all()
-            torch.cuda.synchronize()
-            wall2 = time.perf_counter() - t0
+
+            def wall_of(hits_only):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                nh = run_all(hits_only)
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0, nh
+            run_all(False)                       # warm-up + pixel capacity of the arena
+            wall2_two, nhits2_two = wall_of(False)
+            run_all(True)
+            wall2, nhits2 = wall_of(True)
+            assert nhits2 == nhits2_two, (nhits2, nhits2_two)
             nseg2 = sum(sum(ds.batch_nsteps) for ds in dsets)
             nb2 = sum(len(ds) for ds in dsets)
             extras["prepared_inputs"] = {"metric": "segments/s over all 22 prepared inputs (BASELINE config 2, production-driver loop)",
                                          "value": nseg2 / wall2, "unit": "segments/s", "wall_s": wall2, "files": len(files), "batches": nb2,
                                          "segments": int(nseg2), "hits": int(nhits2), "ms_per_batch": 1e3 * wall2 / nb2,
+                                         "path": "sim.simulate_hits (hits-only, persistent self-cleaning arena, one host sync per batch)",
+                                         "two_call_path": {"value": nseg2 / wall2_two, "ms_per_batch": 1e3 * wall2_two / nb2,
+                                                           "path": "simulate_wfs + simulate_stochastic with the reference's pad_size buckets"},
                                          "timing": "host wall clock, one pass after a warm-up pass (the loop is launch/sync-bound at ~10 k segments per batch)"}
 
     # per-kernel device times of the dominant kernels, same launches as above

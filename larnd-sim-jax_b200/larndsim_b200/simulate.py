@@ -20,7 +20,7 @@ import sys
 import numpy as np
 import torch
 
-from . import consts, dataio, detsim, fee, h5io, losses, sim
+from . import _lib, consts, dataio, detsim, fee, h5io, losses, sim
 
 logger = logging.getLogger("larndsim_b200.simulate")
 DATASETS = ("adc_clean", "adc", "Q", "pixels", "ticks", "eventID", "pix_x", "pix_y", "pix_z")
@@ -91,6 +91,7 @@ def main(config):
     fields = dataset.get_track_fields()
     tree, flat = {}, {k: [] for k in ("adc", "Q", "pix_x", "pix_y", "pix_z", "ticks", "hit_prob", "eventID")}
     n_segments = 0
+    npix_cap = None   # pixel capacity of the hits-only arena, sized from the first batch
     for ibatch in range(len(dataset)):
         size = sim.pad_size(dataset.batch_nsteps[ibatch] if config.chop else len(dataset.batch_row_indices[ibatch]), "batch_size", 0.5)
         tracks = dataset.device_batch(ibatch, capacity=size)
@@ -100,9 +101,23 @@ def main(config):
         # (optimize/simulate.py:111-113); the ids are local by construction here, the packing limit is the int32 one
         detsim.validate_event_ids_for_packing(ref_params, np.arange(n_ev, dtype=np.int64), kind="pixel", context="simulate batch %d" % ibatch)
         rngseed = ibatch if config.seed is None else config.seed
-        if config.mode == "lut":
+        if config.mode == "lut" and not config.save_wfs and npix_cap is not None:
+            # hits-only batches after the first: one call over the persistent, self-cleaning waveform arena with a fixed pixel
+            # capacity (no per-batch allocation / memset, one host synchronisation); the hits do not depend on the padding.
+            # A batch with more pixels than the capacity is flagged on the device: grow and redo it.
+            while True:
+                try:
+                    out = sim.simulate_hits(ref_params, response, tracks, fields, rngseed=rngseed, npix_capacity=npix_cap, n_events=n_ev)
+                    break
+                except _lib.LarndError as e:
+                    if "npix_capacity" not in str(e):
+                        raise
+                    npix_cap *= 2
+            wfs = None
+        elif config.mode == "lut":
             wfs, unique_pixels = sim.simulate_wfs(ref_params, response, tracks, fields, n_events=n_ev)
             out = sim.simulate_stochastic(ref_params, wfs, unique_pixels, rngseed=rngseed)
+            npix_cap = 2 * int(unique_pixels.shape[0])
         else:
             out = sim.simulate_parametrized(ref_params, tracks, fields, rngseed=rngseed, n_events=n_ev)
             wfs = None
