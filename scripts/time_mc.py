@@ -1,4 +1,4 @@
-"""Times the MC-current-mode forward (prepare + unique + analytic current + scatter) with CUDA events:
+"""Times the MC-current-mode forward (prepare + unique + analytic current + scatter) and backward with CUDA events:
 python scripts/time_mc.py 2000000 [path of an alternative liblarnd_b200.so]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,3 +30,10 @@ for dic in (True, False):
     e1.record(); torch.cuda.synchronize()
     print("%s diffusion_in_current=%s segments=%d: %.3f ms/forward, checksum %.6e" %
           (os.path.basename(_lib.LIB_PATH), dic, tracks.shape[0], e0.elapsed_time(e1) / 5, float(st.wfs_full[:, 1:].double().abs().sum())))
+    g = torch.ones_like(st.wfs_full[:, 1:]) * (st.unique_pixels >= 0).unsqueeze(1)
+    grad = sim.mc_backward(st, tracks, g)
+    e0.record()
+    for i in range(5):
+        grad = sim.mc_backward(st, tracks, g)
+    e1.record(); torch.cuda.synchronize()
+    print("   backward: %.3f ms, grad[:6] %s" % (e0.elapsed_time(e1) / 5, [float(x) for x in grad[:6]]))
