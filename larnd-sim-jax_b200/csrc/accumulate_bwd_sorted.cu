@@ -22,8 +22,15 @@
 
 namespace {
 
-constexpr int BT_THREADS = 256;
-constexpr int BT_WARPS = BT_THREADS / 32;
+constexpr int BT_THREADS = 256;        // dense-gradient variants (register-resident response: tuned launch bounds below)
+#ifndef LARND_BT_THREADS_STEPS
+#define LARND_BT_THREADS_STEPS 256
+#endif
+#ifndef LARND_BWD_STEPS_CTAS
+#define LARND_BWD_STEPS_CTAS 4
+#endif
+constexpr int BT_THREADS_STEPS = LARND_BT_THREADS_STEPS;   // step-event variant
+constexpr int BT_WARPS = (BT_THREADS_STEPS > BT_THREADS ? BT_THREADS_STEPS : BT_THREADS) / 32;   // per-warp buffers: the larger CTA
 constexpr int SEGMAX_B = TR * MAXLEN;
 constexpr int NACC = 15;           // dq, dfrac, da, db, dc, dWxg[5], dWyg[5]
 constexpr int GSB = 3 * KPT + 6;   // per-warp G buffer (3*KPT values, padded to a multiple of 8)
@@ -382,7 +389,8 @@ __device__ __forceinline__ void load_response_b(float (&Rw)[3][NS][KP], const fl
 // KP / span range / launch as in k_acc_tiles: the variants holding 3 / 4 response positions (36 / 48 registers, 4 / 3 CTAs
 // per SM) serve the tiles of runs with few impulse positions, the KP = KPT kernel the rest (or everything).
 template <int NS, int KP, bool STEPS = false>  // [region: kernel prologue]
-__global__ void __launch_bounds__(BT_THREADS, STEPS ? 4 : (NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1)))
+__global__ void __launch_bounds__(STEPS ? BT_THREADS_STEPS : BT_THREADS,
+                                  STEPS ? LARND_BWD_STEPS_CTAS : (NS <= 4 ? (KP <= 3 ? 4 : (KP <= 4 ? 3 : 2)) : (NS == 5 && KP <= 4 ? 2 : 1)))
 k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd_params_t p, const int span_lo, const int span_hi,
             const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -399,7 +407,8 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
   lk.n_unique = S.counts[0];
   lk.n_neg = S.counts[1];
   if (threadIdx.x < nb && threadIdx.x < 16) build_bin_groups(threadIdx.x, nb, S.half2, sm.g_n[threadIdx.x], sm.g_ox[threadIdx.x], sm.g_ci[threadIdx.x], sm.g_mask[threadIdx.x]);
-  for (int u = threadIdx.x; u < S.P * S.P; u += BT_THREADS) {
+  constexpr int NTHR = STEPS ? BT_THREADS_STEPS : BT_THREADS;
+  for (int u = threadIdx.x; u < S.P * S.P; u += NTHR) {
     sm.udx[u] = (signed char)(u / S.P - S.n_neigh);
     sm.udy[u] = (signed char)(u % S.P - S.n_neigh);
   }
@@ -448,7 +457,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
     __syncthreads();
     // ---- stage the segments (thread <-> segment) -----------------------------------------------------------------  // [region: stage segments]
     const int nseg = sm.nseg;
-    for (int i = threadIdx.x; i < nseg; i += BT_THREADS) {
+    for (int i = threadIdx.x; i < nseg; i += NTHR) {
       const int r = sm.owner[i];
       const int4 e = sm.run[r];
       const int64_t s = (int64_t)e.x + (i - sm.soff[r]);
@@ -548,7 +557,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
     float gacc[LARND_NPARAMS];   // this thread's parameter gradients of the tile; live only during the chain-rule phase
 #pragma unroll
     for (int k = 0; k < LARND_NPARAMS; ++k) gacc[k] = 0.0f;
-    for (int i = threadIdx.x; i < nseg; i += BT_THREADS) {
+    for (int i = threadIdx.x; i < nseg; i += NTHR) {
       if (sm.m[i] == INT32_MIN) continue;
       const int64_t s = sm.sid[i];
       const float q = sm.q[i];
@@ -570,7 +579,7 @@ k_bwd_tiles(const __grid_constant__ BwdSortArgs A, const __grid_constant__ larnd
   __syncthreads();
   if (threadIdx.x < LARND_NPARAMS) {
     float v = 0.f;
-    for (int w = 0; w < BT_WARPS; ++w) v += sm.red[w][threadIdx.x];
+    for (int w = 0; w < NTHR / 32; ++w) v += sm.red[w][threadIdx.x];
     A.partials[(int64_t)blockIdx.x * 16 + threadIdx.x] = v;
   }
 }
@@ -599,8 +608,8 @@ int larnd_launch_accumulate_bwd_sorted(int64_t n, const larnd_params_t& p, const
       LARND_CUDA(cudaFuncSetAttribute(k_bwd_tiles<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
       attr_steps = true;
     }
-    const int grid = sorted_grid(4, LARND_BWD_SORTED_SLOTS);
-    k_bwd_tiles<4, 2, true><<<grid, BT_THREADS, smem_s, st>>>(A, p, 0, SPAN_MAX_S, 2);
+    const int grid = sorted_grid(LARND_BWD_STEPS_CTAS, LARND_BWD_SORTED_SLOTS);
+    k_bwd_tiles<4, 2, true><<<grid, BT_THREADS_STEPS, smem_s, st>>>(A, p, 0, SPAN_MAX_S, 2);
     LARND_LAUNCH_CHECK("k_bwd_tiles<steps>");
     *n_slots_out = grid;
     return LARND_OK;

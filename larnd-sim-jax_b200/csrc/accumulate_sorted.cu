@@ -31,7 +31,10 @@ namespace {
 // ------------------------------------------------------------------------------------------------ tile consumer
 constexpr int SEGMAX = TR * MAXLEN;  // segments per tile
 #ifndef LARND_KP4_CTAS
-#define LARND_KP4_CTAS 4
+#define LARND_KP4_CTAS 3
+#endif
+#ifndef LARND_KP6_CTAS
+#define LARND_KP6_CTAS 3
 #endif
 // Boundary corrections of a (run, unit) frame live at frame positions j + s <= KP + 2; a lane reads the four positions of
 // its ticks, lanes whose ticks lie beyond read the always-zero rows KP + 3 .. KP + 6 (no branch in the consume loops).
@@ -421,7 +424,7 @@ __device__ __forceinline__ void neigh_run_npos(const SortArgs& A, const TileSmem
 // A launch serves the tiles of spans span_lo .. span_hi (KP >= span_hi + 2), a contiguous range of the tile table, and
 // pulls them through its own counter gcnt[GC_FWD + launch].
 template <int NSV, int KP>
-__global__ void __launch_bounds__(TILE_THREADS, NSV == 1 ? (KP <= 4 ? LARND_KP4_CTAS : 3) : 2)
+__global__ void __launch_bounds__(TILE_THREADS, NSV == 1 ? (KP <= 4 ? LARND_KP4_CTAS : LARND_KP6_CTAS) : 2)
 k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int span_hi, const int launch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<KP>& sm = *reinterpret_cast<TileSmem<KP>*>(smem_raw);
@@ -675,7 +678,7 @@ __global__ void k_reduce_row0(const float* __restrict__ row0, int ncopies, int r
   if (acc != 0.0f) atomicAdd(wfs + c, acc);
 }
 
-static_assert(sizeof(TileSmem<4>) <= 56 * 1024, "the 4-position tile kernel is sized for four CTAs per SM");
+static_assert(sizeof(TileSmem<4>) <= (227 / LARND_KP4_CTAS - 1) * 1024, "the 4-position tile kernel must fit LARND_KP4_CTAS CTAs per SM");
 
 }  // namespace
 
@@ -740,7 +743,7 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     attr_done = true;
   }
   const int grid_small = sorted_grid(nsv == 1 ? LARND_KP4_CTAS : 2, LARND_ROW0_COPIES);  // KP = 4 variant
-  const int grid_big = sorted_grid(nsv == 1 ? 3 : 2, LARND_ROW0_COPIES);
+  const int grid_big = sorted_grid(nsv == 1 ? LARND_KP6_CTAS : 2, LARND_ROW0_COPIES);
   const int ncopies = max(grid_small, grid_big);
   if (!A.skip_garbage) LARND_CUDA(cudaMemsetAsync(ws.row0, 0, (size_t)ncopies * A.r0stride * sizeof(float), st));
   int big_lo = 0;  // first span left to the KPT kernel

@@ -23,7 +23,13 @@ constexpr int GC_SPAN = 8;          // gcnt slots of the per-span tile offsets
 constexpr int GC_FWD = 16;          // gcnt slots of the forward kernels' tile counters (one per launch)
 constexpr int GC_BWD = 24;          // ... of the backward kernels'
 constexpr int MAXLEN = 8;           // segments per run (bounds the divergence of the lane <-> run build loops)
-constexpr int TILE_THREADS = 256;
+// CTA shape of the forward tile kernel, measured at 10 M segments (accumulate slot, ms): 256 x 4 CTAs/SM 12.54 | 256 x 3 12.23 |
+// 288 x 3 11.95 | 320 x 3 11.99 | 224 x 4 12.68 | 192 x 4 13.30 | 384 x 2 13.01 | 512 x 2 13.81.  Nine warps at 72 registers
+// and three 58 KB CTAs per SM (88 KB left to the L1) beat eight warps at 64 registers and four CTAs (32 KB of L1).
+#ifndef LARND_TILE_THREADS
+#define LARND_TILE_THREADS 288
+#endif
+constexpr int TILE_THREADS = LARND_TILE_THREADS;
 constexpr int NW = TILE_THREADS / 32;
 constexpr int HS = 3 * KPT + 1;     // per-lane stride of the train buffer (odd: conflict-free)
 constexpr int ES = KPT + 1;         // per-lane stride of the correction buffer (odd)
