@@ -40,10 +40,15 @@ constexpr int SEGMAX = TR * MAXLEN;  // segments per tile
 // its ticks, lanes whose ticks lie beyond read the always-zero rows KP + 3 .. KP + 6 (no branch in the consume loops).
 // Row stride TRE = 33: a lane-dependent ROW with a uniform column must not land in one bank.
 constexpr int TRE = TR + 1;
-template <int KP> struct ECfg { static constexpr int USED = KP + 3, EK = KP + 7; };
+// (per warp only the rows a lane below USED / 4 can touch, rounded up to whole groups of four; every other lane reads the
+// CTA-wide zero block TileSmem::zE — shared memory given back to the L1, which the kernel is sensitive to)
+template <int KP> struct ECfg { static constexpr int USED = KP + 3, EK = (KP + 3 + 3) / 4 * 4; };
 // per-warp train buffer: built as [run][3 j + template] (stride HS, conflict-free read-modify-write), then re-laid in place
 // as float4 [j][run] = (3 templates, 0) so that the consume loop fetches a position with ONE broadcast 128-bit load
-template <int KP> struct HCfg { static constexpr int FLOATS = (TR * HS > KP * TR * 4) ? TR * HS : KP * TR * 4; };
+template <int KP> struct HCfg {
+  static constexpr int HS = 3 * KP + 1;   // per-lane stride of the build layout (odd: conflict-free)
+  static constexpr int FLOATS = (TR * HS > KP * TR * 4) ? TR * HS : KP * TR * 4;
+};
 
 template <int KP>
 struct TileSmem {
@@ -59,6 +64,7 @@ struct TileSmem {
   float mom[TR][MS];            // neighbour correction moments A1,A2,A3,B1,B3 per position
   __align__(16) float ph[NW][HCfg<KP>::FLOATS];  // per-warp trains of the current group (see HCfg)
   float pE[NW][ECfg<KP>::EK * TRE];               // per-warp boundary corrections: [frame position][run or unit]
+  float zE[4 * TRE];                              // always zero: the corrections of lanes whose ticks lie beyond position USED
   unsigned char g_n[16], g_ox[16][5], g_ci[16][5], g_mask[16][5];
   signed char udx[225], udy[225];  // relative pixel of every neighbour unit (P <= 15)
   int ubin[96];                 // neighbour unit -> response row (template 0 bin; entry P*P: the neighbourhood-sum row)
@@ -162,7 +168,7 @@ __device__ __forceinline__ void consume_main(const SortArgs& A, const TileSmem<K
   bool act[NSV];
 #pragma unroll
   for (int v = 0; v < NSV; ++v) act[v] = 128 * v + 4 * lane - s < A.L + NPOS;
-  const float* const Elane = Ebuf + (4 * lane < ECfg<KP>::USED ? 4 * lane : ECfg<KP>::USED) * TRE;
+  const float* const Elane = 4 * lane < ECfg<KP>::USED ? Ebuf + 4 * lane * TRE : sm.zE;
   const float4* const h4 = reinterpret_cast<const float4*>(hbuf);
   float* const wl = A.wfs + 4 * lane;
   while (todo) {
@@ -265,7 +271,7 @@ __device__ __forceinline__ void neigh_run(const SortArgs& A, const TileSmem<KP>&
   for (int v = 0; v < NSV; ++v) act[v] = 128 * v + 4 * lane - s < A.L + NPOS;
   const float* const t4 = A.t0s + ((int64_t)s * A.n0rows * A.lps + 4 * lane);  // shifted copy s, this lane's ticks
   float* const wl = A.wfs + 4 * lane;
-  const float* const Elane = myE + (4 * lane < ECfg<KP>::USED ? 4 * lane : ECfg<KP>::USED) * TRE;
+  const float* const Elane = 4 * lane < ECfg<KP>::USED ? myE + 4 * lane * TRE : sm.zE;
   const float* const mom = sm.mom[p];
   const int ctbase = A.nt - A.L - tmin;
   float acc0[NSV][4];  // frame of the garbage row: neighbourhood sum minus the neighbours that own a row
@@ -443,6 +449,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
     sm.udy[u] = (signed char)(u % A.P - A.n_neigh);
   }
   for (int i = threadIdx.x; i < NW * ECfg<KP>::EK * TRE; i += TILE_THREADS) (&sm.pE[0][0])[i] = 0.0f;  // incl. the always-zero rows
+  for (int i = threadIdx.x; i < 4 * TRE; i += TILE_THREADS) sm.zE[i] = 0.0f;
   const int tile_lo = A.gcnt[GC_SPAN + span_lo];
   const int ntiles = A.gcnt[GC_SPAN + span_hi + 1];
   int* const tile_counter = A.gcnt + GC_FWD + launch;
@@ -598,7 +605,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
       // [region: phaseA build]
       // build: lane <-> run
       if (row >= 0) {
-        float* h = myh + lane * HS;
+        float* h = myh + lane * HCfg<KP>::HS;
 #pragma unroll
         for (int k = 0; k < 3 * KP; ++k) h[k] = 0.0f;
 #pragma unroll
@@ -633,7 +640,7 @@ k_acc_tiles(const __grid_constant__ SortArgs A, const int span_lo, const int spa
         float hv[3 * KP];
         if (row >= 0) {
 #pragma unroll
-          for (int k = 0; k < 3 * KP; ++k) hv[k] = myh[lane * HS + k];
+          for (int k = 0; k < 3 * KP; ++k) hv[k] = myh[lane * HCfg<KP>::HS + k];
         }
         __syncwarp();
         if (row >= 0) {
@@ -740,6 +747,10 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<1, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
     LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<2, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6));
+#ifdef LARND_CARVEOUT   // experiment: force the shared-memory carveout (percent) to see how much the tile kernels depend on L1 capacity
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, LARND_CARVEOUT));
+    LARND_CUDA(cudaFuncSetAttribute(k_acc_tiles<1, KPT>, cudaFuncAttributePreferredSharedMemoryCarveout, LARND_CARVEOUT));
+#endif
     attr_done = true;
   }
   const int grid_small = sorted_grid(nsv == 1 ? LARND_KP4_CTAS : 2, LARND_ROW0_COPIES);  // KP = 4 variant
