@@ -598,6 +598,14 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
     k_reduce_partials<<<LARND_NPARAMS, 256, 0, st>>>(sorted_partials, n_slots, grad_params);
     LARND_LAUNCH_CHECK("k_reduce_partials");
   }
+  // The chunk kernel below takes what the tile kernel leaves: segments whose window ends beyond the readout — none when the
+  // response is no longer than the readout (T0 + L <= nt <= n_ticks - 2) — and everything when garbage rows carry gradient
+  // (decided on the device unless the caller promised otherwise, or the gradient comes as step events).  When the host knows
+  // there is nothing left, the pass (78 k CTAs writing zero partials + their reduction at spill size) is not launched.
+  if (sorted && lut->nt <= p.n_ticks - 2 && (steps || (flags & 1))) {
+    prof_end(2, st);
+    return LARND_OK;
+  }
   const int need = lut->L + SPAN_MAX + 2;  // gradient window of a run: ticks tmin .. tmin + span + 1 + L - 1
   int rc;
   if (need <= 32 * 2) rc = launch_bwd<2>(A, p, chunks, st);

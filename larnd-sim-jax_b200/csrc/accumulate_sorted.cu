@@ -771,8 +771,12 @@ int larnd_launch_accumulate_sorted(int64_t n, const larnd_params_t& p, const lar
     k_reduce_row0<<<(p.n_ticks + 255) / 256, 256, 0, st>>>(ws.row0, ncopies, A.r0stride, p.n_ticks, wfs);
     LARND_LAUNCH_CHECK("k_reduce_row0");
   }
-  // segments whose window ends beyond the readout: per-segment path of accumulate.cu
-  int rc = larnd_launch_accumulate(n, p, lut, ws, npix_capacity, flags | LARND_ACC_SLOW_ONLY, wfs, wfs_stride, counts, st);
+  // segments whose window ends beyond the readout: per-segment path of accumulate.cu.  A window starts at T0 = nt - L - ct
+  // (ct >= 0) and ends at T0 + L <= nt: with a response no longer than the readout (nt <= n_ticks - 2, seg_is_fast) there is
+  // no such segment and the pass — 78 k CTAs that each find nothing to do at spill size — is not launched at all.
+  int rc = LARND_OK;
+  if (lut->nt > p.n_ticks - 2)
+    rc = larnd_launch_accumulate(n, p, lut, ws, npix_capacity, flags | LARND_ACC_SLOW_ONLY, wfs, wfs_stride, counts, st);
   prof_end(1, st);
   return rc;
 }
