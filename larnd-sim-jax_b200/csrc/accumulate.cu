@@ -44,6 +44,7 @@ struct AccArgs {
   float* wfs;
   unsigned long long* wfs64;  // deterministic mode: (npix, nticks) 64-bit fixed-point accumulators instead of wfs (else nullptr)
   int skip_garbage;
+  int chunk;      // segments per CTA (<= S, larnd_chunk_size)
   int slow_only;  // 1: only segments whose window touches the ends of the readout (the rest is done by accumulate_sorted.cu)
   const int* n_slow;  // slow_only: device count of such segments (k_build_runs), 0 = nothing to do
 };
@@ -286,8 +287,8 @@ k_lut_accumulate(const __grid_constant__ AccArgs A) {
   ChunkSmem& sm = *reinterpret_cast<ChunkSmem*>(smem_raw);
   if (A.counts[2] != 0) return;  // capacity overflow / bad event ids flagged upstream
   const int lane = threadIdx.x & 31;
-  const int64_t s_base = (int64_t)blockIdx.x * S;
-  const int ns = (int)min((int64_t)S, A.n - s_base);
+  const int64_t s_base = (int64_t)blockIdx.x * A.chunk;
+  const int ns = (int)min((int64_t)A.chunk, A.n - s_base);
   const int nb = A.nb;
   const int L = A.L;
   if (A.slow_only) {  // nothing to do for a chunk without boundary segments (the common case)
@@ -606,7 +607,8 @@ int larnd_launch_accumulate(int64_t n, const larnd_params_t& p, const larnd_lut*
   A.skip_garbage = flags & LARND_FLAG_SKIP_GARBAGE;
   A.slow_only = slow_only ? 1 : 0;
   A.n_slow = slow_only ? ws.gcnt + 3 /* GC_SLOW, sorted_runs.cuh */ : nullptr;
-  const int64_t chunks = (n + S - 1) / S;
+  A.chunk = (slow_only || det_acc) ? S : larnd_chunk_size(n);   // (the deterministic sums are defined per 128-segment chunk)
+  const int64_t chunks = (n + A.chunk - 1) / A.chunk;
   // register window = run window (L + 2 + span) + slack for the tick drift between consecutive runs of a track;
   // more slack = fewer flushes but more predicated-off slots in the inner loop.
   int need = lut->L + 2 + SPAN_MAX;  // measured on B200: the tightest window wins (4 slots vs 6 at L=100: -15 % time)

@@ -47,6 +47,7 @@ struct BwdArgs {
   const int* garbage_grad_nonzero;  // device flag written by k_garbage_grad_flag
   StepsView steps;   // compact upstream gradient (larnd_fee_backward_steps) used instead of g when use_steps != 0
   int use_steps;
+  int chunk;          // segments per CTA (<= S, larnd_chunk_size)
   int sorted_active;  // the class-sorted kernel (accumulate_bwd_sorted.cu) runs too and takes every segment it can handle
   const int* n_slow;  // sorted_active: device count of the segments it leaves to this kernel (k_build_runs)
 };
@@ -210,8 +211,8 @@ k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool bad = A.counts[2] != 0;
-  const int64_t s_base = (int64_t)blockIdx.x * S;
-  const int ns = bad ? 0 : (int)min((int64_t)S, A.n - s_base);
+  const int64_t s_base = (int64_t)blockIdx.x * A.chunk;
+  const int ns = bad ? 0 : (int)min((int64_t)A.chunk, A.n - s_base);
   const int nb = A.nb, L = A.L, nt = A.nt;
   const int64_t n = A.n;
   const int* irec = reinterpret_cast<const int*>(A.rec);
@@ -565,7 +566,8 @@ int larnd_launch_accumulate_bwd(int64_t n, const larnd_params_t& p, const larnd_
   A.g = g_wfs; A.g_stride = g_stride;
   A.partials = ws.partials;
   A.skip_garbage = flags & 1;
-  const int64_t chunks = (n + S - 1) / S;
+  A.chunk = larnd_chunk_size(n);
+  const int64_t chunks = (n + A.chunk - 1) / A.chunk;
   int* gflag = reinterpret_cast<int*>(ws.partials + (size_t)ws.n_chunks_max * 16) - 4;  // last 16 bytes of the partials area
   LARND_CUDA(cudaMemsetAsync(gflag, 0, sizeof(int), st));
   A.use_steps = steps ? 1 : 0;

@@ -64,7 +64,7 @@ extern "C" size_t larnd_workspace_bytes(int64_t n, int32_t n_events, int32_t ntp
   if (n < 0 || n_events < 0 || ntpc < 1 || nx < 1 || ny < 1) return 0;
   int64_t nw = bitmap_words(n_events, ntpc, nx, ny);
   int64_t nsb = (nw + LARND_SCAN_WORDS_PER_BLOCK - 1) / LARND_SCAN_WORDS_PER_BLOCK;
-  int64_t nchunks = (n + LARND_CHUNK - 1) / LARND_CHUNK + 1;
+  int64_t nchunks = (n + LARND_CHUNK - 1) / LARND_CHUNK + 1 + LARND_SMALL_CHUNK_SLOTS;
   size_t b = 0;
   b += align_up((size_t)LARND_NFIELDS * (size_t)(n > 0 ? n : 1) * sizeof(float), 256);
   b += align_up((size_t)nw * 4, 256) * 2;
@@ -112,7 +112,7 @@ bool larnd_carve_workspace(void* base, size_t bytes, int64_t n, int32_t n_events
   ws->n = n;
   ws->n_words = nw;
   ws->n_scan_blocks = (nw + LARND_SCAN_WORDS_PER_BLOCK - 1) / LARND_SCAN_WORDS_PER_BLOCK;
-  ws->n_chunks_max = (n + LARND_CHUNK - 1) / LARND_CHUNK + 1;
+  ws->n_chunks_max = (n + LARND_CHUNK - 1) / LARND_CHUNK + 1 + LARND_SMALL_CHUNK_SLOTS;
   ws->pid_offset = ntpc * nx * ny;
   ws->rec = reinterpret_cast<float*>(p);
   p += align_up((size_t)LARND_NFIELDS * (size_t)(n > 0 ? n : 1) * sizeof(float), 256);

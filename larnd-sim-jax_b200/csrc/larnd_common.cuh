@@ -66,7 +66,22 @@ void larnd_carve_sorted(char* p, int64_t n, Workspace* ws);
 int larnd_sorted_supported(const larnd_params_t& p, const larnd_lut* lut);
 
 #define LARND_SCAN_WORDS_PER_BLOCK 2048
-#define LARND_CHUNK 128  // segments per accumulate CTA
+#define LARND_CHUNK 128  // segments per accumulate CTA (capacity of the chunk kernels' staging arrays)
+#define LARND_SMALL_CHUNK_SLOTS 2560  // extra per-chunk partial slots for batches cut into chunks smaller than LARND_CHUNK
+// Segments per CTA of the chunk kernels: a fit-sized batch (~20 k segments) cut into 128-segment chunks is 155 CTAs — one per
+// SM, each walking ~30 runs serially (0.40 / 0.73 ms forward / backward); smaller chunks trade a few more window flushes for
+// four times the CTAs.  A function of n only, so the deterministic mode stays reproducible.
+#ifndef LARND_CHUNK_MIN
+#define LARND_CHUNK_MIN 32
+#endif
+#ifndef LARND_CHUNK_CTAS
+#define LARND_CHUNK_CTAS (4 * 148)
+#endif
+static inline int larnd_chunk_size(int64_t n) {
+  int c = LARND_CHUNK;
+  while (c > LARND_CHUNK_MIN && (n + c - 1) / c < LARND_CHUNK_CTAS) c >>= 1;
+  return c;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
