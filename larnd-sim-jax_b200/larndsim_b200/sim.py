@@ -749,6 +749,11 @@ class HitsArena:
 _default_arenas = {}
 
 
+def release_arenas():
+    """Drops the per-device default arenas of simulate_hits (a spill-sized arena holds ~2 GB of waveform scratch)."""
+    _default_arenas.clear()
+
+
 def simulate_hits(params, response_template, tracks, fields, rngseed=0, npix_capacity=None, n_events=None, raw=None, arena=None):
     """simulate_wfs + simulate_stochastic (sim_jax.py:689-769) as ONE hits-only call: the same 8-tuple of hits, the
     waveforms stay internal scratch (no gradients, nothing to return), which lets the buffer be reused and cleaned by the

@@ -391,3 +391,26 @@ def test_vdrift_follows_the_reference_arithmetic_for_static_and_fitted_efield():
     h = 1e-6
     fd = (oc.get_vdrift(op.replace(eField=op.eField + h)) - oc.get_vdrift(op.replace(eField=op.eField - h))) / (2 * h)
     assert abs(dv - fd) < 1e-8 and dv == dv2
+
+
+def test_parameter_block_is_cached_per_params_object_and_follows_in_place_updates():
+    """sim.make_pod builds the C parameter block once per immutable Params object (it is requested several times per batch);
+    the cache key carries the version counters of the tensor-valued fields, so an optimiser's in-place update is seen, and
+    every call returns its own copy (callers patch fields of it)."""
+    import torch
+    import common as cm
+    from larndsim_b200 import sim
+    pp = cm.product_params(number_pix_neighbors=2, signal_length=150)
+    a, b = sim.make_pod(pp, (32, 25, 25, 1950)), sim.make_pod(pp, (32, 25, 25, 1950))
+    assert bytes(a) == bytes(b) and a is not b
+    a.n_templates = 7
+    assert sim.make_pod(pp, (32, 25, 25, 1950)).n_templates == b.n_templates != 7
+    assert "_pod_cache" not in pp.replace(lifetime=100.0).__dict__          # replace() starts from the declared fields only
+    assert abs(sim.make_pod(pp.replace(lifetime=100.0)).lifetime - 100.0) < 1e-6
+    pg = cm.product_params(grad=("Ab", "lifetime"), number_pix_neighbors=2, signal_length=150)
+    before = sim.make_pod(pg).lifetime
+    with torch.no_grad():
+        pg.lifetime.mul_(0.5)
+    assert abs(sim.make_pod(pg).lifetime - 0.5 * before) < 1e-3 * before
+    with pytest.raises(ValueError):
+        sim.make_pod(pp, (1000, 25, 25, 1950))   # more bank rows than long_diff_template entries
