@@ -203,8 +203,11 @@ __global__ void k_garbage_grad_flag(const float* __restrict__ g, int64_t g_strid
   if (__syncthreads_or(nz) && threadIdx.x == 0) atomicOr(flag, 1);
 }
 
+#ifndef LARND_BWD_CHUNK_CTAS
+#define LARND_BWD_CHUNK_CTAS 3
+#endif
 template <int NG>
-__global__ void __launch_bounds__(BWD_THREADS, 3)
+__global__ void __launch_bounds__(BWD_THREADS, LARND_BWD_CHUNK_CTAS)
 k_lut_backward(const __grid_constant__ BwdArgs A, const __grid_constant__ larnd_params_t p) {
   const bool skip_garbage = A.skip_garbage || (*A.garbage_grad_nonzero == 0);
   extern __shared__ __align__(16) unsigned char smem_raw[];

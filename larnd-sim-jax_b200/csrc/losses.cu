@@ -42,7 +42,7 @@ k_rbf_bbox(const float* __restrict__ pts, int n, float* __restrict__ bbox) {
 __global__ void __launch_bounds__(RT)
 k_rbf_field(const float* __restrict__ tgt, int nt, const float* __restrict__ tbox, const float* __restrict__ src,
             const float* __restrict__ w, int ns, const float* __restrict__ sbox, int n_src_tiles, float inv2s2, float cutoff,
-            float* __restrict__ out /* (nt, 4): S0, S1x, S1y, S1z */) {
+            float* __restrict__ out /* (nt, 4): S0, S1x, S1y, S1z */, int nsplit) {
   __shared__ float4 s_src[RT];
   const int i = blockIdx.x * RT + threadIdx.x;
   const bool live = i < nt;
@@ -51,7 +51,9 @@ k_rbf_field(const float* __restrict__ tgt, int nt, const float* __restrict__ tbo
 #pragma unroll
   for (int k = 0; k < 3; ++k) { blo[k] = tbox[(int64_t)blockIdx.x * 6 + k]; bhi[k] = tbox[(int64_t)blockIdx.x * 6 + 3 + k]; }
   float s0 = 0.0f, s1x = 0.0f, s1y = 0.0f, s1z = 0.0f;
-  for (int tile = 0; tile < n_src_tiles; ++tile) {
+  // gridDim.y = nsplit CTAs share a target tile, each visiting every nsplit-th source tile: a fit-sized hit list is only a
+  // few dozen target tiles (56 CTAs on 148 SMs, 6 % of the warp slots), the source loop is what can be spread
+  for (int tile = blockIdx.y; tile < n_src_tiles; tile += nsplit) {
     // distance between the two boxes (block-uniform): beyond the cutoff every pair underflows to exactly 0
     float d2 = 0.0f;
 #pragma unroll
@@ -76,7 +78,31 @@ k_rbf_field(const float* __restrict__ tgt, int nt, const float* __restrict__ tbo
       s1z = fmaf(kv, dz, s1z);
     }
   }
-  if (live) reinterpret_cast<float4*>(out)[i] = make_float4(s0, s1x, s1y, s1z);
+  if (!live) return;
+  if (nsplit == 1) reinterpret_cast<float4*>(out)[i] = make_float4(s0, s1x, s1y, s1z);
+  else if (s0 != 0.0f || s1x != 0.0f || s1y != 0.0f || s1z != 0.0f) {   // out was zeroed by the launcher
+    atomicAdd(out + (int64_t)i * 4, s0);
+    atomicAdd(out + (int64_t)i * 4 + 1, s1x);
+    atomicAdd(out + (int64_t)i * 4 + 2, s1y);
+    atomicAdd(out + (int64_t)i * 4 + 3, s1z);
+  }
+}
+
+// source-loop split of k_rbf_field: enough CTAs to fill the device when there are few target tiles
+inline int rbf_nsplit(int n_tgt_tiles, int n_src_tiles) {
+  int s = (4 * 148 + n_tgt_tiles - 1) / (n_tgt_tiles > 0 ? n_tgt_tiles : 1);
+  if (s > 16) s = 16;
+  if (s > n_src_tiles) s = n_src_tiles;
+  return s < 1 ? 1 : s;
+}
+
+inline int launch_rbf_field(const float* tgt, int nt, const float* tbox, const float* src, const float* w, int ns, const float* sbox,
+                            int ntt, int nst, float inv2s2, float cutoff, float* out, cudaStream_t st) {
+  const int nsplit = rbf_nsplit(ntt, nst);
+  if (nsplit > 1) LARND_CUDA(cudaMemsetAsync(out, 0, (size_t)nt * 4 * sizeof(float), st));
+  k_rbf_field<<<dim3(ntt, nsplit), RT, 0, st>>>(tgt, nt, tbox, src, w, ns, sbox, nst, inv2s2, cutoff, out, nsplit);
+  LARND_LAUNCH_CHECK("k_rbf_field");
+  return LARND_OK;
 }
 
 }  // namespace
@@ -103,10 +129,8 @@ extern "C" int larnd_rbf_field(const float* targets_d, int32_t n_targets, const 
     k_rbf_bbox<<<nst, RT, 0, st>>>(sources_d, n_sources, sbox);
     LARND_LAUNCH_CHECK("k_rbf_bbox");
   }
-  k_rbf_field<<<ntt, RT, 0, st>>>(targets_d, n_targets, tbox, sources_d, weights_d, n_sources, sbox, nst, 0.5f / (sigma * sigma),
-                                  15.0f * sigma, field_d);
-  LARND_LAUNCH_CHECK("k_rbf_field");
-  return LARND_OK;
+  return launch_rbf_field(targets_d, n_targets, tbox, sources_d, weights_d, n_sources, sbox, ntt, nst, 0.5f / (sigma * sigma), 15.0f * sigma,
+                          field_d, st);
 }
 
 // ---- Dense mse_adc on the front end's (npix, 10) outputs ------------------------------------------------------------
@@ -279,14 +303,12 @@ extern "C" int larnd_mse_adc_sums(const float* adc_d, const float* ticks_d, cons
   k_rbf_bbox<<<ntt, RT, 0, st>>>(hs.pts, n, hs.tbox);
   LARND_LAUNCH_CHECK("k_rbf_bbox");
   const float inv2s2 = 0.5f / (sigma * sigma), cutoff = 15.0f * sigma;
-  k_rbf_field<<<ntt, RT, 0, st>>>(hs.pts, n, hs.tbox, hs.pts, hs.w, n, hs.tbox, ntt, inv2s2, cutoff, hs.fxx);
-  LARND_LAUNCH_CHECK("k_rbf_field(xx)");
+  if ((rc = launch_rbf_field(hs.pts, n, hs.tbox, hs.pts, hs.w, n, hs.tbox, ntt, ntt, inv2s2, cutoff, hs.fxx, st))) return rc;
   if (nrt > 0) {
     k_rbf_bbox<<<nrt, RT, 0, st>>>(ref_points_d, n_ref, hs.rbox);
     LARND_LAUNCH_CHECK("k_rbf_bbox(ref)");
   }
-  k_rbf_field<<<ntt, RT, 0, st>>>(hs.pts, n, hs.tbox, ref_points_d, ref_weights_d, n_ref, hs.rbox, nrt, inv2s2, cutoff, hs.fxy);
-  LARND_LAUNCH_CHECK("k_rbf_field(xy)");
+  if ((rc = launch_rbf_field(hs.pts, n, hs.tbox, ref_points_d, ref_weights_d, n_ref, hs.rbox, ntt, nrt, inv2s2, cutoff, hs.fxy, st))) return rc;
   k_hits_ksums<<<ntt, RT, 0, st>>>(hs.w, reinterpret_cast<const float4*>(hs.fxx), reinterpret_cast<const float4*>(hs.fxy), n, sums_d);
   LARND_LAUNCH_CHECK("k_hits_ksums");
   return LARND_OK;
