@@ -53,6 +53,7 @@ def linspace_f32(start, stop, num):
 class _ParamsBase:
     """Attribute container; subclasses are created by build_params_class."""
     _grad_fields = ()
+    _tensorize = True   # False: the fields of _grad_fields stay plain floats (host-side value carriers of the fused fit step)
 
     def __init__(self, **kw):
         unknown = set(kw) - set(_DEFAULTS)
@@ -63,7 +64,7 @@ class _ParamsBase:
         if vals["long_diff_template"] is None:
             vals["long_diff_template"] = linspace_f32(0.001, 10, 100)
         for k, v in vals.items():
-            if k in self._grad_fields and not torch.is_tensor(v):
+            if k in self._grad_fields and self._tensorize and not torch.is_tensor(v):
                 v = torch.tensor(float(v), dtype=torch.float32, requires_grad=True)
             object.__setattr__(self, k, v)
 
@@ -116,6 +117,19 @@ def build_params_class(params_with_grad):
         if n not in _DEFAULTS:
             raise ValueError("unknown parameter '%s'" % n)
     return type("Params", (_ParamsBase,), {"_grad_fields": tuple(params_with_grad)})
+
+
+_float_classes = {}
+
+
+def float_params_class(cls):
+    """The Params class ``cls`` with the same fitted-field list (what decides e.g. the float32 evaluation of the drift
+    velocity) whose fitted fields are NOT turned into torch leaves: a plain-float value carrier for host-side loops that own
+    the parameter values themselves (fit.FusedFitStep builds one per step; tensor leaves there cost ~0.1 ms of host time)."""
+    c = _float_classes.get(cls)
+    if c is None:
+        c = _float_classes[cls] = type(cls.__name__ + "Floats", (cls,), {"_tensorize": False})
+    return c
 
 
 def _mobility(e, temperature, mob):

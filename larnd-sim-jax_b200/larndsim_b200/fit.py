@@ -235,9 +235,18 @@ class FusedFitStep:
         self.idx = [_lib.PARAM_ORDER.index(nm) for nm in pr.names]
 
     def _with_values(self, values):
-        vals = {nm: float(v) for nm, v in values.items()}
-        base = {nm: float(self.problem.params.value(nm)) for nm in self.problem.names if nm not in vals}
-        return self.problem.params.replace(**dict(base, **vals))
+        """A plain-float Params object (same fitted-field list, no tensor leaves) carrying ``values``."""
+        from .consts import _DEFAULTS, float_params_class
+        if getattr(self, "_float_base", None) is None:
+            pp = self.problem.params
+            d = {k: getattr(pp, k) for k in _DEFAULTS}
+            for nm in self.problem.names:
+                d[nm] = float(pp.value(nm))
+            for k, v in d.items():
+                if torch.is_tensor(v) and v.numel() == 1:
+                    d[k] = float(pp.value(k))
+            self._float_cls, self._float_base = float_params_class(type(pp)), d
+        return self._float_cls(**dict(self._float_base, **{nm: float(v) for nm, v in values.items()}))
 
     def __call__(self, values):
         """(loss, gradients w.r.t. problem.names as a numpy array) for plain-float parameter values."""
