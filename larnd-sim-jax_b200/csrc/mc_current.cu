@@ -215,19 +215,24 @@ struct McArgs {
 };
 
 constexpr int MC_WARPS = 8;
-constexpr int MC_SEGS = 5;                  // segments per CTA of k_mc_accumulate: 5 x 51 = 255 of 256 threads busy
-constexpr int MC_ACC_THREADS = 256;
+constexpr int MC_EDGES = MC_NT + 1;         // bin edges of the 51 samples
+constexpr int MC_SEGS = 4;                  // segments per CTA of k_mc_accumulate: 4 x 52 = 208 of 224 threads busy
+constexpr int MC_ACC_THREADS = 224;
 
-// current_mc + accumulate_signals_parametrized (detsim_jax.py:618-639, 207-228): thread <-> (segment, tick).  tick = t0_tick -
-// 51 + k; < 0 or >= Nticks-1 -> column 0, else +1.  The row normalisation of the diffusion variant (lower edge of the first
-// bin minus upper edge of the last one, detsim_jax.py:470-473) does not depend on the tick: threads k = 0 / 1 of every
-// segment evaluate it once for the two exponential components and hand it over in shared memory, which halves the
-// erf / erfc / exp work per sample.
+// current_mc + accumulate_signals_parametrized (detsim_jax.py:618-639, 207-228): thread <-> (segment, bin edge).  tick =
+// t0_tick - 51 + k; < 0 or >= Nticks-1 -> column 0, else +1.  Every sample is a difference of ONE edge function at the two
+// edges of its bin (integrated_expon_diff :461-474: upper_k - lower_k, rows normalised by lower_0 - upper_50;
+// integrated_expon :536-542), and lower_k is upper_(k+1): the 52 edges e_j = dt/2 - t_j of a segment are evaluated once —
+// thread j, both exponential components — and handed over in shared memory; sample k then takes edges k and k + 1 and the
+// normalisation edges 1 and 50.  The first versions evaluated upper and lower edge per sample (4 edge evaluations per
+// sample, 955 instructions per sample at 90 % issue utilisation); the shared form evaluates 52 / 51 per sample.  The lower
+// edge of sample k thereby becomes fl(dt/2 - t_(k+1)) instead of fl(-t_k - dt/2): an ulp of the argument, well inside the
+// waveform tolerance.
 __global__ void __launch_bounds__(MC_ACC_THREADS)
 k_mc_accumulate(const __grid_constant__ McArgs A, const __grid_constant__ larnd_params_t p) {
-  __shared__ float s_den[MC_SEGS][2];
+  __shared__ float s_E[MC_SEGS][MC_EDGES][2];
   __shared__ float s_garbage[MC_SEGS];
-  const int sl = threadIdx.x / MC_NT, k = threadIdx.x - sl * MC_NT;
+  const int sl = threadIdx.x / MC_EDGES, k = threadIdx.x - sl * MC_EDGES;
   const int64_t s = (int64_t)blockIdx.x * MC_SEGS + sl;
   const bool diffusion = p.diffusion_in_current_sim != 0;
   const float dtk = 5.0f / (MC_NT - 1);
@@ -256,25 +261,29 @@ k_mc_accumulate(const __grid_constant__ McArgs A, const __grid_constant__ larnd_
   const float b = quad(Cp, xd, yd), c = quad(Dp, xd, yd);
   const float loc = -(t0f + quad(Tp, xd, yd));
   const float half = 0.5f * dtk;
-  if (diffusion && live && k < 2) {
-    const float lam = 1.0f / (k == 0 ? b : c);
-    const float lo_first = expon_diff_edge(0.0f - half, loc, lam, sig);
-    const float up_last = expon_diff_edge(-(dtk * (MC_NT - 1)) + half, loc, lam, sig);
-    s_den[sl][k] = lo_first - up_last;
-  }
-  __syncthreads();
   if (live) {
-    // jnp.linspace(0, 5, 51)[k] = 0*(1-s) + 5*s with s = k/50 (exact end point)
+    // jnp.linspace(0, 5, 51)[j] = 0*(1-s) + 5*s with s = j/50 (exact end point); edge 51 lies one bin beyond
     const float sfrac = __fdiv_rn((float)k, (float)(MC_NT - 1));
     const float t = (k == MC_NT - 1) ? 5.0f : __fmul_rn(5.0f, sfrac);
+    const float e = -t + half;   // upper edge of sample k = lower edge of sample k - 1
+    if (diffusion) {
+      s_E[sl][k][0] = expon_diff_edge(e, loc, 1.0f / b, sig);
+      s_E[sl][k][1] = expon_diff_edge(e, loc, 1.0f / c, sig);
+    } else {
+      s_E[sl][k][0] = g_exp(g_min0((loc - e) / b));
+      s_E[sl][k][1] = g_exp(g_min0((loc - e) / c));
+    }
+  }
+  __syncthreads();
+  if (live && k < MC_NT) {
+    const float ub = s_E[sl][k][0], lb = s_E[sl][k + 1][0], uc = s_E[sl][k][1], lc = s_E[sl][k + 1][1];
     float cur;
     if (diffusion) {
-      const float x = -t, lb = 1.0f / b, lc = 1.0f / c;
-      const float nb = expon_diff_edge(x + half, loc, lb, sig) - expon_diff_edge(x - half, loc, lb, sig);
-      const float nc = expon_diff_edge(x + half, loc, lc, sig) - expon_diff_edge(x - half, loc, lc, sig);
-      cur = a * ((nb / s_den[sl][0]) / dtk) + (1.0f - a) * ((nc / s_den[sl][1]) / dtk);
+      const float den_b = s_E[sl][1][0] - s_E[sl][MC_NT - 1][0], den_c = s_E[sl][1][1] - s_E[sl][MC_NT - 1][1];
+      cur = a * (((ub - lb) / den_b) / dtk) + (1.0f - a) * (((uc - lc) / den_c) / dtk);
     } else {
-      cur = current_sample<float>(t, t0f, xd, yd, sig, false, dtk);
+      const float inv = (float)MC_NT;
+      cur = a * ((lb - ub + s_E[sl][0][0] / inv) / dtk) + (1.0f - a) * ((lc - uc + s_E[sl][0][1] / inv) / dtk);
     }
     cur *= q;
     float* base = A.wfs + (int64_t)row * A.nticks;
