@@ -76,13 +76,21 @@ def make_pod(params, lut_shape=None):
     """The C parameter block of ``params`` (a fresh copy per call).  Building it costs ~0.1 ms of Python, several times per
     batch; Params objects are immutable, so the block is cached on the object, keyed on the bank's template count and on the
     identity / version counters of the tensor-valued fields (a fit updates those in place)."""
-    key = (None if lut_shape is None else int(lut_shape[0]),
-           tuple((id(v), v._version) for v in params.__dict__.values() if torch.is_tensor(v)))
-    cache = params.__dict__.get("_pod_cache")
-    if cache is None or cache[0] != key:
-        cache = (key, _build_pod(params, lut_shape))
+    ntpl = None if lut_shape is None else int(lut_shape[0])
+    d = params.__dict__
+    tf = d.get("_tensor_fields")
+    if tf is None:      # the object is immutable: which of its fields are tensors never changes
+        tf = tuple(k for k, v in d.items() if not k.startswith("_") and torch.is_tensor(v))
+        object.__setattr__(params, "_tensor_fields", tf)
+    ver = tuple((id(d[k]), d[k]._version) for k in tf)
+    cache = d.get("_pod_cache")
+    if cache is None or cache[0] != ver:                 # (one entry per bank size: both forms are requested per batch)
+        cache = (ver, {})
         object.__setattr__(params, "_pod_cache", cache)
-    return _lib.ParamsPOD.from_buffer_copy(cache[1])
+    pod = cache[1].get(ntpl)
+    if pod is None:
+        pod = cache[1][ntpl] = _build_pod(params, lut_shape)
+    return _lib.ParamsPOD.from_buffer_copy(pod)
 
 
 def _build_pod(params, lut_shape=None):
