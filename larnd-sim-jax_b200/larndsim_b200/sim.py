@@ -74,9 +74,8 @@ def fill_pod_leaves(P, params):
 
 def make_pod(params, lut_shape=None):
     """The C parameter block of ``params`` (a fresh copy per call).  Building it costs ~0.1 ms of Python, several times per
-    batch; Params objects are immutable, so the block is cached on the object, keyed on the bank's template count and on the
-    identity / version counters of the tensor-valued fields (a fit updates those in place)."""
-    ntpl = None if lut_shape is None else int(lut_shape[0])
+    batch; Params objects are immutable, so the block is cached on the object, keyed on the identity / version counters of the
+    tensor-valued fields (a fit updates those in place).  ``lut_shape``: the bank the block will be used with (validated)."""
     d = params.__dict__
     tf = d.get("_tensor_fields")
     if tf is None:      # the object is immutable: which of its fields are tensors never changes
@@ -84,12 +83,13 @@ def make_pod(params, lut_shape=None):
         object.__setattr__(params, "_tensor_fields", tf)
     ver = tuple((id(d[k]), d[k]._version) for k in tf)
     cache = d.get("_pod_cache")
-    if cache is None or cache[0] != ver:                 # (one entry per bank size: both forms are requested per batch)
-        cache = (ver, {})
+    if cache is None or cache[0] != ver:
+        cache = (ver, _build_pod(params, None))
         object.__setattr__(params, "_pod_cache", cache)
-    pod = cache[1].get(ntpl)
-    if pod is None:
-        pod = cache[1][ntpl] = _build_pod(params, lut_shape)
+    pod = cache[1]
+    # the block does not depend on the bank (n_templates is long_diff_template's length); the bank only has to fit it
+    if lut_shape is not None and int(lut_shape[0]) > pod.n_templates:
+        raise ValueError("response_template has %d templates, params.long_diff_template only %d" % (int(lut_shape[0]), pod.n_templates))
     return _lib.ParamsPOD.from_buffer_copy(pod)
 
 
