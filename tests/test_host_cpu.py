@@ -414,3 +414,28 @@ def test_parameter_block_is_cached_per_params_object_and_follows_in_place_update
     assert abs(sim.make_pod(pg).lifetime - 0.5 * before) < 1e-3 * before
     with pytest.raises(ValueError):
         sim.make_pod(pp, (1000, 25, 25, 1950))   # more bank rows than long_diff_template entries
+
+
+def test_plain_float_params_carrier_builds_the_same_parameter_block():
+    """consts.float_params_class: the value carrier of the fused fit step keeps the fitted-field list (a fitted eField means the
+    float32 evaluation of the drift velocity, like the reference's traced scalar) but holds plain floats — its C parameter
+    block must be byte-identical to the one built from the tensor-leaf Params object."""
+    import torch
+    import common as cm
+    from larndsim_b200 import consts, sim
+    names = ("Ab", "kb", "eField", "lifetime", "tran_diff", "long_diff")
+    pg = cm.product_params(grad=names, number_pix_neighbors=2, signal_length=150)
+    FC = consts.float_params_class(type(pg))
+    assert FC is consts.float_params_class(type(pg)) and FC._grad_fields == type(pg)._grad_fields
+    d = {k: getattr(pg, k) for k in consts._DEFAULTS}
+    for k, v in d.items():
+        if torch.is_tensor(v) and v.numel() == 1:
+            d[k] = float(pg.value(k))
+    pf = FC(**d)
+    assert pf.grad_leaves() == [] and not any(torch.is_tensor(getattr(pf, n)) for n in names)
+    assert bytes(sim.make_pod(pf)) == bytes(sim.make_pod(pg))
+    # a fitted eField takes the float32 drift velocity in both; a static one the double-precision value rounded once
+    ps = cm.product_params(number_pix_neighbors=2, signal_length=150)
+    assert sim.make_pod(ps).vdrift == pytest.approx(sim.make_pod(pg).vdrift, rel=1e-6)
+    pf2 = FC(**dict(d, lifetime=1234.5))
+    assert abs(sim.make_pod(pf2).lifetime - 1234.5) < 1e-3
